@@ -1,0 +1,189 @@
+"""CPU tests: the numpy oracle (oracle/) against the golden vectors produced by the unmodified
+reference (oracle/make_golden.py), and the RGF restatement against the dense oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, rt_err
+from oracle import rgf_oracle, wfm_oracle
+from transport_b200 import configs
+
+TOL = 1e-12
+
+
+def _sweep(h, tnn, tnnn, Es, converger, sources, fn=wfm_oracle.kernel):
+    n = h.shape[-1]
+    R = np.zeros((len(Es), len(sources), n))
+    T = np.zeros_like(R)
+    for i, E in enumerate(Es):
+        for s, src in enumerate(sources):
+            R[i, s], T[i, s] = fn(h, tnn, tnnn, 1.0, E, converger, np.asarray(src, dtype=float), False, False,
+                                  all_debug=False)
+    return R, T
+
+
+def test_barrier_survey_spot_values():
+    g = load_golden("barrier_run_wfm.npz")
+    # SURVEY.md §8c spot values measured from the live reference
+    assert g["T"][0, 0, 0] == pytest.approx(2.436987210571056e-06, rel=1e-13)
+    assert g["T"][100, 0, 0] == pytest.approx(3.629186977233515e-04, rel=1e-13)
+    assert g["T"][198, 0, 0] == pytest.approx(0.9956549695595422, rel=1e-13)
+    R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], "g_closed", [np.array([1.0])])
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+
+
+def test_cfg1_barrier():
+    g = load_golden("cfg1_barrier.npz")
+    h, tnn, tnnn = configs.barrier_blocks(0.4, 11)
+    assert np.array_equal(h, g["h"]) and np.array_equal(tnn, g["tnn"])
+    assert np.array_equal(configs.barrier_energies(10_000)[::50], g["Es"])
+    R, T = _sweep(h, tnn, tnnn, g["Es"], "g_closed", [np.array([1.0])])
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+
+
+def test_cfg2_cicc_dense_and_loops():
+    g = load_golden("cfg2_cicc.npz")
+    srcs = np.eye(8)
+    for k, J in enumerate(g["Js"]):
+        h, tnn, tnnn = configs.cicc_blocks(1, 1.0, J, 0.0, 0.0, 0.0, 3, 2)
+        assert np.array_equal(h, g["h"][k])
+        Es = g["Es"][::6]
+        R, T = _sweep(h, tnn, tnnn, Es, "g_closed", srcs)
+        assert rt_err(T, g["T"][k][::6]) < TOL and rt_err(R, g["R"][k][::6]) < TOL
+    # the loop-for-loop port (CPU baseline) gives the same numbers
+    R, T = _sweep(h, tnn, tnnn, g["Es"][:2], "g_closed", srcs[:2], fn=wfm_oracle.kernel_loops)
+    assert rt_err(T, g["T"][-1][:2, :2]) < TOL and rt_err(R, g["R"][-1][:2, :2]) < TOL
+
+
+def test_cicc_spot_value_from_survey():
+    g = load_golden("cicc_spot.npz")
+    want_T = [0, 0.447045935133, 0.127810093027, 0, 0.119217541793, 0, 0, 0]
+    assert np.allclose(g["T"], want_T, atol=1e-11)
+    R, T = wfm_oracle.kernel(g["h"], g["tnn"], g["tnnn"], 1.0, complex(g["E"]), "g_closed", np.eye(8)[1], False, False)
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                                        if os.path.basename(p).startswith(("general_hop", "cfg3_", "cicc_spin1",
+                                                                           "nondiag", "kondo_n2.npz"))))
+def test_closed_lead_goldens_dense_and_rgf(name):
+    g = load_golden(name)
+    srcs = g["sources"] if "sources" in g.files else np.eye(g["h"].shape[-1])[:g["R"].shape[1]]
+    if name.startswith("cicc_spin1"):
+        srcs = [np.eye(18)[0], np.eye(18)[7]]
+    R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], "g_closed", srcs)
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+    # recursive restatement against the same reference output
+    R2, T2 = rgf_oracle.transmission_closed(g["h"], g["tnn"], g["Es"], srcs)
+    assert rt_err(T2, g["T"]) < 1e-11 and rt_err(R2, g["R"]) < 1e-11
+
+
+def test_nondiag_lead_selfenergies():
+    g = load_golden("nondiag_lead_hop_n4.npz")
+    SL, SR = rgf_oracle.closed_selfenergies(g["h"], g["tnn"], g["Es"])
+    assert np.allclose(SL, g["SigL"], rtol=1e-13, atol=1e-15)
+    assert np.allclose(SR, g["SigR"], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["ricemele_kondo.npz", "ricemele_kondo_vw.npz"])
+def test_ricemele(name):
+    g = load_golden(name)
+    R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], "g_RiceMele", g["sources"])
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+
+
+def test_iterative_converger_kernel():
+    g = load_golden("kondo_n2_iterative.npz")
+    conv = (float(g["imE"]), float(g["conv_tol"]))
+    R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], conv, [np.eye(2)[0]])
+    assert rt_err(T, g["T"]) < 1e-11 and rt_err(R, g["R"]) < 1e-11
+
+
+def test_surface_gf_closed_forms():
+    g = load_golden("g_closed.npz")
+    for i, E in enumerate(g["Es"]):
+        assert np.allclose(wfm_oracle.g_closed(g["diag"], g["off"], E, 1), g["g"][i], rtol=1e-14, atol=0)
+        assert np.allclose(wfm_oracle.g_closed(g["diag"], g["off2"], E, -1), g["g2"][i], rtol=1e-14, atol=0)
+    for i, E in enumerate(g["Ec"]):
+        assert np.allclose(wfm_oracle.g_closed(g["diag"], g["off"], E, 1), g["g3"][i], rtol=1e-14, atol=0)
+    g = load_golden("g_ricemele.npz")
+    for i, E in enumerate(g["Es"]):
+        assert np.allclose(wfm_oracle.g_RiceMele(g["diag"], g["off"], E, -1), g["gL"][i], rtol=1e-14, atol=0)
+        assert np.allclose(wfm_oracle.g_RiceMele(g["diag"], g["off"], E, 1), g["gR"][i], rtol=1e-14, atol=0)
+
+
+def test_g_ith_and_g_iter():
+    g = load_golden("g_iter.npz")
+    imE, tol = float(g["imE"]), float(g["conv_tol"])
+    for i, E in enumerate(g["Es"]):
+        for si, side in enumerate((-1, 1)):
+            cur = np.zeros_like(g["h00"])
+            for it in range(12):
+                cur = wfm_oracle.g_ith(g["h00"], g["h01"], E, side, imE, it, cur)
+                assert np.allclose(cur, g["chain"][i, si, it], rtol=1e-13, atol=1e-15)
+            out, conv, nit = wfm_oracle.g_iter(g["h00"], g["h01"], E, side, imE, tol, full=True)
+            assert nit == g["n_iter"][i, si]
+            assert np.allclose(out, g["g"][i, si], rtol=1e-12, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        wfm_oracle.g_iter(np.eye(3), np.eye(3), 0.0, 1, 1e-2, 1e-3)
+    # decimation reaches the fixed point of the reference's own map
+    zs = g["Es"] + 1j * imE
+    for side in (-1, 1):
+        gs, _ = rgf_oracle.sancho_rubio(g["h00"], g["h01"], zs, side)
+        for i, z in enumerate(zs):
+            nxt = wfm_oracle.g_ith(g["h00"], g["h01"], z.real, side, imE, 1, gs[i])
+            assert np.linalg.norm(nxt - gs[i]) / np.linalg.norm(gs[i]) < 1e-12
+
+
+def test_hmat_hprime_green_psi():
+    g = load_golden("green_n3.npz")
+    h, tnn, tnnn, E = g["h"], g["tnn"], g["tnnn"], complex(g["E"])
+    assert np.array_equal(wfm_oracle.Hmat(h, tnn, tnnn), g["H"])
+    assert np.array_equal(wfm_oracle.Hmat_loops(h, tnn, tnnn), g["H"])
+    assert np.allclose(wfm_oracle.Hprime(h, tnn, tnnn, 1.0, E, "g_closed"), g["Hp"], rtol=1e-14, atol=0)
+    G = wfm_oracle.Green(h, tnn, tnnn, 1.0, E, "g_closed")
+    assert np.allclose(G, g["G"], rtol=1e-12, atol=1e-14)
+    assert np.array_equal(wfm_oracle.mat_2d_to_4d_loops(g["H"], 3), wfm_oracle.mat_2d_to_4d(g["H"], 3))
+    assert np.array_equal(wfm_oracle.mat_4d_to_2d(wfm_oracle.mat_2d_to_4d(g["H"], 3)), g["H"])
+    tz = np.zeros_like(tnnn)
+    psi = wfm_oracle.kernel(h, tnn, tz, 1.0, E, "g_closed", g["src"], True, False, all_debug=False)
+    assert np.allclose(psi, g["psi"], rtol=1e-12, atol=1e-14)
+    R, T = wfm_oracle.kernel(h, tnn, tnnn, 1.0, E, "g_closed", g["src"], False, False, all_debug=False)
+    assert rt_err(R, g["R_tnnn"]) < TOL and rt_err(T, g["T_tnnn"]) < TOL
+    # recursive full Green's function / first column against the reference's dense inverse
+    SL, SR = rgf_oracle.closed_selfenergies(h, tnn, [E])
+    Gf = rgf_oracle.green_full(h, tnn, [E], SL, SR)[0]
+    assert np.allclose(Gf, g["G_nn_only"], rtol=1e-11, atol=1e-13)
+    col = rgf_oracle.green_column0(h, tnn, [E], SL, SR)[0]
+    assert np.allclose(col, g["G_nn_only"][:, 0], rtol=1e-11, atol=1e-13)
+    with pytest.raises(ValueError):
+        wfm_oracle.Hmat(h, tnn[:-1], tnnn)
+    with pytest.raises(TypeError):
+        wfm_oracle.kernel(list(h), tnn, tnnn, 1.0, E, "g_closed", g["src"], False, False)
+
+
+def test_exact_lattice_identities():
+    """Builder-added KATs: clean chain T=1; delta barrier T = 1/(1+(V/(2 t sin ka))^2)."""
+    Es = np.linspace(-1.9, 1.9, 21).astype(complex)
+    h, tnn, tnnn = configs.barrier_blocks(0.0, 5)
+    R, T = rgf_oracle.transmission_closed(h, tnn, Es, [[1.0]])
+    assert np.max(np.abs(T - 1)) < 1e-13 and np.max(np.abs(R)) < 1e-13
+    V = 0.7
+    h, tnn, tnnn = configs.barrier_blocks(V, 1)
+    R, T = rgf_oracle.transmission_closed(h, tnn, Es, [[1.0]])
+    ka = np.arccos(np.real(Es) / -2.0)
+    want = 1.0 / (1.0 + (V / (2 * np.sin(ka))) ** 2)
+    assert np.max(np.abs(T[:, 0, 0] - want)) < 1e-13
+    assert np.max(np.abs(R + T - 1)) < 1e-13
+
+
+def test_caroli_trace_equals_channel_sum():
+    g = load_golden("cfg2_cicc.npz")
+    h, tnn = g["h"][2], g["tnn"]
+    Es = g["Es"][::5]
+    SL, SR = rgf_oracle.closed_selfenergies(h, tnn, Es)
+    G00, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, SL, SR)
+    _, T = rgf_oracle.rt_from_blocks(G00, GN0, SL, SR, np.eye(8))
+    assert np.allclose(T.sum(axis=(1, 2)), rgf_oracle.caroli_trace(GN0, SL, SR), rtol=1e-12)
