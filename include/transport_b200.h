@@ -1,0 +1,172 @@
+/*
+ * transport_b200 — C ABI of the B200-native T(E) scattering hot path.
+ *
+ * Drop-in boundary for the wave-function-matching path of cpbunker/transport.  The reference
+ * has no FFI of its own (it is pure Python); every entry point below replaces
+ * the arithmetic of one reference function and is what a ctypes/cffi binding inside
+ * `transport/wfm/__init__.py` would call.  Citations are relative to the
+ * reference root.
+ *
+ * Conventions (same as the reference):
+ *   - complex numbers are interleaved (re, im) doubles  == numpy complex128;
+ *   - h[M][n][n] on-site blocks, tnn[M-1][n][n] UPPER blocks H_{j,j+1}; the lower block is the
+ *     conjugate transpose (wfm/__init__.py:203-207); blocks 0 and M-1 are the first cells of
+ *     the left/right lead and receive the self-energies (wfm/__init__.py:246-247);
+ *   - all arrays are C-contiguous, row-major;
+ *   - functions return TX_OK (0) or a TX_ERR_* code; tx_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *
+ * No function here has a CPU fallback: without a CUDA device they return TX_ERR_CUDA.
+ */
+#ifndef TRANSPORT_B200_H
+#define TRANSPORT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tx_cplx { double re, im; } tx_cplx;
+
+enum {
+    TX_OK = 0,
+    TX_ERR_ARG = 1,         /* bad argument (shape, mode, null pointer)                       */
+    TX_ERR_CUDA = 2,        /* CUDA runtime failure / no device                               */
+    TX_ERR_SINGULAR = 3,    /* an exactly singular block was met (results contain inf/nan)    */
+    TX_ERR_NOCONV = 4,      /* iterative surface GF did not converge within max_iter          */
+    TX_ERR_UNSUPPORTED = 5  /* shape outside what the kernels cover                           */
+};
+
+/* How the lead self-energies are obtained. */
+enum {
+    TX_LEAD_CLOSED = 0,     /* wfm.g_closed fused into the sweep (wfm/__init__.py:335-340)    */
+    TX_LEAD_TABLE = 1       /* Sigma_L, Sigma_R supplied per energy (from tx_surface_gf_* or caller) */
+};
+
+/* Structure of the hopping blocks tnn. */
+enum {
+    TX_HOP_AUTO = 0,        /* host entry points inspect tnn; device entry points: treated as GENERAL */
+    TX_HOP_SCALAR = 1,      /* every tnn[j] = t_j * I (all reference drivers: tnn = -tl*I)     */
+    TX_HOP_GENERAL = 2      /* arbitrary complex blocks                                        */
+};
+
+/* Surface Green's function flavours (tx_surface_gf). */
+enum {
+    TX_GF_CLOSED = 0,       /* wfm.g_closed      wfm/__init__.py:306-340                       */
+    TX_GF_RICEMELE = 1,     /* wfm.g_RiceMele    wfm/__init__.py:352-414                       */
+    TX_GF_FIXEDPOINT = 2,   /* wfm.g_iter / g_ith, reference stopping rule  :479-551           */
+    TX_GF_SANCHO = 3        /* Sancho-Rubio decimation of the same fixed point                 */
+};
+
+/* ---- library / device management ------------------------------------------------------- */
+const char* tx_version(void);
+const char* tx_last_error(void);
+int tx_device_count(void);                 /* number of CUDA devices, 0 if none              */
+int tx_set_device(int device);
+int tx_device_synchronize(void);
+
+/* ---- the hot path: batched T(E) sweep -------------------------------------------------- */
+/*
+ * Replaces, for every (Hamiltonian p, energy e) point and every source, one call of
+ *   wfm.kernel(h, tnn, tnnn, tl, E, converger, Ajsigma, False, False)   wfm/__init__.py:29-137
+ * i.e. SelfEnergies (:270-304) + Hmat/Hprime (:168-268) + Green's dense inverse (:139-166) +
+ * the R/T channel loop (:108-130), evaluated as one right-to-left block-tridiagonal sweep.
+ *
+ *  h        [n_h][M][n][n]   n_h = 1 (shared) or n_ham
+ *  h1       [M][n][n] or NULL; if given, Hamiltonian p uses h + params[p]*h1  (affine sweeps,
+ *           e.g. the exchange coupling J of run_wfm_gate.py:get_hblocks)
+ *  params   [n_ham] doubles (only read when h1 != NULL)
+ *  tnn      [n_t][M-1][n][n] n_t = 1 (shared) or n_ham
+ *  E        [nE] complex energies (the reference passes Im E = 0)
+ *  lead_mode TX_LEAD_CLOSED: lead blocks h[0], h[M-1] must be diagonal (checked by the caller,
+ *           wfm/__init__.py:327);  TX_LEAD_TABLE: sigL/sigR [n_sig][nE][n][n], n_sig = 1 or n_ham
+ *  sources  [n_src][n] real incident amplitudes (Ajsigma) or NULL
+ *  src_idx  [n_src] channel indices of one-hot sources or NULL; if both are NULL all n one-hot
+ *           sources are evaluated (n_src must then equal n)
+ *  R, T     [n_ham][nE][n_src][n] doubles: per-channel reflection / transmission probabilities
+ *  resid    [n_ham][nE][n_src] doubles or NULL: sum(R)+sum(T)-1 (the reference's unitarity
+ *           assert, wfm/__init__.py:135, evaluated on the device)
+ *  t_total  [n_ham][nE] doubles or NULL: transmission summed over all evaluated sources and
+ *           channels; with all n one-hot sources this is Tr[Gamma_R G Gamma_L G^dag] — the compact
+ *           array the multi-GPU path gathers
+ *
+ * tx_transmission_sweep takes HOST pointers and performs the host<->device copies itself;
+ * tx_transmission_sweep_dev takes DEVICE pointers and a cudaStream_t (as void*), launches
+ * asynchronously and performs no copies.
+ */
+int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                          const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                          const tx_cplx* E, int nE,
+                          int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                          int hop_mode,
+                          const double* sources, const int* src_idx, int n_src,
+                          double* R, double* T, double* resid, double* t_total);
+
+int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                              const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                              const tx_cplx* E, int nE,
+                              int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                              int hop_mode,
+                              const double* sources, const int* src_idx, int n_src,
+                              double* R, double* T, double* resid, double* t_total,
+                              int* singular_flag, void* stream);
+
+/* Number of kernel launches tx_transmission_sweep_dev issues for this shape (for accounting). */
+int tx_sweep_launch_count(int n, int M, int hop_mode);
+
+/* ---- lead surface Green's functions and self-energies (K1) -------------------------------- */
+/*
+ * Batched over energies, one CTA per energy, any n <= 64.  `side` = -1 for the left lead (incoming,
+ * wfm/__init__.py:283), +1 for the right lead (:284).  `mode` is one of TX_GF_*:
+ *   CLOSED      wfm.g_closed   (:306-340)  h00, h01 diagonal in channel space
+ *   RICEMELE    wfm.g_RiceMele (:352-414)  n = 2*n_spin, [A spins..., B spins...] ordering
+ *   FIXEDPOINT  wfm.g_iter     (:479-530)  z = Re E + i|imE|, stops when the relative change of the
+ *               surface DOS stays below conv_tol for conv_rep consecutive iterations past min_iter
+ *   SANCHO      Sancho-Rubio decimation of the same fixed point at z = E + i*imE; stops when
+ *               max|alpha|,|beta| < conv_tol (conv_rep/min_iter unused)
+ * Outputs (each may be NULL): g [nE][n][n]; sigma [nE][n][n] = h01^dag g h01 (side -1) or
+ * h01 g h01^dag (side +1) (wfm.SelfEnergies :301-302); n_iter/conv/converged [nE] (iterative modes).
+ * Non-convergence is reported per energy in `converged`, not as an error code.
+ */
+int tx_surface_gf(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
+                  double imE, double conv_tol, int conv_rep, int min_iter, int max_iter,
+                  tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged);
+int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
+                      double imE, double conv_tol, int conv_rep, int min_iter, int max_iter,
+                      tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged,
+                      int* singular_flag, void* stream);
+/* One fixed-point step, wfm.g_ith (:532-551): ith = 0 -> inv(z - h00); else inv(z - h00 - t g_prev t^dag). */
+int tx_g_ith(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, double imE,
+             int ith, const tx_cplx* g_prev, tx_cplx* g_out);
+
+/* ---- Green's function blocks and Hamiltonian assembly (generic n <= 64) ------------------- */
+/* First block column G[:,0] -> [nE][M][n][n]  (psi_jsigma of wfm.kernel, :98-99). Host pointers. */
+int tx_green_column0(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
+                     const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G);
+/* All blocks of inv(E - H') -> [nE][M][M][n][n]  (wfm.Green, :139-166). Host pointers. */
+int tx_green_full(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
+                  const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G);
+/* Dense block-pentadiagonal H [(M n)][(M n)]  (wfm.Hmat, :168-215). Host pointers. */
+int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, int M, tx_cplx* H);
+
+/* Tuning knob for the n<=8, scalar-hopping, closed-lead kernel: 0 = 4 lanes/point capped at 168
+ * registers (default), 1 = 4 lanes/point uncapped, 2/3 = 8 lanes/point at 168/128 registers.
+ * All variants compute the same thing; used by bench.py --variant to compare them. */
+int tx_set_variant(int variant);
+
+/* ---- measurement helpers --------------------------------------------------------------- */
+/*
+ * Measures the FP64 FMA-pipe peak of the current device with a register-resident DFMA loop
+ * (no memory traffic).  Writes TFLOP/s (2 flops per FMA) to *tflops.  Used only to provide
+ * the roofline denominator that MEASURED_PEAKS.json lacks (it has HBM and bf16 only).
+ */
+int tx_measure_fp64_peak(double* tflops, double* milliseconds);
+/* Same for the legacy FP64 tensor path (mma.sync.m8n8k4.f64). */
+int tx_measure_dmma_peak(double* tflops, double* milliseconds);
+/* Exchange-primitive rates: which = 0 SHFL.b32, 1 LDS.128 group broadcast (1e9 warp-instr/s),
+ * 2 same with a 2-way conflict, 3 DFMA:LDS 8:1 mix (TFLOP/s). */
+int tx_microbench(int which, double* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSPORT_B200_H */

@@ -1,0 +1,21 @@
+"""Prints the FP64 / exchange-primitive rates of the current GPU (csrc/microbench.cu)."""
+import ctypes
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from transport_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+out = {}
+v, ms = ctypes.c_double(), ctypes.c_double()
+_lib.check(lib.tx_measure_fp64_peak(ctypes.byref(v), ctypes.byref(ms)))
+out["dfma_tflops"] = v.value
+_lib.check(lib.tx_measure_dmma_peak(ctypes.byref(v), ctypes.byref(ms)))
+out["dmma_m8n8k4_tflops"] = v.value
+for which, name in ((0, "shfl_b32_Gwarpinstr_s"), (1, "lds128_groupbcast_Gwarpinstr_s"),
+                    (2, "lds128_groupbcast_2way_Gwarpinstr_s"), (3, "dfma_lds_8to1_mix_tflops")):
+    _lib.check(lib.tx_microbench(which, ctypes.byref(v)))
+    out[name] = v.value
+print(json.dumps(out))

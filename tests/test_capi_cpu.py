@@ -1,0 +1,109 @@
+"""CPU tests: the C-ABI library loads, exports every declared symbol, refuses to compute without a
+GPU (no CPU fallback), and the Python shim reproduces the reference's argument errors."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from transport_b200 import _lib, configs, wfm
+from transport_b200.sweep import transmission_sweep, spin_flip_sums
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 15
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(_lib._SIGNATURES) <= set(names)
+    assert b"sm_100a" in lib.tx_version()
+
+
+def test_no_cpu_fallback_without_device():
+    lib = _lib.load()
+    if lib.tx_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h, tnn, tnnn = configs.barrier_blocks(0.4, 3)
+    with pytest.raises(_lib.TransportError) as ei:
+        transmission_sweep(h, tnn, np.array([-1.0 + 0j]))
+    assert ei.value.code == _lib.TX_ERR_CUDA
+    with pytest.raises(_lib.TransportError):
+        wfm.g_closed(np.zeros((1, 1), complex), -np.ones((1, 1), complex), -1.0, 1)
+    with pytest.raises(_lib.TransportError):
+        wfm.Hmat(h, tnn, tnnn)
+
+
+def test_argument_errors_match_reference():
+    h, tnn, tnnn = configs.barrier_blocks(0.4, 3)
+    src = np.array([1.0])
+    with pytest.raises(TypeError):                                   # wfm/__init__.py:57
+        wfm.kernel(list(h), tnn, tnnn, 1.0, -1.0, "g_closed", src, False, False)
+    with pytest.raises(ValueError):                                  # :179
+        wfm.kernel(h, tnn[:-1], tnnn, 1.0, -1.0, "g_closed", src, False, False, all_debug=False)
+    with pytest.raises(ValueError):                                  # :180
+        wfm.Hmat(h, tnn, tnnn[:-1])
+    with pytest.raises(AssertionError):                              # :70 source channel must sit at mu=0
+        hb = h.copy(); hb[0, 0, 0] = 0.3
+        wfm.kernel(hb, tnn, tnnn, 1.0, -1.0, "g_closed", src, False, False)
+    with pytest.raises(AssertionError):                              # :74
+        wfm.kernel(h, tnn, tnnn, 1.0, -1.0, "g_closed", np.array([1.0, 0.0]), False, False)
+    with pytest.raises(Exception, match="not supported"):            # :294
+        wfm.SelfEnergies(h, tnn, tnnn, -1.0, "g_magic")
+    with pytest.raises(ValueError):                                  # :324
+        wfm.g_closed(np.zeros((2, 2)), np.zeros((3, 3)), 0.0, 1)
+    with pytest.raises(ValueError):                                  # :325
+        wfm.g_closed(np.zeros((2, 2)), np.eye(2), 0.0, 2)
+    with pytest.raises(Exception, match="Not diagonal"):             # :327
+        wfm.g_closed(np.ones((2, 2)), np.eye(2), 0.0, 1)
+    with pytest.raises(ValueError, match="Rice-Mele"):               # :370
+        wfm.g_RiceMele(np.zeros((3, 3)), np.zeros((3, 3)), 0.0, 1)
+    with pytest.raises(ValueError, match="Rice-Mele"):               # :375
+        wfm.g_RiceMele(np.zeros((2, 2)), np.ones((2, 2)), 0.0, 1)
+    with pytest.raises(NotImplementedError):                         # :502
+        wfm.g_iter(np.eye(3), np.eye(3), 0.0, 1, 1e-2, 1e-3)
+    with pytest.raises(TypeError):                                   # :537
+        wfm.g_ith(np.eye(2), np.eye(2), 0.0, 1, 1e-2, 1.0, np.eye(2))
+    with pytest.raises(Exception, match="Not diagonal"):
+        hb = np.tile(h, (1, 2, 2)); tb = np.tile(tnn, (1, 2, 2)); hb[0] = 0.1
+        transmission_sweep(hb, tb, np.array([-1.0 + 0j]))
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    lib = _lib.load()
+    z = np.zeros(16, dtype=np.complex128)
+    out = np.zeros(16)
+    flag = np.zeros(1, dtype=np.int32)
+    rc = lib.tx_transmission_sweep_dev(_lib.ptr(z), 1, None, None, _lib.ptr(z), 1, 1, 1, 1, _lib.ptr(z), 1,
+                                       0, None, None, 1, 1, None, None, 1, _lib.ptr(out), _lib.ptr(out), None, None,
+                                       _lib.ptr(flag), None)
+    assert rc == _lib.TX_ERR_ARG and b"bad sizes" in lib.tx_last_error()
+    rc = lib.tx_transmission_sweep_dev(_lib.ptr(z), 1, None, None, _lib.ptr(z), 1, 20, 3, 1, _lib.ptr(z), 1,
+                                       0, None, None, 1, 1, None, None, 20, _lib.ptr(out), _lib.ptr(out), None, None,
+                                       _lib.ptr(flag), None)
+    assert rc == _lib.TX_ERR_UNSUPPORTED
+    rc = lib.tx_surface_gf(_lib.ptr(z), _lib.ptr(z), 3, _lib.ptr(z), 1, 1, _lib.TX_GF_RICEMELE, 0.0, 0.0, 5, 100, 1000,
+                           _lib.ptr(z), None, None, None, None)
+    assert rc == _lib.TX_ERR_ARG
+    assert lib.tx_set_variant(7) == _lib.TX_ERR_ARG
+    assert lib.tx_set_variant(0) == _lib.TX_OK
+
+
+def test_ricemele_helpers_match_golden_parameters():
+    diag = np.array([[0.2, -0.8], [-0.8, -0.2]])
+    off = np.array([[0, 0], [-1.1, 0]])
+    edges = wfm.bandedges_RiceMele(diag, off)
+    assert np.all(np.diff(edges) > 0)
+    ks = np.linspace(0, np.pi, 7)
+    bands = wfm.dispersion_RiceMele(diag, off, ks)
+    assert bands.shape == (2, 7)
+    assert np.isclose(bands[1].max(), edges[3]) and np.isclose(bands[1].min(), edges[2])
+    kk = wfm.inverted_RiceMele(diag, off, bands[1])
+    assert np.allclose(np.cos(kk), np.cos(ks), atol=1e-12)
+    assert "u = 0.20" in wfm.string_RiceMele(diag, off, tex=False)
+
+
+def test_spin_flip_sums():
+    T = np.arange(64, dtype=float).reshape(1, 1, 8, 8)
+    keep, flip = spin_flip_sums(T)
+    assert keep[0, 0, 0] == T[0, 0, 0, :4].sum() and flip[0, 0, 0] == T[0, 0, 0, 4:].sum()
+    assert keep[0, 0, 5] == T[0, 0, 5, 4:].sum() and flip[0, 0, 5] == T[0, 0, 5, :4].sum()

@@ -1,0 +1,284 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(1) the golden vectors produced by the unmodified reference and (2) the numpy oracle on seeded
+inputs.  Bar (BASELINE.json north_star): relative error <= 1e-10 on every R/T channel and
+|sum R + sum T - 1| <= 1e-10.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, rt_err
+from oracle import rgf_oracle, wfm_oracle
+from transport_b200 import _lib, configs, green, leads, wfm
+from transport_b200.sweep import transmission_sweep
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10      # the parity gate of north_star
+UNIT = 1e-10      # unitarity gate (wfm/__init__.py:135)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a GPU box")
+
+
+def _check(R, T, gR, gT, resid=None):
+    assert rt_err(T, gT) < RTOL, rt_err(T, gT)
+    assert rt_err(R, gR) < RTOL, rt_err(R, gR)
+    if resid is not None:
+        ok = np.isfinite(resid)
+        assert np.max(np.abs(resid[ok])) < UNIT
+
+
+# ------------------------------------------------------------------------------- golden vectors
+def test_barrier_goldens_n1():
+    for name in ("barrier_run_wfm.npz", "cfg1_barrier.npz"):
+        g = load_golden(name)
+        R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=[[1.0]], want_resid=True)
+        _check(R[0], T[0], g["R"], g["T"], res)
+        # T spans 1e-6..1 here; every value must hold to 1e-10 relative, not absolute
+        assert np.max(np.abs(T[0] - g["T"]) / g["T"]) < RTOL
+
+
+def test_cfg2_cicc_golden_all_sources():
+    g = load_golden("cfg2_cicc.npz")
+    # batched over the 5 Hamiltonians x 25 energies x all 8 one-hot sources in one launch
+    R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], want_resid=True)
+    _check(R, T, g["R"], g["T"], res)
+    # the affine form H(J) = H0 + J*H1 gives the same answer
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    R2, T2 = transmission_sweep(h0, tnn, g["Es"], h1=h1, params=g["Js"])
+    _check(R2, T2, g["R"], g["T"])
+    # explicit one-hot amplitude vectors take the general-source path
+    R3, T3 = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=np.eye(8)[[1, 6]])
+    _check(R3, T3, g["R"][:, :, [1, 6]], g["T"][:, :, [1, 6]])
+
+
+def test_cicc_spot_value_through_reference_signature():
+    g = load_golden("cicc_spot.npz")
+    Rs, Ts = wfm.kernel(g["h"], g["tnn"], g["tnnn"], 1.0, complex(g["E"]), "g_closed", np.eye(8)[1], False, False,
+                        all_debug=True)
+    assert Rs.dtype == np.float64 and Rs.shape == (8,)
+    _check(Rs, Ts, g["R"], g["T"])
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                                        if os.path.basename(p).startswith(("general_hop", "cfg3_", "nondiag",
+                                                                           "kondo_n2.npz"))))
+def test_closed_lead_goldens(name):
+    g = load_golden(name)
+    srcs = g["sources"] if "sources" in g.files else np.eye(g["h"].shape[-1])
+    R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=srcs, want_resid=True)
+    _check(R[0], T[0], g["R"], g["T"], res if not name.startswith("nondiag") else None)
+
+
+@pytest.mark.parametrize("name", ["ricemele_kondo.npz", "ricemele_kondo_vw.npz"])
+def test_ricemele_goldens(name):
+    g = load_golden(name)
+    for i, E in enumerate(g["Es"][::3]):
+        Rs, Ts = wfm.kernel(g["h"], g["tnn"], g["tnnn"], 1.0, E, "g_RiceMele", g["sources"][0], False, False,
+                            all_debug=True)
+        _check(Rs, Ts, g["R"][3 * i, 0], g["T"][3 * i, 0])
+    SL, SR = leads.self_energies_batched(g["h"], g["tnn"], g["Es"], "g_RiceMele")
+    R, T = transmission_sweep(g["h"], g["tnn"], g["Es"], "table", sources=g["sources"], sigL=SL, sigR=SR)
+    _check(R[0], T[0], g["R"], g["T"])
+
+
+def test_iterative_converger_golden():
+    g = load_golden("kondo_n2_iterative.npz")
+    conv = (float(g["imE"]), float(g["conv_tol"]))
+    for i, E in enumerate(g["Es"]):
+        Rs, Ts = wfm.kernel(g["h"], g["tnn"], g["tnnn"], 1.0, E, conv, np.eye(2)[0], False, False, all_debug=False)
+        assert rt_err(Ts, g["T"][i, 0]) < 1e-9 and rt_err(Rs, g["R"][i, 0]) < 1e-9
+
+
+def test_surface_gf_goldens():
+    g = load_golden("g_closed.npz")
+    for i in range(0, len(g["Es"]), 4):
+        E = g["Es"][i]
+        assert np.allclose(wfm.g_closed(g["diag"], g["off"], E, 1), g["g"][i], rtol=1e-13, atol=1e-15)
+        assert np.allclose(wfm.g_closed(g["diag"], g["off2"], E, -1), g["g2"][i], rtol=1e-13, atol=1e-15)
+    (gc,) = leads.surface_gf(g["diag"], g["off"], g["Ec"], 1, _lib.TX_GF_CLOSED)
+    assert np.allclose(gc, g["g3"], rtol=1e-13, atol=1e-15)
+    g = load_golden("g_ricemele.npz")
+    (gl,) = leads.surface_gf(g["diag"], g["off"], g["Es"], -1, _lib.TX_GF_RICEMELE)
+    (gr,) = leads.surface_gf(g["diag"], g["off"], g["Es"], 1, _lib.TX_GF_RICEMELE)
+    assert np.allclose(gl, g["gL"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(gr, g["gR"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(wfm.g_RiceMele(g["diag"], g["off"], g["Es"][3], -1), g["gL"][3], rtol=1e-12, atol=1e-14)
+
+
+def test_g_ith_g_iter_goldens_and_sancho():
+    g = load_golden("g_iter.npz")
+    imE, tol = float(g["imE"]), float(g["conv_tol"])
+    for si, side in enumerate((-1, 1)):
+        cur = None
+        for it in range(12):
+            cur = leads.g_ith(g["h00"], g["h01"], g["Es"], side, imE, it, cur)
+            assert np.allclose(cur, g["chain"][:, si, it], rtol=1e-12, atol=1e-14)
+        (gg, conv, nit, ok) = leads.surface_gf(g["h00"], g["h01"], g["Es"], side, _lib.TX_GF_FIXEDPOINT,
+                                               imE=imE, conv_tol=tol, full=True)
+        assert ok.all()
+        assert np.array_equal(nit, g["n_iter"][:, si])
+        assert np.allclose(gg, g["g"][:, si], rtol=1e-11, atol=1e-14)
+    out, c, nit = wfm.g_iter(g["h00"], g["h01"], g["Es"][2], 1, imE, tol, full=True)
+    assert nit == g["n_iter"][2, 1] and np.allclose(out, g["g"][2, 1], rtol=1e-11)
+    step = wfm.g_ith(g["h00"], g["h01"], g["Es"][0], -1, imE, 0, np.zeros((2, 2), complex))
+    assert np.allclose(step, g["chain"][0, 0, 0], rtol=1e-12)
+    with pytest.raises(Exception, match="failed to meet"):
+        wfm.g_iter(g["h00"], g["h01"], g["Es"][2], 1, 1e-6, 1e-14, max_iter=300)
+    # Sancho-Rubio: fixed point of the reference's own map ...
+    for side in (-1, 1):
+        (gs, conv, nit, ok) = leads.surface_gf(g["h00"], g["h01"], g["Es"], side, _lib.TX_GF_SANCHO,
+                                               imE=imE, conv_tol=1e-14, max_iter=200, full=True)
+        assert ok.all() and nit.max() < 40
+        for i, E in enumerate(g["Es"]):
+            nxt = wfm_oracle.g_ith(g["h00"], g["h01"], E, side, imE, 1, gs[i])
+            assert np.linalg.norm(nxt - gs[i]) / np.linalg.norm(gs[i]) < 1e-12
+        ref, _ = rgf_oracle.sancho_rubio(g["h00"], g["h01"], g["Es"] + 1j * imE, side)
+        assert np.allclose(gs, ref, rtol=1e-11, atol=1e-13)
+
+
+def test_sancho_ribbon_leads_match_closed_form_channels():
+    """a square-lattice ribbon lead is separable, g = U diag(g_closed(eps_m)) U^T."""
+    n = 16
+    h, tnn, _ = configs.ribbon_blocks(width=n, L=2, W=0.0)
+    h00, h01 = h[0], tnn[0]
+    eps, U = np.linalg.eigh(h00.real)
+    Es = np.array([-2.9, -1.3, 0.45, 2.2], dtype=complex)
+    eta = 1e-9
+    (gs, conv, nit, ok) = leads.surface_gf(h00, h01, Es, 1, _lib.TX_GF_SANCHO, imE=eta, conv_tol=1e-15,
+                                           max_iter=200, full=True)
+    assert ok.all()
+    for i, E in enumerate(Es):
+        gd = np.diagonal(wfm_oracle.g_closed(np.diag(eps).astype(complex), -np.eye(n, dtype=complex), E, 1))
+        want = (U * gd) @ U.T
+        assert np.max(np.abs(gs[i] - want)) < 1e-6     # O(sqrt(eta)) near band edges, exact as eta -> 0
+
+
+def test_green_hmat_hprime_psi_golden():
+    g = load_golden("green_n3.npz")
+    h, tnn, tnnn, E = g["h"], g["tnn"], g["tnnn"], complex(g["E"])
+    assert np.array_equal(wfm.Hmat(h, tnn, tnnn), g["H"])
+    assert np.allclose(wfm.Hprime(h, tnn, tnnn, 1.0, E, "g_closed"), g["Hp"], rtol=1e-13, atol=1e-15)
+    tz = np.zeros_like(tnnn)
+    G = wfm.Green(h, tnn, tz, 1.0, E, "g_closed")
+    assert G.shape == g["G_nn_only"].shape
+    assert np.allclose(G, g["G_nn_only"], rtol=1e-10, atol=1e-13)
+    psi = wfm.kernel(h, tnn, tz, 1.0, E, "g_closed", g["src"], True, False, all_debug=False)
+    assert np.allclose(psi, g["psi"], rtol=1e-10, atol=1e-13)
+    SL, SR = wfm.SelfEnergies(h, tnn, tz, E, "g_closed")
+    oL, oR = wfm_oracle.SelfEnergies(h, tnn, tz, E, "g_closed")
+    assert np.allclose(SL, oL, rtol=1e-13, atol=1e-15) and np.allclose(SR, oR, rtol=1e-13, atol=1e-15)
+    with pytest.raises(NameError):
+        wfm.kernel(h, tnn, tz, 1.0, E, "g_closed", g["src"], False, True, all_debug=False)
+
+
+# ------------------------------------------------------------------------------- seeded vs oracle
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 11, 16])
+@pytest.mark.parametrize("general", [False, True])
+def test_seeded_random_against_dense_oracle(n, general):
+    rng = np.random.default_rng(100 * n + general)
+    M = 7
+    A = rng.standard_normal((M, n, n)) + 1j * rng.standard_normal((M, n, n))
+    h = 0.4 * (A + np.conj(np.swapaxes(A, 1, 2))) / 2
+    h[0] = 0
+    h[-1] = np.diag(0.05 * rng.standard_normal(n))
+    tnn = -np.tile(np.eye(n, dtype=complex), (M - 1, 1, 1))
+    if general:
+        tnn[1:-1] += 0.3 * (rng.standard_normal((M - 3, n, n)) + 1j * rng.standard_normal((M - 3, n, n)))
+    else:
+        tnn *= np.array([1.0, 0.9, 1.1 + 0.2j, 0.7, -1.0, 1.0])[:, None, None]
+    tnnn = np.zeros((M - 2, n, n), dtype=complex)
+    Es = np.linspace(-1.8, 1.7, 9).astype(complex)
+    srcs = np.vstack([np.eye(n)[0], rng.standard_normal(n)])
+    R, T, res = transmission_sweep(h, tnn, Es, sources=srcs, want_resid=True)
+    oR = np.zeros_like(R[0])
+    oT = np.zeros_like(T[0])
+    for i, E in enumerate(Es):
+        for s, src in enumerate(srcs):
+            oR[i, s], oT[i, s] = wfm_oracle.kernel(h, tnn, tnnn, 1.0, E, "g_closed", src, False, False, all_debug=False)
+    _check(R[0], T[0], oR, oT, res)
+    # all one-hot sources in one go (the static path)
+    Ra, Ta = transmission_sweep(h, tnn, Es)
+    _check(Ra[0, :, 0], Ta[0, :, 0], oR[:, 0], oT[:, 0])
+
+
+def test_pivoting_needed_block():
+    """A block whose diagonal vanishes at the chosen energy: unpivoted elimination would divide by 0."""
+    n, M = 4, 4
+    E = 0.5
+    h = np.zeros((M, n, n), dtype=complex)
+    X = np.array([[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=complex)
+    h[1] = E * np.eye(n) + 0.7 * X
+    h[2] = E * np.eye(n) + 0.3 * X[::-1, ::-1]
+    tnn = -np.tile(np.eye(n, dtype=complex), (M - 1, 1, 1))
+    tnnn = np.zeros((M - 2, n, n), dtype=complex)
+    R, T, res = transmission_sweep(h, tnn, np.array([E], dtype=complex), want_resid=True)
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, [E], np.eye(n))
+    _check(R[0], T[0], oR, oT, res)
+    for a in range(n):
+        dR, dT = wfm_oracle.kernel(h, tnn, tnnn, 1.0, E, "g_closed", np.eye(n)[a], False, False)
+        _check(R[0, 0, a], T[0, 0, a], dR, dT)
+
+
+def test_ragged_batches_and_edge_sizes():
+    h, tnn, tnnn = configs.cicc_blocks(1, 1.0, -0.3, 0.0, 0.0, 0.0, 3, 2)
+    for nE in (1, 7, 33):          # not multiples of the 8 points a warp holds
+        Es = np.linspace(-1.95, -0.2, nE).astype(complex)
+        R, T = transmission_sweep(h, tnn, Es)
+        oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(8))
+        _check(R[0], T[0], oR, oT)
+    # smallest legal chain: M = 2 (two lead cells, no scattering region)
+    h2 = np.zeros((2, 2, 2), dtype=complex)
+    t2 = -np.ones((1, 1, 1)) * np.eye(2, dtype=complex)[None]
+    R, T = transmission_sweep(h2, t2, np.array([-0.5 + 0j]))
+    assert np.allclose(T[0, 0], np.eye(2), atol=1e-13) and np.allclose(R[0, 0], 0, atol=1e-13)
+    # energies outside the band: closed source channel -> NaN, as the reference's 0/0
+    R, T = transmission_sweep(h, tnn, np.array([2.5 + 0j]))
+    assert np.isnan(T).all()
+
+
+def test_exactly_singular_block_raises_linalgerror():
+    """E - H' exactly singular: numpy's dense inverse raises LinAlgError (wfm/__init__.py:162)."""
+    h = np.zeros((3, 2, 2), dtype=complex)
+    tnn = -np.tile(np.eye(2, dtype=complex), (2, 1, 1))
+    zero = np.zeros((1, 2, 2), dtype=complex)
+    with pytest.raises(np.linalg.LinAlgError):
+        transmission_sweep(h, tnn, np.array([0.0 + 0j]), "table", sigL=zero, sigR=zero)
+
+
+def test_long_chain_unitarity_and_oracle():
+    """cfg3 down-scaled: N=1000 disordered sites (the dense reference path cannot do this size)."""
+    h, tnn, _ = configs.disordered_blocks(N=1000, n=8, W=0.05, seed=7)
+    Es = np.linspace(-1.9, 1.9, 40).astype(complex)
+    R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+    assert np.max(np.abs(res)) < UNIT
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es[::8], np.eye(8))
+    _check(R[0, ::8], T[0, ::8], oR, oT)
+
+
+def test_green_column_and_full_against_oracle():
+    rng = np.random.default_rng(5)
+    for n in (2, 6, 20):
+        M = 5
+        A = rng.standard_normal((M, n, n)) + 1j * rng.standard_normal((M, n, n))
+        h = 0.3 * (A + np.conj(np.swapaxes(A, 1, 2))) / 2
+        h[0] = 0
+        h[-1] = 0
+        tnn = -np.tile(np.eye(n, dtype=complex), (M - 1, 1, 1)) + 0.1 * rng.standard_normal((M - 1, n, n))
+        tnn[0] = -np.eye(n)
+        tnn[-1] = -np.eye(n)
+        Es = np.array([-1.2, 0.3], dtype=complex)
+        SL, SR = rgf_oracle.closed_selfenergies(h, tnn, Es)
+        dSL, dSR = leads.self_energies_batched(h, tnn, Es, "g_closed")
+        assert np.allclose(dSL, SL, rtol=1e-13, atol=1e-15) and np.allclose(dSR, SR, rtol=1e-13, atol=1e-15)
+        col = green.green_column0(h, tnn, Es, SL, SR)
+        assert np.allclose(col, rgf_oracle.green_column0(h, tnn, Es, SL, SR), rtol=1e-10, atol=1e-13)
+        full = green.green_full(h, tnn, Es, SL, SR)
+        want = np.array([wfm_oracle.Green(h, tnn, np.zeros((M - 2, n, n), complex), 1.0, E, "g_closed") for E in Es])
+        assert np.allclose(full, want, rtol=1e-10, atol=1e-12)

@@ -1,0 +1,114 @@
+"""ctypes binding of libtransport_b200.so (include/transport_b200.h).
+
+The library is the product: there is no Python/numpy fallback for any compute entry point.
+`load()` raises if the shared object has not been built (python -m transport_b200.build), and
+every compute call raises `TransportError` when no CUDA device is present.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libtransport_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "transport_b200.h")
+
+TX_OK, TX_ERR_ARG, TX_ERR_CUDA, TX_ERR_SINGULAR, TX_ERR_NOCONV, TX_ERR_UNSUPPORTED = range(6)
+TX_LEAD_CLOSED, TX_LEAD_TABLE = 0, 1
+TX_HOP_AUTO, TX_HOP_SCALAR, TX_HOP_GENERAL = 0, 1, 2
+TX_GF_CLOSED, TX_GF_RICEMELE, TX_GF_FIXEDPOINT, TX_GF_SANCHO = 0, 1, 2, 3
+
+
+class TransportError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("transport_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+c_void_p, c_int, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+_P = c_void_p
+
+_SIGNATURES = {
+    "tx_version": (ctypes.c_char_p, []),
+    "tx_last_error": (ctypes.c_char_p, []),
+    "tx_device_count": (c_int, []),
+    "tx_set_device": (c_int, [c_int]),
+    "tx_device_synchronize": (c_int, []),
+    "tx_set_variant": (c_int, [c_int]),
+    "tx_sweep_launch_count": (c_int, [c_int, c_int, c_int]),
+    "tx_transmission_sweep": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
+                                      c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P]),
+    "tx_transmission_sweep_dev": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
+                                          c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "tx_surface_gf": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
+                              _P, _P, _P, _P, _P]),
+    "tx_surface_gf_dev": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
+                                  _P, _P, _P, _P, _P, _P, _P]),
+    "tx_g_ith": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_double, c_int, _P, _P]),
+    "tx_green_column0": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "tx_green_full": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "tx_hmat": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "tx_measure_fp64_peak": (c_int, [_P, _P]),
+    "tx_measure_dmma_peak": (c_int, [_P, _P]),
+    "tx_microbench": (c_int, [c_int, _P]),
+}
+
+
+def declared_symbols():
+    """Every function name include/transport_b200.h declares (used by the CPU export test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tx_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load the shared library (once).  Raises if it is missing: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libtransport_b200.so is not built (run `python -m transport_b200.build`); "
+                          "transport_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != TX_OK:
+        raise TransportError(code, load().tx_last_error().decode())
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_void_p)
+
+
+def as_c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    return int(load().tx_device_count())
+
+
+def require_device():
+    if device_count() < 1:
+        raise TransportError(TX_ERR_CUDA, "no CUDA device available (transport_b200 has no CPU fallback)")

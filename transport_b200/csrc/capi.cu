@@ -1,0 +1,314 @@
+// C ABI of libtransport_b200.so (declared in include/transport_b200.h).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "rgf_small.cuh"
+#include "tx_host.h"
+
+using namespace tx;
+
+namespace tx {
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace tx
+
+namespace {
+
+// ---- grow-only device workspace for the host-pointer entry points ------------------------
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return TX_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) return fail(TX_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return TX_OK;
+    }
+};
+struct Workspace {
+    DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, flag;
+    cudaStream_t stream = nullptr;
+    int device = -1;
+};
+std::mutex g_ws_mutex;
+Workspace g_ws[16];
+
+int round_up_block(int n) {
+    if (n <= 1) return 1;
+    if (n <= 2) return 2;
+    if (n <= 4) return 4;
+    if (n <= 8) return 8;
+    if (n <= 16) return 16;
+    return 0;
+}
+
+// Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
+// number of resident 128-thread blocks per SM the register allocation is capped for.
+int g_variant = 0;
+
+template <int N, int LP, int HOP, int LEAD, int MINB>
+int launch_small(const SweepParams& p, cudaStream_t st) {
+    using Cfg = SmallCfg<N, LP, HOP>;
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * Cfg::PER_WARP_BYTES;
+    static bool attr_done[16] = {false};
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 15]) {
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_small<N, LP, HOP, LEAD, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 15] = true;
+    }
+    const long long per_block = (long long)WARPS * Cfg::GPW;
+    const long long blocks = (p.n_pts + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
+    rgf_sweep_small<N, LP, HOP, LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    TX_CUDA(cudaGetLastError());
+    return TX_OK;
+}
+
+template <int N, int LP, int MB_SCALAR, int MB_GENERAL>
+int dispatch_modes(const SweepParams& p, int hop, int lead, cudaStream_t st) {
+    if (hop == HOP_SCALAR) {
+        if (lead == LEAD_CLOSED) return launch_small<N, LP, HOP_SCALAR, LEAD_CLOSED, MB_SCALAR>(p, st);
+        return launch_small<N, LP, HOP_SCALAR, LEAD_TABLE, MB_SCALAR>(p, st);
+    }
+    if (lead == LEAD_CLOSED) return launch_small<N, LP, HOP_GENERAL, LEAD_CLOSED, MB_GENERAL>(p, st);
+    return launch_small<N, LP, HOP_GENERAL, LEAD_TABLE, MB_GENERAL>(p, st);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* tx_version(void) { return "transport_b200 0.1 (sm_100a)"; }
+const char* tx_last_error(void) { return g_err; }
+
+int tx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int tx_set_device(int device) {
+    TX_CUDA(cudaSetDevice(device));
+    return TX_OK;
+}
+
+int tx_device_synchronize(void) {
+    TX_CUDA(cudaDeviceSynchronize());
+    return TX_OK;
+}
+
+int tx_set_variant(int v) {
+    if (v < 0 || v > 3) return fail(TX_ERR_ARG, "variant must be 0..3");
+    g_variant = v;
+    return TX_OK;
+}
+
+int tx_sweep_launch_count(int n, int M, int hop_mode) {
+    (void)M;
+    (void)hop_mode;
+    return round_up_block(n) ? 1 : 0;
+}
+
+int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                              const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                              const tx_cplx* E, int nE,
+                              int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                              int hop_mode,
+                              const double* sources, const int* src_idx, int n_src,
+                              double* R, double* T, double* resid, double* t_total,
+                              int* singular_flag, void* stream) {
+    if (!h || !tnn || !E || !R || !T || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || M < 2 || n_ham < 1 || nE < 1 || n_src < 1)
+        return fail(TX_ERR_ARG, "bad sizes n=%d M=%d n_ham=%d nE=%d n_src=%d", n, M, n_ham, nE, n_src);
+    if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham))
+        return fail(TX_ERR_ARG, "n_h/n_t must be 1 or n_ham");
+    if (h1 && !params) return fail(TX_ERR_ARG, "h1 given without params");
+    if (src_idx) return fail(TX_ERR_ARG, "src_idx is resolved by the host entry point; pass sources to the device entry");
+    if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
+    if (lead_mode == TX_LEAD_TABLE) {
+        if (!sigL || !sigR) return fail(TX_ERR_ARG, "TX_LEAD_TABLE needs sigL and sigR");
+        if (!(n_sig == 1 || n_sig == n_ham)) return fail(TX_ERR_ARG, "n_sig must be 1 or n_ham");
+    } else if (lead_mode != TX_LEAD_CLOSED) {
+        return fail(TX_ERR_ARG, "unknown lead_mode %d", lead_mode);
+    }
+    if (!aligned16(h) || !aligned16(tnn) || !aligned16(E) || (h1 && !aligned16(h1)) ||
+        (sigL && !aligned16(sigL)) || (sigR && !aligned16(sigR)))
+        return fail(TX_ERR_ARG, "complex arrays must be 16-byte aligned");
+    const int N = round_up_block(n);
+    if (N == 0) return fail(TX_ERR_UNSUPPORTED, "block size n=%d > 16 not covered by the small-block sweep", n);
+
+    SweepParams p;
+    p.h = reinterpret_cast<const cd*>(h);
+    p.h_stride = (n_h == 1) ? 0 : (long long)M * n * n;
+    p.h1 = reinterpret_cast<const cd*>(h1);
+    p.params = params;
+    p.tnn = reinterpret_cast<const cd*>(tnn);
+    p.t_stride = (n_t == 1) ? 0 : (long long)(M - 1) * n * n;
+    p.E = reinterpret_cast<const cd*>(E);
+    p.sigL = reinterpret_cast<const cd*>(sigL);
+    p.sigR = reinterpret_cast<const cd*>(sigR);
+    p.sig_stride = (n_sig == 1) ? 0 : (long long)nE * n * n;
+    p.sources = sources;
+    p.R = R;
+    p.T = T;
+    p.resid = resid;
+    p.ttot = t_total;
+    p.singular = singular_flag;
+    p.n_pts = (long long)n_ham * nE;
+    p.n = n;
+    p.M = M;
+    p.nE = nE;
+    p.n_src = n_src;
+
+    const int hop = (hop_mode == TX_HOP_SCALAR) ? HOP_SCALAR : HOP_GENERAL;
+    const int lead = (lead_mode == TX_LEAD_TABLE) ? LEAD_TABLE : LEAD_CLOSED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (N) {
+        case 1: return dispatch_modes<1, 1, 4, 4>(p, hop, lead, st);
+        case 2: return dispatch_modes<2, 1, 4, 4>(p, hop, lead, st);
+        case 4: return dispatch_modes<4, 2, 3, 3>(p, hop, lead, st);
+        case 8:
+            if (hop == HOP_SCALAR && lead == LEAD_CLOSED) {
+                if (g_variant == 1) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
+                if (g_variant == 2) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
+                if (g_variant == 3) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
+            }
+            return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
+        case 16: return dispatch_modes<16, 16, 3, 2>(p, hop, lead, st);
+    }
+    return fail(TX_ERR_UNSUPPORTED, "unreachable");
+}
+
+int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                          const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                          const tx_cplx* E, int nE,
+                          int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                          int hop_mode,
+                          const double* sources, const int* src_idx, int n_src,
+                          double* R, double* T, double* resid, double* t_total) {
+    if (!h || !tnn || !E || !R || !T) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || M < 2 || n_ham < 1 || nE < 1 || n_src < 1)
+        return fail(TX_ERR_ARG, "bad sizes n=%d M=%d n_ham=%d nE=%d n_src=%d", n, M, n_ham, nE, n_src);
+    if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham))
+        return fail(TX_ERR_ARG, "n_h/n_t must be 1 or n_ham");
+    if (sources && src_idx) return fail(TX_ERR_ARG, "give sources or src_idx, not both");
+    if (tx_device_count() < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+
+    const size_t nn = (size_t)n * n;
+    // hopping structure (TX_HOP_AUTO): scalar multiples of the identity -> cheaper kernel
+    if (hop_mode == TX_HOP_AUTO) {
+        hop_mode = TX_HOP_SCALAR;
+        const size_t blocks = (size_t)n_t * (M - 1);
+        for (size_t b = 0; b < blocks && hop_mode == TX_HOP_SCALAR; ++b) {
+            const tx_cplx* t = tnn + b * nn;
+            for (int r = 0; r < n && hop_mode == TX_HOP_SCALAR; ++r)
+                for (int c = 0; c < n; ++c) {
+                    const tx_cplx v = t[(size_t)r * n + c];
+                    if (r == c) {
+                        if (v.re != t[0].re || v.im != t[0].im) hop_mode = TX_HOP_GENERAL;
+                    } else if (v.re != 0.0 || v.im != 0.0) {
+                        hop_mode = TX_HOP_GENERAL;
+                    }
+                }
+        }
+    }
+    // one-hot index lists become amplitude vectors
+    std::vector<double> src_host;
+    if (src_idx) {
+        src_host.assign((size_t)n_src * n, 0.0);
+        for (int i = 0; i < n_src; ++i) {
+            if (src_idx[i] < 0 || src_idx[i] >= n) return fail(TX_ERR_ARG, "src_idx[%d]=%d out of range", i, src_idx[i]);
+            src_host[(size_t)i * n + src_idx[i]] = 1.0;
+        }
+        sources = src_host.data();
+    }
+    if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
+
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace& ws = g_ws[dev & 15];
+    if (!ws.stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+    cudaStream_t st = ws.stream;
+
+    const size_t n_pts = (size_t)n_ham * nE;
+    const size_t bytes_h = (size_t)n_h * M * nn * sizeof(tx_cplx);
+    const size_t bytes_h1 = h1 ? (size_t)M * nn * sizeof(tx_cplx) : 0;
+    const size_t bytes_t = (size_t)n_t * (M - 1) * nn * sizeof(tx_cplx);
+    const size_t bytes_E = (size_t)nE * sizeof(tx_cplx);
+    const size_t bytes_sig = (lead_mode == TX_LEAD_TABLE) ? (size_t)n_sig * nE * nn * sizeof(tx_cplx) : 0;
+    const size_t bytes_src = sources ? (size_t)n_src * n * sizeof(double) : 0;
+    const size_t bytes_out = n_pts * n_src * n * sizeof(double);
+    const size_t bytes_res = resid ? n_pts * n_src * sizeof(double) : 0;
+
+    int rc;
+    if ((rc = ws.h.ensure(bytes_h)) || (rc = ws.tnn.ensure(bytes_t)) || (rc = ws.E.ensure(bytes_E)) ||
+        (rc = ws.R.ensure(bytes_out)) || (rc = ws.T.ensure(bytes_out)) || (rc = ws.flag.ensure(sizeof(int))))
+        return rc;
+    if (h1 && ((rc = ws.h1.ensure(bytes_h1)) || (rc = ws.par.ensure((size_t)n_ham * sizeof(double))))) return rc;
+    if (bytes_sig && ((rc = ws.sigL.ensure(bytes_sig)) || (rc = ws.sigR.ensure(bytes_sig)))) return rc;
+    if (bytes_src && (rc = ws.src.ensure(bytes_src))) return rc;
+    if (bytes_res && (rc = ws.resid.ensure(bytes_res))) return rc;
+    if (t_total && (rc = ws.ttot.ensure(n_pts * sizeof(double)))) return rc;
+
+    TX_CUDA(cudaMemcpyAsync(ws.h.ptr, h, bytes_h, cudaMemcpyHostToDevice, st));
+    TX_CUDA(cudaMemcpyAsync(ws.tnn.ptr, tnn, bytes_t, cudaMemcpyHostToDevice, st));
+    TX_CUDA(cudaMemcpyAsync(ws.E.ptr, E, bytes_E, cudaMemcpyHostToDevice, st));
+    if (h1) {
+        if (!params) return fail(TX_ERR_ARG, "h1 given without params");
+        TX_CUDA(cudaMemcpyAsync(ws.h1.ptr, h1, bytes_h1, cudaMemcpyHostToDevice, st));
+        TX_CUDA(cudaMemcpyAsync(ws.par.ptr, params, (size_t)n_ham * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (bytes_sig) {
+        if (!sigL || !sigR) return fail(TX_ERR_ARG, "TX_LEAD_TABLE needs sigL and sigR");
+        TX_CUDA(cudaMemcpyAsync(ws.sigL.ptr, sigL, bytes_sig, cudaMemcpyHostToDevice, st));
+        TX_CUDA(cudaMemcpyAsync(ws.sigR.ptr, sigR, bytes_sig, cudaMemcpyHostToDevice, st));
+    }
+    if (bytes_src) TX_CUDA(cudaMemcpyAsync(ws.src.ptr, sources, bytes_src, cudaMemcpyHostToDevice, st));
+    TX_CUDA(cudaMemsetAsync(ws.flag.ptr, 0, sizeof(int), st));
+
+    rc = tx_transmission_sweep_dev(
+        (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
+        (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE, lead_mode,
+        bytes_sig ? (const tx_cplx*)ws.sigL.ptr : nullptr, bytes_sig ? (const tx_cplx*)ws.sigR.ptr : nullptr, n_sig,
+        hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src, (double*)ws.R.ptr,
+        (double*)ws.T.ptr, bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
+        (int*)ws.flag.ptr, st);
+    if (rc) return rc;
+
+    int flag = 0;
+    TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+    TX_CUDA(cudaMemcpyAsync(T, ws.T.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+    if (bytes_res) TX_CUDA(cudaMemcpyAsync(resid, ws.resid.ptr, bytes_res, cudaMemcpyDeviceToHost, st));
+    if (t_total) TX_CUDA(cudaMemcpyAsync(t_total, ws.ttot.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TX_CUDA(cudaMemcpyAsync(&flag, ws.flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TX_CUDA(cudaStreamSynchronize(st));
+    if (flag) return fail(TX_ERR_SINGULAR, "a singular block was met during the sweep (results contain inf/nan there)");
+    return TX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Generic-size Green's-function blocks, one CTA per energy (any n <= 64):
+//   tx_green_column0  first block column G[:,0]  -> wavefunction psi_j = i G[j,0] (A o v_L)
+//                     (transport/wfm/__init__.py:98-99)
+//   tx_green_full     all M x M blocks of inv(E - H')           (wfm.Green, :139-166)
+//   tx_hmat           dense block-pentadiagonal assembly         (wfm.Hmat,  :168-215)
+// The reference obtains G by a dense (M n)^3 inverse and reshapes it with a 4-deep Python loop
+// (transport/tdfci/utils.py:290-316); here the blocks come from left/right recursive sweeps.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "block_ops.cuh"
+#include "tx_host.h"
+
+using namespace tx;
+
+namespace {
+
+struct GreenParams {
+    const cd* h;      // [M][n][n]
+    const cd* tnn;    // [M-1][n][n]
+    const cd* E;      // [nE]
+    const cd* sigL;   // [nE][n][n]
+    const cd* sigR;
+    cd* out;          // column0: [nE][M][n][n]; full: [nE][M][M][n][n]
+    cd* work;         // full: [nE][2][M][n][n]  (gL, gR)
+    int* singular;
+    int n, M, nE;
+};
+
+constexpr int GR_THREADS = 128;
+
+__global__ void __launch_bounds__(GR_THREADS) green_column0_kernel(const GreenParams p) {
+    extern __shared__ double2 gr_smem[];
+    __shared__ int s_ipiv[64];
+    __shared__ cd s_colk[64];
+    const int n = p.n, M = p.M, nn = n * n;
+    const int e = blockIdx.x;
+    const cd E = p.E[e];
+    cd* A = reinterpret_cast<cd*>(gr_smem);
+    cd* X = A + nn;
+    cd* Gc = p.out + (long long)e * M * nn;
+    const cd* SL = p.sigL + (long long)e * nn;
+    const cd* SR = p.sigR + (long long)e * nn;
+
+    // right-connected g^R_j, stored in the output slots
+    for (int j = M - 1; j >= 0; --j) {
+        cta_z_minus(A, E, p.h + (long long)j * nn, n);
+        if (j == M - 1) cta_sub(A, SR, nn);
+        if (j == 0) cta_sub(A, SL, nn);
+        if (j < M - 1) {
+            const cd* t = p.tnn + (long long)j * nn;
+            cta_gemm(X, t, OP_N, Gc + (long long)(j + 1) * nn, OP_N, n);     // t_j g_{j+1}
+            cta_gemm_acc(A, X, OP_N, t, OP_H, n, -1.0);                      // - (.) t_j^dag
+        }
+        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        cta_copy(Gc + (long long)j * nn, A, nn);
+    }
+    // G_{j,0} = g^R_j t_{j-1}^dag G_{j-1,0}
+    for (int j = 1; j < M; ++j) {
+        const cd* t = p.tnn + (long long)(j - 1) * nn;
+        cta_gemm(X, t, OP_H, Gc + (long long)(j - 1) * nn, OP_N, n);
+        cta_gemm(A, Gc + (long long)j * nn, OP_N, X, OP_N, n);
+        cta_copy(Gc + (long long)j * nn, A, nn);
+    }
+}
+
+__global__ void __launch_bounds__(GR_THREADS) green_full_kernel(const GreenParams p) {
+    extern __shared__ double2 gr_smem[];
+    __shared__ int s_ipiv[64];
+    __shared__ cd s_colk[64];
+    const int n = p.n, M = p.M, nn = n * n;
+    const int e = blockIdx.x;
+    const cd E = p.E[e];
+    cd* A = reinterpret_cast<cd*>(gr_smem);
+    cd* X = A + nn;
+    cd* G = p.out + (long long)e * M * M * nn;
+    cd* gL = p.work + (long long)e * 2 * M * nn;
+    cd* gR = gL + (long long)M * nn;
+    const cd* SL = p.sigL + (long long)e * nn;
+    const cd* SR = p.sigR + (long long)e * nn;
+    auto blk = [&](int r, int c) { return G + ((long long)r * M + c) * nn; };
+
+    for (int j = 0; j < M; ++j) {                       // left-connected
+        cta_z_minus(A, E, p.h + (long long)j * nn, n);
+        if (j == 0) cta_sub(A, SL, nn);
+        if (j == M - 1) cta_sub(A, SR, nn);
+        if (j > 0) {
+            const cd* t = p.tnn + (long long)(j - 1) * nn;
+            cta_gemm(X, t, OP_H, gL + (long long)(j - 1) * nn, OP_N, n);
+            cta_gemm_acc(A, X, OP_N, t, OP_N, n, -1.0);
+        }
+        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        cta_copy(gL + (long long)j * nn, A, nn);
+    }
+    for (int j = M - 1; j >= 0; --j) {                  // right-connected
+        cta_z_minus(A, E, p.h + (long long)j * nn, n);
+        if (j == 0) cta_sub(A, SL, nn);
+        if (j == M - 1) cta_sub(A, SR, nn);
+        if (j < M - 1) {
+            const cd* t = p.tnn + (long long)j * nn;
+            cta_gemm(X, t, OP_N, gR + (long long)(j + 1) * nn, OP_N, n);
+            cta_gemm_acc(A, X, OP_N, t, OP_H, n, -1.0);
+        }
+        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        cta_copy(gR + (long long)j * nn, A, nn);
+    }
+    for (int j = 0; j < M; ++j) {                       // diagonal blocks
+        cta_z_minus(A, E, p.h + (long long)j * nn, n);
+        if (j == 0) cta_sub(A, SL, nn);
+        if (j == M - 1) cta_sub(A, SR, nn);
+        if (j > 0) {
+            const cd* t = p.tnn + (long long)(j - 1) * nn;
+            cta_gemm(X, t, OP_H, gL + (long long)(j - 1) * nn, OP_N, n);
+            cta_gemm_acc(A, X, OP_N, t, OP_N, n, -1.0);
+        }
+        if (j < M - 1) {
+            const cd* t = p.tnn + (long long)j * nn;
+            cta_gemm(X, t, OP_N, gR + (long long)(j + 1) * nn, OP_N, n);
+            cta_gemm_acc(A, X, OP_N, t, OP_H, n, -1.0);
+        }
+        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        cta_copy(blk(j, j), A, nn);
+    }
+    for (int c = 0; c < M; ++c) {                       // off-diagonal blocks, column by column
+        for (int r = c + 1; r < M; ++r) {
+            cta_gemm(X, p.tnn + (long long)(r - 1) * nn, OP_H, blk(r - 1, c), OP_N, n);
+            cta_gemm(blk(r, c), gR + (long long)r * nn, OP_N, X, OP_N, n);
+        }
+        for (int r = c - 1; r >= 0; --r) {
+            cta_gemm(X, p.tnn + (long long)r * nn, OP_N, blk(r + 1, c), OP_N, n);
+            cta_gemm(blk(r, c), gL + (long long)r * nn, OP_N, X, OP_N, n);
+        }
+    }
+}
+
+__global__ void hmat_kernel(const cd* __restrict__ h, const cd* __restrict__ tnn, const cd* __restrict__ tnnn,
+                            cd* __restrict__ H, int n, int M) {
+    const long long dim = (long long)n * M;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= dim * dim) return;
+    const int row = (int)(idx / dim), col = (int)(idx - (long long)row * dim);
+    const int si = row / n, a = row - si * n;
+    const int sj = col / n, b = col - sj * n;
+    const long long nn = (long long)n * n;
+    cd v = mk(0.0, 0.0);
+    if (si == sj) v = h[si * nn + a * n + b];                       // wfm/__init__.py:200-201
+    else if (si == sj + 1) v = conj(tnn[sj * nn + b * n + a]);      // :203-204
+    else if (si + 1 == sj) v = tnn[si * nn + a * n + b];            // :206-207
+    else if (si == sj + 2) v = conj(tnnn[sj * nn + b * n + a]);     // :209-210
+    else if (si + 2 == sj) v = tnnn[si * nn + a * n + b];           // :212-213
+    H[idx] = v;
+}
+
+struct DevMem {
+    char* p = nullptr;
+    ~DevMem() {
+        if (p) cudaFree(p);
+    }
+};
+
+int green_host(int which, const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
+               const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* out) {
+    if (!h || !tnn || !E || !sigL || !sigR || !out) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..64", n);
+    if (M < 2 || nE < 1) return fail(TX_ERR_ARG, "bad sizes M=%d nE=%d", M, nE);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t nn = (size_t)n * n, bc = sizeof(cd);
+    const size_t b_h = (size_t)M * nn * bc, b_t = (size_t)(M - 1) * nn * bc, b_E = ((size_t)nE * bc + 255) & ~(size_t)255;
+    const size_t b_s = (size_t)nE * nn * bc;
+    const size_t b_out = (size_t)nE * (which == 0 ? M : (size_t)M * M) * nn * bc;
+    const size_t b_work = which == 0 ? 0 : (size_t)nE * 2 * M * nn * bc;
+    DevMem d;
+    TX_CUDA(cudaMalloc(&d.p, b_h + b_t + b_E + 2 * b_s + b_out + b_work + 256));
+    char* q = d.p;
+    GreenParams p{};
+    p.h = (const cd*)q;      TX_CUDA(cudaMemcpy(q, h, b_h, cudaMemcpyHostToDevice));      q += b_h;
+    p.tnn = (const cd*)q;    TX_CUDA(cudaMemcpy(q, tnn, b_t, cudaMemcpyHostToDevice));    q += b_t;
+    p.E = (const cd*)q;      TX_CUDA(cudaMemcpy(q, E, (size_t)nE * bc, cudaMemcpyHostToDevice)); q += b_E;
+    p.sigL = (const cd*)q;   TX_CUDA(cudaMemcpy(q, sigL, b_s, cudaMemcpyHostToDevice));   q += b_s;
+    p.sigR = (const cd*)q;   TX_CUDA(cudaMemcpy(q, sigR, b_s, cudaMemcpyHostToDevice));   q += b_s;
+    p.out = (cd*)q;          q += b_out;
+    p.work = (cd*)q;         q += b_work;
+    p.singular = (int*)q;    TX_CUDA(cudaMemset(q, 0, 4));
+    p.n = n;
+    p.M = M;
+    p.nE = nE;
+    const size_t smem = 2 * nn * bc;
+    if (which == 0) {
+        if (smem > 48 * 1024)
+            TX_CUDA(cudaFuncSetAttribute(green_column0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        green_column0_kernel<<<nE, GR_THREADS, smem>>>(p);
+    } else {
+        if (smem > 48 * 1024)
+            TX_CUDA(cudaFuncSetAttribute(green_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        green_full_kernel<<<nE, GR_THREADS, smem>>>(p);
+    }
+    TX_CUDA(cudaGetLastError());
+    TX_CUDA(cudaDeviceSynchronize());
+    int flag = 0;
+    TX_CUDA(cudaMemcpy(out, p.out, b_out, cudaMemcpyDeviceToHost));
+    TX_CUDA(cudaMemcpy(&flag, p.singular, 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(TX_ERR_SINGULAR, "singular block in the Green's function recursion");
+    return TX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tx_green_column0(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
+                     const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G) {
+    return green_host(0, h, tnn, n, M, E, nE, sigL, sigR, G);
+}
+
+int tx_green_full(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
+                  const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G) {
+    return green_host(1, h, tnn, n, M, E, nE, sigL, sigR, G);
+}
+
+int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, int M, tx_cplx* H) {
+    if (!h || !tnn || !H || (M > 2 && !tnnn)) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || M < 2) return fail(TX_ERR_ARG, "bad sizes n=%d M=%d", n, M);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t nn = (size_t)n * n, bc = sizeof(cd);
+    const size_t b_h = (size_t)M * nn * bc, b_t = (size_t)(M - 1) * nn * bc, b_tt = (size_t)(M > 2 ? M - 2 : 1) * nn * bc;
+    const size_t dim = (size_t)n * M, b_H = dim * dim * bc;
+    DevMem d;
+    TX_CUDA(cudaMalloc(&d.p, b_h + b_t + b_tt + b_H));
+    char* q = d.p;
+    const cd* dh = (const cd*)q;   TX_CUDA(cudaMemcpy(q, h, b_h, cudaMemcpyHostToDevice));     q += b_h;
+    const cd* dt = (const cd*)q;   TX_CUDA(cudaMemcpy(q, tnn, b_t, cudaMemcpyHostToDevice));   q += b_t;
+    const cd* dtt = (const cd*)q;
+    if (M > 2) TX_CUDA(cudaMemcpy(q, tnnn, (size_t)(M - 2) * nn * bc, cudaMemcpyHostToDevice));
+    q += b_tt;
+    cd* dH = (cd*)q;
+    const long long total = (long long)dim * dim;
+    hmat_kernel<<<(unsigned)((total + 255) / 256), 256>>>(dh, dt, dtt, dH, n, M);
+    TX_CUDA(cudaGetLastError());
+    TX_CUDA(cudaMemcpy(H, dH, b_H, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+// K1: batched lead surface Green's functions and self-energies, one CTA per energy.
+//
+// Reference functions replaced (cpbunker/transport, transport/wfm/__init__.py):
+//   g_closed   :306-340   closed form per channel of a monatomic lead
+//   g_RiceMele :352-414   closed form per spin channel of a diatomic (Rice-Mele) lead
+//   g_ith      :532-551   one step of the fixed point  g <- (z - h00 - t g t^dag)^-1
+//   g_iter     :479-530   that iteration with the surface-DOS stopping rule
+//   SelfEnergies :270-304 Sigma_L = t0^dag g_L t0,  Sigma_R = tN g_R tN^dag
+// plus Sancho-Rubio decimation (quadratically convergent) of the same fixed point for
+// multi-channel leads, which the reference cannot do (g_iter refuses n > 2, :502).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "block_ops.cuh"
+#include "tx_host.h"
+
+using namespace tx;
+
+namespace {
+
+struct GfParams {
+    const cd* h00;      // [n][n]
+    const cd* h01;      // [n][n]  upper hopping block of the lead
+    const cd* E;        // [nE]
+    cd* g;              // [nE][n][n] or null
+    cd* sigma;          // [nE][n][n] or null:  side=-1: h01^dag g h01 ; side=+1: h01 g h01^dag
+    const cd* g_prev;   // g_ith only
+    int* n_iter;        // [nE] or null
+    double* conv;       // [nE] or null
+    int* converged;     // [nE] or null
+    cd* scratch;        // global workspace (n > 32), per energy `scratch_per` elements
+    long long scratch_per;
+    int* singular;
+    int n, nE, side, mode;
+    double imE, conv_tol;
+    int conv_rep, min_iter, max_iter, ith;
+};
+
+constexpr int GF_THREADS = 128;
+constexpr int GF_MAX_MATS = 9;
+
+// wfm.g_RiceMele for spin channel s (wfm/__init__.py:379-403)
+__device__ cd ricemele_channel(const cd* diag, const cd* off, int n, int s, cd E) {
+    const int ns = n / 2;
+    const cd dA = diag[s * n + s], dB = diag[(ns + s) * n + (ns + s)];
+    const cd u = scale(dA - dB, 0.5);
+    const cd u0 = scale(dA + dB, 0.5);
+    const cd v = diag[s * n + (ns + s)];
+    const cd w = off[(ns + s) * n + s];
+    const cd x = E - u0;
+    const cd Z = (x + u) * (x - u) + (w + v) * (w - v);
+    const cd den = scale(w * w, 2.0) * (E - u0 - u);
+    const cd pref = cdiv(mk(1.0, 0.0), den);
+    const cd inner = scale(w * w, 4.0) * (u + E - u0) * (u - E + u0) + Z * Z;
+    cd root = csqrt_principal(inner);
+    const cd chk = root * pref;
+    if (chk.y > 0.0) root = mk(-root.x, -root.y);          // retarded: Im g < 0  (:401-402)
+    return pref * (Z + root);
+}
+
+// sigma = h01^dag g h01 (side=-1)  or  h01 g h01^dag (side=+1)
+__device__ void emit_sigma(const GfParams& p, const cd* g, cd* tmp, cd* out) {
+    const int n = p.n;
+    if (p.side == -1) {
+        cta_gemm(tmp, g, OP_N, p.h01, OP_N, n);
+        cta_gemm(out, p.h01, OP_H, tmp, OP_N, n);
+    } else {
+        cta_gemm(tmp, g, OP_N, p.h01, OP_H, n);
+        cta_gemm(out, p.h01, OP_N, tmp, OP_N, n);
+    }
+}
+
+__global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p) {
+    extern __shared__ double2 gf_smem[];
+    __shared__ int s_ipiv[64];
+    __shared__ cd s_colk[64];
+    __shared__ int s_flag;
+    const int n = p.n;
+    const int nn = n * n;
+    const int e = blockIdx.x;
+    const cd E = p.E[e];
+    cd* base = (p.scratch != nullptr) ? p.scratch + (long long)e * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
+    cd* m0 = base;               // g / result
+    cd* m1 = base + nn;
+    cd* m2 = base + 2 * nn;
+
+    if (p.mode == TX_GF_CLOSED || p.mode == TX_GF_RICEMELE) {
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) m0[idx] = mk(0.0, 0.0);
+        __syncthreads();
+        if (p.mode == TX_GF_CLOSED) {
+            for (int c = threadIdx.x; c < n; c += blockDim.x)
+                m0[c * n + c] = g_closed_channel(E, p.h00[c * n + c], p.h01[c * n + c]);
+        } else {
+            const int ns = n / 2;
+            for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+                const cd gs = ricemele_channel(p.h00, p.h01, n, s, E);
+                if (p.side == -1) m0[(ns + s) * n + (ns + s)] = gs;   // <B|g|B>  (:407-410)
+                else m0[s * n + s] = gs;                               // <A|g|A>  (:411-413)
+            }
+        }
+        __syncthreads();
+    } else if (p.mode == TX_GF_FIXEDPOINT) {
+        // g_iter (:504-530) / g_ith (:541-551)
+        const cd z = mk(E.x, fabs(p.imE));
+        const int dpos = (p.side == 1) ? 0 : nn - 1;           // :516-517
+        double dos_prev = 0.0, check = 0.0;
+        int run = 0, it_done = 0, ok = 0;
+        const int first = (p.ith >= 0) ? p.ith : 0;
+        const int last = (p.ith >= 0) ? p.ith + 1 : p.max_iter;
+        if (p.ith > 0) cta_copy(m0, p.g_prev + (long long)e * nn, nn);
+        for (int ith = first; ith < last; ++ith) {
+            cta_z_minus(m1, z, p.h00, n);
+            if (ith > 0) {
+                if (p.side == 1) {                              // t g t^dag   (:548)
+                    cta_gemm(m2, m0, OP_N, p.h01, OP_H, n);
+                    cta_gemm_acc(m1, p.h01, OP_N, m2, OP_N, n, -1.0);
+                } else {                                        // t^dag g t   (:550)
+                    cta_gemm(m2, m0, OP_N, p.h01, OP_N, n);
+                    cta_gemm_acc(m1, p.h01, OP_H, m2, OP_N, n, -1.0);
+                }
+            }
+            cta_inverse(m1, n, s_colk, s_ipiv, p.singular);
+            cta_copy(m0, m1, nn);
+            it_done = ith;
+            if (p.ith < 0) {
+                const double dos = (-1.0 / 3.141592653589793) * m0[dpos].y;
+                if (ith > p.min_iter) {                         // :520-523
+                    check = fabs((dos - dos_prev) / dos);
+                    run = (check < p.conv_tol) ? run + 1 : 0;
+                    if (run >= p.conv_rep) {
+                        ok = 1;
+                        break;
+                    }
+                }
+                dos_prev = dos;
+            }
+        }
+        if (threadIdx.x == 0 && p.ith < 0) {
+            if (p.n_iter) p.n_iter[e] = it_done;
+            if (p.conv) p.conv[e] = check;
+            if (p.converged) p.converged[e] = ok;
+        }
+    } else {   // TX_GF_SANCHO
+        // decimation: eps_s -> surface block, alpha/beta -> renormalised hoppings, z = E + i*imE
+        const cd z = mk(E.x, E.y + p.imE);
+        cd* alpha = base + nn;
+        cd* beta = base + 2 * nn;
+        cd* eps = base + 3 * nn;
+        cd* epss = base + 4 * nn;
+        cd* G = base + 5 * nn;
+        cd* T1 = base + 6 * nn;
+        cd* T2 = base + 7 * nn;
+        cd* tmp = base + 8 * nn;
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            const cd t = p.h01[idx];
+            const cd th = conj(p.h01[c * n + r]);
+            alpha[idx] = (p.side == 1) ? t : th;
+            beta[idx] = (p.side == 1) ? th : t;
+            eps[idx] = p.h00[idx];
+            epss[idx] = p.h00[idx];
+        }
+        __syncthreads();
+        int it = 0, ok = 0;
+        double resid = 0.0;
+        const double tol2 = p.conv_tol * p.conv_tol;
+        for (it = 1; it <= p.max_iter; ++it) {
+            cta_z_minus(G, z, eps, n);
+            cta_inverse(G, n, s_colk, s_ipiv, p.singular);
+            cta_gemm(T1, G, OP_N, beta, OP_N, n);               // G beta
+            cta_gemm(T2, G, OP_N, alpha, OP_N, n);              // G alpha
+            cta_gemm(tmp, alpha, OP_N, T1, OP_N, n);            // alpha G beta
+            for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                epss[idx] = epss[idx] + tmp[idx];
+                eps[idx] = eps[idx] + tmp[idx];
+            }
+            __syncthreads();
+            cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0);    // + beta G alpha
+            cta_gemm(tmp, alpha, OP_N, T2, OP_N, n);            // alpha G alpha
+            cta_gemm(G, beta, OP_N, T1, OP_N, n);               // beta G beta (G is free now)
+            cta_copy(alpha, tmp, nn);
+            cta_copy(beta, G, nn);
+            const double ma = cta_maxnorm2(alpha, nn);
+            const double mb = cta_maxnorm2(beta, nn);
+            resid = fmax(ma, mb);
+            if (resid < tol2) {
+                ok = 1;
+                break;
+            }
+        }
+        cta_z_minus(m0, z, epss, n);
+        cta_inverse(m0, n, s_colk, s_ipiv, p.singular);
+        if (threadIdx.x == 0) {
+            if (p.n_iter) p.n_iter[e] = it;
+            if (p.conv) p.conv[e] = sqrt(resid);
+            if (p.converged) p.converged[e] = ok;
+        }
+    }
+    (void)s_flag;
+    if (p.g) cta_copy(p.g + (long long)e * nn, m0, nn);
+    if (p.sigma) emit_sigma(p, m0, m1, p.sigma + (long long)e * nn);
+}
+
+int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
+    const int n = p.n;
+    const size_t mats = (p.mode == TX_GF_SANCHO) ? GF_MAX_MATS : 3;
+    const size_t bytes = mats * (size_t)n * n * sizeof(cd);
+    size_t smem = bytes;
+    p.scratch = nullptr;
+    p.scratch_per = 0;
+    if (bytes > 200 * 1024) {
+        smem = 0;
+        p.scratch_per = (long long)mats * n * n;
+        cd* ws = nullptr;
+        TX_CUDA(cudaMalloc(&ws, (size_t)p.nE * bytes));
+        p.scratch = ws;
+        *scratch_owner = ws;
+    }
+    if (smem > 48 * 1024)
+        TX_CUDA(cudaFuncSetAttribute(surface_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    surface_gf_kernel<<<p.nE, GF_THREADS, smem, st>>>(p);
+    TX_CUDA(cudaGetLastError());
+    return TX_OK;
+}
+
+int check_gf_args(const void* h00, const void* h01, int n, const void* E, int nE, int side, int mode) {
+    if (!h00 || !h01 || !E) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "surface GF block size n=%d outside 1..64", n);
+    if (nE < 1) return fail(TX_ERR_ARG, "nE must be positive");
+    if (side != 1 && side != -1) return fail(TX_ERR_ARG, "side must be +1 or -1");
+    if (mode < TX_GF_CLOSED || mode > TX_GF_SANCHO) return fail(TX_ERR_ARG, "unknown surface GF mode %d", mode);
+    if (mode == TX_GF_RICEMELE && (n % 2)) return fail(TX_ERR_ARG, "Rice-Mele leads need an even block size");
+    return TX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
+                      double imE, double conv_tol, int conv_rep, int min_iter, int max_iter,
+                      tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged,
+                      int* singular_flag, void* stream) {
+    int rc = check_gf_args(h00, h01, n, E, nE, side, mode);
+    if (rc) return rc;
+    if (!singular_flag) return fail(TX_ERR_ARG, "singular_flag is required");
+    GfParams p{};
+    p.h00 = reinterpret_cast<const cd*>(h00);
+    p.h01 = reinterpret_cast<const cd*>(h01);
+    p.E = reinterpret_cast<const cd*>(E);
+    p.g = reinterpret_cast<cd*>(g);
+    p.sigma = reinterpret_cast<cd*>(sigma);
+    p.g_prev = nullptr;
+    p.n_iter = n_iter;
+    p.conv = conv;
+    p.converged = converged;
+    p.singular = singular_flag;
+    p.n = n;
+    p.nE = nE;
+    p.side = side;
+    p.mode = mode;
+    p.imE = imE;
+    p.conv_tol = conv_tol;
+    p.conv_rep = conv_rep;
+    p.min_iter = min_iter;
+    p.max_iter = max_iter;
+    p.ith = -1;
+    cd* owned = nullptr;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    rc = launch_gf(p, st, &owned);
+    if (owned) {
+        cudaStreamSynchronize(st);
+        cudaFree(owned);
+    }
+    return rc;
+}
+
+// Host-pointer convenience wrappers ----------------------------------------------------------
+static int gf_host(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
+                   double imE, double conv_tol, int conv_rep, int min_iter, int max_iter, int ith,
+                   const tx_cplx* g_prev, tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged) {
+    int rc = check_gf_args(h00, h01, n, E, nE, side, mode);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t nn = (size_t)n * n;
+    const size_t bm = nn * sizeof(cd), bE = (size_t)nE * sizeof(cd), bg = (size_t)nE * bm;
+    char* d = nullptr;
+    // layout: h00 | h01 | E | g | sigma | g_prev | n_iter | conv | converged | flag
+    const size_t off_h00 = 0, off_h01 = bm, off_E = 2 * bm, off_g = off_E + ((bE + 255) & ~(size_t)255);
+    const size_t off_sig = off_g + bg, off_prev = off_sig + bg, off_ni = off_prev + bg;
+    const size_t off_cv = off_ni + (((size_t)nE * 4 + 255) & ~(size_t)255);
+    const size_t off_ok = off_cv + (size_t)nE * 8, off_flag = off_ok + (((size_t)nE * 4 + 255) & ~(size_t)255);
+    const size_t total = off_flag + 256;
+    TX_CUDA(cudaMalloc(&d, total));
+    auto cleanup = [&](int code) {
+        cudaFree(d);
+        return code;
+    };
+    if (cudaMemcpy(d + off_h00, h00, bm, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d + off_h01, h01, bm, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d + off_E, E, bE, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(d + off_flag, 0, 4) != cudaSuccess)
+        return cleanup(fail(TX_ERR_CUDA, "host to device copy failed"));
+    if (g_prev && cudaMemcpy(d + off_prev, g_prev, bg, cudaMemcpyHostToDevice) != cudaSuccess)
+        return cleanup(fail(TX_ERR_CUDA, "host to device copy failed"));
+    GfParams p{};
+    p.h00 = reinterpret_cast<const cd*>(d + off_h00);
+    p.h01 = reinterpret_cast<const cd*>(d + off_h01);
+    p.E = reinterpret_cast<const cd*>(d + off_E);
+    p.g = g ? reinterpret_cast<cd*>(d + off_g) : nullptr;
+    p.sigma = sigma ? reinterpret_cast<cd*>(d + off_sig) : nullptr;
+    p.g_prev = g_prev ? reinterpret_cast<const cd*>(d + off_prev) : nullptr;
+    p.n_iter = reinterpret_cast<int*>(d + off_ni);
+    p.conv = reinterpret_cast<double*>(d + off_cv);
+    p.converged = reinterpret_cast<int*>(d + off_ok);
+    p.singular = reinterpret_cast<int*>(d + off_flag);
+    p.n = n;
+    p.nE = nE;
+    p.side = side;
+    p.mode = mode;
+    p.imE = imE;
+    p.conv_tol = conv_tol;
+    p.conv_rep = conv_rep;
+    p.min_iter = min_iter;
+    p.max_iter = max_iter;
+    p.ith = ith;
+    cd* owned = nullptr;
+    rc = launch_gf(p, nullptr, &owned);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (owned) cudaFree(owned);
+    if (rc) return cleanup(rc);
+    if (e != cudaSuccess) return cleanup(fail(TX_ERR_CUDA, "surface GF kernel failed: %s", cudaGetErrorString(e)));
+    int flag = 0;
+    bool bad = false;
+    if (g) bad |= cudaMemcpy(g, d + off_g, bg, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (sigma) bad |= cudaMemcpy(sigma, d + off_sig, bg, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (n_iter) bad |= cudaMemcpy(n_iter, d + off_ni, (size_t)nE * 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (conv) bad |= cudaMemcpy(conv, d + off_cv, (size_t)nE * 8, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (converged) bad |= cudaMemcpy(converged, d + off_ok, (size_t)nE * 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    bad |= cudaMemcpy(&flag, d + off_flag, 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (bad) return cleanup(fail(TX_ERR_CUDA, "device to host copy failed"));
+    if (flag) return cleanup(fail(TX_ERR_SINGULAR, "singular block in the surface GF iteration"));
+    return cleanup(TX_OK);
+}
+
+int tx_surface_gf(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
+                  double imE, double conv_tol, int conv_rep, int min_iter, int max_iter,
+                  tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged) {
+    return gf_host(h00, h01, n, E, nE, side, mode, imE, conv_tol, conv_rep, min_iter, max_iter, -1, nullptr,
+                   g, sigma, n_iter, conv, converged);
+}
+
+int tx_g_ith(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, double imE,
+             int ith, const tx_cplx* g_prev, tx_cplx* g_out) {
+    if (ith < 0) return fail(TX_ERR_ARG, "ith must be >= 0");
+    if (ith > 0 && !g_prev) return fail(TX_ERR_ARG, "g_prev required for ith > 0");
+    return gf_host(h00, h01, n, E, nE, side, TX_GF_FIXEDPOINT, imE, 0.0, 0, 0, 0, ith, ith > 0 ? g_prev : nullptr,
+                   g_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Shared device helpers: complex128 arithmetic on (re, im) double pairs, closed-form lead GF.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/transport_b200.h"
+
+namespace tx {
+
+struct __align__(16) cd {
+    double x, y;
+};
+
+__host__ __device__ __forceinline__ cd mk(double x, double y) {
+    cd r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+__device__ __forceinline__ cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cd operator*(cd a, cd b) {
+    return mk(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ cd conj(cd a) { return mk(a.x, -a.y); }
+__device__ __forceinline__ cd scale(cd a, double s) { return mk(a.x * s, a.y * s); }
+__device__ __forceinline__ double norm2(cd a) { return fma(a.x, a.x, a.y * a.y); }
+
+// acc += a*b  (4 DFMA)
+__device__ __forceinline__ void cfma(double& ar, double& ai, double br, double bi, double cr, double ci) {
+    ar = fma(br, cr, ar);
+    ar = fma(-bi, ci, ar);
+    ai = fma(br, ci, ai);
+    ai = fma(bi, cr, ai);
+}
+// acc -= a*b  (4 DFMA)
+__device__ __forceinline__ void cfms(double& ar, double& ai, double br, double bi, double cr, double ci) {
+    ar = fma(-br, cr, ar);
+    ar = fma(bi, ci, ar);
+    ai = fma(-br, ci, ai);
+    ai = fma(-bi, cr, ai);
+}
+
+// 1/z.  Blocks here are O(1) in magnitude (energies and hoppings of order the band width), so the
+// plain conj(z)/|z|^2 form is safe from over/underflow.
+__device__ __forceinline__ cd crecip(cd z) {
+    double d = 1.0 / norm2(z);
+    return mk(z.x * d, -z.y * d);
+}
+
+// Complex division with Smith's algorithm — the form numpy and CPython use, so that the
+// closed-form lead GF follows the reference's rounding (exact for a real divisor).
+__device__ __forceinline__ cd cdiv(cd a, cd b) {
+    if (fabs(b.x) >= fabs(b.y)) {
+        if (b.x == 0.0 && b.y == 0.0) return mk(a.x / fabs(b.x), a.y / fabs(b.x));
+        double rat = b.y / b.x;
+        double scl = 1.0 / (b.x + b.y * rat);
+        return mk((a.x + a.y * rat) * scl, (a.y - a.x * rat) * scl);
+    } else {
+        double rat = b.x / b.y;
+        double scl = 1.0 / (b.x * rat + b.y);
+        return mk((a.x * rat + a.y) * scl, (a.y * rat - a.x) * scl);
+    }
+}
+
+// Principal complex square root (C99 csqrt without the over/underflow rescaling).
+__device__ __forceinline__ cd csqrt_principal(cd z) {
+    if (z.x == 0.0 && z.y == 0.0) return mk(0.0, z.y);
+    double m = hypot(z.x, z.y);
+    if (z.x >= 0.0) {
+        double t = sqrt((z.x + m) * 0.5);
+        return mk(t, z.y / (2.0 * t));
+    }
+    double t = sqrt((-z.x + m) * 0.5);
+    return mk(fabs(z.y) / (2.0 * t), copysign(t, z.y));
+}
+
+// numpy >= 2 sign of a complex number: z/|z| (0 for 0); equals the real sign for Im z = 0,
+// which is how every reference driver calls g_closed (SURVEY.md §7 hard part 2).
+__device__ __forceinline__ cd csign(cd z) {
+    if (z.y == 0.0) return mk((z.x > 0.0) - (z.x < 0.0), 0.0);
+    double m = hypot(z.x, z.y);
+    return mk(z.x / m, z.y / m);
+}
+
+// wfm.g_closed for one channel (wfm/__init__.py:337-340):
+//   lam = (E - eps)/(2 t); g = Re(lam/t) - sign(E-eps) |Re sqrt(lam^2-1)| - i |Im sqrt(lam^2-1)|
+__device__ __forceinline__ cd g_closed_channel(cd E, cd eps, cd t) {
+    cd d = E - eps;
+    cd lam = cdiv(d, mk(2.0 * t.x, 2.0 * t.y));
+    cd first = cdiv(lam, t);
+    cd sq = lam * lam;
+    sq.x -= 1.0;
+    // numpy's complex product is (ac-bd, ad+bc) without fma; lam*lam above contracts to fma.
+    // The difference is below 1 ulp of the product and far inside the 1e-10 parity gate.
+    cd root = csqrt_principal(sq);
+    cd sg = csign(d);
+    double ar = fabs(root.x), ai = fabs(root.y);
+    return mk(first.x - sg.x * ar, -sg.y * ar - ai);
+}
+
+}  // namespace tx

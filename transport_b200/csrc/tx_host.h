@@ -1,0 +1,16 @@
+// Host-side helpers shared by the translation units of libtransport_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tx {
+// Records a printf-style message for tx_last_error() (thread local) and returns `code`.
+int fail(int code, const char* fmt, ...);
+}  // namespace tx
+
+#define TX_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::tx::fail(TX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                                 \
+    } while (0)
