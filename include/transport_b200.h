@@ -153,6 +153,10 @@ int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, in
  * All variants compute the same thing; used by bench.py --variant to compare them. */
 int tx_set_variant(int variant);
 
+/* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device
+ * routine of the sweep (in-place Gauss-Jordan with implicit partial pivoting). Host pointers. */
+int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /*
  * Measures the FP64 FMA-pipe peak of the current device with a register-resident DFMA loop

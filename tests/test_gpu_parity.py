@@ -179,6 +179,21 @@ def test_green_hmat_hprime_psi_golden():
 
 
 # ------------------------------------------------------------------------------- seeded vs oracle
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 13, 16])
+def test_device_block_inverse(n):
+    """The sweep's in-register Gauss-Jordan (implicit partial pivoting) against numpy's LU inverse."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((101, n, n)) + 1j * rng.standard_normal((101, n, n))
+    A[7] = np.eye(n)[::-1]                        # permutation matrix: every pivot is off-diagonal
+    A[8] = np.diag(10.0 ** np.linspace(-6, 6, n)) @ A[8]
+    out = np.empty_like(A)
+    _lib.check(_lib.load().tx_debug_invert(_lib.ptr(A), _lib.ptr(out), len(A), n))
+    want = np.linalg.inv(A)
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(out - want) / scale) < 1e-10 * max(1.0, np.linalg.cond(A).max() * 1e-4)
+    assert np.abs(out[7] - A[7].T).max() == 0.0
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 11, 16])
 @pytest.mark.parametrize("general", [False, True])
 def test_seeded_random_against_dense_oracle(n, general):

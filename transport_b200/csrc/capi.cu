@@ -127,6 +127,46 @@ int tx_set_variant(int v) {
     return TX_OK;
 }
 
+// Unit-test hook: batched inverse of n x n blocks with the sweep's own device routine (host pointers).
+int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n) {
+    if (!in || !out || count < 1 || n < 1 || n > 16) return fail(TX_ERR_ARG, "bad arguments");
+    if (tx_device_count() < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    const size_t bytes = (size_t)count * n * n * sizeof(cd);
+    cd *din = nullptr, *dout = nullptr;
+    int* dflag = nullptr;
+    TX_CUDA(cudaMalloc(&din, bytes));
+    TX_CUDA(cudaMalloc(&dout, bytes));
+    TX_CUDA(cudaMalloc(&dflag, sizeof(int)));
+    TX_CUDA(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemset(dflag, 0, sizeof(int)));
+    const int N = round_up_block(n);
+    auto go = [&](auto kern, int NN, int LP) -> int {
+        const int GPW = 32 / LP;
+        const size_t smem = (size_t)4 * (2 * NN + NN * NN) * GPW * 16;
+        TX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long per_block = 4LL * GPW;
+        kern<<<(unsigned)((count + per_block - 1) / per_block), 128, smem>>>(din, dout, count, n, dflag);
+        TX_CUDA(cudaGetLastError());
+        return TX_OK;
+    };
+    int rc = TX_OK;
+    switch (N) {
+        case 1: rc = go(invert_batch_small<1, 1>, 1, 1); break;
+        case 2: rc = go(invert_batch_small<2, 1>, 2, 1); break;
+        case 4: rc = go(invert_batch_small<4, 2>, 4, 2); break;
+        case 8: rc = go(g_variant >= 2 ? invert_batch_small<8, 8> : invert_batch_small<8, 4>, 8, g_variant >= 2 ? 8 : 4); break;
+        case 16: rc = go(invert_batch_small<16, 16>, 16, 16); break;
+    }
+    if (rc == TX_OK) {
+        TX_CUDA(cudaDeviceSynchronize());
+        TX_CUDA(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(din);
+    cudaFree(dout);
+    cudaFree(dflag);
+    return rc;
+}
+
 int tx_sweep_launch_count(int n, int M, int hop_mode) {
     (void)M;
     (void)hop_mode;

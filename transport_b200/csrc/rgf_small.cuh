@@ -58,25 +58,41 @@ struct SmallCfg {
     static constexpr int PER_WARP_BYTES = PER_GROUP * GPW * 16;
 };
 
+// acc += a*b on interleaved (re, im) pairs (4 DFMA)
+__device__ __forceinline__ void cfma2(double2& acc, const double2 a, const double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a*b
+__device__ __forceinline__ void cfms2(double2& acc, const double2 a, const double2 b) {
+    acc.x = fma(-a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y);
+    acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 cmul2(const double2 a, const double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+
 // O = L * B,  L: own rows in registers, B: N x N in shared memory ([k*N+c][group]).
+// Blocks are kept as interleaved (re, im) double2 so that a 16-byte shared-memory access maps
+// onto an aligned register quad without repacking moves.
 template <int N, int RP, int GPW>
-__device__ __forceinline__ void rows_times_smem(const double (&Lr)[RP][N], const double (&Li)[RP][N],
-                                                const double2* __restrict__ B, int grp,
-                                                double (&Or)[RP][N], double (&Oi)[RP][N]) {
+__device__ __forceinline__ void rows_times_smem(const double2 (&L)[RP][N], const double2* B, int grp,
+                                                double2 (&O)[RP][N]) {
 #pragma unroll
     for (int s = 0; s < RP; ++s)
 #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            Or[s][c] = 0.0;
-            Oi[s][c] = 0.0;
-        }
+        for (int c = 0; c < N; ++c) O[s][c] = make_double2(0.0, 0.0);
 #pragma unroll
     for (int k = 0; k < N; ++k)
 #pragma unroll
         for (int c = 0; c < N; ++c) {
             const double2 b = B[(k * N + c) * GPW + grp];
 #pragma unroll
-            for (int s = 0; s < RP; ++s) cfma(Or[s][c], Oi[s][c], Lr[s][k], Li[s][k], b.x, b.y);
+            for (int s = 0; s < RP; ++s) cfma2(O[s][c], L[s][k], b);
         }
 }
 
@@ -86,20 +102,18 @@ __device__ __forceinline__ void rows_times_smem(const double (&Lr)[RP][N], const
 // (one scaling per row at the end).  The result is scattered into shared memory in canonical
 // order:  inv[k][p_j] = A[p_k][j] / d_k.
 template <int N, int LP>
-__device__ __forceinline__ void invert_to_smem(double (&Ar)[N / LP][N], double (&Ai)[N / LP][N],
-                                               double2* __restrict__ piv, double2* __restrict__ gm,
-                                               int grp, int row0, int* singular) {
+__device__ __forceinline__ void invert_to_smem(double2 (&A)[N / LP][N], double2* piv,
+                                               double2* gm, int grp, int row0, int* singular) {
     constexpr int RP = N / LP;
     constexpr int GPW = 32 / LP;
     unsigned long long perm = 0ull;   // nibble k = pivot row of step k
     unsigned used = 0u;               // bit s: local row s already used as a pivot row
     int krow[RP];                     // step at which local row s was the pivot row
-    double dir[RP], dii[RP];          // reciprocal of its pivot
+    double2 dinv[RP];                 // reciprocal of its pivot
 #pragma unroll
     for (int s = 0; s < RP; ++s) {
         krow[s] = 0;
-        dir[s] = 0.0;
-        dii[s] = 0.0;
+        dinv[s] = make_double2(0.0, 0.0);
     }
 
 #pragma unroll
@@ -108,7 +122,7 @@ __device__ __forceinline__ void invert_to_smem(double (&Ar)[N / LP][N], double (
         unsigned long long key = 0ull;
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
-            const double mag = fma(Ar[s][k], Ar[s][k], Ai[s][k] * Ai[s][k]);
+            const double mag = fma(A[s][k].x, A[s][k].x, A[s][k].y * A[s][k].y);
             unsigned long long kk = ((unsigned long long)__double_as_longlong(mag) & ~0x1Full) |
                                     (unsigned long long)(0x10 | (15 - (row0 + s)));
             if ((used >> s) & 1u) kk = 0ull;
@@ -129,35 +143,30 @@ __device__ __forceinline__ void invert_to_smem(double (&Ar)[N / LP][N], double (
         for (int s = 0; s < RP; ++s)
             if (row0 + s == prow) {
 #pragma unroll
-                for (int c = 0; c < N; ++c) pb[c * GPW + grp] = make_double2(Ar[s][c], Ai[s][c]);
+                for (int c = 0; c < N; ++c) pb[c * GPW + grp] = A[s][c];
             }
         __syncwarp();
-        double pr[N], pi[N];
+        double2 pr[N];
 #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            const double2 v = pb[c * GPW + grp];
-            pr[c] = v.x;
-            pi[c] = v.y;
-        }
-        const cd inv = crecip(mk(pr[k], pi[k]));
+        for (int c = 0; c < N; ++c) pr[c] = pb[c * GPW + grp];
+        const cd invc = crecip(mk(pr[k].x, pr[k].y));
+        const double2 inv = make_double2(invc.x, invc.y);
 
         // ---- eliminate column k from every other row; column k then holds the inverse's column
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
             const bool isp = (row0 + s == prow);
-            cd m = mk(Ar[s][k], Ai[s][k]) * inv;
+            double2 m = cmul2(A[s][k], inv);
             if (isp) {
-                m = mk(0.0, 0.0);
+                m = make_double2(0.0, 0.0);
                 used |= 1u << s;
                 krow[s] = k;
-                dir[s] = inv.x;
-                dii[s] = inv.y;
+                dinv[s] = inv;
             }
 #pragma unroll
             for (int c = 0; c < N; ++c)
-                if (c != k) cfms(Ar[s][c], Ai[s][c], m.x, m.y, pr[c], pi[c]);
-            Ar[s][k] = isp ? 1.0 : -m.x;
-            Ai[s][k] = isp ? 0.0 : -m.y;
+                if (c != k) cfms2(A[s][c], m, pr[c]);
+            A[s][k] = isp ? make_double2(1.0, 0.0) : make_double2(-m.x, -m.y);
         }
     }
 
@@ -167,8 +176,7 @@ __device__ __forceinline__ void invert_to_smem(double (&Ar)[N / LP][N], double (
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const int col = (int)((perm >> (4 * j)) & 0xFull);
-            const cd v = mk(Ar[s][j], Ai[s][j]) * mk(dir[s], dii[s]);
-            gm[(krow[s] * N + col) * GPW + grp] = make_double2(v.x, v.y);
+            gm[(krow[s] * N + col) * GPW + grp] = cmul2(A[s][j], dinv[s]);
         }
     }
     __syncwarp();
@@ -204,28 +212,27 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
     const int e = (int)(pt - (long long)ham * p.nE);
     const cd E = p.E[e];
     const long long nn = (long long)n * n;
-    const cd* hbase = p.h + ham * p.h_stride;
-    const cd* tbase = p.tnn + ham * p.t_stride;
+    const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
+    const double2* h1base = reinterpret_cast<const double2*>(p.h1);
+    const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
     const double par = p.h1 ? p.params[ham] : 0.0;
 
-    auto h_at = [&](int j, int r, int c) -> cd {
-        cd v = hbase[(long long)j * nn + r * n + c];
-        if (p.h1) {
-            const cd w = p.h1[(long long)j * nn + r * n + c];
+    auto h_at = [&](int j, int r, int c) -> double2 {
+        double2 v = hbase[(long long)j * nn + r * n + c];
+        if (h1base) {
+            const double2 w = h1base[(long long)j * nn + r * n + c];
             v.x = fma(par, w.x, v.x);
             v.y = fma(par, w.y, v.y);
         }
         return v;
     };
-    auto t_at = [&](int j, int r, int c) -> cd { return tbase[(long long)j * nn + r * n + c]; };
+    auto t_at = [&](int j, int r, int c) -> double2 { return tbase[(long long)j * nn + r * n + c]; };
+    auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
 
     // ------------------------------------------------------------------ prologue: leads
-    cd sigLd[RP];   // diagonal Sigma_L of own rows (scalar-hopping closed leads)
+    double2 sigLd[RP], sigRd[RP];   // diagonal Sigma of own rows (scalar-hopping closed leads)
 #pragma unroll
-    for (int s = 0; s < RP; ++s) sigLd[s] = mk(0.0, 0.0);
-    cd sigRd[RP];
-#pragma unroll
-    for (int s = 0; s < RP; ++s) sigRd[s] = mk(0.0, 0.0);
+    for (int s = 0; s < RP; ++s) sigLd[s] = sigRd[s] = make_double2(0.0, 0.0);
 
     if (LEAD == LEAD_CLOSED) {
 #pragma unroll
@@ -233,12 +240,14 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
             const int r = row0 + s;
             cd gL = mk(0.0, 0.0), gR = mk(0.0, 0.0);
             if (full || r < n) {
-                const cd tL = t_at(0, r, r), tR = t_at(M - 2, r, r);
-                gL = g_closed_channel(E, h_at(0, r, r), tL);        // wfm/__init__.py:283,286
-                gR = g_closed_channel(E, h_at(M - 1, r, r), tR);    // wfm/__init__.py:284,287
+                const cd tL = tocd(t_at(0, r, r)), tR = tocd(t_at(M - 2, r, r));
+                gL = g_closed_channel(E, tocd(h_at(0, r, r)), tL);        // wfm/__init__.py:283,286
+                gR = g_closed_channel(E, tocd(h_at(M - 1, r, r)), tR);    // wfm/__init__.py:284,287
                 if (HOP == HOP_SCALAR) {
-                    sigLd[s] = conj(tL) * (gL * tL);                // :301 for diagonal blocks
-                    sigRd[s] = tR * (gR * conj(tR));                // :302
+                    const cd sl = conj(tL) * (gL * tL);                   // :301 for diagonal blocks
+                    const cd sr = tR * (gR * conj(tR));                   // :302
+                    sigLd[s] = make_double2(sl.x, sl.y);
+                    sigRd[s] = make_double2(sr.x, sr.y);
                 }
             }
             if (HOP == HOP_SCALAR) {
@@ -251,69 +260,56 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
         __syncwarp();
     }
 
-    double Ar[RP][N], Ai[RP][N];   // A_j rows, then scratch
-    double Wr[RP][N], Wi[RP][N];   // W_j rows
+    double2 A[RP][N];   // A_j rows, then scratch
+    double2 W[RP][N];   // W_j rows
 
-    // own rows of a self-energy (general-hopping closed leads or table mode); also publishes v
-    auto sigma_rows = [&](bool left, double (&Sr)[RP][N], double (&Si)[RP][N]) {
-        if (LEAD == LEAD_TABLE) {
-            const cd* sg = (left ? p.sigL : p.sigR) + ham * p.sig_stride + (long long)e * nn;
-#pragma unroll
-            for (int s = 0; s < RP; ++s) {
-                const int r = row0 + s;
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    cd v = mk(0.0, 0.0);
-                    if (full || (r < n && c < n)) v = sg[r * n + c];
-                    Sr[s][c] = v.x;
-                    Si[s][c] = v.y;
-                }
-            }
-        } else {
-            const int jt = left ? 0 : M - 2;
-#pragma unroll
-            for (int s = 0; s < RP; ++s) {
-                const int r = row0 + s;
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    double ar = 0.0, ai = 0.0;
-                    if (full || (r < n && c < n)) {
-                        for (int k = 0; k < n; ++k) {
-                            const double2 gk = gl[((left ? 0 : N) + k) * GPW + grp];
-                            cd a, b;
-                            if (left) {   // Sigma_L[r][c] = sum_k conj(t0[k][r]) g_L[k] t0[k][c]
-                                a = conj(t_at(jt, k, r));
-                                b = mk(gk.x, gk.y) * t_at(jt, k, c);
-                            } else {      // Sigma_R[r][c] = sum_k tN[r][k] g_R[k] conj(tN[c][k])
-                                a = t_at(jt, r, k);
-                                b = mk(gk.x, gk.y) * conj(t_at(jt, c, k));
-                            }
-                            cfma(ar, ai, a.x, a.y, b.x, b.y);
-                        }
-                    }
-                    Sr[s][c] = ar;
-                    Si[s][c] = ai;
-                }
-            }
-        }
-        // velocities from the diagonal (wfm/__init__.py:91)
+    // own rows of a self-energy (general-hopping closed leads or table mode) subtracted from A;
+    // also publishes the velocities v = -2 Im diag Sigma (wfm/__init__.py:91)
+    auto subtract_sigma_rows = [&](bool left) {
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
             const int r = row0 + s;
-            double d = 0.0;
+            double dimag = 0.0;
 #pragma unroll
-            for (int c = 0; c < N; ++c)
-                if (c == r) d = Si[s][c];
+            for (int c = 0; c < N; ++c) {
+                double2 sg = make_double2(0.0, 0.0);
+                if (full || (r < n && c < n)) {
+                    if (LEAD == LEAD_TABLE) {
+                        const double2* tab = reinterpret_cast<const double2*>(left ? p.sigL : p.sigR) +
+                                             ham * p.sig_stride + (long long)e * nn;
+                        sg = tab[r * n + c];
+                    } else {
+                        const int jt = left ? 0 : M - 2;
+                        for (int k = 0; k < n; ++k) {
+                            const double2 gk = gl[((left ? 0 : N) + k) * GPW + grp];
+                            double2 a, b;
+                            if (left) {   // Sigma_L[r][c] = sum_k conj(t0[k][r]) g_L[k] t0[k][c]
+                                const double2 t1 = t_at(jt, k, r);
+                                a = make_double2(t1.x, -t1.y);
+                                b = cmul2(gk, t_at(jt, k, c));
+                            } else {      // Sigma_R[r][c] = sum_k tN[r][k] g_R[k] conj(tN[c][k])
+                                const double2 t2 = t_at(jt, c, k);
+                                a = t_at(jt, r, k);
+                                b = cmul2(gk, make_double2(t2.x, -t2.y));
+                            }
+                            cfma2(sg, a, b);
+                        }
+                    }
+                }
+                A[s][c].x -= sg.x;
+                A[s][c].y -= sg.y;
+                if (c == r) dimag = sg.y;
+            }
             if (left)
-                vv[r * GPW + grp].x = -2.0 * d;
+                vv[r * GPW + grp].x = -2.0 * dimag;
             else
-                vv[r * GPW + grp].y = -2.0 * d;
+                vv[r * GPW + grp].y = -2.0 * dimag;
         }
     };
 
     // ------------------------------------------------------------------ sweep
     for (int j = M - 1; j >= 0; --j) {
-        cd tj = mk(0.0, 0.0);
+        double2 tj = make_double2(0.0, 0.0);
         if (j < M - 1 && HOP == HOP_SCALAR) tj = t_at(j, 0, 0);
 
         // A = E - h_j
@@ -322,17 +318,15 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
             const int r = row0 + s;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
-                cd v = mk(0.0, 0.0);
+                double2 v = make_double2(0.0, 0.0);
                 if (full || (r < n && c < n)) v = h_at(j, r, c);
-                Ar[s][c] = -v.x;
-                Ai[s][c] = -v.y;
+                A[s][c] = make_double2(-v.x, -v.y);
                 if (c == r) {
                     if (full || r < n) {
-                        Ar[s][c] += E.x;
-                        Ai[s][c] += E.y;
+                        A[s][c].x += E.x;
+                        A[s][c].y += E.y;
                     } else {
-                        Ar[s][c] = 1.0;   // padding channel: identity block
-                        Ai[s][c] = 0.0;
+                        A[s][c] = make_double2(1.0, 0.0);   // padding channel: identity block
                     }
                 }
             }
@@ -341,7 +335,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
         if (j < M - 1) {
             if (HOP == HOP_SCALAR) {
                 // A -= |t_j|^2 g_{j+1}   (own rows of g from shared memory)
-                const double kap = norm2(tj);
+                const double kap = fma(tj.x, tj.x, tj.y * tj.y);
 #pragma unroll
                 for (int s = 0; s < RP; ++s) {
                     const int r = row0 + s;
@@ -349,45 +343,40 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
                             const double2 g = gm[(r * N + c) * GPW + grp];
-                            Ar[s][c] = fma(-kap, g.x, Ar[s][c]);
-                            Ai[s][c] = fma(-kap, g.y, Ai[s][c]);
+                            A[s][c].x = fma(-kap, g.x, A[s][c].x);
+                            A[s][c].y = fma(-kap, g.y, A[s][c].y);
                         }
                     }
                 }
             } else {
                 // general hopping: X = t_j g_{j+1},  A -= X t_j^dag,  W <- W t_j^dag
-                double Tr[RP][N], Ti[RP][N];
+                double2 Tm[RP][N], X[RP][N];
 #pragma unroll
                 for (int s = 0; s < RP; ++s) {
                     const int r = row0 + s;
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
-                        cd v = mk(0.0, 0.0);
+                        double2 v = make_double2(0.0, 0.0);
                         if (full || (r < n && c < n)) v = t_at(j, r, c);
-                        Tr[s][c] = v.x;
-                        Ti[s][c] = v.y;
+                        Tm[s][c] = v;
                         tm[(c * N + r) * GPW + grp] = make_double2(v.x, -v.y);   // (t^dag)[c][r]
                     }
                 }
                 __syncwarp();
-                double Xr[RP][N], Xi[RP][N];
-                rows_times_smem<N, RP, GPW>(Tr, Ti, gm, grp, Xr, Xi);      // X = t g
-                rows_times_smem<N, RP, GPW>(Xr, Xi, tm, grp, Tr, Ti);      // (reuse T) = X t^dag
+                rows_times_smem<N, RP, GPW>(Tm, gm, grp, X);      // X = t g
+                rows_times_smem<N, RP, GPW>(X, tm, grp, Tm);      // (reuse) = X t^dag
 #pragma unroll
                 for (int s = 0; s < RP; ++s)
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
-                        Ar[s][c] -= Tr[s][c];
-                        Ai[s][c] -= Ti[s][c];
+                        A[s][c].x -= Tm[s][c].x;
+                        A[s][c].y -= Tm[s][c].y;
                     }
-                rows_times_smem<N, RP, GPW>(Wr, Wi, tm, grp, Xr, Xi);      // W t^dag
+                rows_times_smem<N, RP, GPW>(W, tm, grp, X);       // W t^dag
 #pragma unroll
                 for (int s = 0; s < RP; ++s)
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        Wr[s][c] = Xr[s][c];
-                        Wi[s][c] = Xi[s][c];
-                    }
+                    for (int c = 0; c < N; ++c) W[s][c] = X[s][c];
             }
         }
 
@@ -397,32 +386,22 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
 #pragma unroll
                 for (int s = 0; s < RP; ++s) {
                     const int r = row0 + s;
-                    cd sg = mk(0.0, 0.0);
-                    if (j == M - 1) sg = sg + sigRd[s];
-                    if (j == 0) sg = sg + sigLd[s];
+                    const double2 sg = (j == 0) ? sigLd[s] : sigRd[s];   // M >= 2: distinct iterations
 #pragma unroll
                     for (int c = 0; c < N; ++c)
                         if (c == r) {
-                            Ar[s][c] -= sg.x;
-                            Ai[s][c] -= sg.y;
+                            A[s][c].x -= sg.x;
+                            A[s][c].y -= sg.y;
                         }
                 }
             } else {
-                double Sr[RP][N], Si[RP][N];
-                sigma_rows(j == 0, Sr, Si);   // M >= 2: the two end blocks are distinct iterations
-#pragma unroll
-                for (int s = 0; s < RP; ++s)
-#pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        Ar[s][c] -= Sr[s][c];
-                        Ai[s][c] -= Si[s][c];
-                    }
+                subtract_sigma_rows(j == 0);
             }
         }
 
         // every lane has finished reading g_{j+1} from gm before it is overwritten
         __syncwarp();
-        invert_to_smem<N, LP>(Ar, Ai, piv, gm, grp, row0, p.singular);
+        invert_to_smem<N, LP>(A, piv, gm, grp, row0, p.singular);
 
         if (j == M - 1) {
             // W_{M-1} = g_{M-1}; padding rows start (and stay) at zero
@@ -433,30 +412,22 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
                 for (int c = 0; c < N; ++c) {
                     double2 g = gm[(r * N + c) * GPW + grp];
                     if (!(full || r < n)) g = make_double2(0.0, 0.0);
-                    Wr[s][c] = g.x;
-                    Wi[s][c] = g.y;
+                    W[s][c] = g;
                 }
             }
         } else {
-            rows_times_smem<N, RP, GPW>(Wr, Wi, gm, grp, Ar, Ai);   // (W t^dag) g_j
+            rows_times_smem<N, RP, GPW>(W, gm, grp, A);   // (W t^dag) g_j
             if (HOP == HOP_SCALAR) {
-                const cd tc = conj(tj);
+                const double2 tc = make_double2(tj.x, -tj.y);
 #pragma unroll
                 for (int s = 0; s < RP; ++s)
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        const cd v = mk(Ar[s][c], Ai[s][c]) * tc;
-                        Wr[s][c] = v.x;
-                        Wi[s][c] = v.y;
-                    }
+                    for (int c = 0; c < N; ++c) W[s][c] = cmul2(A[s][c], tc);
             } else {
 #pragma unroll
                 for (int s = 0; s < RP; ++s)
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        Wr[s][c] = Ar[s][c];
-                        Wi[s][c] = Ai[s][c];
-                    }
+                    for (int c = 0; c < N; ++c) W[s][c] = A[s][c];
             }
         }
     }
@@ -468,11 +439,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
     for (int s = 0; s < RP; ++s) {
         const int r = row0 + s;
 #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            const double2 g = gm[(r * N + c) * GPW + grp];
-            Ar[s][c] = g.x;
-            Ai[s][c] = g.y;
-        }
+        for (int c = 0; c < N; ++c) A[s][c] = gm[(r * N + c) * GPW + grp];
     }
     double vL[N], vR[N];
 #pragma unroll
@@ -522,26 +489,24 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
     };
 
     if (p.sources == nullptr) {
-        // all n one-hot sources: alpha = i (static column index)
+        // all n one-hot sources: alpha = i (static column index).  With A = e_alpha:
+        //   i_flux = sqrt(vL[alpha])                                   (:108)
+        //   r = (i G00[s][alpha] vL[alpha] - delta) sqrt(vL[s]) / i_flux  (:116-117)
+        //   t =  i G_{M-1,0}[s][alpha] vL[alpha]  sqrt(vR[s]) / i_flux    (:124-125)
 #pragma unroll
         for (int a = 0; a < N; ++a) {
             if (full || a < n) {
-                const double iflux = sqrt(vL[a]);                 // :108
+                const double rflux = 1.0 / sqrt(vL[a]);
                 double rr[RP], tt[RP];
 #pragma unroll
                 for (int s = 0; s < RP; ++s) {
                     const int r = row0 + s;
-                    // i * G00[r][a] * vL[a] - delta_ra      (:116)
-                    double xr = -Ai[s][a] * vL[a] - (r == a ? 1.0 : 0.0);
-                    double xi = Ar[s][a] * vL[a];
-                    xr = xr * sqL[s] / iflux;
-                    xi = xi * sqL[s] / iflux;
+                    const double fr = sqL[s] * rflux, ft = sqR[s] * rflux;
+                    const double xr = (-A[s][a].y * vL[a] - (r == a ? 1.0 : 0.0)) * fr;
+                    const double xi = (A[s][a].x * vL[a]) * fr;
                     rr[s] = fma(xr, xr, xi * xi);
-                    // i * G_{M-1,0}[r][a] * vL[a]           (:124)
-                    double yr = -Wi[s][a] * vL[a];
-                    double yi = Wr[s][a] * vL[a];
-                    yr = yr * sqR[s] / iflux;
-                    yi = yi * sqR[s] / iflux;
+                    const double yr = (-W[s][a].y * vL[a]) * ft;
+                    const double yi = (W[s][a].x * vL[a]) * ft;
                     tt[s] = fma(yr, yr, yi * yi);
                 }
                 emit(a, rr, tt);
@@ -562,23 +527,24 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
                     f2 = fma(a, av, f2);                          // :108
 #pragma unroll
                     for (int s = 0; s < RP; ++s) {
-                        ur[s] = fma(Ar[s][c], av, ur[s]);
-                        ui[s] = fma(Ai[s][c], av, ui[s]);
-                        wr[s] = fma(Wr[s][c], av, wr[s]);
-                        wi[s] = fma(Wi[s][c], av, wi[s]);
+                        ur[s] = fma(A[s][c].x, av, ur[s]);
+                        ui[s] = fma(A[s][c].y, av, ui[s]);
+                        wr[s] = fma(W[s][c].x, av, wr[s]);
+                        wi[s] = fma(W[s][c].y, av, wi[s]);
                         if (c == row0 + s) mine[s] = a;
                     }
                 }
             }
-            const double iflux = sqrt(f2);
+            const double rflux = 1.0 / sqrt(f2);
             double rr[RP], tt[RP];
 #pragma unroll
             for (int s = 0; s < RP; ++s) {
-                double xr = (-ui[s] - mine[s]) * sqL[s] / iflux;
-                double xi = ur[s] * sqL[s] / iflux;
+                const double fr = sqL[s] * rflux, ft = sqR[s] * rflux;
+                const double xr = (-ui[s] - mine[s]) * fr;
+                const double xi = ur[s] * fr;
                 rr[s] = fma(xr, xr, xi * xi);
-                double yr = -wi[s] * sqR[s] / iflux;
-                double yi = wr[s] * sqR[s] / iflux;
+                const double yr = -wi[s] * ft;
+                const double yi = wr[s] * ft;
                 tt[s] = fma(yr, yr, yi * yi);
             }
             emit(i, rr, tt);
@@ -589,6 +555,39 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
         for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
         if (active && li == 0) p.ttot[pt] = tsum;
     }
+}
+
+// Debug / unit-test kernel: inverts a batch of n x n blocks with the same device routine.
+template <int N, int LP>
+__global__ void __launch_bounds__(128) invert_batch_small(const cd* in, cd* out, long long count, int n, int* singular) {
+    constexpr int RP = N / LP;
+    constexpr int GPW = 32 / LP;
+    extern __shared__ double2 smem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / LP, li = lane % LP, row0 = li * RP;
+    double2* piv = smem_all + (size_t)warp * ((2 * N + N * N) * GPW);
+    double2* gm = piv + 2 * N * GPW;
+    long long b = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * GPW + grp;
+    const bool active = b < count;
+    if (!active) b = count - 1;
+    const double2* src = reinterpret_cast<const double2*>(in) + b * n * n;
+    double2 A[RP][N];
+#pragma unroll
+    for (int s = 0; s < RP; ++s)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            const int r = row0 + s;
+            A[s][c] = (r < n && c < n) ? src[r * n + c] : make_double2(r == c ? 1.0 : 0.0, 0.0);
+        }
+    invert_to_smem<N, LP>(A, piv, gm, grp, row0, singular);
+    double2* dst = reinterpret_cast<double2*>(out) + b * n * n;
+#pragma unroll
+    for (int s = 0; s < RP; ++s)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            const int r = row0 + s;
+            if (active && r < n && c < n) dst[r * n + c] = gm[(r * N + c) * GPW + grp];
+        }
 }
 
 }  // namespace tx

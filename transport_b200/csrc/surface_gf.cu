@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
                 else m0[s * n + s] = gs;                               // <A|g|A>  (:411-413)
             }
         }
+        if (threadIdx.x == 0) {
+            if (p.n_iter) p.n_iter[e] = 0;
+            if (p.conv) p.conv[e] = 0.0;
+            if (p.converged) p.converged[e] = 1;
+        }
         __syncthreads();
     } else if (p.mode == TX_GF_FIXEDPOINT) {
         // g_iter (:504-530) / g_ith (:541-551)
