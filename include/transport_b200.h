@@ -88,6 +88,13 @@ int tx_device_synchronize(void);
  *  t_total  [n_ham][nE] doubles or NULL: transmission summed over all evaluated sources and
  *           channels; with all n one-hot sources this is Tr[Gamma_R G Gamma_L G^dag] — the compact
  *           array the multi-GPU path gathers
+ *  caroli   (host entry only) [n_ham][nE] doubles or NULL: Tr[Gamma_R G Gamma_L G^dag] with the full
+ *           matrices Gamma = i(Sigma - Sigma^dag) — the total transmission when the self-energies
+ *           are not diagonal (multi-channel ribbon leads)
+ *
+ * Block sizes n <= 16 run the register-resident kernel; 16 < n <= 64 (or any n when `caroli` is
+ * requested) run the CTA-per-point kernel tx_transmission_sweep_large_dev, which takes table
+ * self-energies only (the host entry builds the tables with tx_surface_gf_dev for closed-form leads).
  *
  * tx_transmission_sweep takes HOST pointers and performs the host<->device copies itself;
  * tx_transmission_sweep_dev takes DEVICE pointers and a cudaStream_t (as void*), launches
@@ -99,7 +106,7 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
                           int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
                           int hop_mode,
                           const double* sources, const int* src_idx, int n_src,
-                          double* R, double* T, double* resid, double* t_total);
+                          double* R, double* T, double* resid, double* t_total, double* caroli);
 
 int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
                               const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
@@ -109,6 +116,17 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
                               const double* sources, const int* src_idx, int n_src,
                               double* R, double* T, double* resid, double* t_total,
                               int* singular_flag, void* stream);
+
+int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                                    const tx_cplx* E, int nE,
+                                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                                    const double* sources, int n_src,
+                                    double* R, double* T, double* resid, double* t_total, double* caroli,
+                                    tx_cplx* workspace, int* singular_flag, void* stream);
+/* Elements (tx_cplx) of `workspace` the large-block sweep needs for n_pts points (0 if it fits in
+ * shared memory). */
+long long tx_sweep_workspace_elems(int n, long long n_pts);
 
 /* Number of kernel launches tx_transmission_sweep_dev issues for this shape (for accounting). */
 int tx_sweep_launch_count(int n, int M, int hop_mode);
@@ -147,6 +165,13 @@ int tx_green_full(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_c
                   const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G);
 /* Dense block-pentadiagonal H [(M n)][(M n)]  (wfm.Hmat, :168-215). Host pointers. */
 int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, int M, tx_cplx* H);
+
+/* bardeen.Hsysmat (transport/bardeen/__init__.py:690-750): 4-D Hamiltonian [S][S][n][n],
+ * S = 2*Ninf + NL + NR + NC, regions inf|L|C|R|inf with block potentials V* and hoppings t* ([n][n]
+ * each), HC [NC][NC][n][n] pasted in the centre (NC odd).  Host pointers. */
+int tx_hsysmat(const tx_cplx* tinf, const tx_cplx* tL, const tx_cplx* tR, const tx_cplx* VinfL, const tx_cplx* VinfR,
+               const tx_cplx* VL, const tx_cplx* VR, int Ninf, int NL, int NR, const tx_cplx* HC, int NC, int n,
+               tx_cplx* H);
 
 /* Tuning knob for the n<=8, scalar-hopping, closed-lead kernel: 0 = 4 lanes/point capped at 168
  * registers (default), 1 = 4 lanes/point uncapped, 2/3 = 8 lanes/point at 168/128 registers.

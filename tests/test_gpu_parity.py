@@ -297,3 +297,97 @@ def test_green_column_and_full_against_oracle():
         full = green.green_full(h, tnn, Es, SL, SR)
         want = np.array([wfm_oracle.Green(h, tnn, np.zeros((M - 2, n, n), complex), 1.0, E, "g_closed") for E in Es])
         assert np.allclose(full, want, rtol=1e-10, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------- bardeen adaptor, large blocks
+def test_hsysmat_golden():
+    from transport_b200 import bardeen
+    g = load_golden("hsysmat.npz")
+    H = bardeen.Hsysmat(g["tinf"], g["tL"], g["tR"], g["Vinf"], g["VL"], g["VR"], int(g["Ninf"]), int(g["NL"]),
+                        int(g["NR"]), g["HC"])
+    assert H.shape == g["H"].shape and np.array_equal(H, g["H"])
+    H2 = bardeen.Hsysmat(g["tinf"], g["tL"], g["tR"], g["Vinf"], g["VL"], g["VR"], 2, 3, 4, g["HC"], bound=False)
+    assert np.array_equal(np.diagonal(H2[0, 0]), np.diagonal(g["VL"]))
+    with pytest.raises(ValueError):
+        bardeen.Hsysmat(g["tinf"], g["tL"], g["tR"], g["Vinf"], g["VL"], g["VR"], 2, 3, 4, g["HC"][:2, :2])
+    with pytest.raises(TypeError):
+        bardeen.Hsysmat(g["tinf"], g["tL"], g["tR"], g["Vinf"], g["VL"], g["VR"], 2.0, 3, 4, g["HC"])
+
+
+@pytest.mark.parametrize("with_nnn", [False, True])
+def test_ts_wfm_well_against_dense_oracle(with_nnn):
+    """rb* scripts' entry into T(E) (bardeen/__init__.py:634-685), incl. next-nearest-neighbour blocks."""
+    from transport_b200 import bardeen
+    rng = np.random.default_rng(11)
+    n, NC = 2, 5
+    HC = np.zeros((NC, NC, n, n), dtype=complex)
+    for j in range(NC):
+        HC[j, j] = 0.3 * np.eye(n) + 0.05 * np.array([[0, 1], [1, 0]])
+    for j in range(NC - 1):
+        HC[j, j + 1] = -1.0 * np.eye(n)
+        HC[j + 1, j] = -1.0 * np.eye(n)
+    if with_nnn:
+        for j in range(NC - 2):
+            blk = 0.08 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+            HC[j, j + 2] = blk
+            HC[j + 2, j] = np.conj(blk).T
+    tL = tR = 1.0 * np.eye(n)
+    VL = VR = 0.0 * np.eye(n)
+    Emas = np.array([[-1.7, -1.1, -0.2], [-1.6, -0.9, 0.4]])
+    Tb = bardeen.Ts_wfm_well(tL, tR, VL, VR, HC, Emas)
+    assert Tb.shape == (n, 3, n)
+    h, tnn, tnnn = bardeen.blocks_from_HC(1.0, 1.0, 0.0, 0.0, HC)
+    for a in range(n):
+        for m in range(3):
+            _, oT = wfm_oracle.kernel(h, tnn, tnnn, 1.0, complex(Emas[a, m]), "g_closed", np.eye(n)[a], False, False,
+                                      all_debug=False)
+            assert rt_err(Tb[:, m, a], oT) < RTOL
+    with pytest.raises(NotImplementedError):
+        bardeen.Ts_wfm_well(tL, 0.9 * tR, VL, VR, HC, Emas)
+
+
+@pytest.mark.parametrize("n,scalar", [(20, True), (24, False), (33, True), (64, True)])
+def test_large_block_sweep_and_caroli(n, scalar):
+    """16 < n <= 64 goes through the CTA-per-point kernel; parity vs the recursive numpy oracle."""
+    rng = np.random.default_rng(n)
+    M = 5
+    A = rng.standard_normal((M, n, n)) + 1j * rng.standard_normal((M, n, n))
+    h = 0.2 * (A + np.conj(np.swapaxes(A, 1, 2))) / 2
+    h[0] = np.diag(np.zeros(n))
+    h[-1] = np.diag(0.02 * rng.standard_normal(n))
+    tnn = -np.tile(np.eye(n, dtype=complex), (M - 1, 1, 1))
+    if not scalar:
+        tnn[1:-1] += 0.1 * (rng.standard_normal((M - 3, n, n)) + 1j * rng.standard_normal((M - 3, n, n)))
+    Es = np.array([-1.4, 0.3, 1.2], dtype=complex)
+    srcs = np.eye(n)[[0, n // 2]]
+    R, T, res, tot, car = transmission_sweep(h, tnn, Es, sources=srcs, want_resid=True, want_total=True, want_caroli=True)
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, srcs)
+    _check(R[0], T[0], oR, oT, res)
+    SL, SR = rgf_oracle.closed_selfenergies(h, tnn, Es)
+    G00, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, SL, SR)
+    assert np.allclose(car[0], rgf_oracle.caroli_trace(GN0, SL, SR), rtol=1e-10)
+    assert np.allclose(tot[0], T[0].sum(axis=(1, 2)), rtol=1e-12)
+
+
+def test_ribbon_sancho_leads_cfg4_downscaled():
+    """cfg4 shape at reduced size: ribbon width 24, Sancho-Rubio lead tables -> sweep -> Caroli trace;
+    parity vs the numpy restatement of the same algorithm and, for the clean
+    ribbon, the exact channel count."""
+    n, L, eta = 24, 6, 1e-8
+    Es = np.array([-2.3, -0.7, 0.15, 1.9], dtype=complex)
+    for W in (0.0, 1.0):
+        h, tnn, _ = configs.ribbon_blocks(width=n, L=L, W=W, seed=3)
+        SL, SR = leads.self_energies_batched(h, tnn, Es, ("sancho", eta, 1e-14))
+        R, T, car = transmission_sweep(h, tnn, Es, "table", sigL=SL, sigR=SR, sources=np.eye(n)[:1], want_caroli=True)
+        gL, _ = rgf_oracle.sancho_rubio(h[0], tnn[0], Es + 1j * eta, -1)
+        gR, _ = rgf_oracle.sancho_rubio(h[-1], tnn[-1], Es + 1j * eta, 1)
+        oSL = np.conj(tnn[0]).T @ gL @ tnn[0]
+        oSR = tnn[-1] @ gR @ np.conj(tnn[-1]).T
+        assert np.allclose(SL, oSL, rtol=1e-9, atol=1e-12) and np.allclose(SR, oSR, rtol=1e-9, atol=1e-12)
+        _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, oSL, oSR)
+        want = rgf_oracle.caroli_trace(GN0, oSL, oSR)
+        assert np.allclose(car[0], want, rtol=1e-8, atol=1e-10)
+        if W == 0.0:
+            eps = np.linalg.eigvalsh(h[0].real)
+            open_ch = np.array([np.sum(np.abs(E.real - eps) < 2.0) for E in Es])
+            assert np.allclose(car[0], open_ch, atol=1e-4)      # clean ribbon: T = number of open channels

@@ -40,7 +40,10 @@ _SIGNATURES = {
     "tx_set_variant": (c_int, [c_int]),
     "tx_sweep_launch_count": (c_int, [c_int, c_int, c_int]),
     "tx_transmission_sweep": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
-                                      c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P]),
+                                      c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "tx_transmission_sweep_large_dev": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
+                                                _P, _P, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tx_sweep_workspace_elems": (ctypes.c_longlong, [c_int, ctypes.c_longlong]),
     "tx_transmission_sweep_dev": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
                                           c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "tx_surface_gf": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
@@ -51,6 +54,7 @@ _SIGNATURES = {
     "tx_green_column0": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "tx_green_full": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "tx_hmat": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "tx_hsysmat": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "tx_debug_invert": (c_int, [_P, _P, c_int, c_int]),
     "tx_measure_fp64_peak": (c_int, [_P, _P]),
     "tx_measure_dmma_peak": (c_int, [_P, _P]),

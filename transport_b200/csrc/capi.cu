@@ -7,6 +7,7 @@
 #include <mutex>
 #include <vector>
 
+#include "rgf_generic.h"
 #include "rgf_small.cuh"
 #include "tx_host.h"
 
@@ -42,7 +43,7 @@ struct DevBuf {
     }
 };
 struct Workspace {
-    DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, flag;
+    DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, caroli, big, flag;
     cudaStream_t stream = nullptr;
     int device = -1;
 };
@@ -243,13 +244,58 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     return fail(TX_ERR_UNSUPPORTED, "unreachable");
 }
 
+long long tx_sweep_workspace_elems(int n, long long n_pts) { return (long long)rgf_generic_workspace_elems(n, n_pts); }
+
+int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                                    const tx_cplx* E, int nE,
+                                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                                    const double* sources, int n_src,
+                                    double* R, double* T, double* resid, double* t_total, double* caroli,
+                                    tx_cplx* workspace, int* singular_flag, void* stream) {
+    if (!h || !tnn || !E || !sigL || !sigR || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..64", n);
+    if (M < 2 || n_ham < 1 || nE < 1 || n_src < 1) return fail(TX_ERR_ARG, "bad sizes");
+    if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham) || !(n_sig == 1 || n_sig == n_ham))
+        return fail(TX_ERR_ARG, "n_h/n_t/n_sig must be 1 or n_ham");
+    if ((R == nullptr) != (T == nullptr)) return fail(TX_ERR_ARG, "R and T must be given together");
+    if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
+    if (h1 && !params) return fail(TX_ERR_ARG, "h1 given without params");
+    GenericParams p{};
+    p.h = reinterpret_cast<const cd*>(h);
+    p.h_stride = (n_h == 1) ? 0 : (long long)M * n * n;
+    p.h1 = reinterpret_cast<const cd*>(h1);
+    p.params = params;
+    p.tnn = reinterpret_cast<const cd*>(tnn);
+    p.t_stride = (n_t == 1) ? 0 : (long long)(M - 1) * n * n;
+    p.E = reinterpret_cast<const cd*>(E);
+    p.sigL = reinterpret_cast<const cd*>(sigL);
+    p.sigR = reinterpret_cast<const cd*>(sigR);
+    p.sig_stride = (n_sig == 1) ? 0 : (long long)nE * n * n;
+    p.sources = sources;
+    p.R = R;
+    p.T = T;
+    p.resid = resid;
+    p.ttot = t_total;
+    p.caroli = caroli;
+    p.work = reinterpret_cast<cd*>(workspace);
+    p.singular = singular_flag;
+    p.n_pts = (long long)n_ham * nE;
+    p.n = n;
+    p.M = M;
+    p.nE = nE;
+    p.n_src = n_src;
+    p.hop_scalar = (hop_mode == TX_HOP_SCALAR) ? 1 : 0;
+    return launch_rgf_generic(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
                           const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
                           const tx_cplx* E, int nE,
                           int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
                           int hop_mode,
                           const double* sources, const int* src_idx, int n_src,
-                          double* R, double* T, double* resid, double* t_total) {
+                          double* R, double* T, double* resid, double* t_total, double* caroli) {
     if (!h || !tnn || !E || !R || !T) return fail(TX_ERR_ARG, "null pointer argument");
     if (n < 1 || M < 2 || n_ham < 1 || nE < 1 || n_src < 1)
         return fail(TX_ERR_ARG, "bad sizes n=%d M=%d n_ham=%d nE=%d n_src=%d", n, M, n_ham, nE, n_src);
@@ -331,14 +377,59 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     if (bytes_src) TX_CUDA(cudaMemcpyAsync(ws.src.ptr, sources, bytes_src, cudaMemcpyHostToDevice, st));
     TX_CUDA(cudaMemsetAsync(ws.flag.ptr, 0, sizeof(int), st));
 
-    rc = tx_transmission_sweep_dev(
-        (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
-        (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE, lead_mode,
-        bytes_sig ? (const tx_cplx*)ws.sigL.ptr : nullptr, bytes_sig ? (const tx_cplx*)ws.sigR.ptr : nullptr, n_sig,
-        hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src, (double*)ws.R.ptr,
-        (double*)ws.T.ptr, bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
-        (int*)ws.flag.ptr, st);
-    if (rc) return rc;
+    const bool large = (n > 16) || (caroli != nullptr);
+    if (!large) {
+        rc = tx_transmission_sweep_dev(
+            (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
+            (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE, lead_mode,
+            bytes_sig ? (const tx_cplx*)ws.sigL.ptr : nullptr, bytes_sig ? (const tx_cplx*)ws.sigR.ptr : nullptr, n_sig,
+            hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src, (double*)ws.R.ptr,
+            (double*)ws.T.ptr, bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
+            (int*)ws.flag.ptr, st);
+        if (rc) return rc;
+    } else {
+        // generic-size path (n <= 64): self-energy tables first (K1), then one CTA per point
+        int n_sig_use = n_sig;
+        if (lead_mode == TX_LEAD_CLOSED) {
+            // closed-form leads must be common to all Hamiltonians of the batch
+            const size_t lead_off_R = (size_t)(M - 1) * nn, hop_off_R = (size_t)(M - 2) * nn;
+            for (int q = 1; q < n_h; ++q)
+                if (memcmp(h + (size_t)q * M * nn, h, nn * sizeof(tx_cplx)) ||
+                    memcmp(h + (size_t)q * M * nn + lead_off_R, h + lead_off_R, nn * sizeof(tx_cplx)))
+                    return fail(TX_ERR_UNSUPPORTED, "large-block sweep with closed-form leads needs identical lead blocks; pass tables");
+            for (int q = 1; q < n_t; ++q)
+                if (memcmp(tnn + (size_t)q * (M - 1) * nn, tnn, nn * sizeof(tx_cplx)) ||
+                    memcmp(tnn + (size_t)q * (M - 1) * nn + hop_off_R, tnn + hop_off_R, nn * sizeof(tx_cplx)))
+                    return fail(TX_ERR_UNSUPPORTED, "large-block sweep with closed-form leads needs identical lead hoppings; pass tables");
+            if (h1)
+                for (size_t i = 0; i < nn; ++i)
+                    if (h1[i].re != 0 || h1[i].im != 0 || h1[lead_off_R + i].re != 0 || h1[lead_off_R + i].im != 0)
+                        return fail(TX_ERR_UNSUPPORTED, "affine term on the lead blocks is not supported by the large-block sweep");
+            const size_t bs = (size_t)nE * nn * sizeof(tx_cplx);
+            if ((rc = ws.sigL.ensure(bs)) || (rc = ws.sigR.ensure(bs))) return rc;
+            const tx_cplx* dh = (const tx_cplx*)ws.h.ptr;
+            const tx_cplx* dt = (const tx_cplx*)ws.tnn.ptr;
+            rc = tx_surface_gf_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, -1, TX_GF_CLOSED, 0.0, 0.0, 0, 0, 0, nullptr,
+                                   (tx_cplx*)ws.sigL.ptr, nullptr, nullptr, nullptr, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+            rc = tx_surface_gf_dev(dh + lead_off_R, dt + hop_off_R, n, (const tx_cplx*)ws.E.ptr, nE, 1, TX_GF_CLOSED, 0.0, 0.0,
+                                   0, 0, 0, nullptr, (tx_cplx*)ws.sigR.ptr, nullptr, nullptr, nullptr, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+            n_sig_use = 1;
+        }
+        const size_t wse = rgf_generic_workspace_elems(n, (long long)n_pts);
+        if (wse && (rc = ws.big.ensure(wse * sizeof(tx_cplx)))) return rc;
+        if (caroli && (rc = ws.caroli.ensure(n_pts * sizeof(double)))) return rc;
+        rc = tx_transmission_sweep_large_dev(
+            (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
+            (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE,
+            (const tx_cplx*)ws.sigL.ptr, (const tx_cplx*)ws.sigR.ptr, n_sig_use, hop_mode,
+            bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, (double*)ws.R.ptr, (double*)ws.T.ptr,
+            bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
+            caroli ? (double*)ws.caroli.ptr : nullptr, wse ? (tx_cplx*)ws.big.ptr : nullptr, (int*)ws.flag.ptr, st);
+        if (rc) return rc;
+        if (caroli) TX_CUDA(cudaMemcpyAsync(caroli, ws.caroli.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
 
     int flag = 0;
     TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));

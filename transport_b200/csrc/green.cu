@@ -152,6 +152,52 @@ __global__ void hmat_kernel(const cd* __restrict__ h, const cd* __restrict__ tnn
     H[idx] = v;
 }
 
+// bardeen.Hsysmat (transport/bardeen/__init__.py:690-750): regions  inf | L | C | R | inf.
+struct HsysParams {
+    const cd *tinf, *tL, *tR, *VinfL, *VinfR, *VL, *VR, *HC;
+    cd* H;
+    int Ninf, NL, NR, NC, n;
+};
+
+__global__ void hsysmat_kernel(const HsysParams p) {
+    const int n = p.n, lc = p.NC / 2;
+    const int minusinf = -lc - p.NL - p.Ninf;
+    const int S = 2 * p.Ninf + p.NL + p.NR + p.NC;
+    const long long total = (long long)S * S * n * n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int b = (int)(idx % n);
+    const int a = (int)((idx / n) % n);
+    const int k = (int)((idx / ((long long)n * n)) % S);
+    const int i = (int)(idx / ((long long)n * n * S));
+    const int ji = i + minusinf, jk = k + minusinf;
+    const int ab = a * n + b;
+    cd v = mk(0.0, 0.0);
+    auto hop_left_type = [&](int j, cd& acc) {      // site j in the far-left / left-well region (:724-729)
+        if (j < -p.NL - lc) acc = acc - p.tinf[ab];
+        else if (j < -lc) acc = acc - p.tL[ab];
+    };
+    auto hop_right_type = [&](int j, cd& acc) {     // site j in the right-well / far-right region (:730-735)
+        if (j > lc + p.NR) acc = acc - p.tinf[ab];
+        else if (j > lc) acc = acc - p.tR[ab];
+    };
+    if (ji >= -lc && ji <= lc && jk >= -lc && jk <= lc) {
+        v = p.HC[(((long long)(ji + lc) * p.NC + (jk + lc)) * n + a) * n + b];      // :748
+    } else if (i == k) {
+        if (ji < -p.NL - lc) v = p.VinfL[ab];                                       // :713-721
+        else if (ji < -lc) v = p.VL[ab];
+        else if (ji > lc + p.NR) v = p.VinfR[ab];
+        else if (ji > lc) v = p.VR[ab];
+    } else if (k == i + 1) {
+        hop_left_type(ji, v);
+        hop_right_type(jk, v);
+    } else if (k == i - 1) {
+        hop_left_type(jk, v);
+        hop_right_type(ji, v);
+    }
+    p.H[idx] = v;
+}
+
 struct DevMem {
     char* p = nullptr;
     ~DevMem() {
@@ -246,6 +292,38 @@ int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, in
     hmat_kernel<<<(unsigned)((total + 255) / 256), 256>>>(dh, dt, dtt, dH, n, M);
     TX_CUDA(cudaGetLastError());
     TX_CUDA(cudaMemcpy(H, dH, b_H, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+int tx_hsysmat(const tx_cplx* tinf, const tx_cplx* tL, const tx_cplx* tR, const tx_cplx* VinfL, const tx_cplx* VinfR,
+               const tx_cplx* VL, const tx_cplx* VR, int Ninf, int NL, int NR, const tx_cplx* HC, int NC, int n,
+               tx_cplx* H) {
+    if (!tinf || !tL || !tR || !VinfL || !VinfR || !VL || !VR || !HC || !H) return fail(TX_ERR_ARG, "null pointer argument");
+    if (Ninf <= 0 || NL <= 0 || NR <= 0 || NC < 1 || (NC % 2) != 1 || n < 1) return fail(TX_ERR_ARG, "bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t nn = (size_t)n * n, bc = sizeof(cd);
+    const size_t S = (size_t)2 * Ninf + NL + NR + NC;
+    const size_t b_small = nn * bc, b_HC = (size_t)NC * NC * nn * bc, b_H = S * S * nn * bc;
+    DevMem d;
+    TX_CUDA(cudaMalloc(&d.p, 7 * b_small + b_HC + b_H));
+    char* q = d.p;
+    const tx_cplx* srcs[7] = {tinf, tL, tR, VinfL, VinfR, VL, VR};
+    const cd* dp[7];
+    for (int i = 0; i < 7; ++i) {
+        TX_CUDA(cudaMemcpy(q, srcs[i], b_small, cudaMemcpyHostToDevice));
+        dp[i] = (const cd*)q;
+        q += b_small;
+    }
+    TX_CUDA(cudaMemcpy(q, HC, b_HC, cudaMemcpyHostToDevice));
+    HsysParams p{dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], (const cd*)q, (cd*)(q + b_HC), Ninf, NL, NR, NC, n};
+    const long long total = (long long)(S * S * nn);
+    hsysmat_kernel<<<(unsigned)((total + 255) / 256), 256>>>(p);
+    TX_CUDA(cudaGetLastError());
+    TX_CUDA(cudaMemcpy(H, p.H, b_H, cudaMemcpyDeviceToHost));
     return TX_OK;
 }
 

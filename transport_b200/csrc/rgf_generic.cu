@@ -1,0 +1,212 @@
+// K2/K3 for block sizes beyond the register-resident kernel (16 < n <= 64): one CTA per
+// (Hamiltonian, energy) point, blocks in shared memory (n <= 40) or an L2-resident global
+// workspace, CTA-cooperative GEMM / pivoted Gauss-Jordan from block_ops.cuh.
+//
+// Same recursion as rgf_small.cuh (replaces wfm.kernel, transport/wfm/__init__.py:29-137, for
+// multi-channel leads).  Lead self-energies always come from a table (K1).  Besides the reference's
+// per-channel R/T (which use only diag Sigma, :91) it emits the Caroli trace with the full matrix
+// Gamma = i(Sigma - Sigma^dag):  Tr[Gamma_R G Gamma_L G^dag], the meaningful total transmission when
+// Sigma is not diagonal (SURVEY.md §7 hard part 7, §8d cfg4).
+#include <cuda_runtime.h>
+
+#include "block_ops.cuh"
+#include "rgf_generic.h"
+#include "tx_host.h"
+
+using namespace tx;
+
+namespace tx {
+
+constexpr int GEN_THREADS = 256;
+constexpr int GEN_MATS = 5;
+
+__global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericParams p) {
+    extern __shared__ double2 gen_smem[];
+    __shared__ int s_ipiv[64];
+    __shared__ cd s_colk[64];
+    __shared__ double s_vL[64], s_vR[64];
+    __shared__ double s_red[GEN_THREADS / 32];
+    const int n = p.n, M = p.M, nn = n * n;
+    const long long pt = blockIdx.x;
+    const int ham = (int)(pt / p.nE);
+    const int e = (int)(pt - (long long)ham * p.nE);
+    const cd E = p.E[e];
+    cd* base = p.work ? p.work + pt * (long long)GEN_MATS * nn : reinterpret_cast<cd*>(gen_smem);
+    cd* G = base;            // current g_j, finally G_00
+    cd* W = base + nn;       // running product, finally G_{M-1,0}
+    cd* A = base + 2 * nn;
+    cd* X = base + 3 * nn;
+    cd* Y = base + 4 * nn;
+    const cd* hb = p.h + ham * p.h_stride;
+    const cd* tb = p.tnn + ham * p.t_stride;
+    const cd* SL = p.sigL + ham * p.sig_stride + (long long)e * nn;
+    const cd* SR = p.sigR + ham * p.sig_stride + (long long)e * nn;
+    const double par = p.h1 ? p.params[ham] : 0.0;
+
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {      // v = -2 Im diag Sigma  (:91)
+        s_vL[c] = -2.0 * SL[c * n + c].y;
+        s_vR[c] = -2.0 * SR[c * n + c].y;
+    }
+
+    for (int j = M - 1; j >= 0; --j) {
+        // A = E - h_j (- Sigma on the end blocks)
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            cd hv = hb[(long long)j * nn + idx];
+            if (p.h1) {
+                const cd w = p.h1[(long long)j * nn + idx];
+                hv.x = fma(par, w.x, hv.x);
+                hv.y = fma(par, w.y, hv.y);
+            }
+            cd a = (r == c) ? mk(E.x - hv.x, E.y - hv.y) : mk(-hv.x, -hv.y);
+            if (j == M - 1) a = a - SR[idx];
+            if (j == 0) a = a - SL[idx];
+            A[idx] = a;
+        }
+        __syncthreads();
+        if (j < M - 1) {
+            const cd* t = tb + (long long)j * nn;
+            if (p.hop_scalar) {
+                const cd t0 = t[0];
+                const double kap = norm2(t0);
+                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                    cd a = A[idx];
+                    const cd g = G[idx];
+                    a.x = fma(-kap, g.x, a.x);
+                    a.y = fma(-kap, g.y, a.y);
+                    A[idx] = a;
+                    W[idx] = W[idx] * conj(t0);                 // W t^dag
+                }
+                __syncthreads();
+            } else {
+                cta_gemm(X, t, OP_N, G, OP_N, n);               // t g
+                cta_gemm_acc(A, X, OP_N, t, OP_H, n, -1.0);     // A -= (t g) t^dag
+                cta_gemm(X, W, OP_N, t, OP_H, n);               // W t^dag
+                cta_copy(W, X, nn);
+            }
+        }
+        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        if (j == M - 1) {
+            cta_copy(G, A, nn);
+            cta_copy(W, A, nn);
+        } else {
+            cta_gemm(X, W, OP_N, A, OP_N, n);                   // (W t^dag) g_j
+            cta_copy(W, X, nn);
+            cta_copy(G, A, nn);
+        }
+    }
+
+    // ---- epilogue: per-channel R/T with the reference's formulas (:108-130)
+    double tsum = 0.0;
+    if (p.R || p.ttot || p.resid) {
+        for (int i = 0; i < p.n_src; ++i) {
+            double f2 = 0.0;
+            for (int c = 0; c < n; ++c) {
+                const double a = p.sources ? p.sources[(long long)i * n + c] : (c == i ? 1.0 : 0.0);
+                f2 = fma(a, a * s_vL[c], f2);
+            }
+            const double rflux = 1.0 / sqrt(f2);
+            double part = 0.0;
+            for (int s = threadIdx.x; s < n; s += blockDim.x) {
+                double ur = 0, ui = 0, wr = 0, wi = 0, mine = 0;
+                for (int c = 0; c < n; ++c) {
+                    const double a = p.sources ? p.sources[(long long)i * n + c] : (c == i ? 1.0 : 0.0);
+                    const double av = a * s_vL[c];
+                    const cd g = G[s * n + c], w = W[s * n + c];
+                    ur = fma(g.x, av, ur);
+                    ui = fma(g.y, av, ui);
+                    wr = fma(w.x, av, wr);
+                    wi = fma(w.y, av, wi);
+                    if (c == s) mine = a;
+                }
+                const double fr = sqrt(s_vL[s]) * rflux, ft = sqrt(s_vR[s]) * rflux;
+                const double xr = (-ui - mine) * fr, xi = ur * fr;
+                const double yr = -wi * ft, yi = wr * ft;
+                const double rr = fma(xr, xr, xi * xi), tt = fma(yr, yr, yi * yi);
+                if (p.R) {
+                    p.R[(pt * p.n_src + i) * n + s] = rr;
+                    p.T[(pt * p.n_src + i) * n + s] = tt;
+                }
+                part += rr + tt;
+                tsum += tt;
+            }
+            if (p.resid) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double tot = 0.0;
+                    for (int w = 0; w < GEN_THREADS / 32; ++w) tot += s_red[w];
+                    p.resid[pt * p.n_src + i] = tot - 1.0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (p.ttot) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < GEN_THREADS / 32; ++w) tot += s_red[w];
+            p.ttot[pt] = tot;
+        }
+        __syncthreads();
+    }
+    // ---- Caroli trace Tr[Gamma_R W Gamma_L W^dag], Gamma = i (Sigma - Sigma^dag)
+    if (p.caroli) {
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            const cd a = SR[idx], b = conj(SR[c * n + r]);
+            A[idx] = mk(-(a.y - b.y), a.x - b.x);               // i (a - b)
+            const cd a2 = SL[idx], b2 = conj(SL[c * n + r]);
+            X[idx] = mk(-(a2.y - b2.y), a2.x - b2.x);
+        }
+        __syncthreads();
+        cta_gemm(Y, A, OP_N, W, OP_N, n);                       // Gamma_R W
+        cta_gemm(A, Y, OP_N, X, OP_N, n);                       // Gamma_R W Gamma_L
+        double tr = 0.0;
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            const cd y = A[idx], w = W[idx];
+            tr += y.x * w.x + y.y * w.y;                        // Re sum_ij Y_ij conj(W_ij)
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tr;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < GEN_THREADS / 32; ++w) tot += s_red[w];
+            p.caroli[pt] = tot;
+        }
+    }
+}
+
+// Host-side launcher used by capi.cu.  `work` must hold n_pts*GEN_MATS*n*n elements when the blocks
+// do not fit in shared memory (use rgf_generic_workspace_elems to size it).
+size_t rgf_generic_workspace_elems(int n, long long n_pts) {
+    const size_t bytes = (size_t)GEN_MATS * n * n * sizeof(cd);
+    return bytes > 200 * 1024 ? (size_t)n_pts * GEN_MATS * n * n : 0;
+}
+
+int launch_rgf_generic(GenericParams p, cudaStream_t st) {
+    const size_t bytes = (size_t)GEN_MATS * p.n * p.n * sizeof(cd);
+    size_t smem = bytes;
+    if (bytes > 200 * 1024) {
+        if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
+        smem = 0;
+    } else {
+        p.work = nullptr;
+    }
+    if (smem > 48 * 1024)
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (p.n_pts > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
+    rgf_sweep_generic<<<(unsigned)p.n_pts, GEN_THREADS, smem, st>>>(p);
+    TX_CUDA(cudaGetLastError());
+    return TX_OK;
+}
+
+}  // namespace tx

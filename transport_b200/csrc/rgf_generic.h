@@ -1,0 +1,35 @@
+// Interface of the generic-size sweep (rgf_generic.cu) for capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tx_common.cuh"
+
+namespace tx {
+
+struct GenericParams {
+    const cd* h;
+    long long h_stride;
+    const cd* h1;
+    const double* params;
+    const cd* tnn;
+    long long t_stride;
+    const cd* E;
+    const cd* sigL;
+    const cd* sigR;
+    long long sig_stride;
+    const double* sources;   // [n_src][n] or null (all one-hot)
+    double* R;               // [n_pts][n_src][n] or null
+    double* T;
+    double* resid;           // [n_pts][n_src] or null
+    double* ttot;            // [n_pts] or null
+    double* caroli;          // [n_pts] or null
+    cd* work;                // global workspace or null (then dynamic shared memory)
+    int* singular;
+    long long n_pts;
+    int n, M, nE, n_src, hop_scalar;
+};
+
+size_t rgf_generic_workspace_elems(int n, long long n_pts);
+int launch_rgf_generic(GenericParams p, cudaStream_t st);
+
+}  // namespace tx

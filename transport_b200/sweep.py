@@ -37,7 +37,8 @@ def check_closed_leads(h):
 
 
 def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, params=None,
-                       sigL=None, sigR=None, want_resid=False, out=None, want_total=False):
+                       sigL=None, sigR=None, want_resid=False, out=None, want_total=False,
+                       want_caroli=False):
     """Reflection / transmission probabilities for every (Hamiltonian, energy, source).
 
     Args
@@ -50,7 +51,8 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
       out    optional (R, T) float64 arrays to fill (e.g. views of pinned memory)
     Returns
       R, T  float64 [P, nE, n_src, n]  (+ resid [P, nE, n_src] = sum R + sum T - 1 if want_resid,
-      + total [P, nE] = T summed over sources and channels if want_total)
+      + total [P, nE] = T summed over sources and channels if want_total,
+      + caroli [P, nE] = Tr[Gamma_R G Gamma_L G^dag] with matrix Gamma if want_caroli)
     """
     lib = _lib.load()
     h, tnn = _norm_blocks(h, tnn)
@@ -104,10 +106,11 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
             raise ValueError("out arrays must be float64 of shape %s" % (shape,))
     resid = np.empty(shape[:3], dtype=np.float64) if want_resid else None
     total = np.empty(shape[:2], dtype=np.float64) if want_total else None
+    caroli = np.empty(shape[:2], dtype=np.float64) if want_caroli else None
 
     rc = lib.tx_transmission_sweep(ptr(h), n_h, ptr(h1), ptr(params), ptr(tnn), n_t, n, M, n_ham,
                                    ptr(Es), len(Es), lead_mode, ptr(sigL), ptr(sigR), n_sig,
-                                   TX_HOP_AUTO, ptr(src), None, n_src, ptr(R), ptr(T), ptr(resid), ptr(total))
+                                   TX_HOP_AUTO, ptr(src), None, n_src, ptr(R), ptr(T), ptr(resid), ptr(total), ptr(caroli))
     if rc == _lib.TX_ERR_SINGULAR:
         # numpy raises LinAlgError for an exactly singular E - H' (wfm/__init__.py:162)
         raise np.linalg.LinAlgError("Singular matrix")
@@ -117,6 +120,8 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
         ret += (resid,)
     if want_total:
         ret += (total,)
+    if want_caroli:
+        ret += (caroli,)
     return ret
 
 
