@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "rgf_generic.h"
+#include "rgf_n8.cuh"
 #include "rgf_small.cuh"
 #include "tx_host.h"
 
@@ -63,7 +64,7 @@ int round_up_block(int n) {
 // number of resident 128-thread blocks per SM the register allocation is capped for.
 int g_variant = 0;
 
-template <int N, int LP, int HOP, int LEAD, int MINB>
+template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
     using Cfg = SmallCfg<N, LP, HOP>;
     constexpr int WARPS = 4;
@@ -72,14 +73,33 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_small<N, LP, HOP, LEAD, MINB>,
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_small<N, LP, HOP, LEAD, MINB, PIVX>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
     const long long per_block = (long long)WARPS * Cfg::GPW;
     const long long blocks = (p.n_pts + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_small<N, LP, HOP, LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    rgf_sweep_small<N, LP, HOP, LEAD, MINB, PIVX><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    TX_CUDA(cudaGetLastError());
+    return TX_OK;
+}
+
+template <int LEAD, int MINB, int PIVX>
+int launch_n8(const SweepParams& p, cudaStream_t st) {
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * N8Cfg::PER_WARP_BYTES;
+    static bool attr_done[16] = {false};
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 15]) {
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8<LEAD, MINB, PIVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 15] = true;
+    }
+    const long long per_block = (long long)WARPS * 8;
+    const long long blocks = (p.n_pts + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
+    rgf_sweep_n8<LEAD, MINB, PIVX><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }
@@ -123,7 +143,7 @@ int tx_device_synchronize(void) {
 }
 
 int tx_set_variant(int v) {
-    if (v < 0 || v > 3) return fail(TX_ERR_ARG, "variant must be 0..3");
+    if (v < 0 || v > 9) return fail(TX_ERR_ARG, "variant must be 0..9");
     g_variant = v;
     return TX_OK;
 }
@@ -237,6 +257,12 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
                 if (g_variant == 1) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
                 if (g_variant == 2) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
                 if (g_variant == 3) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
+                if (g_variant == 6) return launch_n8<LEAD_CLOSED, 3, 0>(p, st);
+                if (g_variant == 7) return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
+                if (g_variant == 8) return launch_n8<LEAD_CLOSED, 2, 0>(p, st);
+                if (g_variant == 9) return launch_n8<LEAD_CLOSED, 4, 1>(p, st);
+                if (g_variant == 4) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
+                if (g_variant == 5) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
             }
             return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
         case 16: return dispatch_modes<16, 16, 3, 2>(p, hop, lead, st);

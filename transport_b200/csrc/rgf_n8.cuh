@@ -1,0 +1,429 @@
+// Hot kernel of BASELINE config 2: n_loc_dof <= 8 (padded to 8), scalar hopping (tnn[j] = t_j I).
+//
+// Same recursion and same inverse as rgf_small.cuh (4 lanes per point, 2 rows per lane, in-place
+// Gauss-Jordan with implicit partial pivoting), but the running product W_j = conj(t_j) W_{j+1} g_j
+// is NOT kept in registers: W and g live in shared memory in a fragment-friendly layout and the
+// 8x8x8 complex product of every point is issued as eight FP64 tensor-core instructions
+// (mma.sync.m8n8k4.f64; tcgen05 has no f64 kind) by the whole warp, one point at a time.
+//
+// Why (ncu, profiles/r1_ncu_full_rgf_sweep_small_v1.csv): with W in registers the kernel needs
+// 250 registers -> 8 warps/SM, FP64 pipe 32 % busy, latency bound; the register-resident product
+// costs 512 DFMA issue slots + 64 broadcast LDS.128 per lane and site.  DMMA has the same FP64
+// throughput on sm_100a (37 TFLOP/s measured either way) but needs 8 issue slots per point, reads
+// each operand from shared memory exactly once, and frees 64 registers per lane.
+//
+// Shared-memory layout (per warp, in 16-byte complex units):
+//   GT[q][64+1]  g_j of point q stored TRANSPOSED:  g[k][n] at row n, column k
+//   WB[q][64+1]  W   of point q:                   W[r][c] at row r, column c
+//   element (row, col) of a block sits at  row*8 + (col ^ (5*(row&1)))   -- the XOR keeps the two
+//   rows a quarter-warp touches in a fragment load on disjoint bank halves; the 65-element point
+//   stride staggers neighbouring points by four banks.
+//   PV[8][8 groups] pivot row exchange (smem variant) ; the velocities reuse it in the epilogue.
+#pragma once
+#include "rgf_small.cuh"
+
+namespace tx {
+
+struct N8Cfg {
+    static constexpr int PSTRIDE = 65;
+    static constexpr int PER_WARP = 2 * 8 * PSTRIDE + 64;   // GT + WB + PV, in double2
+    static constexpr int PER_WARP_BYTES = PER_WARP * 16;
+};
+
+__device__ __forceinline__ int n8_idx(int row, int col) { return row * 8 + (col ^ (5 * (row & 1))); }
+
+__device__ __forceinline__ void dmma_8x8x4(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// In-place inverse of the 8x8 block (rows spread over 4 lanes, 2 per lane); result scattered
+// transposed into GT of the own point.  Same algorithm as invert_to_smem.
+template <int PIVX>
+__device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular) {
+    constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
+    unsigned perm = 0u;               // nibble k = pivot row of step k
+    unsigned used = 0u;
+    int krow[RP];
+    double2 dinv[RP];
+#pragma unroll
+    for (int s = 0; s < RP; ++s) {
+        krow[s] = 0;
+        dinv[s] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        unsigned long long key = 0ull;
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const double mag = fma(A[s][k].x, A[s][k].x, A[s][k].y * A[s][k].y);
+            unsigned long long kk = ((unsigned long long)__double_as_longlong(mag) & ~0x1Full) |
+                                    (unsigned long long)(0x10 | (15 - (row0 + s)));
+            if ((used >> s) & 1u) kk = 0ull;
+            key = kk > key ? kk : key;
+        }
+#pragma unroll
+        for (int off = LP / 2; off >= 1; off >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
+            key = other > key ? other : key;
+        }
+        const int prow = 15 - (int)(key & 0xFull);
+        if ((key >> 5) == 0ull) *singular = 1;
+        perm |= (unsigned)prow << (4 * k);
+
+        double2 pr[N];
+        if (PIVX == 1) {
+            const int src = ((threadIdx.x & 31) & ~(LP - 1)) | (prow >> 1);
+            const bool second = prow & 1;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const double2 v = second ? A[1][c] : A[0][c];
+                pr[c].x = __shfl_sync(0xffffffffu, v.x, src);
+                pr[c].y = __shfl_sync(0xffffffffu, v.y, src);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < RP; ++s)
+                if (row0 + s == prow) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) pv[c * GPW + grp] = A[s][c];
+                }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < N; ++c) pr[c] = pv[c * GPW + grp];
+            __syncwarp();   // single buffer: everyone has read before the next step overwrites
+        }
+        const cd invc = crecip(mk(pr[k].x, pr[k].y));
+        const double2 inv = make_double2(invc.x, invc.y);
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const bool isp = (row0 + s == prow);
+            const double2 invs = isp ? make_double2(0.0, 0.0) : inv;   // pivot row: multiplier 0
+            const double2 m = cmul2(A[s][k], invs);
+            if (isp) {
+                used |= 1u << s;
+                krow[s] = k;
+                dinv[s] = inv;
+            }
+#pragma unroll
+            for (int c = 0; c < N; ++c)
+                if (c != k) cfms2(A[s][c], m, pr[c]);
+            A[s][k] = make_double2((isp ? 1.0 : 0.0) - m.x, -m.y);
+        }
+    }
+    // inv[krow][col] -> GT(row = col, col = krow)
+#pragma unroll
+    for (int s = 0; s < RP; ++s) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const int col = (int)((perm >> (4 * j)) & 0xFu);
+            gt[n8_idx(col, krow[s])] = cmul2(A[s][j], dinv[s]);
+        }
+    }
+    __syncwarp();
+}
+
+template <int LEAD, int MINB, int PIVX>
+__global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
+    constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
+    extern __shared__ double2 smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp = lane >> 2;
+    const int li = lane & 3;
+    const int row0 = li * RP;
+    const int n = p.n;
+    const int M = p.M;
+    const bool full = (n == N);
+
+    double2* wsm = smem_all + (size_t)warp * N8Cfg::PER_WARP;
+    double2* GT = wsm;                                   // [8 points][65]
+    double2* WB = wsm + 8 * N8Cfg::PSTRIDE;              // [8 points][65]
+    double2* PV = wsm + 16 * N8Cfg::PSTRIDE;             // [8][8]
+    double2* gt = GT + grp * N8Cfg::PSTRIDE;             // own point
+    double2* wb = WB + grp * N8Cfg::PSTRIDE;
+
+    long long pt = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * GPW + grp;
+    const bool active = pt < p.n_pts;
+    if (!active) pt = p.n_pts - 1;
+    const int ham = (int)(pt / p.nE);
+    const int e = (int)(pt - (long long)ham * p.nE);
+    const cd E = p.E[e];
+    const long long nn = (long long)n * n;
+    const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
+    const double2* h1base = reinterpret_cast<const double2*>(p.h1);
+    const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
+    const double par = p.h1 ? p.params[ham] : 0.0;
+
+    auto h_at = [&](int j, int r, int c) -> double2 {
+        double2 v = hbase[(long long)j * nn + r * n + c];
+        if (h1base) {
+            const double2 w = h1base[(long long)j * nn + r * n + c];
+            v.x = fma(par, w.x, v.x);
+            v.y = fma(par, w.y, v.y);
+        }
+        return v;
+    };
+    auto t_at = [&](int j, int r, int c) -> double2 { return tbase[(long long)j * nn + r * n + c]; };
+    auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
+
+    // ------------------------------------------------------------------ prologue: lead self-energies of own rows
+    double2 sigLd[RP], sigRd[RP];
+    double vLo[RP], vRo[RP];
+#pragma unroll
+    for (int s = 0; s < RP; ++s) {
+        sigLd[s] = sigRd[s] = make_double2(0.0, 0.0);
+        vLo[s] = vRo[s] = 0.0;
+    }
+    if (LEAD == LEAD_CLOSED) {
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const int r = row0 + s;
+            if (full || r < n) {
+                const cd tL = tocd(t_at(0, r, r)), tR = tocd(t_at(M - 2, r, r));
+                const cd gL = g_closed_channel(E, tocd(h_at(0, r, r)), tL);        // wfm/__init__.py:283,286
+                const cd gR = g_closed_channel(E, tocd(h_at(M - 1, r, r)), tR);    // :284,287
+                const cd sl = conj(tL) * (gL * tL);                                // :301
+                const cd sr = tR * (gR * conj(tR));                                // :302
+                sigLd[s] = make_double2(sl.x, sl.y);
+                sigRd[s] = make_double2(sr.x, sr.y);
+                vLo[s] = -2.0 * sl.y;                                              // :91
+                vRo[s] = -2.0 * sr.y;
+            }
+        }
+    }
+
+    double2 A[RP][N];
+
+    // ------------------------------------------------------------------ sweep
+    for (int j = M - 1; j >= 0; --j) {
+        double2 tj = make_double2(0.0, 0.0);
+        if (j < M - 1) tj = t_at(j, 0, 0);
+
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const int r = row0 + s;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                double2 v = make_double2(0.0, 0.0);
+                if (full || (r < n && c < n)) v = h_at(j, r, c);
+                A[s][c] = make_double2(-v.x, -v.y);
+                if (c == r) {
+                    if (full || r < n) {
+                        A[s][c].x += E.x;
+                        A[s][c].y += E.y;
+                    } else {
+                        A[s][c] = make_double2(1.0, 0.0);
+                    }
+                }
+            }
+        }
+        if (j < M - 1) {
+            // A -= |t_j|^2 g_{j+1}: own rows of g are columns of GT
+            const double kap = fma(tj.x, tj.x, tj.y * tj.y);
+#pragma unroll
+            for (int s = 0; s < RP; ++s) {
+                const int r = row0 + s;
+                if (full || r < n) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        const double2 g = gt[n8_idx(c, r)];
+                        A[s][c].x = fma(-kap, g.x, A[s][c].x);
+                        A[s][c].y = fma(-kap, g.y, A[s][c].y);
+                    }
+                }
+            }
+        }
+        if (j == M - 1 || j == 0) {
+            if (LEAD == LEAD_CLOSED) {
+#pragma unroll
+                for (int s = 0; s < RP; ++s) {
+                    const int r = row0 + s;
+                    const double2 sg = (j == 0) ? sigLd[s] : sigRd[s];
+#pragma unroll
+                    for (int c = 0; c < N; ++c)
+                        if (c == r) {
+                            A[s][c].x -= sg.x;
+                            A[s][c].y -= sg.y;
+                        }
+                }
+            } else {
+                const double2* tab = reinterpret_cast<const double2*>(j == 0 ? p.sigL : p.sigR) + ham * p.sig_stride +
+                                     (long long)e * nn;
+#pragma unroll
+                for (int s = 0; s < RP; ++s) {
+                    const int r = row0 + s;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        double2 sg = make_double2(0.0, 0.0);
+                        if (full || (r < n && c < n)) sg = tab[r * n + c];
+                        A[s][c].x -= sg.x;
+                        A[s][c].y -= sg.y;
+                        if (c == r) {
+                            if (j == 0) vLo[s] = -2.0 * sg.y;
+                            else vRo[s] = -2.0 * sg.y;
+                        }
+                    }
+                }
+            }
+        }
+
+        __syncwarp();   // all reads of g_{j+1} (own rows above, fragments below in the previous site) are done
+        n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular);
+
+        if (j == M - 1) {
+            // W_{M-1} = g_{M-1} (padding rows zero)
+#pragma unroll
+            for (int s = 0; s < RP; ++s) {
+                const int r = row0 + s;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double2 g = gt[n8_idx(c, r)];
+                    if (!(full || r < n)) g = make_double2(0.0, 0.0);
+                    wb[n8_idx(r, c)] = g;
+                }
+            }
+            __syncwarp();
+        } else {
+            // W <- conj(t_j) (W g_j): eight DMMA per point, the whole warp on one point at a time
+            const int fr = lane >> 2, fc = lane & 3;
+            const int i0 = n8_idx(fr, fc), i1 = n8_idx(fr, fc + 4);
+            const int o0 = n8_idx(fr, 2 * fc), o1 = n8_idx(fr, 2 * fc + 1);
+#pragma unroll 2
+            for (int q = 0; q < GPW; ++q) {
+                const double2* wq = WB + q * N8Cfg::PSTRIDE;
+                const double2* gq = GT + q * N8Cfg::PSTRIDE;
+                const double2 a0 = wq[i0], a1 = wq[i1];
+                const double2 b0 = gq[i0], b1 = gq[i1];
+                // the hopping of point q (points of a warp may belong to different Hamiltonians)
+                const double tqx = __shfl_sync(0xffffffffu, tj.x, q * LP);
+                const double tqy = __shfl_sync(0xffffffffu, tj.y, q * LP);
+                double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
+                dmma_8x8x4(cre, a0.x, b0.x);
+                dmma_8x8x4(cim, a0.x, b0.y);
+                dmma_8x8x4(cre, -a0.y, b0.y);
+                dmma_8x8x4(cim, a0.y, b0.x);
+                dmma_8x8x4(cre, a1.x, b1.x);
+                dmma_8x8x4(cim, a1.x, b1.y);
+                dmma_8x8x4(cre, -a1.y, b1.y);
+                dmma_8x8x4(cim, a1.y, b1.x);
+                __syncwarp();   // every lane has loaded its W fragments of point q
+                double2* wo = WB + q * N8Cfg::PSTRIDE;
+                // times conj(t): (x + iy)(tx - i ty)
+                wo[o0] = make_double2(fma(cre[0], tqx, cim[0] * tqy), fma(cim[0], tqx, -(cre[0] * tqy)));
+                wo[o1] = make_double2(fma(cre[1], tqx, cim[1] * tqy), fma(cim[1], tqx, -(cre[1] * tqy)));
+            }
+            __syncwarp();
+        }
+    }
+
+    // ------------------------------------------------------------------ epilogue (K3)
+    // G_00 = g_0 in GT, G_{M-1,0} = W in WB; velocities published through PV.
+#pragma unroll
+    for (int s = 0; s < RP; ++s) PV[(row0 + s) * GPW + grp] = make_double2(vLo[s], vRo[s]);
+    __syncwarp();
+    double vL[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) vL[c] = PV[c * GPW + grp].x;
+    double sqL[RP], sqR[RP];
+#pragma unroll
+    for (int s = 0; s < RP; ++s) {
+        sqL[s] = sqrt(vLo[s]);
+        sqR[s] = sqrt(vRo[s]);
+    }
+
+    const int n_src = p.n_src;
+    const long long obase = pt * (long long)n_src * n;
+    double tsum = 0.0;
+    auto emit = [&](int i, const double (&rr)[RP], const double (&tt)[RP]) {
+        double sum = 0.0;
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const int r = row0 + s;
+            if (full || r < n) {
+                sum += rr[s] + tt[s];
+                tsum += tt[s];
+                if (active) {
+                    p.R[obase + (long long)i * n + r] = rr[s];
+                    p.T[obase + (long long)i * n + r] = tt[s];
+                }
+            }
+        }
+        if (p.resid) {
+#pragma unroll
+            for (int off = LP / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (active && li == 0) p.resid[pt * n_src + i] = sum - 1.0;
+        }
+    };
+
+    if (p.sources == nullptr) {
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            if (full || a < n) {
+                const double rflux = 1.0 / sqrt(vL[a]);               // 1 / i_flux   (:108)
+                double rr[RP], tt[RP];
+#pragma unroll
+                for (int s = 0; s < RP; ++s) {
+                    const int r = row0 + s;
+                    const double fr = sqL[s] * rflux, ft = sqR[s] * rflux;
+                    const double2 g = gt[n8_idx(a, r)];       // G_00[r][a]
+                    const double2 w = wb[n8_idx(r, a)];       // G_{M-1,0}[r][a]
+                    const double xr = (-g.y * vL[a] - (r == a ? 1.0 : 0.0)) * fr;   // (:116-117)
+                    const double xi = (g.x * vL[a]) * fr;
+                    rr[s] = fma(xr, xr, xi * xi);
+                    const double yr = (-w.y * vL[a]) * ft;                           // (:124-125)
+                    const double yi = (w.x * vL[a]) * ft;
+                    tt[s] = fma(yr, yr, yi * yi);
+                }
+                emit(a, rr, tt);
+            }
+        }
+    } else {
+        for (int i = 0; i < n_src; ++i) {
+            const double* Asrc = p.sources + (long long)i * n;
+            double f2 = 0.0;
+            double ur[RP], ui[RP], wr[RP], wi[RP], mine[RP];
+#pragma unroll
+            for (int s = 0; s < RP; ++s) ur[s] = ui[s] = wr[s] = wi[s] = mine[s] = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                if (full || c < n) {
+                    const double a = Asrc[c];
+                    const double av = a * vL[c];
+                    f2 = fma(a, av, f2);
+#pragma unroll
+                    for (int s = 0; s < RP; ++s) {
+                        const double2 g = gt[n8_idx(c, row0 + s)];
+                        const double2 w = wb[n8_idx(row0 + s, c)];
+                        ur[s] = fma(g.x, av, ur[s]);
+                        ui[s] = fma(g.y, av, ui[s]);
+                        wr[s] = fma(w.x, av, wr[s]);
+                        wi[s] = fma(w.y, av, wi[s]);
+                        if (c == row0 + s) mine[s] = a;
+                    }
+                }
+            }
+            const double rflux = 1.0 / sqrt(f2);
+            double rr[RP], tt[RP];
+#pragma unroll
+            for (int s = 0; s < RP; ++s) {
+                const double fr = sqL[s] * rflux, ft = sqR[s] * rflux;
+                const double xr = (-ui[s] - mine[s]) * fr;
+                const double xi = ur[s] * fr;
+                rr[s] = fma(xr, xr, xi * xi);
+                const double yr = -wi[s] * ft;
+                const double yi = wr[s] * ft;
+                tt[s] = fma(yr, yr, yi * yi);
+            }
+            emit(i, rr, tt);
+        }
+    }
+    if (p.ttot) {
+#pragma unroll
+        for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+        if (active && li == 0) p.ttot[pt] = tsum;
+    }
+}
+
+}  // namespace tx

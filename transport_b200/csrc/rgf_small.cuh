@@ -101,7 +101,7 @@ __device__ __forceinline__ void rows_times_smem(const double2 (&L)[RP][N], const
 // is the pivot row p_k; every other row is reduced with it, the pivot row itself is left unscaled
 // (one scaling per row at the end).  The result is scattered into shared memory in canonical
 // order:  inv[k][p_j] = A[p_k][j] / d_k.
-template <int N, int LP>
+template <int N, int LP, int PIVX = 0>
 __device__ __forceinline__ void invert_to_smem(double2 (&A)[N / LP][N], double2* piv,
                                                double2* gm, int grp, int row0, int* singular) {
     constexpr int RP = N / LP;
@@ -137,18 +137,33 @@ __device__ __forceinline__ void invert_to_smem(double2 (&A)[N / LP][N], double2*
         if ((key >> 5) == 0ull) *singular = 1;
         perm |= (unsigned long long)prow << (4 * k);
 
-        // ---- the owner publishes the pivot row (double-buffered: one __syncwarp per step)
-        double2* pb = piv + (k & 1) * N * GPW;
-#pragma unroll
-        for (int s = 0; s < RP; ++s)
-            if (row0 + s == prow) {
-#pragma unroll
-                for (int c = 0; c < N; ++c) pb[c * GPW + grp] = A[s][c];
-            }
-        __syncwarp();
         double2 pr[N];
+        if (PIVX == 1) {
+            // ---- pivot row by register shuffle from the owner lane (no shared-memory round trip)
+            const int src = ((threadIdx.x & 31) & ~(LP - 1)) | (prow / RP);
+            const int sloc = prow % RP;
 #pragma unroll
-        for (int c = 0; c < N; ++c) pr[c] = pb[c * GPW + grp];
+            for (int c = 0; c < N; ++c) {
+                double2 v = A[0][c];
+#pragma unroll
+                for (int s = 1; s < RP; ++s)
+                    if (sloc == s) v = A[s][c];
+                pr[c].x = __shfl_sync(0xffffffffu, v.x, src);
+                pr[c].y = __shfl_sync(0xffffffffu, v.y, src);
+            }
+        } else {
+            // ---- the owner publishes the pivot row (double-buffered: one __syncwarp per step)
+            double2* pb = piv + (k & 1) * N * GPW;
+#pragma unroll
+            for (int s = 0; s < RP; ++s)
+                if (row0 + s == prow) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) pb[c * GPW + grp] = A[s][c];
+                }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < N; ++c) pr[c] = pb[c * GPW + grp];
+        }
         const cd invc = crecip(mk(pr[k].x, pr[k].y));
         const double2 inv = make_double2(invc.x, invc.y);
 
@@ -182,7 +197,7 @@ __device__ __forceinline__ void invert_to_smem(double2 (&A)[N / LP][N], double2*
     __syncwarp();
 }
 
-template <int N, int LP, int HOP, int LEAD, int MINB>
+template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p) {
     using Cfg = SmallCfg<N, LP, HOP>;
     constexpr int RP = Cfg::RP;
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
 
         // every lane has finished reading g_{j+1} from gm before it is overwritten
         __syncwarp();
-        invert_to_smem<N, LP>(A, piv, gm, grp, row0, p.singular);
+        invert_to_smem<N, LP, PIVX>(A, piv, gm, grp, row0, p.singular);
 
         if (j == M - 1) {
             // W_{M-1} = g_{M-1}; padding rows start (and stay) at zero
