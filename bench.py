@@ -230,6 +230,7 @@ def gpu_arm(args):
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches0 = int(lib.tx_launch_counter())
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
@@ -238,6 +239,7 @@ def gpu_arm(args):
         ev[k][1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    launches = int(lib.tx_launch_counter()) - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     ms_total = float(sum(ms_steps))
@@ -328,7 +330,7 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "points_per_gpu": n_pts, "l2": "256 MB flush between timed steps; "
                        "each step also writes 2.05 GB of R/T", "variant": args.variant,
                        "parallelism": "J axis sharded, dp%d" % world},
-            "e2e": e2e, "gpu_launches": args.steps * lib.tx_sweep_launch_count(NLOC, MBLK, _lib.TX_HOP_SCALAR),
+            "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak, "traffic": None,
                          "peak_source": "tx_measure_fp64_peak: register-resident DFMA loop, measured in this run "

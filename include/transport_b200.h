@@ -130,6 +130,8 @@ long long tx_sweep_workspace_elems(int n, long long n_pts);
 
 /* Number of kernel launches tx_transmission_sweep_dev issues for this shape (for accounting). */
 int tx_sweep_launch_count(int n, int M, int hop_mode);
+/* Running count of sweep / surface-GF kernel launches issued by this library in the process. */
+long long tx_launch_counter(void);
 
 /* ---- lead surface Green's functions and self-energies (K1) -------------------------------- */
 /*

@@ -1,6 +1,7 @@
 // C ABI of libtransport_b200.so (declared in include/transport_b200.h).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -23,6 +24,8 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
 }  // namespace tx
 
 namespace {
@@ -81,13 +84,35 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
     const long long blocks = (p.n_pts + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
     rgf_sweep_small<N, LP, HOP, LEAD, MINB, PIVX><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }
 
+// grow-only per-device buffer for expanded affine Hamiltonian families (tx_transmission_sweep_dev)
+DevBuf g_expand[16];
+
 template <int LEAD, int MINB, int PIVX>
-int launch_n8(const SweepParams& p, cudaStream_t st) {
+int launch_n8(SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
+    if (p.h1) {
+        int devid = 0;
+        TX_CUDA(cudaGetDevice(&devid));
+        const long long per_ham = (long long)p.M * p.n * p.n;
+        const long long n_ham = p.n_pts / p.nE;
+        const long long total = per_ham * n_ham;
+        DevBuf& buf = g_expand[devid & 15];
+        if ((size_t)total * sizeof(cd) > buf.cap) TX_CUDA(cudaStreamSynchronize(st));   // a regrow frees the old buffer
+        int rc = buf.ensure((size_t)total * sizeof(cd));
+        if (rc) return rc;
+        affine_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, p.params, (cd*)buf.ptr, per_ham, total);
+        count_launch();
+        TX_CUDA(cudaGetLastError());
+        p.h = (const cd*)buf.ptr;
+        p.h_stride = per_ham;
+        p.h1 = nullptr;
+        p.params = nullptr;
+    }
     const size_t smem = (size_t)WARPS * N8Cfg::PER_WARP_BYTES;
     static bool attr_done[16] = {false};
     int dev = 0;
@@ -100,6 +125,7 @@ int launch_n8(const SweepParams& p, cudaStream_t st) {
     const long long blocks = (p.n_pts + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
     rgf_sweep_n8<LEAD, MINB, PIVX><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }
@@ -141,6 +167,8 @@ int tx_device_synchronize(void) {
     TX_CUDA(cudaDeviceSynchronize());
     return TX_OK;
 }
+
+long long tx_launch_counter(void) { return g_launches.load(); }
 
 int tx_set_variant(int v) {
     if (v < 0 || v > 9) return fail(TX_ERR_ARG, "variant must be 0..9");

@@ -205,6 +205,7 @@ int launch_rgf_generic(GenericParams p, cudaStream_t st) {
         TX_CUDA(cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p.n_pts > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
     rgf_sweep_generic<<<(unsigned)p.n_pts, GEN_THREADS, smem, st>>>(p);
+    count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }

@@ -18,7 +18,7 @@
 //   element (row, col) of a block sits at  row*8 + (col ^ (5*(row&1)))   -- the XOR keeps the two
 //   rows a quarter-warp touches in a fragment load on disjoint bank halves; the 65-element point
 //   stride staggers neighbouring points by four banks.
-//   PV[8][8 groups] pivot row exchange (smem variant) ; the velocities reuse it in the epilogue.
+//   PV[2][8][8 groups] double-buffered pivot row exchange; the velocities reuse it in the epilogue.
 #pragma once
 #include "rgf_small.cuh"
 
@@ -26,11 +26,13 @@ namespace tx {
 
 struct N8Cfg {
     static constexpr int PSTRIDE = 65;
-    static constexpr int PER_WARP = 2 * 8 * PSTRIDE + 64;   // GT + WB + PV, in double2
+    static constexpr int PER_WARP = 2 * 8 * PSTRIDE + 128;  // GT + WB + PV[2], in double2
     static constexpr int PER_WARP_BYTES = PER_WARP * 16;
 };
 
 __device__ __forceinline__ int n8_idx(int row, int col) { return row * 8 + (col ^ (5 * (row & 1))); }
+
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ void dmma_8x8x4(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -38,88 +40,130 @@ __device__ __forceinline__ void dmma_8x8x4(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+// 1/d without the IEEE slow path: MUFU.RCP64H seed + two Newton steps (~1 ulp; blocks are O(1)).
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double2 fast_crecip(double2 z) {
+    const double d = fast_rcp(fma(z.x, z.x, z.y * z.y));
+    return make_double2(z.x * d, -z.y * d);
+}
+
+// 32-bit pivot key: high word of |a|^2 (monotonic for non-negative doubles) with the low 5 bits
+// replaced by 0x10 | (15 - row); 0 for rows that were already used.
+__device__ __forceinline__ unsigned n8_key(double2 a, int row, bool is_used) {
+    const double mag = fma(a.x, a.x, a.y * a.y);
+    const unsigned k = ((unsigned)__double2hiint(mag) & ~0x1Fu) | (unsigned)(0x10 | (15 - row));
+    return is_used ? 0u : k;
+}
+
 // In-place inverse of the 8x8 block (rows spread over 4 lanes, 2 per lane); result scattered
-// transposed into GT of the own point.  Same algorithm as invert_to_smem.
+// transposed into GT of the own point.  Same algorithm as invert_to_smem (Gauss-Jordan, implicit
+// partial pivoting, unscaled pivot rows), software-pipelined: the pivot search, the broadcast of
+// the pivot element and its reciprocal for step k+1 are issued as soon as column k+1 has been
+// updated in step k, so their latency hides behind the remaining column updates.
 template <int PIVX>
 __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular) {
     constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & ~(LP - 1);
     unsigned perm = 0u;               // nibble k = pivot row of step k
-    unsigned used = 0u;
-    int krow[RP];
-    double2 dinv[RP];
-#pragma unroll
-    for (int s = 0; s < RP; ++s) {
-        krow[s] = 0;
-        dinv[s] = make_double2(0.0, 0.0);
+    bool used0 = false, used1 = false;
+    int krow0 = 0, krow1 = 0;
+    double2 dinv0 = make_double2(0.0, 0.0), dinv1 = make_double2(0.0, 0.0);
+
+    // pivot of step 0
+    unsigned key = max(n8_key(A[0][0], row0, false), n8_key(A[1][0], row0 + 1, false));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+    int prow = 15 - (int)(key & 0xFu);
+    if ((key >> 5) == 0u) *singular = 1;
+    double2 pe;
+    {
+        const double2 v = (prow & 1) ? A[1][0] : A[0][0];
+        pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
+        pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
     }
+    double2 inv = fast_crecip(pe);
+
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        unsigned long long key = 0ull;
-#pragma unroll
-        for (int s = 0; s < RP; ++s) {
-            const double mag = fma(A[s][k].x, A[s][k].x, A[s][k].y * A[s][k].y);
-            unsigned long long kk = ((unsigned long long)__double_as_longlong(mag) & ~0x1Full) |
-                                    (unsigned long long)(0x10 | (15 - (row0 + s)));
-            if ((used >> s) & 1u) kk = 0ull;
-            key = kk > key ? kk : key;
-        }
-#pragma unroll
-        for (int off = LP / 2; off >= 1; off >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
-            key = other > key ? other : key;
-        }
-        const int prow = 15 - (int)(key & 0xFull);
-        if ((key >> 5) == 0ull) *singular = 1;
         perm |= (unsigned)prow << (4 * k);
+        const bool isp0 = (row0 == prow), isp1 = (row0 + 1 == prow);
 
+        // ---- pivot row to every lane of the group
         double2 pr[N];
         if (PIVX == 1) {
-            const int src = ((threadIdx.x & 31) & ~(LP - 1)) | (prow >> 1);
+            const int src = gbase | (prow >> 1);
             const bool second = prow & 1;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
+                if (c == k) continue;
                 const double2 v = second ? A[1][c] : A[0][c];
                 pr[c].x = __shfl_sync(0xffffffffu, v.x, src);
                 pr[c].y = __shfl_sync(0xffffffffu, v.y, src);
             }
         } else {
+            double2* pb = pv + (k & 1) * N * GPW;     // double-buffered: one __syncwarp per step
+            if (isp0) {
 #pragma unroll
-            for (int s = 0; s < RP; ++s)
-                if (row0 + s == prow) {
+                for (int c = 0; c < N; ++c)
+                    if (c != k) pb[c * GPW + grp] = A[0][c];
+            }
+            if (isp1) {
 #pragma unroll
-                    for (int c = 0; c < N; ++c) pv[c * GPW + grp] = A[s][c];
-                }
+                for (int c = 0; c < N; ++c)
+                    if (c != k) pb[c * GPW + grp] = A[1][c];
+            }
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < N; ++c) pr[c] = pv[c * GPW + grp];
-            __syncwarp();   // single buffer: everyone has read before the next step overwrites
-        }
-        const cd invc = crecip(mk(pr[k].x, pr[k].y));
-        const double2 inv = make_double2(invc.x, invc.y);
-#pragma unroll
-        for (int s = 0; s < RP; ++s) {
-            const bool isp = (row0 + s == prow);
-            const double2 invs = isp ? make_double2(0.0, 0.0) : inv;   // pivot row: multiplier 0
-            const double2 m = cmul2(A[s][k], invs);
-            if (isp) {
-                used |= 1u << s;
-                krow[s] = k;
-                dinv[s] = inv;
-            }
-#pragma unroll
             for (int c = 0; c < N; ++c)
-                if (c != k) cfms2(A[s][c], m, pr[c]);
-            A[s][k] = make_double2((isp ? 1.0 : 0.0) - m.x, -m.y);
+                if (c != k) pr[c] = pb[c * GPW + grp];
         }
+
+        // multipliers (0 for the pivot row itself)
+        const double2 m0 = cmul2(A[0][k], isp0 ? make_double2(0.0, 0.0) : inv);
+        const double2 m1 = cmul2(A[1][k], isp1 ? make_double2(0.0, 0.0) : inv);
+        if (isp0) { used0 = true; krow0 = k; dinv0 = inv; }
+        if (isp1) { used1 = true; krow1 = k; dinv1 = inv; }
+
+        // ---- look ahead: finish column k+1 first, then start the search for the next pivot
+        if (k + 1 < N) {
+            cfms2(A[0][k + 1], m0, pr[k + 1]);
+            cfms2(A[1][k + 1], m1, pr[k + 1]);
+            key = max(n8_key(A[0][k + 1], row0, used0), n8_key(A[1][k + 1], row0 + 1, used1));
+            key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+            key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+            prow = 15 - (int)(key & 0xFu);
+            if ((key >> 5) == 0u) *singular = 1;
+            const double2 v = (prow & 1) ? A[1][k + 1] : A[0][k + 1];
+            pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
+            pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
+        }
+        // ---- remaining columns (independent of the shuffles above)
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+            if (c != k && c != k + 1) {
+                cfms2(A[0][c], m0, pr[c]);
+                cfms2(A[1][c], m1, pr[c]);
+            }
+        A[0][k] = make_double2((isp0 ? 1.0 : 0.0) - m0.x, -m0.y);
+        A[1][k] = make_double2((isp1 ? 1.0 : 0.0) - m1.x, -m1.y);
+        if (k + 1 < N) inv = fast_crecip(pe);
     }
-    // inv[krow][col] -> GT(row = col, col = krow)
+
+    // inv[krow][col] -> GT(row = col, col = krow):  element index col*8 + (krow ^ 5*(col&1))
 #pragma unroll
-    for (int s = 0; s < RP; ++s) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const int col = (int)((perm >> (4 * j)) & 0xFu);
-            gt[n8_idx(col, krow[s])] = cmul2(A[s][j], dinv[s]);
-        }
+    for (int j = 0; j < N; ++j) {
+        const int col = (int)((perm >> (4 * j)) & 0xFu);
+        const int base = col * 8, sw = (col & 1) * 5;
+        gt[base + (krow0 ^ sw)] = cmul2(A[0][j], dinv0);
+        gt[base + (krow1 ^ sw)] = cmul2(A[1][j], dinv1);
     }
     __syncwarp();
 }
@@ -152,20 +196,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     const cd E = p.E[e];
     const long long nn = (long long)n * n;
     const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
-    const double2* h1base = reinterpret_cast<const double2*>(p.h1);
     const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
-    const double par = p.h1 ? p.params[ham] : 0.0;
 
-    auto h_at = [&](int j, int r, int c) -> double2 {
-        double2 v = hbase[(long long)j * nn + r * n + c];
-        if (h1base) {
-            const double2 w = h1base[(long long)j * nn + r * n + c];
-            v.x = fma(par, w.x, v.x);
-            v.y = fma(par, w.y, v.y);
-        }
-        return v;
-    };
-    auto t_at = [&](int j, int r, int c) -> double2 { return tbase[(long long)j * nn + r * n + c]; };
+    auto h_at = [&](int j, int r, int c) -> double2 { return __ldg(hbase + (long long)j * nn + r * n + c); };
+    auto t_at = [&](int j, int r, int c) -> double2 { return __ldg(tbase + (long long)j * nn + r * n + c); };
     auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
 
     // ------------------------------------------------------------------ prologue: lead self-energies of own rows
@@ -195,19 +229,34 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     }
 
     double2 A[RP][N];
-
-    // ------------------------------------------------------------------ sweep
-    for (int j = M - 1; j >= 0; --j) {
-        double2 tj = make_double2(0.0, 0.0);
-        if (j < M - 1) tj = t_at(j, 0, 0);
-
+    // Rows of the NEXT site's on-site block: the loads are issued right after the inverse has been
+    // scattered (A is dead then) so that their L2 latency hides behind the tensor-core phase.
+    // (Affine families h0 + J*h1 are expanded by affine_expand_kernel before this kernel runs.)
+    double2 H0[RP][N];
+    auto fetch_rows = [&](int j) {
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
             const int r = row0 + s;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
-                double2 v = make_double2(0.0, 0.0);
-                if (full || (r < n && c < n)) v = h_at(j, r, c);
+                const bool ok = full || (r < n && c < n);
+                H0[s][c] = ok ? __ldg(hbase + (long long)j * nn + r * n + c) : make_double2(0.0, 0.0);
+            }
+        }
+    };
+    fetch_rows(M - 1);
+
+    // ------------------------------------------------------------------ sweep
+    for (int j = M - 1; j >= 0; --j) {
+        double2 tj = make_double2(0.0, 0.0);
+        if (j < M - 1) tj = t_at(j, 0, 0);
+        // A = E - h_j from the rows fetched during the previous site's tensor-core phase
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const int r = row0 + s;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const double2 v = H0[s][c];
                 A[s][c] = make_double2(-v.x, -v.y);
                 if (c == r) {
                     if (full || r < n) {
@@ -271,6 +320,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
 
         __syncwarp();   // all reads of g_{j+1} (own rows above, fragments below in the previous site) are done
         n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular);
+        if (j > 0) fetch_rows(j - 1);
 
         if (j == M - 1) {
             // W_{M-1} = g_{M-1} (padding rows zero)
@@ -286,33 +336,53 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             }
             __syncwarp();
         } else {
-            // W <- conj(t_j) (W g_j): eight DMMA per point, the whole warp on one point at a time
+            // W <- conj(t_j) (W g_j): eight DMMA per point, the whole warp on two points at a time
+            // (8 independent accumulator chains of length 2 hide the tensor-pipe latency)
             const int fr = lane >> 2, fc = lane & 3;
             const int i0 = n8_idx(fr, fc), i1 = n8_idx(fr, fc + 4);
             const int o0 = n8_idx(fr, 2 * fc), o1 = n8_idx(fr, 2 * fc + 1);
-#pragma unroll 2
-            for (int q = 0; q < GPW; ++q) {
-                const double2* wq = WB + q * N8Cfg::PSTRIDE;
-                const double2* gq = GT + q * N8Cfg::PSTRIDE;
-                const double2 a0 = wq[i0], a1 = wq[i1];
-                const double2 b0 = gq[i0], b1 = gq[i1];
-                // the hopping of point q (points of a warp may belong to different Hamiltonians)
-                const double tqx = __shfl_sync(0xffffffffu, tj.x, q * LP);
-                const double tqy = __shfl_sync(0xffffffffu, tj.y, q * LP);
-                double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
-                dmma_8x8x4(cre, a0.x, b0.x);
-                dmma_8x8x4(cim, a0.x, b0.y);
-                dmma_8x8x4(cre, -a0.y, b0.y);
-                dmma_8x8x4(cim, a0.y, b0.x);
-                dmma_8x8x4(cre, a1.x, b1.x);
-                dmma_8x8x4(cim, a1.x, b1.y);
-                dmma_8x8x4(cre, -a1.y, b1.y);
-                dmma_8x8x4(cim, a1.y, b1.x);
-                __syncwarp();   // every lane has loaded its W fragments of point q
-                double2* wo = WB + q * N8Cfg::PSTRIDE;
-                // times conj(t): (x + iy)(tx - i ty)
-                wo[o0] = make_double2(fma(cre[0], tqx, cim[0] * tqy), fma(cim[0], tqx, -(cre[0] * tqy)));
-                wo[o1] = make_double2(fma(cre[1], tqx, cim[1] * tqy), fma(cim[1], tqx, -(cre[1] * tqy)));
+#pragma unroll 1
+            for (int q = 0; q < GPW; q += 2) {
+                double2 a[2][2], b[2][2];
+                double tqx[2], tqy[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double2* wq = WB + (q + u) * N8Cfg::PSTRIDE;
+                    const double2* gq = GT + (q + u) * N8Cfg::PSTRIDE;
+                    a[u][0] = wq[i0];
+                    a[u][1] = wq[i1];
+                    b[u][0] = gq[i0];
+                    b[u][1] = gq[i1];
+                    // the hopping of point q+u (points of a warp may belong to different Hamiltonians)
+                    tqx[u] = __shfl_sync(0xffffffffu, tj.x, (q + u) * LP);
+                    tqy[u] = __shfl_sync(0xffffffffu, tj.y, (q + u) * LP);
+                }
+                double rr0[2][2] = {{0, 0}, {0, 0}}, rr1[2][2] = {{0, 0}, {0, 0}};   // Re: k-halves 0 / 1
+                double ii0[2][2] = {{0, 0}, {0, 0}}, ii1[2][2] = {{0, 0}, {0, 0}};   // Im
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    dmma_8x8x4(rr0[u], a[u][0].x, b[u][0].x);
+                    dmma_8x8x4(ii0[u], a[u][0].x, b[u][0].y);
+                    dmma_8x8x4(rr1[u], a[u][1].x, b[u][1].x);
+                    dmma_8x8x4(ii1[u], a[u][1].x, b[u][1].y);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    dmma_8x8x4(rr0[u], -a[u][0].y, b[u][0].y);
+                    dmma_8x8x4(ii0[u], a[u][0].y, b[u][0].x);
+                    dmma_8x8x4(rr1[u], -a[u][1].y, b[u][1].y);
+                    dmma_8x8x4(ii1[u], a[u][1].y, b[u][1].x);
+                }
+                __syncwarp();   // every lane has loaded its W fragments of points q, q+1
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    double2* wo = WB + (q + u) * N8Cfg::PSTRIDE;
+                    const double x0 = rr0[u][0] + rr1[u][0], y0 = ii0[u][0] + ii1[u][0];
+                    const double x1 = rr0[u][1] + rr1[u][1], y1 = ii0[u][1] + ii1[u][1];
+                    // times conj(t): (x + iy)(tx - i ty)
+                    wo[o0] = make_double2(fma(x0, tqx[u], y0 * tqy[u]), fma(y0, tqx[u], -(x0 * tqy[u])));
+                    wo[o1] = make_double2(fma(x1, tqx[u], y1 * tqy[u]), fma(y1, tqx[u], -(x1 * tqy[u])));
+                }
             }
             __syncwarp();
         }
@@ -424,6 +494,19 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
         if (active && li == 0) p.ttot[pt] = tsum;
     }
+}
+
+// out[ham][i] = h0[i] + params[ham] * h1[i]  — materialises an affine Hamiltonian family (8 KB per
+// Hamiltonian at n = M = 8; the whole family stays L2 resident).
+__global__ void affine_expand_kernel(const cd* __restrict__ h0, const cd* __restrict__ h1,
+                                     const double* __restrict__ params, cd* __restrict__ out, long long per_ham,
+                                     long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long ham = idx / per_ham, i = idx - ham * per_ham;
+    const cd a = h0[i], b = h1[i];
+    const double par = params[ham];
+    out[idx] = mk(fma(par, b.x, a.x), fma(par, b.y, a.y));
 }
 
 }  // namespace tx

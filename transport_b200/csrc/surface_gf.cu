@@ -227,6 +227,7 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     if (smem > 48 * 1024)
         TX_CUDA(cudaFuncSetAttribute(surface_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     surface_gf_kernel<<<p.nE, GF_THREADS, smem, st>>>(p);
+    count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }

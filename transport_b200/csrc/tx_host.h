@@ -5,6 +5,8 @@
 namespace tx {
 // Records a printf-style message for tx_last_error() (thread local) and returns `code`.
 int fail(int code, const char* fmt, ...);
+// Counts kernel launches issued by the library (tx_launch_counter()).
+void count_launch(int n = 1);
 }  // namespace tx
 
 #define TX_CUDA(call)                                                                              \
