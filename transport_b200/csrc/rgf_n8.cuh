@@ -342,47 +342,31 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             const int i0 = n8_idx(fr, fc), i1 = n8_idx(fr, fc + 4);
             const int o0 = n8_idx(fr, 2 * fc), o1 = n8_idx(fr, 2 * fc + 1);
 #pragma unroll 1
-            for (int q = 0; q < GPW; q += 2) {
-                double2 a[2][2], b[2][2];
-                double tqx[2], tqy[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const double2* wq = WB + (q + u) * N8Cfg::PSTRIDE;
-                    const double2* gq = GT + (q + u) * N8Cfg::PSTRIDE;
-                    a[u][0] = wq[i0];
-                    a[u][1] = wq[i1];
-                    b[u][0] = gq[i0];
-                    b[u][1] = gq[i1];
-                    // the hopping of point q+u (points of a warp may belong to different Hamiltonians)
-                    tqx[u] = __shfl_sync(0xffffffffu, tj.x, (q + u) * LP);
-                    tqy[u] = __shfl_sync(0xffffffffu, tj.y, (q + u) * LP);
-                }
-                double rr0[2][2] = {{0, 0}, {0, 0}}, rr1[2][2] = {{0, 0}, {0, 0}};   // Re: k-halves 0 / 1
-                double ii0[2][2] = {{0, 0}, {0, 0}}, ii1[2][2] = {{0, 0}, {0, 0}};   // Im
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    dmma_8x8x4(rr0[u], a[u][0].x, b[u][0].x);
-                    dmma_8x8x4(ii0[u], a[u][0].x, b[u][0].y);
-                    dmma_8x8x4(rr1[u], a[u][1].x, b[u][1].x);
-                    dmma_8x8x4(ii1[u], a[u][1].x, b[u][1].y);
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    dmma_8x8x4(rr0[u], -a[u][0].y, b[u][0].y);
-                    dmma_8x8x4(ii0[u], a[u][0].y, b[u][0].x);
-                    dmma_8x8x4(rr1[u], -a[u][1].y, b[u][1].y);
-                    dmma_8x8x4(ii1[u], a[u][1].y, b[u][1].x);
-                }
-                __syncwarp();   // every lane has loaded its W fragments of points q, q+1
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    double2* wo = WB + (q + u) * N8Cfg::PSTRIDE;
-                    const double x0 = rr0[u][0] + rr1[u][0], y0 = ii0[u][0] + ii1[u][0];
-                    const double x1 = rr0[u][1] + rr1[u][1], y1 = ii0[u][1] + ii1[u][1];
-                    // times conj(t): (x + iy)(tx - i ty)
-                    wo[o0] = make_double2(fma(x0, tqx[u], y0 * tqy[u]), fma(y0, tqx[u], -(x0 * tqy[u])));
-                    wo[o1] = make_double2(fma(x1, tqx[u], y1 * tqy[u]), fma(y1, tqx[u], -(x1 * tqy[u])));
-                }
+            for (int q = 0; q < GPW; ++q) {
+                const double2* wq = WB + q * N8Cfg::PSTRIDE;
+                const double2* gq = GT + q * N8Cfg::PSTRIDE;
+                const double2 a0 = wq[i0], a1 = wq[i1];
+                const double2 b0 = gq[i0], b1 = gq[i1];
+                // the hopping of point q (points of a warp may belong to different Hamiltonians)
+                const double tqx = __shfl_sync(0xffffffffu, tj.x, q * LP);
+                const double tqy = __shfl_sync(0xffffffffu, tj.y, q * LP);
+                double rr0[2] = {0.0, 0.0}, rr1[2] = {0.0, 0.0};   // Re: k-halves 0 / 1
+                double ii0[2] = {0.0, 0.0}, ii1[2] = {0.0, 0.0};   // Im
+                dmma_8x8x4(rr0, a0.x, b0.x);
+                dmma_8x8x4(ii0, a0.x, b0.y);
+                dmma_8x8x4(rr1, a1.x, b1.x);
+                dmma_8x8x4(ii1, a1.x, b1.y);
+                dmma_8x8x4(rr0, -a0.y, b0.y);
+                dmma_8x8x4(ii0, a0.y, b0.x);
+                dmma_8x8x4(rr1, -a1.y, b1.y);
+                dmma_8x8x4(ii1, a1.y, b1.x);
+                __syncwarp();   // every lane has loaded its W fragments of point q
+                double2* wo = WB + q * N8Cfg::PSTRIDE;
+                const double x0 = rr0[0] + rr1[0], y0 = ii0[0] + ii1[0];
+                const double x1 = rr0[1] + rr1[1], y1 = ii0[1] + ii1[1];
+                // times conj(t): (x + iy)(tx - i ty)
+                wo[o0] = make_double2(fma(x0, tqx, y0 * tqy), fma(y0, tqx, -(x0 * tqy)));
+                wo[o1] = make_double2(fma(x1, tqx, y1 * tqy), fma(y1, tqx, -(x1 * tqy)));
             }
             __syncwarp();
         }
@@ -390,17 +374,21 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
 
     // ------------------------------------------------------------------ epilogue (K3)
     // G_00 = g_0 in GT, G_{M-1,0} = W in WB; velocities published through PV.
-#pragma unroll
-    for (int s = 0; s < RP; ++s) PV[(row0 + s) * GPW + grp] = make_double2(vLo[s], vRo[s]);
-    __syncwarp();
-    double vL[N];
-#pragma unroll
-    for (int c = 0; c < N; ++c) vL[c] = PV[c * GPW + grp].x;
     double sqL[RP], sqR[RP];
 #pragma unroll
     for (int s = 0; s < RP; ++s) {
         sqL[s] = sqrt(vLo[s]);
         sqR[s] = sqrt(vRo[s]);
+        // (v_L, 1/sqrt(v_L)) of own channels for everybody in the group
+        PV[(row0 + s) * GPW + grp] = make_double2(vLo[s], 1.0 / sqL[s]);
+    }
+    __syncwarp();
+    double vL[N], rsL[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const double2 v = PV[c * GPW + grp];
+        vL[c] = v.x;
+        rsL[c] = v.y;
     }
 
     const int n_src = p.n_src;
@@ -431,7 +419,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
 #pragma unroll
         for (int a = 0; a < N; ++a) {
             if (full || a < n) {
-                const double rflux = 1.0 / sqrt(vL[a]);               // 1 / i_flux   (:108)
+                const double rflux = rsL[a];                           // 1 / i_flux   (:108)
                 double rr[RP], tt[RP];
 #pragma unroll
                 for (int s = 0; s < RP; ++s) {

@@ -86,13 +86,25 @@ __device__ __forceinline__ cd csign(cd z) {
 // wfm.g_closed for one channel (wfm/__init__.py:337-340):
 //   lam = (E - eps)/(2 t); g = Re(lam/t) - sign(E-eps) |Re sqrt(lam^2-1)| - i |Im sqrt(lam^2-1)|
 __device__ __forceinline__ cd g_closed_channel(cd E, cd eps, cd t) {
+    if (E.y == 0.0 && eps.y == 0.0 && t.y == 0.0) {
+        // All reference drivers: real energy, real lead parameters.  Same formula, real arithmetic
+        // (identical results: Smith division by a real divisor and csqrt of a real are exact maps).
+        const double dr = E.x - eps.x;
+        const double lam = dr / (2.0 * t.x);
+        const double first = lam / t.x;
+        const double z = __dsub_rn(__dmul_rn(lam, lam), 1.0);   // rounded product first, like numpy (no fma)
+        const double sg = (dr > 0.0) - (dr < 0.0);
+        const double root = sqrt(fabs(z));
+        return (z >= 0.0) ? mk(first - sg * root, -0.0) : mk(first, -root);
+    }
     cd d = E - eps;
     cd lam = cdiv(d, mk(2.0 * t.x, 2.0 * t.y));
     cd first = cdiv(lam, t);
-    cd sq = lam * lam;
-    sq.x -= 1.0;
-    // numpy's complex product is (ac-bd, ad+bc) without fma; lam*lam above contracts to fma.
-    // The difference is below 1 ulp of the product and far inside the 1e-10 parity gate.
+    // numpy's complex product is (ac-bd, ad+bc) with every product rounded (no fma): near a band edge
+    // lam^2-1 cancels, so the rounding order is kept identical to stay at the 1e-14 level of parity.
+    cd sq = mk(__dsub_rn(__dmul_rn(lam.x, lam.x), __dmul_rn(lam.y, lam.y)),
+               __dadd_rn(__dmul_rn(lam.x, lam.y), __dmul_rn(lam.y, lam.x)));
+    sq.x = __dsub_rn(sq.x, 1.0);
     cd root = csqrt_principal(sq);
     cd sg = csign(d);
     double ar = fabs(root.x), ai = fabs(root.y);
