@@ -181,8 +181,11 @@ def gpu_arm(args):
 
     # ---- inputs: this rank's J slice of the 1000*world grid, resident in HBM
     h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    from transport_b200 import shard
     Js_all = np.linspace(-1.0, -0.001, N_J * world)
-    Js = np.ascontiguousarray(Js_all[rank * N_J:(rank + 1) * N_J])
+    (j0, j1), _ = shard.plan(N_J * world, N_E, world, rank)      # parameter axis sharded, energies whole
+    Js = np.ascontiguousarray(Js_all[j0:j1])
+    assert len(Js) == N_J
     _, Es = configs.cfg2_grid(N_J, N_E)
     n_pts = N_J * N_E
 
@@ -353,7 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

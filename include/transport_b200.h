@@ -175,9 +175,12 @@ int tx_hsysmat(const tx_cplx* tinf, const tx_cplx* tL, const tx_cplx* tR, const 
                const tx_cplx* VL, const tx_cplx* VR, int Ninf, int NL, int NR, const tx_cplx* HC, int NC, int n,
                tx_cplx* H);
 
-/* Tuning knob for the n<=8, scalar-hopping, closed-lead kernel: 0 = 4 lanes/point capped at 168
- * registers (default), 1 = 4 lanes/point uncapped, 2/3 = 8 lanes/point at 168/128 registers.
- * All variants compute the same thing; used by bench.py --variant to compare them. */
+/* Tuning knob for the 5 <= n <= 8, scalar-hopping, closed-lead sweep (bench.py --variant):
+ *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
+ *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles
+ *   6/7  tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh), 3 CTAs/SM, smem / shuffle pivot row
+ *   8    as 6 with 2 CTAs/SM and no register cap (DEFAULT);   9  as 7 capped at 128 registers
+ * All variants compute the same thing. */
 int tx_set_variant(int variant);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device
@@ -194,7 +197,7 @@ int tx_measure_fp64_peak(double* tflops, double* milliseconds);
 /* Same for the legacy FP64 tensor path (mma.sync.m8n8k4.f64). */
 int tx_measure_dmma_peak(double* tflops, double* milliseconds);
 /* Exchange-primitive rates: which = 0 SHFL.b32, 1 LDS.128 group broadcast (1e9 warp-instr/s),
- * 2 same with a 2-way conflict, 3 DFMA:LDS 8:1 mix (TFLOP/s). */
+ * 2 same with a 2-way conflict, 3 DFMA:LDS 8:1 mix (TFLOP/s), 4 DFMA+DMMA mix with equal flops (TFLOP/s). */
 int tx_microbench(int which, double* value);
 
 #ifdef __cplusplus

@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Secondary measurements: BASELINE configs 1, 3 and 4 on one GPU (config 2 is bench.py's headline).
+
+    python scripts/bench_configs.py [cfg1] [cfg3] [cfg4] [--small]
+
+For each config: device-resident sweep timed with CUDA events (3 warm-ups, L2 flush between steps),
+parity of a subsample against the numpy oracle, roofline fraction (FP64), one JSON line each.
+"""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import rgf_oracle  # noqa: E402  (checker only)
+from transport_b200 import _lib, configs, leads  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+
+def dev_c(a):
+    return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
+
+
+def fp64_peak():
+    v, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.tx_measure_fp64_peak(ctypes.byref(v), ctypes.byref(ms)))
+    return v.value
+
+
+def timed(fn, steps=5, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.mean(ms))
+
+
+def rel_err(got, want):
+    scale = np.maximum(np.abs(want), 1e-13 * np.abs(want).max(axis=-1, keepdims=True))
+    return float(np.max(np.abs(got - want) / np.where(scale == 0, 1, scale)))
+
+
+def run_small(name, h, tnn, Es, n_src_all, flops_per_point, check_idx, steps):
+    """Closed-form leads, scalar hopping, n <= 16: tx_transmission_sweep_dev."""
+    n, M, nE = h.shape[-1], h.shape[0], len(Es)
+    d_h, d_t, d_E = dev_c(h), dev_c(tnn), dev_c(Es)
+    R = torch.empty((nE, n, n), dtype=torch.float64, device=dev)
+    T = torch.empty_like(R)
+    res = torch.empty((nE, n), dtype=torch.float64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        _lib.check(lib.tx_transmission_sweep_dev(d_h.data_ptr(), 1, None, None, d_t.data_ptr(), 1, n, M, 1,
+                                                 d_E.data_ptr(), nE, _lib.TX_LEAD_CLOSED, None, None, 1,
+                                                 _lib.TX_HOP_SCALAR, None, None, n, R.data_ptr(), T.data_ptr(),
+                                                 res.data_ptr(), None, flag.data_ptr(), st))
+    ms = timed(step, steps=steps)
+    assert int(flag.item()) == 0
+    Th = T.cpu().numpy()
+    Rh = R.cpu().numpy()
+    resid = float(np.nanmax(np.abs(res.cpu().numpy())))
+    t0 = time.perf_counter()
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es[check_idx], np.eye(n))
+    cpu_s = time.perf_counter() - t0
+    err = max(rel_err(Th[check_idx], oT), rel_err(Rh[check_idx], oR))
+    # conditioning floor: how much the ORACLE's own answer moves when E is perturbed by ~1 ulp
+    pR, pT = rgf_oracle.transmission_closed(h, tnn, Es[check_idx] * (1 + 2.2e-16), np.eye(n))
+    floor = max(rel_err(pT, oT), rel_err(pR, oR))
+    peak = fp64_peak()
+    ach = flops_per_point * nE / (ms * 1e-3) / 1e12
+    return {"config": name, "n": n, "M": M, "points": nE, "sources": n, "ms_per_sweep": ms,
+            "points_per_s": nE / (ms * 1e-3), "flops_per_point": flops_per_point,
+            "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak},
+            "parity_max_rel_err_vs_oracle": err, "oracle_change_under_1ulp_energy_perturbation": floor,
+            "checked_points": int(len(check_idx)),
+            "unitarity_max_abs": resid,
+            "cpu_oracle_rgf_numpy_points_per_s_1core": len(check_idx) / cpu_s}
+
+
+def cfg1():
+    h, tnn, _ = configs.barrier_blocks(0.4, 11)
+    Es = configs.barrier_energies(10_000)
+    return run_small("cfg1 rbbarrier n=1 M=13, 1e4 energies", h, tnn, Es, 1, 8 * 1 * 13 * 2, np.arange(0, 10_000, 97), 10)
+
+
+def cfg3(small=False):
+    N = 1000 if small else 10_000
+    nE = 10_000 if small else 100_000
+    h, tnn, _ = configs.disordered_blocks(N=N, n=8, W=0.05, seed=1234)
+    Es = np.linspace(-1.9, 1.9, nE).astype(complex)
+    idx = np.arange(0, nE, nE // 8)
+    return run_small("cfg3 disordered chain n=8 N=%d, %d energies" % (N, nE), h, tnn, Es, 8,
+                     8 * 8 ** 3 * (N + 2) * 2, idx, 3)
+
+
+def cfg4(small=False):
+    n = 32 if small else 64
+    nE = 256 if small else 4096
+    h, tnn, _ = configs.ribbon_blocks(width=n, L=32, W=1.0, seed=1234)
+    Es = np.linspace(-3.5, 3.5, nE).astype(complex)
+    eta = 1e-8
+    M = h.shape[0]
+    d_h, d_t, d_E = dev_c(h), dev_c(tnn), dev_c(Es)
+    sigL = torch.empty((nE, n, n, 2), dtype=torch.float64, device=dev)
+    sigR = torch.empty_like(sigL)
+    nit = torch.zeros((2, nE), dtype=torch.int32, device=dev)
+    ok = torch.zeros((2, nE), dtype=torch.int32, device=dev)
+    conv = torch.zeros((2, nE), dtype=torch.float64, device=dev)
+    car = torch.empty(nE, dtype=torch.float64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    wse = int(lib.tx_sweep_workspace_elems(n, nE))
+    work = torch.empty((max(wse, 1), 2), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    nn16 = n * n * 16
+
+    def leads_step():
+        _lib.check(lib.tx_surface_gf_dev(d_h.data_ptr(), d_t.data_ptr(), n, d_E.data_ptr(), nE, -1, _lib.TX_GF_SANCHO,
+                                         eta, 1e-14, 0, 0, 200, None, sigL.data_ptr(), nit[0].data_ptr(),
+                                         conv[0].data_ptr(), ok[0].data_ptr(), flag.data_ptr(), st))
+        _lib.check(lib.tx_surface_gf_dev(d_h.data_ptr() + (M - 1) * nn16, d_t.data_ptr() + (M - 2) * nn16, n,
+                                         d_E.data_ptr(), nE, 1, _lib.TX_GF_SANCHO, eta, 1e-14, 0, 0, 200, None,
+                                         sigR.data_ptr(), nit[1].data_ptr(), conv[1].data_ptr(), ok[1].data_ptr(),
+                                         flag.data_ptr(), st))
+
+    def sweep_step():
+        _lib.check(lib.tx_transmission_sweep_large_dev(d_h.data_ptr(), 1, None, None, d_t.data_ptr(), 1, n, M, 1,
+                                                       d_E.data_ptr(), nE, sigL.data_ptr(), sigR.data_ptr(), 1,
+                                                       _lib.TX_HOP_SCALAR, None, n, None, None, None, None,
+                                                       car.data_ptr(), work.data_ptr() if wse else None,
+                                                       flag.data_ptr(), st))
+    ms_leads = timed(leads_step, steps=2, warmup=1)
+    ms_sweep = timed(sweep_step, steps=2, warmup=1)
+    assert bool(ok.all().item()), "Sancho-Rubio did not converge everywhere"
+    n_it = float(nit.double().mean().item())
+    carh = car.cpu().numpy()
+    idx = np.arange(0, nE, max(1, nE // 6))
+    SL = torch.view_as_complex(sigL[idx]).cpu().numpy()
+    SR = torch.view_as_complex(sigR[idx]).cpu().numpy()
+    _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es[idx], SL, SR)        # same tables on both sides
+    want = rgf_oracle.caroli_trace(GN0, SL, SR)
+    err = float(np.max(np.abs(carh[idx] - want) / np.maximum(np.abs(want), 1e-12)))
+    flops = 8 * n ** 3 * M * 2 + 2 * n_it * (8 + 6 * 8) * n ** 3
+    peak = fp64_peak()
+    ms = ms_leads + ms_sweep
+    ach = flops * nE / (ms * 1e-3) / 1e12
+    return {"config": "cfg4 ribbon n=%d L=32, %d energies, Sancho-Rubio eta=1e-8" % (n, nE), "n": n, "M": M,
+            "points": nE, "ms_leads": ms_leads, "ms_sweep": ms_sweep, "points_per_s": nE / (ms * 1e-3),
+            "sancho_iterations_mean": n_it, "flops_per_point": flops,
+            "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak},
+            "parity_caroli_max_rel_err_vs_oracle_same_tables": err, "checked_points": int(len(idx)),
+            "kernel": "generic CTA-per-point (not yet DMMA-tiled)"}
+
+
+if __name__ == "__main__":
+    small = "--small" in sys.argv
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3", "cfg4"]
+    for w in which:
+        out = {"cfg1": cfg1, "cfg3": lambda: cfg3(small), "cfg4": lambda: cfg4(small)}[w]()
+        print(json.dumps(out), flush=True)

@@ -15,7 +15,7 @@ out["dfma_tflops"] = v.value
 _lib.check(lib.tx_measure_dmma_peak(ctypes.byref(v), ctypes.byref(ms)))
 out["dmma_m8n8k4_tflops"] = v.value
 for which, name in ((0, "shfl_b32_Gwarpinstr_s"), (1, "lds128_groupbcast_Gwarpinstr_s"),
-                    (2, "lds128_groupbcast_2way_Gwarpinstr_s"), (3, "dfma_lds_8to1_mix_tflops")):
+                    (2, "lds128_groupbcast_2way_Gwarpinstr_s"), (3, "dfma_lds_8to1_mix_tflops"), (4, "dfma_plus_dmma_equal_flops_mix_tflops")):
     _lib.check(lib.tx_microbench(which, ctypes.byref(v)))
     out[name] = v.value
 print(json.dumps(out))

@@ -86,6 +86,7 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     assert rc == _lib.TX_ERR_ARG
     assert lib.tx_set_variant(77) == _lib.TX_ERR_ARG
     assert lib.tx_set_variant(0) == _lib.TX_OK
+    assert lib.tx_set_variant(8) == _lib.TX_OK
 
 
 def test_ricemele_helpers_match_golden_parameters():

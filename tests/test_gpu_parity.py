@@ -408,3 +408,38 @@ def test_ribbon_sancho_leads_cfg4_downscaled():
             eps = np.linalg.eigvalsh(h[0].real)
             open_ch = np.array([np.sum(np.abs(E.real - eps) < 2.0) for E in Es])
             assert np.allclose(car[0], open_ch, atol=1e-4)      # clean ribbon: T = number of open channels
+
+
+def test_all_kernel_variants_agree():
+    """Every tuning variant of the n=8 sweep (register-resident, shuffle pivot, DMMA) gives the golden answer;
+    the DMMA kernel is also exercised with padding (n=5..7), table leads and mixed Hamiltonians per warp."""
+    lib = _lib.load()
+    g = load_golden("cfg2_cicc.npz")
+    try:
+        for v in range(10):
+            _lib.check(lib.tx_set_variant(v))
+            R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], want_resid=True)
+            _check(R, T, g["R"], g["T"], res)
+    finally:
+        _lib.check(lib.tx_set_variant(8))
+    rng = np.random.default_rng(3)
+    for n in (5, 6, 7, 8):
+        M = 6
+        P = 3
+        A = rng.standard_normal((P, M, n, n)) + 1j * rng.standard_normal((P, M, n, n))
+        h = 0.3 * (A + np.conj(np.swapaxes(A, 2, 3))) / 2
+        h[:, 0] = 0
+        h[:, -1] = 0
+        tnn = -np.tile(np.eye(n, dtype=complex), (P, M - 1, 1, 1)) * np.array([1.0, 0.8, 1.1])[:, None, None, None]
+        tnn[:, 0] = -np.eye(n)
+        tnn[:, -1] = -np.eye(n)
+        Es = np.linspace(-1.6, 1.5, 5).astype(complex)     # 5 energies: warps mix Hamiltonians
+        R, T = transmission_sweep(h, tnn, Es)
+        for p in range(P):
+            oR, oT = rgf_oracle.transmission_closed(h[p], tnn[p], Es, np.eye(n))
+            _check(R[p], T[p], oR, oT)
+        SL, SR = rgf_oracle.closed_selfenergies(h[0], tnn[0], Es)
+        R2, T2 = transmission_sweep(h, tnn, Es, "table", sigL=SL, sigR=SR, sources=np.eye(n)[:2])
+        for p in range(P):
+            oR, oT = rgf_oracle.transmission_closed(h[p], tnn[p], Es, np.eye(n)[:2])
+            _check(R2[p], T2[p], oR, oT)

@@ -65,7 +65,7 @@ int round_up_block(int n) {
 
 // Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
 // number of resident 128-thread blocks per SM the register allocation is capped for.
-int g_variant = 0;
+int g_variant = 8;
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -281,16 +281,22 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
         case 2: return dispatch_modes<2, 1, 4, 4>(p, hop, lead, st);
         case 4: return dispatch_modes<4, 2, 3, 3>(p, hop, lead, st);
         case 8:
-            if (hop == HOP_SCALAR && lead == LEAD_CLOSED) {
-                if (g_variant == 1) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
-                if (g_variant == 2) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
-                if (g_variant == 3) return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
-                if (g_variant == 6) return launch_n8<LEAD_CLOSED, 3, 0>(p, st);
-                if (g_variant == 7) return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
-                if (g_variant == 8) return launch_n8<LEAD_CLOSED, 2, 0>(p, st);
-                if (g_variant == 9) return launch_n8<LEAD_CLOSED, 4, 1>(p, st);
-                if (g_variant == 4) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
-                if (g_variant == 5) return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
+            if (hop == HOP_SCALAR) {
+                // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
+                // register-resident template reachable for A/B measurements (bench.py --variant)
+                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 2, 0>(p, st);
+                switch (g_variant) {
+                    case 0: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
+                    case 1: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
+                    case 2: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
+                    case 3: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
+                    case 4: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
+                    case 5: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
+                    case 6: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);
+                    case 7: return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
+                    case 9: return launch_n8<LEAD_CLOSED, 4, 1>(p, st);
+                    default: return launch_n8<LEAD_CLOSED, 2, 0>(p, st);   // 8 (default)
+                }
             }
             return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
         case 16: return dispatch_modes<16, 16, 3, 2>(p, hop, lead, st);

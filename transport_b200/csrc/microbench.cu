@@ -44,6 +44,38 @@ __global__ void __launch_bounds__(256) dmma_loop(double* out, double a, double b
     if (s == 123.456) out[0] = s;
 }
 
+// DFMA and DMMA issued back to back from the same warp: do the two FP64 paths share one pipe?
+__global__ void __launch_bounds__(256) dfma_dmma_loop(double* out, double a, double b) {
+    double c[4][2];
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = threadIdx.x + i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = a + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+            x[2 * i] = fma(x[2 * i], b, a);
+            x[2 * i + 1] = fma(x[2 * i + 1], b, a);
+            x[(2 * i + 2) & 7] = fma(x[(2 * i + 2) & 7], b, a);
+            x[(2 * i + 3) & 7] = fma(x[(2 * i + 3) & 7], b, a);
+            x[(2 * i + 4) & 7] = fma(x[(2 * i + 4) & 7], b, a);
+            x[(2 * i + 5) & 7] = fma(x[(2 * i + 5) & 7], b, a);
+            x[(2 * i + 6) & 7] = fma(x[(2 * i + 6) & 7], b, a);
+            x[(2 * i + 7) & 7] = fma(x[(2 * i + 7) & 7], b, a);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) shfl_loop(double* out) {
     unsigned x[8];
 #pragma unroll
@@ -193,6 +225,10 @@ int tx_microbench(int which, double* value) {
         const int stride = which == 1 ? 8 : 4;
         rc = time_kernel([&] { lds_bcast_loop<<<blocks, threads>>>(d, stride); }, &ms);
         *value = 8.0 * ITERS * warps / (ms * 1e-3) / 1e9;
+    } else if (which == 4) {
+        // 4 DMMA (256 FMA each per warp) + 32 DFMA (32 FMA each per warp) per iteration
+        rc = time_kernel([&] { dfma_dmma_loop<<<blocks, threads>>>(d, 1.0000001, 0.9999999); }, &ms);
+        *value = 2.0 * (4.0 * 256.0 + 32.0 * 32.0) * ITERS * warps / (ms * 1e-3) / 1e12;
     } else if (which == 3) {
         rc = time_kernel([&] { mix_loop<<<blocks, threads>>>(d, 1.0000001, 0.5); }, &ms);
         *value = 2.0 * 32.0 * ITERS * warps * 32 / (ms * 1e-3) / 1e12;
