@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -312,9 +312,9 @@ def gpu_arm(args):
         cores = os.cpu_count() or 1
         with mp.get_context("fork").Pool(cores) as pool:
             run_cpu_sample(pool, cores, 1, offset=99)
-            rate, wall = run_cpu_sample(pool, cores, 250, offset=0)
+            rate, wall = run_cpu_sample(pool, cores, 500, offset=0)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d random (J,E) points of the same grid x 8 sources, %.1f s wall" % (cores * 250, wall)}
+               "sample": "%d random (J,E) points of the same grid x 8 sources, %.1f s wall" % (cores * 500, wall)}
 
     if rank == 0:
         peaks = {}
@@ -324,6 +324,12 @@ def gpu_arm(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("rgf_sweep_n8_bytes_per_launch")
+        except Exception:
+            pass
         achieved_tf = FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
         achieved_gbs = BYTES_PER_POINT * n_pts / (k_ms * 1e-3) / 1e9
         line = {
@@ -335,7 +341,8 @@ def gpu_arm(args):
                        "parallelism": "J axis sharded, dp%d" % world},
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak, "traffic": None,
+                         "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                         "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written per launch)",
                          "peak_source": "tx_measure_fp64_peak: register-resident DFMA loop, measured in this run "
                                         "(MEASURED_PEAKS.json carries no FP64 figure)",
                          "flops_per_point": FLOPS_PER_POINT, "kernel_ms": k_ms,

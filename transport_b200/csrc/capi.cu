@@ -49,6 +49,8 @@ struct DevBuf {
 struct Workspace {
     DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, caroli, big, flag;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     int device = -1;
 };
 std::mutex g_ws_mutex;
@@ -438,15 +440,43 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     TX_CUDA(cudaMemsetAsync(ws.flag.ptr, 0, sizeof(int), st));
 
     const bool large = (n > 16) || (caroli != nullptr);
+    bool copied_out = false;
     if (!large) {
-        rc = tx_transmission_sweep_dev(
-            (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
-            (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE, lead_mode,
-            bytes_sig ? (const tx_cplx*)ws.sigL.ptr : nullptr, bytes_sig ? (const tx_cplx*)ws.sigR.ptr : nullptr, n_sig,
-            hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src, (double*)ws.R.ptr,
-            (double*)ws.T.ptr, bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
-            (int*)ws.flag.ptr, st);
-        if (rc) return rc;
+        // Chunk the Hamiltonian axis so that the device->host copy of chunk c overlaps the sweep of
+        // chunk c+1 (two streams, one event per chunk).  The results dominate the PCIe traffic.
+        const size_t per_ham_out = (size_t)nE * n_src * n * sizeof(double);
+        int n_chunks = 1;
+        if (n_ham >= 8 && (size_t)n_ham * per_ham_out > ((size_t)32 << 20)) n_chunks = n_ham >= 64 ? 16 : 4;
+        if (!ws.copy_stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.copy_stream, cudaStreamNonBlocking));
+        if (!ws.ev[0])
+            for (int i = 0; i < 2; ++i) TX_CUDA(cudaEventCreateWithFlags(&ws.ev[i], cudaEventDisableTiming));
+        const size_t h_ham = (size_t)M * nn, t_ham = (size_t)(M - 1) * nn, s_ham = (size_t)nE * nn;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int p0 = (int)((long long)n_ham * c / n_chunks), p1 = (int)((long long)n_ham * (c + 1) / n_chunks);
+            const int np_ = p1 - p0;
+            if (np_ <= 0) continue;
+            const size_t o_pts = (size_t)p0 * nE;
+            rc = tx_transmission_sweep_dev(
+                (const tx_cplx*)ws.h.ptr + (n_h > 1 ? p0 * h_ham : 0), n_h > 1 ? np_ : 1,
+                h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr + p0 : nullptr,
+                (const tx_cplx*)ws.tnn.ptr + (n_t > 1 ? p0 * t_ham : 0), n_t > 1 ? np_ : 1, n, M, np_,
+                (const tx_cplx*)ws.E.ptr, nE, lead_mode,
+                bytes_sig ? (const tx_cplx*)ws.sigL.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr,
+                bytes_sig ? (const tx_cplx*)ws.sigR.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr, n_sig > 1 ? np_ : 1,
+                hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src,
+                (double*)ws.R.ptr + o_pts * n_src * n, (double*)ws.T.ptr + o_pts * n_src * n,
+                bytes_res ? (double*)ws.resid.ptr + o_pts * n_src : nullptr,
+                t_total ? (double*)ws.ttot.ptr + o_pts : nullptr, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+            cudaEvent_t ev = ws.ev[c & 1];
+            TX_CUDA(cudaEventRecord(ev, st));
+            TX_CUDA(cudaStreamWaitEvent(ws.copy_stream, ev, 0));
+            const size_t ob = (size_t)np_ * per_ham_out;
+            TX_CUDA(cudaMemcpyAsync(R + o_pts * n_src * n, (double*)ws.R.ptr + o_pts * n_src * n, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+            TX_CUDA(cudaMemcpyAsync(T + o_pts * n_src * n, (double*)ws.T.ptr + o_pts * n_src * n, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+        }
+        TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
+        copied_out = true;
     } else {
         // generic-size path (n <= 64): self-energy tables first (K1), then one CTA per point
         int n_sig_use = n_sig;
@@ -492,8 +522,10 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     }
 
     int flag = 0;
-    TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
-    TX_CUDA(cudaMemcpyAsync(T, ws.T.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+    if (!copied_out) {
+        TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+        TX_CUDA(cudaMemcpyAsync(T, ws.T.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+    }
     if (bytes_res) TX_CUDA(cudaMemcpyAsync(resid, ws.resid.ptr, bytes_res, cudaMemcpyDeviceToHost, st));
     if (t_total) TX_CUDA(cudaMemcpyAsync(t_total, ws.ttot.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
     TX_CUDA(cudaMemcpyAsync(&flag, ws.flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
