@@ -179,7 +179,9 @@ int tx_hsysmat(const tx_cplx* tinf, const tx_cplx* tL, const tx_cplx* tR, const 
  *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
  *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles
  *   6/7  tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh), 3 CTAs/SM, smem / shuffle pivot row
- *   8    as 6 with 2 CTAs/SM and no register cap (DEFAULT);   9  as 7 capped at 128 registers
+ *   8    as 6 with 2 CTAs/SM and no register cap;   9  as 8 with the eight products of a warp issued
+ *        back to back before one barrier (DEFAULT);   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
+ *        that skip the products / the inversion (WRONG results, measurement only)
  * All variants compute the same thing. */
 int tx_set_variant(int variant);
 

@@ -18,4 +18,7 @@ for which, name in ((0, "shfl_b32_Gwarpinstr_s"), (1, "lds128_groupbcast_Gwarpin
                     (2, "lds128_groupbcast_2way_Gwarpinstr_s"), (3, "dfma_lds_8to1_mix_tflops"), (4, "dfma_plus_dmma_equal_flops_mix_tflops")):
     _lib.check(lib.tx_microbench(which, ctypes.byref(v)))
     out[name] = v.value
+for w in (10, 11, 12, 13):
+    _lib.check(lib.tx_microbench(w, ctypes.byref(v)))
+    out["dfma_tflops_%d_warps_per_scheduler" % (w - 9)] = v.value
 print(json.dumps(out))

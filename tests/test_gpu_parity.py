@@ -416,12 +416,12 @@ def test_all_kernel_variants_agree():
     lib = _lib.load()
     g = load_golden("cfg2_cicc.npz")
     try:
-        for v in range(10):
+        for v in range(11):
             _lib.check(lib.tx_set_variant(v))
             R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], want_resid=True)
             _check(R, T, g["R"], g["T"], res)
     finally:
-        _lib.check(lib.tx_set_variant(8))
+        _lib.check(lib.tx_set_variant(9))
     rng = np.random.default_rng(3)
     for n in (5, 6, 7, 8):
         M = 6

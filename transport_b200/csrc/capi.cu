@@ -67,7 +67,7 @@ int round_up_block(int n) {
 
 // Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
 // number of resident 128-thread blocks per SM the register allocation is capped for.
-int g_variant = 8;
+int g_variant = 9;
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -94,7 +94,7 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
 // grow-only per-device buffer for expanded affine Hamiltonian families (tx_transmission_sweep_dev)
 DevBuf g_expand[16];
 
-template <int LEAD, int MINB, int PIVX>
+template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
 int launch_n8(SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
     if (p.h1) {
@@ -120,13 +120,13 @@ int launch_n8(SweepParams p, cudaStream_t st) {
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8<LEAD, MINB, PIVX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8<LEAD, MINB, PIVX, DMB, EXPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
     const long long per_block = (long long)WARPS * 8;
     const long long blocks = (p.n_pts + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8<LEAD, MINB, PIVX><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    rgf_sweep_n8<LEAD, MINB, PIVX, DMB, EXPER><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
@@ -173,7 +173,7 @@ int tx_device_synchronize(void) {
 long long tx_launch_counter(void) { return g_launches.load(); }
 
 int tx_set_variant(int v) {
-    if (v < 0 || v > 9) return fail(TX_ERR_ARG, "variant must be 0..9");
+    if (v < 0 || v > 15) return fail(TX_ERR_ARG, "variant must be 0..15");
     g_variant = v;
     return TX_OK;
 }
@@ -249,6 +249,7 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     if (!aligned16(h) || !aligned16(tnn) || !aligned16(E) || (h1 && !aligned16(h1)) ||
         (sigL && !aligned16(sigL)) || (sigR && !aligned16(sigR)))
         return fail(TX_ERR_ARG, "complex arrays must be 16-byte aligned");
+    if (!aligned16(R) || !aligned16(T)) return fail(TX_ERR_ARG, "R and T must be 16-byte aligned");
     const int N = round_up_block(n);
     if (N == 0) return fail(TX_ERR_UNSUPPORTED, "block size n=%d > 16 not covered by the small-block sweep", n);
 
@@ -286,7 +287,7 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
             if (hop == HOP_SCALAR) {
                 // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
                 // register-resident template reachable for A/B measurements (bench.py --variant)
-                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 2, 0>(p, st);
+                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 2, 0, 8>(p, st);
                 switch (g_variant) {
                     case 0: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
                     case 1: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
@@ -296,8 +297,11 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
                     case 5: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
                     case 6: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);
                     case 7: return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
-                    case 9: return launch_n8<LEAD_CLOSED, 4, 1>(p, st);
-                    default: return launch_n8<LEAD_CLOSED, 2, 0>(p, st);   // 8 (default)
+                    case 10: return launch_n8<LEAD_CLOSED, 3, 0, 8>(p, st);
+                    case 11: return launch_n8<LEAD_CLOSED, 2, 0, 1, 1>(p, st);   // timing experiment: no products (wrong results)
+                    case 12: return launch_n8<LEAD_CLOSED, 2, 0, 1, 2>(p, st);   // timing experiment: no inversion (wrong results)
+                    case 8: return launch_n8<LEAD_CLOSED, 2, 0>(p, st);
+                    default: return launch_n8<LEAD_CLOSED, 2, 0, 8>(p, st);   // 9 (default)
                 }
             }
             return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);

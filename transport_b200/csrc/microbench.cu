@@ -229,6 +229,12 @@ int tx_microbench(int which, double* value) {
         // 4 DMMA (256 FMA each per warp) + 32 DFMA (32 FMA each per warp) per iteration
         rc = time_kernel([&] { dfma_dmma_loop<<<blocks, threads>>>(d, 1.0000001, 0.9999999); }, &ms);
         *value = 2.0 * (4.0 * 256.0 + 32.0 * 32.0) * ITERS * warps / (ms * 1e-3) / 1e12;
+    } else if (which >= 10 && which < 20) {
+        // DFMA peak at reduced occupancy: (which-10+1) warps per scheduler, 16 independent chains per thread
+        const int wps = which - 10 + 1;
+        const int thr = 128, blk = sm_count() * wps;       // wps blocks of 4 warps per SM
+        rc = time_kernel([&] { dfma_loop<<<blk, thr>>>(d, 1.0000001, 0.9999999); }, &ms);
+        *value = 2.0 * 16.0 * ITERS * (double)blk * thr / (ms * 1e-3) / 1e12;
     } else if (which == 3) {
         rc = time_kernel([&] { mix_loop<<<blocks, threads>>>(d, 1.0000001, 0.5); }, &ms);
         *value = 2.0 * 32.0 * ITERS * warps * 32 / (ms * 1e-3) / 1e12;

@@ -62,14 +62,23 @@ __device__ __forceinline__ unsigned n8_key(double2 a, int row, bool is_used) {
     return is_used ? 0u : k;
 }
 
+// Scheduling fence for one column of the block: the compiler may not move arithmetic on these four
+// registers across it, and it is ordered with the shuffles / shared-memory operations around it.
+// Warps issue in order, so WHERE an instruction sits decides what overlaps with what; these fences
+// pin chunks of independent column updates right behind each long-latency operation.
+#define TX_PIN_COL(A, c) \
+    asm volatile("" : "+d"(A[0][c].x), "+d"(A[0][c].y), "+d"(A[1][c].x), "+d"(A[1][c].y))
+
 // In-place inverse of the 8x8 block (rows spread over 4 lanes, 2 per lane); result scattered
 // transposed into GT of the own point.  Same algorithm as invert_to_smem (Gauss-Jordan, implicit
-// partial pivoting, unscaled pivot rows), software-pipelined: the pivot search, the broadcast of
-// the pivot element and its reciprocal for step k+1 are issued as soon as column k+1 has been
-// updated in step k, so their latency hides behind the remaining column updates.
+// partial pivoting, unscaled pivot rows), software-pipelined by hand: within step k the search for
+// pivot k+1 (two butterfly shuffles), the broadcast of the pivot element, the publication of the
+// next pivot row and its reload are interleaved with the column updates of step k, and the
+// reciprocal of pivot k+1 is computed while that reload is in flight.
 template <int PIVX>
-__device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular) {
-    constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
+__device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular,
+                                          unsigned zmask) {
+    constexpr int N = 8, LP = 4, GPW = 8;
     const int lane = threadIdx.x & 31;
     const int gbase = lane & ~(LP - 1);
     unsigned perm = 0u;               // nibble k = pivot row of step k
@@ -77,27 +86,19 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
     int krow0 = 0, krow1 = 0;
     double2 dinv0 = make_double2(0.0, 0.0), dinv1 = make_double2(0.0, 0.0);
 
-    // pivot of step 0
-    unsigned key = max(n8_key(A[0][0], row0, false), n8_key(A[1][0], row0 + 1, false));
-    key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
-    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
-    int prow = 15 - (int)(key & 0xFu);
-    if ((key >> 5) == 0u) *singular = 1;
-    double2 pe;
-    {
-        const double2 v = (prow & 1) ? A[1][0] : A[0][0];
-        pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
-        pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
-    }
-    double2 inv = fast_crecip(pe);
+    // `zmask` is a run-time zero: OR-ing (bits & zmask) into a shuffle result makes its first use
+    // truly depend on the last update of a chunk, which is the only way to keep ptxas from
+    // scheduling that use (and the stall on the shuffle) in front of the independent updates.
+    auto after = [&](unsigned x, const double2& a, const double2& b) -> unsigned {
+        return x | (((unsigned)__double2hiint(a.y) ^ (unsigned)__double2hiint(b.y)) & zmask);
+    };
 
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        perm |= (unsigned)prow << (4 * k);
-        const bool isp0 = (row0 == prow), isp1 = (row0 + 1 == prow);
-
-        // ---- pivot row to every lane of the group
-        double2 pr[N];
+    auto update_col = [&](int c, const double2 m0, const double2 m1, const double2 prc) {
+        cfms2(A[0][c], m0, prc);
+        cfms2(A[1][c], m1, prc);
+    };
+    // pivot row of step k -> pr[c], c != k
+    auto fetch_pivot_row = [&](int k, int prow, double2 (&pr)[N]) {
         if (PIVX == 1) {
             const int src = gbase | (prow >> 1);
             const bool second = prow & 1;
@@ -110,12 +111,12 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
             }
         } else {
             double2* pb = pv + (k & 1) * N * GPW;     // double-buffered: one __syncwarp per step
-            if (isp0) {
+            if (row0 == prow) {
 #pragma unroll
                 for (int c = 0; c < N; ++c)
                     if (c != k) pb[c * GPW + grp] = A[0][c];
             }
-            if (isp1) {
+            if (row0 + 1 == prow) {
 #pragma unroll
                 for (int c = 0; c < N; ++c)
                     if (c != k) pb[c * GPW + grp] = A[1][c];
@@ -125,36 +126,83 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
             for (int c = 0; c < N; ++c)
                 if (c != k) pr[c] = pb[c * GPW + grp];
         }
+    };
 
-        // multipliers (0 for the pivot row itself)
-        const double2 m0 = cmul2(A[0][k], isp0 ? make_double2(0.0, 0.0) : inv);
+    // ---- pivot of step 0
+    unsigned key = max(n8_key(A[0][0], row0, false), n8_key(A[1][0], row0 + 1, false));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
+    key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+    int prow = 15 - (int)(key & 0xFu);
+    if ((key >> 5) == 0u) *singular = 1;
+    double2 pe;
+    {
+        const double2 v = (prow & 1) ? A[1][0] : A[0][0];
+        pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
+        pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
+    }
+    double2 pr[N];
+    fetch_pivot_row(0, prow, pr);
+    double2 inv = fast_crecip(pe);
+
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        perm |= (unsigned)prow << (4 * k);
+        const bool isp0 = (row0 == prow), isp1 = (row0 + 1 == prow);
+        const double2 m0 = cmul2(A[0][k], isp0 ? make_double2(0.0, 0.0) : inv);   // 0 for the pivot row itself
         const double2 m1 = cmul2(A[1][k], isp1 ? make_double2(0.0, 0.0) : inv);
         if (isp0) { used0 = true; krow0 = k; dinv0 = inv; }
         if (isp1) { used1 = true; krow1 = k; dinv1 = inv; }
 
-        // ---- look ahead: finish column k+1 first, then start the search for the next pivot
         if (k + 1 < N) {
-            cfms2(A[0][k + 1], m0, pr[k + 1]);
-            cfms2(A[1][k + 1], m1, pr[k + 1]);
+            // the columns other than k and k+1, in three chunks
+            int rest[6];
+            {
+                int cnt = 0;
+#pragma unroll
+                for (int c = 0; c < N; ++c)
+                    if (c != k && c != k + 1) rest[cnt++] = c;
+            }
+            // column k+1 first, then start the search for the next pivot
+            update_col(k + 1, m0, m1, pr[k + 1]);
             key = max(n8_key(A[0][k + 1], row0, used0), n8_key(A[1][k + 1], row0 + 1, used1));
-            key = max(key, __shfl_xor_sync(0xffffffffu, key, 2));
-            key = max(key, __shfl_xor_sync(0xffffffffu, key, 1));
+            unsigned other = __shfl_xor_sync(0xffffffffu, key, 2);
+            TX_PIN_COL(A, rest[0]); TX_PIN_COL(A, rest[1]);
+            update_col(rest[0], m0, m1, pr[rest[0]]);
+            update_col(rest[1], m0, m1, pr[rest[1]]);
+            TX_PIN_COL(A, rest[0]); TX_PIN_COL(A, rest[1]);
+            other = after(other, A[0][rest[1]], A[1][rest[1]]);   // first use of the shuffle result: behind the chunk
+            key = max(key, other);
+            other = __shfl_xor_sync(0xffffffffu, key, 1);
+            TX_PIN_COL(A, rest[2]); TX_PIN_COL(A, rest[3]);
+            update_col(rest[2], m0, m1, pr[rest[2]]);
+            update_col(rest[3], m0, m1, pr[rest[3]]);
+            TX_PIN_COL(A, rest[2]); TX_PIN_COL(A, rest[3]);
+            other = after(other, A[0][rest[3]], A[1][rest[3]]);
+            key = max(key, other);
             prow = 15 - (int)(key & 0xFu);
             if ((key >> 5) == 0u) *singular = 1;
-            const double2 v = (prow & 1) ? A[1][k + 1] : A[0][k + 1];
-            pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
-            pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
-        }
-        // ---- remaining columns (independent of the shuffles above)
-#pragma unroll
-        for (int c = 0; c < N; ++c)
-            if (c != k && c != k + 1) {
-                cfms2(A[0][c], m0, pr[c]);
-                cfms2(A[1][c], m1, pr[c]);
+            {
+                const double2 v = (prow & 1) ? A[1][k + 1] : A[0][k + 1];
+                pe.x = __shfl_sync(0xffffffffu, v.x, gbase | (prow >> 1));
+                pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
             }
-        A[0][k] = make_double2((isp0 ? 1.0 : 0.0) - m0.x, -m0.y);
-        A[1][k] = make_double2((isp1 ? 1.0 : 0.0) - m1.x, -m1.y);
-        if (k + 1 < N) inv = fast_crecip(pe);
+            TX_PIN_COL(A, rest[4]); TX_PIN_COL(A, rest[5]);
+            update_col(rest[4], m0, m1, pr[rest[4]]);
+            update_col(rest[5], m0, m1, pr[rest[5]]);
+            A[0][k] = make_double2((isp0 ? 1.0 : 0.0) - m0.x, -m0.y);
+            A[1][k] = make_double2((isp1 ? 1.0 : 0.0) - m1.x, -m1.y);
+            TX_PIN_COL(A, rest[4]); TX_PIN_COL(A, rest[5]); TX_PIN_COL(A, k);
+            // publish / reload the next pivot row; its reciprocal is computed while the loads fly
+            fetch_pivot_row(k + 1, prow, pr);
+            asm volatile("" : "+d"(pe.x), "+d"(pe.y));
+            inv = fast_crecip(pe);
+        } else {
+#pragma unroll
+            for (int c = 0; c < N; ++c)
+                if (c != k) update_col(c, m0, m1, pr[c]);
+            A[0][k] = make_double2((isp0 ? 1.0 : 0.0) - m0.x, -m0.y);
+            A[1][k] = make_double2((isp1 ? 1.0 : 0.0) - m1.x, -m1.y);
+        }
     }
 
     // inv[krow][col] -> GT(row = col, col = krow):  element index col*8 + (krow ^ 5*(col&1))
@@ -168,7 +216,7 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
     __syncwarp();
 }
 
-template <int LEAD, int MINB, int PIVX>
+template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
     extern __shared__ double2 smem_all[];
@@ -228,6 +276,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         }
     }
 
+    const unsigned zmask = (unsigned)(p.n_pts >> 62);   // run-time zero (see n8_invert)
     double2 A[RP][N];
     // Rows of the NEXT site's on-site block: the loads are issued right after the inverse has been
     // scattered (A is dead then) so that their L2 latency hides behind the tensor-core phase.
@@ -319,7 +368,15 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         }
 
         __syncwarp();   // all reads of g_{j+1} (own rows above, fragments below in the previous site) are done
-        n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular);
+        if (EXPER == 2) {   // timing experiment only: no inversion, A is scattered as if it were g
+#pragma unroll
+            for (int s = 0; s < RP; ++s)
+#pragma unroll
+                for (int c = 0; c < N; ++c) gt[n8_idx(c, row0 + s)] = A[s][c];
+            __syncwarp();
+        } else {
+            n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular, zmask);
+        }
         if (j > 0) fetch_rows(j - 1);
 
         if (j == M - 1) {
@@ -335,12 +392,46 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 }
             }
             __syncwarp();
-        } else {
+        } else if (EXPER != 1) {
             // W <- conj(t_j) (W g_j): eight DMMA per point, the whole warp on two points at a time
             // (8 independent accumulator chains of length 2 hide the tensor-pipe latency)
             const int fr = lane >> 2, fc = lane & 3;
             const int i0 = n8_idx(fr, fc), i1 = n8_idx(fr, fc + 4);
             const int o0 = n8_idx(fr, 2 * fc), o1 = n8_idx(fr, 2 * fc + 1);
+            if (DMB == 8) {
+                // all eight points in flight: products kept in registers, one barrier, then the stores
+                double2 out0[GPW], out1[GPW];
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    const double2* wq = WB + q * N8Cfg::PSTRIDE;
+                    const double2* gq = GT + q * N8Cfg::PSTRIDE;
+                    const double2 a0 = wq[i0], a1 = wq[i1];
+                    const double2 b0 = gq[i0], b1 = gq[i1];
+                    const double tqx = __shfl_sync(0xffffffffu, tj.x, q * LP);
+                    const double tqy = __shfl_sync(0xffffffffu, tj.y, q * LP);
+                    double rr0[2] = {0.0, 0.0}, rr1[2] = {0.0, 0.0};
+                    double ii0[2] = {0.0, 0.0}, ii1[2] = {0.0, 0.0};
+                    dmma_8x8x4(rr0, a0.x, b0.x);
+                    dmma_8x8x4(ii0, a0.x, b0.y);
+                    dmma_8x8x4(rr1, a1.x, b1.x);
+                    dmma_8x8x4(ii1, a1.x, b1.y);
+                    dmma_8x8x4(rr0, -a0.y, b0.y);
+                    dmma_8x8x4(ii0, a0.y, b0.x);
+                    dmma_8x8x4(rr1, -a1.y, b1.y);
+                    dmma_8x8x4(ii1, a1.y, b1.x);
+                    const double x0 = rr0[0] + rr1[0], y0 = ii0[0] + ii1[0];
+                    const double x1 = rr0[1] + rr1[1], y1 = ii0[1] + ii1[1];
+                    out0[q] = make_double2(fma(x0, tqx, y0 * tqy), fma(y0, tqx, -(x0 * tqy)));
+                    out1[q] = make_double2(fma(x1, tqx, y1 * tqy), fma(y1, tqx, -(x1 * tqy)));
+                }
+                __syncwarp();   // every lane has loaded all its W fragments
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    double2* wo = WB + q * N8Cfg::PSTRIDE;
+                    wo[o0] = out0[q];
+                    wo[o1] = out1[q];
+                }
+            } else {
 #pragma unroll 1
             for (int q = 0; q < GPW; ++q) {
                 const double2* wq = WB + q * N8Cfg::PSTRIDE;
@@ -367,6 +458,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 // times conj(t): (x + iy)(tx - i ty)
                 wo[o0] = make_double2(fma(x0, tqx, y0 * tqy), fma(y0, tqx, -(x0 * tqy)));
                 wo[o1] = make_double2(fma(x1, tqx, y1 * tqy), fma(y1, tqx, -(x1 * tqy)));
+            }
             }
             __syncwarp();
         }
@@ -396,15 +488,25 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     double tsum = 0.0;
     auto emit = [&](int i, const double (&rr)[RP], const double (&tt)[RP]) {
         double sum = 0.0;
+        if (full) {
+            // n == 8: the two channels of a lane are adjacent -> one 16-byte store per array
+            sum = (rr[0] + tt[0]) + (rr[1] + tt[1]);
+            tsum += tt[0] + tt[1];
+            if (active) {
+                *reinterpret_cast<double2*>(p.R + obase + (long long)i * N + row0) = make_double2(rr[0], rr[1]);
+                *reinterpret_cast<double2*>(p.T + obase + (long long)i * N + row0) = make_double2(tt[0], tt[1]);
+            }
+        } else {
 #pragma unroll
-        for (int s = 0; s < RP; ++s) {
-            const int r = row0 + s;
-            if (full || r < n) {
-                sum += rr[s] + tt[s];
-                tsum += tt[s];
-                if (active) {
-                    p.R[obase + (long long)i * n + r] = rr[s];
-                    p.T[obase + (long long)i * n + r] = tt[s];
+            for (int s = 0; s < RP; ++s) {
+                const int r = row0 + s;
+                if (r < n) {
+                    sum += rr[s] + tt[s];
+                    tsum += tt[s];
+                    if (active) {
+                        p.R[obase + (long long)i * n + r] = rr[s];
+                        p.T[obase + (long long)i * n + r] = tt[s];
+                    }
                 }
             }
         }
