@@ -16,7 +16,13 @@ __device__ __forceinline__ cd ld_op(const cd* A, int n, int r, int c, int op) {
 }
 
 // C = op(A) * op(B)            (C must not alias A or B)
+__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate);
+
 __device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n) {
+    if ((n & 7) == 0 && n >= 16) {
+        cta_gemm_dmma(C, A, opA, B, opB, n, 1.0, false);
+        return;
+    }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
         const int r = idx / n, c = idx - r * n;
         double ar = 0.0, ai = 0.0;
@@ -30,8 +36,54 @@ __device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int op
     __syncthreads();
 }
 
+// ---- FP64 tensor-core path (mma.sync.m8n8k4.f64) for n a multiple of 8 -------------------------------
+// One warp per 8x8 output tile, k advanced 4 at a time; a complex product is four real DMMAs
+// (re += ar*br, re += (-ai)*bi, im += ar*bi, im += ai*br).  Fragment ownership (lane = 4*g + t):
+//   A (8x4, row): lane holds A[g][t]     B (4x8, col): lane holds B[t][g]     C (8x8): lane holds C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma844(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
+__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tiles = n >> 3;
+    for (int tile = warp; tile < tiles * tiles; tile += nwarps) {
+        const int tr = (tile / tiles) << 3, tc = (tile % tiles) << 3;
+        double re[2] = {0.0, 0.0}, im[2] = {0.0, 0.0}, re2[2] = {0.0, 0.0}, im2[2] = {0.0, 0.0};
+#pragma unroll 4
+        for (int k = 0; k < n; k += 4) {
+            const cd a = ld_op(A, n, tr + g, k + t, opA);
+            const cd b = ld_op(B, n, k + t, tc + g, opB);
+            dmma844(re, a.x, b.x);
+            dmma844(im, a.x, b.y);
+            dmma844(re2, -a.y, b.y);
+            dmma844(im2, a.y, b.x);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = (tr + g) * n + tc + 2 * t + i;
+            cd v = mk(sgn * (re[i] + re2[i]), sgn * (im[i] + im2[i]));
+            if (accumulate) {
+                const cd c0 = C[idx];
+                v.x += c0.x;
+                v.y += c0.y;
+            }
+            C[idx] = v;
+        }
+    }
+    __syncthreads();
+}
+
 // C += sgn * op(A) * op(B)
 __device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn) {
+    if ((n & 7) == 0 && n >= 16) {
+        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true);
+        return;
+    }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
         const int r = idx / n, c = idx - r * n;
         double ar = 0.0, ai = 0.0;
@@ -151,6 +203,18 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
         }
     }
     __syncthreads();
+}
+
+// Inverse of X using the shared-memory staging block S when X itself lives in global memory: every
+// elimination step rewrites the whole block, which must not go through L2 sixty-four times.
+__device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ipiv, int* singular) {
+    if (S == nullptr || S == X) {
+        cta_inverse(X, n, colk, ipiv, singular);
+        return;
+    }
+    cta_copy(S, X, n * n);
+    cta_inverse(S, n, colk, ipiv, singular);
+    cta_copy(X, S, n * n);
 }
 
 // max |A_ij|^2 over the block, broadcast to all threads

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericPa
     const int e = (int)(pt - (long long)ham * p.nE);
     const cd E = p.E[e];
     cd* base = p.work ? p.work + pt * (long long)GEN_MATS * nn : reinterpret_cast<cd*>(gen_smem);
+    cd* stage = p.work ? reinterpret_cast<cd*>(gen_smem) : nullptr;   // inverse staging when blocks are global
     cd* G = base;            // current g_j, finally G_00
     cd* W = base + nn;       // running product, finally G_{M-1,0}
     cd* A = base + 2 * nn;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericPa
                 cta_copy(W, X, nn);
             }
         }
-        cta_inverse(A, n, s_colk, s_ipiv, p.singular);
+        cta_inverse_staged(A, stage, n, s_colk, s_ipiv, p.singular);
         if (j == M - 1) {
             cta_copy(G, A, nn);
             cta_copy(W, A, nn);
@@ -197,7 +198,7 @@ int launch_rgf_generic(GenericParams p, cudaStream_t st) {
     size_t smem = bytes;
     if (bytes > 200 * 1024) {
         if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
-        smem = 0;
+        smem = (size_t)p.n * p.n * sizeof(cd);   // staging block for the inverse
     } else {
         p.work = nullptr;
     }

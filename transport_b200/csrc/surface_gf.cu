@@ -39,7 +39,7 @@ struct GfParams {
     int conv_rep, min_iter, max_iter, ith;
 };
 
-constexpr int GF_THREADS = 128;
+constexpr int GF_THREADS = 256;
 constexpr int GF_MAX_MATS = 9;
 
 // wfm.g_RiceMele for spin channel s (wfm/__init__.py:379-403)
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
     const int e = blockIdx.x;
     const cd E = p.E[e];
     cd* base = (p.scratch != nullptr) ? p.scratch + (long long)e * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
+    cd* stage = (p.scratch != nullptr) ? reinterpret_cast<cd*>(gf_smem) : nullptr;   // inverse staging when blocks are global
     cd* m0 = base;               // g / result
     cd* m1 = base + nn;
     cd* m2 = base + 2 * nn;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
                     cta_gemm_acc(m1, p.h01, OP_H, m2, OP_N, n, -1.0);
                 }
             }
-            cta_inverse(m1, n, s_colk, s_ipiv, p.singular);
+            cta_inverse_staged(m1, stage, n, s_colk, s_ipiv, p.singular);
             cta_copy(m0, m1, nn);
             it_done = ith;
             if (p.ith < 0) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
         const double tol2 = p.conv_tol * p.conv_tol;
         for (it = 1; it <= p.max_iter; ++it) {
             cta_z_minus(G, z, eps, n);
-            cta_inverse(G, n, s_colk, s_ipiv, p.singular);
+            cta_inverse_staged(G, stage, n, s_colk, s_ipiv, p.singular);
             cta_gemm(T1, G, OP_N, beta, OP_N, n);               // G beta
             cta_gemm(T2, G, OP_N, alpha, OP_N, n);              // G alpha
             cta_gemm(tmp, alpha, OP_N, T1, OP_N, n);            // alpha G beta
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
             }
         }
         cta_z_minus(m0, z, epss, n);
-        cta_inverse(m0, n, s_colk, s_ipiv, p.singular);
+        cta_inverse_staged(m0, stage, n, s_colk, s_ipiv, p.singular);
         if (threadIdx.x == 0) {
             if (p.n_iter) p.n_iter[e] = it;
             if (p.conv) p.conv[e] = sqrt(resid);
@@ -217,7 +218,7 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     p.scratch = nullptr;
     p.scratch_per = 0;
     if (bytes > 200 * 1024) {
-        smem = 0;
+        smem = (size_t)n * n * sizeof(cd);      // staging block for the inverse
         p.scratch_per = (long long)mats * n * n;
         cd* ws = nullptr;
         TX_CUDA(cudaMalloc(&ws, (size_t)p.nE * bytes));
