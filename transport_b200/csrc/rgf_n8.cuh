@@ -97,6 +97,18 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
         cfms2(A[0][c], m0, prc);
         cfms2(A[1][c], m1, prc);
     };
+    // two columns at once, written as two passes of eight mutually independent FMAs each (the second
+    // FMA of a complex multiply-subtract depends on the first: spacing them hides the DFMA latency)
+    auto update_2col = [&](int c, int d, const double2 m0, const double2 m1, const double2 pc, const double2 pd) {
+        A[0][c].x = fma(-m0.x, pc.x, A[0][c].x);  A[0][c].y = fma(-m0.x, pc.y, A[0][c].y);
+        A[1][c].x = fma(-m1.x, pc.x, A[1][c].x);  A[1][c].y = fma(-m1.x, pc.y, A[1][c].y);
+        A[0][d].x = fma(-m0.x, pd.x, A[0][d].x);  A[0][d].y = fma(-m0.x, pd.y, A[0][d].y);
+        A[1][d].x = fma(-m1.x, pd.x, A[1][d].x);  A[1][d].y = fma(-m1.x, pd.y, A[1][d].y);
+        A[0][c].x = fma(m0.y, pc.y, A[0][c].x);   A[0][c].y = fma(-m0.y, pc.x, A[0][c].y);
+        A[1][c].x = fma(m1.y, pc.y, A[1][c].x);   A[1][c].y = fma(-m1.y, pc.x, A[1][c].y);
+        A[0][d].x = fma(m0.y, pd.y, A[0][d].x);   A[0][d].y = fma(-m0.y, pd.x, A[0][d].y);
+        A[1][d].x = fma(m1.y, pd.y, A[1][d].x);   A[1][d].y = fma(-m1.y, pd.x, A[1][d].y);
+    };
     // pivot row of step k -> pr[c], c != k
     auto fetch_pivot_row = [&](int k, int prow, double2 (&pr)[N]) {
         if (PIVX == 1) {
@@ -167,15 +179,13 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
             key = max(n8_key(A[0][k + 1], row0, used0), n8_key(A[1][k + 1], row0 + 1, used1));
             unsigned other = __shfl_xor_sync(0xffffffffu, key, 2);
             TX_PIN_COL(A, rest[0]); TX_PIN_COL(A, rest[1]);
-            update_col(rest[0], m0, m1, pr[rest[0]]);
-            update_col(rest[1], m0, m1, pr[rest[1]]);
+            update_2col(rest[0], rest[1], m0, m1, pr[rest[0]], pr[rest[1]]);
             TX_PIN_COL(A, rest[0]); TX_PIN_COL(A, rest[1]);
             other = after(other, A[0][rest[1]], A[1][rest[1]]);   // first use of the shuffle result: behind the chunk
             key = max(key, other);
             other = __shfl_xor_sync(0xffffffffu, key, 1);
             TX_PIN_COL(A, rest[2]); TX_PIN_COL(A, rest[3]);
-            update_col(rest[2], m0, m1, pr[rest[2]]);
-            update_col(rest[3], m0, m1, pr[rest[3]]);
+            update_2col(rest[2], rest[3], m0, m1, pr[rest[2]], pr[rest[3]]);
             TX_PIN_COL(A, rest[2]); TX_PIN_COL(A, rest[3]);
             other = after(other, A[0][rest[3]], A[1][rest[3]]);
             key = max(key, other);
@@ -187,8 +197,7 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
                 pe.y = __shfl_sync(0xffffffffu, v.y, gbase | (prow >> 1));
             }
             TX_PIN_COL(A, rest[4]); TX_PIN_COL(A, rest[5]);
-            update_col(rest[4], m0, m1, pr[rest[4]]);
-            update_col(rest[5], m0, m1, pr[rest[5]]);
+            update_2col(rest[4], rest[5], m0, m1, pr[rest[4]], pr[rest[5]]);
             A[0][k] = make_double2((isp0 ? 1.0 : 0.0) - m0.x, -m0.y);
             A[1][k] = make_double2((isp1 ? 1.0 : 0.0) - m1.x, -m1.y);
             TX_PIN_COL(A, rest[4]); TX_PIN_COL(A, rest[5]); TX_PIN_COL(A, k);
