@@ -324,10 +324,14 @@ def gpu_arm(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
+        traffic, ncu_note = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("rgf_sweep_n8_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("rgf_sweep_n8_bytes_per_launch")
+            ncu_note = {"binding_unit": "L1/shared-memory data pipe (LSU wavefronts)",
+                        "lsu_data_pipe_pct_of_peak": tj.get("lsu_data_pipe_pct_of_peak"),
+                        "fp64_plus_dmma_pipe_pct_of_peak": tj.get("fp64_plus_dmma_shared_pipe_pct_of_peak")}
         except Exception:
             pass
         achieved_tf = FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
@@ -343,6 +347,7 @@ def gpu_arm(args):
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak, "traffic": traffic,
                          "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written per launch)",
+                         "ncu": ncu_note,
                          "peak_source": "tx_measure_fp64_peak: register-resident DFMA loop, measured in this run "
                                         "(MEASURED_PEAKS.json carries no FP64 figure)",
                          "flops_per_point": FLOPS_PER_POINT, "kernel_ms": k_ms,
