@@ -175,6 +175,15 @@ int tx_hsysmat(const tx_cplx* tinf, const tx_cplx* tL, const tx_cplx* tR, const 
                const tx_cplx* VL, const tx_cplx* VR, int Ninf, int NL, int NR, const tx_cplx* HC, int NC, int n,
                tx_cplx* H);
 
+/* Landauer current from a transmission function (reference: fcdmft/__init__.py
+ * landauer:238-270 + np.trapz :426): jE[b][i] = T[i] (n_L - n_R)/(2 pi), I[b] = trapz(jE[b], E), with
+ * Fermi functions at kBT (a step function for kBT == 0) and chemical potentials muL[b], muR[b].
+ * T, E [nE]; jE [n_bias][nE] or NULL; I [n_bias].  Host pointers / device pointers + stream. */
+int tx_landauer_current(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
+                        double kBT, double* jE, double* I);
+int tx_landauer_current_dev(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
+                            double kBT, double* jE, double* I, void* stream);
+
 /* Tuning knob for the 5 <= n <= 8, scalar-hopping, closed-lead sweep (bench.py --variant):
  *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
  *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles

@@ -443,3 +443,30 @@ def test_all_kernel_variants_agree():
         for p in range(P):
             oR, oT = rgf_oracle.transmission_closed(h[p], tnn[p], Es, np.eye(n)[:2])
             _check(R2[p], T2[p], oR, oT)
+
+
+def test_landauer_current_and_rhat_extensions():
+    """reflection operator from G_00 and the Landauer current integral."""
+    from transport_b200 import current
+    h, tnn, tnnn = configs.cicc_blocks(1, 1.0, -0.4, 0.0, 0.0, 0.0, 3, 2)
+    Es = np.linspace(-1.95, -0.05, 400).astype(complex)
+    R, T, tot = transmission_sweep(h, tnn, Es, want_total=True)
+    mu_L = np.array([-1.0, -0.8, -0.5, -1.2])
+    mu_R = np.array([-1.2, -1.0, -0.9, -1.2])
+    for kBT in (0.0, 0.03):
+        I, jE = current.landauer_current(tot[0], Es.real, mu_L, mu_R, kBT, want_density=True)
+        for b in range(len(mu_L)):
+            if kBT == 0.0:
+                nL, nR = (Es.real <= mu_L[b]).astype(float), (Es.real <= mu_R[b]).astype(float)
+            else:
+                nL = 1 / (np.exp((Es.real - mu_L[b]) / kBT) + 1)
+                nR = 1 / (np.exp((Es.real - mu_R[b]) / kBT) + 1)
+            want_j = tot[0] * (nL - nR) / (2 * np.pi)
+            assert np.allclose(jE[b], want_j, rtol=1e-13, atol=1e-16)
+            assert np.isclose(I[b], np.trapezoid(want_j, Es.real), rtol=1e-12, atol=1e-15)
+    assert abs(I[-1]) < 1e-15                      # no bias, no current
+    # Rhat: all channels share ka_L here, so |Rhat[beta, alpha]|^2 are the reflection probabilities
+    E = complex(-1.3)
+    Rhat = wfm.Rhat_matrix(h, tnn, tnnn, 1.0, E)
+    Rk = np.array([wfm.kernel(h, tnn, tnnn, 1.0, E, "g_closed", np.eye(8)[a], False, False)[0] for a in range(8)])
+    assert np.allclose(np.abs(Rhat.T) ** 2, Rk, rtol=1e-10, atol=1e-13)

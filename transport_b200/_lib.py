@@ -55,6 +55,8 @@ _SIGNATURES = {
     "tx_green_column0": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "tx_green_full": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "tx_hmat": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "tx_landauer_current": (c_int, [_P, _P, c_int, _P, _P, c_int, c_double, _P, _P]),
+    "tx_landauer_current_dev": (c_int, [_P, _P, c_int, _P, _P, c_int, c_double, _P, _P, _P]),
     "tx_hsysmat": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "tx_debug_invert": (c_int, [_P, _P, c_int, c_int]),
     "tx_measure_fp64_peak": (c_int, [_P, _P]),

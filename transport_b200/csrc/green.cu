@@ -198,6 +198,37 @@ __global__ void hsysmat_kernel(const HsysParams p) {
     p.H[idx] = v;
 }
 
+// Landauer current from an already computed transmission function (the
+// reference's fcdmft/__init__.py:landauer:238-270 forms jE = Tr[...] (nL - nR)/(2 pi) per energy and
+// integrates it with np.trapz, :426).  One CTA per bias point.
+__global__ void __launch_bounds__(256) landauer_kernel(const double* __restrict__ T, const double* __restrict__ E, int nE,
+                                                       const double* __restrict__ muL, const double* __restrict__ muR,
+                                                       double kBT, double* __restrict__ jE, double* __restrict__ I) {
+    __shared__ double s_red[8];
+    const int b = blockIdx.x;
+    const double mL = muL[b], mR = muR[b];
+    auto occ = [&](double e, double mu) -> double {
+        if (kBT == 0.0) return e <= mu ? 1.0 : 0.0;           // step function (:241-245)
+        return 1.0 / (exp((e - mu) / kBT) + 1.0);              // :247-248
+    };
+    auto dens = [&](int i) -> double { return T[i] * (occ(E[i], mL) - occ(E[i], mR)) / (2.0 * 3.141592653589793); };
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nE; i += blockDim.x) {
+        const double ji = dens(i);
+        if (jE) jE[(long long)b * nE + i] = ji;
+        if (i + 1 < nE) acc += 0.5 * (E[i + 1] - E[i]) * (ji + dens(i + 1));   // trapezoid rule
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += s_red[w];
+        I[b] = tot;
+    }
+}
+
 struct DevMem {
     char* p = nullptr;
     ~DevMem() {
@@ -292,6 +323,42 @@ int tx_hmat(const tx_cplx* h, const tx_cplx* tnn, const tx_cplx* tnnn, int n, in
     hmat_kernel<<<(unsigned)((total + 255) / 256), 256>>>(dh, dt, dtt, dH, n, M);
     TX_CUDA(cudaGetLastError());
     TX_CUDA(cudaMemcpy(H, dH, b_H, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+int tx_landauer_current_dev(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
+                            double kBT, double* jE, double* I, void* stream) {
+    if (!T || !E || !muL || !muR || !I) return fail(TX_ERR_ARG, "null pointer argument");
+    if (nE < 2 || n_bias < 1 || kBT < 0.0) return fail(TX_ERR_ARG, "bad sizes nE=%d n_bias=%d kBT=%g", nE, n_bias, kBT);
+    landauer_kernel<<<n_bias, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(T, E, nE, muL, muR, kBT, jE, I);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    return TX_OK;
+}
+
+int tx_landauer_current(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
+                        double kBT, double* jE, double* I) {
+    if (!T || !E || !muL || !muR || !I) return fail(TX_ERR_ARG, "null pointer argument");
+    if (nE < 2 || n_bias < 1 || kBT < 0.0) return fail(TX_ERR_ARG, "bad sizes nE=%d n_bias=%d kBT=%g", nE, n_bias, kBT);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t bE = (size_t)nE * 8, bB = (size_t)n_bias * 8, bJ = jE ? (size_t)n_bias * nE * 8 : 0;
+    DevMem d;
+    TX_CUDA(cudaMalloc(&d.p, 2 * bE + 3 * bB + bJ + 64));
+    char* q = d.p;
+    double* dT = (double*)q;  TX_CUDA(cudaMemcpy(q, T, bE, cudaMemcpyHostToDevice));    q += bE;
+    double* dE = (double*)q;  TX_CUDA(cudaMemcpy(q, E, bE, cudaMemcpyHostToDevice));    q += bE;
+    double* dL = (double*)q;  TX_CUDA(cudaMemcpy(q, muL, bB, cudaMemcpyHostToDevice));  q += bB;
+    double* dR = (double*)q;  TX_CUDA(cudaMemcpy(q, muR, bB, cudaMemcpyHostToDevice));  q += bB;
+    double* dI = (double*)q;  q += bB;
+    double* dJ = jE ? (double*)q : nullptr;
+    int rc = tx_landauer_current_dev(dT, dE, nE, dL, dR, n_bias, kBT, dJ, dI, nullptr);
+    if (rc) return rc;
+    TX_CUDA(cudaMemcpy(I, dI, bB, cudaMemcpyDeviceToHost));
+    if (jE) TX_CUDA(cudaMemcpy(jE, dJ, bJ, cudaMemcpyDeviceToHost));
     return TX_OK;
 }
 

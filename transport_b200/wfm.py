@@ -158,6 +158,23 @@ def g_ith(diag, offdiag, E, inoutsign, imE, ith, g_prev) -> np.ndarray:
                        None if ith == 0 else np.asarray(g_prev)[None])[0]
 
 
+def Rhat_matrix(h, tnn, tnnn, tl, E, converger="g_closed") -> np.ndarray:
+    """Reflection operator  Rhat = 2i tl G_00 sin(ka_L) - 1  (n x n complex), the formula that is commented
+    out in the reference (transport/wfm/__init__.py:103) and whose absence makes `kernel(..., is_Rhat=True)`
+    raise NameError there (:105).  Extension for the gate-fidelity drivers (run_wfm_gate.py:465,603);
+    `kernel` itself keeps the reference's behaviour.  ka_L follows `Hprime`'s convention (:253):
+    ka_L = arccos((E - diag h[0]) / (-2 tl)), one value per channel (applied to the source column)."""
+    from . import green
+    if not len(tnn) + 1 == len(h): raise ValueError
+    if not len(tnnn) + 2 == len(h): raise ValueError
+    if np.any(tnnn): raise NotImplementedError("Rhat with next-nearest-neighbour blocks")
+    n = np.shape(h[0])[0]
+    SigL, SigR = SelfEnergies(h, tnn, tnnn, E, converger)
+    G00 = green.green_column0(h, tnn, np.array([E], dtype=complex), SigL[None], SigR[None])[0, 0]
+    ka_L = np.arccos((E - np.diagonal(h[0])) / (-2 * tl))
+    return 2 * tl * complex(0, 1) * G00 * np.sin(ka_L)[None, :] - np.eye(n)
+
+
 # ---- Rice-Mele band helpers: scalar host formulas, not on the device path --------------------
 def _rm_uvw(diag, offdiag):
     u0 = np.sum(np.diagonal(diag)) / len(diag)
