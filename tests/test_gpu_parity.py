@@ -470,3 +470,43 @@ def test_landauer_current_and_rhat_extensions():
     Rhat = wfm.Rhat_matrix(h, tnn, tnnn, 1.0, E)
     Rk = np.array([wfm.kernel(h, tnn, tnnn, 1.0, E, "g_closed", np.eye(8)[a], False, False)[0] for a in range(8)])
     assert np.allclose(np.abs(Rhat.T) ** 2, Rk, rtol=1e-10, atol=1e-13)
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE config 2 at full size (1000 J x 1000 E x 8 sources) through the host C ABI: unitarity on all
+    8e6 (point, source) pairs, the golden rows, T_total = sum of channels, and sweep linearity in the batch
+    (a sub-batch reproduces the same bits)."""
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    Js, Es = configs.cfg2_grid(1000, 1000)
+    R, T, res, tot = transmission_sweep(h0, tnn, Es, h1=h1, params=Js, want_resid=True, want_total=True)
+    assert R.shape == (1000, 1000, 8, 8)
+    assert np.isfinite(R).all() and np.isfinite(T).all()
+    assert np.max(np.abs(res)) < UNIT
+    assert np.allclose(tot, T.sum(axis=(2, 3)), rtol=1e-12, atol=1e-15)
+    assert T.min() >= 0 and R.min() >= 0
+    g = load_golden("cfg2_cicc.npz")
+    for k, jidx in enumerate([0, 250, 500, 750, 999]):
+        _check(R[jidx, ::40], T[jidx, ::40], g["R"][k], g["T"][k])
+    R2, T2 = transmission_sweep(h0, tnn, Es[100:133], h1=h1, params=Js[400:403])
+    assert np.array_equal(T2, T[400:403, 100:133]) and np.array_equal(R2, R[400:403, 100:133])
+
+
+def test_cfg1_full_size_and_cfg3_long_chain_properties():
+    """config 1 at full size against the golden stride; config 3 at N=10^4 sites on a strided energy grid:
+    finite, non-negative, unitarity within the conditioning of the problem at that length (a 1-ulp change of
+    E moves the oracle's own T by ~1e-9, see profiles/README.md), exact agreement of a re-run (determinism)."""
+    g = load_golden("cfg1_barrier.npz")
+    h, tnn, _ = configs.barrier_blocks(0.4, 11)
+    Es = configs.barrier_energies(10_000)
+    R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+    assert np.max(np.abs(res)) < UNIT
+    _check(R[0, ::50], T[0, ::50], g["R"], g["T"])
+    below = (Es.real + 2.0) < 0.4                      # under the barrier top: pure tunnelling, monotone in E
+    assert np.all(np.diff(T[0, below, 0, 0]) > 0)
+    h, tnn, _ = configs.disordered_blocks(N=10_000, n=8, W=0.05, seed=1234)
+    Es = np.linspace(-1.9, 1.9, 100_000).astype(complex)[::500]
+    R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+    assert np.isfinite(R).all() and np.isfinite(T).all() and T.min() >= 0
+    assert np.max(np.abs(res)) < 1e-7
+    R2, T2 = transmission_sweep(h, tnn, Es)
+    assert np.array_equal(T, T2) and np.array_equal(R, R2)
