@@ -193,6 +193,10 @@ int tx_landauer_current_dev(const double* T, const double* E, int nE, const doub
  *        that skip the products / the inversion (WRONG results, measurement only)
  * All variants compute the same thing. */
 int tx_set_variant(int variant);
+/* Library options.  option 0: value != 0 (default) lets the 5 <= n <= 8 scalar-hopping sweep treat the
+ * right-hand tail of sites whose on-site blocks are diagonal (leads, barrier regions V*I, clean spacer
+ * sites) per channel instead of as blocks; value 0 forces the block path on every site (A/B measurements). */
+int tx_set_option(int option, int value);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device
  * routine of the sweep (in-place Gauss-Jordan with implicit partial pivoting). Host pointers. */

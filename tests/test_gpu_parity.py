@@ -510,3 +510,29 @@ def test_cfg1_full_size_and_cfg3_long_chain_properties():
     assert np.max(np.abs(res)) < 1e-7
     R2, T2 = transmission_sweep(h, tnn, Es)
     assert np.array_equal(T, T2) and np.array_equal(R, R2)
+
+
+def test_diagonal_tail_fast_path_matches_block_path():
+    """Sites right of the last channel-coupling block are swept per channel (option 0); forcing the block path
+    on every site must give the same numbers, for tails of every length including the whole chain."""
+    lib = _lib.load()
+    Es = np.linspace(-1.9, -0.1, 21).astype(complex)
+    cases = []
+    for NB in (1, 3, 40):
+        cases.append(configs.cicc_blocks(1, 1.0, -0.7, 0.05, 0.3, 0.0, NB, 2)[:2])      # barrier tail at V_B
+    h, tnn, _ = configs.barrier_blocks(0.4, 9, n=8)                                       # fully diagonal chain
+    cases.append((h, tnn))
+    h, tnn, _ = configs.disordered_blocks(N=12, n=7, W=0.2, seed=5)                       # no diagonal tail, padded
+    cases.append((h, tnn))
+    for h, tnn in cases:
+        n = h.shape[-1]
+        try:
+            _lib.check(lib.tx_set_option(0, 0))
+            Rb, Tb = transmission_sweep(h, tnn, Es)
+        finally:
+            _lib.check(lib.tx_set_option(0, 1))
+        Rf, Tf, res = transmission_sweep(h, tnn, Es, want_resid=True)
+        assert rt_err(Tf, Tb) < 1e-12 and rt_err(Rf, Rb) < 1e-12
+        assert np.max(np.abs(res)) < UNIT
+        oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(n))
+        _check(Rf[0], Tf[0], oR, oT)

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "tx_set_device": (c_int, [c_int]),
     "tx_device_synchronize": (c_int, []),
     "tx_set_variant": (c_int, [c_int]),
+    "tx_set_option": (c_int, [c_int, c_int]),
     "tx_sweep_launch_count": (c_int, [c_int, c_int, c_int]),
     "tx_launch_counter": (ctypes.c_longlong, []),
     "tx_transmission_sweep": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,

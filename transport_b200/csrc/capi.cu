@@ -93,10 +93,31 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
 
 // grow-only per-device buffer for expanded affine Hamiltonian families (tx_transmission_sweep_dev)
 DevBuf g_expand[16];
+DevBuf g_nondiag[16];
+bool g_diag_tail = true;    // tx_set_option(0, ...): sweep the diagonal right tail per channel
 
 template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
 int launch_n8(SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
+    p.nondiag_max = nullptr;
+    p.nondiag_stride = 0;
+    if (LEAD == LEAD_CLOSED && g_diag_tail) {
+        // structure scan: which right-hand sites have diagonal on-site blocks
+        int devid = 0;
+        TX_CUDA(cudaGetDevice(&devid));
+        const int n_hs = (p.h_stride == 0) ? 1 : (int)(p.n_pts / p.nE);
+        DevBuf& nb = g_nondiag[devid & 15];
+        if ((size_t)n_hs * sizeof(int) > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
+        int rc = nb.ensure((size_t)n_hs * sizeof(int));
+        if (rc) return rc;
+        TX_CUDA(cudaMemsetAsync(nb.ptr, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
+        const long long total = (long long)n_hs * p.M * p.n;
+        nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, (int*)nb.ptr);
+        TX_CUDA(cudaGetLastError());
+        count_launch();
+        p.nondiag_max = (const int*)nb.ptr;
+        p.nondiag_stride = (p.h_stride == 0) ? 0 : 1;
+    }
     if (p.h1) {
         int devid = 0;
         TX_CUDA(cudaGetDevice(&devid));
@@ -171,6 +192,14 @@ int tx_device_synchronize(void) {
 }
 
 long long tx_launch_counter(void) { return g_launches.load(); }
+
+int tx_set_option(int option, int value) {
+    if (option == 0) {
+        g_diag_tail = value != 0;
+        return TX_OK;
+    }
+    return fail(TX_ERR_ARG, "unknown option %d", option);
+}
 
 int tx_set_variant(int v) {
     if (v < 0 || v > 15) return fail(TX_ERR_ARG, "variant must be 0..15");
@@ -270,6 +299,8 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     p.resid = resid;
     p.ttot = t_total;
     p.singular = singular_flag;
+    p.nondiag_max = nullptr;
+    p.nondiag_stride = 0;
     p.n_pts = (long long)n_ham * nE;
     p.n = n;
     p.M = M;

@@ -302,10 +302,79 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             }
         }
     };
-    fetch_rows(M - 1);
+    // ------------------------------------------------------------------ diagonal tail
+    // Every site to the right of the last non-diagonal on-site block (leads, barrier regions V*I, clean
+    // spacer sites) has a diagonal A_j as long as Sigma_R is diagonal: the inverse is n reciprocals and W
+    // stays diagonal.  Those sites are swept per channel here (each lane its own two channels); the block
+    // machinery below starts at the first site that really couples channels.  Same arithmetic as
+    // Gauss-Jordan on a diagonal matrix, so parity is unaffected.
+    int jd = M;                       // sites j >= jd are handled here
+    if (LEAD == LEAD_CLOSED && p.nondiag_max != nullptr) {
+        int mine = p.nondiag_max[ham * p.nondiag_stride] + 1;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, off));
+        jd = mine;                    // warp-uniform, conservative over the warp's points
+    }
+    fetch_rows(jd > 0 ? min(jd, M) - 1 : 0);
+    if (jd < M) {
+        double2 gd[RP], wd[RP], hd[RP];
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            gd[s] = wd[s] = make_double2(0.0, 0.0);
+            const int r = row0 + s;
+            hd[s] = (full || r < n) ? h_at(M - 1, r, r) : make_double2(0.0, 0.0);
+        }
+        for (int j = M - 1; j >= jd; --j) {
+            const double2 tj = (j < M - 1) ? t_at(j, 0, 0) : make_double2(0.0, 0.0);
+            const double kap = fma(tj.x, tj.x, tj.y * tj.y);
+            double2 hnext[RP];
+#pragma unroll
+            for (int s = 0; s < RP; ++s) {     // next site's diagonal, one iteration ahead
+                const int r = row0 + s;
+                hnext[s] = (j > jd && (full || r < n)) ? h_at(j - 1, r, r) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int s = 0; s < RP; ++s) {
+                const int r = row0 + s;
+                if (full || r < n) {
+                    double2 a = make_double2(E.x - hd[s].x, E.y - hd[s].y);
+                    if (j == M - 1) {
+                        a.x -= sigRd[s].x;
+                        a.y -= sigRd[s].y;
+                    } else {
+                        a.x = fma(-kap, gd[s].x, a.x);
+                        a.y = fma(-kap, gd[s].y, a.y);
+                    }
+                    if (j == 0) {
+                        a.x -= sigLd[s].x;
+                        a.y -= sigLd[s].y;
+                    }
+                    if (a.x == 0.0 && a.y == 0.0) *p.singular = 1;
+                    const double2 gnew = fast_crecip(a);
+                    wd[s] = (j == M - 1) ? gnew : cmul2(cmul2(wd[s], gnew), make_double2(tj.x, -tj.y));
+                    gd[s] = gnew;
+                } else {
+                    gd[s] = make_double2(1.0, 0.0);   // padding channel
+                    wd[s] = make_double2(0.0, 0.0);
+                }
+                hd[s] = hnext[s];
+            }
+        }
+        // expand into the block layout the general sites (and the epilogue) read
+#pragma unroll
+        for (int s = 0; s < RP; ++s) {
+            const int r = row0 + s;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                gt[n8_idx(c, r)] = (c == r) ? gd[s] : make_double2(0.0, 0.0);
+                wb[n8_idx(r, c)] = (c == r) ? wd[s] : make_double2(0.0, 0.0);
+            }
+        }
+        __syncwarp();
+    }
 
     // ------------------------------------------------------------------ sweep
-    for (int j = M - 1; j >= 0; --j) {
+    for (int j = min(jd, M) - 1; j >= 0; --j) {
         double2 tj = make_double2(0.0, 0.0);
         if (j < M - 1) tj = t_at(j, 0, 0);
         // A = E - h_j from the rows fetched during the previous site's tensor-core phase
@@ -593,6 +662,27 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
         if (active && li == 0) p.ttot[pt] = tsum;
     }
+}
+
+// nondiag_max[q] = largest site j whose on-site block has a non-zero off-diagonal element (rows checked
+// by separate threads; -1 if every block is diagonal).  One thread per (Hamiltonian, site, row).
+__global__ void nondiag_scan_kernel(const cd* __restrict__ h, const cd* __restrict__ h1, int n_h, int M, int n,
+                                    int* __restrict__ nondiag_max) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_h * M * n;
+    if (idx >= total) return;
+    const int r = (int)(idx % n);
+    const int j = (int)((idx / n) % M);
+    const int q = (int)(idx / ((long long)n * M));
+    const cd* row = h + ((long long)q * M + j) * n * n + (long long)r * n;
+    const cd* row1 = h1 ? h1 + (long long)j * n * n + (long long)r * n : nullptr;
+    bool nz = false;
+    for (int c = 0; c < n; ++c) {
+        if (c == r) continue;
+        nz |= (row[c].x != 0.0) || (row[c].y != 0.0);
+        if (row1) nz |= (row1[c].x != 0.0) || (row1[c].y != 0.0);
+    }
+    if (nz) atomicMax(nondiag_max + q, j);
 }
 
 // out[ham][i] = h0[i] + params[ham] * h1[i]  — materialises an affine Hamiltonian family (8 KB per

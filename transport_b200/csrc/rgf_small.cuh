@@ -42,6 +42,8 @@ struct SweepParams {
     double* resid;           // [n_pts][n_src] or null
     double* ttot;            // [n_pts] or null: sum over sources and channels of T (= Tr[Gamma_R G Gamma_L G^dag] for all sources)
     int* singular;           // device flag, set to 1 if a zero pivot was met
+    const int* nondiag_max;  // [n_ham or 1] or null: largest site index whose on-site block is not diagonal (-1: none)
+    long long nondiag_stride;
     long long n_pts;
     int n, M, nE, n_src;
 };
