@@ -187,9 +187,9 @@ int tx_landauer_current_dev(const double* T, const double* E, int nE, const doub
 /* Tuning knob for the 5 <= n <= 8, scalar-hopping, closed-lead sweep (bench.py --variant):
  *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
  *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles
- *   6/7  tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh), 3 CTAs/SM, smem / shuffle pivot row
+ *   6/7  tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh), 3 CTAs/SM, smem (6 = DEFAULT) / shuffle pivot row
  *   8    as 6 with 2 CTAs/SM and no register cap;   9  as 8 with the eight products of a warp issued
- *        back to back before one barrier (DEFAULT);   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
+ *        back to back before one barrier;   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
  *        that skip the products / the inversion (WRONG results, measurement only)
  * All variants compute the same thing. */
 int tx_set_variant(int variant);

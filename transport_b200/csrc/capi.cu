@@ -67,7 +67,7 @@ int round_up_block(int n) {
 
 // Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
 // number of resident 128-thread blocks per SM the register allocation is capped for.
-int g_variant = 9;
+int g_variant = 6;
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -101,22 +101,33 @@ int launch_n8(SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
     p.nondiag_max = nullptr;
     p.nondiag_stride = 0;
-    if (LEAD == LEAD_CLOSED && g_diag_tail) {
-        // structure scan: which right-hand sites have diagonal on-site blocks
+    p.site_class = nullptr;
+    p.class_stride = 0;
+    if (g_diag_tail) {
+        // structure scan: diagonal right tail (closed leads) and scalar runs
         int devid = 0;
         TX_CUDA(cudaGetDevice(&devid));
         const int n_hs = (p.h_stride == 0) ? 1 : (int)(p.n_pts / p.nE);
         DevBuf& nb = g_nondiag[devid & 15];
-        if ((size_t)n_hs * sizeof(int) > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
-        int rc = nb.ensure((size_t)n_hs * sizeof(int));
+        const size_t need = (size_t)n_hs * (1 + (size_t)p.M) * sizeof(int);
+        if (need > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
+        int rc = nb.ensure(need);
         if (rc) return rc;
-        TX_CUDA(cudaMemsetAsync(nb.ptr, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
+        int* nd = (int*)nb.ptr;
+        int* cl = nd + n_hs;
+        TX_CUDA(cudaMemsetAsync(nd, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
+        const long long ncl = (long long)n_hs * p.M;
+        fill_int_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, 2, ncl);
         const long long total = (long long)n_hs * p.M * p.n;
-        nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, (int*)nb.ptr);
+        nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, nd, cl);
         TX_CUDA(cudaGetLastError());
-        count_launch();
-        p.nondiag_max = (const int*)nb.ptr;
-        p.nondiag_stride = (p.h_stride == 0) ? 0 : 1;
+        count_launch(2);
+        if (LEAD == LEAD_CLOSED) {
+            p.nondiag_max = nd;
+            p.nondiag_stride = (p.h_stride == 0) ? 0 : 1;
+        }
+        p.site_class = cl;
+        p.class_stride = (p.h_stride == 0) ? 0 : p.M;
     }
     if (p.h1) {
         int devid = 0;
@@ -301,6 +312,8 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     p.singular = singular_flag;
     p.nondiag_max = nullptr;
     p.nondiag_stride = 0;
+    p.site_class = nullptr;
+    p.class_stride = 0;
     p.n_pts = (long long)n_ham * nE;
     p.n = n;
     p.M = M;
@@ -318,7 +331,7 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
             if (hop == HOP_SCALAR) {
                 // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
                 // register-resident template reachable for A/B measurements (bench.py --variant)
-                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 2, 0, 8>(p, st);
+                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 3, 0>(p, st);
                 switch (g_variant) {
                     case 0: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
                     case 1: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
@@ -326,13 +339,13 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
                     case 3: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
                     case 4: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
                     case 5: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
-                    case 6: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);
+                    case 6: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);   // default
                     case 7: return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
                     case 10: return launch_n8<LEAD_CLOSED, 3, 0, 8>(p, st);
                     case 11: return launch_n8<LEAD_CLOSED, 2, 0, 1, 1>(p, st);   // timing experiment: no products (wrong results)
                     case 12: return launch_n8<LEAD_CLOSED, 2, 0, 1, 2>(p, st);   // timing experiment: no inversion (wrong results)
                     case 8: return launch_n8<LEAD_CLOSED, 2, 0>(p, st);
-                    default: return launch_n8<LEAD_CLOSED, 2, 0, 8>(p, st);   // 9 (default)
+                    default: return launch_n8<LEAD_CLOSED, 2, 0, 8>(p, st);   // 9
                 }
             }
             return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);

@@ -44,6 +44,8 @@ struct SweepParams {
     int* singular;           // device flag, set to 1 if a zero pivot was met
     const int* nondiag_max;  // [n_ham or 1] or null: largest site index whose on-site block is not diagonal (-1: none)
     long long nondiag_stride;
+    const int* site_class;   // [n_ham or 1][M] or null: 0 general, 1 diagonal, 2 scalar multiple of I
+    long long class_stride;
     long long n_pts;
     int n, M, nE, n_src;
 };
