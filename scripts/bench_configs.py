@@ -21,6 +21,10 @@ from oracle import rgf_oracle  # noqa: E402  (checker only)
 from transport_b200 import _lib, configs, leads  # noqa: E402
 
 lib = _lib.load()
+if os.environ.get("TX_VARIANT"):
+    _lib.check(lib.tx_set_variant(int(os.environ["TX_VARIANT"])))
+if os.environ.get("TX_NO_STRUCTURE"):
+    _lib.check(lib.tx_set_option(0, 0))
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)

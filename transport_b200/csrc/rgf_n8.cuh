@@ -324,8 +324,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             const int r = row0 + s;
             hd[s] = (full || r < n) ? h_at(M - 1, r, r) : make_double2(0.0, 0.0);
         }
+        double2 tcur = make_double2(0.0, 0.0);
         for (int j = M - 1; j >= jd; --j) {
-            const double2 tj = (j < M - 1) ? t_at(j, 0, 0) : make_double2(0.0, 0.0);
+            const double2 tj = tcur;
+            const double2 tnext = (j > jd) ? t_at(j - 1, 0, 0) : make_double2(0.0, 0.0);   // one site ahead
             const double kap = fma(tj.x, tj.x, tj.y * tj.y);
             double2 hnext[RP];
 #pragma unroll
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 }
                 hd[s] = hnext[s];
             }
+            tcur = tnext;
         }
         // expand into the block layout the general sites (and the epilogue) read
 #pragma unroll
@@ -382,13 +385,30 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     // ONE inverse and ONE product:   X = (c I + d G)^-1,   W_a = (prod conj t_i) W X,
     //     g_a = (dN/d) I + (cN - dN c/d) X.
     // The four scalar coefficients are renormalised by powers of two at every site (exponent carried to W).
-    const int* cls = p.site_class ? p.site_class + (long long)ham * p.class_stride : nullptr;
+    // Site classes are read through a 32-site window held in registers (lane l = site win_base + l, already
+    // reduced to the least structured class among the eight points of the warp), so that walking down the
+    // chain costs one global round trip per 32 sites instead of one per site.
+    const bool have_cls = (p.site_class != nullptr);
+    int win_base = 0x7fffffff, win_cls = 0;
+    auto load_window = [&](int top) {          // window [top-31, top]
+        win_base = top - 31;
+        const int site = win_base + lane;
+        int c = 2;
+#pragma unroll
+        for (int q = 0; q < GPW; ++q) {
+            const int hq = __shfl_sync(0xffffffffu, ham, q * LP);
+            const int v = (site >= 0 && site < M) ? p.site_class[(long long)hq * p.class_stride + site] : 0;
+            c = min(c, v);
+        }
+        win_cls = c;
+    };
     auto warp_class = [&](int i) -> int {      // warp-uniform: the least structured class among the points
-        int c = cls ? cls[i] : 0;
-        return __reduce_min_sync(0xffffffffu, c);
+        if (!have_cls) return 0;
+        if (i < win_base || i > win_base + 31) load_window(i);
+        return __shfl_sync(0xffffffffu, win_cls, i - win_base);
     };
     bool sigL_scalar = false;
-    if (LEAD == LEAD_CLOSED && cls) {          // Sigma_L = sigma * I ? (then site 0 may join a run)
+    if (LEAD == LEAD_CLOSED && have_cls) {     // Sigma_L = sigma * I ? (then site 0 may join a run)
         bool same = (sigLd[0].x == sigLd[1].x) && (sigLd[0].y == sigLd[1].y) && full;
         const double ox = __shfl_sync(0xffffffffu, sigLd[0].x, lane & ~3), oy = __shfl_sync(0xffffffffu, sigLd[0].y, lane & ~3);
         same = same && (ox == sigLd[0].x) && (oy == sigLd[0].y);
