@@ -177,3 +177,62 @@ def sancho_rubio(h00, h01, zs, side, tol=1e-14, max_iter=200):
         if max(np.abs(alpha).max(), np.abs(beta).max()) < tol:
             break
     return np.linalg.inv(zI - eps_s), it
+
+
+def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stats=False):
+    """The same two blocks by the *telescoped* sweep the sm_100a kernel `rgf_sweep_n8t` runs (scalar hopping
+    t_j = tau_j I only).  Inside a chunk of sites [a..b] the left-connected g_j are never formed:
+
+        D_{b+1} = I,  D_{b+2} := g_{b+1},   D_j = z_j D_{j+1} - |t_j|^2 D_{j+2},   z_j = E - h_j (- Sigma)
+        g_j = D_{j+1} D_j^-1   =>   prod_{j=b..a} g_j = D_a^-1   (telescopes)
+        X = D_a^-1,   g_a = D_{a+1} X,   W_a = (prod conj t_j) W_{b+1} X
+
+    so a chunk of k sites costs k-1 products + 1 inverse + 2 products instead of k inverses + k products.
+    A chunk is closed after `kmax` sites or as soon as max|D_j| / prod|t| exceeds `gmax` (error growth
+    bound); with kmax=1 this is exactly `rgf_blocks`.  Checker for the kernel's numerics; not product code.
+    """
+    Es = np.asarray(Es, dtype=complex)
+    M, n = h.shape[0], h.shape[-1]
+    nE = len(Es)
+    eye = np.broadcast_to(np.eye(n, dtype=complex), (nE, n, n))
+    zE = Es[:, None, None] * np.eye(n)
+    tau_all = np.array([tnn[j][0, 0] for j in range(M - 1)])
+    g = None                     # g_{b+1}
+    W = None                     # W_{b+1} (None = identity)
+    j = M - 1
+    chunks = []
+    while j >= 0:
+        b = j
+        Dp2 = g                  # D_{b+2}
+        Dp1 = eye.copy()         # D_{b+1}
+        tprod = 1.0 + 0j
+        scale = 1.0
+        k = 0
+        while True:
+            z = zE - h[j]
+            if j == M - 1:
+                z = z - SigR
+            if j == 0:
+                z = z - SigL
+            D = z @ Dp1
+            if j < M - 1:
+                kap = abs(tau_all[j]) ** 2
+                tprod = tprod * np.conj(tau_all[j])
+                scale *= abs(tau_all[j])
+                if Dp2 is not None:
+                    D = D - kap * Dp2
+            k += 1
+            growth = np.abs(D).max() / max(scale, 1e-300)
+            a = j
+            if j == 0 or k >= kmax or growth > gmax:
+                break
+            Dp2, Dp1 = Dp1, D
+            j -= 1
+        X = np.linalg.inv(D)
+        g = Dp1 @ X if k > 1 else X
+        W = tprod * (X if W is None else W @ X)
+        chunks.append(k)
+        j = a - 1
+    if return_stats:
+        return g, W, chunks
+    return g, W

@@ -10,6 +10,7 @@
 
 #include "rgf_generic.h"
 #include "rgf_n8.cuh"
+#include "rgf_n8t.cuh"
 #include "rgf_small.cuh"
 #include "tx_host.h"
 
@@ -67,7 +68,9 @@ int round_up_block(int n) {
 
 // Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
 // number of resident 128-thread blocks per SM the register allocation is capped for.
-int g_variant = 6;
+int g_variant = 13;
+int g_chunk_kmax = 8;    // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
+int g_chunk_gexp = 6;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -95,6 +98,55 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
 DevBuf g_expand[16];
 DevBuf g_nondiag[16];
 bool g_diag_tail = true;    // tx_set_option(0, ...): sweep the diagonal right tail per channel
+
+// h0 + J*h1 families are expanded once into a grow-only per-device buffer (8 KB per Hamiltonian at n = M = 8).
+int materialise_affine(SweepParams& p, cudaStream_t st) {
+    if (!p.h1) return TX_OK;
+    int devid = 0;
+    TX_CUDA(cudaGetDevice(&devid));
+    const long long per_ham = (long long)p.M * p.n * p.n;
+    const long long n_ham = p.n_pts / p.nE;
+    const long long total = per_ham * n_ham;
+    DevBuf& buf = g_expand[devid & 15];
+    if ((size_t)total * sizeof(cd) > buf.cap) TX_CUDA(cudaStreamSynchronize(st));   // a regrow frees the old buffer
+    int rc = buf.ensure((size_t)total * sizeof(cd));
+    if (rc) return rc;
+    affine_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, p.params, (cd*)buf.ptr, per_ham, total);
+    count_launch();
+    TX_CUDA(cudaGetLastError());
+    p.h = (const cd*)buf.ptr;
+    p.h_stride = per_ham;
+    p.h1 = nullptr;
+    p.params = nullptr;
+    return TX_OK;
+}
+
+// Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.
+template <int LEAD, int MINB>
+int launch_n8t(SweepParams p, cudaStream_t st) {
+    constexpr int WARPS = 4;
+    p.nondiag_max = nullptr;
+    p.site_class = nullptr;
+    {
+        int rc = materialise_affine(p, st);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)WARPS * N8TCfg::PER_WARP_BYTES;
+    static bool attr_done[16] = {false};
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 15]) {
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev & 15] = true;
+    }
+    const long long per_block = (long long)WARPS * 8;
+    const long long blocks = (p.n_pts + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
+    rgf_sweep_n8t<LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp);
+    count_launch();
+    TX_CUDA(cudaGetLastError());
+    return TX_OK;
+}
 
 template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
 int launch_n8(SweepParams p, cudaStream_t st) {
@@ -129,23 +181,9 @@ int launch_n8(SweepParams p, cudaStream_t st) {
         p.site_class = cl;
         p.class_stride = (p.h_stride == 0) ? 0 : p.M;
     }
-    if (p.h1) {
-        int devid = 0;
-        TX_CUDA(cudaGetDevice(&devid));
-        const long long per_ham = (long long)p.M * p.n * p.n;
-        const long long n_ham = p.n_pts / p.nE;
-        const long long total = per_ham * n_ham;
-        DevBuf& buf = g_expand[devid & 15];
-        if ((size_t)total * sizeof(cd) > buf.cap) TX_CUDA(cudaStreamSynchronize(st));   // a regrow frees the old buffer
-        int rc = buf.ensure((size_t)total * sizeof(cd));
+    {
+        int rc = materialise_affine(p, st);
         if (rc) return rc;
-        affine_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, p.params, (cd*)buf.ptr, per_ham, total);
-        count_launch();
-        TX_CUDA(cudaGetLastError());
-        p.h = (const cd*)buf.ptr;
-        p.h_stride = per_ham;
-        p.h1 = nullptr;
-        p.params = nullptr;
     }
     const size_t smem = (size_t)WARPS * N8Cfg::PER_WARP_BYTES;
     static bool attr_done[16] = {false};
@@ -207,6 +245,16 @@ long long tx_launch_counter(void) { return g_launches.load(); }
 int tx_set_option(int option, int value) {
     if (option == 0) {
         g_diag_tail = value != 0;
+        return TX_OK;
+    }
+    if (option == 1) {
+        if (value < 1 || value > 64) return fail(TX_ERR_ARG, "chunk length must be 1..64");
+        g_chunk_kmax = value;
+        return TX_OK;
+    }
+    if (option == 2) {
+        if (value < 0 || value > 500) return fail(TX_ERR_ARG, "growth exponent must be 0..500");
+        g_chunk_gexp = value;
         return TX_OK;
     }
     return fail(TX_ERR_ARG, "unknown option %d", option);
@@ -331,6 +379,10 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
             if (hop == HOP_SCALAR) {
                 // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
                 // register-resident template reachable for A/B measurements (bench.py --variant)
+                if (g_variant >= 13) {   // telescoped sweep (default)
+                    if (lead == LEAD_TABLE) return launch_n8t<LEAD_TABLE, 2>(p, st);
+                    return launch_n8t<LEAD_CLOSED, 2>(p, st);
+                }
                 if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 3, 0>(p, st);
                 switch (g_variant) {
                     case 0: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);

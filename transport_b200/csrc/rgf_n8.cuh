@@ -75,7 +75,7 @@ __device__ __forceinline__ unsigned n8_key(double2 a, int row, bool is_used) {
 // pivot k+1 (two butterfly shuffles), the broadcast of the pivot element, the publication of the
 // next pivot row and its reload are interleaved with the column updates of step k, and the
 // reciprocal of pivot k+1 is computed while that reload is in flight.
-template <int PIVX>
+template <int PIVX, int SWZ = 0>
 __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular,
                                           unsigned zmask) {
     constexpr int N = 8, LP = 4, GPW = 8;
@@ -218,7 +218,7 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const int col = (int)((perm >> (4 * j)) & 0xFu);
-        const int base = col * 8, sw = (col & 1) * 5;
+        const int base = col * 8, sw = SWZ ? col : (col & 1) * 5;   // SWZ: layout of rgf_n8t.cuh
         gt[base + (krow0 ^ sw)] = cmul2(A[0][j], dinv0);
         gt[base + (krow1 ^ sw)] = cmul2(A[1][j], dinv1);
     }
