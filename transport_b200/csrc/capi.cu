@@ -139,10 +139,12 @@ int launch_n8t(SweepParams p, cudaStream_t st) {
         TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
-    const long long per_block = (long long)WARPS * 8;
-    const long long blocks = (p.n_pts + per_block - 1) / per_block;
+    // a warp = eight consecutive energies of one Hamiltonian (energy axis padded to a multiple of eight)
+    const int warps_per_ham = (p.nE + 7) / 8;
+    const long long n_warps = (p.n_pts / p.nE) * warps_per_ham;
+    const long long blocks = (n_warps + WARPS - 1) / WARPS;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8t<LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp);
+    rgf_sweep_n8t<LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
@@ -379,7 +381,9 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
             if (hop == HOP_SCALAR) {
                 // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
                 // register-resident template reachable for A/B measurements (bench.py --variant)
-                if (g_variant >= 13) {   // telescoped sweep (default)
+                // telescoped sweep (default); its warps take eight energies of one Hamiltonian, so very short
+                // energy axes that are not a multiple of eight go to the point-per-4-lanes kernel instead
+                if (g_variant >= 13 && (nE >= 64 || nE % 8 == 0)) {
                     if (lead == LEAD_TABLE) return launch_n8t<LEAD_TABLE, 2>(p, st);
                     return launch_n8t<LEAD_CLOSED, 2>(p, st);
                 }
@@ -391,7 +395,7 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
                     case 3: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
                     case 4: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
                     case 5: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
-                    case 6: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);   // default
+                    case 6: case 13: case 14: case 15: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);   // plain sweep
                     case 7: return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
                     case 10: return launch_n8<LEAD_CLOSED, 3, 0, 8>(p, st);
                     case 11: return launch_n8<LEAD_CLOSED, 2, 0, 1, 1>(p, st);   // timing experiment: no products (wrong results)

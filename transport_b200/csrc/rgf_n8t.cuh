@@ -29,7 +29,7 @@
 // q*65 + r*8 + (c ^ r) -- conflict-free for F reads/writes, for Rw row reads and for the transposing F write:
 //   XB  D_a (for the inverse), then X stored transposed, finally G_00        YB  Y_{a+1} stored transposed
 //   WB  W                                                                     PV  pivot rows / Sigma_R / velocities
-//   SL  Sigma_L diagonal per point     EB  energies of the eight points       IQ  Hamiltonian / energy index per point
+//   SL  E - Sigma_L per (point, channel)     EB  energies of the eight points
 #pragma once
 #include "rgf_n8.cuh"
 
@@ -37,7 +37,7 @@ namespace tx {
 
 struct N8TCfg {
     static constexpr int PSTRIDE = 65;
-    static constexpr int PER_WARP = 3 * 8 * PSTRIDE + 128 + 64 + 8 + 4;   // in double2
+    static constexpr int PER_WARP = 3 * 8 * PSTRIDE + 128 + 64 + 8;   // in double2
     static constexpr int PER_WARP_BYTES = PER_WARP * 16;
 };
 
@@ -54,7 +54,8 @@ __device__ __forceinline__ void cdmma(double (&re)[2], double (&im)[2], const do
 }
 
 template <int LEAD, int MINB>
-__global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, const int kmax, const int gexp2) {
+__global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, const int kmax, const int gexp2,
+                                                           const int warps_per_ham, const long long n_warps) {
     constexpr int N = 8, RP = 2, GPW = 8;
     constexpr unsigned FULLM = 0xffffffffu;
     extern __shared__ double2 smem_all[];
@@ -71,25 +72,24 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     double2* XB = wsm;
     double2* YB = XB + 8 * N8TCfg::PSTRIDE;
     double2* WB = YB + 8 * N8TCfg::PSTRIDE;
-    double2* PV = WB + 8 * N8TCfg::PSTRIDE;   // [128]
-    double2* SL = PV + 128;                   // [8 points][8 channels]
-    double2* EB = SL + 64;                    // [8]
-    int* IQ = reinterpret_cast<int*>(EB + 8); // [0..7] Hamiltonian index, [8..15] energy index
+    double2* PV = WB + 8 * N8TCfg::PSTRIDE;   // [128]  pivot rows; before the first inverse: E - Sigma_R per (point, channel)
+    double2* SL = PV + 128;                   // [8 points][8 channels]  E - Sigma_L
+    double2* EB = SL + 64;                    // [8]  energies of the eight points
 
-    const long long pt0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * GPW;
-    long long pt = pt0 + gid;
-    const bool active = pt < p.n_pts;
-    if (!active) pt = p.n_pts - 1;
-    const int ham = (int)(pt / p.nE);
-    const int e = (int)(pt - (long long)ham * p.nE);
+    // A warp owns eight consecutive energies of ONE Hamiltonian (the energy axis is padded to a multiple of
+    // eight per Hamiltonian), so the block fragments of a site are loaded once and shared by the eight points.
+    long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool warp_live = wg < n_warps;
+    if (!warp_live) wg = n_warps - 1;
+    const int ham = (int)(wg / warps_per_ham);
+    const int e_raw = (int)(wg - (long long)ham * warps_per_ham) * GPW + gid;
+    const bool active = warp_live && e_raw < p.nE;
+    const int e = min(e_raw, p.nE - 1);
+    const long long pt = (long long)ham * p.nE + e;
     const cd E = p.E[e];
     const long long nn = (long long)n * n;
-    const double2* hall = reinterpret_cast<const double2*>(p.h);
-    const double2* tall = reinterpret_cast<const double2*>(p.tnn);
-    const double2* hbase = hall + ham * p.h_stride;
-    const double2* tbase = tall + ham * p.t_stride;
-    // one Hamiltonian for the whole warp?  (then block fragments are loaded once per site, not once per point)
-    const bool uniform = __all_sync(FULLM, ham == __shfl_sync(FULLM, ham, 0));
+    const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
+    const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
     const double2 zero2 = make_double2(0.0, 0.0);
 
     auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
@@ -97,10 +97,9 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     // ------------------------------------------------------------------ prologue (Rw): leads of own channels
     double vLo[RP], vRo[RP];
     {
-        double2 sigLd[RP], sigRd[RP];
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
-            sigLd[s] = sigRd[s] = zero2;
+            double2 sigLd = zero2, sigRd = zero2;
             vLo[s] = vRo[s] = 0.0;
             const int r = row0 + s;
             if (full || r < n) {
@@ -111,8 +110,8 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                     const cd gR = g_closed_channel(E, tocd(__ldg(hbase + (long long)(M - 1) * nn + r * n + r)), tR);        // :284,287
                     const cd sl = conj(tL) * (gL * tL);                                                                      // :301
                     const cd sr = tR * (gR * conj(tR));                                                                      // :302
-                    sigLd[s] = make_double2(sl.x, sl.y);
-                    sigRd[s] = make_double2(sr.x, sr.y);
+                    sigLd = make_double2(sl.x, sl.y);
+                    sigRd = make_double2(sr.x, sr.y);
                     vLo[s] = -2.0 * sl.y;                                                                                    // :91
                     vRo[s] = -2.0 * sr.y;
                 } else {
@@ -121,15 +120,15 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                     vRo[s] = -2.0 * reinterpret_cast<const double2*>(p.sigR)[off].y;
                 }
             }
-            PV[gid * 8 + r] = sigRd[s];
-            SL[gid * 8 + r] = sigLd[s];
+            // effective energies of the two end sites (closed leads: Sigma is diagonal; table mode: Sigma is
+            // subtracted as a full block where the site is built, the tables here just hold E)
+            PV[gid * 8 + r] = make_double2(E.x - sigRd.x, E.y - sigRd.y);
+            SL[gid * 8 + r] = make_double2(E.x - sigLd.x, E.y - sigLd.y);
         }
-        if (tid == 0) {
-            EB[gid] = make_double2(E.x, E.y);
-            IQ[gid] = ham;
-            IQ[8 + gid] = e;
-        }
+        if (tid == 0) EB[gid] = make_double2(E.x, E.y);
     }
+    // all energies real?  (every reference driver: then Im of the B fragment does not depend on the point)
+    const bool realE = __all_sync(FULLM, E.y == 0.0);
 
     // ------------------------------------------------------------------ F-role constants
     const double m0 = (gid == 2 * tid) ? 1.0 : 0.0;        // diagonal masks of the two fragment elements
@@ -158,120 +157,124 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         a0 = in0 ? __ldg(blk + (2 * tid) * n + gid) : zero2;
         a1 = in1 ? __ldg(blk + (2 * tid + 1) * n + gid) : zero2;
     };
-    auto hptr = [&](int q, int j) -> const double2* {
-        return (uniform ? hbase : hall + (long long)IQ[q] * p.h_stride) + (long long)j * nn;
-    };
-    auto tval = [&](int q, int j) -> double2 {
-        return __ldg((uniform ? tbase : tall + (long long)IQ[q] * p.t_stride) + (long long)j * nn);
-    };
     auto sigptr = [&](const cd* tab, int q) -> const double2* {
-        return reinterpret_cast<const double2*>(tab) + (long long)IQ[q] * p.sig_stride + (long long)IQ[8 + q] * nn;
+        const int eq = min((e_raw - gid) + q, p.nE - 1);
+        return reinterpret_cast<const double2*>(tab) + ham * p.sig_stride + (long long)eq * nn;
     };
     auto expo = [](double v) -> int { return (int)((hi_abs(v) >> 20) & 0x7ffu) - 1023; };
 
-    // growth of the chunk's recurrence: 2 log2(max|Y|) - log2(prod |t|^2) > gexp2 ?   (warp-uniform)
-    auto grown = [&](const double2 (&Y)[GPW][2], int ke) -> bool {
+    // growth of the chunk's recurrence (warp-uniform): 2 log2 max|U| + log2(scale2) > gexp2 ?
+    // U = Y / d,  scale2 = d^2 / prod |t|^2
+    auto grown = [&](const double2 (&U)[GPW][2], double scale2) -> bool {
         unsigned mx = 0u;
 #pragma unroll
         for (int q = 0; q < GPW; ++q) {
-            mx = max(mx, max(hi_abs(Y[q][0].x), hi_abs(Y[q][0].y)));
-            mx = max(mx, max(hi_abs(Y[q][1].x), hi_abs(Y[q][1].y)));
+            mx = max(mx, max(hi_abs(U[q][0].x), hi_abs(U[q][0].y)));
+            mx = max(mx, max(hi_abs(U[q][1].x), hi_abs(U[q][1].y)));
         }
         mx = __reduce_max_sync(FULLM, mx);
-        return 2 * ((int)(mx >> 20) - 1023) - ke > gexp2;
+        return 2 * ((int)(mx >> 20) - 1023) + expo(scale2) > gexp2;
     };
 
-    // one site inside a chunk:  Q <- P Z_j - |t_j|^2 Q     (P = Y_{j+1}, Q = Y_{j+2} -> Y_j), 0 <= j <= M-2
-    auto site_step = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2], int j, int& ke, double2& tau) -> bool {
-        double2 H0 = zero2, H1 = zero2, tj = zero2;
-        if (uniform) {
-            load_frag(hbase + (long long)j * nn, H0, H1);
-            tj = __ldg(tbase + (long long)j * nn);
+    // One site inside a chunk, in the scaled variables U_j = Y_j / d_j with d_j = -|t_j|^2 d_{j+2}:
+    //     Q <- P (f_j Z_j) + Q,   f_j = d_{j+1} / d_j      (P = U_{j+1}, Q = U_{j+2} -> U_j),  1 <= j+1 <= M-1
+    // so the accumulators start from Q itself (no multiplication); for |t| = 1 the factors are +-1 and the
+    // arithmetic is bit-identical to the unscaled recurrence.  (H0, H1) = f_j * h_j fragment, fj = f_j.
+    auto site_step = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2], int j, double fj, double2 H0, double2 H1) {
+        const double fm0 = fj * m0, fm1 = fj * m1;
+        double2 pad0 = zero2, pad1 = zero2;
+        if (!full) {   // padding channels: z = 1 + |t|^2 keeps D = 1 there; U_pad = 1/d
+            // f_j (1 + kap) with kap = -d_j / d_{j+2}: supplied by the caller through H on the diagonal (see below)
+            pad0 = H0;
+            pad1 = H1;
         }
-        double kmin = 1e300;
+        const bool endsite = (j == 0);
+        const double2* ep = endsite ? SL + gid : EB;
+        const int es = endsite ? 8 : 1;
+        if (realE && !endsite) {
+            const double2 nb0 = make_double2(0.0, H0.y), nb1 = make_double2(0.0, H1.y);   // -Im B
 #pragma unroll
-        for (int q = 0; q < GPW; ++q) {
-            double2 a0 = H0, a1 = H1, t = tj;
-            if (!uniform) {
-                load_frag(hptr(q, j), a0, a1);
-                t = tval(q, j);
+            for (int q = 0; q < GPW; ++q) {
+                const double ex = ep[q * es].x;
+                double b0x = fma(fm0, ex, -H0.x), b1x = fma(fm1, ex, -H1.x);
+                if (!full) {
+                    if (!in0) b0x = pad0.x;
+                    if (!in1) b1x = pad1.x;
+                }
+                double re[2] = {Q[q][0].x, Q[q][1].x};
+                double im[2] = {Q[q][0].y, Q[q][1].y};
+                dmma_8x8x4(re, P[q][0].x, b0x);
+                dmma_8x8x4(im, P[q][0].y, b0x);
+                dmma_8x8x4(re, P[q][0].y, nb0.y);
+                dmma_8x8x4(im, P[q][0].x, -nb0.y);
+                dmma_8x8x4(re, P[q][1].x, b1x);
+                dmma_8x8x4(im, P[q][1].y, b1x);
+                dmma_8x8x4(re, P[q][1].y, nb1.y);
+                dmma_8x8x4(im, P[q][1].x, -nb1.y);
+                Q[q][0] = make_double2(re[0], im[0]);
+                Q[q][1] = make_double2(re[1], im[1]);
             }
-            const double kap = fma(t.x, t.x, t.y * t.y);
-            kmin = fmin(kmin, kap);
-            const double2 Eq = EB[q];
-            double2 b0 = make_double2(fma(m0, Eq.x, -a0.x), fma(m0, Eq.y, -a0.y));
-            double2 b1 = make_double2(fma(m1, Eq.x, -a1.x), fma(m1, Eq.y, -a1.y));
-            if (j == 0) {
-                if (LEAD == LEAD_CLOSED) {
-                    const double2 sg = SL[q * 8 + gid];
-                    b0.x = fma(-m0, sg.x, b0.x);  b0.y = fma(-m0, sg.y, b0.y);
-                    b1.x = fma(-m1, sg.x, b1.x);  b1.y = fma(-m1, sg.y, b1.y);
-                } else {
+        } else {
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {
+                const double2 Eq = ep[q * es];
+                double2 b0 = make_double2(fma(fm0, Eq.x, -H0.x), fma(fm0, Eq.y, -H0.y));
+                double2 b1 = make_double2(fma(fm1, Eq.x, -H1.x), fma(fm1, Eq.y, -H1.y));
+                if (LEAD == LEAD_TABLE && endsite) {
                     double2 s0, s1;
                     load_frag(sigptr(p.sigL, q), s0, s1);
-                    b0.x -= s0.x;  b0.y -= s0.y;
-                    b1.x -= s1.x;  b1.y -= s1.y;
+                    b0.x = fma(-fj, s0.x, b0.x);  b0.y = fma(-fj, s0.y, b0.y);
+                    b1.x = fma(-fj, s1.x, b1.x);  b1.y = fma(-fj, s1.y, b1.y);
                 }
+                if (!full) {
+                    if (!in0) b0 = make_double2(pad0.x, 0.0);
+                    if (!in1) b1 = make_double2(pad1.x, 0.0);
+                }
+                double re[2] = {Q[q][0].x, Q[q][1].x};
+                double im[2] = {Q[q][0].y, Q[q][1].y};
+                cdmma(re, im, P[q][0], b0);
+                cdmma(re, im, P[q][1], b1);
+                Q[q][0] = make_double2(re[0], im[0]);
+                Q[q][1] = make_double2(re[1], im[1]);
             }
-            if (!in0) b0 = make_double2(m0 * (1.0 + kap), 0.0);    // padding channels: D stays the identity there
-            if (!in1) b1 = make_double2(m1 * (1.0 + kap), 0.0);
-            double re[2] = {-kap * Q[q][0].x, -kap * Q[q][1].x};
-            double im[2] = {-kap * Q[q][0].y, -kap * Q[q][1].y};
-            cdmma(re, im, P[q][0], b0);
-            cdmma(re, im, P[q][1], b1);
-            Q[q][0] = make_double2(re[0], im[0]);
-            Q[q][1] = make_double2(re[1], im[1]);
         }
-        ke += expo(kmin);
-        if (uniform) tau = cmul2(tau, make_double2(tj.x, -tj.y));
-        return grown(Q, ke);
     };
 
     double2 Ya[GPW][2], Yb[GPW][2];
-    bool first = true;
     int j = M - 1;
     while (j >= 0) {
         // -------------------------------------------------------------- chunk start at site b:
         //   Ya <- Z_b - |t_b|^2 g_{b+1}^T   (Ya holds g_{b+1}^T; first chunk: Z_{M-1} with Sigma_R),   Yb <- I
         const int b = j;
-        int ke = 0;
         double2 tau = make_double2(1.0, 0.0);
+        double S2;                                    // prod |t_i|^2 over the chunk's sites (growth normaliser)
         {
             const int jt = (b < M - 1) ? b : M - 2;
-            double2 H0 = zero2, H1 = zero2, tj = zero2;
-            if (uniform) {
-                load_fragT(hbase + (long long)b * nn, H0, H1);
-                tj = __ldg(tbase + (long long)jt * nn);
-            }
-            double kmin = 1e300;
+            double2 a0, a1;
+            load_fragT(hbase + (long long)b * nn, a0, a1);
+            const double2 tj = __ldg(tbase + (long long)jt * nn);
+            S2 = fma(tj.x, tj.x, tj.y * tj.y);
+            const double kap = (b < M - 1) ? S2 : 0.0;
+            if (b < M - 1) tau = make_double2(tj.x, -tj.y);
+            const bool endsite = (b == 0 || b == M - 1);
+            const double2* ep = (b == 0) ? SL + gid : ((b == M - 1) ? PV + gid : EB);
+            const int es = endsite ? 8 : 1;
 #pragma unroll
             for (int q = 0; q < GPW; ++q) {
-                double2 a0 = H0, a1 = H1, t = tj;
-                if (!uniform) {
-                    load_fragT(hptr(q, b), a0, a1);
-                    t = tval(q, jt);
-                }
-                const double kscale = fma(t.x, t.x, t.y * t.y);
-                kmin = fmin(kmin, kscale);
-                const double kap = (b < M - 1) ? kscale : 0.0;
-                const double2 Eq = EB[q];
+                const double2 Eq = ep[q * es];
                 double2 z0 = make_double2(fma(m0, Eq.x, -a0.x), fma(m0, Eq.y, -a0.y));
                 double2 z1 = make_double2(fma(m1, Eq.x, -a1.x), fma(m1, Eq.y, -a1.y));
-                if (b == M - 1 || b == 0) {
-                    if (LEAD == LEAD_CLOSED) {
-                        const double2 sg = (b == 0) ? SL[q * 8 + gid] : PV[q * 8 + gid];
-                        z0.x = fma(-m0, sg.x, z0.x);  z0.y = fma(-m0, sg.y, z0.y);
-                        z1.x = fma(-m1, sg.x, z1.x);  z1.y = fma(-m1, sg.y, z1.y);
-                    } else {
-                        double2 s0, s1;
-                        load_fragT(sigptr(b == 0 ? p.sigL : p.sigR, q), s0, s1);
-                        z0.x -= s0.x;  z0.y -= s0.y;
-                        z1.x -= s1.x;  z1.y -= s1.y;
-                    }
+                if (LEAD == LEAD_TABLE && endsite) {
+                    double2 s0, s1;
+                    load_fragT(sigptr(b == 0 ? p.sigL : p.sigR, q), s0, s1);
+                    z0.x -= s0.x;  z0.y -= s0.y;
+                    z1.x -= s1.x;  z1.y -= s1.y;
                 }
-                if (!in0) z0 = make_double2(m0 * (1.0 + kap), 0.0);
-                if (!in1) z1 = make_double2(m1 * (1.0 + kap), 0.0);
-                if (first) {
+                if (!full) {
+                    if (!in0) z0 = make_double2(m0 * (1.0 + kap), 0.0);
+                    if (!in1) z1 = make_double2(m1 * (1.0 + kap), 0.0);
+                }
+                if (b == M - 1) {
                     Ya[q][0] = z0;
                     Ya[q][1] = z1;
                 } else {
@@ -281,30 +284,55 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 Yb[q][0] = make_double2(m0, 0.0);
                 Yb[q][1] = make_double2(m1, 0.0);
             }
-            ke = expo(kmin);
-            if (uniform && b < M - 1) tau = make_double2(tj.x, -tj.y);
         }
         int k = 1, phase = 0;
-        bool grow = grown(Ya, ke);
+        double dcur = 1.0, dprev = 1.0;               // d_{j}, d_{j+1} of the scaled recurrence
+        bool grow = grown(Ya, 1.0 / S2);
         while (j > 0 && k < kmax && !grow) {
+            const double2 tj = __ldg(tbase + (long long)(j - 1) * nn);
+            const double kap = fma(tj.x, tj.x, tj.y * tj.y);
+            if (!(kap > 0.0)) break;                  // decoupled site (or NaN): it starts its own chunk
             --j;
             ++k;
-            if (phase == 0) grow = site_step(Ya, Yb, j, ke, tau);
-            else grow = site_step(Yb, Ya, j, ke, tau);
+            const double dj = -kap * dprev;           // d_j = -|t_j|^2 d_{j+2}
+            const double fj = dcur / dj;              // f_j = d_{j+1} / d_j
+            double2 H0, H1;
+            load_frag(hbase + (long long)j * nn, H0, H1);
+            H0 = make_double2(fj * H0.x, fj * H0.y);
+            H1 = make_double2(fj * H1.x, fj * H1.y);
+            if (!full) {                              // padding: B diagonal = f_j (1 + kap), handed over in H
+                if (!in0) H0 = make_double2(m0 * fj * (1.0 + kap), 0.0);
+                if (!in1) H1 = make_double2(m1 * fj * (1.0 + kap), 0.0);
+            }
+            if (phase == 0) site_step(Ya, Yb, j, fj, H0, H1);
+            else site_step(Yb, Ya, j, fj, H0, H1);
             phase ^= 1;
+            dprev = dcur;
+            dcur = dj;
+            S2 *= kap;
+            tau = cmul2(tau, make_double2(tj.x, -tj.y));
+            grow = (phase == 0) ? grown(Ya, dj * dj / S2) : grown(Yb, dj * dj / S2);
         }
         const int a = j;
 
         // -------------------------------------------------------------- close the chunk at site a
-        // D_a -> XB (slot (q; r; c) = D_a[r][c] = Y_a[c][r]),  Y_{a+1} -> YB stored transposed
+        // D_a / d_a -> XB (slot (q; r; c) = U_a[c][r]),  U_{a+1} -> YB stored transposed
+        if (phase == 0) {
 #pragma unroll
-        for (int q = 0; q < GPW; ++q) {
-            const double2 c0 = phase ? Yb[q][0] : Ya[q][0], c1 = phase ? Yb[q][1] : Ya[q][1];
-            const double2 p0 = phase ? Ya[q][0] : Yb[q][0], p1 = phase ? Ya[q][1] : Yb[q][1];
-            XB[q * N8TCfg::PSTRIDE + x0i] = c0;
-            XB[q * N8TCfg::PSTRIDE + x1i] = c1;
-            YB[q * N8TCfg::PSTRIDE + x0i] = p0;
-            YB[q * N8TCfg::PSTRIDE + x1i] = p1;
+            for (int q = 0; q < GPW; ++q) {
+                XB[q * N8TCfg::PSTRIDE + x0i] = Ya[q][0];
+                XB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
+                YB[q * N8TCfg::PSTRIDE + x0i] = Yb[q][0];
+                YB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {
+                XB[q * N8TCfg::PSTRIDE + x0i] = Yb[q][0];
+                XB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
+                YB[q * N8TCfg::PSTRIDE + x0i] = Ya[q][0];
+                YB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
+            }
         }
         __syncwarp();
         {
@@ -317,36 +345,33 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             __syncwarp();
             n8_invert<0, 1>(A, PV, xb, gid, row0, p.singular, zmask);   // X[k][c] -> slot (c; k): stored transposed
         }
-        // W <- tau W X   and   g_a^T = X^T Y_{a+1}   (the X fragment serves as B of the first and A of the second)
+        // W <- tau W X   and   g_a^T = X^T Y_{a+1}   (the X fragment serves as B of the first and A of the second);
+        // undoing the scaling:  X = Xs / d_a,  Y_{a+1} = d_{a+1} U_{a+1}
+        {
+            const double rda = 1.0 / dcur;
+            const double gsc = (k > 1 ? dprev : 1.0) * rda;
+            const double2 tq = make_double2(tau.x * rda, tau.y * rda);
 #pragma unroll
-        for (int q = 0; q < GPW; ++q) {
-            const double2* xq = XB + q * N8TCfg::PSTRIDE;
-            double2* wq = WB + q * N8TCfg::PSTRIDE;
-            const double2* yq = YB + q * N8TCfg::PSTRIDE;
-            const double2 x0 = xq[f0i], x1 = xq[f1i];     // X[2t+s][g]
-            const double2 w0 = wq[f0i], w1 = wq[f1i];     // W[g][2t+s]
-            const double2 y0 = yq[f0i], y1 = yq[f1i];     // Y_{a+1}[2t+s][g]
-            double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};
-            double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
-            cdmma(wr, wi, w0, x0);
-            cdmma(gr, gi, x0, y0);
-            cdmma(wr, wi, w1, x1);
-            cdmma(gr, gi, x1, y1);
-            double2 tq = tau;
-            if (!uniform) {
-                tq = make_double2(1.0, 0.0);
-                for (int i = a; i <= b && i < M - 1; ++i) {
-                    const double2 t = tval(q, i);
-                    tq = cmul2(tq, make_double2(t.x, -t.y));
-                }
+            for (int q = 0; q < GPW; ++q) {
+                const double2* xq = XB + q * N8TCfg::PSTRIDE;
+                double2* wq = WB + q * N8TCfg::PSTRIDE;
+                const double2* yq = YB + q * N8TCfg::PSTRIDE;
+                const double2 x0 = xq[f0i], x1 = xq[f1i];     // Xs[2t+s][g]
+                const double2 w0 = wq[f0i], w1 = wq[f1i];     // W[g][2t+s]
+                const double2 y0 = yq[f0i], y1 = yq[f1i];     // U_{a+1}[2t+s][g]
+                double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};
+                double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
+                cdmma(wr, wi, w0, x0);
+                cdmma(gr, gi, x0, y0);
+                cdmma(wr, wi, w1, x1);
+                cdmma(gr, gi, x1, y1);
+                wq[f0i] = make_double2(fma(wr[0], tq.x, -(wi[0] * tq.y)), fma(wi[0], tq.x, wr[0] * tq.y));
+                wq[f1i] = make_double2(fma(wr[1], tq.x, -(wi[1] * tq.y)), fma(wi[1], tq.x, wr[1] * tq.y));
+                Ya[q][0] = make_double2(gr[0] * gsc, gi[0] * gsc);
+                Ya[q][1] = make_double2(gr[1] * gsc, gi[1] * gsc);
             }
-            wq[f0i] = make_double2(fma(wr[0], tq.x, -(wi[0] * tq.y)), fma(wi[0], tq.x, wr[0] * tq.y));
-            wq[f1i] = make_double2(fma(wr[1], tq.x, -(wi[1] * tq.y)), fma(wi[1], tq.x, wr[1] * tq.y));
-            Ya[q][0] = make_double2(gr[0], gi[0]);
-            Ya[q][1] = make_double2(gr[1], gi[1]);
         }
         __syncwarp();   // every fragment of X and Y_{a+1} has been read: XB / YB may be overwritten
-        first = false;
         j = a - 1;
     }
 
