@@ -21,4 +21,8 @@ for which, name in ((0, "shfl_b32_Gwarpinstr_s"), (1, "lds128_groupbcast_Gwarpin
 for w in (10, 11, 12, 13):
     _lib.check(lib.tx_microbench(w, ctypes.byref(v)))
     out["dfma_tflops_%d_warps_per_scheduler" % (w - 9)] = v.value
+for wps in (1, 2, 3):
+    for ch in (1, 2, 4, 8, 16):
+        _lib.check(lib.tx_microbench(100 * wps + ch, ctypes.byref(v)))
+        out["dmma_tflops_%dwps_%dchains" % (wps, ch)] = round(v.value, 2)
 print(json.dumps(out))

@@ -122,8 +122,8 @@ int materialise_affine(SweepParams& p, cudaStream_t st) {
 }
 
 // Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.
-template <int LEAD, int MINB>
-int launch_n8t(SweepParams p, cudaStream_t st) {
+template <int LEAD, int MINB, bool FULL>
+int launch_n8t_full(SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
     p.nondiag_max = nullptr;
     p.site_class = nullptr;
@@ -136,7 +136,7 @@ int launch_n8t(SweepParams p, cudaStream_t st) {
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
     // a warp = eight consecutive energies of one Hamiltonian (energy axis padded to a multiple of eight)
@@ -144,10 +144,15 @@ int launch_n8t(SweepParams p, cudaStream_t st) {
     const long long n_warps = (p.n_pts / p.nE) * warps_per_ham;
     const long long blocks = (n_warps + WARPS - 1) / WARPS;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8t<LEAD, MINB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
+    rgf_sweep_n8t<LEAD, MINB, FULL><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
+}
+
+template <int LEAD, int MINB>
+int launch_n8t(const SweepParams& p, cudaStream_t st) {
+    return p.n == 8 ? launch_n8t_full<LEAD, MINB, true>(p, st) : launch_n8t_full<LEAD, MINB, false>(p, st);
 }
 
 template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>

@@ -44,6 +44,28 @@ __global__ void __launch_bounds__(256) dmma_loop(double* out, double a, double b
     if (s == 123.456) out[0] = s;
 }
 
+// DMMA with CH independent accumulator chains per warp (latency / occupancy scan)
+template <int CH>
+__global__ void __launch_bounds__(128) dmma_chain_loop(double* out, double a, double b) {
+    double c[CH][2];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) c[i][0] = c[i][1] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 16 / CH; ++r)
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[i][0]), "+d"(c[i][1])
+                             : "d"(a), "d"(b));
+            }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
 // DFMA and DMMA issued back to back from the same warp: do the two FP64 paths share one pipe?
 __global__ void __launch_bounds__(256) dfma_dmma_loop(double* out, double a, double b) {
     double c[4][2];
@@ -235,6 +257,17 @@ int tx_microbench(int which, double* value) {
         const int thr = 128, blk = sm_count() * wps;       // wps blocks of 4 warps per SM
         rc = time_kernel([&] { dfma_loop<<<blk, thr>>>(d, 1.0000001, 0.9999999); }, &ms);
         *value = 2.0 * 16.0 * ITERS * (double)blk * thr / (ms * 1e-3) / 1e12;
+    } else if (which >= 100 && which < 1000) {
+        // DMMA TFLOP/s with (which/100) warps per scheduler and (which%100) independent chains per warp (16 DMMA per iteration)
+        const int wps = which / 100, ch = which % 100;
+        const int thr = 128, blk = sm_count() * wps;
+        auto go = [&](auto kern) { return time_kernel([&] { kern<<<blk, thr>>>(d, 1.0000001, 0.9999999); }, &ms); };
+        if (ch == 1) rc = go(dmma_chain_loop<1>);
+        else if (ch == 2) rc = go(dmma_chain_loop<2>);
+        else if (ch == 4) rc = go(dmma_chain_loop<4>);
+        else if (ch == 8) rc = go(dmma_chain_loop<8>);
+        else if (ch == 16) rc = go(dmma_chain_loop<16>);
+        *value = 2.0 * 256.0 * 16.0 * ITERS * (double)blk * (thr / 32) / (ms * 1e-3) / 1e12;
     } else if (which == 3) {
         rc = time_kernel([&] { mix_loop<<<blocks, threads>>>(d, 1.0000001, 0.5); }, &ms);
         *value = 2.0 * 32.0 * ITERS * warps * 32 / (ms * 1e-3) / 1e12;

@@ -53,7 +53,7 @@ __device__ __forceinline__ void cdmma(double (&re)[2], double (&im)[2], const do
     dmma_8x8x4(im, a.y, b.x);
 }
 
-template <int LEAD, int MINB>
+template <int LEAD, int MINB, bool FULL>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, const int kmax, const int gexp2,
                                                            const int warps_per_ham, const long long n_warps) {
     constexpr int N = 8, RP = 2, GPW = 8;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     const int row0 = tid * RP;
     const int n = p.n;
     const int M = p.M;
-    const bool full = (n == N);
+    constexpr bool full = FULL;    // n == 8 (no padding channels)
 
     double2* wsm = smem_all + (size_t)warp * N8TCfg::PER_WARP;
     double2* XB = wsm;
@@ -192,27 +192,38 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         const double2* ep = endsite ? SL + gid : EB;
         const int es = endsite ? 8 : 1;
         if (realE && !endsite) {
-            const double2 nb0 = make_double2(0.0, H0.y), nb1 = make_double2(0.0, H1.y);   // -Im B
+            // B = (b_s.x, -H_s.y): the imaginary part is common to the eight points.  The DMMAs are issued in four
+            // rounds over four points (asm volatile keeps this order): dependent instructions sit 8 apart.
+            const double hy0 = H0.y, hy1 = H1.y, ny0 = -H0.y, ny1 = -H1.y;
 #pragma unroll
-            for (int q = 0; q < GPW; ++q) {
-                const double ex = ep[q * es].x;
-                double b0x = fma(fm0, ex, -H0.x), b1x = fma(fm1, ex, -H1.x);
-                if (!full) {
-                    if (!in0) b0x = pad0.x;
-                    if (!in1) b1x = pad1.x;
+            for (int q4 = 0; q4 < GPW; q4 += 4) {
+                double b0x[4], b1x[4], re[4][2], im[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q4 + u;
+                    const double ex = ep[q * es].x;
+                    b0x[u] = fma(fm0, ex, -H0.x);
+                    b1x[u] = fma(fm1, ex, -H1.x);
+                    if (!full) {
+                        if (!in0) b0x[u] = pad0.x;
+                        if (!in1) b1x[u] = pad1.x;
+                    }
+                    re[u][0] = Q[q][0].x;  re[u][1] = Q[q][1].x;
+                    im[u][0] = Q[q][0].y;  im[u][1] = Q[q][1].y;
                 }
-                double re[2] = {Q[q][0].x, Q[q][1].x};
-                double im[2] = {Q[q][0].y, Q[q][1].y};
-                dmma_8x8x4(re, P[q][0].x, b0x);
-                dmma_8x8x4(im, P[q][0].y, b0x);
-                dmma_8x8x4(re, P[q][0].y, nb0.y);
-                dmma_8x8x4(im, P[q][0].x, -nb0.y);
-                dmma_8x8x4(re, P[q][1].x, b1x);
-                dmma_8x8x4(im, P[q][1].y, b1x);
-                dmma_8x8x4(re, P[q][1].y, nb1.y);
-                dmma_8x8x4(im, P[q][1].x, -nb1.y);
-                Q[q][0] = make_double2(re[0], im[0]);
-                Q[q][1] = make_double2(re[1], im[1]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { dmma_8x8x4(re[u], P[q4 + u][0].x, b0x[u]);  dmma_8x8x4(im[u], P[q4 + u][0].y, b0x[u]); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { dmma_8x8x4(re[u], P[q4 + u][0].y, hy0);     dmma_8x8x4(im[u], P[q4 + u][0].x, ny0); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { dmma_8x8x4(re[u], P[q4 + u][1].x, b1x[u]);  dmma_8x8x4(im[u], P[q4 + u][1].y, b1x[u]); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { dmma_8x8x4(re[u], P[q4 + u][1].y, hy1);     dmma_8x8x4(im[u], P[q4 + u][1].x, ny1); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    Q[q4 + u][0] = make_double2(re[u][0], im[u][0]);
+                    Q[q4 + u][1] = make_double2(re[u][1], im[u][1]);
+                }
             }
         } else {
 #pragma unroll
@@ -286,32 +297,47 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             }
         }
         int k = 1, phase = 0;
-        double dcur = 1.0, dprev = 1.0;               // d_{j}, d_{j+1} of the scaled recurrence
-        bool grow = grown(Ya, 1.0 / S2);
+        // scaled recurrence: d_j = -|t_j|^2 d_{j+2}; both d and 1/d are tracked by multiplication (one MUFU
+        // reciprocal of |t_j|^2 per site, no division)
+        double dcur = 1.0, dprev = 1.0, rdcur = 1.0, rdprev = 1.0;   // d_j, d_{j+1} and reciprocals
+        double rS2 = fast_rcp(S2);                                   // 1 / prod |t_i|^2
+        bool grow = grown(Ya, rS2);
+        // next site's fragment and hopping, one site ahead of the tensor-core work
+        double2 Hn0 = zero2, Hn1 = zero2, tn = zero2;
+        if (j > 0) {
+            load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
+            tn = __ldg(tbase + (long long)(j - 1) * nn);
+        }
         while (j > 0 && k < kmax && !grow) {
-            const double2 tj = __ldg(tbase + (long long)(j - 1) * nn);
+            const double2 tj = tn;
             const double kap = fma(tj.x, tj.x, tj.y * tj.y);
             if (!(kap > 0.0)) break;                  // decoupled site (or NaN): it starts its own chunk
             --j;
             ++k;
+            const double rk = fast_rcp(kap);
             const double dj = -kap * dprev;           // d_j = -|t_j|^2 d_{j+2}
-            const double fj = dcur / dj;              // f_j = d_{j+1} / d_j
-            double2 H0, H1;
-            load_frag(hbase + (long long)j * nn, H0, H1);
-            H0 = make_double2(fj * H0.x, fj * H0.y);
-            H1 = make_double2(fj * H1.x, fj * H1.y);
+            const double rdj = -rk * rdprev;
+            const double fj = dcur * rdj;             // f_j = d_{j+1} / d_j
+            double2 H0 = make_double2(fj * Hn0.x, fj * Hn0.y);
+            double2 H1 = make_double2(fj * Hn1.x, fj * Hn1.y);
             if (!full) {                              // padding: B diagonal = f_j (1 + kap), handed over in H
                 if (!in0) H0 = make_double2(m0 * fj * (1.0 + kap), 0.0);
                 if (!in1) H1 = make_double2(m1 * fj * (1.0 + kap), 0.0);
+            }
+            if (j > 0) {
+                load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
+                tn = __ldg(tbase + (long long)(j - 1) * nn);
             }
             if (phase == 0) site_step(Ya, Yb, j, fj, H0, H1);
             else site_step(Yb, Ya, j, fj, H0, H1);
             phase ^= 1;
             dprev = dcur;
             dcur = dj;
-            S2 *= kap;
+            rdprev = rdcur;
+            rdcur = rdj;
+            rS2 *= rk;
             tau = cmul2(tau, make_double2(tj.x, -tj.y));
-            grow = (phase == 0) ? grown(Ya, dj * dj / S2) : grown(Yb, dj * dj / S2);
+            grow = (phase == 0) ? grown(Ya, dj * dj * rS2) : grown(Yb, dj * dj * rS2);
         }
         const int a = j;
 
@@ -348,8 +374,8 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         // W <- tau W X   and   g_a^T = X^T Y_{a+1}   (the X fragment serves as B of the first and A of the second);
         // undoing the scaling:  X = Xs / d_a,  Y_{a+1} = d_{a+1} U_{a+1}
         {
-            const double rda = 1.0 / dcur;
-            const double gsc = (k > 1 ? dprev : 1.0) * rda;
+            const double rda = rdcur;
+            const double gsc = dprev * rda;
             const double2 tq = make_double2(tau.x * rda, tau.y * rda);
 #pragma unroll
             for (int q = 0; q < GPW; ++q) {
