@@ -70,7 +70,7 @@ int round_up_block(int n) {
 // number of resident 128-thread blocks per SM the register allocation is capped for.
 int g_variant = 13;
 int g_chunk_kmax = 8;    // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
-int g_chunk_gexp = 6;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
+int g_chunk_gexp = 5;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     // ------------------------------------------------------------------ prologue (Rw): leads of own channels
     double vLo[RP], vRo[RP];
     {
+        auto same2 = [](cd a, cd b) -> bool { return a.x == b.x && a.y == b.y; };
+        cd eLp = mk(0.0, 0.0), tLp = mk(0.0, 0.0), gLp = mk(0.0, 0.0);
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
             double2 sigLd = zero2, sigRd = zero2;
@@ -106,8 +108,14 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 if (LEAD == LEAD_CLOSED) {
                     const cd tL = tocd(__ldg(tbase + (long long)r * n + r));
                     const cd tR = tocd(__ldg(tbase + (long long)(M - 2) * nn + r * n + r));
-                    const cd gL = g_closed_channel(E, tocd(__ldg(hbase + (long long)r * n + r)), tL);                       // wfm/__init__.py:283,286
-                    const cd gR = g_closed_channel(E, tocd(__ldg(hbase + (long long)(M - 1) * nn + r * n + r)), tR);        // :284,287
+                    const cd eL = tocd(__ldg(hbase + (long long)r * n + r));
+                    const cd eR = tocd(__ldg(hbase + (long long)(M - 1) * nn + r * n + r));
+                    // identical channels / identical leads (the usual case) are evaluated once
+                    const bool sameLprev = (s > 0) && same2(eL, eLp) && same2(tL, tLp);
+                    const cd gL = sameLprev ? gLp : g_closed_channel(E, eL, tL);                                            // wfm/__init__.py:283,286
+                    const bool sameRL = same2(eR, eL) && same2(tR, tL);
+                    const cd gR = sameRL ? gL : g_closed_channel(E, eR, tR);                                                // :284,287
+                    eLp = eL;  tLp = tL;  gLp = gL;
                     const cd sl = conj(tL) * (gL * tL);                                                                      // :301
                     const cd sr = tR * (gR * conj(tR));                                                                      // :302
                     sigLd = make_double2(sl.x, sl.y);
@@ -301,17 +309,22 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         // reciprocal of |t_j|^2 per site, no division)
         double dcur = 1.0, dprev = 1.0, rdcur = 1.0, rdprev = 1.0;   // d_j, d_{j+1} and reciprocals
         double rS2 = fast_rcp(S2);                                   // 1 / prod |t_i|^2
-        bool grow = grown(Ya, rS2);
+        // The growth test lags one site behind the recurrence (it looks at P = U_{j+1} while the tensor cores
+        // work on U_j), so that its integer reduction never sits between two sites' DMMAs.
+        double nrm = rS2;                             // d_{j+1}^2 / prod |t|^2 for the matrix under test
         // next site's fragment and hopping, one site ahead of the tensor-core work
         double2 Hn0 = zero2, Hn1 = zero2, tn = zero2;
         if (j > 0) {
             load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
             tn = __ldg(tbase + (long long)(j - 1) * nn);
         }
-        while (j > 0 && k < kmax && !grow) {
+        // one more site: Q <- U_j from P = U_{j+1}; false if the chunk has to be closed at the current site
+        auto advance = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2]) -> bool {
+            if (!(j > 0 && k < kmax)) return false;
             const double2 tj = tn;
             const double kap = fma(tj.x, tj.x, tj.y * tj.y);
-            if (!(kap > 0.0)) break;                  // decoupled site (or NaN): it starts its own chunk
+            if (!(kap > 0.0)) return false;           // decoupled site (or NaN): it starts its own chunk
+            if (grown(P, nrm)) return false;
             --j;
             ++k;
             const double rk = fast_rcp(kap);
@@ -328,16 +341,20 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
                 tn = __ldg(tbase + (long long)(j - 1) * nn);
             }
-            if (phase == 0) site_step(Ya, Yb, j, fj, H0, H1);
-            else site_step(Yb, Ya, j, fj, H0, H1);
+            site_step(P, Q, j, fj, H0, H1);
             phase ^= 1;
             dprev = dcur;
             dcur = dj;
             rdprev = rdcur;
             rdcur = rdj;
             rS2 *= rk;
+            nrm = dj * dj * rS2;
             tau = cmul2(tau, make_double2(tj.x, -tj.y));
-            grow = (phase == 0) ? grown(Ya, dj * dj * rS2) : grown(Yb, dj * dj * rS2);
+            return true;
+        };
+        for (;;) {                                    // two sites per round: the arrays swap roles without moves
+            if (!advance(Ya, Yb)) break;
+            if (!advance(Yb, Ya)) break;
         }
         const int a = j;
 
@@ -411,10 +428,15 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     // ------------------------------------------------------------------ epilogue (K3, Rw role)
     double sqL[RP], sqR[RP];
 #pragma unroll
-    for (int s = 0; s < RP; ++s) {
-        sqL[s] = sqrt(vLo[s]);
-        sqR[s] = sqrt(vRo[s]);
-        PV[(row0 + s) * GPW + gid] = make_double2(vLo[s], 1.0 / sqL[s]);
+    for (int s = 0; s < RP; ++s) {   // equal velocities (the usual case) share one square root / reciprocal
+        sqL[s] = (s > 0 && vLo[s] == vLo[0]) ? sqL[0] : sqrt(vLo[s]);
+        sqR[s] = (vRo[s] == vLo[s]) ? sqL[s] : ((s > 0 && vRo[s] == vRo[0]) ? sqR[0] : sqrt(vRo[s]));
+    }
+    {
+        const double r0 = 1.0 / sqL[0];
+        const double r1 = (sqL[1] == sqL[0]) ? r0 : 1.0 / sqL[1];
+        PV[(row0 + 0) * GPW + gid] = make_double2(vLo[0], r0);
+        PV[(row0 + 1) * GPW + gid] = make_double2(vLo[1], r1);
     }
     __syncwarp();
     double vL[N], rsL[N];

@@ -90,8 +90,16 @@ __device__ __forceinline__ cd g_closed_channel(cd E, cd eps, cd t) {
         // All reference drivers: real energy, real lead parameters.  Same formula, real arithmetic
         // (identical results: Smith division by a real divisor and csqrt of a real are exact maps).
         const double dr = E.x - eps.x;
-        const double lam = dr / (2.0 * t.x);
-        const double first = lam / t.x;
+        double lam, first;
+        if ((__double2hiint(t.x) & 0x000fffff) == 0 && __double2loint(t.x) == 0 && fabs(t.x) > 1e-300 && fabs(t.x) < 1e300) {
+            // |t| a power of two (t = -1 in every reference driver): the two divisions are exact products
+            const double rt = 1.0 / t.x;
+            lam = dr * (0.5 * rt);
+            first = lam * rt;
+        } else {
+            lam = dr / (2.0 * t.x);
+            first = lam / t.x;
+        }
         const double z = __dsub_rn(__dmul_rn(lam, lam), 1.0);   // rounded product first, like numpy (no fma)
         const double sg = (dr > 0.0) - (dr < 0.0);
         const double root = sqrt(fabs(z));
