@@ -23,6 +23,10 @@ from transport_b200 import _lib, configs, leads  # noqa: E402
 lib = _lib.load()
 if os.environ.get("TX_VARIANT"):
     _lib.check(lib.tx_set_variant(int(os.environ["TX_VARIANT"])))
+if os.environ.get("TX_KMAX"):
+    _lib.check(lib.tx_set_option(1, int(os.environ["TX_KMAX"])))
+if os.environ.get("TX_GEXP"):
+    _lib.check(lib.tx_set_option(2, int(os.environ["TX_GEXP"])))
 if os.environ.get("TX_NO_STRUCTURE"):
     _lib.check(lib.tx_set_option(0, 0))
 dev = torch.device("cuda", 0)

@@ -7,6 +7,8 @@ lib = _lib.load(); dev = torch.device("cuda", 0)
 def dev_c(a): return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 _lib.check(lib.tx_set_variant(variant))
+if os.environ.get('TX_KMAX'): _lib.check(lib.tx_set_option(1, int(os.environ['TX_KMAX'])))
+if os.environ.get('TX_GEXP'): _lib.check(lib.tx_set_option(2, int(os.environ['TX_GEXP'])))
 Js, Es = configs.cfg2_grid(1000, 1000)
 out = {}
 for NB in (3, 11, 27):

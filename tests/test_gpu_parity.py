@@ -416,12 +416,12 @@ def test_all_kernel_variants_agree():
     lib = _lib.load()
     g = load_golden("cfg2_cicc.npz")
     try:
-        for v in range(11):
+        for v in list(range(11)) + [13]:
             _lib.check(lib.tx_set_variant(v))
             R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], want_resid=True)
             _check(R, T, g["R"], g["T"], res)
     finally:
-        _lib.check(lib.tx_set_variant(6))
+        _lib.check(lib.tx_set_variant(13))
     rng = np.random.default_rng(3)
     for n in (5, 6, 7, 8):
         M = 6
@@ -475,7 +475,7 @@ def test_landauer_current_and_rhat_extensions():
 def test_cfg2_full_size_properties():
     """BASELINE config 2 at full size (1000 J x 1000 E x 8 sources) through the host C ABI: unitarity on all
     8e6 (point, source) pairs, the golden rows, T_total = sum of channels, and sweep linearity in the batch
-    (a sub-batch reproduces the same bits)."""
+    (a warp-aligned sub-batch reproduces the same bits)."""
     h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
     Js, Es = configs.cfg2_grid(1000, 1000)
     R, T, res, tot = transmission_sweep(h0, tnn, Es, h1=h1, params=Js, want_resid=True, want_total=True)
@@ -487,8 +487,12 @@ def test_cfg2_full_size_properties():
     g = load_golden("cfg2_cicc.npz")
     for k, jidx in enumerate([0, 250, 500, 750, 999]):
         _check(R[jidx, ::40], T[jidx, ::40], g["R"][k], g["T"][k])
-    R2, T2 = transmission_sweep(h0, tnn, Es[100:133], h1=h1, params=Js[400:403])
-    assert np.array_equal(T2, T[400:403, 100:133]) and np.array_equal(R2, R[400:403, 100:133])
+    # a sub-batch aligned to the eight energies of a warp reproduces the same bits; an unaligned, short one
+    # (served by the point-per-4-lanes kernel) the same numbers
+    R2, T2 = transmission_sweep(h0, tnn, Es[96:136], h1=h1, params=Js[400:403])
+    assert np.array_equal(T2, T[400:403, 96:136]) and np.array_equal(R2, R[400:403, 96:136])
+    R3, T3 = transmission_sweep(h0, tnn, Es[100:133], h1=h1, params=Js[400:403])
+    assert rt_err(T3, T[400:403, 100:133]) < 1e-11 and rt_err(R3, R[400:403, 100:133]) < 1e-11
 
 
 def test_cfg1_full_size_and_cfg3_long_chain_properties():
@@ -551,3 +555,86 @@ def test_diagonal_tail_fast_path_matches_block_path():
         assert np.max(np.abs(res)) < UNIT
         oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(n))
         _check(Rf[0], Tf[0], oR, oT)
+
+
+# ------------------------------------------------------------------------------- telescoped sweep (rgf_n8t.cuh)
+def _telescoped_cases():
+    rng = np.random.default_rng(41)
+    cases = {}
+    cases["disorder_n8"] = configs.disordered_blocks(N=40, n=8, W=0.3, seed=3)[:2]
+    cases["disorder_n6_padded"] = configs.disordered_blocks(N=21, n=6, W=0.2, seed=4)[:2]
+    # evanescent barrier of mixed heights between two channel-coupling regions: the growth bound has to close chunks
+    h, tnn, _ = configs.disordered_blocks(N=50, n=8, W=0.2, seed=5)
+    for j in range(15, 35):
+        h[j] += np.diag(rng.uniform(0.0, 5.0, 8))
+    cases["mixed_barrier"] = (h, tnn)
+    # complex, non-unit scalar hoppings (|t| far from 1: the recurrence's scaling factors matter)
+    h, tnn, _ = configs.disordered_blocks(N=30, n=7, W=0.5, tl=2.7, seed=6)
+    ph = np.exp(1j * rng.uniform(0, 2 * np.pi, len(tnn)))
+    ph[0] = ph[-1] = 1.0
+    tnn = tnn * ph[:, None, None] * rng.uniform(0.5, 1.5, len(tnn))[:, None, None]
+    tnn[0] = tnn[-1] = -2.7 * np.eye(7)
+    cases["complex_hopping_n7"] = (h, tnn)
+    return cases
+
+
+@pytest.mark.parametrize("kmax,gexp", [(1, 5), (2, 5), (3, 0), (8, 5), (32, 5), (32, 2), (64, 9)])
+def test_telescoped_sweep_chunk_lengths(kmax, gexp):
+    """Every chunk length / growth bound of the telescoped sweep reproduces the plain recursion (kmax = 1 IS the
+    plain recursion: one inverse per site) and the numpy oracle."""
+    lib = _lib.load()
+    try:
+        _lib.check(lib.tx_set_option(1, kmax))
+        _lib.check(lib.tx_set_option(2, gexp))
+        for name, (h, tnn) in _telescoped_cases().items():
+            n = h.shape[-1]
+            scale = float(np.abs(tnn[0][0, 0]))
+            Es = (np.linspace(-1.9, 1.9, 24) * scale).astype(complex)
+            R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+            oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(n))
+            _check(R[0], T[0], oR, oT, res)
+    finally:
+        _lib.check(lib.tx_set_option(1, 32))
+        _lib.check(lib.tx_set_option(2, 5))
+
+
+def test_telescoped_sweep_edge_cases():
+    """Energy axes that are / are not multiples of the eight points of a warp, several Hamiltonians, complex
+    energies (the general fragment path), table-mode leads, amplitude-vector sources, a decoupled site (t = 0)."""
+    rng = np.random.default_rng(43)
+    h, tnn, _ = configs.disordered_blocks(N=18, n=8, W=0.3, seed=8)
+    for nE in (8, 16, 64, 65, 100):
+        Es = np.linspace(-1.9, 1.9, nE).astype(complex)
+        R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+        oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(8))
+        _check(R[0], T[0], oR, oT, res)
+    # three Hamiltonians x 72 energies, amplitude-vector sources
+    P = 3
+    hs = np.stack([configs.disordered_blocks(N=18, n=8, W=0.1 * (p + 1), seed=20 + p)[0] for p in range(P)])
+    Es = np.linspace(-1.8, 1.8, 72).astype(complex)
+    srcs = np.vstack([np.eye(8)[3], rng.standard_normal(8)])
+    R, T, res = transmission_sweep(hs, tnn, Es, sources=srcs, want_resid=True)
+    for p in range(P):
+        oR, oT = rgf_oracle.transmission_closed(hs[p], tnn, Es, srcs)
+        _check(R[p], T[p], oR, oT, res[p])
+    # complex energies: retarded GF at finite eta (R + T < 1: absorption, so no unitarity check)
+    Ec = np.linspace(-1.5, 1.5, 16) + 0.01j
+    R, T = transmission_sweep(h, tnn, Ec)
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Ec, np.eye(8))
+    _check(R[0], T[0], oR, oT)
+    # table-mode leads (n = 8 and padded n = 6) with the closed-form self-energies as tables
+    for n in (8, 6):
+        hh, tt, _ = configs.disordered_blocks(N=14, n=n, W=0.3, seed=9)
+        Es = np.linspace(-1.7, 1.7, 24).astype(complex)
+        SL, SR = rgf_oracle.closed_selfenergies(hh, tt, Es)
+        R, T, res = transmission_sweep(hh, tt, Es, "table", sigL=SL, sigR=SR, want_resid=True)
+        oR, oT = rgf_oracle.transmission_closed(hh, tt, Es, np.eye(n))
+        _check(R[0], T[0], oR, oT, res)
+    # a decoupled site: t_5 = 0 cuts the chain, T = 0 and R = 1 exactly as the dense inverse gives
+    t0 = tnn.copy()
+    t0[5] = 0
+    Es = np.linspace(-1.5, 1.5, 16).astype(complex)
+    R, T, res = transmission_sweep(h, t0, Es, want_resid=True)
+    oR, oT = rgf_oracle.transmission_closed(h, t0, Es, np.eye(8))
+    assert np.all(T == 0)
+    _check(R[0], T[0], oR, oT, res)

@@ -187,3 +187,26 @@ def test_caroli_trace_equals_channel_sum():
     G00, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, SL, SR)
     _, T = rgf_oracle.rt_from_blocks(G00, GN0, SL, SR, np.eye(8))
     assert np.allclose(T.sum(axis=(1, 2)), rgf_oracle.caroli_trace(GN0, SL, SR), rtol=1e-12)
+
+
+@pytest.mark.parametrize("kmax,gmax", [(1, 64.0), (4, 64.0), (8, 64.0), (32, 32.0), (64, 4.0)])
+def test_telescoped_restatement_matches_plain_recursion(kmax, gmax):
+    """`rgf_blocks_telescoped` (the restatement of the sm_100a kernel's chunked recurrence) against the plain
+    recursion, itself pinned to the dense reference path above: same blocks to round-off for every chunk length."""
+    cases = [configs.cicc_blocks(1, 1.0, -0.6, 0.0, 0.0, 0.0, 3, 2)[:2],
+             configs.disordered_blocks(N=60, n=8, W=0.3, seed=2)[:2],
+             configs.disordered_blocks(N=25, n=5, W=0.5, tl=2.7, seed=3)[:2],
+             configs.barrier_blocks(0.4, 11, 1.0, 1)[:2]]
+    for h, tnn in cases:
+        n = h.shape[-1]
+        scale = float(abs(tnn[0][0, 0]))
+        Es = (np.linspace(-1.9, 1.9, 12) * scale).astype(complex)
+        SL, SR = rgf_oracle.closed_selfenergies(h, tnn, Es)
+        G0, W0 = rgf_oracle.rgf_blocks(h, tnn, Es, SL, SR)
+        G1, W1, chunks = rgf_oracle.rgf_blocks_telescoped(h, tnn, Es, SL, SR, kmax, gmax, return_stats=True)
+        assert sum(chunks) == len(h) and max(chunks) <= kmax
+        R0, T0 = rgf_oracle.rt_from_blocks(G0, W0, SL, SR, np.eye(n))
+        R1, T1 = rgf_oracle.rt_from_blocks(G1, W1, SL, SR, np.eye(n))
+        assert rt_err(T1, T0) < 1e-10 and rt_err(R1, R0) < 1e-10
+        if kmax == 1:
+            assert np.allclose(G1, G0, rtol=1e-13, atol=1e-15) and np.allclose(W1, W0, rtol=1e-13, atol=1e-15)

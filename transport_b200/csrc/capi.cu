@@ -69,7 +69,7 @@ int round_up_block(int n) {
 // Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
 // number of resident 128-thread blocks per SM the register allocation is capped for.
 int g_variant = 13;
-int g_chunk_kmax = 8;    // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
+int g_chunk_kmax = 32;   // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
 int g_chunk_gexp = 5;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
