@@ -147,12 +147,6 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     const int x0i = n8t_idx(2 * tid, gid), x1i = n8t_idx(2 * tid + 1, gid);          // transposing F write
     const unsigned zmask = (unsigned)(p.n_pts >> 62);   // run-time zero (see n8_invert)
 
-    // W_M = I
-#pragma unroll
-    for (int q = 0; q < GPW; ++q) {
-        WB[q * N8TCfg::PSTRIDE + f0i] = make_double2(m0, 0.0);
-        WB[q * N8TCfg::PSTRIDE + f1i] = make_double2(m1, 0.0);
-    }
     __syncwarp();
 
     // block fragment [g][2t+s] (contiguous) / transposed fragment [2t+s][g] of an n x n block
@@ -394,24 +388,44 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             const double rda = rdcur;
             const double gsc = dprev * rda;
             const double2 tq = make_double2(tau.x * rda, tau.y * rda);
+            if (b == M - 1) {
+                // first chunk: W_M = I, so W = tau X is a scaled copy (X[g][2t+s] sits at the transposing slots)
 #pragma unroll
-            for (int q = 0; q < GPW; ++q) {
-                const double2* xq = XB + q * N8TCfg::PSTRIDE;
-                double2* wq = WB + q * N8TCfg::PSTRIDE;
-                const double2* yq = YB + q * N8TCfg::PSTRIDE;
-                const double2 x0 = xq[f0i], x1 = xq[f1i];     // Xs[2t+s][g]
-                const double2 w0 = wq[f0i], w1 = wq[f1i];     // W[g][2t+s]
-                const double2 y0 = yq[f0i], y1 = yq[f1i];     // U_{a+1}[2t+s][g]
-                double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};
-                double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
-                cdmma(wr, wi, w0, x0);
-                cdmma(gr, gi, x0, y0);
-                cdmma(wr, wi, w1, x1);
-                cdmma(gr, gi, x1, y1);
-                wq[f0i] = make_double2(fma(wr[0], tq.x, -(wi[0] * tq.y)), fma(wi[0], tq.x, wr[0] * tq.y));
-                wq[f1i] = make_double2(fma(wr[1], tq.x, -(wi[1] * tq.y)), fma(wi[1], tq.x, wr[1] * tq.y));
-                Ya[q][0] = make_double2(gr[0] * gsc, gi[0] * gsc);
-                Ya[q][1] = make_double2(gr[1] * gsc, gi[1] * gsc);
+                for (int q = 0; q < GPW; ++q) {
+                    const double2* xq = XB + q * N8TCfg::PSTRIDE;
+                    double2* wq = WB + q * N8TCfg::PSTRIDE;
+                    const double2* yq = YB + q * N8TCfg::PSTRIDE;
+                    const double2 x0 = xq[f0i], x1 = xq[f1i];     // Xs[2t+s][g]
+                    const double2 y0 = yq[f0i], y1 = yq[f1i];     // U_{a+1}[2t+s][g]
+                    const double2 c0 = xq[x0i], c1 = xq[x1i];     // Xs[g][2t+s]
+                    double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
+                    cdmma(gr, gi, x0, y0);
+                    cdmma(gr, gi, x1, y1);
+                    wq[f0i] = cmul2(c0, tq);
+                    wq[f1i] = cmul2(c1, tq);
+                    Ya[q][0] = make_double2(gr[0] * gsc, gi[0] * gsc);
+                    Ya[q][1] = make_double2(gr[1] * gsc, gi[1] * gsc);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    const double2* xq = XB + q * N8TCfg::PSTRIDE;
+                    double2* wq = WB + q * N8TCfg::PSTRIDE;
+                    const double2* yq = YB + q * N8TCfg::PSTRIDE;
+                    const double2 x0 = xq[f0i], x1 = xq[f1i];     // Xs[2t+s][g]
+                    const double2 w0 = wq[f0i], w1 = wq[f1i];     // W[g][2t+s]
+                    const double2 y0 = yq[f0i], y1 = yq[f1i];     // U_{a+1}[2t+s][g]
+                    double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};
+                    double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
+                    cdmma(wr, wi, w0, x0);
+                    cdmma(gr, gi, x0, y0);
+                    cdmma(wr, wi, w1, x1);
+                    cdmma(gr, gi, x1, y1);
+                    wq[f0i] = make_double2(fma(wr[0], tq.x, -(wi[0] * tq.y)), fma(wi[0], tq.x, wr[0] * tq.y));
+                    wq[f1i] = make_double2(fma(wr[1], tq.x, -(wi[1] * tq.y)), fma(wi[1], tq.x, wr[1] * tq.y));
+                    Ya[q][0] = make_double2(gr[0] * gsc, gi[0] * gsc);
+                    Ya[q][1] = make_double2(gr[1] * gsc, gi[1] * gsc);
+                }
             }
         }
         __syncwarp();   // every fragment of X and Y_{a+1} has been read: XB / YB may be overwritten
