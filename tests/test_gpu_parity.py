@@ -578,10 +578,12 @@ def _telescoped_cases():
     return cases
 
 
-@pytest.mark.parametrize("kmax,gexp", [(1, 5), (2, 5), (3, 0), (8, 5), (32, 5), (32, 2), (64, 9)])
+@pytest.mark.parametrize("kmax,gexp", [(1, 4), (2, 4), (3, 0), (8, 4), (32, 4), (32, 2), (64, 5)])
 def test_telescoped_sweep_chunk_lengths(kmax, gexp):
-    """Every chunk length / growth bound of the telescoped sweep reproduces the plain recursion (kmax = 1 IS the
-    plain recursion: one inverse per site) and the numpy oracle."""
+    """Every chunk length of the telescoped sweep, with growth bounds around the default 2^4, reproduces the plain
+    recursion (kmax = 1 IS the plain recursion: one inverse per site) and the numpy oracle -- including the
+    1e-24 tunnelling entries of the mixed barrier, which are measured relative to themselves.  (Without a growth
+    bound the component-wise accuracy of such entries degrades as growth^2; the numpy restatement shows the same.)"""
     lib = _lib.load()
     try:
         _lib.check(lib.tx_set_option(1, kmax))
@@ -595,7 +597,7 @@ def test_telescoped_sweep_chunk_lengths(kmax, gexp):
             _check(R[0], T[0], oR, oT, res)
     finally:
         _lib.check(lib.tx_set_option(1, 32))
-        _lib.check(lib.tx_set_option(2, 5))
+        _lib.check(lib.tx_set_option(2, 4))
 
 
 def test_telescoped_sweep_edge_cases():

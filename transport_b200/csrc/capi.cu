@@ -70,7 +70,7 @@ int round_up_block(int n) {
 // number of resident 128-thread blocks per SM the register allocation is capped for.
 int g_variant = 13;
 int g_chunk_kmax = 32;   // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
-int g_chunk_gexp = 5;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
+int g_chunk_gexp = 4;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -121,22 +121,50 @@ int materialise_affine(SweepParams& p, cudaStream_t st) {
     return TX_OK;
 }
 
-// Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.
-template <int LEAD, int MINB, bool FULL>
-int launch_n8t_full(SweepParams p, cudaStream_t st) {
-    constexpr int WARPS = 4;
-    p.nondiag_max = nullptr;
-    p.site_class = nullptr;
-    {
-        int rc = materialise_affine(p, st);
-        if (rc) return rc;
+// Structure scan of the on-site blocks (nondiag_scan_kernel): per Hamiltonian the last non-diagonal site and
+// per site a class (2 scalar multiple of I, 1 diagonal, 0 general).  Must run before materialise_affine.
+int scan_structure(SweepParams& p, cudaStream_t st, bool want_tail) {
+    int devid = 0;
+    TX_CUDA(cudaGetDevice(&devid));
+    const int n_hs = (p.h_stride == 0) ? 1 : (int)(p.n_pts / p.nE);
+    DevBuf& nb = g_nondiag[devid & 15];
+    const size_t need = ((size_t)n_hs * (1 + (size_t)p.M) + 1) * sizeof(int);
+    if (need > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
+    int rc = nb.ensure(need);
+    if (rc) return rc;
+    int* nd = (int*)nb.ptr;
+    int* cl = nd + n_hs;
+    TX_CUDA(cudaMemsetAsync(nd, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
+    const long long ncl = (long long)n_hs * p.M;
+    fill_int_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, 2, ncl);
+    const long long total = (long long)n_hs * p.M * p.n;
+    nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, nd, cl);
+    int* cnt = cl + ncl;
+    TX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+    class_count_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, ncl, p.M, cnt);
+    TX_CUDA(cudaGetLastError());
+    count_launch(3);
+    p.class_count = cnt;
+    p.class_sites = (long long)n_hs * (p.M > 2 ? p.M - 2 : 0);
+    if (want_tail) {
+        p.nondiag_max = nd;
+        p.nondiag_stride = (p.h_stride == 0) ? 0 : 1;
     }
+    p.site_class = cl;
+    p.class_stride = (p.h_stride == 0) ? 0 : p.M;
+    return TX_OK;
+}
+
+// Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.
+template <int LEAD, int MINB, bool FULL, bool DIAG>
+int launch_n8t_inst(const SweepParams& p, cudaStream_t st) {
+    constexpr int WARPS = 4;
     const size_t smem = (size_t)WARPS * N8TCfg::PER_WARP_BYTES;
     static bool attr_done[16] = {false};
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
     // a warp = eight consecutive energies of one Hamiltonian (energy axis padded to a multiple of eight)
@@ -144,10 +172,32 @@ int launch_n8t_full(SweepParams p, cudaStream_t st) {
     const long long n_warps = (p.n_pts / p.nE) * warps_per_ham;
     const long long blocks = (n_warps + WARPS - 1) / WARPS;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8t<LEAD, MINB, FULL><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
+    rgf_sweep_n8t<LEAD, MINB, FULL, DIAG><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
+}
+
+template <int LEAD, int MINB, bool FULL>
+int launch_n8t_full(SweepParams p, cudaStream_t st) {
+    p.nondiag_max = nullptr;
+    p.site_class = nullptr;
+    p.class_stride = 0;
+    p.class_count = nullptr;
+    p.class_sites = 0;
+    if (g_diag_tail) {
+        int rc = scan_structure(p, st, false);
+        if (rc) return rc;
+    }
+    {
+        int rc = materialise_affine(p, st);
+        if (rc) return rc;
+    }
+    if (!g_diag_tail) return launch_n8t_inst<LEAD, MINB, FULL, false>(p, st);
+    // both instantiations; each returns at once unless the device-side site statistics select it
+    int rc = launch_n8t_inst<LEAD, MINB, FULL, true>(p, st);
+    if (rc) return rc;
+    return launch_n8t_inst<LEAD, MINB, FULL, false>(p, st);
 }
 
 template <int LEAD, int MINB>
@@ -163,30 +213,8 @@ int launch_n8(SweepParams p, cudaStream_t st) {
     p.site_class = nullptr;
     p.class_stride = 0;
     if (g_diag_tail) {
-        // structure scan: diagonal right tail (closed leads) and scalar runs
-        int devid = 0;
-        TX_CUDA(cudaGetDevice(&devid));
-        const int n_hs = (p.h_stride == 0) ? 1 : (int)(p.n_pts / p.nE);
-        DevBuf& nb = g_nondiag[devid & 15];
-        const size_t need = (size_t)n_hs * (1 + (size_t)p.M) * sizeof(int);
-        if (need > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
-        int rc = nb.ensure(need);
+        int rc = scan_structure(p, st, LEAD == LEAD_CLOSED);
         if (rc) return rc;
-        int* nd = (int*)nb.ptr;
-        int* cl = nd + n_hs;
-        TX_CUDA(cudaMemsetAsync(nd, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
-        const long long ncl = (long long)n_hs * p.M;
-        fill_int_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, 2, ncl);
-        const long long total = (long long)n_hs * p.M * p.n;
-        nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, nd, cl);
-        TX_CUDA(cudaGetLastError());
-        count_launch(2);
-        if (LEAD == LEAD_CLOSED) {
-            p.nondiag_max = nd;
-            p.nondiag_stride = (p.h_stride == 0) ? 0 : 1;
-        }
-        p.site_class = cl;
-        p.class_stride = (p.h_stride == 0) ? 0 : p.M;
     }
     {
         int rc = materialise_affine(p, st);
@@ -369,6 +397,8 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     p.nondiag_stride = 0;
     p.site_class = nullptr;
     p.class_stride = 0;
+    p.class_count = nullptr;
+    p.class_sites = 0;
     p.n_pts = (long long)n_ham * nE;
     p.n = n;
     p.M = M;

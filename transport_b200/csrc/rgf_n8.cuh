@@ -837,6 +837,14 @@ __global__ void nondiag_scan_kernel(const cd* __restrict__ h, const cd* __restri
     if (cl < 2) atomicMin(site_class + (long long)q * M + j, cl);
 }
 
+// count[0] = number of interior sites (0 < j < M-1) of the batch whose on-site block is diagonal
+__global__ void class_count_kernel(const int* __restrict__ site_class, long long n_sites, int M, int* __restrict__ count) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_sites) return;
+    const int j = (int)(idx % M);
+    if (j > 0 && j < M - 1 && site_class[idx] >= 1) atomicAdd(count, 1);
+}
+
 __global__ void fill_int_kernel(int* __restrict__ dst, int value, long long count) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < count) dst[idx] = value;

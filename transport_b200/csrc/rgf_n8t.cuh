@@ -53,7 +53,7 @@ __device__ __forceinline__ void cdmma(double (&re)[2], double (&im)[2], const do
     dmma_8x8x4(im, a.y, b.x);
 }
 
-template <int LEAD, int MINB, bool FULL>
+template <int LEAD, int MINB, bool FULL, bool DIAG>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, const int kmax, const int gexp2,
                                                            const int warps_per_ham, const long long n_warps) {
     constexpr int N = 8, RP = 2, GPW = 8;
@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     const int e = min(e_raw, p.nE - 1);
     const long long pt = (long long)ham * p.nE + e;
     const cd E = p.E[e];
+    // Two instantiations are launched back to back when the structure scan ran: the one with the diagonal-site
+    // path serves batches where at least 1/8 of the interior sites are diagonal, the lean one the rest (the
+    // decision is taken on the device, no host synchronisation).
+    if (p.class_count != nullptr && ((long long)(*p.class_count) * 8 >= p.class_sites) != DIAG) return;
     const long long nn = (long long)n * n;
     const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
     const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
@@ -178,6 +182,21 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         return 2 * ((int)(mx >> 20) - 1023) + expo(scale2) > gexp2;
     };
 
+    // Site classes (structure scan of the launcher: 0 general, >= 1 diagonal on-site block) through a 32-site
+    // window held in registers: lane l = site win_top - l.  Table-mode Sigma_L is a full block: site 0 is general there.
+    const int* cls = p.site_class ? p.site_class + (long long)ham * p.class_stride : nullptr;
+    int win_top = -1, win_val = 0;
+    auto site_is_diag = [&](int i) -> bool {
+        if (!DIAG || cls == nullptr) return false;
+        if (LEAD == LEAD_TABLE && i == 0) return false;
+        if (i > win_top || i < win_top - 31) {
+            win_top = i;
+            const int site = i - lane;
+            win_val = (site >= 0) ? __ldg(cls + site) : 0;
+        }
+        return __shfl_sync(FULLM, win_val, win_top - i) >= 1;
+    };
+
     // One site inside a chunk, in the scaled variables U_j = Y_j / d_j with d_j = -|t_j|^2 d_{j+2}:
     //     Q <- P (f_j Z_j) + Q,   f_j = d_{j+1} / d_j      (P = U_{j+1}, Q = U_{j+2} -> U_j),  1 <= j+1 <= M-1
     // so the accumulators start from Q itself (no multiplication); for |t| = 1 the factors are +-1 and the
@@ -253,6 +272,29 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         }
     };
 
+    // The same site when h_j is DIAGONAL (clean spacer sites, barrier regions, lead cells -- most sites of the
+    // reference's own chains): P (f_j Z_j) is a column scaling, so the step is two complex FMAs per point on
+    // the FP64 pipe instead of eight DMMAs.   (D0, D1) = f_j * h_j[c][c] for the lane's columns c = 2t, 2t+1.
+    auto diag_step = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2], int j, double fj, double2 D0, double2 D1,
+                         double padz) {
+        const bool endsite = (j == 0);
+        const double2* ep = endsite ? SL + 2 * tid : EB;
+        const int es = endsite ? 8 : 1;
+#pragma unroll
+        for (int q = 0; q < GPW; ++q) {
+            const double2 E0 = ep[q * es];
+            const double2 E1 = endsite ? ep[q * es + 1] : E0;
+            double2 z0 = make_double2(fma(fj, E0.x, -D0.x), fma(fj, E0.y, -D0.y));
+            double2 z1 = make_double2(fma(fj, E1.x, -D1.x), fma(fj, E1.y, -D1.y));
+            if (!full) {
+                if (2 * tid >= n) z0 = make_double2(padz, 0.0);
+                if (2 * tid + 1 >= n) z1 = make_double2(padz, 0.0);
+            }
+            cfma2(Q[q][0], P[q][0], z0);
+            cfma2(Q[q][1], P[q][1], z1);
+        }
+    };
+
     double2 Ya[GPW][2], Yb[GPW][2];
     int j = M - 1;
     while (j >= 0) {
@@ -303,22 +345,32 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         // reciprocal of |t_j|^2 per site, no division)
         double dcur = 1.0, dprev = 1.0, rdcur = 1.0, rdprev = 1.0;   // d_j, d_{j+1} and reciprocals
         double rS2 = fast_rcp(S2);                                   // 1 / prod |t_i|^2
-        // The growth test lags one site behind the recurrence (it looks at P = U_{j+1} while the tensor cores
-        // work on U_j), so that its integer reduction never sits between two sites' DMMAs.
+        // The growth test looks at the newest matrix before every further site.  (Letting it lag one site behind,
+        // to overlap its integer reduction with the DMMAs, was measured: no gain, and in evanescent regions the
+        // extra site of growth costs a factor 20 in the accuracy of 1e-24 tunnelling entries.)
         double nrm = rS2;                             // d_{j+1}^2 / prod |t|^2 for the matrix under test
         // next site's fragment and hopping, one site ahead of the tensor-core work
         double2 Hn0 = zero2, Hn1 = zero2, tn = zero2;
-        if (j > 0) {
-            load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
-            tn = __ldg(tbase + (long long)(j - 1) * nn);
-        }
+        bool diag_next = false;                       // is site j-1 diagonal?  (then Hn holds its diagonal entries)
+        auto prefetch = [&](int i) {                  // site i >= 0
+            diag_next = site_is_diag(i);
+            if (diag_next) {
+                const double2* blk = hbase + (long long)i * nn;
+                Hn0 = (full || 2 * tid < n) ? __ldg(blk + (2 * tid) * (n + 1)) : zero2;
+                Hn1 = (full || 2 * tid + 1 < n) ? __ldg(blk + (2 * tid + 1) * (n + 1)) : zero2;
+            } else {
+                load_frag(hbase + (long long)i * nn, Hn0, Hn1);
+            }
+            tn = __ldg(tbase + (long long)i * nn);
+        };
+        if (j > 0) prefetch(j - 1);
         // one more site: Q <- U_j from P = U_{j+1}; false if the chunk has to be closed at the current site
         auto advance = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2]) -> bool {
             if (!(j > 0 && k < kmax)) return false;
             const double2 tj = tn;
             const double kap = fma(tj.x, tj.x, tj.y * tj.y);
             if (!(kap > 0.0)) return false;           // decoupled site (or NaN): it starts its own chunk
-            if (grown(P, nrm)) return false;
+            if (grown(P, nrm)) return false;          // P = U_{j+1} is the newest matrix of the chunk
             --j;
             ++k;
             const double rk = fast_rcp(kap);
@@ -327,15 +379,14 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             const double fj = dcur * rdj;             // f_j = d_{j+1} / d_j
             double2 H0 = make_double2(fj * Hn0.x, fj * Hn0.y);
             double2 H1 = make_double2(fj * Hn1.x, fj * Hn1.y);
-            if (!full) {                              // padding: B diagonal = f_j (1 + kap), handed over in H
+            const bool diag_now = diag_next;
+            if (!full && !diag_now) {                 // padding: B diagonal = f_j (1 + kap), handed over in H
                 if (!in0) H0 = make_double2(m0 * fj * (1.0 + kap), 0.0);
                 if (!in1) H1 = make_double2(m1 * fj * (1.0 + kap), 0.0);
             }
-            if (j > 0) {
-                load_frag(hbase + (long long)(j - 1) * nn, Hn0, Hn1);
-                tn = __ldg(tbase + (long long)(j - 1) * nn);
-            }
-            site_step(P, Q, j, fj, H0, H1);
+            if (j > 0) prefetch(j - 1);
+            if (diag_now) diag_step(P, Q, j, fj, H0, H1, fj * (1.0 + kap));
+            else site_step(P, Q, j, fj, H0, H1);
             phase ^= 1;
             dprev = dcur;
             dcur = dj;

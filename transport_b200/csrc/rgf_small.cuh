@@ -46,6 +46,8 @@ struct SweepParams {
     long long nondiag_stride;
     const int* site_class;   // [n_ham or 1][M] or null: 0 general, 1 diagonal, 2 scalar multiple of I
     long long class_stride;
+    const int* class_count;  // null, or device counter: interior sites of the batch with a diagonal on-site block
+    long long class_sites;   // interior sites of the batch (rgf_sweep_n8t picks its instantiation from the ratio)
     long long n_pts;
     int n, M, nE, n_src;
 };
