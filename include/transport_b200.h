@@ -184,18 +184,24 @@ int tx_landauer_current(const double* T, const double* E, int nE, const double* 
 int tx_landauer_current_dev(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
                             double kBT, double* jE, double* I, void* stream);
 
-/* Tuning knob for the 5 <= n <= 8, scalar-hopping, closed-lead sweep (bench.py --variant):
+/* Tuning knob for the 5 <= n <= 8, scalar-hopping sweep (bench.py --variant):
+ *   13   DEFAULT: telescoped sweep (rgf_n8t.cuh): register-resident DMMA recurrence, one inverse per chunk
+ *        of up to kmax sites, diagonal sites as column scalings; eight energies of one Hamiltonian per warp
+ *        (energy axes shorter than 64 that are not a multiple of eight fall back to variant 6)
+ *   6/7  plain sweep, one inverse per site, tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh),
+ *        3 CTAs/SM, smem / shuffle pivot row;   8  as 6 with 2 CTAs/SM and no register cap;   9  as 8 with the
+ *        eight products of a warp issued back to back;   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
+ *        that skip the products / the inversion (WRONG results, measurement only)
  *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
  *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles
- *   6/7  tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh), 3 CTAs/SM, smem (6 = DEFAULT) / shuffle pivot row
- *   8    as 6 with 2 CTAs/SM and no register cap;   9  as 8 with the eight products of a warp issued
- *        back to back before one barrier;   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
- *        that skip the products / the inversion (WRONG results, measurement only)
  * All variants compute the same thing. */
 int tx_set_variant(int variant);
-/* Library options.  option 0: value != 0 (default) lets the 5 <= n <= 8 scalar-hopping sweep treat the
- * right-hand tail of sites whose on-site blocks are diagonal (leads, barrier regions V*I, clean spacer
- * sites) per channel instead of as blocks; value 0 forces the block path on every site (A/B measurements). */
+/* Library options.
+ *   option 0: value != 0 (default) enables the structure scan of the on-site blocks: diagonal sites take the
+ *             column-scaling step of the telescoped sweep (the plain sweep uses it for its diagonal right tail
+ *             and scalar runs); value 0 treats every site as a general block (A/B measurements).
+ *   option 1: longest chunk of the telescoped sweep in sites, 1..64 (default 32; 1 = one inverse per site).
+ *   option 2: log2 of the growth bound that closes a chunk early, 0..500 (default 4: max |D_j| / prod |t| < 32). */
 int tx_set_option(int option, int value);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device

@@ -40,7 +40,10 @@ for r in rows[2:]:
         continue
     m = re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ix['Source']].strip())
     op = m.group(2).split('.')[0] if m else '?'
-    ni, ns = int(r[ix['Instructions Executed']]), int(r[ix['# Samples']])
+    try:
+        ni, ns = int(r[ix['Instructions Executed']]), int(r[ix['# Samples']])
+    except ValueError:
+        continue   # repeated header of a further kernel in the report
     ops[op] += ni
     samp[op] += ns
     ti += ni
