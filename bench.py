@@ -177,8 +177,26 @@ def gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    try:   # run on the CPUs next to this GPU, so that pinned host buffers are allocated on its NUMA node
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        numa = "cpus %d" % len(os.sched_getaffinity(0))
+    except Exception as exc:   # affinity is an optimisation of the e2e leg only
+        numa = "unbound (%s)" % type(exc).__name__
     lib = _lib.load()
     _lib.check(lib.tx_set_device(local_rank))
+    # NCCL (and torchrun banners) may write to stdout; the contract is ONE JSON line there, so everything
+    # else goes to stderr and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -351,7 +369,7 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_gpu": n_pts, "l2": "256 MB flush between timed steps; "
                        "each step also writes 2.05 GB of R/T", "variant": args.variant,
-                       "parallelism": "J axis sharded, dp%d" % world},
+                       "parallelism": "J axis sharded, dp%d" % world, "host_affinity": numa},
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak, "traffic": traffic,
@@ -372,7 +390,8 @@ def gpu_arm(args):
             "cpu_baseline": cpu, "clocks": clocks, "parity_max_rel_err_vs_reference_golden": parity,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
