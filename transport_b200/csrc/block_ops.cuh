@@ -47,32 +47,63 @@ __device__ __forceinline__ void dmma844(double (&d)[2], double a, double b) {
 }
 
 // C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
+// A warp works on a strip of up to four 8x8 output tiles of one tile row: the A fragment of a k-step is loaded
+// once and reused for the four column tiles (16 DMMA per 5 fragment loads), and the loads of the next k-step are
+// issued before the DMMAs of the current one (operands usually sit in L2/L1, not in shared memory).
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate) {
+    constexpr int NT = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int tiles = n >> 3;
-    for (int tile = warp; tile < tiles * tiles; tile += nwarps) {
-        const int tr = (tile / tiles) << 3, tc = (tile % tiles) << 3;
-        double re[2] = {0.0, 0.0}, im[2] = {0.0, 0.0}, re2[2] = {0.0, 0.0}, im2[2] = {0.0, 0.0};
-#pragma unroll 4
+    const int strips = (tiles + NT - 1) / NT;
+    for (int item = warp; item < tiles * strips; item += nwarps) {
+        const int tr = (item / strips) << 3;
+        const int tc0 = (item % strips) * NT;
+        const int nt = min(NT, tiles - tc0);
+        double re[NT][2], im[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
+        cd a = ld_op(A, n, tr + g, t, opA);
+        cd b[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) b[u] = (u < nt) ? ld_op(B, n, t, ((tc0 + u) << 3) + g, opB) : mk(0.0, 0.0);
         for (int k = 0; k < n; k += 4) {
-            const cd a = ld_op(A, n, tr + g, k + t, opA);
-            const cd b = ld_op(B, n, k + t, tc + g, opB);
-            dmma844(re, a.x, b.x);
-            dmma844(im, a.x, b.y);
-            dmma844(re2, -a.y, b.y);
-            dmma844(im2, a.y, b.x);
+            const cd ac = a;
+            cd bc[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) bc[u] = b[u];
+            if (k + 4 < n) {
+                a = ld_op(A, n, tr + g, k + 4 + t, opA);
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    if (u < nt) b[u] = ld_op(B, n, k + 4 + t, ((tc0 + u) << 3) + g, opB);
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                dmma844(re[u], ac.x, bc[u].x);
+                dmma844(im[u], ac.x, bc[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                dmma844(re[u], -ac.y, bc[u].y);
+                dmma844(im[u], ac.y, bc[u].x);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int idx = (tr + g) * n + tc + 2 * t + i;
-            cd v = mk(sgn * (re[i] + re2[i]), sgn * (im[i] + im2[i]));
-            if (accumulate) {
-                const cd c0 = C[idx];
-                v.x += c0.x;
-                v.y += c0.y;
+        for (int u = 0; u < NT; ++u) {
+            if (u < nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int idx = (tr + g) * n + ((tc0 + u) << 3) + 2 * t + i;
+                    cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+                    if (accumulate) {
+                        const cd c0 = C[idx];
+                        v.x += c0.x;
+                        v.y += c0.y;
+                    }
+                    C[idx] = v;
+                }
             }
-            C[idx] = v;
         }
     }
     __syncthreads();
@@ -178,15 +209,25 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
             A[k * n + c] = (c == k) ? inv : A[k * n + c] * inv;
         }
         __syncthreads();
-        // eliminate column k from the other rows
-        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-            const int r = idx / n, c = idx - r * n;
-            if (r == k) continue;
-            const cd f = colk[r];
-            const cd pk = A[k * n + c];
-            cd a = (c == k) ? mk(0.0, 0.0) : A[idx];
-            cfms(a.x, a.y, f.x, f.y, pk.x, pk.y);
-            A[idx] = a;
+        // eliminate column k from the other rows (row/column indices advanced without a division)
+        {
+            int r = threadIdx.x / n, c = threadIdx.x - r * n;
+            const int dr = blockDim.x / n, dc = blockDim.x - dr * n;
+            for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+                if (r != k) {
+                    const cd f = colk[r];
+                    const cd pk = A[k * n + c];
+                    cd a = (c == k) ? mk(0.0, 0.0) : A[idx];
+                    cfms(a.x, a.y, f.x, f.y, pk.x, pk.y);
+                    A[idx] = a;
+                }
+                r += dr;
+                c += dc;
+                if (c >= n) {
+                    c -= n;
+                    ++r;
+                }
+            }
         }
         __syncthreads();
     }

@@ -487,6 +487,8 @@ int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1
     p.nE = nE;
     p.n_src = n_src;
     p.hop_scalar = (hop_mode == TX_HOP_SCALAR) ? 1 : 0;
+    p.kmax = g_chunk_kmax;
+    p.gexp = g_chunk_gexp;
     return launch_rgf_generic(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

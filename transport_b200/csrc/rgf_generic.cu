@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericPa
         s_vR[c] = -2.0 * SR[c * n + c].y;
     }
 
-    for (int j = M - 1; j >= 0; --j) {
-        // A = E - h_j (- Sigma on the end blocks)
+    // z_j = E - h_j (- Sigma on the end blocks) into dst
+    auto build_z = [&](cd* dst, int j) {
         for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
             const int r = idx / n, c = idx - r * n;
             cd hv = hb[(long long)j * nn + idx];
@@ -62,9 +62,84 @@ __global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericPa
             cd a = (r == c) ? mk(E.x - hv.x, E.y - hv.y) : mk(-hv.x, -hv.y);
             if (j == M - 1) a = a - SR[idx];
             if (j == 0) a = a - SL[idx];
-            A[idx] = a;
+            dst[idx] = a;
         }
         __syncthreads();
+    };
+
+    if (p.hop_scalar && p.kmax > 1) {
+        // ---- telescoped sweep (see rgf_n8t.cuh): inside a chunk [a..b]
+        //   D_{b+1} = I, D_{b+2} := g_{b+1},  D_j = z_j D_{j+1} - |t_j|^2 D_{j+2},  X = D_a^-1,  g_a = D_{a+1} X,
+        //   W_a = (prod conj t_j) W_{b+1} X  -- one product per site, one inverse per chunk.
+        cd* cur = A;      // D_{j+1}
+        cd* prev = X;     // D_{j+2}
+        cd* tmp = Y;      // z_j / scratch
+        const double gmax2 = ldexp(1.0, 2 * p.gexp + 2);
+        int j = M - 1;
+        while (j >= 0) {
+            const int b = j;
+            cd tau = mk(1.0, 0.0);
+            double S2 = norm2(tb[(long long)((b < M - 1) ? b : M - 2) * nn]);
+            build_z(cur, b);
+            if (b < M - 1) {
+                const cd t0 = tb[(long long)b * nn];
+                const double kap = norm2(t0);
+                tau = conj(t0);
+                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                    cd a = cur[idx];
+                    const cd g = G[idx];
+                    a.x = fma(-kap, g.x, a.x);
+                    a.y = fma(-kap, g.y, a.y);
+                    cur[idx] = a;
+                }
+                __syncthreads();
+            }
+            int k = 1;
+            bool prev_is_identity = true;
+            while (j > 0 && k < p.kmax) {
+                const cd t0 = tb[(long long)(j - 1) * nn];
+                const double kap = norm2(t0);
+                if (!(kap > 0.0)) break;                                   // decoupled site: its own chunk
+                if (!(cta_maxnorm2(cur, nn) < gmax2 * S2)) break;          // growth bound (also stops on NaN)
+                --j;
+                ++k;
+                build_z(tmp, j);
+                // prev <- -kap * prev  (prev = I for the second site of a chunk)
+                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                    if (prev_is_identity) {
+                        const int r = idx / n, c = idx - r * n;
+                        prev[idx] = mk(r == c ? -kap : 0.0, 0.0);
+                    } else {
+                        const cd v = prev[idx];
+                        prev[idx] = mk(-kap * v.x, -kap * v.y);
+                    }
+                }
+                __syncthreads();
+                cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0);           // D_j = z_j D_{j+1} - kap D_{j+2}
+                cd* sw = prev;
+                prev = cur;
+                cur = sw;
+                prev_is_identity = false;
+                S2 *= kap;
+                tau = tau * conj(t0);
+            }
+            // close at site a = j:  cur = D_a, prev = D_{a+1} (identity if k == 1)
+            cta_inverse_staged(cur, stage, n, s_colk, s_ipiv, p.singular);   // X
+            if (prev_is_identity) cta_copy(G, cur, nn);
+            else cta_gemm(G, prev, OP_N, cur, OP_N, n);                      // g_a = D_{a+1} X
+            if (b == M - 1) {
+                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) W[idx] = cur[idx] * tau;
+                __syncthreads();
+            } else {
+                cta_gemm(tmp, W, OP_N, cur, OP_N, n);                        // W X
+                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) W[idx] = tmp[idx] * tau;
+                __syncthreads();
+            }
+            --j;
+        }
+    } else
+    for (int j = M - 1; j >= 0; --j) {
+        build_z(A, j);
         if (j < M - 1) {
             const cd* t = tb + (long long)j * nn;
             if (p.hop_scalar) {

@@ -27,6 +27,7 @@ struct GenericParams {
     int* singular;
     long long n_pts;
     int n, M, nE, n_src, hop_scalar;
+    int kmax, gexp;          // telescoped sweep (scalar hopping): longest chunk, log2 of the growth bound
 };
 
 size_t rgf_generic_workspace_elems(int n, long long n_pts);
