@@ -54,7 +54,8 @@ enum {
     TX_GF_CLOSED = 0,       /* wfm.g_closed      wfm/__init__.py:306-340                       */
     TX_GF_RICEMELE = 1,     /* wfm.g_RiceMele    wfm/__init__.py:352-414                       */
     TX_GF_FIXEDPOINT = 2,   /* wfm.g_iter / g_ith, reference stopping rule  :479-551           */
-    TX_GF_SANCHO = 3        /* Sancho-Rubio decimation of the same fixed point                 */
+    TX_GF_SANCHO = 3,       /* Sancho-Rubio decimation of the same fixed point                 */
+    TX_GF_SEPARABLE = 4     /* h01 = t*I: g = U diag(g_closed(eps_m)) U^dag, h00 = U eps U^dag  */
 };
 
 /* ---- library / device management ------------------------------------------------------- */
@@ -143,6 +144,10 @@ long long tx_launch_counter(void);
  *               surface DOS stays below conv_tol for conv_rep consecutive iterations past min_iter
  *   SANCHO      Sancho-Rubio decimation of the same fixed point at z = E + i*imE; stops when
  *               max|alpha|,|beta| < conv_tol (conv_rep/min_iter unused)
+ *   SEPARABLE   multi-channel lead whose hopping block is a scalar multiple of the identity (square-lattice
+ *               ribbons): g commutes with h00, so g = U diag(g_closed(z, eps_m, t)) U^dag with the reference's
+ *               g_closed per transverse mode and h00 = U diag(eps) U^dag (Jacobi eigensolver on the device, once
+ *               per call); exact at imE = 0, no iteration.  z = E + i*imE.
  * Outputs (each may be NULL): g [nE][n][n]; sigma [nE][n][n] = h01^dag g h01 (side -1) or
  * h01 g h01^dag (side +1) (wfm.SelfEnergies :301-302); n_iter/conv/converged [nE] (iterative modes).
  * Non-convergence is reported per energy in `converged`, not as an error code.

@@ -640,3 +640,40 @@ def test_telescoped_sweep_edge_cases():
     oR, oT = rgf_oracle.transmission_closed(h, t0, Es, np.eye(8))
     assert np.all(T == 0)
     _check(R[0], T[0], oR, oT, res)
+
+
+def test_separable_multichannel_leads():
+    """TX_GF_SEPARABLE (scalar hopping block): g = U diag(g_closed(eps_m)) U^dag with the device Jacobi
+    eigensolver, against the same expression built with numpy's eigh and the oracle's g_closed; against
+    Sancho-Rubio at small eta away from the band edges; refusal of a non-scalar hopping block."""
+    rng = np.random.default_rng(11)
+    for n, tval in ((5, -1.0), (24, -1.3), (64, -1.0)):
+        if n == 64:
+            h00 = configs.ribbon_blocks(width=64, L=1)[0][0]
+        else:
+            X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+            h00 = 0.5 * (X + X.conj().T) / 2
+        h01 = tval * np.eye(n, dtype=complex)
+        Es = np.linspace(-3.4, 3.4, 21).astype(complex) * abs(tval)
+        eps, U = np.linalg.eigh(h00)
+        for side in (-1, 1):
+            ((g, sig),) = leads.surface_gf(h00, h01, Es, side, _lib.TX_GF_SEPARABLE, want_sigma=True)
+            for i, E in enumerate(Es):
+                gm = np.array([wfm_oracle.g_closed(np.array([[e_m]], dtype=complex), np.array([[tval]], dtype=complex), E, side)[0, 0]
+                               for e_m in eps])
+                want = (U * gm) @ U.conj().T
+                scale = np.abs(want).max()
+                assert np.abs(g[i] - want).max() < 1e-11 * scale, (n, i, np.abs(g[i] - want).max() / scale)
+                assert np.abs(sig[i] - abs(tval) ** 2 * want).max() < 1e-11 * scale * abs(tval) ** 2
+    # agreement with the decimation as eta -> 0 (g_closed is the eta = 0 limit; O(sqrt(eta)) near band edges)
+    h00 = configs.ribbon_blocks(width=16, L=1)[0][0]
+    h01 = -np.eye(16, dtype=complex)
+    Es = np.array([-2.9, -1.3, 0.45, 2.2], dtype=complex)
+    (g_sep,) = leads.surface_gf(h00, h01, Es, 1, _lib.TX_GF_SEPARABLE)
+    (g_sr, conv, nit, ok) = leads.surface_gf(h00, h01, Es, 1, _lib.TX_GF_SANCHO, imE=1e-9, conv_tol=1e-15, max_iter=200, full=True)
+    assert ok.all()
+    assert np.abs(g_sep - g_sr).max() < 1e-6
+    with pytest.raises(_lib.TransportError):
+        bad = h01.copy()
+        bad[0, 1] = 0.1
+        leads.surface_gf(h00, bad, Es, 1, _lib.TX_GF_SEPARABLE)

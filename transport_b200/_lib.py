@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "transport_b200.h")
 TX_OK, TX_ERR_ARG, TX_ERR_CUDA, TX_ERR_SINGULAR, TX_ERR_NOCONV, TX_ERR_UNSUPPORTED = range(6)
 TX_LEAD_CLOSED, TX_LEAD_TABLE = 0, 1
 TX_HOP_AUTO, TX_HOP_SCALAR, TX_HOP_GENERAL = 0, 1, 2
-TX_GF_CLOSED, TX_GF_RICEMELE, TX_GF_FIXEDPOINT, TX_GF_SANCHO = 0, 1, 2, 3
+TX_GF_CLOSED, TX_GF_RICEMELE, TX_GF_FIXEDPOINT, TX_GF_SANCHO, TX_GF_SEPARABLE = 0, 1, 2, 3, 4
 
 
 class TransportError(RuntimeError):

@@ -31,6 +31,8 @@ struct GfParams {
     int* n_iter;        // [nE] or null
     double* conv;       // [nE] or null
     int* converged;     // [nE] or null
+    const double* evals;  // SEPARABLE: eigenvalues of h00 [n]
+    const cd* evecs;      // SEPARABLE: eigenvectors of h00 [n][n] (columns)
     cd* scratch;        // global workspace (n > 32), per energy `scratch_per` elements
     long long scratch_per;
     int* singular;
@@ -73,16 +75,173 @@ __device__ void emit_sigma(const GfParams& p, const cd* g, cd* tmp, cd* out) {
     }
 }
 
-__global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p) {
+// Hermitian eigendecomposition of one n x n block (n <= 64) by parallel cyclic Jacobi, one CTA:
+// round-robin tournament of n/2 disjoint rotations per round, rotations J = [[c, s], [-conj s, c]] chosen to
+// annihilate A[p][q], applied as A <- J^dag A J (columns, then rows) and V <- V J.  A and V live in shared memory.
+// Serves the separable closed form below (once per lead, not per energy).  status: bit 0 = h01 is not a scalar
+// multiple of the identity, bit 1 = h00 is not Hermitian, bit 2 = no convergence.
+__global__ void __launch_bounds__(GF_THREADS) hermitian_eig_kernel(const cd* __restrict__ h00, const cd* __restrict__ h01,
+                                                                   int n, double* __restrict__ evals,
+                                                                   cd* __restrict__ evecs, int* __restrict__ status) {
+    extern __shared__ double2 eig_smem[];
+    __shared__ double s_c[32];
+    __shared__ cd s_s[32];
+    __shared__ int s_p[32], s_q[32];
+    __shared__ double s_red[GF_THREADS / 32];
+    __shared__ int s_bad;
+    cd* A = reinterpret_cast<cd*>(eig_smem);
+    cd* V = A + n * n;
+    const int tid = threadIdx.x, nn = n * n;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    double scale2 = 0.0;
+    for (int idx = tid; idx < nn; idx += blockDim.x) {
+        const int r = idx / n, c = idx - r * n;
+        const cd a = h00[idx], at = h00[c * n + r], t = h01[idx], t0 = h01[0];
+        A[idx] = a;
+        V[idx] = mk(r == c ? 1.0 : 0.0, 0.0);
+        scale2 = fmax(scale2, norm2(a));
+        const double tol = 1e-24 * (norm2(a) + norm2(t0) + 1e-300);
+        if (norm2(mk(a.x - at.x, a.y + at.y)) > 1e-24 * (norm2(a) + 1e-300)) atomicOr(&s_bad, 2);
+        const cd want = (r == c) ? t0 : mk(0.0, 0.0);
+        if (norm2(t - want) > tol) atomicOr(&s_bad, 1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) scale2 = fmax(scale2, __shfl_xor_sync(0xffffffffu, scale2, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = scale2;
+    __syncthreads();
+    scale2 = 1e-300;
+    for (int w = 0; w < GF_THREADS / 32; ++w) scale2 = fmax(scale2, s_red[w]);
+    __syncthreads();
+    const int m = n + (n & 1);                    // tournament size (a bye for odd n)
+    const int npairs = m / 2;
+    bool converged = false;
+    for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
+        for (int round = 0; round < m - 1; ++round) {
+            if (tid < npairs) {
+                int pp, qq;
+                if (tid == 0) {
+                    pp = m - 1;
+                    qq = round % (m - 1);
+                } else {
+                    pp = (round + tid) % (m - 1);
+                    qq = (round - tid + 2 * (m - 1)) % (m - 1);
+                }
+                double c = 1.0;
+                cd sv = mk(0.0, 0.0);
+                if (pp < n && qq < n) {
+                    const double al = A[pp * n + pp].x, ga = A[qq * n + qq].x;
+                    const cd be = A[pp * n + qq];
+                    const double ab = sqrt(norm2(be));
+                    if (ab > 1e-300) {
+                        const double tau = (al - ga) / (2.0 * ab);
+                        const double t = (tau == 0.0) ? -1.0 : -copysign(1.0, tau) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                        c = 1.0 / sqrt(fma(t, t, 1.0));
+                        const double f = t * c / ab;
+                        sv = mk(f * be.x, f * be.y);
+                    }
+                } else {
+                    pp = qq = -1;
+                }
+                s_c[tid] = c;
+                s_s[tid] = sv;
+                s_p[tid] = pp;
+                s_q[tid] = qq;
+            }
+            __syncthreads();
+            // columns of A and V:  X[:,p] <- c X[:,p] - conj(s) X[:,q],  X[:,q] <- s X[:,p] + c X[:,q]
+            for (int w = tid; w < npairs * n; w += blockDim.x) {
+                const int k = w / n, r = w - k * n;
+                const int pp = s_p[k], qq = s_q[k];
+                if (pp < 0) continue;
+                const double c = s_c[k];
+                const cd sv = s_s[k], sc = conj(sv);
+                cd xp = A[r * n + pp], xq = A[r * n + qq];
+                A[r * n + pp] = scale(xp, c) - sc * xq;
+                A[r * n + qq] = sv * xp + scale(xq, c);
+                xp = V[r * n + pp];
+                xq = V[r * n + qq];
+                V[r * n + pp] = scale(xp, c) - sc * xq;
+                V[r * n + qq] = sv * xp + scale(xq, c);
+            }
+            __syncthreads();
+            // rows of A:  A[p,:] <- c A[p,:] - s A[q,:],  A[q,:] <- conj(s) A[p,:] + c A[q,:]
+            for (int w = tid; w < npairs * n; w += blockDim.x) {
+                const int k = w / n, cc = w - k * n;
+                const int pp = s_p[k], qq = s_q[k];
+                if (pp < 0) continue;
+                const double c = s_c[k];
+                const cd sv = s_s[k], sc = conj(sv);
+                const cd xp = A[pp * n + cc], xq = A[qq * n + cc];
+                A[pp * n + cc] = scale(xp, c) - sv * xq;
+                A[qq * n + cc] = sc * xp + scale(xq, c);
+            }
+            __syncthreads();
+        }
+        double off = 0.0;
+        for (int idx = tid; idx < nn; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            if (r != c) off = fmax(off, norm2(A[idx]));
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = off;
+        __syncthreads();
+        off = 0.0;
+        for (int w = 0; w < GF_THREADS / 32; ++w) off = fmax(off, s_red[w]);
+        __syncthreads();
+        converged = off <= 1e-30 * scale2;        // |off-diagonal| <= 1e-15 |A|: CTA-uniform
+    }
+    for (int c = tid; c < n; c += blockDim.x) evals[c] = A[c * n + c].x;
+    for (int idx = tid; idx < nn; idx += blockDim.x) evecs[idx] = V[idx];
+    if (tid == 0) *status = s_bad | (converged ? 0 : 4);
+}
+
+// TX_GF_SEPARABLE, one CTA per energy: scalar hopping h01 = t I, so the surface GF is a function of h00,
+//   g = U diag(g_closed(z, eps_m, t)) U^dag   (the reference's g_closed per transverse mode, wfm/__init__.py:337-340),
+// Sigma = |t|^2 g on both sides.  U, eps from hermitian_eig_kernel; one n x n block (U diag(g)) in shared memory.
+__global__ void __launch_bounds__(GF_THREADS) separable_gf_kernel(const GfParams p) {
+    extern __shared__ double2 gf_smem[];
+    const int n = p.n;
+    const int nn = n * n;
+    const int e = blockIdx.x;
+    const cd E = p.E[e];
+    const cd z = mk(E.x, E.y + p.imE);
+    const cd t0 = p.h01[0];
+    cd* B = reinterpret_cast<cd*>(gf_smem);
+    for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+        const int c = idx % n;
+        const cd gm = g_closed_channel(z, mk(p.evals[c], 0.0), t0);
+        B[idx] = p.evecs[idx] * gm;
+    }
+    __syncthreads();
+    cd* out = p.g ? p.g + (long long)e * nn : p.sigma + (long long)e * nn;
+    if (threadIdx.x == 0) {
+        if (p.n_iter) p.n_iter[e] = 0;
+        if (p.conv) p.conv[e] = 0.0;
+        if (p.converged) p.converged[e] = 1;
+    }
+    cta_gemm(out, B, OP_N, p.evecs, OP_H, n);
+    const double kap = norm2(t0);
+    if (p.g && p.sigma) {
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) p.sigma[(long long)e * nn + idx] = scale(out[idx], kap);
+    } else if (p.sigma) {
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) out[idx] = scale(out[idx], kap);
+    }
+}
+
+__device__ void surface_gf_body(const GfParams& p, const int e) {
     extern __shared__ double2 gf_smem[];
     __shared__ int s_ipiv[64];
     __shared__ cd s_colk[64];
     __shared__ int s_flag;
     const int n = p.n;
     const int nn = n * n;
-    const int e = blockIdx.x;
     const cd E = p.E[e];
-    cd* base = (p.scratch != nullptr) ? p.scratch + (long long)e * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
+    // the global workspace (blocks too large for shared memory) is indexed by CTA, not by energy: only the
+    // resident CTAs need one, and a few hundred of them stay L2-resident
+    cd* base = (p.scratch != nullptr) ? p.scratch + (long long)blockIdx.x * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
     cd* stage = (p.scratch != nullptr) ? reinterpret_cast<cd*>(gf_smem) : nullptr;   // inverse staging when blocks are global
     cd* m0 = base;               // g / result
     cd* m1 = base + nn;
@@ -210,8 +369,57 @@ __global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p
     if (p.sigma) emit_sigma(p, m0, m1, p.sigma + (long long)e * nn);
 }
 
+// One CTA per energy, persistent over the energy axis (grid = resident CTAs).
+__global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p) {
+    for (int e = blockIdx.x; e < p.nE; e += gridDim.x) {
+        surface_gf_body(p, e);
+        __syncthreads();
+    }
+}
+
+// grow-only workspace of the decimation for blocks beyond shared memory (per device)
+struct GfScratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+GfScratch g_gf_scratch[16];
+
 int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     const int n = p.n;
+    if (p.mode == TX_GF_SEPARABLE) {
+        // eigendecomposition of h00 once, then one CTA per energy with a single n x n block in shared memory
+        if (!p.g && !p.sigma) return fail(TX_ERR_ARG, "TX_GF_SEPARABLE needs g or sigma");
+        const size_t nn = (size_t)n * n;
+        char* ws = nullptr;
+        TX_CUDA(cudaMalloc(&ws, nn * sizeof(cd) + 64 * sizeof(double) + 256));
+        *scratch_owner = reinterpret_cast<cd*>(ws);
+        cd* evecs = reinterpret_cast<cd*>(ws);
+        double* evals = reinterpret_cast<double*>(ws + nn * sizeof(cd));
+        int* status = reinterpret_cast<int*>(ws + nn * sizeof(cd) + 64 * sizeof(double));
+        const size_t smem_eig = 2 * nn * sizeof(cd);
+        if (smem_eig > 48 * 1024)
+            TX_CUDA(cudaFuncSetAttribute(hermitian_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eig));
+        hermitian_eig_kernel<<<1, GF_THREADS, smem_eig, st>>>(p.h00, p.h01, n, evals, evecs, status);
+        count_launch();
+        TX_CUDA(cudaGetLastError());
+        int host_status = 0;
+        TX_CUDA(cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TX_CUDA(cudaStreamSynchronize(st));
+        if (host_status & 1) return fail(TX_ERR_ARG, "TX_GF_SEPARABLE needs a hopping block that is a scalar multiple of the identity");
+        if (host_status & 2) return fail(TX_ERR_ARG, "TX_GF_SEPARABLE needs a Hermitian on-site block");
+        if (host_status & 4) return fail(TX_ERR_NOCONV, "Jacobi eigensolver did not converge");
+        p.evals = evals;
+        p.evecs = evecs;
+        p.scratch = nullptr;
+        p.scratch_per = 0;
+        const size_t smem = nn * sizeof(cd);
+        if (smem > 48 * 1024)
+            TX_CUDA(cudaFuncSetAttribute(separable_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        separable_gf_kernel<<<p.nE, GF_THREADS, smem, st>>>(p);
+        count_launch();
+        TX_CUDA(cudaGetLastError());
+        return TX_OK;
+    }
     const size_t mats = (p.mode == TX_GF_SANCHO) ? GF_MAX_MATS : 3;
     const size_t bytes = mats * (size_t)n * n * sizeof(cd);
     size_t smem = bytes;
@@ -220,14 +428,28 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     if (bytes > 200 * 1024) {
         smem = (size_t)n * n * sizeof(cd);      // staging block for the inverse
         p.scratch_per = (long long)mats * n * n;
-        cd* ws = nullptr;
-        TX_CUDA(cudaMalloc(&ws, (size_t)p.nE * bytes));
-        p.scratch = ws;
-        *scratch_owner = ws;
     }
     if (smem > 48 * 1024)
         TX_CUDA(cudaFuncSetAttribute(surface_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    surface_gf_kernel<<<p.nE, GF_THREADS, smem, st>>>(p);
+    int dev = 0, sms = 0, per_sm = 1;
+    TX_CUDA(cudaGetDevice(&dev));
+    TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_gf_kernel, GF_THREADS, smem));
+    const int grid = (int)((long long)p.nE < (long long)sms * per_sm ? p.nE : sms * (per_sm > 0 ? per_sm : 1));
+    if (p.scratch_per) {
+        GfScratch& sc = g_gf_scratch[dev & 15];
+        const size_t need = (size_t)grid * bytes;
+        if (need > sc.cap) {
+            TX_CUDA(cudaDeviceSynchronize());
+            if (sc.ptr) cudaFree(sc.ptr);
+            sc.ptr = nullptr;
+            sc.cap = 0;
+            TX_CUDA(cudaMalloc(&sc.ptr, need));
+            sc.cap = need;
+        }
+        p.scratch = reinterpret_cast<cd*>(sc.ptr);
+    }
+    surface_gf_kernel<<<grid, GF_THREADS, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
@@ -238,7 +460,7 @@ int check_gf_args(const void* h00, const void* h01, int n, const void* E, int nE
     if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "surface GF block size n=%d outside 1..64", n);
     if (nE < 1) return fail(TX_ERR_ARG, "nE must be positive");
     if (side != 1 && side != -1) return fail(TX_ERR_ARG, "side must be +1 or -1");
-    if (mode < TX_GF_CLOSED || mode > TX_GF_SANCHO) return fail(TX_ERR_ARG, "unknown surface GF mode %d", mode);
+    if (mode < TX_GF_CLOSED || mode > TX_GF_SEPARABLE) return fail(TX_ERR_ARG, "unknown surface GF mode %d", mode);
     if (mode == TX_GF_RICEMELE && (n % 2)) return fail(TX_ERR_ARG, "Rice-Mele leads need an even block size");
     return TX_OK;
 }

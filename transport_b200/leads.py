@@ -60,7 +60,11 @@ def _mode_of(converger):
             return _lib.TX_GF_RICEMELE, {}
         if converger == "sancho":
             return _lib.TX_GF_SANCHO, dict(imE=0.0, conv_tol=SANCHO_TOL, max_iter=SANCHO_MAX_ITER)
+        if converger == "separable":
+            return _lib.TX_GF_SEPARABLE, {}
     if isinstance(converger, tuple):
+        if len(converger) == 2 and converger[0] == "separable":
+            return _lib.TX_GF_SEPARABLE, dict(imE=float(converger[1]))
         if len(converger) >= 2 and converger[0] == "sancho":
             eta = float(converger[1])
             tol = float(converger[2]) if len(converger) > 2 else SANCHO_TOL
