@@ -129,7 +129,8 @@ int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1
  * shared memory). */
 long long tx_sweep_workspace_elems(int n, long long n_pts);
 
-/* Number of kernel launches tx_transmission_sweep_dev issues for this shape (for accounting). */
+/* Number of kernel launches tx_transmission_sweep_dev issues for this shape (for accounting; an affine
+ * family h0 + J*h1 adds one expansion kernel, short energy axes may fall back to the plain sweep). */
 int tx_sweep_launch_count(int n, int M, int hop_mode);
 /* Running count of sweep / surface-GF kernel launches issued by this library in the process. */
 long long tx_launch_counter(void);

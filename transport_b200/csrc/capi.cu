@@ -343,8 +343,12 @@ int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n) {
 
 int tx_sweep_launch_count(int n, int M, int hop_mode) {
     (void)M;
-    (void)hop_mode;
-    return round_up_block(n) ? 1 : 0;
+    const int N = round_up_block(n);
+    if (N == 0) return 0;
+    // 5 <= n <= 8 with scalar hopping: structure scan (fill, scan, count) + the two instantiations of the
+    // telescoped sweep (one of them returns at once); an affine family adds its expansion kernel
+    if (N == 8 && hop_mode == TX_HOP_SCALAR) return g_diag_tail ? 5 : 1;
+    return 1;
 }
 
 int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
