@@ -190,6 +190,61 @@ int tx_landauer_current(const double* T, const double* E, int nE, const double* 
 int tx_landauer_current_dev(const double* T, const double* E, int nE, const double* muL, const double* muR, int n_bias,
                             double kBT, double* jE, double* I, void* stream);
 
+/* ---- Bardeen transfer-Hamiltonian path (BASELINE config 5; transport/bardeen/__init__.py) ---------------
+ * The reference diagonalises dense well Hamiltonians with np.linalg.eigh (:459, :483, get_mstates :755-761)
+ * and keeps the states below an energy cutoff (:463, :486, :174-182).  For chains every per-channel well
+ * Hamiltonian is real symmetric tridiagonal: d[n_mat][S] diagonal, e[n_mat][S-1] off-diagonal.
+ *
+ * tx_tridiag_eigh_below: eigenpairs with eigenvalue < cut_states[mat], ascending, at most max_states per
+ * matrix: evals [n_mat][max_states], evecs [n_mat][max_states][S] (unit norm; may be NULL);
+ * n_states[mat] = number of eigenvalues < cut_states[mat] (NOT clamped: > max_states means truncated),
+ * n_below[mat] = number < cut_count[mat] (cut_count NULL: same as cut_states; n_below may be NULL).
+ * max_states = 0 only counts.  Host pointers.  The _dev forms take device pointers and a stream;
+ * scratch has the size of evecs. */
+int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                          const double* cut_count, int max_states, double* evals, double* evecs, int* n_states,
+                          int* n_below);
+int tx_tridiag_count_below_dev(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                               const double* cut_count, int* n_states, int* n_below, void* stream);
+int tx_tridiag_eigh_below_dev(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                              const int* n_states, int max_states, double* evals, double* evecs, double* scratch,
+                              void* stream);
+/* tx_bardeen_wells: P independent geometries x n channels.  Left-well states (dL, eL [P][n][S], [P][n][S-1];
+ * kept below cutL [P][n]) and right-well states (dR, eR; computed below cutR_states, counted below
+ * cutR_count) and the window-averaged Oppenheimer matrix elements (kernel_well :127-151, kernel_well_prime
+ * :502-519, matrix_element :835-857)
+ *   Mavg[p][beta][m][alpha] = mean over k with |EL[p][alpha][m] - ER[p][beta][k]| < interval of
+ *                             <psiR[beta][k] | Hdiff[:, :, beta, alpha] | psiL[alpha][m]>
+ * with each element made >= 0 first when sign_fix (:141), the nearest k when interval is NaN, 0.0 when no
+ * state qualifies.  Hdiff = Hsys - HL is block tridiagonal in the site index: hd0 [P][S][n][n],
+ * hdU [P][S-1][n][n] = Hdiff[j][j+1], hdL [P][S-1][n][n] = Hdiff[j+1][j] (real).
+ * Outputs: EL, ER [P][n][max_states]; nL, nR_states, nR_below [P][n]; Mavg [P][n][max_states][n];
+ * psiL, psiR [P][n][max_states][S] or NULL.  max_states = 0: counts only (size the buffers, call again). */
+int tx_bardeen_wells(const double* dL, const double* eL, const double* dR, const double* eR, const double* cutL,
+                     const double* cutR_states, const double* cutR_count, const double* hd0, const double* hdU,
+                     const double* hdL, int P, int n, int S, int max_states, double interval, int sign_fix, double* EL,
+                     int* nL, double* ER, int* nR_states, int* nR_below, double* Mavg, double* psiL, double* psiR);
+long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states);
+int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
+                         const double* cutL, const double* cutR_states, const double* cutR_count,
+                         const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
+                         double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
+                         int* nR_below, double* Mavg, void* workspace, void* stream);
+/* bardeen.current (:537-575, nFD :1014-1020): I[p][alpha][beta][i] = 2 pi sum_m stat(E[p][alpha][m], Vb[i])
+ * M2[p][alpha][m][beta], stat = fL (1 - fR) - fR (1 - fL), muL = muR + Vb[i].  E [P][n][nb], M2 [P][n][nb][n]. */
+int tx_bardeen_current(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,
+                       double kBT, double* I);
+int tx_bardeen_current_dev(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,
+                           double kBT, double* I, void* stream);
+/* bardeen.Ts_bardeen (:577-632): T[alpha][m][beta] = NL/(k tL[alpha]) NR/tR[beta] dos M2[alpha][m][beta];
+ * per-channel lead parameters tL, VL, tR, VR [n].  Outside the band k and dos take the real parts of numpy's
+ * complex branches (k = 0 or pi, dos = 0).  flags [2 + n*n]: flags[0] = number of wavenumbers outside the band,
+ * flags[1] = number of densities of states above the band top, flags[2 + alpha*n + beta] = number of m with a
+ * real density of states; the reference (:611, :624, max of the imaginary parts) raises ValueError when
+ * flags[0] > 0, flags[1] > 0 or one of the remaining counts is 0. */
+int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double* tL, const double* VL, const double* tR,
+                  const double* VR, int NL, int NR, double* T, int* flags);
+
 /* Tuning knob for the 5 <= n <= 8, scalar-hopping sweep (bench.py --variant):
  *   13   DEFAULT: telescoped sweep (rgf_n8t.cuh): register-resident DMMA recurrence, one inverse per chunk
  *        of up to kmax sites, diagonal sites as column scalings; eight energies of one Hamiltonian per warp

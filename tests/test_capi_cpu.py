@@ -108,3 +108,51 @@ def test_spin_flip_sums():
     keep, flip = spin_flip_sums(T)
     assert keep[0, 0, 0] == T[0, 0, 0, :4].sum() and flip[0, 0, 0] == T[0, 0, 0, 4:].sum()
     assert keep[0, 0, 5] == T[0, 0, 5, 4:].sum() and flip[0, 0, 5] == T[0, 0, 5, :4].sum()
+
+
+def test_bardeen_host_assembly_matches_oracle_hsysmat():
+    """host-side slicing of the region parameters into block-tridiagonal arrays (no device needed)"""
+    from oracle import bardeen_oracle as bo
+    from transport_b200 import bardeen
+    rng = np.random.default_rng(3)
+    n, NC = 2, 5
+    mats = [np.diag(rng.normal(size=n)) for _ in range(6)]             # tinfty, tL, tR, Vinfty, VL, VR
+    HC = np.zeros((NC, NC, n, n), dtype=complex)
+    for j in range(NC):
+        HC[j, j] = rng.normal(size=(n, n))
+    for j in range(NC - 1):
+        HC[j, j + 1] = rng.normal(size=(n, n)); HC[j + 1, j] = rng.normal(size=(n, n))
+    H = bo.Hsysmat(*mats, 3, 4, 6, HC)
+    dg, up, lo = bardeen.hsys_site_blocks(*mats, 3, 4, 6, HC)
+    S = H.shape[0]
+    i = np.arange(S)
+    assert np.array_equal(H[i, i], dg) and np.array_equal(H[i[:-1], i[:-1] + 1], up) and np.array_equal(H[i[:-1] + 1, i[:-1]], lo)
+    H[i, i] = 0; H[i[:-1], i[:-1] + 1] = 0; H[i[:-1] + 1, i[:-1]] = 0
+    assert not np.any(H)
+    HC[0, 2] = 1.0
+    with pytest.raises(NotImplementedError):
+        bardeen.hsys_site_blocks(*mats, 3, 4, 6, HC)
+    with pytest.raises(ValueError):                                    # bardeen/__init__.py:705 NC odd
+        bardeen.hsys_site_blocks(*mats, 3, 4, 6, HC[:4, :4])
+
+
+def test_bardeen_argument_errors_match_reference():
+    from transport_b200 import bardeen
+    one = np.eye(1)
+    HC = np.zeros((3, 3, 1, 1), dtype=complex)
+    with pytest.raises(ValueError):                                    # :70 shape mismatch
+        bardeen.kernel_well(one, one, one, one, one, one, one, one, 2, 3, 3, HC, HC[:1, :1], one, one)
+    with pytest.raises(ValueError):                                    # :73 len(defines_Sz)
+        bardeen.kernel_well(one, one, one, one, one, one, one, one, 2, 3, 3, HC, HC, np.eye(2), one)
+    with pytest.raises(AssertionError):                                # :432 HC == HCprime
+        bardeen.kernel_well_prime(one, one, one, one, one, one, one, one, 2, 3, 3, HC, HC, one)
+    with pytest.raises(ValueError, match="spin diagonal"):             # :81
+        HC2 = np.zeros((3, 3, 2, 2), dtype=complex)
+        bardeen.kernel_well_prime(np.eye(2), np.ones((2, 2)), np.eye(2), np.eye(2), np.eye(2), np.eye(2), np.eye(2),
+                                  np.eye(2), 2, 3, 3, HC2 + 1, HC2, np.eye(2))
+    with pytest.raises(TypeError):                                     # :541
+        bardeen.current([[0.0]], np.ones((1, 1, 1)), np.array([0.1]), one, 0.0, 0.1)
+    with pytest.raises(_lib.TransportError):                           # no CPU fallback
+        if _lib.device_count() > 0:
+            raise _lib.TransportError(2, "gpu present")
+        bardeen.current(np.array([[0.0]]), np.ones((1, 1, 1)), np.array([0.1]), one, 0.0, 0.1)

@@ -59,6 +59,15 @@ _SIGNATURES = {
     "tx_landauer_current": (c_int, [_P, _P, c_int, _P, _P, c_int, c_double, _P, _P]),
     "tx_landauer_current_dev": (c_int, [_P, _P, c_int, _P, _P, c_int, c_double, _P, _P, _P]),
     "tx_hsysmat": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "tx_tridiag_eigh_below": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P]),
+    "tx_tridiag_count_below_dev": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "tx_tridiag_eigh_below_dev": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P]),
+    "tx_bardeen_wells": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, c_double, c_int] + [_P] * 8),
+    "tx_bardeen_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int, c_int]),
+    "tx_bardeen_wells_dev": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, c_double, c_int] + [_P] * 8),
+    "tx_bardeen_current": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P]),
+    "tx_bardeen_current_dev": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P]),
+    "tx_bardeen_ts": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "tx_debug_invert": (c_int, [_P, _P, c_int, c_int]),
     "tx_measure_fp64_peak": (c_int, [_P, _P]),
     "tx_measure_dmma_peak": (c_int, [_P, _P]),

@@ -1,5 +1,9 @@
-"""Drop-in mirror of the two `transport.bardeen` functions on the T(E) path
-(reference: transport/bardeen/__init__.py): `Hsysmat` (:690-750) and `Ts_wfm_well` (:634-685).
+"""Drop-in mirror of `transport.bardeen` (reference: transport/bardeen/__init__.py): `Hsysmat` (:690-750),
+`Ts_wfm_well` (:634-685) and the transfer-Hamiltonian path of BASELINE config 5 — `kernel_well` (:17-257),
+`kernel_well_prime` (:400-532), `current` (:537-575), `Ts_bardeen` (:577-632) — plus the batched entry
+`wells_batched` the scalar ones are a batch-of-one of.  Every number comes from libtransport_b200.so
+(csrc/bardeen.cu); numpy is used for argument checks and for slicing the region parameters into the
+tridiagonal arrays the C ABI takes.
 
 `Ts_wfm_well` in the reference still calls `wfm.kernel` with the old 6-argument signature and raises
 TypeError against the current tree.  Here it is fixed forward: the block
@@ -10,7 +14,7 @@ super-blocks of size 2n, which turns the pentadiagonal chain into a block-tridia
 import numpy as np
 
 from . import _lib, leads
-from ._lib import as_c128, check, ptr
+from ._lib import as_c128, as_f64, check, ptr
 from .sweep import transmission_sweep
 
 
@@ -135,3 +139,196 @@ def Ts_wfm_well(tL, tR, VL, VR, HC, Emas, verbose=0) -> np.ndarray:
         for m in range(n_bound):
             Tbmas[:, m, alpha] = T[alpha * n_bound + m, alpha]
     return Tbmas
+
+
+# ------------------------------------------------------------------------------------------------
+# Bardeen transfer-Hamiltonian path (config 5)
+# ------------------------------------------------------------------------------------------------
+def _scalar_hopping(t):
+    """bardeen/__init__.py:78-88, :444-454: hopping matrices must be spin diagonal and spin independent."""
+    if np.any(t - np.diagflat(np.diagonal(t))): raise ValueError("not spin diagonal")
+    diag = np.diagonal(t)
+    if np.any(diag - diag[0]): raise ValueError("not spin independent")
+    return t[0, 0]
+
+
+def hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninfty, NL, NR, HC):
+    """The block-tridiagonal content of Hsysmat(...) (bound=True) without the S x S zeros:
+    (diag[S,n,n], upper[S-1,n,n] = H[j,j+1], lower[S-1,n,n] = H[j+1,j]).  HC must be a chain
+    (block tridiagonal in the site index); anything else is outside what the device path covers."""
+    HC = np.asarray(HC)
+    NC, n = HC.shape[0], HC.shape[-1]
+    if NC % 2 != 1: raise ValueError
+    for i in range(NC):
+        for j in range(NC):
+            if abs(i - j) > 1 and np.any(HC[i, j]):
+                raise NotImplementedError("HC couples sites beyond nearest neighbours: not a tridiagonal chain")
+    S = 2 * Ninfty + NL + NR + NC
+    a, b = Ninfty, Ninfty + NL
+    c, d = b + NC, b + NC + NR
+    diag = np.zeros((S, n, n), dtype=complex)
+    up = np.zeros((S - 1, n, n), dtype=complex)
+    lo = np.zeros((S - 1, n, n), dtype=complex)
+    diag[:a] = Vinfty; diag[a:b] = VL; diag[c:d] = VR; diag[d:] = Vinfty
+    idx = np.arange(NC)
+    diag[b:c] = HC[idx, idx]
+    up[:a] = -tinfty; up[a:b] = -tL; up[c - 1:d - 1] = -tR; up[d - 1:] = -tinfty
+    lo[:] = up
+    up[b:c - 1] = HC[idx[:-1], idx[:-1] + 1]
+    lo[b:c - 1] = HC[idx[:-1] + 1, idx[:-1]]
+    return diag, up, lo
+
+
+def _channel_tridiagonals(blocks):
+    """Per-channel real symmetric tridiagonals d[n,S], e[n,S-1] of a block-tridiagonal Hamiltonian whose
+    blocks are diagonal in the channel index (the reference takes H[:, :, a, a], :459 and :483)."""
+    diag, up, lo = blocks
+    n = diag.shape[-1]
+    ch = np.arange(n)
+    d, e, el = diag[:, ch, ch].T, up[:, ch, ch].T, lo[:, ch, ch].T
+    if np.any(np.imag(d)) or np.any(np.imag(e)) or np.any(e != el):
+        raise NotImplementedError("well Hamiltonians must be real symmetric (complex hoppings are not covered)")
+    return as_f64(np.real(d)), as_f64(np.real(e))
+
+
+def _is_channel_diagonal(blocks):
+    n = blocks[0].shape[-1]
+    off = ~np.eye(n, dtype=bool)
+    return not any(np.any(b[:, off]) for b in blocks)
+
+
+def wells_batched(dL, eL, dR, eR, cutL, cutR_states, cutR_count, hd0, hdU, hdL, interval, sign_fix,
+                  want_states=False):
+    """One device pass over P geometries x n channels (tx_bardeen_wells).  Shapes: dL, dR [P,n,S];
+    eL, eR [P,n,S-1]; cut* [P,n]; hd0 [P,S,n,n]; hdU, hdL [P,S-1,n,n].
+    Returns dict(EL, nL, ER, nR_states, nR_below, Mavg[, psiL, psiR]); Mavg[p, beta, m, alpha]."""
+    lib = _lib.load()
+    dL, eL, dR, eR = as_f64(dL), as_f64(eL), as_f64(dR), as_f64(eR)
+    P, n, S = dL.shape
+    cutL, cutRs, cutRc = as_f64(cutL), as_f64(cutR_states), as_f64(cutR_count)
+    hd0, hdU, hdL = as_f64(hd0), as_f64(hdU), as_f64(hdL)
+    assert eL.shape == (P, n, S - 1) and dR.shape == dL.shape and eR.shape == eL.shape
+    assert hd0.shape == (P, S, n, n) and hdU.shape == (P, S - 1, n, n) and hdL.shape == hdU.shape
+    nL = np.zeros((P, n), dtype=np.int32); nRs = np.zeros_like(nL); nRb = np.zeros_like(nL)
+    args = [ptr(dL), ptr(eL), ptr(dR), ptr(eR), ptr(cutL), ptr(cutRs), ptr(cutRc), ptr(hd0), ptr(hdU), ptr(hdL), P, n, S]
+    check(lib.tx_bardeen_wells(*args, 0, float(interval), int(sign_fix), None, ptr(nL), None, ptr(nRs), ptr(nRb),
+                               None, None, None))
+    ms = int(max(nL.max(), nRs.max(), 1))
+    EL = np.zeros((P, n, ms)); ER = np.zeros((P, n, ms)); Mavg = np.zeros((P, n, ms, n))
+    psiL = np.zeros((P, n, ms, S)) if want_states else None
+    psiR = np.zeros((P, n, ms, S)) if want_states else None
+    check(lib.tx_bardeen_wells(*args, ms, float(interval), int(sign_fix), ptr(EL), ptr(nL), ptr(ER), ptr(nRs), ptr(nRb),
+                               ptr(Mavg), ptr(psiL), ptr(psiR)))
+    out = dict(EL=EL, nL=nL, ER=ER, nR_states=nRs, nR_below=nRb, Mavg=Mavg)
+    if want_states:
+        out.update(psiL=psiL, psiR=psiR)
+    return out
+
+
+def _real_blocks(blocks):
+    if any(np.any(np.imag(b)) for b in blocks):
+        raise NotImplementedError("complex Hsys - HL is not covered by the device path")
+    return [as_f64(np.real(b)) for b in blocks]
+
+
+def kernel_well_prime(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR, HC, HCprime, E_cutoff,
+                      interval=1e-9, verbose=0) -> tuple:
+    """Oppenheimer matrix elements |M_{beta m alpha}|^2 between Sz-resolved well states, averaged over the
+    final states inside the energy window (bardeen/__init__.py:400-532).  Returns (Emas[n, nb] complex,
+    Mbmas[n(beta), nb, n(alpha)] float)."""
+    if np.shape(HC) != np.shape(HCprime): raise ValueError
+    n = np.shape(HC)[-1]
+    assert np.any(HC - HCprime)                             # :432
+    tLa, tRa = _scalar_hopping(tL), _scalar_hopping(tR)
+    bL = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VRprime, Ninfty, NL, NR, HCprime)
+    bR = hsys_site_blocks(tinfty, tL, tR, Vinfty, VLprime, VR, Ninfty, NL, NR, HCprime)
+    bS = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninfty, NL, NR, HC)
+    assert _is_channel_diagonal(bL)                         # is_alpha_conserving, :457
+    assert _is_channel_diagonal(bR)                         # :481
+    dL, eL = _channel_tridiagonals(bL)
+    dR, eR = _channel_tridiagonals(bR)
+    hd = _real_blocks([s - l for s, l in zip(bS, bL)])      # Hdiff = Hsys - HL, :497
+    Ecut = np.real(np.diagonal(np.asarray(E_cutoff)))
+    cutL = Ecut - 2 * np.real(tLa)
+    cutR = Ecut - 2 * np.real(tRa)
+    r = wells_batched(dL[None], eL[None], dR[None], eR[None], cutL[None], cutR[None], cutR[None],
+                      hd[0][None], hd[1][None], hd[2][None], interval, sign_fix=False)
+    nL = r["nL"][0]
+    nb = int(nL.max())
+    if np.any(nL < 1) or np.any(r["nR_states"][0] < 1):
+        raise IndexError("a channel has no bound state below E_cutoff")     # the reference's Ems[-1] fails too
+    # ragged channels are padded with their last bound state (:468-478)
+    pick = np.minimum(np.arange(nb)[None, :], (nL - 1)[:, None])            # [alpha, m] -> stored m
+    Emas = np.take_along_axis(r["EL"][0], pick, axis=1).astype(complex)
+    Mavg = r["Mavg"][0]                                                     # [beta, m, alpha]
+    Mbmas = np.empty((n, nb, n), dtype=float)
+    for alpha in range(n):
+        Mbmas[:, :, alpha] = Mavg[:, pick[alpha], alpha]
+    return Emas, Mbmas * Mbmas
+
+
+def kernel_well(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR, HC, HCobs, defines_Sz,
+                E_cutoff, interval=1e-12, expval_tol=1e-12, verbose=0) -> tuple:
+    """Effective Oppenheimer matrix elements of bardeen/__init__.py:17-257 for n_loc_dof = 1 (rbbarrier.py,
+    rbstep.py — the geometries of BASELINE config 5).  With one local degree of freedom the observable basis is
+    the eigenbasis (HCobs = HC), the basis change :160-166 is the identity and the spin classification :192-232
+    is trivial, so Mbmas_eff[0, mu, 0] = |<M_mu>|^2 for mu < nu_cut and (rounding noise in the reference, exactly
+    0 here) for mu >= nu_cut, the reference's row cut :181 acting on the diagonal."""
+    if np.shape(HC) != np.shape(HCobs): raise ValueError
+    n = np.shape(HC)[-1]
+    if n != len(defines_Sz): raise ValueError
+    tLa, tRa = _scalar_hopping(tL), _scalar_hopping(tR)
+    if n != 1 or np.any(np.asarray(HC) - np.asarray(HCobs)):
+        raise NotImplementedError("kernel_well is covered for n_loc_dof = 1 with HCobs = HC; "
+                                  "spin-resolved wells go through kernel_well_prime")
+    bL = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VRprime, Ninfty, NL, NR, HC)
+    bR = hsys_site_blocks(tinfty, tL, tR, Vinfty, VLprime, VR, Ninfty, NL, NR, HC)
+    bS = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninfty, NL, NR, HC)
+    dL, eL = _channel_tridiagonals(bL)
+    dR, eR = _channel_tridiagonals(bR)
+    hd = _real_blocks([s - l for s, l in zip(bS, bL)])
+    cut = float(np.max(np.real(E_cutoff)))                  # :174
+    cutL = np.array([cut - 2 * np.real(tLa)])
+    cutR = np.array([cut - 2 * np.real(tRa)])
+    # the reference averages over ALL right-well states inside the window (:127-151), also above the cutoff
+    cutR_states = np.array([np.inf]) if np.isnan(interval) else cutR + abs(interval)
+    r = wells_batched(dL[None], eL[None], dR[None], eR[None], cutL[None], cutR_states[None], cutR[None],
+                      hd[0][None], hd[1][None], hd[2][None], interval, sign_fix=True)
+    mu_cut, nu_cut = int(r["nL"][0, 0]), int(r["nR_below"][0, 0])
+    Emas = r["EL"][0, :, :mu_cut].astype(complex)
+    M = r["Mavg"][0, :, :mu_cut, :].copy()
+    M[:, nu_cut:, :] = 0.0
+    return Emas, M * M
+
+
+def current(Emas, Mbmas, Vb, tbulk, muR, kBT, verbose=0) -> np.ndarray:
+    """Current as a function of bias voltage, Iab[alpha, beta, Vb] (bardeen/__init__.py:537-575)."""
+    for arr in [Emas, Mbmas, Vb]:
+        if not isinstance(arr, np.ndarray): raise TypeError
+    n, nb = np.shape(Emas)
+    E = as_f64(np.real(Emas))
+    M = as_f64(Mbmas)
+    V = as_f64(Vb)
+    Iab = np.empty((n, n, len(V)), dtype=float)
+    check(_lib.load().tx_bardeen_current(ptr(E), ptr(M), 1, n, nb, ptr(V), len(V), float(muR), float(kBT), ptr(Iab)))
+    return Iab
+
+
+def Ts_bardeen(Emas, Mbmas, tL, tR, VL, VR, NL, NR, verbose=0) -> np.ndarray:
+    """Transmission coefficients from the averaged matrix elements (bardeen/__init__.py:577-632)."""
+    if Mbmas.dtype != float: raise TypeError
+    n, nb = np.shape(Emas)
+    if len(np.shape(Mbmas)) != 3: raise ValueError
+    if np.shape(Mbmas)[0] != n: raise ValueError
+    conv = []
+    for c in [tL, VL, tR, VR]:
+        if np.any(c - np.diagflat(np.diagonal(c))): raise ValueError
+        conv.append(as_f64(np.real(np.diagonal(c))))
+    E = as_f64(np.real(Emas))
+    M = as_f64(Mbmas)
+    T = np.empty_like(M)
+    flags = np.zeros(2 + n * n, dtype=np.int32)
+    check(_lib.load().tx_bardeen_ts(ptr(E), ptr(M), n, nb, ptr(conv[0]), ptr(conv[1]), ptr(conv[2]), ptr(conv[3]),
+                                    int(NL), int(NR), ptr(T), ptr(flags)))
+    if flags[0] or flags[1] or np.any(flags[2:] == 0): raise ValueError     # :611, :624
+    return T

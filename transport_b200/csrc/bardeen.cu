@@ -1,0 +1,630 @@
+// Bardeen transfer-Hamiltonian path (BASELINE config 5): bound states of the
+// left/right well Hamiltonians, Oppenheimer matrix elements with energy-window averaging, Fermi-weighted
+// current and the Bardeen transmission estimate.  Reference: transport/bardeen/__init__.py
+//     kernel_well :17-257, kernel_well_prime :400-532, matrix_element :835-857,
+//     current :537-575 (nFD :1014-1020), Ts_bardeen :577-632.
+//
+// The reference diagonalises dense (S n)^2 matrices with np.linalg.eigh and keeps the states below an
+// energy cutoff.  For the chains its drivers build (rbbarrier.py, rbstep.py, rbmenez_nosup_el.py) every
+// per-channel well Hamiltonian is a real symmetric TRIDIAGONAL matrix, so here:
+//   * eigenvalues below the cutoff: Sturm-count multisection, one warp per eigenvalue, the 32 lanes
+//     evaluating 32 shifts of the bracket per pass (5 bits per pass instead of 1);
+//   * eigenvectors: twisted factorisation (forward LDL^T and backward UDU^T pivots of T - lambda,
+//     twist where |gamma| is smallest) — O(S) per state, and the exponentially small tails under the
+//     barrier, which are all the matrix elements see, come out with high RELATIVE accuracy;
+//   * matrix elements: one CTA per (problem, alpha, m, beta), y = Hdiff[beta,alpha] psi_m in shared
+//     memory, dot products only with the right-well states inside the energy window.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+
+#include "../../include/transport_b200.h"
+#include "tx_host.h"
+
+using namespace tx;
+
+namespace {
+
+constexpr int EIG_WARPS = 4;
+
+// number of eigenvalues < x (negative pivots of T - x), d and e2 = e*e in shared memory
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int S, double x,
+                                           double pivmin) {
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    int cnt = q < 0.0;
+    for (int i = 1; i < S; ++i) {
+        q = (d[i] - x) - e2[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q < 0.0;
+    }
+    return cnt;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// counts[mat][0] = #eig < cut_states[mat], counts[mat][1] = #eig < cut_count[mat].  One warp per matrix,
+// lanes 0/1 take the two shifts (global-memory reads: this kernel is a few microseconds).
+__global__ void tridiag_count_kernel(const double* __restrict__ d, const double* __restrict__ e, int S, int n_mat,
+                                     const double* __restrict__ cut_states, const double* __restrict__ cut_count,
+                                     int* __restrict__ n_states, int* __restrict__ n_below) {
+    const int mat = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (mat >= n_mat) return;
+    const double* dm = d + (size_t)mat * S;
+    const double* em = e + (size_t)mat * (S - 1);
+    double emax = 0.0;
+    for (int i = lane; i < S - 1; i += 32) emax = fmax(emax, em[i] * em[i]);
+    emax = warp_max(emax);
+    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    if (lane < 2) {
+        const double x = lane == 0 ? cut_states[mat] : cut_count[mat];
+        double q = dm[0] - x;
+        if (fabs(q) < pivmin) q = -pivmin;
+        int cnt = q < 0.0;
+        for (int i = 1; i < S; ++i) {
+            const double ee = em[i - 1];
+            q = (dm[i] - x) - ee * ee / q;
+            if (fabs(q) < pivmin) q = -pivmin;
+            cnt += q < 0.0;
+        }
+        if (lane == 0) n_states[mat] = cnt;
+        else n_below[mat] = cnt;
+    }
+}
+
+// One warp per (matrix, k): eigenvalue k (ascending) and its eigenvector.  grid = (ceil(max_states /
+// EIG_WARPS), n_mat).  Dynamic shared memory: d[S], e[S] (offdiagonal), e2[S].
+__global__ void __launch_bounds__(EIG_WARPS * 32)
+tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
+                   const double* __restrict__ cut_states, const int* __restrict__ n_states, int max_states,
+                   double* __restrict__ evals, double* __restrict__ evecs, double* __restrict__ scratch) {
+    extern __shared__ double sm[];
+    double* d = sm;
+    double* e = sm + S;
+    double* e2 = sm + 2 * S;
+    const int mat = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * EIG_WARPS + warp;
+    int nb = n_states[mat];
+    if (nb > max_states) nb = max_states;
+    if (blockIdx.x * EIG_WARPS >= nb) return;                   // whole CTA idle
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        d[i] = d_g[(size_t)mat * S + i];
+        const double ee = i < S - 1 ? e_g[(size_t)mat * (S - 1) + i] : 0.0;
+        e[i] = ee;
+        e2[i] = ee * ee;
+    }
+    __syncthreads();
+    if (k >= nb) return;
+
+    // Gershgorin bounds and pivmin
+    double glo = DBL_MAX, ghi = -DBL_MAX, emax = 0.0;
+    for (int i = lane; i < S; i += 32) {
+        const double r = (i ? fabs(e[i - 1]) : 0.0) + fabs(e[i]);
+        glo = fmin(glo, d[i] - r);
+        ghi = fmax(ghi, d[i] + r);
+        emax = fmax(emax, e2[i]);
+    }
+    glo = warp_min(glo);
+    ghi = warp_max(ghi);
+    emax = warp_max(emax);
+    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    const double tnorm = fmax(fabs(glo), fabs(ghi));
+    glo -= 2.0 * DBL_EPSILON * tnorm * S + 2.0 * pivmin;
+
+    // ---- multisection: count(lo) <= k < count(hi)
+    double lo = glo, hi = cut_states[mat];
+    for (int pass = 0; pass < 40; ++pass) {
+        const double x = lo + (hi - lo) * ((lane + 1) * (1.0 / 33.0));
+        const int c = sturm_count(d, e2, S, x, pivmin);
+        const unsigned above = __ballot_sync(0xffffffffu, c > k);
+        double nlo = lo, nhi = hi;
+        if (above == 0u) {
+            nlo = __shfl_sync(0xffffffffu, x, 31);
+        } else {
+            const int first = __ffs(above) - 1;
+            nhi = __shfl_sync(0xffffffffu, x, first);
+            const double below = __shfl_sync(0xffffffffu, x, first > 0 ? first - 1 : 0);
+            if (first > 0) nlo = below;
+        }
+        lo = fmax(lo, nlo);
+        hi = fmin(hi, nhi);
+        if (hi - lo <= DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin) break;
+    }
+    const double lam = 0.5 * (lo + hi);
+    if (lane == 0) evals[(size_t)mat * max_states + k] = lam;
+    if (evecs == nullptr) return;
+
+    // ---- twisted factorisation: lane 0 runs the forward pivots D+, lane 1 the backward pivots D-
+    double* z = evecs + ((size_t)mat * max_states + k) * S;      // D+ first, overwritten by the vector
+    double* dm = scratch + ((size_t)mat * max_states + k) * S;   // D-
+    if (lane < 2) {
+        const bool fwd = lane == 0;
+        double* out = fwd ? z : dm;
+        int idx = fwd ? 0 : S - 1;
+        const int step = fwd ? 1 : -1;
+        double q = d[idx] - lam;
+        if (fabs(q) < pivmin) q = -pivmin;
+        out[idx] = q;
+        for (int i = 1; i < S; ++i) {
+            const double ee = e2[fwd ? idx : idx - 1];
+            idx += step;
+            q = (d[idx] - lam) - ee / q;
+            if (fabs(q) < pivmin) q = -pivmin;
+            out[idx] = q;
+        }
+    }
+    __syncwarp();
+    // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - lam)
+    double best = DBL_MAX;
+    int r = 0;
+    for (int i = lane; i < S; i += 32) {
+        const double g = fabs(z[i] + dm[i] - (d[i] - lam));
+        if (g < best) {
+            best = g;
+            r = i;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int orr = __shfl_xor_sync(0xffffffffu, r, off);
+        if (ob < best || (ob == best && orr < r)) {
+            best = ob;
+            r = orr;
+        }
+    }
+    __syncwarp();
+    // z_r = 1; downwards z_i = -(e_i / D+_i) z_{i+1} (lane 0), upwards z_{i+1} = -(e_i / D-_{i+1}) z_i (lane 1)
+    if (lane == 0) {
+        double v = 1.0;
+        z[r] = 1.0;
+        for (int i = r - 1; i >= 0; --i) {
+            v = -(e[i] / z[i]) * v;
+            z[i] = v;
+        }
+    } else if (lane == 1) {
+        double v = 1.0;
+        for (int i = r; i < S - 1; ++i) {
+            v = -(e[i] / dm[i + 1]) * v;
+            z[i + 1] = v;
+        }
+    }
+    __syncwarp();
+    double nrm = 0.0;
+    for (int i = lane; i < S; i += 32) nrm = fma(z[i], z[i], nrm);
+    nrm = warp_sum(nrm);
+    const double sc = 1.0 / sqrt(nrm);
+    for (int i = lane; i < S; i += 32) z[i] *= sc;
+}
+
+// Window-averaged Oppenheimer matrix elements.  grid = (max_states, n*n, P): CTA (m, alpha*n+beta, p).
+//   Mavg[p][beta][m][alpha] = mean over k with |EL[alpha][m] - ER[beta][k]| < interval of
+//                             <psiR[beta][k] | Hdiff[:, :, beta, alpha] | psiL[alpha][m]>
+// (sign fixed to >= 0 before averaging when sign_fix, bardeen:141; nearest k when interval is NaN and the
+// window is empty, :146-151; 0 when nothing qualifies).  Hdiff is block tridiagonal in the site index:
+// hd0[p][S][n][n], hdU[p][S-1][n][n] = Hdiff[j, j+1], hdL[p][S-1][n][n] = Hdiff[j+1, j].
+__global__ void __launch_bounds__(128)
+bardeen_melem_kernel(const double* __restrict__ EL, const int* __restrict__ nL, const double* __restrict__ psiL,
+                     const double* __restrict__ ER, const int* __restrict__ nR, const double* __restrict__ psiR,
+                     const double* __restrict__ hd0, const double* __restrict__ hdU, const double* __restrict__ hdL,
+                     int n, int S, int max_states, double interval, int sign_fix, double* __restrict__ Mavg) {
+    extern __shared__ double y[];
+    __shared__ double s_red[4];
+    __shared__ int s_lohi[2];
+    const int m = blockIdx.x, alpha = blockIdx.y / n, beta = blockIdx.y % n, p = blockIdx.z;
+    const size_t chL = (size_t)p * n + alpha, chR = (size_t)p * n + beta;
+    double* out = Mavg + (((size_t)p * n + beta) * max_states + m) * n + alpha;
+    const int nl = min(nL[chL], max_states), nr = min(nR[chR], max_states);
+    if (m >= nl) {
+        if (threadIdx.x == 0) *out = 0.0;
+        return;
+    }
+    const double Em = EL[chL * max_states + m];
+    const double* Er = ER + chR * max_states;
+    // window (uniform over the CTA)
+    int cnt = 0, nearest = -1;
+    double dmin = DBL_MAX;
+    for (int k = 0; k < nr; ++k) {
+        const double dE = fabs(Em - Er[k]);
+        if (dE < interval) ++cnt;
+        if (dE < dmin) {
+            dmin = dE;
+            nearest = k;
+        }
+    }
+    const bool use_nearest = (cnt == 0) && isnan(interval) && nearest >= 0;
+    if (cnt == 0 && !use_nearest) {
+        if (threadIdx.x == 0) *out = 0.0;
+        return;
+    }
+    // y = Hdiff[beta, alpha] psi_m and its support
+    if (threadIdx.x == 0) {
+        s_lohi[0] = S;
+        s_lohi[1] = -1;
+    }
+    __syncthreads();
+    const double* psi = psiL + (chL * max_states + m) * S;
+    const size_t nn = (size_t)n * n, ba = (size_t)beta * n + alpha;
+    const double* h0 = hd0 + (size_t)p * S * nn + ba;
+    const double* hU = hdU + (size_t)p * (S - 1) * nn + ba;
+    const double* hL = hdL + (size_t)p * (S - 1) * nn + ba;
+    int my_lo = S, my_hi = -1;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        double v = h0[(size_t)j * nn] * psi[j];
+        if (j + 1 < S) v = fma(hU[(size_t)j * nn], psi[j + 1], v);
+        if (j > 0) v = fma(hL[(size_t)(j - 1) * nn], psi[j - 1], v);
+        y[j] = v;
+        if (v != 0.0) {
+            my_lo = min(my_lo, j);
+            my_hi = max(my_hi, j);
+        }
+    }
+    if (my_hi >= 0) {
+        atomicMin(&s_lohi[0], my_lo);
+        atomicMax(&s_lohi[1], my_hi);
+    }
+    __syncthreads();
+    const int j0 = s_lohi[0], j1 = s_lohi[1] + 1;
+    double sum = 0.0;
+    for (int k = 0; k < nr; ++k) {
+        const bool take = use_nearest ? (k == nearest) : (fabs(Em - Er[k]) < interval);
+        if (!take) continue;
+        const double* pr = psiR + (chR * max_states + k) * S;
+        double acc = 0.0;
+        for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) acc = fma(pr[j], y[j], acc);
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        double el = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        __syncthreads();
+        if (sign_fix && el < 0.0) el = -el;
+        sum += el;
+    }
+    if (threadIdx.x == 0) *out = sum / (double)(use_nearest ? 1 : cnt);
+}
+
+// Iab[p][alpha][beta][i] = 2 pi sum_m stat(E[p][alpha][m], Vb[i]) M2[p][alpha][m][beta]   (bardeen:537-575)
+// stat = fL (1 - fR) - fR (1 - fL), f = 1/(exp((eps - mu)/kBT) + 1), muL = muR + Vb.  One warp per output.
+__global__ void bardeen_current_kernel(const double* __restrict__ E, const double* __restrict__ M2, int P, int n, int nb,
+                                       const double* __restrict__ Vb, int nVb, double muR, double kBT,
+                                       double* __restrict__ I) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)P * n * n * nVb;
+    if (w >= total) return;
+    const int i = (int)(w % nVb);
+    const int beta = (int)((w / nVb) % n);
+    const int alpha = (int)((w / ((long long)nVb * n)) % n);
+    const int p = (int)(w / ((long long)nVb * n * n));
+    const double muL = muR + Vb[i];
+    const double* Ea = E + ((size_t)p * n + alpha) * nb;
+    const double* Ma = M2 + ((size_t)p * n + alpha) * nb * n + beta;
+    double acc = 0.0;
+    for (int m = lane; m < nb; m += 32) {
+        const double fL = 1.0 / (exp((Ea[m] - muL) / kBT) + 1.0);
+        const double fR = 1.0 / (exp((Ea[m] - muR) / kBT) + 1.0);
+        acc = fma(fL * (1.0 - fR) - fR * (1.0 - fL), Ma[(size_t)m * n], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) I[w] = 2.0 * 3.141592653589793 * acc;
+}
+
+// Tbmas[alpha][m][beta] = NL/(k tL[alpha]) NR/tR[beta] dos M2[alpha][m][beta]   (bardeen:577-632)
+// k = Re arccos((E - VL[alpha]) / (-2 tL[alpha])), dos = Re 1/sqrt(1 - ((E - VR[beta]) / (2 tR[beta]))^2) with
+// numpy's complex branches (the reference's Emas is complex): outside the band k = 0 or pi and dos = 0.
+// flag[0] counts wavenumbers outside the band (:611 raises on any, for tL > 0), flag[1] densities of states above
+// the band top (x > 1, :624 raises), flag[2 + alpha*n + beta] the in-band ones: below the band bottom the
+// reference's check (max of the imaginary parts, which are negative there) fires only if NO m is in band.
+__global__ void bardeen_ts_kernel(const double* __restrict__ E, const double* __restrict__ M2, int n, int nb,
+                                  const double* __restrict__ tL, const double* __restrict__ VL,
+                                  const double* __restrict__ tR, const double* __restrict__ VR, double NL, double NR,
+                                  double* __restrict__ T, int* __restrict__ flag) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * nb * n) return;
+    const int beta = idx % n, m = (idx / n) % nb, alpha = idx / (n * nb);
+    const double Em = E[alpha * nb + m];
+    const double ck = (Em - VL[alpha]) / (-2.0 * tL[alpha]);
+    double ka;
+    if (fabs(ck) <= 1.0) {
+        ka = acos(ck);
+    } else {
+        ka = ck > 0.0 ? 0.0 : 3.141592653589793;
+        atomicAdd(flag, 1);
+    }
+    const double x = (Em - VR[beta]) / (2.0 * tR[beta]);
+    const double arg = 1.0 - x * x;
+    double dos = 0.0;
+    if (arg >= 0.0) {
+        dos = 1.0 / sqrt(arg);
+        atomicAdd(flag + 2 + alpha * n + beta, 1);
+    } else if (x > 1.0) {
+        atomicAdd(flag + 1, 1);
+    }
+    T[idx] = NL / (ka * tL[alpha]) * NR / tR[beta] * dos * M2[idx];
+}
+
+struct DevMem {
+    char* p = nullptr;
+    ~DevMem() {
+        if (p) cudaFree(p);
+    }
+};
+
+int have_device() {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    return TX_OK;
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int launch_eig(const double* d, const double* e, int S, int n_mat, const double* cut_states, const int* n_states,
+               int max_states, double* evals, double* evecs, double* scratch, cudaStream_t st) {
+    const size_t smem = (size_t)3 * S * sizeof(double);
+    if (smem > 200 * 1024) return fail(TX_ERR_UNSUPPORTED, "chain length S=%d exceeds the shared-memory staged limit (8533)", S);
+    static bool attr_set = false;
+    if (!attr_set || smem > 48 * 1024) {
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((max_states + EIG_WARPS - 1) / EIG_WARPS, n_mat);
+    tridiag_eig_kernel<<<grid, EIG_WARPS * 32, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals, evecs, scratch);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    return TX_OK;
+}
+
+int launch_count(const double* d, const double* e, int S, int n_mat, const double* cut_states, const double* cut_count,
+                 int* n_states, int* n_below, cudaStream_t st) {
+    tridiag_count_kernel<<<(n_mat + 3) / 4, 128, 0, st>>>(d, e, S, n_mat, cut_states, cut_count, n_states, n_below);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    return TX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tx_tridiag_count_below_dev(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                               const double* cut_count, int* n_states, int* n_below, void* stream) {
+    if (!d || !e || !cut_states || !cut_count || !n_states || !n_below) return fail(TX_ERR_ARG, "null pointer argument");
+    if (S < 2 || n_mat < 1) return fail(TX_ERR_ARG, "bad sizes S=%d n_mat=%d", S, n_mat);
+    return launch_count(d, e, S, n_mat, cut_states, cut_count, n_states, n_below, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tx_tridiag_eigh_below_dev(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                              const int* n_states, int max_states, double* evals, double* evecs, double* scratch,
+                              void* stream) {
+    if (!d || !e || !cut_states || !n_states || !evals) return fail(TX_ERR_ARG, "null pointer argument");
+    if (evecs && !scratch) return fail(TX_ERR_ARG, "eigenvectors need a scratch buffer of the same size");
+    if (S < 2 || n_mat < 1 || max_states < 1) return fail(TX_ERR_ARG, "bad sizes S=%d n_mat=%d max_states=%d", S, n_mat, max_states);
+    return launch_eig(d, e, S, n_mat, cut_states, n_states, max_states, evals, evecs, scratch,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, const double* cut_states,
+                          const double* cut_count, int max_states, double* evals, double* evecs, int* n_states,
+                          int* n_below) {
+    if (!d || !e || !cut_states || !n_states) return fail(TX_ERR_ARG, "null pointer argument");
+    if (S < 2 || n_mat < 1 || max_states < 0) return fail(TX_ERR_ARG, "bad sizes S=%d n_mat=%d max_states=%d", S, n_mat, max_states);
+    if (max_states > 0 && !evals) return fail(TX_ERR_ARG, "null eigenvalue buffer");
+    if (int rc = have_device()) return rc;
+    if (!cut_count) cut_count = cut_states;
+    const size_t bd = align256((size_t)n_mat * S * 8), be = align256((size_t)n_mat * (S - 1) * 8), bc = align256((size_t)n_mat * 8);
+    const size_t bv = align256((size_t)n_mat * max_states * 8), bz = evecs ? align256((size_t)n_mat * max_states * S * 8) : 0;
+    DevMem mem;
+    TX_CUDA(cudaMalloc(&mem.p, bd + be + 4 * bc + bv + 2 * bz + 256));
+    char* q = mem.p;
+    double* dd = (double*)q;  q += bd;
+    double* de = (double*)q;  q += be;
+    double* dcs = (double*)q; q += bc;
+    double* dcc = (double*)q; q += bc;
+    int* dns = (int*)q;       q += bc;
+    int* dnb = (int*)q;       q += bc;
+    double* dv = (double*)q;  q += bv;
+    double* dz = evecs ? (double*)q : nullptr;  q += bz;
+    double* dscr = evecs ? (double*)q : nullptr;
+    TX_CUDA(cudaMemcpy(dd, d, (size_t)n_mat * S * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(de, e, (size_t)n_mat * (S - 1) * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dcs, cut_states, (size_t)n_mat * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dcc, cut_count, (size_t)n_mat * 8, cudaMemcpyHostToDevice));
+    if (int rc = launch_count(dd, de, S, n_mat, dcs, dcc, dns, dnb, nullptr)) return rc;
+    if (max_states > 0)
+        if (int rc = launch_eig(dd, de, S, n_mat, dcs, dns, max_states, dv, dz, dscr, nullptr)) return rc;
+    TX_CUDA(cudaMemcpy(n_states, dns, (size_t)n_mat * 4, cudaMemcpyDeviceToHost));
+    if (n_below) TX_CUDA(cudaMemcpy(n_below, dnb, (size_t)n_mat * 4, cudaMemcpyDeviceToHost));
+    if (max_states > 0) {
+        TX_CUDA(cudaMemcpy(evals, dv, (size_t)n_mat * max_states * 8, cudaMemcpyDeviceToHost));
+        if (evecs) TX_CUDA(cudaMemcpy(evecs, dz, (size_t)n_mat * max_states * S * 8, cudaMemcpyDeviceToHost));
+    }
+    return TX_OK;
+}
+
+long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states) {
+    // psiL, psiR, scratch (shared by both wells, used one after the other on the same stream)
+    return (long long)(3 * align256((size_t)P * n * max_states * S * 8) + 256);
+}
+
+int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
+                         const double* cutL, const double* cutR_states, const double* cutR_count,
+                         const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
+                         double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
+                         int* nR_below, double* Mavg, void* workspace, void* stream) {
+    if (!dL || !eL || !dR || !eR || !cutL || !cutR_states || !cutR_count || !hd0 || !hdU || !hdL || !EL || !nL || !ER ||
+        !nR_states || !nR_below || !Mavg || !workspace)
+        return fail(TX_ERR_ARG, "null pointer argument");
+    if (P < 1 || n < 1 || S < 2 || max_states < 1) return fail(TX_ERR_ARG, "bad sizes P=%d n=%d S=%d max_states=%d", P, n, S, max_states);
+    if ((size_t)S * 8 > 200 * 1024) return fail(TX_ERR_UNSUPPORTED, "chain length S=%d too long", S);
+    if ((long long)n * n > 65535 || P > 65535) return fail(TX_ERR_UNSUPPORTED, "grid too large (n=%d, P=%d)", n, P);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t bz = align256((size_t)P * n * max_states * S * 8);
+    double* psiL = (double*)workspace;
+    double* psiR = (double*)((char*)workspace + bz);
+    double* scr = (double*)((char*)workspace + 2 * bz);
+    const int n_mat = P * n;
+    if (int rc = launch_count(dL, eL, S, n_mat, cutL, cutL, nL, nR_below /* overwritten below */, st)) return rc;
+    if (int rc = launch_count(dR, eR, S, n_mat, cutR_states, cutR_count, nR_states, nR_below, st)) return rc;
+    if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, scr, st)) return rc;
+    if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, scr, st)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TX_CUDA(cudaFuncSetAttribute(bardeen_melem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(max_states, n * n, P);
+    bardeen_melem_kernel<<<grid, 128, (size_t)S * 8, st>>>(EL, nL, psiL, ER, nR_states, psiR, hd0, hdU, hdL, n, S, max_states,
+                                                          interval, sign_fix, Mavg);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    return TX_OK;
+}
+
+int tx_bardeen_wells(const double* dL, const double* eL, const double* dR, const double* eR, const double* cutL,
+                     const double* cutR_states, const double* cutR_count, const double* hd0, const double* hdU,
+                     const double* hdL, int P, int n, int S, int max_states, double interval, int sign_fix, double* EL,
+                     int* nL, double* ER, int* nR_states, int* nR_below, double* Mavg, double* psiL, double* psiR) {
+    if (!dL || !eL || !dR || !eR || !cutL || !cutR_states || !cutR_count || !hd0 || !hdU || !hdL || !nL || !nR_states ||
+        !nR_below)
+        return fail(TX_ERR_ARG, "null pointer argument");
+    if (P < 1 || n < 1 || S < 2 || max_states < 0) return fail(TX_ERR_ARG, "bad sizes P=%d n=%d S=%d max_states=%d", P, n, S, max_states);
+    if (max_states > 0 && (!EL || !ER || !Mavg)) return fail(TX_ERR_ARG, "null output buffer");
+    if (int rc = have_device()) return rc;
+    const int n_mat = P * n;
+    const size_t bd = align256((size_t)n_mat * S * 8), be = align256((size_t)n_mat * (S - 1) * 8), bc = align256((size_t)n_mat * 8);
+    const size_t nn = (size_t)n * n;
+    const size_t bh0 = align256((size_t)P * S * nn * 8), bh1 = align256((size_t)P * (S - 1) * nn * 8);
+    const int ms = max_states > 0 ? max_states : 1;
+    const size_t bv = align256((size_t)n_mat * ms * 8), bm = align256((size_t)n_mat * ms * n * 8);
+    const size_t bw = max_states > 0 ? (size_t)tx_bardeen_workspace_bytes(P, n, S, max_states) : 0;
+    DevMem mem;
+    TX_CUDA(cudaMalloc(&mem.p, 2 * bd + 2 * be + 6 * bc + bh0 + 2 * bh1 + 2 * bv + bm + bw + 256));
+    char* q = mem.p;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    double* ddL = (double*)take(bd); double* deL = (double*)take(be);
+    double* ddR = (double*)take(bd); double* deR = (double*)take(be);
+    double* dcL = (double*)take(bc); double* dcRs = (double*)take(bc); double* dcRc = (double*)take(bc);
+    int* dnL = (int*)take(bc); int* dnRs = (int*)take(bc); int* dnRb = (int*)take(bc);
+    double* dh0 = (double*)take(bh0); double* dhU = (double*)take(bh1); double* dhL = (double*)take(bh1);
+    double* dEL = (double*)take(bv); double* dER = (double*)take(bv); double* dM = (double*)take(bm);
+    char* ws = take(bw);
+    auto up = [&](void* dst, const void* src, size_t b) { return cudaMemcpy(dst, src, b, cudaMemcpyHostToDevice); };
+    TX_CUDA(up(ddL, dL, (size_t)n_mat * S * 8));
+    TX_CUDA(up(deL, eL, (size_t)n_mat * (S - 1) * 8));
+    TX_CUDA(up(ddR, dR, (size_t)n_mat * S * 8));
+    TX_CUDA(up(deR, eR, (size_t)n_mat * (S - 1) * 8));
+    TX_CUDA(up(dcL, cutL, (size_t)n_mat * 8));
+    TX_CUDA(up(dcRs, cutR_states, (size_t)n_mat * 8));
+    TX_CUDA(up(dcRc, cutR_count, (size_t)n_mat * 8));
+    TX_CUDA(up(dh0, hd0, (size_t)P * S * nn * 8));
+    TX_CUDA(up(dhU, hdU, (size_t)P * (S - 1) * nn * 8));
+    TX_CUDA(up(dhL, hdL, (size_t)P * (S - 1) * nn * 8));
+    if (max_states == 0) {
+        // counting pass only: the caller sizes its buffers from the counts and calls again
+        if (int rc = launch_count(ddL, deL, S, n_mat, dcL, dcL, dnL, dnRb, nullptr)) return rc;
+        if (int rc = launch_count(ddR, deR, S, n_mat, dcRs, dcRc, dnRs, dnRb, nullptr)) return rc;
+    } else {
+        if (int rc = tx_bardeen_wells_dev(ddL, deL, ddR, deR, dcL, dcRs, dcRc, dh0, dhU, dhL, P, n, S, max_states, interval,
+                                          sign_fix, dEL, dnL, dER, dnRs, dnRb, dM, ws, nullptr))
+            return rc;
+    }
+    auto down = [&](void* dst, const void* src, size_t b) { return cudaMemcpy(dst, src, b, cudaMemcpyDeviceToHost); };
+    TX_CUDA(down(nL, dnL, (size_t)n_mat * 4));
+    TX_CUDA(down(nR_states, dnRs, (size_t)n_mat * 4));
+    TX_CUDA(down(nR_below, dnRb, (size_t)n_mat * 4));
+    if (max_states > 0) {
+        TX_CUDA(down(EL, dEL, (size_t)n_mat * max_states * 8));
+        TX_CUDA(down(ER, dER, (size_t)n_mat * max_states * 8));
+        TX_CUDA(down(Mavg, dM, (size_t)n_mat * max_states * n * 8));
+        const size_t bz = align256((size_t)n_mat * max_states * S * 8);
+        if (psiL) TX_CUDA(down(psiL, ws, (size_t)n_mat * max_states * S * 8));
+        if (psiR) TX_CUDA(down(psiR, ws + bz, (size_t)n_mat * max_states * S * 8));
+    }
+    return TX_OK;
+}
+
+int tx_bardeen_current_dev(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,
+                           double kBT, double* I, void* stream) {
+    if (!E || !M2 || !Vb || !I) return fail(TX_ERR_ARG, "null pointer argument");
+    if (P < 1 || n < 1 || nb < 1 || nVb < 1) return fail(TX_ERR_ARG, "bad sizes P=%d n=%d nb=%d nVb=%d", P, n, nb, nVb);
+    const long long warps = (long long)P * n * n * nVb;
+    bardeen_current_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        E, M2, P, n, nb, Vb, nVb, muR, kBT, I);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    return TX_OK;
+}
+
+int tx_bardeen_current(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,
+                       double kBT, double* I) {
+    if (!E || !M2 || !Vb || !I) return fail(TX_ERR_ARG, "null pointer argument");
+    if (P < 1 || n < 1 || nb < 1 || nVb < 1) return fail(TX_ERR_ARG, "bad sizes P=%d n=%d nb=%d nVb=%d", P, n, nb, nVb);
+    if (int rc = have_device()) return rc;
+    const size_t bE = align256((size_t)P * n * nb * 8), bM = align256((size_t)P * n * nb * n * 8), bV = align256((size_t)nVb * 8);
+    const size_t bI = (size_t)P * n * n * nVb * 8;
+    DevMem mem;
+    TX_CUDA(cudaMalloc(&mem.p, bE + bM + bV + bI + 256));
+    double* dE = (double*)mem.p;
+    double* dM = (double*)(mem.p + bE);
+    double* dV = (double*)(mem.p + bE + bM);
+    double* dI = (double*)(mem.p + bE + bM + bV);
+    TX_CUDA(cudaMemcpy(dE, E, (size_t)P * n * nb * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dM, M2, (size_t)P * n * nb * n * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dV, Vb, (size_t)nVb * 8, cudaMemcpyHostToDevice));
+    if (int rc = tx_bardeen_current_dev(dE, dM, P, n, nb, dV, nVb, muR, kBT, dI, nullptr)) return rc;
+    TX_CUDA(cudaMemcpy(I, dI, bI, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double* tL, const double* VL, const double* tR,
+                  const double* VR, int NL, int NR, double* T, int* flags) {
+    if (!E || !M2 || !tL || !VL || !tR || !VR || !T || !flags) return fail(TX_ERR_ARG, "null pointer argument");
+    if (n < 1 || nb < 1) return fail(TX_ERR_ARG, "bad sizes n=%d nb=%d", n, nb);
+    if (int rc = have_device()) return rc;
+    const size_t bE = align256((size_t)n * nb * 8), bM = align256((size_t)n * nb * n * 8), bp = align256((size_t)n * 8);
+    DevMem mem;
+    TX_CUDA(cudaMalloc(&mem.p, bE + 2 * bM + 4 * bp + (size_t)(2 + n * n) * 4 + 256));
+    char* q = mem.p;
+    double* dE = (double*)q;  q += bE;
+    double* dM = (double*)q;  q += bM;
+    double* dT = (double*)q;  q += bM;
+    double* dp[4];
+    const double* hp[4] = {tL, VL, tR, VR};
+    for (int i = 0; i < 4; ++i) {
+        dp[i] = (double*)q;
+        q += bp;
+        TX_CUDA(cudaMemcpy(dp[i], hp[i], (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    int* dflag = (int*)q;
+    TX_CUDA(cudaMemset(dflag, 0, (size_t)(2 + n * n) * 4));
+    TX_CUDA(cudaMemcpy(dE, E, (size_t)n * nb * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dM, M2, (size_t)n * nb * n * 8, cudaMemcpyHostToDevice));
+    const int total = n * nb * n;
+    bardeen_ts_kernel<<<(total + 127) / 128, 128>>>(dE, dM, n, nb, dp[0], dp[1], dp[2], dp[3], (double)NL, (double)NR, dT, dflag);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    TX_CUDA(cudaMemcpy(T, dT, (size_t)total * 8, cudaMemcpyDeviceToHost));
+    TX_CUDA(cudaMemcpy(flags, dflag, (size_t)(2 + n * n) * 4, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+}  // extern "C"
