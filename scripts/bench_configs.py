@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Secondary measurements: BASELINE configs 1, 3 and 4 on one GPU (config 2 is bench.py's headline).
+"""Secondary measurements: BASELINE configs 1, 3, 4 and 5 on one GPU (config 2 is bench.py's headline).
 
-    python scripts/bench_configs.py [cfg1] [cfg3] [cfg4] [--small]
+    python scripts/bench_configs.py [cfg1] [cfg3] [cfg4] [cfg5] [--small]
 
 For each config: device-resident sweep timed with CUDA events (3 warm-ups, L2 flush between steps),
 parity of a subsample against the numpy oracle, roofline fraction (FP64), one JSON line each.
@@ -190,9 +190,108 @@ def cfg4(small=False):
             "kernel": "CTA-per-point generic kernel; DMMA block products, shared-memory staged Gauss-Jordan inverse"}
 
 
+def cfg5(small=False):
+    """rbstep.py-style sweep of the right-well step height (rbstep.py:43-104): P geometries in one device pass —
+    bound states of both wells, window-averaged matrix elements, current over the bias grid of rbbarrier.py:447-450."""
+    from oracle import bardeen_oracle as bo                      # checker + CPU baseline only
+    from transport_b200 import bardeen
+    out = []
+    one = np.eye(1)
+    for NLR in ((200,) if small else (200, 800)):
+        P = 64 if small else 256
+        VRs = np.linspace(-0.05, 0.05, P)
+        Vinf, VL = 0.5 * one, 0.0 * one
+        HC = np.zeros((11, 11, 1, 1), dtype=complex)
+        for j in range(11):
+            HC[j, j] = 0.4
+        for j in range(10):
+            HC[j, j + 1] = HC[j + 1, j] = -1.0
+        arrs = {k: [] for k in ("dL", "eL", "dR", "eR", "h0", "hU", "hL")}
+        t0 = time.time()
+        for v in VRs:
+            VR = v * one
+            bL = bardeen.hsys_site_blocks(one, one, one, Vinf, VL, Vinf, 20, NLR, NLR, HC)
+            bR = bardeen.hsys_site_blocks(one, one, one, Vinf, VR + Vinf, VR, 20, NLR, NLR, HC)
+            bS = bardeen.hsys_site_blocks(one, one, one, Vinf, VL, VR, 20, NLR, NLR, HC)
+            a, b = bardeen._channel_tridiagonals(bL); arrs["dL"].append(a); arrs["eL"].append(b)
+            a, b = bardeen._channel_tridiagonals(bR); arrs["dR"].append(a); arrs["eR"].append(b)
+            hd = [np.real(x - y) for x, y in zip(bS, bL)]
+            arrs["h0"].append(hd[0]); arrs["hU"].append(hd[1]); arrs["hL"].append(hd[2])
+        host_assembly_s = time.time() - t0
+        A = {k: np.ascontiguousarray(np.array(v), dtype=np.float64) for k, v in arrs.items()}
+        S = A["dL"].shape[-1]
+        interval = 1e-2
+        cut = np.full((P, 1), 0.1 - 2.0)
+        # e2e through the host entry (H2D + counts + second pass sized from the counts + D2H)
+        t0 = time.time()
+        r = bardeen.wells_batched(A["dL"], A["eL"], A["dR"], A["eR"], cut, cut + interval, cut, A["h0"], A["hU"], A["hL"],
+                                  interval, sign_fix=True)
+        e2e_first_s = time.time() - t0
+        t0 = time.time()
+        r = bardeen.wells_batched(A["dL"], A["eL"], A["dR"], A["eR"], cut, cut + interval, cut, A["h0"], A["hU"], A["hL"],
+                                  interval, sign_fix=True)
+        e2e_s = time.time() - t0
+        ms = int(max(r["nL"].max(), r["nR_states"].max()))
+        # device resident
+        D = {k: torch.from_numpy(v).to(dev) for k, v in A.items()}
+        dcut = torch.from_numpy(cut).to(dev); dcut2 = torch.from_numpy(cut + interval).to(dev)
+        EL = torch.zeros((P, 1, ms), dtype=torch.float64, device=dev); ER = torch.zeros_like(EL)
+        Mavg = torch.zeros((P, 1, ms, 1), dtype=torch.float64, device=dev)
+        nL = torch.zeros((P, 1), dtype=torch.int32, device=dev); nRs = torch.zeros_like(nL); nRb = torch.zeros_like(nL)
+        ws = torch.empty(int(lib.tx_bardeen_workspace_bytes(P, 1, S, ms)), dtype=torch.uint8, device=dev)
+        Vb = torch.linspace(-0.05, 0.05, 99, dtype=torch.float64, device=dev)
+        Iab = torch.zeros((P, 1, 1, 99), dtype=torch.float64, device=dev)
+        M2 = torch.zeros_like(Mavg)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def wells_step():
+            _lib.check(lib.tx_bardeen_wells_dev(D["dL"].data_ptr(), D["eL"].data_ptr(), D["dR"].data_ptr(), D["eR"].data_ptr(),
+                                                dcut.data_ptr(), dcut2.data_ptr(), dcut.data_ptr(), D["h0"].data_ptr(),
+                                                D["hU"].data_ptr(), D["hL"].data_ptr(), P, 1, S, ms, interval, 1,
+                                                EL.data_ptr(), nL.data_ptr(), ER.data_ptr(), nRs.data_ptr(), nRb.data_ptr(),
+                                                Mavg.data_ptr(), ws.data_ptr(), st))
+
+        def step():
+            wells_step()
+            torch.mul(Mavg, Mavg, out=M2)
+            _lib.check(lib.tx_bardeen_current_dev(EL.data_ptr(), M2.data_ptr(), P, 1, ms, Vb.data_ptr(), 99, -1.95, 0.01,
+                                                  Iab.data_ptr(), st))
+        ms_step = timed(step, steps=5, warmup=3)
+        ms_wells = timed(wells_step, steps=5, warmup=3)
+        assert np.array_equal(nL.cpu().numpy(), r["nL"]) and np.allclose(Mavg.cpu().numpy(), r["Mavg"], rtol=1e-12, atol=0)
+        # parity + CPU baseline: the oracle's kernel_well (dense LAPACK eigh x4, as the reference) on a few geometries
+        idx = [0, P // 2, P - 1] if NLR == 200 else [P // 3]
+        err, cpu_s = 0.0, 0.0
+        for p in idx:
+            VR = VRs[p] * one
+            t0 = time.time()
+            E0, M0 = bo.kernel_well(one, one, one, Vinf, VL, VR + Vinf, VR, Vinf, 20, NLR, NLR, HC, HC, one, 0.1 * one,
+                                    interval=interval)
+            cpu_s += time.time() - t0
+            mu, nu = int(r["nL"][p, 0]), int(r["nR_below"][p, 0])
+            M = r["Mavg"][p, 0, :mu, 0] ** 2
+            M[nu:] = 0.0
+            big = M0[0, :, 0] > 1e-30
+            err = max(err, float(np.max(np.abs(r["EL"][p, 0, :mu] - E0[0].real))),
+                      float(np.max(np.abs(M[big] - M0[0, big, 0]) / M0[0, big, 0])) if big.any() else 0.0)
+        states = int(r["nL"].sum() + r["nR_states"].sum())
+        out.append({"config": "cfg5 bardeen rbstep sweep: %d step heights, N_L=N_R=%d (S=%d), interval 1e-2, 99 bias points" % (P, NLR, S),
+                    "geometries": P, "S": S, "bound_states_total": states, "max_states": ms,
+                    "ms_per_sweep_device_resident": ms_step, "ms_wells_only": ms_wells,
+                    "geometries_per_s": P / (ms_step * 1e-3),
+                    "e2e_host_call_s": e2e_s, "e2e_first_call_s": e2e_first_s, "e2e_geometries_per_s": P / e2e_s,
+                    "host_assembly_s": host_assembly_s,
+                    "cpu_oracle_dense_eigh_s_per_geometry_1core": cpu_s / len(idx),
+                    "speedup_device_resident_vs_1core": (cpu_s / len(idx)) / (ms_step * 1e-3 / P),
+                    "parity_max_err_vs_oracle(E abs, |M|^2 rel)": err, "checked_geometries": len(idx),
+                    "kernel": "Sturm multisection (warp per eigenvalue) + twisted factorisation + windowed dot products"})
+    return out
+
+
 if __name__ == "__main__":
     small = "--small" in sys.argv
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3", "cfg4"]
     for w in which:
-        out = {"cfg1": cfg1, "cfg3": lambda: cfg3(small), "cfg4": lambda: cfg4(small)}[w]()
-        print(json.dumps(out), flush=True)
+        out = {"cfg1": cfg1, "cfg3": lambda: cfg3(small), "cfg4": lambda: cfg4(small), "cfg5": lambda: cfg5(small)}[w]()
+        for line in (out if isinstance(out, list) else [out]):
+            print(json.dumps(line), flush=True)
