@@ -256,7 +256,12 @@ def cfg5(small=False):
             torch.mul(Mavg, Mavg, out=M2)
             _lib.check(lib.tx_bardeen_current_dev(EL.data_ptr(), M2.data_ptr(), P, 1, ms, Vb.data_ptr(), 99, -1.95, 0.01,
                                                   Iab.data_ptr(), st))
+        def eigenvalues_only_step():
+            for dd, ee, cc, nn, EE in ((D["dL"], D["eL"], dcut, nL, EL), (D["dR"], D["eR"], dcut2, nRs, ER)):
+                _lib.check(lib.tx_tridiag_eigh_below_dev(dd.data_ptr(), ee.data_ptr(), S, P, cc.data_ptr(), nn.data_ptr(), ms,
+                                                         EE.data_ptr(), None, None, st))
         ms_step = timed(step, steps=5, warmup=3)
+        ms_evals = timed(eigenvalues_only_step, steps=5, warmup=2)
         ms_wells = timed(wells_step, steps=5, warmup=3)
         assert np.array_equal(nL.cpu().numpy(), r["nL"]) and np.allclose(Mavg.cpu().numpy(), r["Mavg"], rtol=1e-12, atol=0)
         # parity + CPU baseline: the oracle's kernel_well (dense LAPACK eigh x4, as the reference) on a few geometries
@@ -277,7 +282,7 @@ def cfg5(small=False):
         states = int(r["nL"].sum() + r["nR_states"].sum())
         out.append({"config": "cfg5 bardeen rbstep sweep: %d step heights, N_L=N_R=%d (S=%d), interval 1e-2, 99 bias points" % (P, NLR, S),
                     "geometries": P, "S": S, "bound_states_total": states, "max_states": ms,
-                    "ms_per_sweep_device_resident": ms_step, "ms_wells_only": ms_wells,
+                    "ms_per_sweep_device_resident": ms_step, "ms_wells_only": ms_wells, "ms_eigenvalues_only": ms_evals,
                     "geometries_per_s": P / (ms_step * 1e-3),
                     "e2e_host_call_s": e2e_s, "e2e_first_call_s": e2e_first_s, "e2e_geometries_per_s": P / e2e_s,
                     "host_assembly_s": host_assembly_s,

@@ -42,27 +42,50 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def _headers_hash():
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cuh", ".h")):
+                with open(os.path.join(root, name), "rb") as f:
+                    h.update(name.encode())
+                    h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library; returns its path."""
+    """Compile every CUDA source into one shared library; returns its path.  A translation unit is recompiled
+    when it, any header, or the flags changed (per-object stamps under lib/)."""
     os.makedirs(LIBDIR, exist_ok=True)
     fp = _fingerprint()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as f:
             if f.read().strip() == fp:
                 return LIB
+    hh = _headers_hash()
     objs = []
     procs = []
     for src in _sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
-    for cmd, pr in procs:
+        with open(src, "rb") as f:
+            want = hashlib.sha256(hh.encode() + f.read()).hexdigest()
+        ostamp = obj + ".stamp"
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(ostamp):
+            with open(ostamp) as f:
+                if f.read().strip() == want:
+                    continue
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((cmd, ostamp, want, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, ostamp, want, pr in procs:
         out, _ = pr.communicate()
         if verbose or pr.returncode:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        with open(ostamp, "w") as f:
+            f.write(want)
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.check_call(cmd)
     with open(STAMP, "w") as f:

@@ -27,18 +27,57 @@ namespace {
 
 constexpr int EIG_WARPS = 4;
 
-// number of eigenvalues < x (negative pivots of T - x), d and e2 = e*e in shared memory
-__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int S, double x,
-                                           double pivmin) {
-    double q = d[0] - x;
-    if (fabs(q) < pivmin) q = -pivmin;
-    int cnt = q < 0.0;
-    for (int i = 1; i < S; ++i) {
-        q = (d[i] - x) - e2[i - 1] / q;
-        if (fabs(q) < pivmin) q = -pivmin;
-        cnt += q < 0.0;
+// Number of eigenvalues < x = number of sign changes in the sequence of leading principal minors of T - x,
+//     p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2},      p_{-1} = 1,
+// evaluated without divisions: one dependent DFMA per site (the pivot form q_i = p_i / p_{i-1} costs a dependent
+// FP64 division, ~10x the pipe time).  de(i) returns (d_i, e_{i-1}^2) of the matrix scaled by an exact power of two
+// that brings its Gershgorin norm below 1 (xs is scaled alike), so |p| grows by less than 3 per site; every 8 sites
+// the pair (p_{i-1}, p_i) is renormalised by the exponent of its larger entry (an exact scaling that keeps every
+// sign).  Signs are shifted into a bit history (one SHF per site) and the changes counted with one POPC per 8 sites.
+// A zero minor inside the sequence contributes exactly one change together with its successor (p_{i+1} = -e^2
+// p_{i-1}), as Sturm's rule demands; a zero LAST minor (x is an eigenvalue) counts as a change: "< x" becomes "<= x"
+// on that set of measure zero, the same convention as the -pivmin rule of the pivot form.
+template <typename FDE>
+__device__ __forceinline__ int sturm_count(int S, double xs, FDE de) {
+    double p0 = 1.0;
+    double p1 = de(0).x - xs;
+    if (p1 == 0.0) p1 = -0x1p-100;
+    int cnt = p1 < 0.0;
+    unsigned sgn = (unsigned)__double2hiint(p1) >> 31;          // bit 0 = sign of the newest minor
+    int i = 1;
+    for (; i + 8 <= S; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = de(i + j);
+            const double u = v.y * p0;
+            p0 = p1;
+            p1 = fma(v.x - xs, p1, -u);
+            sgn = __funnelshift_l((unsigned)__double2hiint(p1), sgn, 1);
+        }
+        cnt += __popc((sgn ^ (sgn >> 1)) & 0xffu);
+        const int h = max(__double2hiint(p0) & 0x7ff00000, __double2hiint(p1) & 0x7ff00000);
+        const double sc = __hiloint2double(0x7fe00000 - h, 0);  // 2^(1023 - exponent)
+        p0 *= sc;
+        p1 *= sc;
     }
+    for (; i < S; ++i) {
+        const double2 v = de(i);
+        const double u = v.y * p0;
+        p0 = p1;
+        p1 = fma(v.x - xs, p1, -u);
+        sgn = __funnelshift_l((unsigned)__double2hiint(p1), sgn, 1);
+        cnt += (sgn ^ (sgn >> 1)) & 1u;
+    }
+    if (p1 == 0.0 && S > 1) cnt += !(((sgn >> 1) ^ sgn) & 1u);  // zero last minor: count it as a change (once)
     return cnt;
+}
+
+// exact power of two s with s * tnorm in [0.5, 1)  (1 for a zero matrix)
+__device__ __forceinline__ double pow2_scale(double tnorm) {
+    if (!(tnorm > 0.0) || !isfinite(tnorm)) return 1.0;
+    int ex;
+    frexp(tnorm, &ex);
+    return ldexp(1.0, -ex);
 }
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -57,8 +96,8 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// counts[mat][0] = #eig < cut_states[mat], counts[mat][1] = #eig < cut_count[mat].  One warp per matrix,
-// lanes 0/1 take the two shifts (global-memory reads: this kernel is a few microseconds).
+// n_states[mat] = #eig < cut_states[mat], n_below[mat] = #eig < cut_count[mat].  One warp per matrix, lanes 0/1
+// take the two shifts (global-memory reads: this kernel is a few microseconds).
 __global__ void tridiag_count_kernel(const double* __restrict__ d, const double* __restrict__ e, int S, int n_mat,
                                      const double* __restrict__ cut_states, const double* __restrict__ cut_count,
                                      int* __restrict__ n_states, int* __restrict__ n_below) {
@@ -67,36 +106,34 @@ __global__ void tridiag_count_kernel(const double* __restrict__ d, const double*
     if (mat >= n_mat) return;
     const double* dm = d + (size_t)mat * S;
     const double* em = e + (size_t)mat * (S - 1);
-    double emax = 0.0;
-    for (int i = lane; i < S - 1; i += 32) emax = fmax(emax, em[i] * em[i]);
-    emax = warp_max(emax);
-    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    double tnorm = 0.0;
+    for (int i = lane; i < S; i += 32) {
+        const double r = (i ? fabs(em[i - 1]) : 0.0) + (i < S - 1 ? fabs(em[i]) : 0.0);
+        tnorm = fmax(tnorm, fabs(dm[i]) + r);
+    }
+    tnorm = warp_max(tnorm);
+    const double sc = pow2_scale(tnorm);
     if (lane < 2) {
-        const double x = lane == 0 ? cut_states[mat] : cut_count[mat];
-        double q = dm[0] - x;
-        if (fabs(q) < pivmin) q = -pivmin;
-        int cnt = q < 0.0;
-        for (int i = 1; i < S; ++i) {
-            const double ee = em[i - 1];
-            q = (dm[i] - x) - ee * ee / q;
-            if (fabs(q) < pivmin) q = -pivmin;
-            cnt += q < 0.0;
-        }
+        double x = lane == 0 ? cut_states[mat] : cut_count[mat];
+        x = fmin(fmax(x, -4.0 * tnorm), 4.0 * tnorm);            // +-inf cutoffs: all / none
+        const int cnt = sturm_count(S, x * sc, [&](int i) {
+            const double es = i ? em[i - 1] * sc : 0.0;
+            return make_double2(dm[i] * sc, es * es);
+        });
         if (lane == 0) n_states[mat] = cnt;
         else n_below[mat] = cnt;
     }
 }
 
 // One warp per (matrix, k): eigenvalue k (ascending) and its eigenvector.  grid = (ceil(max_states /
-// EIG_WARPS), n_mat).  Dynamic shared memory: d[S], e[S] (offdiagonal), e2[S].
+// EIG_WARPS), n_mat).  Dynamic shared memory: (d, e^2)[S] interleaved, e[S].
 __global__ void __launch_bounds__(EIG_WARPS * 32)
 tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
                    const double* __restrict__ cut_states, const int* __restrict__ n_states, int max_states,
                    double* __restrict__ evals, double* __restrict__ evecs, double* __restrict__ scratch) {
-    extern __shared__ double sm[];
-    double* d = sm;
-    double* e = sm + S;
-    double* e2 = sm + 2 * S;
+    extern __shared__ double2 sm2[];
+    double2* de = sm2;                                  // (d_i, e_{i-1}^2), scaled
+    double* e = reinterpret_cast<double*>(sm2 + S);     // e_i, scaled
     const int mat = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * EIG_WARPS + warp;
@@ -104,34 +141,40 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
     if (nb > max_states) nb = max_states;
     if (blockIdx.x * EIG_WARPS >= nb) return;                   // whole CTA idle
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        d[i] = d_g[(size_t)mat * S + i];
-        const double ee = i < S - 1 ? e_g[(size_t)mat * (S - 1) + i] : 0.0;
-        e[i] = ee;
-        e2[i] = ee * ee;
+        de[i].x = d_g[(size_t)mat * S + i];
+        e[i] = i < S - 1 ? e_g[(size_t)mat * (S - 1) + i] : 0.0;
     }
     __syncthreads();
-    if (k >= nb) return;
-
-    // Gershgorin bounds and pivmin
-    double glo = DBL_MAX, ghi = -DBL_MAX, emax = 0.0;
+    // Gershgorin bounds (every warp computes the same numbers), then the matrix is rescaled in place by the exact
+    // power of two that brings its norm below 1: eigenvectors are unchanged, eigenvalues scale exactly
+    double glo = DBL_MAX, ghi = -DBL_MAX;
     for (int i = lane; i < S; i += 32) {
         const double r = (i ? fabs(e[i - 1]) : 0.0) + fabs(e[i]);
-        glo = fmin(glo, d[i] - r);
-        ghi = fmax(ghi, d[i] + r);
-        emax = fmax(emax, e2[i]);
+        glo = fmin(glo, de[i].x - r);
+        ghi = fmax(ghi, de[i].x + r);
     }
     glo = warp_min(glo);
     ghi = warp_max(ghi);
-    emax = warp_max(emax);
-    const double pivmin = DBL_MIN * fmax(1.0, emax);
-    const double tnorm = fmax(fabs(glo), fabs(ghi));
-    glo -= 2.0 * DBL_EPSILON * tnorm * S + 2.0 * pivmin;
+    const double sc = pow2_scale(fmax(fabs(glo), fabs(ghi)));
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const double es = e[i] * sc;
+        e[i] = es;
+        de[i].x *= sc;
+        if (i + 1 < S) de[i + 1].y = es * es;
+        if (i == 0) de[0].y = 0.0;
+    }
+    __syncthreads();
+    if (k >= nb) return;
+    const double pivmin = DBL_MIN * 4.0;
+    const double tnorm = fmax(fabs(glo), fabs(ghi)) * sc;        // in [0.5, 1)
+    glo = glo * sc - 2.0 * DBL_EPSILON * S - 2.0 * pivmin;
 
-    // ---- multisection: count(lo) <= k < count(hi)
-    double lo = glo, hi = cut_states[mat];
+    // ---- multisection (scaled units): count(lo) <= k < count(hi)
+    double lo = glo, hi = fmin(fmax(cut_states[mat], -4.0 * tnorm / sc), 4.0 * tnorm / sc) * sc;
     for (int pass = 0; pass < 40; ++pass) {
         const double x = lo + (hi - lo) * ((lane + 1) * (1.0 / 33.0));
-        const int c = sturm_count(d, e2, S, x, pivmin);
+        const int c = sturm_count(S, x, [&](int i) { return de[i]; });
         const unsigned above = __ballot_sync(0xffffffffu, c > k);
         double nlo = lo, nhi = hi;
         if (above == 0u) {
@@ -147,7 +190,7 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         if (hi - lo <= DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin) break;
     }
     const double lam = 0.5 * (lo + hi);
-    if (lane == 0) evals[(size_t)mat * max_states + k] = lam;
+    if (lane == 0) evals[(size_t)mat * max_states + k] = lam / sc;
     if (evecs == nullptr) return;
 
     // ---- twisted factorisation: lane 0 runs the forward pivots D+, lane 1 the backward pivots D-
@@ -158,13 +201,13 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         double* out = fwd ? z : dm;
         int idx = fwd ? 0 : S - 1;
         const int step = fwd ? 1 : -1;
-        double q = d[idx] - lam;
+        double q = de[idx].x - lam;
         if (fabs(q) < pivmin) q = -pivmin;
         out[idx] = q;
         for (int i = 1; i < S; ++i) {
-            const double ee = e2[fwd ? idx : idx - 1];
+            const double ee = de[fwd ? idx + 1 : idx].y;      // e_{idx}^2 (forward) / e_{idx-1}^2 (backward)
             idx += step;
-            q = (d[idx] - lam) - ee / q;
+            q = (de[idx].x - lam) - ee / q;
             if (fabs(q) < pivmin) q = -pivmin;
             out[idx] = q;
         }
@@ -174,7 +217,7 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
     double best = DBL_MAX;
     int r = 0;
     for (int i = lane; i < S; i += 32) {
-        const double g = fabs(z[i] + dm[i] - (d[i] - lam));
+        const double g = fabs(z[i] + dm[i] - (de[i].x - lam));
         if (g < best) {
             best = g;
             r = i;
@@ -209,8 +252,8 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
     double nrm = 0.0;
     for (int i = lane; i < S; i += 32) nrm = fma(z[i], z[i], nrm);
     nrm = warp_sum(nrm);
-    const double sc = 1.0 / sqrt(nrm);
-    for (int i = lane; i < S; i += 32) z[i] *= sc;
+    const double zs = 1.0 / sqrt(nrm);
+    for (int i = lane; i < S; i += 32) z[i] *= zs;
 }
 
 // Window-averaged Oppenheimer matrix elements.  grid = (max_states, n*n, P): CTA (m, alpha*n+beta, p).
