@@ -72,33 +72,48 @@ def eigvals_below(d, e, cutoff, lanes=32, max_pass=40):
     return out
 
 
+def _pivots_from_minors(ds, e2s_next, lam, pivmin):
+    """pivots D_i = p_i / p_{i-1} of the LDL^T factorisation of T - lam along one direction, from the division-free
+    minor recurrence (pair renormalised every 8 sites); e2s_next[i] couples site i to site i+1 of this direction."""
+    S = len(ds)
+    D = np.empty(S)
+    p0, p1 = 1.0, ds[0] - lam
+    if abs(p1) < pivmin:
+        p1 = -pivmin
+    D[0] = p1
+    for i in range(1, S):
+        pn = (ds[i] - lam) * p1 - e2s_next[i - 1] * p0
+        if pn == 0.0:
+            pn = -p1 * 2.0 ** -100
+        q = pn / p1
+        if not abs(q) >= pivmin:
+            q = -pivmin
+        D[i] = q
+        p0, p1 = p1, pn
+        if i % 8 == 0:
+            ex = max(np.frexp(p0)[1], np.frexp(p1)[1])
+            p0, p1 = np.ldexp(p0, -ex), np.ldexp(p1, -ex)
+    return D
+
+
 def twisted_vector(d, e, lam):
+    """eigenvector of eigenvalue lam by the twisted factorisation, on the power-of-two scaled matrix"""
+    d = np.asarray(d, dtype=float); e = np.asarray(e, dtype=float)
     S = len(d)
-    e2 = e * e
-    pivmin = np.finfo(float).tiny * max(1.0, e2.max() if len(e2) else 1.0)
-    Dp = np.empty(S); Dm = np.empty(S)
-    q = d[0] - lam
-    for i in range(S):
-        if i:
-            q = (d[i] - lam) - e2[i - 1] / q
-        if abs(q) < pivmin:
-            q = -pivmin
-        Dp[i] = q
-    q = d[S - 1] - lam
-    for i in range(S - 1, -1, -1):
-        if i < S - 1:
-            q = (d[i] - lam) - e2[i] / q
-        if abs(q) < pivmin:
-            q = -pivmin
-        Dm[i] = q
-    gamma = Dp + Dm - (d - lam)
+    sc, _ = pow2_scale(d, e)
+    ds, es, lam = d * sc, e * sc, lam * sc
+    e2s = es * es
+    pivmin = 4 * np.finfo(float).tiny
+    Dp = _pivots_from_minors(ds, e2s, lam, pivmin)
+    Dm = _pivots_from_minors(ds[::-1], e2s[::-1], lam, pivmin)[::-1]
+    gamma = Dp + Dm - (ds - lam)
     r = int(np.argmin(np.abs(gamma)))
     z = np.zeros(S)
     z[r] = 1.0
     for i in range(r - 1, -1, -1):
-        z[i] = -(e[i] / Dp[i]) * z[i + 1]
+        z[i] = -(es[i] / Dp[i]) * z[i + 1]
     for i in range(r, S - 1):
-        z[i + 1] = -(e[i] / Dm[i + 1]) * z[i]
+        z[i + 1] = -(es[i] / Dm[i + 1]) * z[i]
     return z / np.sqrt(np.dot(z, z))
 
 

@@ -193,7 +193,8 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
     if (lane == 0) evals[(size_t)mat * max_states + k] = lam / sc;
     if (evecs == nullptr) return;
 
-    // ---- twisted factorisation: lane 0 runs the forward pivots D+, lane 1 the backward pivots D-
+    // ---- twisted factorisation.  Pivots D+_i = p_i / p_{i-1} of the forward (lane 0) and D-_i of the backward
+    // (lane 1) factorisation from the same division-free minor recurrence: the division is off the dependent chain.
     double* z = evecs + ((size_t)mat * max_states + k) * S;      // D+ first, overwritten by the vector
     double* dm = scratch + ((size_t)mat * max_states + k) * S;   // D-
     if (lane < 2) {
@@ -201,15 +202,26 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         double* out = fwd ? z : dm;
         int idx = fwd ? 0 : S - 1;
         const int step = fwd ? 1 : -1;
-        double q = de[idx].x - lam;
-        if (fabs(q) < pivmin) q = -pivmin;
-        out[idx] = q;
+        double p0 = 1.0;
+        double p1 = de[idx].x - lam;
+        if (fabs(p1) < pivmin) p1 = -pivmin;
+        out[idx] = p1;
         for (int i = 1; i < S; ++i) {
-            const double ee = de[fwd ? idx + 1 : idx].y;      // e_{idx}^2 (forward) / e_{idx-1}^2 (backward)
+            const double ee = de[fwd ? idx + 1 : idx].y;         // e_{idx}^2 (forward) / e_{idx-1}^2 (backward)
             idx += step;
-            q = (de[idx].x - lam) - ee / q;
-            if (fabs(q) < pivmin) q = -pivmin;
+            double pn = fma(de[idx].x - lam, p1, -(ee * p0));
+            if (pn == 0.0) pn = -p1 * 0x1p-100;
+            double q = pn / p1;
+            if (!(fabs(q) >= pivmin)) q = -pivmin;
             out[idx] = q;
+            p0 = p1;
+            p1 = pn;
+            if ((i & 7) == 0) {
+                const int h = max(__double2hiint(p0) & 0x7ff00000, __double2hiint(p1) & 0x7ff00000);
+                const double rs = __hiloint2double(0x7fe00000 - h, 0);
+                p0 *= rs;
+                p1 *= rs;
+            }
         }
     }
     __syncwarp();
@@ -233,21 +245,33 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         }
     }
     __syncwarp();
-    // z_r = 1; downwards z_i = -(e_i / D+_i) z_{i+1} (lane 0), upwards z_{i+1} = -(e_i / D-_{i+1}) z_i (lane 1)
-    if (lane == 0) {
-        double v = 1.0;
-        z[r] = 1.0;
-        for (int i = r - 1; i >= 0; --i) {
-            v = -(e[i] / z[i]) * v;
-            z[i] = v;
+    // z_r = 1; downwards z_i = rho_i z_{i+1}, rho_i = -e_i / D+_i; upwards z_{i+1} = rho_i z_i, rho_i = -e_i / D-_{i+1}.
+    // Each chain is a running product: every lane multiplies through a contiguous piece, a warp scan of the piece
+    // totals gives each piece its starting value (these are eigenvector components themselves, so they are O(1) or
+    // decaying), and a second pass writes the components.
+    auto chain = [&](int L, auto rho, auto store) {
+        const int per = (L + 31) >> 5;
+        const int j0 = min(L, lane * per), j1 = min(L, j0 + per);
+        double t = 1.0;
+        for (int j = j0; j < j1; ++j) t *= rho(j);
+        double inc = t;                                          // inclusive scan of the piece totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc *= o;
         }
-    } else if (lane == 1) {
-        double v = 1.0;
-        for (int i = r; i < S - 1; ++i) {
-            v = -(e[i] / dm[i + 1]) * v;
-            z[i + 1] = v;
+        double v = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) v = 1.0;
+        for (int j = j0; j < j1; ++j) {
+            v *= rho(j);
+            store(j, v);
         }
-    }
+    };
+    chain(r, [&](int j) { const int i = r - 1 - j; return -(e[i] / z[i]); },
+          [&](int j, double v) { z[r - 1 - j] = v; });
+    chain(S - 1 - r, [&](int j) { const int i = r + j; return -(e[i] / dm[i + 1]); },
+          [&](int j, double v) { z[r + 1 + j] = v; });
+    if (lane == 0) z[r] = 1.0;
     __syncwarp();
     double nrm = 0.0;
     for (int i = lane; i < S; i += 32) nrm = fma(z[i], z[i], nrm);
