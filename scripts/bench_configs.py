@@ -197,7 +197,12 @@ def cfg5(small=False):
     from transport_b200 import bardeen
     out = []
     one = np.eye(1)
-    for NLR in ((200,) if small else (200, 800)):
+    sizes = (200,) if small else (200, 800)
+    if os.environ.get("TX_CFG5_NLR"):
+        sizes = (int(os.environ["TX_CFG5_NLR"]),)
+    if os.environ.get("TX_EIG_MODE"):
+        _lib.check(lib.tx_set_option(3, int(os.environ["TX_EIG_MODE"])))
+    for NLR in sizes:
         P = 64 if small else 256
         VRs = np.linspace(-0.05, 0.05, P)
         Vinf, VL = 0.5 * one, 0.0 * one

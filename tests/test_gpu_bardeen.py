@@ -102,8 +102,16 @@ def _eigh_below(d, e, cut, max_states=None, vectors=True):
     return ns, ev, vec
 
 
+@pytest.fixture(params=[1, 2], ids=["warp_per_state", "lane_per_state"])
+def eig_mode(request):
+    """both tridiagonal eigen-solver organisations (tx_set_option(3, mode)); the default picks by batch size"""
+    check(_lib.load().tx_set_option(3, request.param))
+    yield request.param
+    check(_lib.load().tx_set_option(3, 0))
+
+
 @pytest.mark.parametrize("S", [2, 3, 33, 257, 1651])
-def test_tridiag_eigh_random(S):
+def test_tridiag_eigh_random(S, eig_mode):
     """seeded random tridiagonals, batch of 5 with different cutoffs, against LAPACK"""
     rng = np.random.default_rng(S)
     d = rng.normal(size=(5, S)); e = rng.normal(size=(5, S - 1))
@@ -126,7 +134,7 @@ def test_tridiag_eigh_random(S):
     assert ns[3] == S and ns[4] == 0
 
 
-def test_tridiag_truncation_and_restatement():
+def test_tridiag_truncation_and_restatement(eig_mode):
     """max_states smaller than the count reports the true count; the numpy restatement of the device
     algorithm (oracle/tridiag_oracle.py) gives the same numbers"""
     rng = np.random.default_rng(7)
@@ -139,7 +147,7 @@ def test_tridiag_truncation_and_restatement():
     assert np.max(np.abs(np.abs(vec[0]) - np.abs(Z[:4]))) < 1e-12
 
 
-def test_tail_relative_accuracy():
+def test_tail_relative_accuracy(eig_mode):
     """the eigenvector tails under the barrier (amplitude 1e-12 and below) agree with the numpy restatement in
     RELATIVE terms — what the matrix elements need and what dense LAPACK cannot deliver"""
     g = load_golden("bardeen_barrier_N200.npz")
@@ -155,7 +163,7 @@ def test_tail_relative_accuracy():
     assert np.max(np.abs(a - b) / b) < 1e-9
 
 
-def test_seeded_wells_against_oracle():
+def test_seeded_wells_against_oracle(eig_mode):
     """asymmetric two-channel wells with a spin-flip centre, random potentials: device vs LAPACK oracle"""
     rng = np.random.default_rng(11)
     n = 2
@@ -188,7 +196,7 @@ def test_seeded_wells_against_oracle():
                         assert abs(M1[be, m, al] - M0[be, m, al]) <= MTOL * M0[be, m, al] + 1e-300
 
 
-def test_batched_step_sweep_against_oracle():
+def test_batched_step_sweep_against_oracle(eig_mode):
     """rbstep-style sweep of the right-well step height, all geometries in ONE device call"""
     g = load_golden("bardeen_step_m05.npz")
     VRs = np.array([-0.05, -0.02, -0.005, 0.01, 0.05])

@@ -130,7 +130,7 @@ __global__ void tridiag_count_kernel(const double* __restrict__ d, const double*
 __global__ void __launch_bounds__(EIG_WARPS * 32)
 tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
                    const double* __restrict__ cut_states, const int* __restrict__ n_states, int max_states,
-                   double* __restrict__ evals, double* __restrict__ evecs, double* __restrict__ scratch) {
+                   double* __restrict__ evals) {
     extern __shared__ double2 sm2[];
     double2* de = sm2;                                  // (d_i, e_{i-1}^2), scaled
     double* e = reinterpret_cast<double*>(sm2 + S);     // e_i, scaled
@@ -191,39 +191,189 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
     }
     const double lam = 0.5 * (lo + hi);
     if (lane == 0) evals[(size_t)mat * max_states + k] = lam / sc;
-    if (evecs == nullptr) return;
+}
 
-    // ---- twisted factorisation.  Pivots D+_i = p_i / p_{i-1} of the forward (lane 0) and D-_i of the backward
-    // (lane 1) factorisation from the same division-free minor recurrence: the division is off the dependent chain.
-    double* z = evecs + ((size_t)mat * max_states + k) * S;      // D+ first, overwritten by the vector
-    double* dm = scratch + ((size_t)mat * max_states + k) * S;   // D-
-    if (lane < 2) {
-        const bool fwd = lane == 0;
-        double* out = fwd ? z : dm;
-        int idx = fwd ? 0 : S - 1;
-        const int step = fwd ? 1 : -1;
-        double p0 = 1.0;
-        double p1 = de[idx].x - lam;
-        if (fabs(p1) < pivmin) p1 = -pivmin;
-        out[idx] = p1;
-        for (int i = 1; i < S; ++i) {
-            const double ee = de[fwd ? idx + 1 : idx].y;         // e_{idx}^2 (forward) / e_{idx-1}^2 (backward)
-            idx += step;
-            double pn = fma(de[idx].x - lam, p1, -(ee * p0));
-            if (pn == 0.0) pn = -p1 * 0x1p-100;
-            double q = pn / p1;
-            if (!(fabs(q) >= pivmin)) q = -pivmin;
-            out[idx] = q;
-            p0 = p1;
-            p1 = pn;
-            if ((i & 7) == 0) {
-                const int h = max(__double2hiint(p0) & 0x7ff00000, __double2hiint(p1) & 0x7ff00000);
-                const double rs = __hiloint2double(0x7fe00000 - h, 0);
-                p0 *= rs;
-                p1 *= rs;
-            }
+// ---- lane-per-state path (large batches) -------------------------------------------------------------------
+// With thousands of states in flight a warp per state wastes the machine: multisection spends 32 Sturm counts per
+// 5 bits.  Here every LANE owns one eigenvalue of the CTA's matrix and bisects it alone (1 bit per count, 6x fewer
+// FP64 operations per eigenvalue and 32 eigenvalues per instruction); all lanes read the same (d_i, e_i^2) word of
+// shared memory (broadcast).  A CTA of LP_THREADS lanes covers LP_THREADS consecutive eigenvalues of one matrix.
+constexpr int LP_THREADS = 128;
+
+__device__ __forceinline__ double stage_scaled(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
+                                               double2* de, double* e, double& glo_out, double& tnorm_out) {
+    __shared__ double s_lo[LP_THREADS / 32], s_hi[LP_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        de[i].x = d_g[i];
+        e[i] = i < S - 1 ? e_g[i] : 0.0;
+    }
+    __syncthreads();
+    double glo = DBL_MAX, ghi = -DBL_MAX;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const double r = (i ? fabs(e[i - 1]) : 0.0) + fabs(e[i]);
+        glo = fmin(glo, de[i].x - r);
+        ghi = fmax(ghi, de[i].x + r);
+    }
+    glo = warp_min(glo);
+    ghi = warp_max(ghi);
+    if (lane == 0) {
+        s_lo[warp] = glo;
+        s_hi[warp] = ghi;
+    }
+    __syncthreads();
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        glo = fmin(glo, s_lo[w]);
+        ghi = fmax(ghi, s_hi[w]);
+    }
+    const double sc = pow2_scale(fmax(fabs(glo), fabs(ghi)));
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const double es = e[i] * sc;
+        e[i] = es;
+        de[i].x *= sc;
+        if (i + 1 < S) de[i + 1].y = es * es;
+        if (i == 0) de[0].y = 0.0;
+    }
+    __syncthreads();
+    tnorm_out = fmax(fabs(glo), fabs(ghi)) * sc;
+    glo_out = glo * sc;
+    return sc;
+}
+
+__global__ void __launch_bounds__(LP_THREADS)
+tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
+                           const double* __restrict__ cut_states, const int* __restrict__ n_states, int max_states,
+                           double* __restrict__ evals) {
+    extern __shared__ double2 sm2[];
+    double2* de = sm2;
+    double* e = reinterpret_cast<double*>(sm2 + S);
+    const int mat = blockIdx.y;
+    const int k = blockIdx.x * LP_THREADS + threadIdx.x;
+    const int nb = min(n_states[mat], max_states);
+    if (blockIdx.x * LP_THREADS >= nb) return;
+    double glo, tnorm;
+    const double sc = stage_scaled(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de, e, glo, tnorm);
+    if (k >= nb) return;
+    const double pivmin = DBL_MIN * 4.0;
+    double lo = glo - 2.0 * DBL_EPSILON * S - 2.0 * pivmin;
+    double hi = fmin(fmax(cut_states[mat], -4.0 * tnorm / sc), 4.0 * tnorm / sc) * sc;
+    for (int it = 0; it < 1100; ++it) {                          // count(lo) <= k < count(hi)
+        if (hi - lo <= DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin) break;
+        const double mid = lo + 0.5 * (hi - lo);
+        if (!(mid > lo && mid < hi)) break;
+        const int c = sturm_count(S, mid, [&](int i) { return de[i]; });
+        if (c > k) hi = mid;
+        else lo = mid;
+    }
+    evals[(size_t)mat * max_states + k] = 0.5 * (lo + hi) / sc;
+}
+
+// Eigenvectors: one warp per state, twisted factorisation (forward LDL^T pivots D+, backward UDU^T pivots D-, twist
+// at the smallest |gamma|) with every site recurrence spread over the 32 lanes.
+//   * Pivots.  D_i = p_i / p_{i-1} with p the minor recurrence, i.e. (p_i, p_{i-1}) = M_i (p_{i-1}, p_{i-2}),
+//     M_i = [[d_i - lam, -e^2], [1, 0]].  Each lane multiplies the M_i of its contiguous piece of the chain (two
+//     sequences, from (1,0) and (0,1)), a warp scan of the 2x2 piece matrices gives every piece its incoming pair,
+//     and a second pass over the piece emits the pivots: critical path 2 S/32 sites instead of S.  Only ratios of
+//     the pair matter, so pieces and prefixes are renormalised by exact powers of two at will.
+//   * Vector.  z_r = 1, z_i = rho_i z_{i+1} below the twist and z_{i+1} = rho_i z_i above it: running products,
+//     again a per-lane piece plus a warp scan of the piece totals (these are eigenvector components themselves).
+// D+ is staged in the output row, D- in the scratch row; both are overwritten by the vector / dead afterwards.
+constexpr int VEC_WARPS = 4;
+
+__device__ __forceinline__ void renorm2(double& a, double& b) {
+    const int h = max(__double2hiint(a) & 0x7ff00000, __double2hiint(b) & 0x7ff00000);
+    const double rs = __hiloint2double(0x7fe00000 - h, 0);
+    a *= rs;
+    b *= rs;
+}
+__device__ __forceinline__ void renorm4(double& a, double& b, double& c, double& d) {
+    const int h = max(max(__double2hiint(a) & 0x7ff00000, __double2hiint(b) & 0x7ff00000),
+                      max(__double2hiint(c) & 0x7ff00000, __double2hiint(d) & 0x7ff00000));
+    const double rs = __hiloint2double(0x7fe00000 - h, 0);
+    a *= rs;
+    b *= rs;
+    c *= rs;
+    d *= rs;
+}
+
+// Pivots of one direction.  site(j) maps the j-th site of the direction to (d - lam, e^2 coupling it to the site
+// before it in the direction; ignored for j = 0); out(j, q) stores the pivot.
+template <typename FS, typename FO>
+__device__ __forceinline__ void pivots_by_scan(int S, int lane, double pivmin, FS site, FO out) {
+    const int per = (S + 31) >> 5;
+    const int j0 = min(S, lane * per), j1 = min(S, j0 + per);
+    // piece matrix [[a, b], [c, d]]: (p_{j1-1}, p_{j1-2}) = [[a, b], [c, d]] (p_{j0-1}, p_{j0-2})
+    double a = 1.0, b = 0.0, c = 0.0, d = 1.0;
+    for (int j = j0; j < j1; ++j) {
+        const double2 v = site(j);
+        const double e2 = j ? v.y : 0.0;
+        const double na = fma(v.x, a, -(e2 * c)), nb = fma(v.x, b, -(e2 * d));
+        c = a;
+        d = b;
+        a = na;
+        b = nb;
+        if (((j - j0) & 7) == 7) renorm4(a, b, c, d);
+    }
+    renorm4(a, b, c, d);
+    // inclusive scan: prefix_l = piece_l * piece_{l-1} * ... * piece_0
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double oa = __shfl_up_sync(0xffffffffu, a, off), ob = __shfl_up_sync(0xffffffffu, b, off);
+        const double oc = __shfl_up_sync(0xffffffffu, c, off), od = __shfl_up_sync(0xffffffffu, d, off);
+        if (lane >= off) {
+            const double na = fma(a, oa, b * oc), nb = fma(a, ob, b * od);
+            const double nc = fma(c, oa, d * oc), nd = fma(c, ob, d * od);
+            a = na;
+            b = nb;
+            c = nc;
+            d = nd;
+            renorm4(a, b, c, d);
         }
     }
+    // incoming pair of this piece = (exclusive prefix) applied to (p_{-1}, p_{-2}) = (1, 0): its first column
+    double p1 = __shfl_up_sync(0xffffffffu, a, 1), p0 = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) {
+        p1 = 1.0;
+        p0 = 0.0;
+    }
+    for (int j = j0; j < j1; ++j) {
+        const double2 v = site(j);
+        const double e2 = j ? v.y : 0.0;
+        double pn = fma(v.x, p1, -(e2 * p0));
+        if (pn == 0.0) pn = -p1 * 0x1p-100;
+        double q = pn / p1;
+        if (!(fabs(q) >= pivmin)) q = -pivmin;
+        out(j, q);
+        p0 = p1;
+        p1 = pn;
+        if (((j - j0) & 7) == 7) renorm2(p0, p1);
+    }
+}
+
+__global__ void __launch_bounds__(VEC_WARPS * 32)
+tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
+                      const int* __restrict__ n_states, int max_states, const double* __restrict__ evals,
+                      double* __restrict__ evecs, double* __restrict__ scratch) {
+    extern __shared__ double2 sm2[];
+    double2* de = sm2;
+    double* e = reinterpret_cast<double*>(sm2 + S);
+    const int mat = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * VEC_WARPS + warp;
+    const int nb = min(n_states[mat], max_states);
+    if (blockIdx.x * VEC_WARPS >= nb) return;
+    double glo, tnorm;
+    const double sc = stage_scaled(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de, e, glo, tnorm);
+    if (k >= nb) return;
+    const double pivmin = DBL_MIN * 4.0;
+    const double lam = evals[(size_t)mat * max_states + k] * sc;
+    double* z = evecs + ((size_t)mat * max_states + k) * S;      // D+ first, overwritten by the vector
+    double* dm = scratch + ((size_t)mat * max_states + k) * S;   // D-
+    pivots_by_scan(S, lane, pivmin, [&](int j) { return make_double2(de[j].x - lam, de[j].y); },
+                   [&](int j, double q) { z[j] = q; });
+    pivots_by_scan(S, lane, pivmin,
+                   [&](int j) { const int i = S - 1 - j; return make_double2(de[i].x - lam, i + 1 < S ? de[i + 1].y : 0.0); },
+                   [&](int j, double q) { dm[S - 1 - j] = q; });
     __syncwarp();
     // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - lam)
     double best = DBL_MAX;
@@ -245,10 +395,7 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         }
     }
     __syncwarp();
-    // z_r = 1; downwards z_i = rho_i z_{i+1}, rho_i = -e_i / D+_i; upwards z_{i+1} = rho_i z_i, rho_i = -e_i / D-_{i+1}.
-    // Each chain is a running product: every lane multiplies through a contiguous piece, a warp scan of the piece
-    // totals gives each piece its starting value (these are eigenvector components themselves, so they are O(1) or
-    // decaying), and a second pass writes the components.
+    double nrm = 0.0;
     auto chain = [&](int L, auto rho, auto store) {
         const int per = (L + 31) >> 5;
         const int j0 = min(L, lane * per), j1 = min(L, j0 + per);
@@ -265,17 +412,16 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
         for (int j = j0; j < j1; ++j) {
             v *= rho(j);
             store(j, v);
+            nrm = fma(v, v, nrm);
         }
     };
     chain(r, [&](int j) { const int i = r - 1 - j; return -(e[i] / z[i]); },
           [&](int j, double v) { z[r - 1 - j] = v; });
     chain(S - 1 - r, [&](int j) { const int i = r + j; return -(e[i] / dm[i + 1]); },
           [&](int j, double v) { z[r + 1 + j] = v; });
+    nrm = warp_sum(nrm) + 1.0;
     if (lane == 0) z[r] = 1.0;
     __syncwarp();
-    double nrm = 0.0;
-    for (int i = lane; i < S; i += 32) nrm = fma(z[i], z[i], nrm);
-    nrm = warp_sum(nrm);
     const double zs = 1.0 / sqrt(nrm);
     for (int i = lane; i < S; i += 32) z[i] *= zs;
 }
@@ -444,19 +590,37 @@ int have_device() {
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+int g_eig_mode = 0;   // tx_set_option(3, .): 0 auto, 1 warp per state (multisection), 2 lane per state (bisection)
+
 int launch_eig(const double* d, const double* e, int S, int n_mat, const double* cut_states, const int* n_states,
                int max_states, double* evals, double* evecs, double* scratch, cudaStream_t st) {
     const size_t smem = (size_t)3 * S * sizeof(double);
     if (smem > 200 * 1024) return fail(TX_ERR_UNSUPPORTED, "chain length S=%d exceeds the shared-memory staged limit (8533)", S);
     static bool attr_set = false;
-    if (!attr_set || smem > 48 * 1024) {
+    if (!attr_set) {
         TX_CUDA(cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eigval_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dim3 grid((max_states + EIG_WARPS - 1) / EIG_WARPS, n_mat);
-    tridiag_eig_kernel<<<grid, EIG_WARPS * 32, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals, evecs, scratch);
+    // a warp per state has the shorter critical path (11 multisection passes against 53 bisections) and wins until the
+    // machine is full; beyond that the lane-per-state kernels do 6x less arithmetic per eigenvalue
+    const bool lanes = g_eig_mode == 2 || (g_eig_mode == 0 && (long long)n_mat * max_states >= 4096);
+    if (!lanes) {
+        dim3 grid((max_states + EIG_WARPS - 1) / EIG_WARPS, n_mat);
+        tridiag_eig_kernel<<<grid, EIG_WARPS * 32, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals);
+    } else {
+        dim3 grid((max_states + LP_THREADS - 1) / LP_THREADS, n_mat);
+        tridiag_eigval_lane_kernel<<<grid, LP_THREADS, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals);
+    }
     TX_CUDA(cudaGetLastError());
     count_launch();
+    if (evecs) {
+        dim3 grid((max_states + VEC_WARPS - 1) / VEC_WARPS, n_mat);
+        tridiag_eigvec_kernel<<<grid, VEC_WARPS * 32, smem, st>>>(d, e, S, n_states, max_states, evals, evecs, scratch);
+        TX_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return TX_OK;
 }
 
@@ -469,6 +633,14 @@ int launch_count(const double* d, const double* e, int S, int n_mat, const doubl
 }
 
 }  // namespace
+
+namespace tx {
+int set_eig_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(TX_ERR_ARG, "eigen-solver mode %d outside 0..2", mode);
+    g_eig_mode = mode;
+    return TX_OK;
+}
+}  // namespace tx
 
 extern "C" {
 

@@ -292,6 +292,7 @@ int tx_set_option(int option, int value) {
         g_chunk_gexp = value;
         return TX_OK;
     }
+    if (option == 3) return set_eig_mode(value);
     return fail(TX_ERR_ARG, "unknown option %d", option);
 }
 

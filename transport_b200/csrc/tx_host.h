@@ -7,6 +7,8 @@ namespace tx {
 int fail(int code, const char* fmt, ...);
 // Counts kernel launches issued by the library (tx_launch_counter()).
 void count_launch(int n = 1);
+// bardeen.cu: 0 auto, 1 warp per state, 2 lane per state (tx_set_option(3, mode)).
+int set_eig_mode(int mode);
 }  // namespace tx
 
 #define TX_CUDA(call)                                                                              \
