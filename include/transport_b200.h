@@ -263,9 +263,9 @@ int tx_set_variant(int variant);
  *             and scalar runs); value 0 treats every site as a general block (A/B measurements).
  *   option 1: longest chunk of the telescoped sweep in sites, 1..64 (default 32; 1 = one inverse per site).
  *   option 2: log2 of the growth bound that closes a chunk early, 0..500 (default 4: max |D_j| / prod |t| < 32).
- *   option 3: tridiagonal eigen-solver of the Bardeen path: 0 (default) picks by batch size, 1 a warp per state
- *             (multisection, shortest critical path), 2 a lane per state (bisection, least arithmetic; chosen
- *             automatically from 4096 states per call). */
+ *   option 3: eigenvalue kernel of the Bardeen path: 0 (default) picks by batch size, 1 a warp per eigenvalue
+ *             (multisection, shortest critical path), 2 a lane per eigenvalue (bisection, least arithmetic; chosen
+ *             automatically from 8192 state slots per call). */
 int tx_set_option(int option, int value);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device

@@ -277,8 +277,8 @@ tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restr
 //     the pair matter, so pieces and prefixes are renormalised by exact powers of two at will.
 //   * Vector.  z_r = 1, z_i = rho_i z_{i+1} below the twist and z_{i+1} = rho_i z_i above it: running products,
 //     again a per-lane piece plus a warp scan of the piece totals (these are eigenvector components themselves).
-// D+ is staged in the output row, D- in the scratch row; both are overwritten by the vector / dead afterwards.
-constexpr int VEC_WARPS = 4;
+// Everything lives in shared memory: D+ in the warp's work row, D- consumed on the fly (and recomputed once the
+// twist is known), the ratios and finally the normalised vector in the same row, one coalesced copy to HBM.
 
 __device__ __forceinline__ void renorm2(double& a, double& b) {
     const int h = max(__double2hiint(a) & 0x7ff00000, __double2hiint(b) & 0x7ff00000);
@@ -296,12 +296,10 @@ __device__ __forceinline__ void renorm4(double& a, double& b, double& c, double&
     d *= rs;
 }
 
-// Pivots of one direction.  site(j) maps the j-th site of the direction to (d - lam, e^2 coupling it to the site
-// before it in the direction; ignored for j = 0); out(j, q) stores the pivot.
-template <typename FS, typename FO>
-__device__ __forceinline__ void pivots_by_scan(int S, int lane, double pivmin, FS site, FO out) {
-    const int per = (S + 31) >> 5;
-    const int j0 = min(S, lane * per), j1 = min(S, j0 + per);
+// Incoming pair (p_{j0-1}, p_{j0-2}) of this lane's piece [j0, j1) of one direction.  site(j) maps the j-th site of
+// the direction to (d - lam, e^2 coupling it to the site before it in the direction; ignored for j = 0).
+template <typename FS>
+__device__ __forceinline__ void piece_incoming(int j0, int j1, int lane, FS site, double& p1, double& p0) {
     // piece matrix [[a, b], [c, d]]: (p_{j1-1}, p_{j1-2}) = [[a, b], [c, d]] (p_{j0-1}, p_{j0-2})
     double a = 1.0, b = 0.0, c = 0.0, d = 1.0;
     for (int j = j0; j < j1; ++j) {
@@ -330,12 +328,18 @@ __device__ __forceinline__ void pivots_by_scan(int S, int lane, double pivmin, F
             renorm4(a, b, c, d);
         }
     }
-    // incoming pair of this piece = (exclusive prefix) applied to (p_{-1}, p_{-2}) = (1, 0): its first column
-    double p1 = __shfl_up_sync(0xffffffffu, a, 1), p0 = __shfl_up_sync(0xffffffffu, c, 1);
+    // (exclusive prefix) applied to (p_{-1}, p_{-2}) = (1, 0): its first column
+    p1 = __shfl_up_sync(0xffffffffu, a, 1);
+    p0 = __shfl_up_sync(0xffffffffu, c, 1);
     if (lane == 0) {
         p1 = 1.0;
         p0 = 0.0;
     }
+}
+
+// Pivots q_j = p_j / p_{j-1} of the piece from its incoming pair (the division is off the dependent chain).
+template <typename FS, typename FO>
+__device__ __forceinline__ void piece_pivots(int j0, int j1, double p1, double p0, double pivmin, FS site, FO out) {
     for (int j = j0; j < j1; ++j) {
         const double2 v = site(j);
         const double e2 = j ? v.y : 0.0;
@@ -350,41 +354,47 @@ __device__ __forceinline__ void pivots_by_scan(int S, int lane, double pivmin, F
     }
 }
 
-__global__ void __launch_bounds__(VEC_WARPS * 32)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
                       const int* __restrict__ n_states, int max_states, const double* __restrict__ evals,
-                      double* __restrict__ evecs, double* __restrict__ scratch) {
+                      double* __restrict__ evecs) {
     extern __shared__ double2 sm2[];
     double2* de = sm2;
     double* e = reinterpret_cast<double*>(sm2 + S);
     const int mat = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k = blockIdx.x * VEC_WARPS + warp;
+    double* w = e + S + (size_t)warp * S;                        // this warp's work row: D+ -> rho -> vector
+    const int k = blockIdx.x * WARPS + warp;
     const int nb = min(n_states[mat], max_states);
-    if (blockIdx.x * VEC_WARPS >= nb) return;
+    if (blockIdx.x * WARPS >= nb) return;
     double glo, tnorm;
     const double sc = stage_scaled(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de, e, glo, tnorm);
     if (k >= nb) return;
     const double pivmin = DBL_MIN * 4.0;
     const double lam = evals[(size_t)mat * max_states + k] * sc;
-    double* z = evecs + ((size_t)mat * max_states + k) * S;      // D+ first, overwritten by the vector
-    double* dm = scratch + ((size_t)mat * max_states + k) * S;   // D-
-    pivots_by_scan(S, lane, pivmin, [&](int j) { return make_double2(de[j].x - lam, de[j].y); },
-                   [&](int j, double q) { z[j] = q; });
-    pivots_by_scan(S, lane, pivmin,
-                   [&](int j) { const int i = S - 1 - j; return make_double2(de[i].x - lam, i + 1 < S ? de[i + 1].y : 0.0); },
-                   [&](int j, double q) { dm[S - 1 - j] = q; });
+    // contiguous pieces of odd length: lane-strided shared-memory accesses then hit distinct banks
+    const int per = ((S + 31) >> 5) | 1;
+    const int j0 = min(S, lane * per), j1 = min(S, j0 + per);
+    auto fwd = [&](int j) { return make_double2(de[j].x - lam, de[j].y); };
+    auto bwd = [&](int j) { const int i = S - 1 - j; return make_double2(de[i].x - lam, i + 1 < S ? de[i + 1].y : 0.0); };
+    double p1, p0;
+    piece_incoming(j0, j1, lane, fwd, p1, p0);
+    piece_pivots(j0, j1, p1, p0, pivmin, fwd, [&](int j, double q) { w[j] = q; });
     __syncwarp();
-    // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - lam)
+    // backward pivots on the fly: gamma_i = D+_i + D-_i - (d_i - lam), twist index r = argmin |gamma_i|
+    double b1, b0;
+    piece_incoming(j0, j1, lane, bwd, b1, b0);
     double best = DBL_MAX;
     int r = 0;
-    for (int i = lane; i < S; i += 32) {
-        const double g = fabs(z[i] + dm[i] - (de[i].x - lam));
-        if (g < best) {
+    piece_pivots(j0, j1, b1, b0, pivmin, bwd, [&](int j, double q) {
+        const int i = S - 1 - j;
+        const double g = fabs(w[i] + q - (de[i].x - lam));
+        if (g < best || (g == best && i < r)) {
             best = g;
             r = i;
         }
-    }
+    });
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, off);
@@ -395,35 +405,70 @@ tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__
         }
     }
     __syncwarp();
-    double nrm = 0.0;
-    auto chain = [&](int L, auto rho, auto store) {
-        const int per = (L + 31) >> 5;
-        const int j0 = min(L, lane * per), j1 = min(L, j0 + per);
-        double t = 1.0;
-        for (int j = j0; j < j1; ++j) t *= rho(j);
-        double inc = t;                                          // inclusive scan of the piece totals
+    // link ratios in place: below the twist rho_i = -e_i / D+_i (z_i = rho_i z_{i+1}); from the twist upwards
+    // rho_i = -e_i / D-_{i+1} (z_{i+1} = rho_i z_i), the backward pivots being recomputed from the saved incoming pair
+    for (int i = lane; i < r; i += 32) w[i] = -(e[i] / w[i]);
+    piece_pivots(j0, j1, b1, b0, pivmin, bwd, [&](int j, double q) {
+        const int i = S - 1 - j;
+        if (i - 1 >= r) w[i - 1] = -(e[i - 1] / q);
+    });
+    __syncwarp();
+    // running products away from the twist: per-lane pieces, a warp scan of the piece totals, and the piece sums of
+    // squares give the norm before anything is written
+    double start[2], ssq[2];
+    const int Ls[2] = {r, S - 1 - r};
+    int c0[2], c1[2];
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const int L = Ls[dir];
+        const int cper = ((L + 31) >> 5) | 1;
+        c0[dir] = min(L, lane * cper);
+        c1[dir] = min(L, c0[dir] + cper);
+        double t = 1.0, q = 0.0;
+        for (int j = c0[dir]; j < c1[dir]; ++j) {
+            t *= dir == 0 ? w[r - 1 - j] : w[r + j];
+            q = fma(t, t, q);
+        }
+        ssq[dir] = q;
+        double in = t;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc *= o;
+            const double o = __shfl_up_sync(0xffffffffu, in, off);
+            if (lane >= off) in *= o;
         }
-        double v = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) v = 1.0;
-        for (int j = j0; j < j1; ++j) {
-            v *= rho(j);
-            store(j, v);
-            nrm = fma(v, v, nrm);
-        }
-    };
-    chain(r, [&](int j) { const int i = r - 1 - j; return -(e[i] / z[i]); },
-          [&](int j, double v) { z[r - 1 - j] = v; });
-    chain(S - 1 - r, [&](int j) { const int i = r + j; return -(e[i] / dm[i + 1]); },
-          [&](int j, double v) { z[r + 1 + j] = v; });
+        double st = __shfl_up_sync(0xffffffffu, in, 1);
+        if (lane == 0) st = 1.0;
+        start[dir] = st;                                         // component at the piece start (z_r = 1)
+    }
+    double nrm = fma(start[0] * start[0], ssq[0], start[1] * start[1] * ssq[1]);
     nrm = warp_sum(nrm) + 1.0;
-    if (lane == 0) z[r] = 1.0;
-    __syncwarp();
     const double zs = 1.0 / sqrt(nrm);
-    for (int i = lane; i < S; i += 32) z[i] *= zs;
+    __syncwarp();
+    // downwards: each lane reads a ratio and overwrites it with the normalised component (indices < r)
+    {
+        double v = start[0] * zs;
+        for (int j = c0[0]; j < c1[0]; ++j) {
+            v *= w[r - 1 - j];
+            w[r - 1 - j] = v;
+        }
+    }
+    // upwards: component r+j+1 lands where ratio r+j+1 is still to be read by the next step of the same lane or the
+    // first step of the next lane, so every lane reads one ratio ahead and the first one before anybody writes
+    {
+        double v = start[1] * zs;
+        double next = c0[1] < c1[1] ? w[r + c0[1]] : 0.0;
+        __syncwarp();
+        for (int j = c0[1]; j < c1[1]; ++j) {
+            const double rho = next;
+            if (j + 1 < c1[1]) next = w[r + j + 1];
+            v *= rho;
+            w[r + j + 1] = v;
+        }
+    }
+    if (lane == 0) w[r] = zs;
+    __syncwarp();
+    double* z = evecs + ((size_t)mat * max_states + k) * S;
+    for (int i = lane; i < S; i += 32) z[i] = w[i];
 }
 
 // Window-averaged Oppenheimer matrix elements.  grid = (max_states, n*n, P): CTA (m, alpha*n+beta, p).
@@ -600,12 +645,16 @@ int launch_eig(const double* d, const double* e, int S, int n_mat, const double*
     if (!attr_set) {
         TX_CUDA(cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TX_CUDA(cudaFuncSetAttribute(tridiag_eigval_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    // a warp per state has the shorter critical path (11 multisection passes against 53 bisections) and wins until the
-    // machine is full; beyond that the lane-per-state kernels do 6x less arithmetic per eigenvalue
-    const bool lanes = g_eig_mode == 2 || (g_eig_mode == 0 && (long long)n_mat * max_states >= 4096);
+    // a warp per eigenvalue has the shorter critical path (11 multisection passes against 53 bisections) and wins until
+    // the machine is full; beyond that a lane per eigenvalue does 6x less arithmetic per eigenvalue.  Measured
+    // crossover on B200: ~8700 states per call (S = 451: 5230 states 0.29 vs 0.38 ms; S = 1651: 21 000 states 3.6 vs 1.4 ms).
+    // (Four interleaved shifts per lane, 5-section, were measured too: slower, 1.69 vs 1.44 ms — with ~1.3 warps per
+    // scheduler the doubly loaded schedulers are FP64-pipe bound and 5-section does 1.7x the arithmetic.)
+    const bool lanes = g_eig_mode == 2 || (g_eig_mode == 0 && (long long)n_mat * max_states >= 8192);
     if (!lanes) {
         dim3 grid((max_states + EIG_WARPS - 1) / EIG_WARPS, n_mat);
         tridiag_eig_kernel<<<grid, EIG_WARPS * 32, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals);
@@ -616,8 +665,17 @@ int launch_eig(const double* d, const double* e, int S, int n_mat, const double*
     TX_CUDA(cudaGetLastError());
     count_launch();
     if (evecs) {
-        dim3 grid((max_states + VEC_WARPS - 1) / VEC_WARPS, n_mat);
-        tridiag_eigvec_kernel<<<grid, VEC_WARPS * 32, smem, st>>>(d, e, S, n_states, max_states, evals, evecs, scratch);
+        // (d, e^2), e and one work row per warp in shared memory: 4 warps while 56 S bytes fit, else 1 (S <= 6400)
+        (void)scratch;
+        if ((size_t)56 * S <= 200 * 1024) {
+            dim3 grid((max_states + 3) / 4, n_mat);
+            tridiag_eigvec_kernel<4><<<grid, 128, (size_t)56 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
+        } else if ((size_t)32 * S <= 200 * 1024) {
+            dim3 grid(max_states, n_mat);
+            tridiag_eigvec_kernel<1><<<grid, 32, (size_t)32 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
+        } else {
+            return fail(TX_ERR_UNSUPPORTED, "chain length S=%d exceeds the eigenvector kernel's shared-memory limit (6400)", S);
+        }
         TX_CUDA(cudaGetLastError());
         count_launch();
     }
