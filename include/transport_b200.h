@@ -200,7 +200,8 @@ int tx_landauer_current_dev(const double* T, const double* E, int nE, const doub
  * n_states[mat] = number of eigenvalues < cut_states[mat] (NOT clamped: > max_states means truncated),
  * n_below[mat] = number < cut_count[mat] (cut_count NULL: same as cut_states; n_below may be NULL).
  * max_states = 0 only counts.  Host pointers.  The _dev forms take device pointers and a stream;
- * scratch has the size of evecs. */
+ * scratch is unused (the eigenvector kernel keeps its work rows in shared memory) and may be NULL.
+ * Limits: S <= 8533 for eigenvalues, S <= 6400 with eigenvectors (shared-memory staging). */
 int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, const double* cut_states,
                           const double* cut_count, int max_states, double* evals, double* evecs, int* n_states,
                           int* n_below);
@@ -264,8 +265,8 @@ int tx_set_variant(int variant);
  *   option 1: longest chunk of the telescoped sweep in sites, 1..64 (default 32; 1 = one inverse per site).
  *   option 2: log2 of the growth bound that closes a chunk early, 0..500 (default 4: max |D_j| / prod |t| < 32).
  *   option 3: eigenvalue kernel of the Bardeen path: 0 (default) picks by batch size, 1 a warp per eigenvalue
- *             (multisection, shortest critical path), 2 a lane per eigenvalue (bisection, least arithmetic; chosen
- *             automatically from 8192 state slots per call). */
+ *             (multisection, shortest critical path), 2 a lane per eigenvalue (bracketed interpolation, least arithmetic; chosen
+ *             automatically from 2048 state slots per call). */
 int tx_set_option(int option, int value);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device

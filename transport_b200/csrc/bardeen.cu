@@ -72,6 +72,54 @@ __device__ __forceinline__ int sturm_count(int S, double xs, FDE de) {
     return cnt;
 }
 
+// The same count, also returning the value of the last minor p_{S-1}(x) = det(T - x) as mant * 2^expo (the exponents
+// taken out by the renormalisations are summed): the lane-per-eigenvalue kernel interpolates on it.
+template <typename FDE>
+__device__ __forceinline__ int sturm_count_f(int S, double xs, FDE de, double& mant, int& expo) {
+    double p0 = 1.0;
+    double p1 = de(0).x - xs;
+    if (p1 == 0.0) p1 = -0x1p-100;
+    int cnt = p1 < 0.0;
+    int E = 0;
+    unsigned sgn = (unsigned)__double2hiint(p1) >> 31;
+    int i = 1;
+    for (; i + 8 <= S; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = de(i + j);
+            const double u = v.y * p0;
+            p0 = p1;
+            p1 = fma(v.x - xs, p1, -u);
+            sgn = __funnelshift_l((unsigned)__double2hiint(p1), sgn, 1);
+        }
+        cnt += __popc((sgn ^ (sgn >> 1)) & 0xffu);
+        const int h = max(__double2hiint(p0) & 0x7ff00000, __double2hiint(p1) & 0x7ff00000);
+        const double sc = __hiloint2double(0x7fe00000 - h, 0);
+        p0 *= sc;
+        p1 *= sc;
+        E += (h >> 20) - 1023;
+    }
+    for (; i < S; ++i) {
+        const double2 v = de(i);
+        const double u = v.y * p0;
+        p0 = p1;
+        p1 = fma(v.x - xs, p1, -u);
+        sgn = __funnelshift_l((unsigned)__double2hiint(p1), sgn, 1);
+        cnt += (sgn ^ (sgn >> 1)) & 1u;
+    }
+    if (p1 == 0.0 && S > 1) cnt += !(((sgn >> 1) ^ sgn) & 1u);
+    const int hi = __double2hiint(p1);
+    const int eb = (hi >> 20) & 0x7ff;
+    if (eb == 0 || eb == 0x7ff) {                                // zero / denormal / non-finite: no usable value
+        mant = 0.0;
+        expo = 0;
+    } else {
+        mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(p1));
+        expo = E + eb - 1023;
+    }
+    return cnt;
+}
+
 // exact power of two s with s * tnorm in [0.5, 1)  (1 for a zero matrix)
 __device__ __forceinline__ double pow2_scale(double tnorm) {
     if (!(tnorm > 0.0) || !isfinite(tnorm)) return 1.0;
@@ -196,8 +244,8 @@ tridiag_eig_kernel(const double* __restrict__ d_g, const double* __restrict__ e_
 // ---- lane-per-state path (large batches) -------------------------------------------------------------------
 // With thousands of states in flight a warp per state wastes the machine: multisection spends 32 Sturm counts per
 // 5 bits.  Here every LANE owns one eigenvalue of the CTA's matrix and bisects it alone (1 bit per count, 6x fewer
-// FP64 operations per eigenvalue and 32 eigenvalues per instruction); all lanes read the same (d_i, e_i^2) word of
-// shared memory (broadcast).  A CTA of LP_THREADS lanes covers LP_THREADS consecutive eigenvalues of one matrix.
+// FP64 operations per eigenvalue and 32 eigenvalues per instruction), helped by interpolation on the last minor once
+// its bracket is isolated; all lanes read the same (d_i, e_i^2) word of shared memory (broadcast).  A CTA of LP_THREADS lanes covers LP_THREADS consecutive eigenvalues of one matrix.
 constexpr int LP_THREADS = 128;
 
 __device__ __forceinline__ double stage_scaled(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
@@ -257,13 +305,42 @@ tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restr
     const double pivmin = DBL_MIN * 4.0;
     double lo = glo - 2.0 * DBL_EPSILON * S - 2.0 * pivmin;
     double hi = fmin(fmax(cut_states[mat], -4.0 * tnorm / sc), 4.0 * tnorm / sc) * sc;
-    for (int it = 0; it < 1100; ++it) {                          // count(lo) <= k < count(hi)
+    // Bracketing by Sturm counts (rigorous), the next shift by interpolation once the bracket isolates the eigenvalue:
+    // count(hi) - count(lo) == 1 means det(T - x) changes sign exactly once inside, and the Illinois variant of
+    // regula falsi on the last minor converges superlinearly (21-33 counts per eigenvalue instead of 53 bisections).
+    // Every fourth step is a bisection, so the bracket halves at least that often whatever the minor's rounding does.
+    int c_lo = 0, c_hi = n_states[mat];
+    double m_lo = 0.0, m_hi = 0.0;
+    int E_lo = 0, E_hi = 0, side = 0;
+    for (int it = 0; it < 1100; ++it) {                          // c_lo = count(lo) <= k < count(hi) = c_hi
         if (hi - lo <= DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin) break;
         const double mid = lo + 0.5 * (hi - lo);
         if (!(mid > lo && mid < hi)) break;
-        const int c = sturm_count(S, mid, [&](int i) { return de[i]; });
-        if (c > k) hi = mid;
-        else lo = mid;
+        double x = mid;
+        if (c_hi - c_lo == 1 && m_lo != 0.0 && m_hi != 0.0 && (it & 3) != 3) {
+            const int dE = max(-1000, min(1000, E_hi - E_lo));
+            const double ratio = ldexp(m_hi / m_lo, dE);         // f(hi) / f(lo) < 0
+            const double xi = lo + (hi - lo) / (1.0 - ratio);
+            if (ratio < 0.0 && xi > lo && xi < hi) {
+                // step over the estimate, away from the nearer end, by 2 % of the distance to it (at least half the
+                // tolerance): regula falsi alone closes in from one side and leaves the other end of the bracket behind
+                const double tol = DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin;
+                const double dl = xi - lo, dh = hi - xi;
+                x = dl < dh ? fmin(xi + fmax(0.02 * dl, 0.5 * tol), mid) : fmax(xi - fmax(0.02 * dh, 0.5 * tol), mid);
+            }
+        }
+        double m;
+        int E;
+        const int c = sturm_count_f(S, x, [&](int i) { return de[i]; }, m, E);
+        if (c > k) {
+            hi = x; c_hi = c; m_hi = m; E_hi = E;
+            if (side > 0) E_lo -= 1;                             // Illinois: the retained end's value is halved
+            side = 1;
+        } else {
+            lo = x; c_lo = c; m_lo = m; E_lo = E;
+            if (side < 0) E_hi -= 1;
+            side = -1;
+        }
     }
     evals[(size_t)mat * max_states + k] = 0.5 * (lo + hi) / sc;
 }
@@ -649,12 +726,13 @@ int launch_eig(const double* d, const double* e, int S, int n_mat, const double*
         TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    // a warp per eigenvalue has the shorter critical path (11 multisection passes against 53 bisections) and wins until
-    // the machine is full; beyond that a lane per eigenvalue does 6x less arithmetic per eigenvalue.  Measured
-    // crossover on B200: ~8700 states per call (S = 451: 5230 states 0.29 vs 0.38 ms; S = 1651: 21 000 states 3.6 vs 1.4 ms).
-    // (Four interleaved shifts per lane, 5-section, were measured too: slower, 1.69 vs 1.44 ms — with ~1.3 warps per
-    // scheduler the doubly loaded schedulers are FP64-pipe bound and 5-section does 1.7x the arithmetic.)
-    const bool lanes = g_eig_mode == 2 || (g_eig_mode == 0 && (long long)n_mat * max_states >= 8192);
+    // A warp per eigenvalue has the shorter critical path (11 multisection passes against 21-33 interpolated counts)
+    // and serves small calls; a lane per eigenvalue does ~10x less arithmetic per eigenvalue and wins as soon as
+    // there are a few thousand states (measured on B200, both wells of 256 geometries: S = 451, 10 461 states:
+    // 0.58 vs 0.43 ms; S = 1651, 42 225 states: 7.3 vs 2.3 ms).  Four interleaved shifts per lane (5-section) were
+    // measured too and are slower (1.69 vs 1.44 ms per well): with ~1.3 warps per scheduler the doubly loaded
+    // schedulers are FP64-pipe bound and 5-section does 1.7x the arithmetic.
+    const bool lanes = g_eig_mode == 2 || (g_eig_mode == 0 && (long long)n_mat * max_states >= 2048);
     if (!lanes) {
         dim3 grid((max_states + EIG_WARPS - 1) / EIG_WARPS, n_mat);
         tridiag_eig_kernel<<<grid, EIG_WARPS * 32, smem, st>>>(d, e, S, cut_states, n_states, max_states, evals);
@@ -713,7 +791,6 @@ int tx_tridiag_eigh_below_dev(const double* d, const double* e, int S, int n_mat
                               const int* n_states, int max_states, double* evals, double* evecs, double* scratch,
                               void* stream) {
     if (!d || !e || !cut_states || !n_states || !evals) return fail(TX_ERR_ARG, "null pointer argument");
-    if (evecs && !scratch) return fail(TX_ERR_ARG, "eigenvectors need a scratch buffer of the same size");
     if (S < 2 || n_mat < 1 || max_states < 1) return fail(TX_ERR_ARG, "bad sizes S=%d n_mat=%d max_states=%d", S, n_mat, max_states);
     return launch_eig(d, e, S, n_mat, cut_states, n_states, max_states, evals, evecs, scratch,
                       reinterpret_cast<cudaStream_t>(stream));
@@ -730,7 +807,7 @@ int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, co
     const size_t bd = align256((size_t)n_mat * S * 8), be = align256((size_t)n_mat * (S - 1) * 8), bc = align256((size_t)n_mat * 8);
     const size_t bv = align256((size_t)n_mat * max_states * 8), bz = evecs ? align256((size_t)n_mat * max_states * S * 8) : 0;
     DevMem mem;
-    TX_CUDA(cudaMalloc(&mem.p, bd + be + 4 * bc + bv + 2 * bz + 256));
+    TX_CUDA(cudaMalloc(&mem.p, bd + be + 4 * bc + bv + bz + 256));
     char* q = mem.p;
     double* dd = (double*)q;  q += bd;
     double* de = (double*)q;  q += be;
@@ -739,15 +816,14 @@ int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, co
     int* dns = (int*)q;       q += bc;
     int* dnb = (int*)q;       q += bc;
     double* dv = (double*)q;  q += bv;
-    double* dz = evecs ? (double*)q : nullptr;  q += bz;
-    double* dscr = evecs ? (double*)q : nullptr;
+    double* dz = evecs ? (double*)q : nullptr;
     TX_CUDA(cudaMemcpy(dd, d, (size_t)n_mat * S * 8, cudaMemcpyHostToDevice));
     TX_CUDA(cudaMemcpy(de, e, (size_t)n_mat * (S - 1) * 8, cudaMemcpyHostToDevice));
     TX_CUDA(cudaMemcpy(dcs, cut_states, (size_t)n_mat * 8, cudaMemcpyHostToDevice));
     TX_CUDA(cudaMemcpy(dcc, cut_count, (size_t)n_mat * 8, cudaMemcpyHostToDevice));
     if (int rc = launch_count(dd, de, S, n_mat, dcs, dcc, dns, dnb, nullptr)) return rc;
     if (max_states > 0)
-        if (int rc = launch_eig(dd, de, S, n_mat, dcs, dns, max_states, dv, dz, dscr, nullptr)) return rc;
+        if (int rc = launch_eig(dd, de, S, n_mat, dcs, dns, max_states, dv, dz, nullptr, nullptr)) return rc;
     TX_CUDA(cudaMemcpy(n_states, dns, (size_t)n_mat * 4, cudaMemcpyDeviceToHost));
     if (n_below) TX_CUDA(cudaMemcpy(n_below, dnb, (size_t)n_mat * 4, cudaMemcpyDeviceToHost));
     if (max_states > 0) {
@@ -758,8 +834,8 @@ int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, co
 }
 
 long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states) {
-    // psiL, psiR, scratch (shared by both wells, used one after the other on the same stream)
-    return (long long)(3 * align256((size_t)P * n * max_states * S * 8) + 256);
+    // psiL, psiR
+    return (long long)(2 * align256((size_t)P * n * max_states * S * 8) + 256);
 }
 
 int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
@@ -777,12 +853,11 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
     const size_t bz = align256((size_t)P * n * max_states * S * 8);
     double* psiL = (double*)workspace;
     double* psiR = (double*)((char*)workspace + bz);
-    double* scr = (double*)((char*)workspace + 2 * bz);
     const int n_mat = P * n;
     if (int rc = launch_count(dL, eL, S, n_mat, cutL, cutL, nL, nR_below /* overwritten below */, st)) return rc;
     if (int rc = launch_count(dR, eR, S, n_mat, cutR_states, cutR_count, nR_states, nR_below, st)) return rc;
-    if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, scr, st)) return rc;
-    if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, scr, st)) return rc;
+    if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, nullptr, st)) return rc;
+    if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, nullptr, st)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         TX_CUDA(cudaFuncSetAttribute(bardeen_melem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
