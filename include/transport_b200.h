@@ -273,6 +273,12 @@ int tx_set_option(int option, int value);
  * routine of the sweep (in-place Gauss-Jordan with implicit partial pivoting). Host pointers. */
 int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n);
 
+/* Same for the CTA-cooperative inverse of the large-block paths (n <= 64; blocked tensor-core Gauss-Jordan with
+ * implicit partial pivoting when n is a multiple of 8 and >= 16).  Returns TX_ERR_SINGULAR on a zero pivot. */
+int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n);
+/* Device time in ms of the last tx_debug_invert_staged kernel launch (CUDA events; measurement hook). */
+double tx_debug_last_invert_ms(void);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /*
  * Measures the FP64 FMA-pipe peak of the current device with a register-resident DFMA loop

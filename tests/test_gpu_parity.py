@@ -677,3 +677,29 @@ def test_separable_multichannel_leads():
         bad = h01.copy()
         bad[0, 1] = 0.1
         leads.surface_gf(h00, bad, Es, 1, _lib.TX_GF_SEPARABLE)
+
+
+@pytest.mark.parametrize("n", [8, 16, 24, 40, 56, 64, 13])
+def test_staged_inverse_blocked_gauss_jordan(n):
+    """the CTA inverse of the large-block paths (blocked tensor-core Gauss-Jordan with implicit partial pivoting for
+    n % 8 == 0, n >= 16) against numpy, including blocks that cannot be inverted without pivoting"""
+    from transport_b200._lib import as_c128, check, ptr
+    rng = np.random.default_rng(n)
+    count = 6
+    A = rng.normal(size=(count, n, n)) + 1j * rng.normal(size=(count, n, n))
+    A[1, :n // 2, :n // 2] = 0.0                                  # zero leading block: pivoting required
+    A[2] = np.eye(n)[::-1] * (1 + 0.5j) + 1e-3 * A[2]             # anti-diagonal dominant
+    A[3] = np.diag(np.exp(rng.uniform(-8, 8, size=n))) @ A[3]     # badly row-scaled
+    A[4] = 3.0 * np.eye(n) - 0.5 * (A[4] + A[4].conj().T) / np.sqrt(n) + 1e-8j * np.eye(n)   # E - h - Sigma like
+    out = np.empty_like(A)
+    check(_lib.load().tx_debug_invert_staged(ptr(as_c128(A)), ptr(out), count, n))
+    for b in range(count):
+        ref = np.linalg.inv(A[b])
+        scale = np.abs(ref).max()
+        assert np.max(np.abs(out[b] - ref)) < 1e-11 * scale * np.linalg.cond(A[b]) ** 0.5, (n, b)
+        assert np.max(np.abs(out[b] @ A[b] - np.eye(n))) < 1e-9, (n, b)
+    S = A[0].copy()
+    S[:, 3] = 0.0                                                 # exactly singular
+    with pytest.raises(_lib.TransportError) as ei:
+        check(_lib.load().tx_debug_invert_staged(ptr(as_c128(S[None])), ptr(out[:1]), 1, n))
+    assert ei.value.code == _lib.TX_ERR_SINGULAR

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "tx_bardeen_current_dev": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P]),
     "tx_bardeen_ts": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "tx_debug_invert": (c_int, [_P, _P, c_int, c_int]),
+    "tx_debug_invert_staged": (c_int, [_P, _P, c_int, c_int]),
+    "tx_debug_last_invert_ms": (c_double, []),
     "tx_measure_fp64_peak": (c_int, [_P, _P]),
     "tx_measure_dmma_peak": (c_int, [_P, _P]),
     "tx_microbench": (c_int, [c_int, _P]),

@@ -246,11 +246,159 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
     __syncthreads();
 }
 
-// Inverse of X using the shared-memory staging block S when X itself lives in global memory: every
-// elimination step rewrites the whole block, which must not go through L2 sixty-four times.
+// Blocked Gauss-Jordan inverse for n a multiple of 8 (n <= 64), X in global memory, S a shared-memory staging block
+// of n rows with leading dimension n + 1 (conflict-free fragment accesses).  Per panel of 8 columns:
+//   1. warp 0 runs the 8 elimination steps on the n x 8 panel entirely in registers (a lane owns rows l and l + 32),
+//      IMPLICIT partial pivoting over the rows not used so far: no row is moved, the pivot row of step k is recorded
+//      in perm[k];
+//   2. the accumulated transformation of the 8 steps is applied to all other columns as ONE rank-8 update on the FP64
+//      tensor cores: with P the pivot rows, R = A[P, others] (copied out, then zeroed in place) and G the finished
+//      panel,   A[:, others] += G R      (in-place Gauss-Jordan leaves in column k exactly the column of the
+//      transformation that belongs to pivot row perm[k]).
+// Afterwards S holds (PA)^-1 with logical row k in physical row perm[k]:  X[k][perm[c]] = S[perm[k]][c].
+// 2 block barriers + one panel latency per 8 columns instead of 4-5 barriers and a full sweep of the block per column.
+__device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
+    __shared__ cd s_R[8 * 64];
+    __shared__ cd s_prow[8];
+    __shared__ int s_perm[64];
+    const int ld = n + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int r = idx / n, c = idx - r * n;
+        S[r * ld + c] = X[idx];
+    }
+    __syncthreads();
+    bool used0 = false, used1 = false;                 // warp 0: rows lane and lane + 32 already served as pivots
+    const int r0 = lane, r1 = lane + 32;
+    const int tiles = n >> 3;
+    for (int kb = 0; kb < n; kb += 8) {
+        if (warp == 0) {
+            cd a0[8], a1[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                a0[c] = (r0 < n) ? S[r0 * ld + kb + c] : mk(0.0, 0.0);
+                a1[c] = (r1 < n) ? S[r1 * ld + kb + c] : mk(0.0, 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double m0 = (used0 || r0 >= n) ? -1.0 : norm2(a0[j]);
+                const double m1 = (used1 || r1 >= n) ? -1.0 : norm2(a1[j]);
+                double best = (m1 > m0 || !(m1 == m1)) ? m1 : m0;
+                int brow = (m1 > m0 || !(m1 == m1)) ? r1 : r0;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+                    if (ob > best || !(ob == ob) || (ob == best && orow < brow)) {
+                        best = ob;
+                        brow = orow;
+                    }
+                }
+                const int pr = brow;
+                if (lane == 0) {
+                    s_perm[kb + j] = pr;
+                    if (!(best > 0.0)) *singular = 1;
+                }
+                if (pr == r0 || pr == r1) {              // owner: scaled pivot row of the panel, 1/pivot in column j
+                    const bool first = pr == r0;
+                    const cd inv = crecip(first ? a0[j] : a1[j]);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const cd v = first ? a0[c] : a1[c];
+                        s_prow[c] = (c == j) ? inv : v * inv;
+                    }
+                    if (first) used0 = true;
+                    else used1 = true;
+                }
+                __syncwarp();
+                {
+                    const cd f0 = a0[j], f1 = a1[j];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const cd pw = s_prow[c];                 // broadcast read: keeps the panel at 64 registers
+                        if (pr == r0) {
+                            a0[c] = pw;
+                        } else {
+                            cd v = (c == j) ? mk(0.0, 0.0) : a0[c];
+                            cfms(v.x, v.y, f0.x, f0.y, pw.x, pw.y);
+                            a0[c] = v;
+                        }
+                        if (pr == r1) {
+                            a1[c] = pw;
+                        } else {
+                            cd v = (c == j) ? mk(0.0, 0.0) : a1[c];
+                            cfms(v.x, v.y, f1.x, f1.y, pw.x, pw.y);
+                            a1[c] = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (r0 < n) S[r0 * ld + kb + c] = a0[c];
+                if (r1 < n) S[r1 * ld + kb + c] = a1[c];
+            }
+        }
+        __syncthreads();
+        // R = old pivot rows (all columns outside the panel), zeroed in place
+        for (int idx = threadIdx.x; idx < 8 * n; idx += blockDim.x) {
+            const int j = idx / n, c = idx - j * n;
+            if (c < kb || c >= kb + 8) {
+                const int pr = s_perm[kb + j];
+                s_R[j * 64 + c] = S[pr * ld + c];
+                S[pr * ld + c] = mk(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+        // A[:, others] += G R : a warp takes a tile row, the G fragments are loaded once for its column tiles
+        {
+            const int g = lane >> 2, t = lane & 3;
+            for (int tr = warp; tr < tiles; tr += nwarps) {
+                const cd ga = S[(tr * 8 + g) * ld + kb + t];
+                const cd gb = S[(tr * 8 + g) * ld + kb + 4 + t];
+                for (int tc = 0; tc < tiles; ++tc) {
+                    if (tc * 8 == kb) continue;
+                    const cd ra = s_R[t * 64 + tc * 8 + g];
+                    const cd rb = s_R[(4 + t) * 64 + tc * 8 + g];
+                    cd* cp = S + (tr * 8 + g) * ld + tc * 8 + 2 * t;
+                    const cd c0 = cp[0], c1 = cp[1];
+                    double re[2] = {c0.x, c1.x}, im[2] = {c0.y, c1.y};
+                    dmma844(re, ga.x, ra.x);
+                    dmma844(im, ga.x, ra.y);
+                    dmma844(re, -ga.y, ra.y);
+                    dmma844(im, ga.y, ra.x);
+                    dmma844(re, gb.x, rb.x);
+                    dmma844(im, gb.x, rb.y);
+                    dmma844(re, -gb.y, rb.y);
+                    dmma844(im, gb.y, rb.x);
+                    cp[0] = mk(re[0], im[0]);
+                    cp[1] = mk(re[1], im[1]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // undo the implicit row permutation while copying out:  X[k][perm[c]] = S[perm[k]][c]
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int k = idx / n, c = idx - k * n;
+        X[k * n + s_perm[c]] = S[s_perm[k] * ld + c];
+    }
+    __syncthreads();
+}
+
+// Bytes of shared-memory staging the inverse of a global-memory block needs (leading dimension n + 1 for the blocked path).
+__host__ __device__ inline size_t inverse_stage_bytes(int n) { return (size_t)n * (n + 1) * sizeof(cd); }
+
+// Inverse of X using the shared-memory staging block S (inverse_stage_bytes(n)) when X itself lives in global memory:
+// every elimination step rewrites the block, which must not go through L2 sixty-four times.
 __device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ipiv, int* singular) {
     if (S == nullptr || S == X) {
         cta_inverse(X, n, colk, ipiv, singular);
+        return;
+    }
+    if ((n & 7) == 0 && n >= 16 && n <= 64) {
+        cta_inverse_blocked(X, S, n, singular);
         return;
     }
     cta_copy(S, X, n * n);

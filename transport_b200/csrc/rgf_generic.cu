@@ -20,7 +20,7 @@ namespace tx {
 constexpr int GEN_THREADS = 256;
 constexpr int GEN_MATS = 5;
 
-__global__ void __launch_bounds__(GEN_THREADS) rgf_sweep_generic(const GenericParams p) {
+__global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const GenericParams p) {
     extern __shared__ double2 gen_smem[];
     __shared__ int s_ipiv[64];
     __shared__ cd s_colk[64];
@@ -273,11 +273,11 @@ int launch_rgf_generic(GenericParams p, cudaStream_t st) {
     size_t smem = bytes;
     if (bytes > 200 * 1024) {
         if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
-        smem = (size_t)p.n * p.n * sizeof(cd);   // staging block for the inverse
+        smem = inverse_stage_bytes(p.n);         // staging block for the inverse
     } else {
         p.work = nullptr;
     }
-    if (smem > 48 * 1024)
+    if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
         TX_CUDA(cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p.n_pts > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
     rgf_sweep_generic<<<(unsigned)p.n_pts, GEN_THREADS, smem, st>>>(p);

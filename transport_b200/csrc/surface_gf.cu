@@ -10,6 +10,8 @@
 // multi-channel leads, which the reference cannot do (g_iter refuses n > 2, :502).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <cstdarg>
 #include <cstdio>
 #include <vector>
@@ -369,8 +371,26 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
     if (p.sigma) emit_sigma(p, m0, m1, p.sigma + (long long)e * nn);
 }
 
+// Unit-test hook for the CTA-cooperative inverse of block_ops.cuh (staged / blocked path): one CTA per block.
+__global__ void __launch_bounds__(GF_THREADS) invert_staged_kernel(const cd* __restrict__ in, cd* __restrict__ out, int n,
+                                                                   int* singular, int unblocked) {
+    extern __shared__ double2 gf_smem[];
+    __shared__ int s_ipiv[64];
+    __shared__ cd s_colk[64];
+    const long long off = (long long)blockIdx.x * n * n;
+    cta_copy(out + off, in + off, n * n);
+    if (unblocked) {                                    // the column-by-column Gauss-Jordan, for A/B measurements
+        cd* S = reinterpret_cast<cd*>(gf_smem);
+        cta_copy(S, out + off, n * n);
+        cta_inverse(S, n, s_colk, s_ipiv, singular);
+        cta_copy(out + off, S, n * n);
+        return;
+    }
+    cta_inverse_staged(out + off, reinterpret_cast<cd*>(gf_smem), n, s_colk, s_ipiv, singular);
+}
+
 // One CTA per energy, persistent over the energy axis (grid = resident CTAs).
-__global__ void __launch_bounds__(GF_THREADS) surface_gf_kernel(const GfParams p) {
+__global__ void __launch_bounds__(GF_THREADS, 2) surface_gf_kernel(const GfParams p) {
     for (int e = blockIdx.x; e < p.nE; e += gridDim.x) {
         surface_gf_body(p, e);
         __syncthreads();
@@ -426,10 +446,10 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     p.scratch = nullptr;
     p.scratch_per = 0;
     if (bytes > 200 * 1024) {
-        smem = (size_t)n * n * sizeof(cd);      // staging block for the inverse
+        smem = inverse_stage_bytes(n);          // staging block for the inverse
         p.scratch_per = (long long)mats * n * n;
     }
-    if (smem > 48 * 1024)
+    if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
         TX_CUDA(cudaFuncSetAttribute(surface_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 1;
     TX_CUDA(cudaGetDevice(&dev));
@@ -592,6 +612,50 @@ int tx_g_ith(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, in
     if (ith > 0 && !g_prev) return fail(TX_ERR_ARG, "g_prev required for ith > 0");
     return gf_host(h00, h01, n, E, nE, side, TX_GF_FIXEDPOINT, imE, 0.0, 0, 0, 0, ith, ith > 0 ? g_prev : nullptr,
                    g_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+static float g_last_invert_ms = 0.f;
+double tx_debug_last_invert_ms(void) { return (double)g_last_invert_ms; }
+
+int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
+    if (!in || !out || count < 1 || n < 1 || n > 64) return fail(TX_ERR_ARG, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t bytes = (size_t)count * n * n * sizeof(cd);
+    cd *din = nullptr, *dout = nullptr;
+    int* dflag = nullptr;
+    TX_CUDA(cudaMalloc(&din, bytes));
+    TX_CUDA(cudaMalloc(&dout, bytes));
+    TX_CUDA(cudaMalloc(&dflag, sizeof(int)));
+    TX_CUDA(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemset(dflag, 0, sizeof(int)));
+    const size_t smem = inverse_stage_bytes(n);
+    const int unblocked = getenv("TX_INVERT_UNBLOCKED") != nullptr;
+    TX_CUDA(cudaFuncSetAttribute(invert_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    invert_staged_kernel<<<count, GF_THREADS, smem>>>((const cd*)din, dout, n, dflag, unblocked);   // warm-up (same result)
+    cudaEventRecord(ev0);
+    invert_staged_kernel<<<count, GF_THREADS, smem>>>((const cd*)din, dout, n, dflag, unblocked);
+    cudaEventRecord(ev1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) cudaEventElapsedTime(&g_last_invert_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(din);
+    cudaFree(dout);
+    cudaFree(dflag);
+    if (e != cudaSuccess) return fail(TX_ERR_CUDA, "invert_staged_kernel failed: %s", cudaGetErrorString(e));
+    if (flag) return fail(TX_ERR_SINGULAR, "singular block");
+    return TX_OK;
 }
 
 }  // extern "C"
