@@ -276,6 +276,8 @@ int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n);
 /* Same for the CTA-cooperative inverse of the large-block paths (n <= 64; blocked tensor-core Gauss-Jordan with
  * implicit partial pivoting when n is a multiple of 8 and >= 16).  Returns TX_ERR_SINGULAR on a zero pivot. */
 int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n);
+/* Measurement hook: device time of `count` CTAs each doing `reps` n x n complex products on global-memory blocks. */
+int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out);
 /* Device time in ms of the last tx_debug_invert_staged kernel launch (CUDA events; measurement hook). */
 double tx_debug_last_invert_ms(void);
 

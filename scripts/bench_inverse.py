@@ -18,3 +18,12 @@ for n in (24, 40, 56, 64):
     err = max(np.abs(out[i] @ A[i] - np.eye(n)).max() for i in range(0, count, 97))
     print(json.dumps({"n": n, "blocks": count, "ms": ms, "us_per_block_per_sm_slot": ms * 1e3 / (count / 296.0),
                       "gflops_8n3": 8 * n ** 3 * count / (ms * 1e-3) / 1e9, "max_resid": err}))
+
+import ctypes
+for n in (24, 40, 64):
+    ms = ctypes.c_double()
+    reps = 20
+    check(lib.tx_debug_gemm_ms(n, 296, reps, ctypes.byref(ms)))
+    us = ms.value * 1e3 / reps
+    print(json.dumps({"gemm_n": n, "ctas": 296, "us_per_product_2_ctas_per_sm": us,
+                      "tflops": 8 * n ** 3 * 296 / (us * 1e-6) / 1e12}))

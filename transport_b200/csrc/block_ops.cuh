@@ -131,24 +131,56 @@ __device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, in
     __syncthreads();
 }
 
+// The elementwise passes below run on blocks that usually sit in L2 / HBM (large-block workspaces): every thread
+// issues FOUR independent loads before its first store, otherwise a pass is a chain of 16 dependent memory latencies.
 __device__ inline void cta_copy(cd* dst, const cd* src, int count) {
-    for (int idx = threadIdx.x; idx < count; idx += blockDim.x) dst[idx] = src[idx];
+    const int bd = blockDim.x;
+    int idx = threadIdx.x;
+    for (; idx + 3 * bd < count; idx += 4 * bd) {
+        const cd v0 = src[idx], v1 = src[idx + bd], v2 = src[idx + 2 * bd], v3 = src[idx + 3 * bd];
+        dst[idx] = v0;
+        dst[idx + bd] = v1;
+        dst[idx + 2 * bd] = v2;
+        dst[idx + 3 * bd] = v3;
+    }
+    for (; idx < count; idx += bd) dst[idx] = src[idx];
     __syncthreads();
 }
 
 // A = z*I - H
 __device__ inline void cta_z_minus(cd* A, cd z, const cd* H, int n) {
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        const int r = idx / n, c = idx - r * n;
-        const cd hv = H[idx];
-        A[idx] = (r == c) ? mk(z.x - hv.x, z.y - hv.y) : mk(-hv.x, -hv.y);
+    const int bd = blockDim.x, count = n * n;
+    int idx = threadIdx.x;
+    auto one = [&](int i, cd hv) {
+        const int r = i / n, c = i - r * n;
+        A[i] = (r == c) ? mk(z.x - hv.x, z.y - hv.y) : mk(-hv.x, -hv.y);
+    };
+    for (; idx + 3 * bd < count; idx += 4 * bd) {
+        const cd v0 = H[idx], v1 = H[idx + bd], v2 = H[idx + 2 * bd], v3 = H[idx + 3 * bd];
+        one(idx, v0);
+        one(idx + bd, v1);
+        one(idx + 2 * bd, v2);
+        one(idx + 3 * bd, v3);
     }
+    for (; idx < count; idx += bd) one(idx, H[idx]);
     __syncthreads();
 }
 
 // A -= B
 __device__ inline void cta_sub(cd* A, const cd* B, int count) {
-    for (int idx = threadIdx.x; idx < count; idx += blockDim.x) {
+    const int bd = blockDim.x;
+    int idx = threadIdx.x;
+    for (; idx + 3 * bd < count; idx += 4 * bd) {
+        cd a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = A[idx + u * bd];
+            b[u] = B[idx + u * bd];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) A[idx + u * bd] = mk(a[u].x - b[u].x, a[u].y - b[u].y);
+    }
+    for (; idx < count; idx += bd) {
         cd a = A[idx];
         const cd b = B[idx];
         a.x -= b.x;
@@ -407,12 +439,26 @@ __device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ip
 }
 
 // max |A_ij|^2 over the block, broadcast to all threads
-__device__ inline double cta_maxnorm2(const cd* A, int count) {
+__device__ inline double cta_maxnorm2(const cd* A, int count, const cd* B = nullptr) {
+    // max over A (and B when given: one pass, one pair of barriers for both)
     __shared__ double s_red[32];
     double m = 0.0;
-    for (int idx = threadIdx.x; idx < count; idx += blockDim.x) {
-        const double v = norm2(A[idx]);
+    const int bd = blockDim.x;
+    auto take = [&](cd x) {
+        const double v = norm2(x);
         m = (v > m || !(v == v)) ? v : m;
+    };
+    for (int pass = 0; pass < (B ? 2 : 1); ++pass) {
+        const cd* P = pass ? B : A;
+        int idx = threadIdx.x;
+        for (; idx + 3 * bd < count; idx += 4 * bd) {
+            const cd v0 = P[idx], v1 = P[idx + bd], v2 = P[idx + 2 * bd], v3 = P[idx + 3 * bd];
+            take(v0);
+            take(v1);
+            take(v2);
+            take(v3);
+        }
+        for (; idx < count; idx += bd) take(P[idx]);
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {

@@ -49,22 +49,48 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
         s_vR[c] = -2.0 * SR[c * n + c].y;
     }
 
+    // Elementwise passes over blocks that sit in L2 / HBM: four independent loads per thread and array before the first
+    // store (otherwise a pass is a chain of dependent memory latencies).  f(idx) -> value to store at dst[idx].
+    auto for_each4 = [&](cd* dst, auto load, auto store) {
+        const int bd = blockDim.x;
+        int idx = threadIdx.x;
+        for (; idx + 3 * bd < nn; idx += 4 * bd) {
+            auto v0 = load(idx), v1 = load(idx + bd), v2 = load(idx + 2 * bd), v3 = load(idx + 3 * bd);
+            dst[idx] = store(idx, v0);
+            dst[idx + bd] = store(idx + bd, v1);
+            dst[idx + 2 * bd] = store(idx + 2 * bd, v2);
+            dst[idx + 3 * bd] = store(idx + 3 * bd, v3);
+        }
+        for (; idx < nn; idx += bd) dst[idx] = store(idx, load(idx));
+        __syncthreads();
+    };
+    struct ZIn {
+        cd h, w, s;
+    };
     // z_j = E - h_j (- Sigma on the end blocks) into dst
     auto build_z = [&](cd* dst, int j) {
-        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
-            const int r = idx / n, c = idx - r * n;
-            cd hv = hb[(long long)j * nn + idx];
-            if (p.h1) {
-                const cd w = p.h1[(long long)j * nn + idx];
-                hv.x = fma(par, w.x, hv.x);
-                hv.y = fma(par, w.y, hv.y);
-            }
-            cd a = (r == c) ? mk(E.x - hv.x, E.y - hv.y) : mk(-hv.x, -hv.y);
-            if (j == M - 1) a = a - SR[idx];
-            if (j == 0) a = a - SL[idx];
-            dst[idx] = a;
-        }
-        __syncthreads();
+        const cd* hj = hb + (long long)j * nn;
+        const cd* wj = p.h1 ? p.h1 + (long long)j * nn : nullptr;
+        const cd* sg = (j == M - 1) ? SR : (j == 0 ? SL : nullptr);
+        for_each4(dst,
+                  [&](int idx) {
+                      ZIn in;
+                      in.h = hj[idx];
+                      in.w = wj ? wj[idx] : mk(0.0, 0.0);
+                      in.s = sg ? sg[idx] : mk(0.0, 0.0);
+                      return in;
+                  },
+                  [&](int idx, ZIn in) {
+                      const int r = idx / n, c = idx - r * n;
+                      cd hv = in.h;
+                      if (wj) {
+                          hv.x = fma(par, in.w.x, hv.x);
+                          hv.y = fma(par, in.w.y, hv.y);
+                      }
+                      cd a = (r == c) ? mk(E.x - hv.x, E.y - hv.y) : mk(-hv.x, -hv.y);
+                      if (sg) a = a - in.s;
+                      return a;
+                  });
     };
 
     if (p.hop_scalar && p.kmax > 1) {
@@ -85,14 +111,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 const cd t0 = tb[(long long)b * nn];
                 const double kap = norm2(t0);
                 tau = conj(t0);
-                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
-                    cd a = cur[idx];
-                    const cd g = G[idx];
-                    a.x = fma(-kap, g.x, a.x);
-                    a.y = fma(-kap, g.y, a.y);
-                    cur[idx] = a;
-                }
-                __syncthreads();
+                struct Two {
+                    cd a, g;
+                };
+                for_each4(cur, [&](int idx) { Two t; t.a = cur[idx]; t.g = G[idx]; return t; },
+                          [&](int, Two t) { return mk(fma(-kap, t.g.x, t.a.x), fma(-kap, t.g.y, t.a.y)); });
             }
             int k = 1;
             bool prev_is_identity = true;
@@ -105,16 +128,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 ++k;
                 build_z(tmp, j);
                 // prev <- -kap * prev  (prev = I for the second site of a chunk)
-                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
-                    if (prev_is_identity) {
+                if (prev_is_identity) {
+                    for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
                         const int r = idx / n, c = idx - r * n;
                         prev[idx] = mk(r == c ? -kap : 0.0, 0.0);
-                    } else {
-                        const cd v = prev[idx];
-                        prev[idx] = mk(-kap * v.x, -kap * v.y);
                     }
+                    __syncthreads();
+                } else {
+                    for_each4(prev, [&](int idx) { return prev[idx]; }, [&](int, cd v) { return mk(-kap * v.x, -kap * v.y); });
                 }
-                __syncthreads();
                 cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0);           // D_j = z_j D_{j+1} - kap D_{j+2}
                 cd* sw = prev;
                 prev = cur;
@@ -128,12 +150,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
             if (prev_is_identity) cta_copy(G, cur, nn);
             else cta_gemm(G, prev, OP_N, cur, OP_N, n);                      // g_a = D_{a+1} X
             if (b == M - 1) {
-                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) W[idx] = cur[idx] * tau;
-                __syncthreads();
+                for_each4(W, [&](int idx) { return cur[idx]; }, [&](int, cd v) { return v * tau; });
             } else {
                 cta_gemm(tmp, W, OP_N, cur, OP_N, n);                        // W X
-                for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) W[idx] = tmp[idx] * tau;
-                __syncthreads();
+                for_each4(W, [&](int idx) { return tmp[idx]; }, [&](int, cd v) { return v * tau; });
             }
             --j;
         }

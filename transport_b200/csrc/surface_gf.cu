@@ -340,19 +340,41 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
             cta_gemm(T1, G, OP_N, beta, OP_N, n);               // G beta
             cta_gemm(T2, G, OP_N, alpha, OP_N, n);              // G alpha
             cta_gemm(tmp, alpha, OP_N, T1, OP_N, n);            // alpha G beta
-            for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
-                epss[idx] = epss[idx] + tmp[idx];
-                eps[idx] = eps[idx] + tmp[idx];
+            {
+                const int bd = blockDim.x;
+                int idx = threadIdx.x;
+                for (; idx + 3 * bd < nn; idx += 4 * bd) {      // four independent loads per array before the stores
+                    cd a[4], b[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        a[u] = epss[idx + u * bd];
+                        b[u] = eps[idx + u * bd];
+                        c[u] = tmp[idx + u * bd];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        epss[idx + u * bd] = a[u] + c[u];
+                        eps[idx + u * bd] = b[u] + c[u];
+                    }
+                }
+                for (; idx < nn; idx += bd) {
+                    epss[idx] = epss[idx] + tmp[idx];
+                    eps[idx] = eps[idx] + tmp[idx];
+                }
             }
             __syncthreads();
             cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0);    // + beta G alpha
             cta_gemm(tmp, alpha, OP_N, T2, OP_N, n);            // alpha G alpha
             cta_gemm(G, beta, OP_N, T1, OP_N, n);               // beta G beta (G is free now)
-            cta_copy(alpha, tmp, nn);
-            cta_copy(beta, G, nn);
-            const double ma = cta_maxnorm2(alpha, nn);
-            const double mb = cta_maxnorm2(beta, nn);
-            resid = fmax(ma, mb);
+            {                                                    // new alpha = tmp, new beta = G: swap roles, no copies
+                cd* sw = alpha;
+                alpha = tmp;
+                tmp = sw;
+                sw = beta;
+                beta = G;
+                G = sw;
+            }
+            resid = cta_maxnorm2(alpha, nn, beta);
             if (resid < tol2) {
                 ok = 1;
                 break;
@@ -387,6 +409,13 @@ __global__ void __launch_bounds__(GF_THREADS) invert_staged_kernel(const cd* __r
         return;
     }
     cta_inverse_staged(out + off, reinterpret_cast<cd*>(gf_smem), n, s_colk, s_ipiv, singular);
+}
+
+// Measurement hook: `reps` products C = A B per CTA on blocks in global memory (what the large-block paths do).
+__global__ void __launch_bounds__(GF_THREADS, 2) gemm_bench_kernel(const cd* __restrict__ A, const cd* __restrict__ B, cd* C, int n,
+                                                                    int reps) {
+    const long long off = (long long)blockIdx.x * n * n;
+    for (int r = 0; r < reps; ++r) cta_gemm(C + off, A + off, OP_N, B + off, OP_N, n);
 }
 
 // One CTA per energy, persistent over the energy axis (grid = resident CTAs).
@@ -655,6 +684,35 @@ int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
     cudaFree(dflag);
     if (e != cudaSuccess) return fail(TX_ERR_CUDA, "invert_staged_kernel failed: %s", cudaGetErrorString(e));
     if (flag) return fail(TX_ERR_SINGULAR, "singular block");
+    return TX_OK;
+}
+
+int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out) {
+    if (n < 8 || n > 64 || count < 1 || reps < 1 || !ms_out) return fail(TX_ERR_ARG, "bad arguments");
+    const size_t bytes = (size_t)count * n * n * sizeof(cd);
+    cd *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    TX_CUDA(cudaMalloc(&dA, bytes));
+    TX_CUDA(cudaMalloc(&dB, bytes));
+    TX_CUDA(cudaMalloc(&dC, bytes));
+    TX_CUDA(cudaMemset(dA, 0, bytes));
+    TX_CUDA(cudaMemset(dB, 0, bytes));
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    gemm_bench_kernel<<<count, GF_THREADS>>>(dA, dB, dC, n, 1);
+    cudaEventRecord(ev0);
+    gemm_bench_kernel<<<count, GF_THREADS>>>(dA, dB, dC, n, reps);
+    cudaEventRecord(ev1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dC);
+    if (e != cudaSuccess) return fail(TX_ERR_CUDA, "gemm_bench_kernel failed: %s", cudaGetErrorString(e));
+    *ms_out = ms;
     return TX_OK;
 }
 
