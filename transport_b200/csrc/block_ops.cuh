@@ -280,18 +280,22 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
 
 // Blocked Gauss-Jordan inverse for n a multiple of 8 (n <= 64), X in global memory, S a shared-memory staging block
 // of n rows with leading dimension n + 1 (conflict-free fragment accesses).  Per panel of 8 columns:
-//   1. warp 0 runs the 8 elimination steps on the n x 8 panel entirely in registers (a lane owns rows l and l + 32),
+//   1. the 8 elimination steps on the n x 8 panel run in registers, two entries per thread (4n threads), with
 //      IMPLICIT partial pivoting over the rows not used so far: no row is moved, the pivot row of step k is recorded
-//      in perm[k];
+//      in perm[k]; a step is two block barriers (column + 64-bit max key to shared memory; raw pivot row).  (One warp
+//      owning the whole panel needs no barriers but 64 dependent DFMAs per lane and step, which starve behind the
+//      co-resident CTA's DMMA stream on the shared FP64 pipe: measured 3.5k clk per step inside the kernels.)
 //   2. the accumulated transformation of the 8 steps is applied to all other columns as ONE rank-8 update on the FP64
 //      tensor cores: with P the pivot rows, R = A[P, others] (copied out, then zeroed in place) and G the finished
 //      panel,   A[:, others] += G R      (in-place Gauss-Jordan leaves in column k exactly the column of the
 //      transformation that belongs to pivot row perm[k]).
 // Afterwards S holds (PA)^-1 with logical row k in physical row perm[k]:  X[k][perm[c]] = S[perm[k]][c].
-// 2 block barriers + one panel latency per 8 columns instead of 4-5 barriers and a full sweep of the block per column.
+// Per column: 2 barriers and 2 complex FMAs per thread instead of 4-5 barriers and a full read-modify-write of the block.
 __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
     __shared__ cd s_R[8 * 64];
     __shared__ cd s_prow[8];
+    __shared__ cd s_colk2[2 * 64];
+    __shared__ unsigned long long s_key[32];
     __shared__ int s_perm[64];
     const int ld = n + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -300,77 +304,69 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
         S[r * ld + c] = X[idx];
     }
     __syncthreads();
-    bool used0 = false, used1 = false;                 // warp 0: rows lane and lane + 32 already served as pivots
-    const int r0 = lane, r1 = lane + 32;
+    // panel ownership: thread t holds row r = t % n, columns 2cp and 2cp + 1 (cp = t / n < 4) of the current panel
+    const int cp = threadIdx.x / n, r = threadIdx.x - cp * n;
+    const bool act = cp < 4;
+    bool used = false;                                 // my row has already served as a pivot row
     const int tiles = n >> 3;
     for (int kb = 0; kb < n; kb += 8) {
-        if (warp == 0) {
-            cd a0[8], a1[8];
+        cd a0 = act ? S[r * ld + kb + 2 * cp] : mk(0.0, 0.0);
+        cd a1 = act ? S[r * ld + kb + 2 * cp + 1] : mk(0.0, 0.0);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                a0[c] = (r0 < n) ? S[r0 * ld + kb + c] : mk(0.0, 0.0);
-                a1[c] = (r1 < n) ? S[r1 * ld + kb + c] : mk(0.0, 0.0);
+        for (int j = 0; j < 8; ++j) {
+            cd* colk = s_colk2 + (j & 1) * 64;
+            // stage 1: column j of the panel to shared memory, pivot = largest |.|^2 among the unused rows.  The key is
+            // the bit pattern of |a|^2 (monotone for non-negative doubles, NaN above everything) with 64 - row in
+            // its low 7 bits: one 64-bit max picks the pivot, ties go to the lowest row, 0 = not a candidate.
+            unsigned long long key = 0ull;
+            if (act && cp == (j >> 1)) {
+                const cd v = (j & 1) ? a1 : a0;
+                colk[r] = v;
+                if (!used) key = ((unsigned long long)__double_as_longlong(norm2(v)) & ~127ull) | (unsigned long long)(64 - r);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double m0 = (used0 || r0 >= n) ? -1.0 : norm2(a0[j]);
-                const double m1 = (used1 || r1 >= n) ? -1.0 : norm2(a1[j]);
-                double best = (m1 > m0 || !(m1 == m1)) ? m1 : m0;
-                int brow = (m1 > m0 || !(m1 == m1)) ? r1 : r0;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-                    if (ob > best || !(ob == ob) || (ob == best && orow < brow)) {
-                        best = ob;
-                        brow = orow;
-                    }
-                }
-                const int pr = brow;
-                if (lane == 0) {
-                    s_perm[kb + j] = pr;
-                    if (!(best > 0.0)) *singular = 1;
-                }
-                if (pr == r0 || pr == r1) {              // owner: scaled pivot row of the panel, 1/pivot in column j
-                    const bool first = pr == r0;
-                    const cd inv = crecip(first ? a0[j] : a1[j]);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const cd v = first ? a0[c] : a1[c];
-                        s_prow[c] = (c == j) ? inv : v * inv;
-                    }
-                    if (first) used0 = true;
-                    else used1 = true;
-                }
-                __syncwarp();
-                {
-                    const cd f0 = a0[j], f1 = a1[j];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const cd pw = s_prow[c];                 // broadcast read: keeps the panel at 64 registers
-                        if (pr == r0) {
-                            a0[c] = pw;
-                        } else {
-                            cd v = (c == j) ? mk(0.0, 0.0) : a0[c];
-                            cfms(v.x, v.y, f0.x, f0.y, pw.x, pw.y);
-                            a0[c] = v;
-                        }
-                        if (pr == r1) {
-                            a1[c] = pw;
-                        } else {
-                            cd v = (c == j) ? mk(0.0, 0.0) : a1[c];
-                            cfms(v.x, v.y, f1.x, f1.y, pw.x, pw.y);
-                            a1[c] = v;
-                        }
-                    }
-                }
-                __syncwarp();
+            for (int off = 16; off >= 1; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+                key = o > key ? o : key;
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (r0 < n) S[r0 * ld + kb + c] = a0[c];
-                if (r1 < n) S[r1 * ld + kb + c] = a1[c];
+            if (lane == 0) s_key[warp] = key;
+            __syncthreads();
+            key = s_key[0];
+            for (int w = 1; w < nwarps; ++w) key = s_key[w] > key ? s_key[w] : key;
+            const int pr = 64 - (int)(key & 127ull);
+            const cd pivot = colk[pr];
+            if (threadIdx.x == 0) {
+                s_perm[kb + j] = pr;
+                if (!(norm2(pivot) > 0.0)) *singular = 1;
             }
+            if (act && r == pr) {                      // raw pivot row of the panel
+                s_prow[2 * cp] = a0;
+                s_prow[2 * cp + 1] = a1;
+                used = true;
+            }
+            __syncthreads();
+            // stage 2: every thread updates its two entries (the pivot row becomes row/pivot with 1/pivot in column j)
+            if (act) {
+                const cd inv = crecip(pivot);
+                const cd pw0 = (2 * cp == j) ? inv : s_prow[2 * cp] * inv;
+                const cd pw1 = (2 * cp + 1 == j) ? inv : s_prow[2 * cp + 1] * inv;
+                if (r == pr) {
+                    a0 = pw0;
+                    a1 = pw1;
+                } else {
+                    const cd f = colk[r];
+                    cd v0 = (2 * cp == j) ? mk(0.0, 0.0) : a0;
+                    cd v1 = (2 * cp + 1 == j) ? mk(0.0, 0.0) : a1;
+                    cfms(v0.x, v0.y, f.x, f.y, pw0.x, pw0.y);
+                    cfms(v1.x, v1.y, f.x, f.y, pw1.x, pw1.y);
+                    a0 = v0;
+                    a1 = v1;
+                }
+            }
+        }
+        if (act) {
+            S[r * ld + kb + 2 * cp] = a0;
+            S[r * ld + kb + 2 * cp + 1] = a1;
         }
         __syncthreads();
         // R = old pivot rows (all columns outside the panel), zeroed in place
