@@ -46,11 +46,80 @@ __device__ __forceinline__ void dmma844(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+// Compile-time size, no transposes (every product of the Sancho-Rubio loop and of the telescoped sweep): per-lane
+// operand pointers are formed once per strip and advanced by constants, the k loop is fully unrolled, so the address
+// arithmetic that makes up a third of the generic routine's instructions disappears.
+template <int N>
+__device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, double sgn, bool accumulate) {
+    constexpr int NT = 4;
+    constexpr int TILES = N / 8;
+    constexpr int STRIPS = (TILES + NT - 1) / NT;
+    static_assert(TILES % NT == 0, "strips of four tiles");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int item = warp; item < TILES * STRIPS; item += nwarps) {
+        const int tr = (item / STRIPS) << 3;
+        const int tc0 = (item % STRIPS) * NT;
+        double re[NT][2], im[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
+        const cd* pa = A + (tr + g) * N + t;                     // A[tr+g][k+t], k += 4
+        const cd* pb = B + t * N + (tc0 << 3) + g;               // B[k+t][(tc0+u)*8+g], k += 4
+        // fragments of the next k-step are in flight while the DMMAs of the current one issue (two k-steps ahead was
+        // measured too: no gain, the products are not bound by operand latency)
+        cd a = pa[0];
+        cd b[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) b[u] = pb[u * 8];
+#pragma unroll
+        for (int k = 0; k < N; k += 4) {
+            const cd ac = a;
+            cd bc[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) bc[u] = b[u];
+            if (k + 4 < N) {
+                a = pa[k + 4];
+#pragma unroll
+                for (int u = 0; u < NT; ++u) b[u] = pb[(k + 4) * N + u * 8];
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                dmma844(re[u], ac.x, bc[u].x);
+                dmma844(im[u], ac.x, bc[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                dmma844(re[u], -ac.y, bc[u].y);
+                dmma844(im[u], ac.y, bc[u].x);
+            }
+        }
+        cd* pc = C + (tr + g) * N + (tc0 << 3) + 2 * t;
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+                if (accumulate) {
+                    const cd c0 = pc[u * 8 + i];
+                    v.x += c0.x;
+                    v.y += c0.y;
+                }
+                pc[u * 8 + i] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
 // A warp works on a strip of up to four 8x8 output tiles of one tile row: the A fragment of a k-step is loaded
 // once and reused for the four column tiles (16 DMMA per 5 fragment loads), and the loads of the next k-step are
 // issued before the DMMAs of the current one (operands usually sit in L2/L1, not in shared memory).
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate) {
+    if (n == 64 && opA == OP_N && opB == OP_N) {
+        cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate);
+        return;
+    }
     constexpr int NT = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
