@@ -347,6 +347,19 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
     __syncthreads();
 }
 
+// 1/z with the reciprocal of |z|^2 from MUFU.RCP64H + two Newton steps (~1 ulp, no IEEE slow path): the reciprocal
+// sits on the critical path of every elimination step of the blocked inverse.
+__device__ __forceinline__ cd crecip_fast(cd z) {
+    const double d = norm2(z);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return mk(z.x * r, -z.y * r);
+}
+
 // Blocked Gauss-Jordan inverse for n a multiple of 8 (n <= 64), X in global memory, S a shared-memory staging block
 // of n rows with leading dimension n + 1 (conflict-free fragment accesses).  Per panel of 8 columns:
 //   1. the 8 elimination steps on the n x 8 panel run in registers, two entries per thread (4n threads), with
@@ -364,7 +377,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
     __shared__ cd s_R[8 * 64];
     __shared__ cd s_prow[8];
     __shared__ cd s_colk2[2 * 64];
-    __shared__ unsigned long long s_key[32];
+    __shared__ unsigned s_key[32];
     __shared__ int s_perm[64];
     const int ld = n + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -385,24 +398,21 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
         for (int j = 0; j < 8; ++j) {
             cd* colk = s_colk2 + (j & 1) * 64;
             // stage 1: column j of the panel to shared memory, pivot = largest |.|^2 among the unused rows.  The key is
-            // the bit pattern of |a|^2 (monotone for non-negative doubles, NaN above everything) with 64 - row in
-            // its low 7 bits: one 64-bit max picks the pivot, ties go to the lowest row, 0 = not a candidate.
-            unsigned long long key = 0ull;
+            // the high word of |a|^2 (sign 0, exponent, 20 mantissa bits: monotone, NaN above everything) with 64 - row
+            // in its low 7 bits: one REDUX per warp picks the pivot (13 mantissa bits decide — ample for partial
+            // pivoting), ties go to the lowest row, 0 = not a candidate.
+            unsigned key = 0u;
             if (act && cp == (j >> 1)) {
                 const cd v = (j & 1) ? a1 : a0;
                 colk[r] = v;
-                if (!used) key = ((unsigned long long)__double_as_longlong(norm2(v)) & ~127ull) | (unsigned long long)(64 - r);
+                if (!used) key = ((unsigned)__double2hiint(norm2(v)) & ~127u) | (unsigned)(64 - r);
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
-                key = o > key ? o : key;
-            }
+            key = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) s_key[warp] = key;
             __syncthreads();
             key = s_key[0];
-            for (int w = 1; w < nwarps; ++w) key = s_key[w] > key ? s_key[w] : key;
-            const int pr = 64 - (int)(key & 127ull);
+            for (int w = 1; w < nwarps; ++w) key = max(key, s_key[w]);
+            const int pr = 64 - (int)(key & 127u);
             const cd pivot = colk[pr];
             if (threadIdx.x == 0) {
                 s_perm[kb + j] = pr;
@@ -416,7 +426,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
             __syncthreads();
             // stage 2: every thread updates its two entries (the pivot row becomes row/pivot with 1/pivot in column j)
             if (act) {
-                const cd inv = crecip(pivot);
+                const cd inv = crecip_fast(pivot);
                 const cd pw0 = (2 * cp == j) ? inv : s_prow[2 * cp] * inv;
                 const cd pw1 = (2 * cp + 1 == j) ? inv : s_prow[2 * cp + 1] * inv;
                 if (r == pr) {
