@@ -679,8 +679,16 @@ def test_separable_multichannel_leads():
         leads.surface_gf(h00, bad, Es, 1, _lib.TX_GF_SEPARABLE)
 
 
-@pytest.mark.parametrize("n", [8, 16, 24, 40, 56, 64, 13])
-def test_staged_inverse_blocked_gauss_jordan(n):
+@pytest.fixture(params=["staged", "in_place"])
+def inverse_mode(request, monkeypatch):
+    """blocks staged from global memory (n >= 56 in the kernels) or resident in shared memory (n <= 48)"""
+    if request.param == "in_place":
+        monkeypatch.setenv("TX_INVERT_INPLACE", "1")
+    return request.param
+
+
+@pytest.mark.parametrize("n", [8, 16, 24, 40, 48, 56, 64, 13])
+def test_staged_inverse_blocked_gauss_jordan(n, inverse_mode):
     """the CTA inverse of the large-block paths (blocked tensor-core Gauss-Jordan with implicit partial pivoting for
     n % 8 == 0, n >= 16) against numpy, including blocks that cannot be inverted without pivoting"""
     from transport_b200._lib import as_c128, check, ptr

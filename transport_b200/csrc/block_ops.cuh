@@ -373,19 +373,24 @@ __device__ __forceinline__ cd crecip_fast(cd z) {
 //      transformation that belongs to pivot row perm[k]).
 // Afterwards S holds (PA)^-1 with logical row k in physical row perm[k]:  X[k][perm[c]] = S[perm[k]][c].
 // Per column: 2 barriers and 2 complex FMAs per thread instead of 4-5 barriers and a full read-modify-write of the block.
+// S == X: in place on a block that already lives in shared memory (leading dimension n); the permutation is then undone
+// through registers (n <= 48 with 256 threads: at most 9 entries per thread).
 __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
     __shared__ cd s_R[8 * 64];
     __shared__ cd s_prow[8];
     __shared__ cd s_colk2[2 * 64];
     __shared__ unsigned s_key[32];
     __shared__ int s_perm[64];
-    const int ld = n + 1;
+    const bool in_place = S == X;
+    const int ld = in_place ? n : n + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        const int r = idx / n, c = idx - r * n;
-        S[r * ld + c] = X[idx];
+    if (!in_place) {
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            S[r * ld + c] = X[idx];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // panel ownership: thread t holds row r = t % n, columns 2cp and 2cp + 1 (cp = t / n < 4) of the current panel
     const int cp = threadIdx.x / n, r = threadIdx.x - cp * n;
     const bool act = cp < 4;
@@ -487,6 +492,29 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
         __syncthreads();
     }
     // undo the implicit row permutation while copying out:  X[k][perm[c]] = S[perm[k]][c]
+    if (in_place) {
+        constexpr int MAXE = 9;                        // 48 * 48 / 256
+        cd v[MAXE];
+#pragma unroll
+        for (int u = 0; u < MAXE; ++u) {
+            const int idx = threadIdx.x + u * blockDim.x;
+            if (idx < n * n) {
+                const int k = idx / n, c = idx - k * n;
+                v[u] = S[s_perm[k] * ld + c];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < MAXE; ++u) {
+            const int idx = threadIdx.x + u * blockDim.x;
+            if (idx < n * n) {
+                const int k = idx / n, c = idx - k * n;
+                X[k * n + s_perm[c]] = v[u];
+            }
+        }
+        __syncthreads();
+        return;
+    }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
         const int k = idx / n, c = idx - k * n;
         X[k * n + s_perm[c]] = S[s_perm[k] * ld + c];
@@ -501,7 +529,9 @@ __host__ __device__ inline size_t inverse_stage_bytes(int n) { return (size_t)n 
 // every elimination step rewrites the block, which must not go through L2 sixty-four times.
 __device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ipiv, int* singular) {
     if (S == nullptr || S == X) {
-        cta_inverse(X, n, colk, ipiv, singular);
+        // block already in shared memory: blocked in place while the un-permutation fits the registers
+        if ((n & 7) == 0 && n >= 16 && n * n <= 9 * (int)blockDim.x && 4 * n <= (int)blockDim.x) cta_inverse_blocked(X, X, n, singular);
+        else cta_inverse(X, n, colk, ipiv, singular);
         return;
     }
     if ((n & 7) == 0 && n >= 16 && n <= 64) {

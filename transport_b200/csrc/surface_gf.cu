@@ -401,10 +401,11 @@ __global__ void __launch_bounds__(GF_THREADS) invert_staged_kernel(const cd* __r
     __shared__ cd s_colk[64];
     const long long off = (long long)blockIdx.x * n * n;
     cta_copy(out + off, in + off, n * n);
-    if (unblocked) {                                    // the column-by-column Gauss-Jordan, for A/B measurements
-        cd* S = reinterpret_cast<cd*>(gf_smem);
+    if (unblocked) {                                    // 1: the column-by-column Gauss-Jordan, for A/B measurements;
+        cd* S = reinterpret_cast<cd*>(gf_smem);         // 2: the block resident in shared memory (in-place paths, n <= 48)
         cta_copy(S, out + off, n * n);
-        cta_inverse(S, n, s_colk, s_ipiv, singular);
+        if (unblocked == 1) cta_inverse(S, n, s_colk, s_ipiv, singular);
+        else cta_inverse_staged(S, nullptr, n, s_colk, s_ipiv, singular);
         cta_copy(out + off, S, n * n);
         return;
     }
@@ -662,7 +663,7 @@ int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
     TX_CUDA(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
     TX_CUDA(cudaMemset(dflag, 0, sizeof(int)));
     const size_t smem = inverse_stage_bytes(n);
-    const int unblocked = getenv("TX_INVERT_UNBLOCKED") != nullptr;
+    const int unblocked = getenv("TX_INVERT_UNBLOCKED") ? 1 : (getenv("TX_INVERT_INPLACE") ? 2 : 0);
     TX_CUDA(cudaFuncSetAttribute(invert_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
