@@ -346,7 +346,8 @@ def test_ts_wfm_well_against_dense_oracle(with_nnn):
         bardeen.Ts_wfm_well(tL, 0.9 * tR, VL, VR, HC, Emas)
 
 
-@pytest.mark.parametrize("n,scalar", [(20, True), (24, False), (33, True), (64, True)])
+@pytest.mark.parametrize("n,scalar", [(20, True), (24, False), (33, True), (40, False), (48, True), (56, True), (64, True),
+                                      (64, False)])
 def test_large_block_sweep_and_caroli(n, scalar):
     """16 < n <= 64 goes through the CTA-per-point kernel; parity vs the recursive numpy oracle."""
     rng = np.random.default_rng(n)
