@@ -548,6 +548,44 @@ tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__
     for (int i = lane; i < S; i += 32) z[i] = w[i];
 }
 
+// Rows of y = Hdiff[beta, alpha] psi that can be nonzero: [lo, hi] per (problem, alpha, beta), computed once per call
+// (Hdiff = Hsys - HL lives on the right well for kernel_well, on the few central sites for kernel_well_prime), so that
+// the matrix-element CTAs touch only that part of the states.  support[(p*n*n + alpha*n + beta)*2 + {0,1}] = lo, hi
+// (lo > hi: Hdiff[beta, alpha] vanishes).
+__global__ void __launch_bounds__(128)
+hdiff_support_kernel(const double* __restrict__ hd0, const double* __restrict__ hdU, const double* __restrict__ hdL, int n, int S,
+                     int* __restrict__ support) {
+    __shared__ int s_lohi[2];
+    const int alpha = (blockIdx.x / n) % n, beta = blockIdx.x % n, p = blockIdx.x / (n * n);
+    const size_t nn = (size_t)n * n, ba = (size_t)beta * n + alpha;
+    const double* h0 = hd0 + (size_t)p * S * nn + ba;
+    const double* hU = hdU + (size_t)p * (S - 1) * nn + ba;
+    const double* hL = hdL + (size_t)p * (S - 1) * nn + ba;
+    if (threadIdx.x == 0) {
+        s_lohi[0] = S;
+        s_lohi[1] = -1;
+    }
+    __syncthreads();
+    int lo = S, hi = -1;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        const bool nz = h0[(size_t)j * nn] != 0.0 || (j + 1 < S && hU[(size_t)j * nn] != 0.0) ||
+                        (j > 0 && hL[(size_t)(j - 1) * nn] != 0.0);
+        if (nz) {
+            lo = min(lo, j);
+            hi = max(hi, j);
+        }
+    }
+    if (hi >= 0) {
+        atomicMin(&s_lohi[0], lo);
+        atomicMax(&s_lohi[1], hi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        support[2 * blockIdx.x] = s_lohi[0];
+        support[2 * blockIdx.x + 1] = s_lohi[1];
+    }
+}
+
 // Window-averaged Oppenheimer matrix elements.  grid = (max_states, n*n, P): CTA (m, alpha*n+beta, p).
 //   Mavg[p][beta][m][alpha] = mean over k with |EL[alpha][m] - ER[beta][k]| < interval of
 //                             <psiR[beta][k] | Hdiff[:, :, beta, alpha] | psiL[alpha][m]>
@@ -558,10 +596,10 @@ __global__ void __launch_bounds__(128)
 bardeen_melem_kernel(const double* __restrict__ EL, const int* __restrict__ nL, const double* __restrict__ psiL,
                      const double* __restrict__ ER, const int* __restrict__ nR, const double* __restrict__ psiR,
                      const double* __restrict__ hd0, const double* __restrict__ hdU, const double* __restrict__ hdL,
-                     int n, int S, int max_states, double interval, int sign_fix, double* __restrict__ Mavg) {
+                     const int* __restrict__ support, int n, int S, int max_states, double interval, int sign_fix,
+                     double* __restrict__ Mavg) {
     extern __shared__ double y[];
     __shared__ double s_red[4];
-    __shared__ int s_lohi[2];
     const int m = blockIdx.x, alpha = blockIdx.y / n, beta = blockIdx.y % n, p = blockIdx.z;
     const size_t chL = (size_t)p * n + alpha, chR = (size_t)p * n + beta;
     double* out = Mavg + (((size_t)p * n + beta) * max_states + m) * n + alpha;
@@ -588,34 +626,24 @@ bardeen_melem_kernel(const double* __restrict__ EL, const int* __restrict__ nL, 
         if (threadIdx.x == 0) *out = 0.0;
         return;
     }
-    // y = Hdiff[beta, alpha] psi_m and its support
-    if (threadIdx.x == 0) {
-        s_lohi[0] = S;
-        s_lohi[1] = -1;
+    // y = Hdiff[beta, alpha] psi_m on the rows where it can be nonzero
+    const int j0 = support[2 * ((p * n + alpha) * n + beta)], j1 = support[2 * ((p * n + alpha) * n + beta) + 1] + 1;
+    if (j0 >= j1) {
+        if (threadIdx.x == 0) *out = 0.0;
+        return;
     }
-    __syncthreads();
     const double* psi = psiL + (chL * max_states + m) * S;
     const size_t nn = (size_t)n * n, ba = (size_t)beta * n + alpha;
     const double* h0 = hd0 + (size_t)p * S * nn + ba;
     const double* hU = hdU + (size_t)p * (S - 1) * nn + ba;
     const double* hL = hdL + (size_t)p * (S - 1) * nn + ba;
-    int my_lo = S, my_hi = -1;
-    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
         double v = h0[(size_t)j * nn] * psi[j];
         if (j + 1 < S) v = fma(hU[(size_t)j * nn], psi[j + 1], v);
         if (j > 0) v = fma(hL[(size_t)(j - 1) * nn], psi[j - 1], v);
         y[j] = v;
-        if (v != 0.0) {
-            my_lo = min(my_lo, j);
-            my_hi = max(my_hi, j);
-        }
-    }
-    if (my_hi >= 0) {
-        atomicMin(&s_lohi[0], my_lo);
-        atomicMax(&s_lohi[1], my_hi);
     }
     __syncthreads();
-    const int j0 = s_lohi[0], j1 = s_lohi[1] + 1;
     double sum = 0.0;
     for (int k = 0; k < nr; ++k) {
         const bool take = use_nearest ? (k == nearest) : (fabs(Em - Er[k]) < interval);
@@ -834,8 +862,8 @@ int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, co
 }
 
 long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states) {
-    // psiL, psiR
-    return (long long)(2 * align256((size_t)P * n * max_states * S * 8) + 256);
+    // psiL, psiR, support ranges of Hdiff
+    return (long long)(2 * align256((size_t)P * n * max_states * S * 8) + align256((size_t)P * n * n * 8) + 256);
 }
 
 int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
@@ -848,7 +876,8 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
         return fail(TX_ERR_ARG, "null pointer argument");
     if (P < 1 || n < 1 || S < 2 || max_states < 1) return fail(TX_ERR_ARG, "bad sizes P=%d n=%d S=%d max_states=%d", P, n, S, max_states);
     if ((size_t)S * 8 > 200 * 1024) return fail(TX_ERR_UNSUPPORTED, "chain length S=%d too long", S);
-    if ((long long)n * n > 65535 || P > 65535) return fail(TX_ERR_UNSUPPORTED, "grid too large (n=%d, P=%d)", n, P);
+    if ((long long)n * n > 65535 || P > 65535 || (long long)P * n * n > 0x3fffffffLL)
+        return fail(TX_ERR_UNSUPPORTED, "grid too large (n=%d, P=%d)", n, P);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t bz = align256((size_t)P * n * max_states * S * 8);
     double* psiL = (double*)workspace;
@@ -863,9 +892,13 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
         TX_CUDA(cudaFuncSetAttribute(bardeen_melem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
+    int* support = (int*)((char*)workspace + 2 * bz);
+    hdiff_support_kernel<<<P * n * n, 128, 0, st>>>(hd0, hdU, hdL, n, S, support);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
     dim3 grid(max_states, n * n, P);
-    bardeen_melem_kernel<<<grid, 128, (size_t)S * 8, st>>>(EL, nL, psiL, ER, nR_states, psiR, hd0, hdU, hdL, n, S, max_states,
-                                                          interval, sign_fix, Mavg);
+    bardeen_melem_kernel<<<grid, 128, (size_t)S * 8, st>>>(EL, nL, psiL, ER, nR_states, psiR, hd0, hdU, hdL, support, n, S,
+                                                          max_states, interval, sign_fix, Mavg);
     TX_CUDA(cudaGetLastError());
     count_launch();
     return TX_OK;
