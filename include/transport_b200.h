@@ -201,7 +201,7 @@ int tx_landauer_current_dev(const double* T, const double* E, int nE, const doub
  * n_below[mat] = number < cut_count[mat] (cut_count NULL: same as cut_states; n_below may be NULL).
  * max_states = 0 only counts.  Host pointers.  The _dev forms take device pointers and a stream;
  * scratch is unused (the eigenvector kernel keeps its work rows in shared memory) and may be NULL.
- * Limits: S <= 8533 for eigenvalues, S <= 6400 with eigenvectors (shared-memory staging). */
+ * Limit: S <= 8533 (shared-memory staging). */
 int tx_tridiag_eigh_below(const double* d, const double* e, int S, int n_mat, const double* cut_states,
                           const double* cut_count, int max_states, double* evals, double* evecs, int* n_states,
                           int* n_below);

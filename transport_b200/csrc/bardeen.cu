@@ -288,6 +288,30 @@ __device__ __forceinline__ double stage_scaled(const double* __restrict__ d_g, c
     return sc;
 }
 
+// Same staging for the eigenvector kernel, which wants the off-diagonal itself (sign) next to the diagonal:
+// de[i] = (d_i, e_{i-1}) scaled (e_{-1} = 0); 16 bytes per site instead of 24 leaves room for more work rows.
+__device__ __forceinline__ double stage_scaled_de(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
+                                                  double2* de) {
+    __shared__ double s_hi[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) de[i] = make_double2(d_g[i], i ? e_g[i - 1] : 0.0);
+    __syncthreads();
+    double tn = 0.0;
+    for (int i = threadIdx.x; i < S; i += blockDim.x)
+        tn = fmax(tn, fabs(de[i].x) + fabs(de[i].y) + (i + 1 < S ? fabs(de[i + 1].y) : 0.0));
+    tn = warp_max(tn);
+    if (lane == 0) s_hi[warp] = tn;
+    __syncthreads();
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tn = fmax(tn, s_hi[w]);
+    const double sc = pow2_scale(tn);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        de[i].x *= sc;
+        de[i].y *= sc;
+    }
+    __syncthreads();
+    return sc;
+}
+
 __global__ void __launch_bounds__(LP_THREADS)
 tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restrict__ e_g, int S,
                            const double* __restrict__ cut_states, const int* __restrict__ n_states, int max_states,
@@ -437,24 +461,27 @@ tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__
                       const int* __restrict__ n_states, int max_states, const double* __restrict__ evals,
                       double* __restrict__ evecs) {
     extern __shared__ double2 sm2[];
-    double2* de = sm2;
-    double* e = reinterpret_cast<double*>(sm2 + S);
+    double2* de = sm2;                                           // (d_i, e_{i-1}), scaled
     const int mat = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* w = e + S + (size_t)warp * S;                        // this warp's work row: D+ -> rho -> vector
+    double* w = reinterpret_cast<double*>(sm2 + S) + (size_t)warp * S;   // this warp's work row: D+ -> rho -> vector
     const int k = blockIdx.x * WARPS + warp;
     const int nb = min(n_states[mat], max_states);
     if (blockIdx.x * WARPS >= nb) return;
-    double glo, tnorm;
-    const double sc = stage_scaled(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de, e, glo, tnorm);
+    const double sc = stage_scaled_de(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de);
     if (k >= nb) return;
+    auto e = [&](int i) { return de[i + 1].y; };                 // e_i couples sites i and i + 1
     const double pivmin = DBL_MIN * 4.0;
     const double lam = evals[(size_t)mat * max_states + k] * sc;
     // contiguous pieces of odd length: lane-strided shared-memory accesses then hit distinct banks
     const int per = ((S + 31) >> 5) | 1;
     const int j0 = min(S, lane * per), j1 = min(S, j0 + per);
-    auto fwd = [&](int j) { return make_double2(de[j].x - lam, de[j].y); };
-    auto bwd = [&](int j) { const int i = S - 1 - j; return make_double2(de[i].x - lam, i + 1 < S ? de[i + 1].y : 0.0); };
+    auto fwd = [&](int j) { const double2 v = de[j]; return make_double2(v.x - lam, v.y * v.y); };
+    auto bwd = [&](int j) {
+        const int i = S - 1 - j;
+        const double ee = i + 1 < S ? de[i + 1].y : 0.0;
+        return make_double2(de[i].x - lam, ee * ee);
+    };
     double p1, p0;
     piece_incoming(j0, j1, lane, fwd, p1, p0);
     piece_pivots(j0, j1, p1, p0, pivmin, fwd, [&](int j, double q) { w[j] = q; });
@@ -484,10 +511,10 @@ tridiag_eigvec_kernel(const double* __restrict__ d_g, const double* __restrict__
     __syncwarp();
     // link ratios in place: below the twist rho_i = -e_i / D+_i (z_i = rho_i z_{i+1}); from the twist upwards
     // rho_i = -e_i / D-_{i+1} (z_{i+1} = rho_i z_i), the backward pivots being recomputed from the saved incoming pair
-    for (int i = lane; i < r; i += 32) w[i] = -(e[i] / w[i]);
+    for (int i = lane; i < r; i += 32) w[i] = -(e(i) / w[i]);
     piece_pivots(j0, j1, b1, b0, pivmin, bwd, [&](int j, double q) {
         const int i = S - 1 - j;
-        if (i - 1 >= r) w[i - 1] = -(e[i - 1] / q);
+        if (i - 1 >= r) w[i - 1] = -(e(i - 1) / q);
     });
     __syncwarp();
     // running products away from the twist: per-lane pieces, a warp scan of the piece totals, and the piece sums of
@@ -750,6 +777,7 @@ int launch_eig(const double* d, const double* e, int S, int n_mat, const double*
     if (!attr_set) {
         TX_CUDA(cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TX_CUDA(cudaFuncSetAttribute(tridiag_eigval_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         TX_CUDA(cudaFuncSetAttribute(tridiag_eigvec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -771,16 +799,20 @@ int launch_eig(const double* d, const double* e, int S, int n_mat, const double*
     TX_CUDA(cudaGetLastError());
     count_launch();
     if (evecs) {
-        // (d, e^2), e and one work row per warp in shared memory: 4 warps while 56 S bytes fit, else 1 (S <= 6400)
+        // (d, e) and one work row per warp in shared memory: 16 S + 8 S per warp bytes.  Six warps per CTA while two
+        // CTAs fit an SM (12 warps/SM), else four, else one (S <= 8533)
         (void)scratch;
-        if ((size_t)56 * S <= 200 * 1024) {
+        if ((size_t)64 * S <= 110 * 1024) {
+            dim3 grid((max_states + 5) / 6, n_mat);
+            tridiag_eigvec_kernel<6><<<grid, 192, (size_t)64 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
+        } else if ((size_t)48 * S <= 200 * 1024) {
             dim3 grid((max_states + 3) / 4, n_mat);
-            tridiag_eigvec_kernel<4><<<grid, 128, (size_t)56 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
-        } else if ((size_t)32 * S <= 200 * 1024) {
+            tridiag_eigvec_kernel<4><<<grid, 128, (size_t)48 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
+        } else if ((size_t)24 * S <= 200 * 1024) {
             dim3 grid(max_states, n_mat);
-            tridiag_eigvec_kernel<1><<<grid, 32, (size_t)32 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
+            tridiag_eigvec_kernel<1><<<grid, 32, (size_t)24 * S, st>>>(d, e, S, n_states, max_states, evals, evecs);
         } else {
-            return fail(TX_ERR_UNSUPPORTED, "chain length S=%d exceeds the eigenvector kernel's shared-memory limit (6400)", S);
+            return fail(TX_ERR_UNSUPPORTED, "chain length S=%d exceeds the eigenvector kernel's shared-memory limit (8533)", S);
         }
         TX_CUDA(cudaGetLastError());
         count_launch();
