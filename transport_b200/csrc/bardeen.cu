@@ -325,17 +325,40 @@ tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restr
     if (blockIdx.x * LP_THREADS >= nb) return;
     double glo, tnorm;
     const double sc = stage_scaled(d_g + (size_t)mat * S, e_g + (size_t)mat * (S - 1), S, de, e, glo, tnorm);
-    if (k >= nb) return;
     const double pivmin = DBL_MIN * 4.0;
     double lo = glo - 2.0 * DBL_EPSILON * S - 2.0 * pivmin;
     double hi = fmin(fmax(cut_states[mat], -4.0 * tnorm / sc), 4.0 * tnorm / sc) * sc;
+    int c_lo = 0, c_hi = n_states[mat];
+    double m_lo = 0.0, m_hi = 0.0;
+    int E_lo = 0, E_hi = 0, side = 0;
+    // First pass, cooperative: the CTA's 128 threads probe 128 equispaced shifts of [lo, hi]; every eigenvalue then
+    // starts from the probe interval that contains it (7 bisections' worth for the price of one count, and most
+    // intervals already isolate their eigenvalue, so interpolation starts at once).
+    {
+        __shared__ double s_px[LP_THREADS], s_pm[LP_THREADS];
+        __shared__ int s_pc[LP_THREADS], s_pE[LP_THREADS];
+        const double x = lo + (hi - lo) * ((threadIdx.x + 1) * (1.0 / (LP_THREADS + 1)));
+        double m;
+        int E;
+        s_pc[threadIdx.x] = sturm_count_f(S, x, [&](int i) { return de[i]; }, m, E);
+        s_px[threadIdx.x] = x;
+        s_pm[threadIdx.x] = m;
+        s_pE[threadIdx.x] = E;
+        __syncthreads();
+        if (k >= nb) return;
+        int t = 0;
+        while (t < LP_THREADS && s_pc[t] <= k) ++t;              // first probe above eigenvalue k
+        if (t < LP_THREADS) {
+            hi = s_px[t]; c_hi = s_pc[t]; m_hi = s_pm[t]; E_hi = s_pE[t];
+        }
+        if (t > 0) {
+            lo = s_px[t - 1]; c_lo = s_pc[t - 1]; m_lo = s_pm[t - 1]; E_lo = s_pE[t - 1];
+        }
+    }
     // Bracketing by Sturm counts (rigorous), the next shift by interpolation once the bracket isolates the eigenvalue:
     // count(hi) - count(lo) == 1 means det(T - x) changes sign exactly once inside, and the Illinois variant of
     // regula falsi on the last minor converges superlinearly (21-33 counts per eigenvalue instead of 53 bisections).
     // Every fourth step is a bisection, so the bracket halves at least that often whatever the minor's rounding does.
-    int c_lo = 0, c_hi = n_states[mat];
-    double m_lo = 0.0, m_hi = 0.0;
-    int E_lo = 0, E_hi = 0, side = 0;
     for (int it = 0; it < 1100; ++it) {                          // c_lo = count(lo) <= k < count(hi) = c_hi
         if (hi - lo <= DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin) break;
         const double mid = lo + 0.5 * (hi - lo);
