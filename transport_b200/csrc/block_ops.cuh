@@ -347,6 +347,32 @@ __device__ inline void cta_inverse(cd* A, int n, cd* colk, int* ipiv, int* singu
     __syncthreads();
 }
 
+// X[k][perm[c]] <- X[perm[k]][c] in place on an n x n block in shared memory (n * n <= 9 * blockDim.x): every thread
+// reads its entries, barrier, writes them to their destinations.  Not inlined: the nine staged entries must not add to
+// the register pressure of the kernels that call the inverse (they are capped at 128 registers for two CTAs per SM).
+static __device__ __noinline__ void unpermute_in_place(cd* X, int n, const int* perm) {
+    constexpr int MAXE = 9;
+    cd v[MAXE];
+#pragma unroll
+    for (int u = 0; u < MAXE; ++u) {
+        const int idx = threadIdx.x + u * blockDim.x;
+        if (idx < n * n) {
+            const int k = idx / n, c = idx - k * n;
+            v[u] = X[perm[k] * n + c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < MAXE; ++u) {
+        const int idx = threadIdx.x + u * blockDim.x;
+        if (idx < n * n) {
+            const int k = idx / n, c = idx - k * n;
+            X[k * n + perm[c]] = v[u];
+        }
+    }
+    __syncthreads();
+}
+
 // 1/z with the reciprocal of |z|^2 from MUFU.RCP64H + two Newton steps (~1 ulp, no IEEE slow path): the reciprocal
 // sits on the critical path of every elimination step of the blocked inverse.
 __device__ __forceinline__ cd crecip_fast(cd z) {
@@ -493,26 +519,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
     }
     // undo the implicit row permutation while copying out:  X[k][perm[c]] = S[perm[k]][c]
     if (in_place) {
-        constexpr int MAXE = 9;                        // 48 * 48 / 256
-        cd v[MAXE];
-#pragma unroll
-        for (int u = 0; u < MAXE; ++u) {
-            const int idx = threadIdx.x + u * blockDim.x;
-            if (idx < n * n) {
-                const int k = idx / n, c = idx - k * n;
-                v[u] = S[s_perm[k] * ld + c];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < MAXE; ++u) {
-            const int idx = threadIdx.x + u * blockDim.x;
-            if (idx < n * n) {
-                const int k = idx / n, c = idx - k * n;
-                X[k * n + s_perm[c]] = v[u];
-            }
-        }
-        __syncthreads();
+        unpermute_in_place(X, n, s_perm);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
