@@ -291,7 +291,7 @@ def kernel_well(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR
     cutL = np.array([cut - 2 * np.real(tLa)])
     cutR = np.array([cut - 2 * np.real(tRa)])
     # the reference averages over ALL right-well states inside the window (:127-151), also above the cutoff
-    cutR_states = np.array([np.inf]) if np.isnan(interval) else cutR + abs(interval)
+    cutR_states = np.array([np.inf]) if np.isnan(interval) else np.maximum(cutR, cutL) + abs(interval)
     r = wells_batched(dL[None], eL[None], dR[None], eR[None], cutL[None], cutR_states[None], cutR[None],
                       hd[0][None], hd[1][None], hd[2][None], interval, sign_fix=True)
     mu_cut, nu_cut = int(r["nL"][0, 0]), int(r["nR_below"][0, 0])
