@@ -16,7 +16,8 @@ __device__ __forceinline__ cd ld_op(const cd* A, int n, int r, int c, int op) {
 }
 
 // C = op(A) * op(B)            (C must not alias A or B)
-__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate);
+__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
+                                     double cscale = 1.0);
 
 __device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n) {
     if ((n & 7) == 0 && n >= 16) {
@@ -50,7 +51,8 @@ __device__ __forceinline__ void dmma844(double (&d)[2], double a, double b) {
 // operand pointers are formed once per strip and advanced by constants, the k loop is fully unrolled, so the address
 // arithmetic that makes up a third of the generic routine's instructions disappears.
 template <int N>
-__device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, double sgn, bool accumulate) {
+__device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, double sgn, bool accumulate,
+                                        double cscale) {
     constexpr int NT = 4;
     constexpr int TILES = N / 8;
     constexpr int STRIPS = (TILES + NT - 1) / NT;
@@ -101,8 +103,8 @@ __device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const c
                 cd v = mk(sgn * re[u][i], sgn * im[u][i]);
                 if (accumulate) {
                     const cd c0 = pc[u * 8 + i];
-                    v.x += c0.x;
-                    v.y += c0.y;
+                    v.x = fma(cscale, c0.x, v.x);
+                    v.y = fma(cscale, c0.y, v.y);
                 }
                 pc[u * 8 + i] = v;
             }
@@ -115,9 +117,10 @@ __device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const c
 // A warp works on a strip of up to four 8x8 output tiles of one tile row: the A fragment of a k-step is loaded
 // once and reused for the four column tiles (16 DMMA per 5 fragment loads), and the loads of the next k-step are
 // issued before the DMMAs of the current one (operands usually sit in L2/L1, not in shared memory).
-__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate) {
+__device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
+                                     double cscale) {
     if (n == 64 && opA == OP_N && opB == OP_N) {
-        cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate);
+        cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate, cscale);
         return;
     }
     constexpr int NT = 4;
@@ -167,8 +170,8 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
                     cd v = mk(sgn * re[u][i], sgn * im[u][i]);
                     if (accumulate) {
                         const cd c0 = C[idx];
-                        v.x += c0.x;
-                        v.y += c0.y;
+                        v.x = fma(cscale, c0.x, v.x);
+                        v.y = fma(cscale, c0.y, v.y);
                     }
                     C[idx] = v;
                 }
@@ -178,10 +181,10 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
     __syncthreads();
 }
 
-// C += sgn * op(A) * op(B)
-__device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn) {
+// C = cscale * C + sgn * op(A) * op(B)
+__device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, double cscale = 1.0) {
     if ((n & 7) == 0 && n >= 16) {
-        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true);
+        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true, cscale);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -193,8 +196,8 @@ __device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, in
             cfma(ar, ai, a.x, a.y, b.x, b.y);
         }
         cd v = C[idx];
-        v.x = fma(sgn, ar, v.x);
-        v.y = fma(sgn, ai, v.y);
+        v.x = fma(sgn, ar, cscale * v.x);
+        v.y = fma(sgn, ai, cscale * v.y);
         C[idx] = v;
     }
     __syncthreads();

@@ -127,17 +127,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 --j;
                 ++k;
                 build_z(tmp, j);
-                // prev <- -kap * prev  (prev = I for the second site of a chunk)
+                // D_j = z_j D_{j+1} - kap D_{j+2}: the scaling of D_{j+2} rides on the product's epilogue
                 if (prev_is_identity) {
                     for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
                         const int r = idx / n, c = idx - r * n;
                         prev[idx] = mk(r == c ? -kap : 0.0, 0.0);
                     }
                     __syncthreads();
+                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0);
                 } else {
-                    for_each4(prev, [&](int idx) { return prev[idx]; }, [&](int, cd v) { return mk(-kap * v.x, -kap * v.y); });
+                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap);
                 }
-                cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0);           // D_j = z_j D_{j+1} - kap D_{j+2}
                 cd* sw = prev;
                 prev = cur;
                 cur = sw;
