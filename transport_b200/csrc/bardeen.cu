@@ -367,13 +367,17 @@ tridiag_eigval_lane_kernel(const double* __restrict__ d_g, const double* __restr
         if (c_hi - c_lo == 1 && m_lo != 0.0 && m_hi != 0.0 && (it & 3) != 3) {
             const int dE = max(-1000, min(1000, E_hi - E_lo));
             const double ratio = ldexp(m_hi / m_lo, dE);         // f(hi) / f(lo) < 0
-            const double xi = lo + (hi - lo) / (1.0 - ratio);
-            if (ratio < 0.0 && xi > lo && xi < hi) {
-                // step over the estimate, away from the nearer end, by 2 % of the distance to it (at least half the
-                // tolerance): regula falsi alone closes in from one side and leaves the other end of the bracket behind
+            if (ratio < 0.0) {
+                // The estimate is clamped into the bracket, not rejected, when it rounds onto an end (|f| at that end
+                // is ~0: the end IS the root to working precision) — the probe just inside that end then closes the
+                // bracket at once, where rejecting it would leave one-sided bisection (43 counts instead of 20).
+                // Then step over the estimate, away from the nearer end, by 2 % of the distance to it (at least half
+                // the tolerance): regula falsi alone closes in from one side and leaves the other end behind.
+                const double xi = fmin(fmax(lo + (hi - lo) / (1.0 - ratio), lo), hi);
                 const double tol = DBL_EPSILON * (fabs(lo) + fabs(hi)) + DBL_EPSILON * 1e-3 * tnorm + 2.0 * pivmin;
                 const double dl = xi - lo, dh = hi - xi;
-                x = dl < dh ? fmin(xi + fmax(0.02 * dl, 0.5 * tol), mid) : fmax(xi - fmax(0.02 * dh, 0.5 * tol), mid);
+                const double xs = dl < dh ? fmin(xi + fmax(0.02 * dl, 0.5 * tol), mid) : fmax(xi - fmax(0.02 * dh, 0.5 * tol), mid);
+                if (xs > lo && xs < hi) x = xs;
             }
         }
         double m;
