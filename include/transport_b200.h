@@ -65,6 +65,25 @@ int tx_device_count(void);                 /* number of CUDA devices, 0 if none 
 int tx_set_device(int device);
 int tx_device_synchronize(void);
 
+/* ---- contexts: reentrancy and stream selection (SURVEY.md §8b "threading / reentrancy") ---------------
+ * The reference is synchronous and reentrant (plain Python functions, no global state).  Here everything a
+ * sweep call needs besides its arguments lives in a tx_context: the device workspace of the host-pointer
+ * entries, the scratch of the device-pointer entries (expanded affine families, site classes), the CUDA
+ * stream the work is issued on and the tuning options.  Calls on ONE context are serialised (a host mutex;
+ * reuse of its scratch by a later call on another stream is ordered by an event); calls on DISTINCT contexts
+ * are independent, so host threads / streams that want concurrency create one context each.
+ * Entry points without a context argument (and a NULL context) use a per-device default context, i.e. they
+ * are thread-safe but serialised per device.
+ *   tx_context_set_stream: use_stream != 0 -> the host-pointer entries issue their copies and kernels on
+ *       `stream` (a cudaStream_t; NULL = the legacy default stream) and synchronise that stream before they
+ *       return; use_stream == 0 (default) -> a context-owned non-blocking stream.
+ *   tx_context_set_option: per-context copy of tx_set_option (options 0, 1, 2, 4).                     */
+typedef struct tx_context tx_context;
+int tx_context_create(int device, tx_context** out);
+int tx_context_destroy(tx_context* ctx);
+int tx_context_set_stream(tx_context* ctx, void* stream, int use_stream);
+int tx_context_set_option(tx_context* ctx, int option, int value);
+
 /* ---- the hot path: batched T(E) sweep -------------------------------------------------- */
 /*
  * Replaces, for every (Hamiltonian p, energy e) point and every source, one call of
@@ -125,6 +144,36 @@ int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1
                                     const double* sources, int n_src,
                                     double* R, double* T, double* resid, double* t_total, double* caroli,
                                     tx_cplx* workspace, int* singular_flag, void* stream);
+/*
+ * The same sweeps with the spin-resolved channel sums fused into the K3 epilogue — the reduction the reference's
+ * drivers do on the host after wfm.kernel (run_wfm_gate.py:404-405,473-477: the n_loc_dof channels split at
+ * n_mol_dof into electron spin up / down) — and with every output array optional, so that a sweep that only
+ * needs compact results moves 16-128 bytes per point instead of 16 n n_src:
+ *   ctx      context or NULL (per-device default context)
+ *   n_up     channels [0, n_up) carry electron spin up, [n_up, n) spin down
+ *   spin_n   2 or 4
+ *   spin     [n_ham][nE][n_src][spin_n] doubles or NULL:
+ *              [0] sum of T over the channels of the source's own spin sector     (no spin flip)
+ *              [1] sum of T over the other sector                                 (spin flip)
+ *              [2], [3] the same for R                                            (spin_n == 4 only)
+ *            A source's sector is the one holding the larger share of its incident weight sum_c A_c^2 (a one-hot
+ *            source: its own channel's sector).
+ *   R, T     may both be NULL (no per-channel arrays are allocated, written or copied); at least one output array
+ *            must be given.
+ * tx_transmission_sweep / tx_transmission_sweep_dev are these with ctx = NULL and spin = NULL.
+ */
+int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                               const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE,
+                               int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                               const double* sources, const int* src_idx, int n_src, double* R, double* T,
+                               double* resid, double* t_total, double* caroli, int n_up, int spin_n, double* spin);
+int tx_transmission_sweep_spin_dev(tx_context* ctx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                                   const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE,
+                                   int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                                   const double* sources, const int* src_idx, int n_src, double* R, double* T,
+                                   double* resid, double* t_total, int n_up, int spin_n, double* spin,
+                                   int* singular_flag, void* stream);
+
 /* Elements (tx_cplx) of `workspace` the large-block sweep needs for n_pts points (0 if it fits in
  * shared memory). */
 long long tx_sweep_workspace_elems(int n, long long n_pts);
@@ -246,19 +295,7 @@ int tx_bardeen_current_dev(const double* E, const double* M2, int P, int n, int 
 int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double* tL, const double* VL, const double* tR,
                   const double* VR, int NL, int NR, double* T, int* flags);
 
-/* Tuning knob for the 5 <= n <= 8, scalar-hopping sweep (bench.py --variant):
- *   13   DEFAULT: telescoped sweep (rgf_n8t.cuh): register-resident DMMA recurrence, one inverse per chunk
- *        of up to kmax sites, diagonal sites as column scalings; eight energies of one Hamiltonian per warp
- *        (energy axes shorter than 64 that are not a multiple of eight fall back to variant 6)
- *   6/7  plain sweep, one inverse per site, tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh),
- *        3 CTAs/SM, smem / shuffle pivot row;   8  as 6 with 2 CTAs/SM and no register cap;   9  as 8 with the
- *        eight products of a warp issued back to back;   10  as 9 with 3 CTAs/SM;   11, 12  timing experiments
- *        that skip the products / the inversion (WRONG results, measurement only)
- *   0/1  register-resident products (rgf_small.cuh), 4 lanes/point, 168 / 250 registers
- *   2/3  same, 8 lanes/point;   4/5  same as 1/0 with the pivot row moved by register shuffles
- * All variants compute the same thing. */
-int tx_set_variant(int variant);
-/* Library options.
+/* Process-wide defaults of the tuning options (contexts created later inherit them; the default contexts follow them).
  *   option 0: value != 0 (default) enables the structure scan of the on-site blocks: diagonal sites take the
  *             column-scaling step of the telescoped sweep (the plain sweep uses it for its diagonal right tail
  *             and scalar runs); value 0 treats every site as a general block (A/B measurements).
@@ -266,7 +303,15 @@ int tx_set_variant(int variant);
  *   option 2: log2 of the growth bound that closes a chunk early, 0..500 (default 4: max |D_j| / prod |t| < 32).
  *   option 3: eigenvalue kernel of the Bardeen path: 0 (default) picks by batch size, 1 a warp per eigenvalue
  *             (multisection, shortest critical path), 2 a lane per eigenvalue (bracketed interpolation, least arithmetic; chosen
- *             automatically from 2048 state slots per call). */
+ *             automatically from 2048 state slots per call).  Process-wide only.
+ *   option 4: kernel of the 5 <= n <= 8, scalar-hopping sweep (= tx_set_variant):
+ *             13  DEFAULT: telescoped sweep (rgf_n8t.cuh): register-resident DMMA recurrence, one inverse per chunk
+ *                 of up to kmax sites, diagonal sites as column scalings; eight energies of one Hamiltonian per warp
+ *                 (energy axes shorter than 64 that are not a multiple of eight fall back to 6)
+ *              6  plain sweep, one inverse per site, tensor-core (DMMA) products, W in shared memory (rgf_n8.cuh)
+ *              0  register-resident products (rgf_small.cuh), 4 lanes per point — the kernel general hopping uses
+ *             All three compute the same thing (test_all_kernel_variants_agree). */
+int tx_set_variant(int variant);
 int tx_set_option(int option, int value);
 
 /* Unit-test hook: out[b] = inverse(in[b]) for `count` n x n blocks (n <= 16) using the device

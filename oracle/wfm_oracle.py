@@ -322,3 +322,24 @@ def kernel_loops(h, tnn, tnnn, tl, E, converger, Ajsigma, is_psi_jsigma, is_Rhat
     """`kernel` with the reference's Python loop nests kept (the CPU-baseline "port")."""
     return kernel(h, tnn, tnnn, tl, E, converger, Ajsigma, is_psi_jsigma, is_Rhat,
                   all_debug=all_debug, verbose=verbose, _loops=True)
+
+
+# ----------------------------------------------------------------------------------------
+# spin-resolved sums of the drivers  (run_wfm_gate.py:404-405, :473-477)
+# ----------------------------------------------------------------------------------------
+def spin_flip_sums(X, n_elec_up=None, sources=None):
+    """Sums of a per-channel probability array X[..., n_src, n] (T or R) over the electron-spin sectors the
+    drivers split the channels into (`np.array(range(n_loc_dof)) < n_mol_dof`, run_wfm_gate.py:473-477):
+    channels [:n_elec_up] carry electron spin up (default n//2).  Returns (same, other) [..., n_src]: the weight
+    leaving in the source's own sector / in the other one.  A source's sector is the one holding the larger share
+    of its incident weight (`sources` [n_src, n]; default: one-hot sources in channel order)."""
+    n = X.shape[-1]
+    half = n // 2 if n_elec_up is None else n_elec_up
+    up = X[..., :half].sum(-1)
+    dn = X[..., half:].sum(-1)
+    if sources is None:
+        src_up = np.arange(X.shape[-2]) < half
+    else:
+        A2 = np.asarray(sources, dtype=float) ** 2
+        src_up = A2[:, :half].sum(-1) >= A2[:, half:].sum(-1)
+    return np.where(src_up, up, dn), np.where(src_up, dn, up)

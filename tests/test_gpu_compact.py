@@ -1,0 +1,150 @@
+"""GPU parity tests of the compact outputs and the context API (run with -m gpu on a B200).
+
+The spin-resolved sums the reference's drivers form on the host from wfm.kernel's per-channel arrays
+(run_wfm_gate.py:404-405,473-477) are produced by the device epilogue; they must equal the same sums taken
+over the reference's golden R/T, for every kernel family (n <= 4 register kernel, n = 8 telescoped / plain /
+register-resident, 8 < n <= 16, CTA-per-point kernel for n > 16), with and without the per-channel arrays.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rt_err
+from oracle import rgf_oracle
+from oracle.wfm_oracle import spin_flip_sums
+from transport_b200 import _lib, configs
+from transport_b200.sweep import Context, transmission_sweep
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a GPU box")
+
+
+def _want_spin(R, T, n_up=None, sources=None, spin_n=4):
+    tn, tf = spin_flip_sums(T, n_up, sources)
+    if spin_n == 2:
+        return np.stack([tn, tf], axis=-1)
+    rn, rf = spin_flip_sums(R, n_up, sources)
+    return np.stack([tn, tf, rn, rf], axis=-1)
+
+
+def _close(got, want, tol=1e-10):
+    scale = np.maximum(np.abs(want), 1e-13 * np.abs(want).max(axis=-1, keepdims=True))
+    assert np.max(np.abs(got - want) / np.where(scale == 0, 1, scale)) < tol
+
+
+@pytest.mark.parametrize("variant", [13, 6, 0])
+def test_spin_sums_cfg2_golden_all_kernels(variant):
+    """cfg2 golden (the reference's own R/T): spin sums with and without the per-channel arrays."""
+    lib = _lib.load()
+    g = load_golden("cfg2_cicc.npz")
+    want4 = _want_spin(g["R"], g["T"])
+    try:
+        _lib.check(lib.tx_set_variant(variant))
+        R, T, spin = transmission_sweep(g["h"], g["tnn"], g["Es"], want_spin=4)
+        assert rt_err(T, g["T"]) < 1e-10 and rt_err(R, g["R"]) < 1e-10
+        _close(spin, want4)
+        # the device sums are the sums of the device's own channels, to round-off
+        assert np.allclose(spin, _want_spin(R, T), rtol=1e-13, atol=1e-300)
+        # compact: no R/T at all; T pair only
+        tot, spin2 = transmission_sweep(g["h"], g["tnn"], g["Es"], want_rt=False, want_total=True, want_spin=2)
+        _close(spin2, want4[..., :2])
+        assert np.array_equal(spin2, spin[..., :2])
+        assert np.allclose(tot, g["T"].sum(axis=(2, 3)), rtol=1e-10)
+        only = transmission_sweep(g["h"], g["tnn"], g["Es"], want_rt=False, want_spin=4)
+        assert np.array_equal(only, spin)
+        # a different sector boundary and explicit (non one-hot) source vectors
+        srcs = np.array([[1.0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0.6, 0.8, 0], [0.5, 0.5, 0, 0, 0, 0, 0.1, 0]])
+        R3, T3, spin3 = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=srcs, want_spin=4, n_elec_up=2)
+        assert np.allclose(spin3, _want_spin(R3, T3, 2, srcs), rtol=1e-13, atol=1e-300)
+    finally:
+        _lib.check(lib.tx_set_variant(13))
+
+
+@pytest.mark.parametrize("name", ["kondo_n2.npz", "general_hop_n4.npz", "general_hop_n6.npz", "general_hop_n12.npz",
+                                  "general_hop_n16.npz", "cfg3_disorder_N30.npz", "cicc_spin1_n18.npz",
+                                  "cicc_spin32_n32.npz"])
+def test_spin_sums_other_block_sizes(name):
+    g = load_golden(name)
+    n = g["h"].shape[-1]
+    srcs = g["sources"] if "sources" in g.files else np.eye(n)
+    if name.startswith("cicc_spin1_"):
+        srcs = np.eye(18)[[0, 7]]
+    gR, gT = g["R"], g["T"]
+    R, T, spin = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=srcs, want_spin=4)
+    assert rt_err(T[0], gT) < 1e-10 and rt_err(R[0], gR) < 1e-10
+    _close(spin[0], _want_spin(gR, gT, None, srcs))
+    spin_only = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=srcs, want_rt=False, want_spin=4)
+    assert np.array_equal(spin_only, spin)
+
+
+def test_spin_sums_large_blocks_n64():
+    n, M = 64, 4
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((M, n, n)) + 1j * rng.standard_normal((M, n, n))
+    h = 0.2 * (A + np.conj(np.swapaxes(A, 1, 2))) / 2
+    h[0] = 0
+    h[-1] = np.diag(0.02 * rng.standard_normal(n))
+    tnn = -np.tile(np.eye(n, dtype=complex), (M - 1, 1, 1))
+    Es = np.array([-1.1, 0.4], dtype=complex)
+    srcs = np.eye(n)[[3, 40]]
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, srcs)
+    spin = transmission_sweep(h, tnn, Es, sources=srcs, want_rt=False, want_spin=4, n_elec_up=24)
+    _close(spin[0], _want_spin(oR, oT, 24, srcs))
+
+
+def test_compact_full_size_cfg2_matches_full_outputs():
+    """Size-independent property at BASELINE's full cfg2 size: the compact sweep (no R/T arrays) gives bit-identical
+    sums to the full sweep's epilogue, and they add up to the per-point total and to unitarity."""
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    Js, Es = configs.cfg2_grid(1000, 1000)
+    tot, spin = transmission_sweep(h0, tnn, Es, h1=h1, params=Js, want_rt=False, want_total=True, want_spin=4)
+    assert spin.shape == (1000, 1000, 8, 4) and np.isfinite(spin).all()
+    assert np.max(np.abs(spin.sum(-1) - 1.0)) < 1e-10                       # R + T = 1 per source
+    assert np.allclose(tot, spin[..., :2].sum(axis=(2, 3)), rtol=1e-12)
+    g = load_golden("cfg2_cicc.npz")
+    want = _want_spin(g["R"], g["T"])
+    for k, jidx in enumerate([0, 250, 500, 750, 999]):
+        _close(spin[jidx, ::40], want[k])
+
+
+def test_contexts_run_concurrently_from_threads():
+    """Two host threads, one context each (own workspace, own stream): same bits as the default context."""
+    g = load_golden("cfg2_cicc.npz")
+    R0, T0 = transmission_sweep(g["h"], g["tnn"], g["Es"])
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    Js, Es = configs.cfg2_grid(64, 256)
+    Ra, Ta = transmission_sweep(h0, tnn, Es, h1=h1, params=Js)
+    out, errs = {}, []
+
+    def work(key, reps):
+        try:
+            with Context(0) as cx:
+                for _ in range(reps):
+                    if key == "a":
+                        out[key] = transmission_sweep(h0, tnn, Es, h1=h1, params=Js, context=cx)
+                    else:
+                        out[key] = transmission_sweep(g["h"], g["tnn"], g["Es"], context=cx)
+        except Exception as exc:      # surfaced below
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=("a", 6)), threading.Thread(target=work, args=("b", 40))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert np.array_equal(out["a"][0], Ra) and np.array_equal(out["a"][1], Ta)
+    assert np.array_equal(out["b"][0], R0) and np.array_equal(out["b"][1], T0)
+    # per-context options do not leak into the default context
+    with Context(0) as cx:
+        cx.set_option(4, 6)
+        R6, T6 = transmission_sweep(g["h"], g["tnn"], g["Es"], context=cx)
+    assert rt_err(T6, T0) < 1e-11
+    R1, T1 = transmission_sweep(g["h"], g["tnn"], g["Es"])
+    assert np.array_equal(T1, T0)

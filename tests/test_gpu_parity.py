@@ -68,10 +68,14 @@ def test_cicc_spot_value_through_reference_signature():
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
                                         if os.path.basename(p).startswith(("general_hop", "cfg3_", "nondiag",
-                                                                           "kondo_n2.npz"))))
+                                                                           "kondo_n2.npz", "cicc_spin"))))
 def test_closed_lead_goldens(name):
+    """Every closed-form-lead golden of the live reference, through the C ABI; cicc_spin1 (n = 18) and cicc_spin32
+    (n = 32) pin the CTA-per-point large-block kernel to the reference itself."""
     g = load_golden(name)
     srcs = g["sources"] if "sources" in g.files else np.eye(g["h"].shape[-1])
+    if name.startswith("cicc_spin1_"):
+        srcs = np.eye(18)[[0, 7]]
     R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], sources=srcs, want_resid=True)
     _check(R[0], T[0], g["R"], g["T"], res if not name.startswith("nondiag") else None)
 
@@ -412,12 +416,12 @@ def test_ribbon_sancho_leads_cfg4_downscaled():
 
 
 def test_all_kernel_variants_agree():
-    """Every tuning variant of the n=8 sweep (register-resident, shuffle pivot, DMMA) gives the golden answer;
+    """Every kernel of the n=8 sweep (register-resident, plain DMMA, telescoped) gives the golden answer;
     the DMMA kernel is also exercised with padding (n=5..7), table leads and mixed Hamiltonians per warp."""
     lib = _lib.load()
     g = load_golden("cfg2_cicc.npz")
     try:
-        for v in list(range(11)) + [13]:
+        for v in (0, 6, 13):
             _lib.check(lib.tx_set_variant(v))
             R, T, res = transmission_sweep(g["h"], g["tnn"], g["Es"], want_resid=True)
             _check(R, T, g["R"], g["T"], res)

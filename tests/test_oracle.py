@@ -66,12 +66,12 @@ def test_cicc_spot_value_from_survey():
 
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                                        if os.path.basename(p).startswith(("general_hop", "cfg3_", "cicc_spin1",
+                                        if os.path.basename(p).startswith(("general_hop", "cfg3_", "cicc_spin",
                                                                            "nondiag", "kondo_n2.npz"))))
 def test_closed_lead_goldens_dense_and_rgf(name):
     g = load_golden(name)
     srcs = g["sources"] if "sources" in g.files else np.eye(g["h"].shape[-1])[:g["R"].shape[1]]
-    if name.startswith("cicc_spin1"):
+    if name.startswith("cicc_spin1_"):
         srcs = [np.eye(18)[0], np.eye(18)[7]]
     R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], "g_closed", srcs)
     assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL

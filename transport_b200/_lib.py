@@ -48,6 +48,16 @@ _SIGNATURES = {
     "tx_sweep_workspace_elems": (ctypes.c_longlong, [c_int, ctypes.c_longlong]),
     "tx_transmission_sweep_dev": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
                                           c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "tx_transmission_sweep_spin": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
+                                           c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P,
+                                           c_int, c_int, _P]),
+    "tx_transmission_sweep_spin_dev": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int,
+                                               c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P,
+                                               c_int, c_int, _P, _P, _P]),
+    "tx_context_create": (c_int, [c_int, _P]),
+    "tx_context_destroy": (c_int, [_P]),
+    "tx_context_set_stream": (c_int, [_P, _P, c_int]),
+    "tx_context_set_option": (c_int, [_P, c_int, c_int]),
     "tx_surface_gf": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
                               _P, _P, _P, _P, _P]),
     "tx_surface_gf_dev": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,

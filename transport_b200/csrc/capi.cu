@@ -31,7 +31,7 @@ void count_launch(int n) { g_launches += n; }
 
 namespace {
 
-// ---- grow-only device workspace for the host-pointer entry points ------------------------
+// ---- grow-only device buffer ---------------------------------------------------------------
 struct DevBuf {
     void* ptr = nullptr;
     size_t cap = 0;
@@ -46,16 +46,64 @@ struct DevBuf {
         cap = want;
         return TX_OK;
     }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
 };
-struct Workspace {
-    DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, caroli, big, flag;
-    cudaStream_t stream = nullptr;
+
+// Tuning state (tx_set_variant / tx_set_option set the process defaults; a context carries its own copy).
+struct Options {
+    int variant = 13;       // 13 telescoped sweep, 6 plain sweep (DMMA products), 0 register-resident template
+    int chunk_kmax = 32;    // longest telescoped chunk of rgf_sweep_n8t
+    int chunk_gexp = 4;     // log2 of the growth bound that closes a chunk early
+    bool diag_tail = true;  // structure scan of the on-site blocks
+};
+Options g_default_opts;
+
+}  // namespace
+
+// A context owns everything a sweep call needs besides its arguments: the device workspace of the host-pointer
+// entry, the scratch of the device-pointer entry (expanded affine families, site classes), streams, events and
+// the tuning options.  Calls on one context are serialised (host mutex; scratch reuse is ordered across streams
+// by an event); calls on distinct contexts are independent, so threads / streams that want concurrency create
+// their own.  Entry points without a context argument use the per-device default context.
+struct tx_context {
+    int device = 0;
+    std::mutex mu;
+    Options opt;
+    DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, caroli, spin, big, flag;
+    DevBuf expand, nondiag;
+    cudaStream_t own_stream = nullptr;    // created on first use
+    cudaStream_t user_stream = nullptr;   // tx_context_set_stream
+    bool has_user_stream = false;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    int device = -1;
+    cudaEvent_t scratch_ev = nullptr;     // recorded after the last kernels that read expand / nondiag
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
+    bool follows_defaults = false;        // default contexts track tx_set_variant / tx_set_option
 };
-std::mutex g_ws_mutex;
-Workspace g_ws[16];
+
+namespace {
+
+std::mutex g_ctx_mutex;
+tx_context* g_default_ctx[16] = {nullptr};
+
+int default_context(tx_context** out) {
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    tx_context*& c = g_default_ctx[dev & 15];
+    if (!c) {
+        c = new tx_context();
+        c->device = dev;
+        c->follows_defaults = true;
+    }
+    *out = c;
+    return TX_OK;
+}
 
 int round_up_block(int n) {
     if (n <= 1) return 1;
@@ -65,12 +113,6 @@ int round_up_block(int n) {
     if (n <= 16) return 16;
     return 0;
 }
-
-// Tuning variant of the n<=8 scalar-hopping kernel (tx_set_variant): lanes per point and the
-// number of resident 128-thread blocks per SM the register allocation is capped for.
-int g_variant = 13;
-int g_chunk_kmax = 32;   // tx_set_option(1, ...): longest telescoped chunk of rgf_sweep_n8t
-int g_chunk_gexp = 4;    // tx_set_option(2, ...): log2 of the growth bound that closes a chunk early
 
 template <int N, int LP, int HOP, int LEAD, int MINB, int PIVX = 0>
 int launch_small(const SweepParams& p, cudaStream_t st) {
@@ -94,21 +136,14 @@ int launch_small(const SweepParams& p, cudaStream_t st) {
     return TX_OK;
 }
 
-// grow-only per-device buffer for expanded affine Hamiltonian families (tx_transmission_sweep_dev)
-DevBuf g_expand[16];
-DevBuf g_nondiag[16];
-bool g_diag_tail = true;    // tx_set_option(0, ...): sweep the diagonal right tail per channel
-
-// h0 + J*h1 families are expanded once into a grow-only per-device buffer (8 KB per Hamiltonian at n = M = 8).
-int materialise_affine(SweepParams& p, cudaStream_t st) {
+// h0 + J*h1 families are expanded once into the context's grow-only buffer (8 KB per Hamiltonian at n = M = 8).
+int materialise_affine(tx_context& cx, SweepParams& p, cudaStream_t st) {
     if (!p.h1) return TX_OK;
-    int devid = 0;
-    TX_CUDA(cudaGetDevice(&devid));
     const long long per_ham = (long long)p.M * p.n * p.n;
     const long long n_ham = p.n_pts / p.nE;
     const long long total = per_ham * n_ham;
-    DevBuf& buf = g_expand[devid & 15];
-    if ((size_t)total * sizeof(cd) > buf.cap) TX_CUDA(cudaStreamSynchronize(st));   // a regrow frees the old buffer
+    DevBuf& buf = cx.expand;
+    if ((size_t)total * sizeof(cd) > buf.cap) TX_CUDA(cudaDeviceSynchronize());   // a regrow frees the old buffer
     int rc = buf.ensure((size_t)total * sizeof(cd));
     if (rc) return rc;
     affine_expand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, p.params, (cd*)buf.ptr, per_ham, total);
@@ -118,32 +153,32 @@ int materialise_affine(SweepParams& p, cudaStream_t st) {
     p.h_stride = per_ham;
     p.h1 = nullptr;
     p.params = nullptr;
+    cx.scratch_used = true;
     return TX_OK;
 }
 
-// Structure scan of the on-site blocks (nondiag_scan_kernel): per Hamiltonian the last non-diagonal site and
-// per site a class (2 scalar multiple of I, 1 diagonal, 0 general).  Must run before materialise_affine.
-int scan_structure(SweepParams& p, cudaStream_t st, bool want_tail) {
-    int devid = 0;
-    TX_CUDA(cudaGetDevice(&devid));
+// Structure scan of the on-site blocks (structure_scan_kernel): per Hamiltonian the last non-diagonal site and
+// per site a class (2 scalar multiple of I, 1 diagonal, 0 general), plus the batch-wide count of diagonal interior
+// sites.  Must run before materialise_affine.
+int scan_structure(tx_context& cx, SweepParams& p, cudaStream_t st, bool want_tail) {
     const int n_hs = (p.h_stride == 0) ? 1 : (int)(p.n_pts / p.nE);
-    DevBuf& nb = g_nondiag[devid & 15];
+    DevBuf& nb = cx.nondiag;
     const size_t need = ((size_t)n_hs * (1 + (size_t)p.M) + 1) * sizeof(int);
-    if (need > nb.cap) TX_CUDA(cudaStreamSynchronize(st));
+    if (need > nb.cap) TX_CUDA(cudaDeviceSynchronize());
     int rc = nb.ensure(need);
     if (rc) return rc;
     int* nd = (int*)nb.ptr;
     int* cl = nd + n_hs;
-    TX_CUDA(cudaMemsetAsync(nd, 0xFF, (size_t)n_hs * sizeof(int), st));     // -1
     const long long ncl = (long long)n_hs * p.M;
-    fill_int_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, 2, ncl);
-    const long long total = (long long)n_hs * p.M * p.n;
-    nondiag_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, nd, cl);
     int* cnt = cl + ncl;
+    // cnt = 0 and nd = -1 are set by one memset each; the classes are written (not accumulated) by the scan
+    TX_CUDA(cudaMemsetAsync(nd, 0xFF, (size_t)n_hs * sizeof(int), st));
     TX_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
-    class_count_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, st>>>(cl, ncl, p.M, cnt);
+    // one warp per (Hamiltonian, site)
+    const long long warps = ncl;
+    structure_scan_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(p.h, p.h1, n_hs, p.M, p.n, nd, cl, cnt);
     TX_CUDA(cudaGetLastError());
-    count_launch(3);
+    count_launch(1);
     p.class_count = cnt;
     p.class_sites = (long long)n_hs * (p.M > 2 ? p.M - 2 : 0);
     if (want_tail) {
@@ -152,72 +187,77 @@ int scan_structure(SweepParams& p, cudaStream_t st, bool want_tail) {
     }
     p.site_class = cl;
     p.class_stride = (p.h_stride == 0) ? 0 : p.M;
+    cx.scratch_used = true;
     return TX_OK;
 }
 
-// Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.
+// Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.  Persistent grid: as many CTAs
+// as are resident on the device, each warp striding over its items.
 template <int LEAD, int MINB, bool FULL, bool DIAG>
-int launch_n8t_inst(const SweepParams& p, cudaStream_t st) {
+int launch_n8t_inst(const tx_context& cx, const SweepParams& p, cudaStream_t st) {
     constexpr int WARPS = 4;
     const size_t smem = (size_t)WARPS * N8TCfg::PER_WARP_BYTES;
-    static bool attr_done[16] = {false};
+    static int resident[16] = {0};
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 15]) {
+    if (!resident[dev & 15]) {
         TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[dev & 15] = true;
+        int per_sm = 0, sms = 0;
+        TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgf_sweep_n8t<LEAD, MINB, FULL, DIAG>, WARPS * 32, smem));
+        TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        resident[dev & 15] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     // a warp = eight consecutive energies of one Hamiltonian (energy axis padded to a multiple of eight)
     const int warps_per_ham = (p.nE + 7) / 8;
     const long long n_warps = (p.n_pts / p.nE) * warps_per_ham;
-    const long long blocks = (n_warps + WARPS - 1) / WARPS;
-    if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8t<LEAD, MINB, FULL, DIAG><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, g_chunk_kmax, 2 * g_chunk_gexp, warps_per_ham, n_warps);
+    long long blocks = (n_warps + WARPS - 1) / WARPS;
+    if (blocks > resident[dev & 15]) blocks = resident[dev & 15];
+    rgf_sweep_n8t<LEAD, MINB, FULL, DIAG><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, cx.opt.chunk_kmax, 2 * cx.opt.chunk_gexp, warps_per_ham, n_warps);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }
 
 template <int LEAD, int MINB, bool FULL>
-int launch_n8t_full(SweepParams p, cudaStream_t st) {
+int launch_n8t_full(tx_context& cx, SweepParams p, cudaStream_t st) {
     p.nondiag_max = nullptr;
     p.site_class = nullptr;
     p.class_stride = 0;
     p.class_count = nullptr;
     p.class_sites = 0;
-    if (g_diag_tail) {
-        int rc = scan_structure(p, st, false);
+    if (cx.opt.diag_tail) {
+        int rc = scan_structure(cx, p, st, false);
         if (rc) return rc;
     }
     {
-        int rc = materialise_affine(p, st);
+        int rc = materialise_affine(cx, p, st);
         if (rc) return rc;
     }
-    if (!g_diag_tail) return launch_n8t_inst<LEAD, MINB, FULL, false>(p, st);
-    // both instantiations; each returns at once unless the device-side site statistics select it
-    int rc = launch_n8t_inst<LEAD, MINB, FULL, true>(p, st);
+    if (!cx.opt.diag_tail) return launch_n8t_inst<LEAD, MINB, FULL, false>(cx, p, st);
+    // both instantiations; the one the device-side site statistics do not select returns at once
+    int rc = launch_n8t_inst<LEAD, MINB, FULL, true>(cx, p, st);
     if (rc) return rc;
-    return launch_n8t_inst<LEAD, MINB, FULL, false>(p, st);
+    return launch_n8t_inst<LEAD, MINB, FULL, false>(cx, p, st);
 }
 
 template <int LEAD, int MINB>
-int launch_n8t(const SweepParams& p, cudaStream_t st) {
-    return p.n == 8 ? launch_n8t_full<LEAD, MINB, true>(p, st) : launch_n8t_full<LEAD, MINB, false>(p, st);
+int launch_n8t(tx_context& cx, const SweepParams& p, cudaStream_t st) {
+    return p.n == 8 ? launch_n8t_full<LEAD, MINB, true>(cx, p, st) : launch_n8t_full<LEAD, MINB, false>(cx, p, st);
 }
 
-template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
-int launch_n8(SweepParams p, cudaStream_t st) {
+template <int LEAD, int MINB, int PIVX, int DMB = 1>
+int launch_n8(tx_context& cx, SweepParams p, cudaStream_t st) {
     constexpr int WARPS = 4;
     p.nondiag_max = nullptr;
     p.nondiag_stride = 0;
     p.site_class = nullptr;
     p.class_stride = 0;
-    if (g_diag_tail) {
-        int rc = scan_structure(p, st, LEAD == LEAD_CLOSED);
+    if (cx.opt.diag_tail) {
+        int rc = scan_structure(cx, p, st, LEAD == LEAD_CLOSED);
         if (rc) return rc;
     }
     {
-        int rc = materialise_affine(p, st);
+        int rc = materialise_affine(cx, p, st);
         if (rc) return rc;
     }
     const size_t smem = (size_t)WARPS * N8Cfg::PER_WARP_BYTES;
@@ -225,13 +265,13 @@ int launch_n8(SweepParams p, cudaStream_t st) {
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8<LEAD, MINB, PIVX, DMB, EXPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8<LEAD, MINB, PIVX, DMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = true;
     }
     const long long per_block = (long long)WARPS * 8;
     const long long blocks = (p.n_pts + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_n8<LEAD, MINB, PIVX, DMB, EXPER><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+    rgf_sweep_n8<LEAD, MINB, PIVX, DMB><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
@@ -249,11 +289,27 @@ int dispatch_modes(const SweepParams& p, int hop, int lead, cudaStream_t st) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Output arrays of a sweep (any may be null; R and T go together).
+struct SweepOut {
+    double *R, *T, *resid, *t_total, *caroli, *spin;
+    int n_up, spin_n;
+};
+
+int check_spin(const SweepOut& o, int n) {
+    if ((o.R == nullptr) != (o.T == nullptr)) return fail(TX_ERR_ARG, "R and T must be given together (or both NULL)");
+    if (o.spin) {
+        if (o.spin_n != 2 && o.spin_n != 4) return fail(TX_ERR_ARG, "spin_n must be 2 or 4");
+        if (o.n_up < 0 || o.n_up > n) return fail(TX_ERR_ARG, "n_up=%d outside 0..n", o.n_up);
+    }
+    if (!o.R && !o.resid && !o.t_total && !o.caroli && !o.spin) return fail(TX_ERR_ARG, "no output array given");
+    return TX_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char* tx_version(void) { return "transport_b200 0.1 (sm_100a)"; }
+const char* tx_version(void) { return "transport_b200 0.2 (sm_100a)"; }
 const char* tx_last_error(void) { return g_err; }
 
 int tx_device_count(void) {
@@ -277,29 +333,87 @@ int tx_device_synchronize(void) {
 
 long long tx_launch_counter(void) { return g_launches.load(); }
 
-int tx_set_option(int option, int value) {
+static int set_option_on(Options& o, int option, int value) {
     if (option == 0) {
-        g_diag_tail = value != 0;
+        o.diag_tail = value != 0;
         return TX_OK;
     }
     if (option == 1) {
         if (value < 1 || value > 64) return fail(TX_ERR_ARG, "chunk length must be 1..64");
-        g_chunk_kmax = value;
+        o.chunk_kmax = value;
         return TX_OK;
     }
     if (option == 2) {
         if (value < 0 || value > 500) return fail(TX_ERR_ARG, "growth exponent must be 0..500");
-        g_chunk_gexp = value;
+        o.chunk_gexp = value;
         return TX_OK;
     }
-    if (option == 3) return set_eig_mode(value);
+    if (option == 4) {
+        if (value != 0 && value != 6 && value != 13) return fail(TX_ERR_ARG, "variant must be 13, 6 or 0");
+        o.variant = value;
+        return TX_OK;
+    }
     return fail(TX_ERR_ARG, "unknown option %d", option);
 }
 
-int tx_set_variant(int v) {
-    if (v < 0 || v > 15) return fail(TX_ERR_ARG, "variant must be 0..15");
-    g_variant = v;
+int tx_set_option(int option, int value) {
+    if (option == 3) return set_eig_mode(value);
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    return set_option_on(g_default_opts, option, value);
+}
+
+int tx_set_variant(int v) { return tx_set_option(4, v); }
+
+int tx_context_create(int device, tx_context** out) {
+    if (!out) return fail(TX_ERR_ARG, "null pointer argument");
+    int ndev = tx_device_count();
+    if (ndev < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TX_ERR_ARG, "device %d outside 0..%d", device, ndev - 1);
+    tx_context* c = new tx_context();
+    c->device = device;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        c->opt = g_default_opts;
+    }
+    *out = c;
     return TX_OK;
+}
+
+int tx_context_destroy(tx_context* c) {
+    if (!c) return TX_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->scratch_ev) cudaEventSynchronize(c->scratch_ev);
+    DevBuf* bufs[] = {&c->h, &c->h1, &c->par, &c->tnn, &c->E, &c->sigL, &c->sigR, &c->src, &c->R, &c->T, &c->resid,
+                      &c->ttot, &c->caroli, &c->spin, &c->big, &c->flag, &c->expand, &c->nondiag};
+    for (DevBuf* b : bufs) b->release();
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->scratch_ev) cudaEventDestroy(c->scratch_ev);
+    cudaSetDevice(prev);
+    delete c;
+    return TX_OK;
+}
+
+int tx_context_set_stream(tx_context* c, void* stream, int use_stream) {
+    if (!c) return fail(TX_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->user_stream = reinterpret_cast<cudaStream_t>(stream);
+    c->has_user_stream = use_stream != 0;
+    return TX_OK;
+}
+
+int tx_context_set_option(tx_context* c, int option, int value) {
+    if (!c) return fail(TX_ERR_ARG, "null context");
+    if (option == 3) return fail(TX_ERR_ARG, "option 3 (eigenvalue kernel) is process-wide: use tx_set_option");
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->follows_defaults = false;
+    return set_option_on(c->opt, option, value);
 }
 
 // Unit-test hook: batched inverse of n x n blocks with the sweep's own device routine (host pointers).
@@ -329,7 +443,7 @@ int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n) {
         case 1: rc = go(invert_batch_small<1, 1>, 1, 1); break;
         case 2: rc = go(invert_batch_small<2, 1>, 2, 1); break;
         case 4: rc = go(invert_batch_small<4, 2>, 4, 2); break;
-        case 8: rc = go(g_variant >= 2 ? invert_batch_small<8, 8> : invert_batch_small<8, 4>, 8, g_variant >= 2 ? 8 : 4); break;
+        case 8: rc = go(invert_batch_small<8, 4>, 8, 4); break;
         case 16: rc = go(invert_batch_small<16, 16>, 16, 16); break;
     }
     if (rc == TX_OK) {
@@ -346,28 +460,31 @@ int tx_sweep_launch_count(int n, int M, int hop_mode) {
     (void)M;
     const int N = round_up_block(n);
     if (N == 0) return 0;
-    // 5 <= n <= 8 with scalar hopping: structure scan (fill, scan, count) + the two instantiations of the
-    // telescoped sweep (one of them returns at once); an affine family adds its expansion kernel
-    if (N == 8 && hop_mode == TX_HOP_SCALAR) return g_diag_tail ? 5 : 1;
+    // 5 <= n <= 8 with scalar hopping: structure scan + the two instantiations of the telescoped sweep (one of
+    // them returns at once); an affine family adds its expansion kernel
+    if (N == 8 && hop_mode == TX_HOP_SCALAR) return g_default_opts.diag_tail ? 3 : 1;
     return 1;
 }
 
-int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
-                              const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
-                              const tx_cplx* E, int nE,
-                              int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
-                              int hop_mode,
-                              const double* sources, const int* src_idx, int n_src,
-                              double* R, double* T, double* resid, double* t_total,
-                              int* singular_flag, void* stream) {
-    if (!h || !tnn || !E || !R || !T || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
+}  // extern "C"
+
+namespace {
+
+// Argument checks of the device-pointer sweep (run before any CUDA call, so that bad arguments are reported as
+// such even without a device).
+int check_small_args(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE, int lead_mode,
+                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode, const double* sources, int n_src,
+                    const SweepOut& o, const int* singular_flag) {
+    if (!h || !tnn || !E || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
     if (n < 1 || M < 2 || n_ham < 1 || nE < 1 || n_src < 1)
         return fail(TX_ERR_ARG, "bad sizes n=%d M=%d n_ham=%d nE=%d n_src=%d", n, M, n_ham, nE, n_src);
     if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham))
         return fail(TX_ERR_ARG, "n_h/n_t must be 1 or n_ham");
     if (h1 && !params) return fail(TX_ERR_ARG, "h1 given without params");
-    if (src_idx) return fail(TX_ERR_ARG, "src_idx is resolved by the host entry point; pass sources to the device entry");
     if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
+    if (int rc = check_spin(o, n)) return rc;
+    if (o.caroli) return fail(TX_ERR_ARG, "caroli is produced by the large-block sweep only");
     if (lead_mode == TX_LEAD_TABLE) {
         if (!sigL || !sigR) return fail(TX_ERR_ARG, "TX_LEAD_TABLE needs sigL and sigR");
         if (!(n_sig == 1 || n_sig == n_ham)) return fail(TX_ERR_ARG, "n_sig must be 1 or n_ham");
@@ -377,9 +494,25 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     if (!aligned16(h) || !aligned16(tnn) || !aligned16(E) || (h1 && !aligned16(h1)) ||
         (sigL && !aligned16(sigL)) || (sigR && !aligned16(sigR)))
         return fail(TX_ERR_ARG, "complex arrays must be 16-byte aligned");
-    if (!aligned16(R) || !aligned16(T)) return fail(TX_ERR_ARG, "R and T must be 16-byte aligned");
+    if (!aligned16(o.R) || !aligned16(o.T) || !aligned16(o.spin)) return fail(TX_ERR_ARG, "R, T and spin must be 16-byte aligned");
     const int N = round_up_block(n);
     if (N == 0) return fail(TX_ERR_UNSUPPORTED, "block size n=%d > 16 not covered by the small-block sweep", n);
+    return TX_OK;
+}
+
+// Device-pointer sweep for n <= 16 on stream `st`; the caller holds cx.mu.
+int sweep_small_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE, int lead_mode,
+                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode, const double* sources, int n_src,
+                    const SweepOut& o, int* singular_flag, cudaStream_t st) {
+    if (int rc = check_small_args(h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR, n_sig, hop_mode,
+                                  sources, n_src, o, singular_flag))
+        return rc;
+    const int N = round_up_block(n);
+    if (cx.follows_defaults) {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        cx.opt = g_default_opts;
+    }
 
     SweepParams p;
     p.h = reinterpret_cast<const cd*>(h);
@@ -393,10 +526,13 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
     p.sigR = reinterpret_cast<const cd*>(sigR);
     p.sig_stride = (n_sig == 1) ? 0 : (long long)nE * n * n;
     p.sources = sources;
-    p.R = R;
-    p.T = T;
-    p.resid = resid;
-    p.ttot = t_total;
+    p.R = o.R;
+    p.T = o.T;
+    p.resid = o.resid;
+    p.ttot = o.t_total;
+    p.spin = o.spin;
+    p.n_up = o.n_up;
+    p.spin_n = o.spin_n;
     p.singular = singular_flag;
     p.nondiag_max = nullptr;
     p.nondiag_stride = 0;
@@ -412,61 +548,53 @@ int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, cons
 
     const int hop = (hop_mode == TX_HOP_SCALAR) ? HOP_SCALAR : HOP_GENERAL;
     const int lead = (lead_mode == TX_LEAD_TABLE) ? LEAD_TABLE : LEAD_CLOSED;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the context's scratch (expanded Hamiltonians, site classes) may still be read by kernels of an earlier call
+    // on another stream: order this call behind them
+    if (cx.scratch_used && cx.scratch_stream != st && cx.scratch_ev) TX_CUDA(cudaStreamWaitEvent(st, cx.scratch_ev, 0));
+    cx.scratch_used = false;
+    int rc = TX_ERR_UNSUPPORTED;
     switch (N) {
-        case 1: return dispatch_modes<1, 1, 4, 4>(p, hop, lead, st);
-        case 2: return dispatch_modes<2, 1, 4, 4>(p, hop, lead, st);
-        case 4: return dispatch_modes<4, 2, 3, 3>(p, hop, lead, st);
+        case 1: rc = dispatch_modes<1, 1, 4, 4>(p, hop, lead, st); break;
+        case 2: rc = dispatch_modes<2, 1, 4, 4>(p, hop, lead, st); break;
+        case 4: rc = dispatch_modes<4, 2, 3, 3>(p, hop, lead, st); break;
         case 8:
-            if (hop == HOP_SCALAR) {
-                // default: tensor-core (DMMA) product kernel, rgf_n8.cuh; variants 0-5 keep the
-                // register-resident template reachable for A/B measurements (bench.py --variant)
-                // telescoped sweep (default); its warps take eight energies of one Hamiltonian, so very short
-                // energy axes that are not a multiple of eight go to the point-per-4-lanes kernel instead
-                if (g_variant >= 13 && (nE >= 64 || nE % 8 == 0)) {
-                    if (lead == LEAD_TABLE) return launch_n8t<LEAD_TABLE, 2>(p, st);
-                    return launch_n8t<LEAD_CLOSED, 2>(p, st);
-                }
-                if (lead == LEAD_TABLE) return launch_n8<LEAD_TABLE, 3, 0>(p, st);
-                switch (g_variant) {
-                    case 0: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
-                    case 1: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2>(p, st);
-                    case 2: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 3>(p, st);
-                    case 3: return launch_small<8, 8, HOP_SCALAR, LEAD_CLOSED, 4>(p, st);
-                    case 4: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 2, 1>(p, st);
-                    case 5: return launch_small<8, 4, HOP_SCALAR, LEAD_CLOSED, 3, 1>(p, st);
-                    case 6: case 13: case 14: case 15: return launch_n8<LEAD_CLOSED, 3, 0>(p, st);   // plain sweep
-                    case 7: return launch_n8<LEAD_CLOSED, 3, 1>(p, st);
-                    case 10: return launch_n8<LEAD_CLOSED, 3, 0, 8>(p, st);
-                    case 11: return launch_n8<LEAD_CLOSED, 2, 0, 1, 1>(p, st);   // timing experiment: no products (wrong results)
-                    case 12: return launch_n8<LEAD_CLOSED, 2, 0, 1, 2>(p, st);   // timing experiment: no inversion (wrong results)
-                    case 8: return launch_n8<LEAD_CLOSED, 2, 0>(p, st);
-                    default: return launch_n8<LEAD_CLOSED, 2, 0, 8>(p, st);   // 9
-                }
+            if (hop == HOP_SCALAR && cx.opt.variant != 0) {
+                // default: telescoped sweep; its warps take eight energies of one Hamiltonian, so very short energy
+                // axes that are not a multiple of eight go to the plain sweep (one point per four lanes) instead
+                if (cx.opt.variant == 13 && (nE >= 64 || nE % 8 == 0))
+                    rc = (lead == LEAD_TABLE) ? launch_n8t<LEAD_TABLE, 2>(cx, p, st) : launch_n8t<LEAD_CLOSED, 2>(cx, p, st);
+                else
+                    rc = (lead == LEAD_TABLE) ? launch_n8<LEAD_TABLE, 3, 0>(cx, p, st) : launch_n8<LEAD_CLOSED, 3, 0>(cx, p, st);
+            } else {
+                rc = dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
             }
-            return dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
-        case 16: return dispatch_modes<16, 16, 3, 2>(p, hop, lead, st);
+            break;
+        case 16: rc = dispatch_modes<16, 16, 3, 2>(p, hop, lead, st); break;
     }
-    return fail(TX_ERR_UNSUPPORTED, "unreachable");
+    if (rc == TX_OK && cx.scratch_used) {
+        if (!cx.scratch_ev) TX_CUDA(cudaEventCreateWithFlags(&cx.scratch_ev, cudaEventDisableTiming));
+        TX_CUDA(cudaEventRecord(cx.scratch_ev, st));
+        cx.scratch_stream = st;
+    }
+    return rc;
 }
 
-long long tx_sweep_workspace_elems(int n, long long n_pts) { return (long long)rgf_generic_workspace_elems(n, n_pts); }
-
-int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
-                                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
-                                    const tx_cplx* E, int nE,
-                                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
-                                    const double* sources, int n_src,
-                                    double* R, double* T, double* resid, double* t_total, double* caroli,
-                                    tx_cplx* workspace, int* singular_flag, void* stream) {
+int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params, const tx_cplx* tnn,
+                    int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE, const tx_cplx* sigL, const tx_cplx* sigR,
+                    int n_sig, int hop_mode, const double* sources, int n_src, const SweepOut& o, tx_cplx* workspace,
+                    int* singular_flag, cudaStream_t st) {
     if (!h || !tnn || !E || !sigL || !sigR || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
     if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..64", n);
     if (M < 2 || n_ham < 1 || nE < 1 || n_src < 1) return fail(TX_ERR_ARG, "bad sizes");
     if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham) || !(n_sig == 1 || n_sig == n_ham))
         return fail(TX_ERR_ARG, "n_h/n_t/n_sig must be 1 or n_ham");
-    if ((R == nullptr) != (T == nullptr)) return fail(TX_ERR_ARG, "R and T must be given together");
     if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
     if (h1 && !params) return fail(TX_ERR_ARG, "h1 given without params");
+    if (int rc = check_spin(o, n)) return rc;
+    if (cx.follows_defaults) {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        cx.opt = g_default_opts;
+    }
     GenericParams p{};
     p.h = reinterpret_cast<const cd*>(h);
     p.h_stride = (n_h == 1) ? 0 : (long long)M * n * n;
@@ -479,11 +607,14 @@ int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1
     p.sigR = reinterpret_cast<const cd*>(sigR);
     p.sig_stride = (n_sig == 1) ? 0 : (long long)nE * n * n;
     p.sources = sources;
-    p.R = R;
-    p.T = T;
-    p.resid = resid;
-    p.ttot = t_total;
-    p.caroli = caroli;
+    p.R = o.R;
+    p.T = o.T;
+    p.resid = o.resid;
+    p.ttot = o.t_total;
+    p.caroli = o.caroli;
+    p.spin = o.spin;
+    p.n_up = o.n_up;
+    p.spin_n = o.spin_n;
     p.work = reinterpret_cast<cd*>(workspace);
     p.singular = singular_flag;
     p.n_pts = (long long)n_ham * nE;
@@ -492,24 +623,86 @@ int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1
     p.nE = nE;
     p.n_src = n_src;
     p.hop_scalar = (hop_mode == TX_HOP_SCALAR) ? 1 : 0;
-    p.kmax = g_chunk_kmax;
-    p.gexp = g_chunk_gexp;
-    return launch_rgf_generic(p, reinterpret_cast<cudaStream_t>(stream));
+    p.kmax = cx.opt.chunk_kmax;
+    p.gexp = cx.opt.chunk_gexp;
+    return launch_rgf_generic(p, st);
 }
 
-int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
-                          const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
-                          const tx_cplx* E, int nE,
-                          int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
-                          int hop_mode,
-                          const double* sources, const int* src_idx, int n_src,
-                          double* R, double* T, double* resid, double* t_total, double* caroli) {
-    if (!h || !tnn || !E || !R || !T) return fail(TX_ERR_ARG, "null pointer argument");
+int resolve_context(tx_context* ctx, tx_context** out) {
+    if (ctx) {
+        *out = ctx;
+        return TX_OK;
+    }
+    return default_context(out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tx_transmission_sweep_spin_dev(tx_context* ctx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                                   const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE,
+                                   int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                                   const double* sources, const int* src_idx, int n_src, double* R, double* T,
+                                   double* resid, double* t_total, int n_up, int spin_n, double* spin,
+                                   int* singular_flag, void* stream) {
+    if (src_idx) return fail(TX_ERR_ARG, "src_idx is resolved by the host entry point; pass sources to the device entry");
+    const SweepOut o{R, T, resid, t_total, nullptr, spin, n_up, spin_n};
+    if (int rc = check_small_args(h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR, n_sig, hop_mode,
+                                  sources, n_src, o, singular_flag))
+        return rc;
+    tx_context* cx = nullptr;
+    if (int rc = resolve_context(ctx, &cx)) return rc;
+    std::lock_guard<std::mutex> lock(cx->mu);
+    return sweep_small_dev(*cx, h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR, n_sig, hop_mode,
+                           sources, n_src, o, singular_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tx_transmission_sweep_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                              const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                              const tx_cplx* E, int nE,
+                              int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                              int hop_mode,
+                              const double* sources, const int* src_idx, int n_src,
+                              double* R, double* T, double* resid, double* t_total,
+                              int* singular_flag, void* stream) {
+    return tx_transmission_sweep_spin_dev(nullptr, h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR,
+                                          n_sig, hop_mode, sources, src_idx, n_src, R, T, resid, t_total, 0, 0, nullptr,
+                                          singular_flag, stream);
+}
+
+long long tx_sweep_workspace_elems(int n, long long n_pts) { return (long long)rgf_generic_workspace_elems(n, n_pts); }
+
+int tx_transmission_sweep_large_dev(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                                    const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                                    const tx_cplx* E, int nE,
+                                    const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                                    const double* sources, int n_src,
+                                    double* R, double* T, double* resid, double* t_total, double* caroli,
+                                    tx_cplx* workspace, int* singular_flag, void* stream) {
+    tx_context* cx = nullptr;
+    if (int rc = resolve_context(nullptr, &cx)) return rc;
+    std::lock_guard<std::mutex> lock(cx->mu);
+    const SweepOut o{R, T, resid, t_total, caroli, nullptr, 0, 0};
+    return sweep_large_dev(*cx, h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, sigL, sigR, n_sig, hop_mode, sources, n_src,
+                           o, workspace, singular_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                               const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE,
+                               int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode,
+                               const double* sources, const int* src_idx, int n_src, double* R, double* T,
+                               double* resid, double* t_total, double* caroli, int n_up, int spin_n, double* spin) {
+    if (!h || !tnn || !E) return fail(TX_ERR_ARG, "null pointer argument");
     if (n < 1 || M < 2 || n_ham < 1 || nE < 1 || n_src < 1)
         return fail(TX_ERR_ARG, "bad sizes n=%d M=%d n_ham=%d nE=%d n_src=%d", n, M, n_ham, nE, n_src);
     if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham))
         return fail(TX_ERR_ARG, "n_h/n_t must be 1 or n_ham");
     if (sources && src_idx) return fail(TX_ERR_ARG, "give sources or src_idx, not both");
+    {
+        const SweepOut chk{R, T, resid, t_total, caroli, spin, n_up, spin_n};
+        if (int rc = check_spin(chk, n)) return rc;
+    }
     if (tx_device_count() < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
 
     const size_t nn = (size_t)n * n;
@@ -542,12 +735,22 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     }
     if (!sources && n_src != n) return fail(TX_ERR_ARG, "sources == NULL requires n_src == n");
 
-    int dev = 0;
-    TX_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace& ws = g_ws[dev & 15];
-    if (!ws.stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
-    cudaStream_t st = ws.stream;
+    tx_context* cxp = nullptr;
+    if (int rc = resolve_context(ctx, &cxp)) return rc;
+    tx_context& ws = *cxp;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    if (ctx) {
+        int cur = 0;
+        TX_CUDA(cudaGetDevice(&cur));
+        if (cur != ws.device) return fail(TX_ERR_ARG, "context belongs to device %d, current device is %d", ws.device, cur);
+    }
+    cudaStream_t st;
+    if (ws.has_user_stream) {
+        st = ws.user_stream;
+    } else {
+        if (!ws.own_stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.own_stream, cudaStreamNonBlocking));
+        st = ws.own_stream;
+    }
 
     const size_t n_pts = (size_t)n_ham * nE;
     const size_t bytes_h = (size_t)n_h * M * nn * sizeof(tx_cplx);
@@ -556,17 +759,20 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     const size_t bytes_E = (size_t)nE * sizeof(tx_cplx);
     const size_t bytes_sig = (lead_mode == TX_LEAD_TABLE) ? (size_t)n_sig * nE * nn * sizeof(tx_cplx) : 0;
     const size_t bytes_src = sources ? (size_t)n_src * n * sizeof(double) : 0;
-    const size_t bytes_out = n_pts * n_src * n * sizeof(double);
+    const size_t bytes_out = R ? n_pts * n_src * n * sizeof(double) : 0;
     const size_t bytes_res = resid ? n_pts * n_src * sizeof(double) : 0;
+    const size_t bytes_spin = spin ? n_pts * n_src * spin_n * sizeof(double) : 0;
 
     int rc;
     if ((rc = ws.h.ensure(bytes_h)) || (rc = ws.tnn.ensure(bytes_t)) || (rc = ws.E.ensure(bytes_E)) ||
-        (rc = ws.R.ensure(bytes_out)) || (rc = ws.T.ensure(bytes_out)) || (rc = ws.flag.ensure(sizeof(int))))
+        (rc = ws.flag.ensure(sizeof(int))))
         return rc;
+    if (bytes_out && ((rc = ws.R.ensure(bytes_out)) || (rc = ws.T.ensure(bytes_out)))) return rc;
     if (h1 && ((rc = ws.h1.ensure(bytes_h1)) || (rc = ws.par.ensure((size_t)n_ham * sizeof(double))))) return rc;
     if (bytes_sig && ((rc = ws.sigL.ensure(bytes_sig)) || (rc = ws.sigR.ensure(bytes_sig)))) return rc;
     if (bytes_src && (rc = ws.src.ensure(bytes_src))) return rc;
     if (bytes_res && (rc = ws.resid.ensure(bytes_res))) return rc;
+    if (bytes_spin && (rc = ws.spin.ensure(bytes_spin))) return rc;
     if (t_total && (rc = ws.ttot.ensure(n_pts * sizeof(double)))) return rc;
 
     TX_CUDA(cudaMemcpyAsync(ws.h.ptr, h, bytes_h, cudaMemcpyHostToDevice, st));
@@ -590,7 +796,7 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     if (!large) {
         // Chunk the Hamiltonian axis so that the device->host copy of chunk c overlaps the sweep of
         // chunk c+1 (two streams, one event per chunk).  The results dominate the PCIe traffic.
-        const size_t per_ham_out = (size_t)nE * n_src * n * sizeof(double);
+        const size_t per_ham_out = (size_t)nE * n_src * (R ? 2 * n : (spin ? spin_n : 0)) * sizeof(double);
         int n_chunks = 1;
         if (n_ham >= 8 && (size_t)n_ham * per_ham_out > ((size_t)32 << 20)) n_chunks = n_ham >= 64 ? 16 : 4;
         if (!ws.copy_stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.copy_stream, cudaStreamNonBlocking));
@@ -602,27 +808,34 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
             const int np_ = p1 - p0;
             if (np_ <= 0) continue;
             const size_t o_pts = (size_t)p0 * nE;
-            rc = tx_transmission_sweep_dev(
+            const SweepOut o{R ? (double*)ws.R.ptr + o_pts * n_src * n : nullptr, R ? (double*)ws.T.ptr + o_pts * n_src * n : nullptr,
+                             bytes_res ? (double*)ws.resid.ptr + o_pts * n_src : nullptr,
+                             t_total ? (double*)ws.ttot.ptr + o_pts : nullptr, nullptr,
+                             spin ? (double*)ws.spin.ptr + o_pts * n_src * spin_n : nullptr, n_up, spin_n};
+            rc = sweep_small_dev(ws,
                 (const tx_cplx*)ws.h.ptr + (n_h > 1 ? p0 * h_ham : 0), n_h > 1 ? np_ : 1,
                 h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr + p0 : nullptr,
                 (const tx_cplx*)ws.tnn.ptr + (n_t > 1 ? p0 * t_ham : 0), n_t > 1 ? np_ : 1, n, M, np_,
                 (const tx_cplx*)ws.E.ptr, nE, lead_mode,
                 bytes_sig ? (const tx_cplx*)ws.sigL.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr,
                 bytes_sig ? (const tx_cplx*)ws.sigR.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr, n_sig > 1 ? np_ : 1,
-                hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, nullptr, n_src,
-                (double*)ws.R.ptr + o_pts * n_src * n, (double*)ws.T.ptr + o_pts * n_src * n,
-                bytes_res ? (double*)ws.resid.ptr + o_pts * n_src : nullptr,
-                t_total ? (double*)ws.ttot.ptr + o_pts : nullptr, (int*)ws.flag.ptr, st);
+                hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, o, (int*)ws.flag.ptr, st);
             if (rc) return rc;
+            if (n_chunks == 1) break;   // single chunk: the copies below follow on the same stream
             cudaEvent_t ev = ws.ev[c & 1];
             TX_CUDA(cudaEventRecord(ev, st));
             TX_CUDA(cudaStreamWaitEvent(ws.copy_stream, ev, 0));
-            const size_t ob = (size_t)np_ * per_ham_out;
-            TX_CUDA(cudaMemcpyAsync(R + o_pts * n_src * n, (double*)ws.R.ptr + o_pts * n_src * n, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
-            TX_CUDA(cudaMemcpyAsync(T + o_pts * n_src * n, (double*)ws.T.ptr + o_pts * n_src * n, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+            if (R) {
+                const size_t ob = (size_t)np_ * nE * n_src * n * sizeof(double);
+                TX_CUDA(cudaMemcpyAsync(R + o_pts * n_src * n, o.R, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+                TX_CUDA(cudaMemcpyAsync(T + o_pts * n_src * n, o.T, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+            }
+            if (spin)
+                TX_CUDA(cudaMemcpyAsync(spin + o_pts * n_src * spin_n, o.spin, (size_t)np_ * nE * n_src * spin_n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, ws.copy_stream));
+            copied_out = true;
         }
-        TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
-        copied_out = true;
+        if (copied_out) TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
     } else {
         // generic-size path (n <= 64): self-energy tables first (K1), then one CTA per point
         int n_sig_use = n_sig;
@@ -656,21 +869,25 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
         const size_t wse = rgf_generic_workspace_elems(n, (long long)n_pts);
         if (wse && (rc = ws.big.ensure(wse * sizeof(tx_cplx)))) return rc;
         if (caroli && (rc = ws.caroli.ensure(n_pts * sizeof(double)))) return rc;
-        rc = tx_transmission_sweep_large_dev(
-            (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr : nullptr,
-            (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham, (const tx_cplx*)ws.E.ptr, nE,
-            (const tx_cplx*)ws.sigL.ptr, (const tx_cplx*)ws.sigR.ptr, n_sig_use, hop_mode,
-            bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, (double*)ws.R.ptr, (double*)ws.T.ptr,
-            bytes_res ? (double*)ws.resid.ptr : nullptr, t_total ? (double*)ws.ttot.ptr : nullptr,
-            caroli ? (double*)ws.caroli.ptr : nullptr, wse ? (tx_cplx*)ws.big.ptr : nullptr, (int*)ws.flag.ptr, st);
+        const SweepOut o{R ? (double*)ws.R.ptr : nullptr, R ? (double*)ws.T.ptr : nullptr, bytes_res ? (double*)ws.resid.ptr : nullptr,
+                         t_total ? (double*)ws.ttot.ptr : nullptr, caroli ? (double*)ws.caroli.ptr : nullptr,
+                         spin ? (double*)ws.spin.ptr : nullptr, n_up, spin_n};
+        rc = sweep_large_dev(ws, (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr,
+                             h1 ? (const double*)ws.par.ptr : nullptr, (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham,
+                             (const tx_cplx*)ws.E.ptr, nE, (const tx_cplx*)ws.sigL.ptr, (const tx_cplx*)ws.sigR.ptr, n_sig_use,
+                             hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, o,
+                             wse ? (tx_cplx*)ws.big.ptr : nullptr, (int*)ws.flag.ptr, st);
         if (rc) return rc;
         if (caroli) TX_CUDA(cudaMemcpyAsync(caroli, ws.caroli.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
 
     int flag = 0;
     if (!copied_out) {
-        TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
-        TX_CUDA(cudaMemcpyAsync(T, ws.T.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+        if (R) {
+            TX_CUDA(cudaMemcpyAsync(R, ws.R.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+            TX_CUDA(cudaMemcpyAsync(T, ws.T.ptr, bytes_out, cudaMemcpyDeviceToHost, st));
+        }
+        if (spin) TX_CUDA(cudaMemcpyAsync(spin, ws.spin.ptr, bytes_spin, cudaMemcpyDeviceToHost, st));
     }
     if (bytes_res) TX_CUDA(cudaMemcpyAsync(resid, ws.resid.ptr, bytes_res, cudaMemcpyDeviceToHost, st));
     if (t_total) TX_CUDA(cudaMemcpyAsync(t_total, ws.ttot.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -678,6 +895,17 @@ int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const do
     TX_CUDA(cudaStreamSynchronize(st));
     if (flag) return fail(TX_ERR_SINGULAR, "a singular block was met during the sweep (results contain inf/nan there)");
     return TX_OK;
+}
+
+int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
+                          const tx_cplx* tnn, int n_t, int n, int M, int n_ham,
+                          const tx_cplx* E, int nE,
+                          int lead_mode, const tx_cplx* sigL, const tx_cplx* sigR, int n_sig,
+                          int hop_mode,
+                          const double* sources, const int* src_idx, int n_src,
+                          double* R, double* T, double* resid, double* t_total, double* caroli) {
+    return tx_transmission_sweep_spin(nullptr, h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR, n_sig,
+                                      hop_mode, sources, src_idx, n_src, R, T, resid, t_total, caroli, 0, 0, nullptr);
 }
 
 }  // extern "C"

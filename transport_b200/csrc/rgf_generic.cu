@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
     __shared__ cd s_colk[64];
     __shared__ double s_vL[64], s_vR[64];
     __shared__ double s_red[GEN_THREADS / 32];
+    __shared__ double s_red4[4][GEN_THREADS / 32];
     const int n = p.n, M = p.M, nn = n * n;
     const long long pt = blockIdx.x;
     const int ham = (int)(pt / p.nE);
@@ -194,13 +195,16 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
 
     // ---- epilogue: per-channel R/T with the reference's formulas (:108-130)
     double tsum = 0.0;
-    if (p.R || p.ttot || p.resid) {
+    if (p.R || p.ttot || p.resid || p.spin) {
         for (int i = 0; i < p.n_src; ++i) {
-            double f2 = 0.0;
+            double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector
             for (int c = 0; c < n; ++c) {
                 const double a = p.sources ? p.sources[(long long)i * n + c] : (c == i ? 1.0 : 0.0);
                 f2 = fma(a, a * s_vL[c], f2);
+                if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
             }
+            const bool src_up = wu >= wd;
+            double sp[4] = {0.0, 0.0, 0.0, 0.0};               // T same / other sector, R same / other (emit_spin)
             const double rflux = 1.0 / sqrt(f2);
             double part = 0.0;
             for (int s = threadIdx.x; s < n; s += blockDim.x) {
@@ -225,6 +229,26 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 }
                 part += rr + tt;
                 tsum += tt;
+                const bool same = (s < p.n_up) == src_up;
+                sp[0] += same ? tt : 0.0;
+                sp[1] += same ? 0.0 : tt;
+                sp[2] += same ? rr : 0.0;
+                sp[3] += same ? 0.0 : rr;
+            }
+            if (p.spin) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) sp[q] += __shfl_xor_sync(0xffffffffu, sp[q], off);
+                    if ((threadIdx.x & 31) == 0) s_red4[q][threadIdx.x >> 5] = sp[q];
+                }
+                __syncthreads();
+                if (threadIdx.x < p.spin_n) {
+                    double tot = 0.0;
+                    for (int w = 0; w < GEN_THREADS / 32; ++w) tot += s_red4[threadIdx.x][w];
+                    p.spin[(pt * p.n_src + i) * p.spin_n + threadIdx.x] = tot;
+                }
+                __syncthreads();
             }
             if (p.resid) {
 #pragma unroll

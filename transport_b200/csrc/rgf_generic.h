@@ -23,6 +23,8 @@ struct GenericParams {
     double* resid;           // [n_pts][n_src] or null
     double* ttot;            // [n_pts] or null
     double* caroli;          // [n_pts] or null
+    double* spin;            // [n_pts][n_src][spin_n] or null (see emit_spin in rgf_small.cuh)
+    int n_up, spin_n;
     cd* work;                // global workspace or null (then dynamic shared memory)
     int* singular;
     long long n_pts;

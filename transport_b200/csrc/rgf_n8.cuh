@@ -225,7 +225,7 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
     __syncwarp();
 }
 
-template <int LEAD, int MINB, int PIVX, int DMB = 1, int EXPER = 0>
+template <int LEAD, int MINB, int PIVX, int DMB = 1>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     constexpr int N = 8, RP = 2, LP = 4, GPW = 8;
     extern __shared__ double2 smem_all[];
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         int wexp = 0;
         double2 alpha = make_double2(0.0, 0.0), beta = make_double2(1.0, 0.0);   // g_a = alpha I + beta X
         double2 tj = make_double2(0.0, 0.0);
-        if (EXPER == 0 && run_member(j) && run_member(j - 1)) {
+        if (run_member(j) && run_member(j - 1)) {
             is_run = true;
             double2 c = make_double2(1.0, 0.0), d = make_double2(0.0, 0.0);
             double2 cN = make_double2(0.0, 0.0), dN = make_double2(1.0, 0.0);
@@ -562,15 +562,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
         }   // single site
 
         __syncwarp();   // all reads of g_{j+1} (own rows above, fragments below in the previous site) are done
-        if (EXPER == 2) {   // timing experiment only: no inversion, A is scattered as if it were g
-#pragma unroll
-            for (int s = 0; s < RP; ++s)
-#pragma unroll
-                for (int c = 0; c < N; ++c) gt[n8_idx(c, row0 + s)] = A[s][c];
-            __syncwarp();
-        } else {
-            n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular, zmask);
-        }
+        n8_invert<PIVX>(A, PV, gt, grp, row0, p.singular, zmask);
         if (a > 0) fetch_rows(a - 1);
 
         if (j == M - 1 && !is_run) {
@@ -586,7 +578,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 }
             }
             __syncwarp();
-        } else if (EXPER != 1) {
+        } else {
             // W <- conj(t_j) (W g_j): eight DMMA per point, the whole warp on two points at a time
             // (8 independent accumulator chains of length 2 hide the tensor-pipe latency)
             const int fr = lane >> 2, fc = lane & 3;
@@ -710,13 +702,13 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     const int n_src = p.n_src;
     const long long obase = pt * (long long)n_src * n;
     double tsum = 0.0;
-    auto emit = [&](int i, const double (&rr)[RP], const double (&tt)[RP]) {
+    auto emit = [&](int i, bool src_up, const double (&rr)[RP], const double (&tt)[RP]) {
         double sum = 0.0;
         if (full) {
             // n == 8: the two channels of a lane are adjacent -> one 16-byte store per array
             sum = (rr[0] + tt[0]) + (rr[1] + tt[1]);
             tsum += tt[0] + tt[1];
-            if (active) {
+            if (active && p.R) {
                 *reinterpret_cast<double2*>(p.R + obase + (long long)i * N + row0) = make_double2(rr[0], rr[1]);
                 *reinterpret_cast<double2*>(p.T + obase + (long long)i * N + row0) = make_double2(tt[0], tt[1]);
             }
@@ -727,7 +719,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 if (r < n) {
                     sum += rr[s] + tt[s];
                     tsum += tt[s];
-                    if (active) {
+                    if (active && p.R) {
                         p.R[obase + (long long)i * n + r] = rr[s];
                         p.T[obase + (long long)i * n + r] = tt[s];
                     }
@@ -739,6 +731,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             for (int off = LP / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (active && li == 0) p.resid[pt * n_src + i] = sum - 1.0;
         }
+        if (p.spin) emit_spin<RP, LP>(p, pt, i, src_up, active, li, row0, n, rr, tt);
     };
 
     if (p.sources == nullptr) {
@@ -760,13 +753,13 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                     const double yi = (w.x * vL[a]) * ft;
                     tt[s] = fma(yr, yr, yi * yi);
                 }
-                emit(a, rr, tt);
+                emit(a, a < p.n_up, rr, tt);
             }
         }
     } else {
         for (int i = 0; i < n_src; ++i) {
             const double* Asrc = p.sources + (long long)i * n;
-            double f2 = 0.0;
+            double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector (emit_spin)
             double ur[RP], ui[RP], wr[RP], wi[RP], mine[RP];
 #pragma unroll
             for (int s = 0; s < RP; ++s) ur[s] = ui[s] = wr[s] = wi[s] = mine[s] = 0.0;
@@ -776,6 +769,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                     const double a = Asrc[c];
                     const double av = a * vL[c];
                     f2 = fma(a, av, f2);
+                    if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
 #pragma unroll
                     for (int s = 0; s < RP; ++s) {
                         const double2 g = gt[n8_idx(c, row0 + s)];
@@ -800,7 +794,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
                 const double yi = wr[s] * ft;
                 tt[s] = fma(yr, yr, yi * yi);
             }
-            emit(i, rr, tt);
+            emit(i, wu >= wd, rr, tt);
         }
     }
     if (p.ttot) {
@@ -810,44 +804,40 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
     }
 }
 
-// Structure scan of the on-site blocks, one thread per (Hamiltonian, site, row):
-//   nondiag_max[q]   = largest site j whose block has a non-zero off-diagonal element (-1 if none)
-//   site_class[q][j] = 2 scalar multiple of the identity, 1 diagonal, 0 general   (initialised to 2 by the host)
+// Structure scan of the on-site blocks, one warp per (Hamiltonian, site), lanes striding over the n*n elements:
+//   nondiag_max[q]   = largest site j whose block has a non-zero off-diagonal element (host memsets it to -1)
+//   site_class[q][j] = 2 scalar multiple of the identity, 1 diagonal, 0 general   (written, no initialisation needed)
+//   count[0]        += interior sites (0 < j < M-1) whose block is diagonal       (host memsets it to 0)
 // For an affine family h0 + J*h1 both terms must have the structure (independent of J).
-__global__ void nondiag_scan_kernel(const cd* __restrict__ h, const cd* __restrict__ h1, int n_h, int M, int n,
-                                    int* __restrict__ nondiag_max, int* __restrict__ site_class) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n_h * M * n;
-    if (idx >= total) return;
-    const int r = (int)(idx % n);
-    const int j = (int)((idx / n) % M);
-    const int q = (int)(idx / ((long long)n * M));
-    const cd* blk = h + ((long long)q * M + j) * n * n;
+__global__ void structure_scan_kernel(const cd* __restrict__ h, const cd* __restrict__ h1, int n_h, int M, int n,
+                                      int* __restrict__ nondiag_max, int* __restrict__ site_class, int* __restrict__ count) {
+    const long long site = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (site >= (long long)n_h * M) return;
+    const int j = (int)(site % M);
+    const int q = (int)(site / M);
+    const cd* blk = h + site * n * n;
     const cd* blk1 = h1 ? h1 + (long long)j * n * n : nullptr;
-    bool nz = false;
-    for (int c = 0; c < n; ++c) {
-        if (c == r) continue;
-        nz |= (blk[r * n + c].x != 0.0) || (blk[r * n + c].y != 0.0);
-        if (blk1) nz |= (blk1[r * n + c].x != 0.0) || (blk1[r * n + c].y != 0.0);
+    bool nz = false, same = true;
+    for (int i = lane; i < n * n; i += 32) {
+        const int r = i / n, c = i - r * n;
+        const cd v = blk[i];
+        if (r != c) {
+            nz |= (v.x != 0.0) || (v.y != 0.0);
+            if (blk1) nz |= (blk1[i].x != 0.0) || (blk1[i].y != 0.0);
+        } else {
+            same = same && (v.x == blk[0].x) && (v.y == blk[0].y);
+            if (blk1) same = same && (blk1[i].x == blk1[0].x) && (blk1[i].y == blk1[0].y);
+        }
     }
-    bool same = (blk[r * n + r].x == blk[0].x) && (blk[r * n + r].y == blk[0].y);
-    if (blk1) same = same && (blk1[r * n + r].x == blk1[0].x) && (blk1[r * n + r].y == blk1[0].y);
-    if (nz) atomicMax(nondiag_max + q, j);
-    const int cl = nz ? 0 : (same ? 2 : 1);
-    if (cl < 2) atomicMin(site_class + (long long)q * M + j, cl);
-}
-
-// count[0] = number of interior sites (0 < j < M-1) of the batch whose on-site block is diagonal
-__global__ void class_count_kernel(const int* __restrict__ site_class, long long n_sites, int M, int* __restrict__ count) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_sites) return;
-    const int j = (int)(idx % M);
-    if (j > 0 && j < M - 1 && site_class[idx] >= 1) atomicAdd(count, 1);
-}
-
-__global__ void fill_int_kernel(int* __restrict__ dst, int value, long long count) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < count) dst[idx] = value;
+    nz = __any_sync(0xffffffffu, nz);
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) {
+        const int cl = nz ? 0 : (same ? 2 : 1);
+        site_class[site] = cl;
+        if (nz) atomicMax(nondiag_max + q, j);
+        if (cl >= 1 && j > 0 && j < M - 1) atomicAdd(count, 1);
+    }
 }
 
 // out[ham][i] = h0[i] + params[ham] * h1[i]  — materialises an affine Hamiltonian family (8 KB per

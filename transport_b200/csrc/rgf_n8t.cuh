@@ -76,27 +76,36 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     double2* SL = PV + 128;                   // [8 points][8 channels]  E - Sigma_L
     double2* EB = SL + 64;                    // [8]  energies of the eight points
 
-    // A warp owns eight consecutive energies of ONE Hamiltonian (the energy axis is padded to a multiple of
-    // eight per Hamiltonian), so the block fragments of a site are loaded once and shared by the eight points.
-    long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    const bool warp_live = wg < n_warps;
-    if (!warp_live) wg = n_warps - 1;
+    // Two instantiations are launched back to back when the structure scan ran: the one with the diagonal-site
+    // path serves batches where at least 1/8 of the interior sites are diagonal, the lean one the rest (the
+    // decision is taken on the device, no host synchronisation; the grid is persistent, so the idle one is a
+    // few hundred CTAs that return at once).
+    if (p.class_count != nullptr && ((long long)(*p.class_count) * 8 >= p.class_sites) != DIAG) return;
+    const long long nn = (long long)n * n;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
+    // F-role constants
+    const double m0 = (gid == 2 * tid) ? 1.0 : 0.0;        // diagonal masks of the two fragment elements
+    const double m1 = (gid == 2 * tid + 1) ? 1.0 : 0.0;
+    const bool in0 = full || (gid < n && 2 * tid < n);      // element inside the real n x n block?
+    const bool in1 = full || (gid < n && 2 * tid + 1 < n);
+    const int f0i = n8t_idx(gid, 2 * tid), f1i = n8t_idx(gid, 2 * tid + 1);          // own F slots
+    const int x0i = n8t_idx(2 * tid, gid), x1i = n8t_idx(2 * tid + 1, gid);          // transposing F write
+    const unsigned zmask = (unsigned)(p.n_pts >> 62);   // run-time zero (see n8_invert)
+
+    // Persistent grid: a warp owns eight consecutive energies of ONE Hamiltonian at a time (the energy axis is
+    // padded to a multiple of eight per Hamiltonian), so the block fragments of a site are loaded once and shared by
+    // the eight points; finished warps take the next item on their own (no CTA-wide tail).
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp; wg < n_warps; wg += wstride) {
     const int ham = (int)(wg / warps_per_ham);
     const int e_raw = (int)(wg - (long long)ham * warps_per_ham) * GPW + gid;
-    const bool active = warp_live && e_raw < p.nE;
+    const bool active = e_raw < p.nE;
     const int e = min(e_raw, p.nE - 1);
     const long long pt = (long long)ham * p.nE + e;
     const cd E = p.E[e];
-    // Two instantiations are launched back to back when the structure scan ran: the one with the diagonal-site
-    // path serves batches where at least 1/8 of the interior sites are diagonal, the lean one the rest (the
-    // decision is taken on the device, no host synchronisation).
-    if (p.class_count != nullptr && ((long long)(*p.class_count) * 8 >= p.class_sites) != DIAG) return;
-    const long long nn = (long long)n * n;
     const double2* hbase = reinterpret_cast<const double2*>(p.h) + ham * p.h_stride;
     const double2* tbase = reinterpret_cast<const double2*>(p.tnn) + ham * p.t_stride;
-    const double2 zero2 = make_double2(0.0, 0.0);
-
-    auto tocd = [](double2 v) -> cd { return mk(v.x, v.y); };
 
     // ------------------------------------------------------------------ prologue (Rw): leads of own channels
     double vLo[RP], vRo[RP];
@@ -141,15 +150,6 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     }
     // all energies real?  (every reference driver: then Im of the B fragment does not depend on the point)
     const bool realE = __all_sync(FULLM, E.y == 0.0);
-
-    // ------------------------------------------------------------------ F-role constants
-    const double m0 = (gid == 2 * tid) ? 1.0 : 0.0;        // diagonal masks of the two fragment elements
-    const double m1 = (gid == 2 * tid + 1) ? 1.0 : 0.0;
-    const bool in0 = full || (gid < n && 2 * tid < n);      // element inside the real n x n block?
-    const bool in1 = full || (gid < n && 2 * tid + 1 < n);
-    const int f0i = n8t_idx(gid, 2 * tid), f1i = n8t_idx(gid, 2 * tid + 1);          // own F slots
-    const int x0i = n8t_idx(2 * tid, gid), x1i = n8t_idx(2 * tid + 1, gid);          // transposing F write
-    const unsigned zmask = (unsigned)(p.n_pts >> 62);   // run-time zero (see n8_invert)
 
     __syncwarp();
 
@@ -517,12 +517,12 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     const int n_src = p.n_src;
     const long long obase = pt * (long long)n_src * n;
     double tsum = 0.0;
-    auto emit = [&](int i, const double (&rr)[RP], const double (&tt)[RP]) {
+    auto emit = [&](int i, bool src_up, const double (&rr)[RP], const double (&tt)[RP]) {
         double sum = 0.0;
         if (full) {
             sum = (rr[0] + tt[0]) + (rr[1] + tt[1]);
             tsum += tt[0] + tt[1];
-            if (active) {
+            if (active && p.R) {
                 *reinterpret_cast<double2*>(p.R + obase + (long long)i * N + row0) = make_double2(rr[0], rr[1]);
                 *reinterpret_cast<double2*>(p.T + obase + (long long)i * N + row0) = make_double2(tt[0], tt[1]);
             }
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 if (r < n) {
                     sum += rr[s] + tt[s];
                     tsum += tt[s];
-                    if (active) {
+                    if (active && p.R) {
                         p.R[obase + (long long)i * n + r] = rr[s];
                         p.T[obase + (long long)i * n + r] = tt[s];
                     }
@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             sum += __shfl_xor_sync(FULLM, sum, 1);
             if (active && tid == 0) p.resid[pt * n_src + i] = sum - 1.0;
         }
+        if (p.spin) emit_spin<RP, 4>(p, pt, i, src_up, active, tid, row0, n, rr, tt);
     };
 
     if (p.sources == nullptr) {
@@ -566,13 +567,13 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                     const double yi = (w.x * vL[a]) * ft;
                     tt[s] = fma(yr, yr, yi * yi);
                 }
-                emit(a, rr, tt);
+                emit(a, a < p.n_up, rr, tt);
             }
         }
     } else {
         for (int i = 0; i < n_src; ++i) {
             const double* Asrc = p.sources + (long long)i * n;
-            double f2 = 0.0;
+            double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector (emit_spin)
             double ur[RP], ui[RP], wr[RP], wi[RP], mine[RP];
 #pragma unroll
             for (int s = 0; s < RP; ++s) ur[s] = ui[s] = wr[s] = wi[s] = mine[s] = 0.0;
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                     const double a = Asrc[c];
                     const double av = a * vL[c];
                     f2 = fma(a, av, f2);
+                    if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
 #pragma unroll
                     for (int s = 0; s < RP; ++s) {
                         const double2 g = g00[n8t_idx(row0 + s, c)];
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 const double yi = wr[s] * ft;
                 tt[s] = fma(yr, yr, yi * yi);
             }
-            emit(i, rr, tt);
+            emit(i, wu >= wd, rr, tt);
         }
     }
     if (p.ttot) {
@@ -614,6 +616,8 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         tsum += __shfl_xor_sync(FULLM, tsum, 1);
         if (active && tid == 0) p.ttot[pt] = tsum;
     }
+    __syncwarp();   // the epilogue's shared-memory reads are done before the next item's prologue writes
+    }   // persistent loop over the warp's items
 }
 
 }  // namespace tx

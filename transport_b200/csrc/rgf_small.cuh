@@ -41,6 +41,8 @@ struct SweepParams {
     double* T;
     double* resid;           // [n_pts][n_src] or null
     double* ttot;            // [n_pts] or null: sum over sources and channels of T (= Tr[Gamma_R G Gamma_L G^dag] for all sources)
+    double* spin;            // [n_pts][n_src][spin_n] or null: spin-resolved channel sums (emit_spin below)
+    int n_up, spin_n;        // channels [0, n_up) carry electron spin up; spin_n = 2 (T only) or 4 (T and R)
     int* singular;           // device flag, set to 1 if a zero pivot was met
     const int* nondiag_max;  // [n_ham or 1] or null: largest site index whose on-site block is not diagonal (-1: none)
     long long nondiag_stride;
@@ -80,6 +82,47 @@ __device__ __forceinline__ void cfms2(double2& acc, const double2 a, const doubl
 }
 __device__ __forceinline__ double2 cmul2(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+
+// Spin-resolved channel sums of one source, fused into the K3 epilogue (the reduction the reference's drivers do
+// on the host: run_wfm_gate.py:404-405,473-477 split the n_loc_dof channels at n_mol_dof into electron spin up /
+// down).  Channels [0, n_up) are the "up" sector.  Output per (point, source):
+//     spin[0] = sum of T over the channels of the SOURCE's sector   (no spin flip)
+//     spin[1] = sum of T over the other sector                      (spin flip)
+//     spin[2], spin[3] = the same for R                             (only when spin_n == 4)
+// The LP lanes of a point each hold RP channels (row0 ...); lane li == 0 stores.
+template <int RP, int LP>
+__device__ __forceinline__ void emit_spin(const SweepParams& p, long long pt, int i, bool src_up, bool active, int li,
+                                          int row0, int n, const double (&rr)[RP], const double (&tt)[RP]) {
+    double ts = 0.0, to = 0.0, rs = 0.0, ro = 0.0;
+#pragma unroll
+    for (int s = 0; s < RP; ++s) {
+        const int r = row0 + s;
+        if (r < n) {
+            const bool same = (r < p.n_up) == src_up;
+            ts += same ? tt[s] : 0.0;
+            to += same ? 0.0 : tt[s];
+            rs += same ? rr[s] : 0.0;
+            ro += same ? 0.0 : rr[s];
+        }
+    }
+#pragma unroll
+    for (int off = LP / 2; off >= 1; off >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, off);
+        to += __shfl_xor_sync(0xffffffffu, to, off);
+    }
+    if (p.spin_n == 4) {
+#pragma unroll
+        for (int off = LP / 2; off >= 1; off >>= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            ro += __shfl_xor_sync(0xffffffffu, ro, off);
+        }
+    }
+    if (active && li == 0) {
+        double* o = p.spin + (pt * p.n_src + i) * p.spin_n;
+        *reinterpret_cast<double2*>(o) = make_double2(ts, to);
+        if (p.spin_n == 4) *reinterpret_cast<double2*>(o + 2) = make_double2(rs, ro);
+    }
 }
 
 // O = L * B,  L: own rows in registers, B: N x N in shared memory ([k*N+c][group]).
@@ -488,7 +531,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
     const long long obase = pt * (long long)n_src * n;
 
     double tsum = 0.0;   // sum of T over own channels and all sources
-    auto emit = [&](int i, const double (&rr)[RP], const double (&tt)[RP]) {
+    auto emit = [&](int i, bool src_up, const double (&rr)[RP], const double (&tt)[RP]) {
         double sum = 0.0;
 #pragma unroll
         for (int s = 0; s < RP; ++s) {
@@ -496,7 +539,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
             if (full || r < n) {
                 sum += rr[s] + tt[s];
                 tsum += tt[s];
-                if (active) {
+                if (active && p.R) {
                     p.R[obase + (long long)i * n + r] = rr[s];
                     p.T[obase + (long long)i * n + r] = tt[s];
                 }
@@ -507,6 +550,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
             for (int off = LP / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (active && li == 0) p.resid[pt * n_src + i] = sum - 1.0;
         }
+        if (p.spin) emit_spin<RP, LP>(p, pt, i, src_up, active, li, row0, n, rr, tt);
     };
 
     if (p.sources == nullptr) {
@@ -530,13 +574,13 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
                     const double yi = (W[s][a].x * vL[a]) * ft;
                     tt[s] = fma(yr, yr, yi * yi);
                 }
-                emit(a, rr, tt);
+                emit(a, a < p.n_up, rr, tt);
             }
         }
     } else {
         for (int i = 0; i < n_src; ++i) {
             const double* Asrc = p.sources + (long long)i * n;
-            double f2 = 0.0;
+            double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector (emit_spin)
             double ur[RP], ui[RP], wr[RP], wi[RP], mine[RP];
 #pragma unroll
             for (int s = 0; s < RP; ++s) ur[s] = ui[s] = wr[s] = wi[s] = mine[s] = 0.0;
@@ -546,6 +590,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
                     const double a = Asrc[c];
                     const double av = a * vL[c];                  // Ajsigma * v_L
                     f2 = fma(a, av, f2);                          // :108
+                    if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
 #pragma unroll
                     for (int s = 0; s < RP; ++s) {
                         ur[s] = fma(A[s][c].x, av, ur[s]);
@@ -568,7 +613,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
                 const double yi = wr[s] * ft;
                 tt[s] = fma(yr, yr, yi * yi);
             }
-            emit(i, rr, tt);
+            emit(i, wu >= wd, rr, tt);
         }
     }
     if (p.ttot) {

@@ -36,9 +36,46 @@ def check_closed_leads(h):
             raise Exception("Not diagonal:\n" + str(blk))
 
 
+class Context:
+    """A `tx_context`: private device workspace, scratch, stream and tuning options (include/transport_b200.h).
+    Calls through one Context are serialised; distinct Contexts are independent, so host threads that want
+    concurrent sweeps make one each.  `stream` is a raw cudaStream_t handle (int) or None for a context-owned
+    non-blocking stream."""
+
+    def __init__(self, device=0, stream=None):
+        import ctypes
+        lib = _lib.load()
+        self._lib = lib
+        self._h = ctypes.c_void_p()
+        check(lib.tx_context_create(int(device), ctypes.byref(self._h)))
+        if stream is not None:
+            check(lib.tx_context_set_stream(self._h, ctypes.c_void_p(int(stream)), 1))
+
+    def set_option(self, option, value):
+        check(self._lib.tx_context_set_option(self._h, int(option), int(value)))
+
+    def close(self):
+        if self._h:
+            self._lib.tx_context_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, params=None,
                        sigL=None, sigR=None, want_resid=False, out=None, want_total=False,
-                       want_caroli=False):
+                       want_caroli=False, want_rt=True, want_spin=False, n_elec_up=None, spin_out=None,
+                       context=None):
     """Reflection / transmission probabilities for every (Hamiltonian, energy, source).
 
     Args
@@ -49,10 +86,16 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
       sources None -> all n one-hot sources; else [n_src, n] real amplitude vectors (Ajsigma)
       h1, params  optional affine family: Hamiltonian p = h + params[p]*h1  (h must then be [M,n,n])
       out    optional (R, T) float64 arrays to fill (e.g. views of pinned memory)
+      want_rt  False: the per-channel arrays are neither allocated, written nor copied (compact sweeps)
+      want_spin  2 or 4 (True = 4): spin-resolved sums fused into the device epilogue, [P, nE, n_src, want_spin] =
+             (T no-flip, T flip[, R no-flip, R flip]) with channels [:n_elec_up] = electron spin up (default n//2;
+             run_wfm_gate.py:404-405,473-477); `spin_out` optionally supplies the array to fill
+      context  a `Context` (own workspace / stream) or None for the per-device default context
     Returns
-      R, T  float64 [P, nE, n_src, n]  (+ resid [P, nE, n_src] = sum R + sum T - 1 if want_resid,
+      R, T  float64 [P, nE, n_src, n] (if want_rt)  (+ resid [P, nE, n_src] = sum R + sum T - 1 if want_resid,
       + total [P, nE] = T summed over sources and channels if want_total,
-      + caroli [P, nE] = Tr[Gamma_R G Gamma_L G^dag] with matrix Gamma if want_caroli)
+      + caroli [P, nE] = Tr[Gamma_R G Gamma_L G^dag] with matrix Gamma if want_caroli,
+      + spin [P, nE, n_src, 2|4] if want_spin)
     """
     lib = _lib.load()
     h, tnn = _norm_blocks(h, tnn)
@@ -97,7 +140,13 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
         n_src = src.shape[0]
 
     shape = (n_ham, len(Es), n_src, n)
-    if out is None:
+    if not want_rt:
+        if out is not None:
+            raise ValueError("out given with want_rt=False")
+        if not (want_resid or want_total or want_caroli or want_spin):
+            raise ValueError("no output requested")
+        R = T = None
+    elif out is None:
         R = np.empty(shape, dtype=np.float64)
         T = np.empty(shape, dtype=np.float64)
     else:
@@ -107,31 +156,35 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
     resid = np.empty(shape[:3], dtype=np.float64) if want_resid else None
     total = np.empty(shape[:2], dtype=np.float64) if want_total else None
     caroli = np.empty(shape[:2], dtype=np.float64) if want_caroli else None
+    spin, spin_n, n_up = None, 0, 0
+    if want_spin:
+        spin_n = 4 if want_spin is True else int(want_spin)
+        if spin_n not in (2, 4):
+            raise ValueError("want_spin must be 2 or 4")
+        n_up = n // 2 if n_elec_up is None else int(n_elec_up)
+        if spin_out is None:
+            spin = np.empty(shape[:3] + (spin_n,), dtype=np.float64)
+        else:
+            spin = spin_out
+            if spin.shape != shape[:3] + (spin_n,) or spin.dtype != np.float64:
+                raise ValueError("spin_out must be float64 of shape %s" % (shape[:3] + (spin_n,),))
 
-    rc = lib.tx_transmission_sweep(ptr(h), n_h, ptr(h1), ptr(params), ptr(tnn), n_t, n, M, n_ham,
-                                   ptr(Es), len(Es), lead_mode, ptr(sigL), ptr(sigR), n_sig,
-                                   TX_HOP_AUTO, ptr(src), None, n_src, ptr(R), ptr(T), ptr(resid), ptr(total), ptr(caroli))
+    rc = lib.tx_transmission_sweep_spin(context._h if context is not None else None,
+                                        ptr(h), n_h, ptr(h1), ptr(params), ptr(tnn), n_t, n, M, n_ham,
+                                        ptr(Es), len(Es), lead_mode, ptr(sigL), ptr(sigR), n_sig,
+                                        TX_HOP_AUTO, ptr(src), None, n_src, ptr(R), ptr(T), ptr(resid), ptr(total),
+                                        ptr(caroli), n_up, spin_n, ptr(spin))
     if rc == _lib.TX_ERR_SINGULAR:
         # numpy raises LinAlgError for an exactly singular E - H' (wfm/__init__.py:162)
         raise np.linalg.LinAlgError("Singular matrix")
     check(rc)
-    ret = (R, T)
+    ret = (R, T) if want_rt else ()
     if want_resid:
         ret += (resid,)
     if want_total:
         ret += (total,)
     if want_caroli:
         ret += (caroli,)
-    return ret
-
-
-def spin_flip_sums(T, n_elec_up=None):
-    """Spin-resolved sums used by `run_wfm_gate.py:404-405,473-477`: channels [:n/2] carry electron
-    spin up, [n/2:] spin down.  Returns (T_noflip, T_flip) [..., n_src]: transmitted weight with the
-    electron spin equal / opposite to the source channel's."""
-    n = T.shape[-1]
-    half = n // 2 if n_elec_up is None else n_elec_up
-    up = T[..., :half].sum(-1)
-    dn = T[..., half:].sum(-1)
-    src_up = np.arange(T.shape[-2]) < half
-    return np.where(src_up, up, dn), np.where(src_up, dn, up)
+    if want_spin:
+        ret += (spin,)
+    return ret[0] if len(ret) == 1 else ret
