@@ -1,32 +1,39 @@
 #!/usr/bin/env python
-"""Benchmark of the T(E) hot path on the BASELINE.json headline configuration.
+"""Benchmark of the T(E) hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant V]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config cfg1|cfg2|cfg3|cfg4|cfg5] [--scaling weak|strong] [--no-secondary] [--no-cpu]
 
-Workload (BASELINE.json configs[1]): two spin-1/2 impurities, n_loc_dof = 8,
-M = 8 blocks, H(J) = H0 + J*H1, J = linspace(-1,-0.001,1000) x E = logspace(-4,0,1000) - 2 -> 10^6
-(energy, parameter) points PER GPU (weak scaling: rank r takes its own 1000-value J slice of a
-1000*N-value grid), all 8 one-hot sources per point.  A step = one pass of the sweep over the
-rank's 10^6 points with inputs resident in HBM, plus (N>1) the NCCL all-gather of the compact
-per-point transmission totals.
+Headline (default, BASELINE.json configs[1]): two spin-1/2 impurities, n_loc_dof = 8, M = 8 blocks,
+H(J) = H0 + J*H1, J = linspace(-1,-0.001,1000) x E = logspace(-4,0,1000) - 2 -> 10^6 (energy, parameter) points PER GPU
+(weak scaling: rank r takes its own 1000-value J slice of a 1000*N-value grid; `--scaling strong` shards ONE 10^6-point
+grid), all 8 one-hot sources per point.  A step = one pass of the sweep over the rank's points with inputs resident in
+HBM; on N > 1 GPUs the per-point totals are gathered INSIDE the sweep: the K3 epilogue stores them into every rank's
+result buffer over NVLink (CUDA-IPC peer memory), and a device-side flag barrier closes the step — no collective
+follows the kernel (`--gather nccl` runs the round-1 NCCL all-gather instead).
 
-One JSON line is printed by rank 0 (see the task contract): metric value, e2e through the public
-host-buffer API, roofline of the dominant kernel (FP64 FMA pipe; HBM figures alongside), the CPU
-baseline (the oracle's loop-for-loop port of the reference, all host cores) and clocks.
+One JSON line is printed by rank 0: metric value, e2e through the public host-buffer API (full per-channel R/T as the
+reference returns them) plus the compact spin-resolved path, roofline of the dominant kernel, the CPU baseline (the
+oracle's loop-for-loop port of the reference, all host cores), clocks sampled during the timed region, and (N = 1) a
+`secondary` block with BASELINE configs 1, 3, 4 and 5 under the same rules (scripts/bench_configs.py).  `--config cfgK`
+makes any of them the headline line instead, at any N.
 """
 import argparse
+import ctypes
 import json
 import multiprocessing as mp
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+for p in (ROOT, os.path.join(ROOT, "scripts")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import benchutil as bu  # noqa: E402
 
 N_J, N_E, NLOC, MBLK = 1000, 1000, 8, 8
 FLOPS_PER_POINT = 8 * NLOC ** 3 * MBLK * 2          # 8 n^3 M (1+g), g=1 scalar hopping  
@@ -36,20 +43,20 @@ FLOPS_PER_POINT = 8 * NLOC ** 3 * MBLK * 2          # 8 n^3 M (1+g), g=1 scalar 
 # one product per site, which the telescoping removes; both fractions are reported.
 EXECUTED_FLOPS_PER_POINT = 4 * 8 * NLOC ** 3 + 6 * 8 * NLOC ** 2 + 40 * NLOC ** 2
 BYTES_PER_POINT = 24 + 16 * NLOC * NLOC             # unique bytes: E, J, R and T for 8 sources
-METRIC = "T(E) points/sec (energy x param)"
-UNIT = "points/s"
-WORKLOAD = "cfg2: rbmenez-style two spin-1/2 impurities, n_loc_dof=8, M=8, 1000 J x 1000 E, all 8 sources"
+METRIC, UNIT = bu.METRIC, bu.UNIT
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
+def config_dict(name, world, scaling):
+    """The `config` object of the JSON line: identical keys and values in both arms (ours / reference)."""
+    from bench_configs import WORKLOADS
+    return {"workload": WORKLOADS[name], "config": name, "scaling": scaling, "parallelism": "dp%d" % world,
+            "dtype": "complex128 arithmetic, float64 outputs"}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (cfg2)
 def _cpu_worker(args):
     """Times the oracle's loop-for-loop port of wfm.kernel on a slice of (J, E) points."""
-    os.environ["OMP_NUM_THREADS"] = "1"
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(1)
-    except Exception:
-        pass
+    bu.one_thread_blas()
     from oracle import wfm_oracle
     from transport_b200 import configs
     pts, = args
@@ -85,249 +92,296 @@ def run_cpu_sample(pool, cores, pts_per_core, offset=0):
 
 
 def reference_arm(args):
-    """`--impl reference`: the reference's CPU algorithm (oracle port, Python loops + dense inverse,
-    transport/wfm/__init__.py:29-215) on all host cores; rank 0 only."""
+    """`--impl reference`: the reference's CPU algorithm (oracle port: Python loops + dense inverse,
+    transport/wfm/__init__.py:29-215; oracle/bardeen_oracle.py for cfg5) on all host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    import bench_configs as bc
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
-    pts_per_core = 12
-    with mp.get_context("fork").Pool(cores) as pool:
-        for w in range(args.warmup):
-            run_cpu_sample(pool, cores, 2, offset=100 + w)
-        t_tot, n_tot = 0.0, 0
-        for k in range(args.steps):
-            rate, wall = run_cpu_sample(pool, cores, pts_per_core, offset=k)
+    unit = UNIT
+    if args.config == "cfg2":
+        pts_per_core = 12
+        with mp.get_context("fork").Pool(cores) as pool:
+            for w in range(args.warmup):
+                run_cpu_sample(pool, cores, 2, offset=100 + w)
+            t_tot, n_tot = 0.0, 0
+            for k in range(args.steps):
+                rate, wall = run_cpu_sample(pool, cores, pts_per_core, offset=k)
+                t_tot += wall
+                n_tot += cores * pts_per_core
+        value = n_tot / t_tot
+        ms = 1e3 * t_tot / args.steps
+        sample = "%d random (J,E) points of the cfg2 grid x 8 sources per step, %d steps" % (cores * pts_per_core, args.steps)
+        kind = "port"
+    else:
+        # bounded samples of the other configs, sized by scripts/bench_configs.py's own CPU legs
+        from transport_b200 import configs
+        steps = max(1, min(args.steps, 3))
+        t_tot, n_tot, sample = 0.0, 0, ""
+        kind = "port"
+        for k in range(steps):
+            if args.config == "cfg1":
+                h, tnn, tnnn = configs.barrier_blocks(0.4, 11)
+                Es = configs.barrier_energies(10_000)[k::steps]
+                chunks = [(h, tnn, tnnn, Es[i::cores], [np.array([1.0])]) for i in range(cores)]
+                rate, wall, _ = bc._pool_rate(bc._cpu_kernel_loops, chunks, len(Es))
+                n_tot += len(Es)
+                sample = "every %d-th of the 10^4 energies per step, reference-loop port" % steps
+            elif args.config == "cfg3":
+                h, tnn, _ = configs.disordered_blocks(N=10_000, n=8, W=0.05, seed=1234)
+                Es = np.linspace(-1.9, 1.9, cores).astype(complex)
+                chunks = [(h, tnn, Es[i::cores], np.eye(8)) for i in range(cores)]
+                rate, wall, _ = bc._pool_rate(bc._cpu_rgf, chunks, cores)
+                n_tot += cores
+                sample = ("%d energies x 8 sources at full length per step with the numpy restatement of the RECURSIVE algorithm "
+                          "(oracle/rgf_oracle.py): the reference's dense path cannot run M = 10 002 (102 GB)" % cores)
+            elif args.config == "cfg4":
+                h, tnn, _ = configs.ribbon_blocks(width=64, L=32, W=1.0, seed=1234)
+                Es = np.linspace(-3.5, 3.5, 2 * cores).astype(complex)
+                chunks = [(h, tnn, Es[i::cores], 1e-8) for i in range(cores)]
+                rate, wall, _ = bc._pool_rate(bc._cpu_ribbon, chunks, 2 * cores)
+                n_tot += 2 * cores
+                sample = "%d energies per step, numpy restatement (Sancho-Rubio + recursive sweep; the reference refuses n>2 leads)" % (2 * cores)
+            else:
+                unit = "geometries/s"
+                VRs = np.linspace(-0.05, 0.05, 256)
+                use = min(cores, 32)
+                chunks = [([VRs[(7 * i + k) % 256]], 200) for i in range(use)]
+                rate, wall, _ = bc._pool_rate(bc._cpu_bardeen, chunks, use)
+                n_tot += use
+                sample = "%d geometries per step (N_LR = 200), oracle kernel_well = the reference's dense-eigh algorithm" % use
             t_tot += wall
-            n_tot += cores * pts_per_core
-    value = n_tot / t_tot
-    sample = "%d random (J,E) points of the cfg2 grid x 8 sources per step, %d steps" % (cores * pts_per_core, args.steps)
+        value = n_tot / t_tot
+        ms = 1e3 * t_tot / steps
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC if unit == UNIT else "bardeen geometries/sec", "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "complex128 (f64)",
+        "data": "synthetic", "config": config_dict(args.config, world, args.scaling),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ clocks
-class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+# ------------------------------------------------------------------------------------------ peer gather
+class PeerGather:
+    """Per-point totals gathered inside the sweep: every rank's [world * n_pts] result buffer is cudaMalloc'ed by the
+    library, exported with CUDA IPC and mapped by the peers; the sweep epilogue stores into all of them."""
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            parts = [x.strip() for x in row.split(",")]
-            if len(parts) < 7:
+    def __init__(self, env, n_pts):
+        from transport_b200 import _lib
+        import torch
+        self.env, self.lib, self._lib = env, env.lib, _lib
+        dist = env.dist
+        W = env.world
+        self.n_pts = n_pts
+        self.buf = ctypes.c_void_p()
+        self.flags = ctypes.c_void_p()
+        _lib.check(self.lib.tx_peer_alloc(8 * n_pts * W, ctypes.byref(self.buf)))
+        _lib.check(self.lib.tx_peer_alloc(64, ctypes.byref(self.flags)))
+        hb, hf = (ctypes.c_ubyte * 64)(), (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.tx_peer_export(self.buf, hb))
+        _lib.check(self.lib.tx_peer_export(self.flags, hf))
+        mine = torch.tensor(list(bytes(hb)) + list(bytes(hf)), dtype=torch.uint8, device=env.dev)
+        allh = torch.empty(W * 128, dtype=torch.uint8, device=env.dev)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().reshape(W, 128)
+        self.bufs, self.flagp, self.opened = [], [], []
+        for r in range(W):
+            if r == env.rank:
+                self.bufs.append(self.buf.value)
+                self.flagp.append(self.flags.value)
                 continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            pb, pf = ctypes.c_void_p(), ctypes.c_void_p()
+            _lib.check(self.lib.tx_peer_open((ctypes.c_ubyte * 64)(*allh[r, :64].tolist()), ctypes.byref(pb)))
+            _lib.check(self.lib.tx_peer_open((ctypes.c_ubyte * 64)(*allh[r, 64:].tolist()), ctypes.byref(pf)))
+            self.bufs.append(pb.value)
+            self.flagp.append(pf.value)
+            self.opened += [pb, pf]
+        self.ctx = ctypes.c_void_p()
+        _lib.check(self.lib.tx_context_create(env.local_rank, ctypes.byref(self.ctx)))
+        arr = (ctypes.c_void_p * W)(*self.bufs)
+        _lib.check(self.lib.tx_context_set_gather(self.ctx, arr, W, env.rank * n_pts))
+        self.flag_arr = (ctypes.c_void_p * W)(*self.flagp)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=env.dev)
+        self.epoch = 0
+        dist.barrier()
+
+    def barrier_dev(self, stream):
+        self.epoch += 1
+        self._lib.check(self.lib.tx_peer_barrier_dev(self.flag_arr, self.env.world, self.env.rank, self.epoch,
+                                                     self.timed_out.data_ptr(), stream))
+
+    def gathered(self):
+        """The rank's gathered array as a torch tensor view (copied out)."""
+        torch = self.env.torch
+        out = torch.empty(self.n_pts * self.env.world, dtype=torch.float64, device=self.env.dev)
+        # wrap the raw device pointer with the CUDA array interface
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.n_pts * self.env.world,), "typestr": "<f8",
+                                        "data": (self.buf.value, False), "version": 2}
+        out.copy_(torch.as_tensor(raw, device=self.env.dev))
+        return out
+
+    def close(self):
+        self.env.torch.cuda.synchronize()
+        self.env.dist.barrier()
+        for p in self.opened:
+            self.lib.tx_peer_close(p)
+        self.env.dist.barrier()
+        self.lib.tx_context_destroy(self.ctx)
+        self.lib.tx_peer_free(self.buf)
+        self.lib.tx_peer_free(self.flags)
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
-def gpu_arm(args):
+# ------------------------------------------------------------------------------------------ GPU arm, cfg2
+def run_cfg2(env, args, scaling):
     import torch
-    from transport_b200 import _lib, configs
+    from transport_b200 import _lib, configs, shard
     from transport_b200.sweep import transmission_sweep
+    lib, dev, world, rank = env.lib, env.dev, env.world, env.rank
+    dist = env.dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = None
-    try:   # run on the CPUs next to this GPU, so that pinned host buffers are allocated on its NUMA node
-        import pynvml
-        pynvml.nvmlInit()
-        try:
-            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
-            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
-        except Exception:
-            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-        pynvml.nvmlDeviceSetCpuAffinity(handle)
-        numa = "cpus %d" % len(os.sched_getaffinity(0))
-    except Exception as exc:   # affinity is an optimisation of the e2e leg only
-        numa = "unbound (%s)" % type(exc).__name__
-    lib = _lib.load()
-    _lib.check(lib.tx_set_device(local_rank))
-    # NCCL (and torchrun banners) may write to stdout; the contract is ONE JSON line there, so everything
-    # else goes to stderr and the line is written to the saved descriptor at the end
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.check(lib.tx_set_variant(args.variant))
-
-    # ---- inputs: this rank's J slice of the 1000*world grid, resident in HBM
+    # ---- inputs: this rank's J slice, resident in HBM
     h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
-    from transport_b200 import shard
-    Js_all = np.linspace(-1.0, -0.001, N_J * world)
-    (j0, j1), _ = shard.plan(N_J * world, N_E, world, rank)      # parameter axis sharded, energies whole
+    n_j_total = N_J * world if scaling == "weak" else N_J
+    Js_all = np.linspace(-1.0, -0.001, n_j_total)
+    (j0, j1), _ = shard.plan(n_j_total, N_E, world, rank)      # parameter axis sharded, energies whole
     Js = np.ascontiguousarray(Js_all[j0:j1])
-    assert len(Js) == N_J
+    n_j = len(Js)
+    n_j_max = -(-n_j_total // world)
     _, Es = configs.cfg2_grid(N_J, N_E)
-    n_pts = N_J * N_E
+    n_pts = n_j * N_E
+    n_pts_total = n_j_total * N_E
 
-    def dev_c(a):
-        return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
-
-    d_h0, d_h1, d_tnn, d_E = dev_c(h0), dev_c(h1), dev_c(tnn), dev_c(Es)
-    d_J = torch.from_numpy(Js).to(dev)
+    d_h0, d_h1, d_tnn, d_E = env.dev_c(h0), env.dev_c(h1), env.dev_c(tnn), env.dev_c(Es)
+    d_J = env.dev_f(Js)
     d_R = torch.empty((n_pts, NLOC, NLOC), dtype=torch.float64, device=dev)
     d_T = torch.empty_like(d_R)
     d_tot = torch.empty(n_pts, dtype=torch.float64, device=dev)
     d_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    d_gather = torch.empty(n_pts * world, dtype=torch.float64, device=dev) if world > 1 else None
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = env.stream
+    gather_mode = "none"
+    pg = None
+    d_gather = None
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "peer":
+            try:
+                pg = PeerGather(env, n_j_max * N_E)
+            except Exception as exc:      # both gathers run on the device; the choice is recorded in the line
+                sys.stderr.write("peer-memory gather unavailable (%s): using the NCCL all-gather\n" % exc)
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            d_gather = torch.empty(n_j_max * N_E * world, dtype=torch.float64, device=dev)
+            d_pad = torch.zeros(n_j_max * N_E, dtype=torch.float64, device=dev)
 
-    def step():
-        rc = lib.tx_transmission_sweep_dev(
-            d_h0.data_ptr(), 1, d_h1.data_ptr(), d_J.data_ptr(), d_tnn.data_ptr(), 1, NLOC, MBLK, N_J,
+    def sweep(ctx=None, R=d_R, T=d_T):
+        rc = lib.tx_transmission_sweep_spin_dev(
+            ctx, d_h0.data_ptr(), 1, d_h1.data_ptr(), d_J.data_ptr(), d_tnn.data_ptr(), 1, NLOC, MBLK, n_j,
             d_E.data_ptr(), N_E, _lib.TX_LEAD_CLOSED, None, None, 1, _lib.TX_HOP_SCALAR,
-            None, None, NLOC, d_R.data_ptr(), d_T.data_ptr(), None, d_tot.data_ptr(),
+            None, None, NLOC, R.data_ptr(), T.data_ptr(), None, d_tot.data_ptr(), 0, 0, None,
             d_flag.data_ptr(), stream.cuda_stream)
         _lib.check(rc)
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_tot)
 
-    # ---- FP64 peak (roofline denominator; MEASURED_PEAKS.json has no FP64 entry)
-    import ctypes
-    pk, pkms = ctypes.c_double(), ctypes.c_double()
-    _lib.check(lib.tx_measure_fp64_peak(ctypes.byref(pk), ctypes.byref(pkms)))
-    fp64_peak = pk.value
+    def step():
+        if pg is not None:
+            sweep(pg.ctx)
+            pg.barrier_dev(stream.cuda_stream)
+        else:
+            sweep()
+            if gather_mode == "nccl":
+                d_pad[:n_pts] = d_tot
+                dist.all_gather_into_tensor(d_gather, d_pad)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    sampler = bu.ClockSampler(env)
+    l0 = int(lib.tx_launch_counter())
+    ms_per_step, t_wall = env.timed(step, args.steps, args.warmup, sampler if rank == 0 else None)
+    launches = (int(lib.tx_launch_counter()) - l0) * args.steps // (args.steps + max(args.warmup, 3))
     assert int(d_flag.item()) == 0, "singular block in the benchmark sweep"
+    clocks = sampler.summary() if rank == 0 else None
+    value = n_pts_total / (ms_per_step * 1e-3)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    launches0 = int(lib.tx_launch_counter())
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = int(lib.tx_launch_counter()) - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    ms_total = float(sum(ms_steps))
+    gather_ok = None
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = n_pts * world / (ms_per_step * 1e-3)
+        # the gathered array must equal an NCCL all-gather of the ranks' totals, bit for bit
+        ref_pad = torch.zeros(n_j_max * N_E, dtype=torch.float64, device=dev)
+        ref_pad[:n_pts] = d_tot
+        ref = torch.empty(n_j_max * N_E * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ref, ref_pad)
+        if pg is not None:
+            assert int(pg.timed_out.item()) == 0, "peer barrier timed out"
+            got = pg.gathered()
+            sizes = [shard.plan(n_j_total, N_E, world, r)[0] for r in range(world)]
+            gather_ok = all(torch.equal(got[r * n_j_max * N_E:r * n_j_max * N_E + (b - a) * N_E],
+                                        ref[r * n_j_max * N_E:r * n_j_max * N_E + (b - a) * N_E]) for r, (a, b) in enumerate(sizes))
+        else:
+            gather_ok = bool(torch.equal(d_gather, ref))
+        assert gather_ok, "gathered totals differ from the NCCL all-gather of the same data"
 
-    # ---- kernel-only time (the sweep kernel alone, same stream) for the roofline
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for k in range(args.steps):
-        flush.zero_()
-        kev[k][0].record(stream)
-        rc = lib.tx_transmission_sweep_dev(
-            d_h0.data_ptr(), 1, d_h1.data_ptr(), d_J.data_ptr(), d_tnn.data_ptr(), 1, NLOC, MBLK, N_J,
-            d_E.data_ptr(), N_E, _lib.TX_LEAD_CLOSED, None, None, 1, _lib.TX_HOP_SCALAR,
-            None, None, NLOC, d_R.data_ptr(), d_T.data_ptr(), None, d_tot.data_ptr(),
-            d_flag.data_ptr(), stream.cuda_stream)
-        kev[k][1].record(stream)
-    torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    # ---- kernel-only time (the sweep alone, same stream) for the roofline
+    k_ms, _ = env.timed(sweep, args.steps, 3)
 
     # ---- parity spot-check of the benchmarked arrays against the golden vectors of the reference
     parity = None
     if rank == 0 and world == 1:
         g = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_cicc.npz"))
-        Tn = d_T.view(N_J, N_E, NLOC, NLOC)
+        Tn = d_T.view(n_j, N_E, NLOC, NLOC)
+        Rn = d_R.view(n_j, N_E, NLOC, NLOC)
         worst = 0.0
         for k, jidx in enumerate([0, 250, 500, 750, 999]):
-            got = Tn[jidx, ::40].cpu().numpy()
-            want = g["T"][k]
-            scale = np.maximum(np.abs(want), 1e-13 * np.abs(want).max(axis=-1, keepdims=True))
-            worst = max(worst, float(np.max(np.abs(got - want) / np.where(scale == 0, 1, scale))))
+            worst = max(worst, bu.rel_err(Tn[jidx, ::40].cpu().numpy(), g["T"][k]), bu.rel_err(Rn[jidx, ::40].cpu().numpy(), g["R"][k]))
         parity = worst
 
     # ---- e2e through the public host-buffer API (pinned host memory, copies inside the timed region)
-    e2e = None
-    if rank == 0 or world > 1:
-        R_host = torch.empty((N_J, N_E, NLOC, NLOC), dtype=torch.float64, pin_memory=True)
-        T_host = torch.empty_like(R_host).pin_memory()
-        Rn, Tn_ = R_host.numpy(), T_host.numpy()
-        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-        ph0, ph1, ptn, pE, pJ = pin(h0), pin(h1), pin(tnn), pin(Es), pin(Js)
-        transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, out=(Rn, Tn_))      # warm-up (workspace alloc)
-        barrier()
-        n_e2e = max(2, min(args.steps, 5))
+    def time_e2e(fn, reps):
+        fn()                                                                     # warm-up (workspace allocation)
+        env.barrier()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, out=(Rn, Tn_))
-            _ = float(Tn_[0, 0, 0, 0])                                           # host read of the result
-        barrier()
-        dt = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": n_pts * world / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(ph0.nbytes + ph1.nbytes + ptn.nbytes + pE.nbytes + pJ.nbytes),
-               "d2h_bytes_per_step": int(Rn.nbytes + Tn_.nbytes), "ms_per_step": dt * 1e3,
-               "api": "transport_b200.sweep.transmission_sweep -> tx_transmission_sweep (host pointers)"}
+        for _ in range(reps):
+            fn()
+        env.barrier()
+        return env.max_over_ranks((time.perf_counter() - t0) / reps)
+
+    n_e2e = max(2, min(args.steps, 5))
+    pin = env.pin
+    ph0, ph1, ptn, pE, pJ = pin(h0), pin(h1), pin(tnn), pin(Es), pin(Js)
+    h2d = int(ph0.nbytes + ph1.nbytes + ptn.nbytes + pE.nbytes + pJ.nbytes)
+    R_host = torch.empty((n_j, N_E, NLOC, NLOC), dtype=torch.float64, pin_memory=True).numpy()
+    T_host = torch.empty((n_j, N_E, NLOC, NLOC), dtype=torch.float64, pin_memory=True).numpy()
+
+    def full():
+        transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, out=(R_host, T_host))
+        return float(T_host[0, 0, 0, 0])                                         # host read of the result
+    dt = time_e2e(full, n_e2e)
+    pcie = env.pcie_d2h_gbs()
+    e2e = {"value": n_pts_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(R_host.nbytes + T_host.nbytes), "ms_per_step": dt * 1e3,
+           "outputs": "full per-channel R and T [J, E, source, channel] — what wfm.kernel returns per call",
+           "pcie_d2h_peak_gbs_measured": pcie, "pcie_frac": (R_host.nbytes + T_host.nbytes) / dt / 1e9 / pcie,
+           "api": "transport_b200.sweep.transmission_sweep -> tx_transmission_sweep_spin (host pointers)"}
+    del R_host, T_host
+    compact = {}
+    for spin_n in (2, 4):
+        sp = torch.empty((n_j, N_E, NLOC, spin_n), dtype=torch.float64, pin_memory=True).numpy()
+
+        def comp(sp=sp, spin_n=spin_n):
+            tot, s = transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, want_rt=False, want_total=True, want_spin=spin_n,
+                                        spin_out=sp)
+            return float(s[0, 0, 0, 0]) + float(tot[0, 0])
+        dtc = time_e2e(comp, n_e2e)
+        compact[spin_n] = {"value": n_pts_total / dtc, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": int(sp.nbytes + n_pts * 8), "ms_per_step": dtc * 1e3,
+                           "outputs": ("spin-resolved sums per source (T no-flip, T flip%s) + per-point total, reduced in the device "
+                                       "epilogue (run_wfm_gate.py:404-405,473-477 reduce the same on the host)"
+                                       % (", R no-flip, R flip" if spin_n == 4 else "")),
+                           "pcie_frac": (sp.nbytes + n_pts * 8) / dtc / 1e9 / pcie}
+        del sp
 
     # ---- CPU baseline: the oracle's loop-for-loop port on all host cores (rank 0, N=1 only)
     cpu = None
@@ -339,72 +393,124 @@ def gpu_arm(args):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d random (J,E) points of the same grid x 8 sources, %.1f s wall" % (cores * 500, wall)}
 
+    if pg is not None:
+        pg.close()
+    fp64_peak = env.fp64_peak()
+    hbm_peak, hbm_src = bu.hbm_peak()
+    traffic, ncu_note = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj.get("bytes_per_launch")
+        ncu_note = {k: tj.get(k) for k in ("kernel", "binding", "fp64_plus_dmma_shared_pipe_pct_of_peak", "dmma_subpipe_pct_of_peak",
+                                           "fp64_pipe_pct_of_peak", "lsu_data_pipe_pct_of_peak", "issue_active_pct_of_peak", "source")}
+    except Exception:
+        pass
+    ach_tf = FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
+    ach_gbs = BYTES_PER_POINT * n_pts / (k_ms * 1e-3) / 1e9
+    exe_tf = EXECUTED_FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
+    return {
+        "value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+        "e2e_compact": compact[2], "e2e_compact4": compact[4], "cpu_baseline": cpu,
+        "parity_max_rel_err": parity,
+        "parity_against": "tests/golden/cfg2_cicc.npz (unmodified reference, 5 J x 25 E x 8 sources)" if parity is not None else None,
+        "gather": {"mode": {"peer": "fused: K3 epilogue stores the per-point totals into every rank's buffer over NVLink (CUDA IPC peer "
+                                    "memory) + device-side flag barrier; no collective",
+                            "nccl": "NCCL all_gather_into_tensor after the sweep", "none": "single GPU"}[gather_mode],
+                   "verified_equal_to_nccl_all_gather": gather_ok, "bytes_per_rank": n_pts * 8},
+        "points_per_gpu": n_pts, "wall_s_timed_region": t_wall,
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                     "traffic": traffic,
+                     "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written per launch)",
+                     "ncu": ncu_note,
+                     "peak_source": "tx_measure_fp64_peak: register-resident DFMA loop, measured in this run "
+                                    "(MEASURED_PEAKS.json carries no FP64 figure)",
+                     "flops_per_point": FLOPS_PER_POINT, "kernel_ms": k_ms,
+                     "executed": {"flops_per_point": EXECUTED_FLOPS_PER_POINT, "achieved": exe_tf, "frac": exe_tf / fp64_peak,
+                                  "note": "frac above is ALGORITHMIC flops (SURVEY 8d: one inverse + one product per site) over the "
+                                          "measured DFMA peak; the telescoped sweep executes fewer, so the algorithmic fraction can exceed 1"},
+                     "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                             "bytes_per_point": BYTES_PER_POINT, "peak_source": hbm_src}},
+    }
+
+
+def gpu_arm(args):
+    import bench_configs as bc
+    env = bu.Env()
+    # NCCL (and torchrun banners) may write to stdout; the contract is ONE JSON line there, so everything
+    # else goes to stderr and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    env.init_dist()
+    rank, world = env.rank, env.world
+    name = args.config
+    extra = {}
+    if name == "cfg2":
+        res = run_cfg2(env, args, args.scaling)
+        if world > 1 and args.scaling == "weak" and not args.no_strong:
+            # the same grid as ONE 10^6-point job sharded over the ranks (north_star's own phrasing of config 2)
+            s_args = argparse.Namespace(**vars(args))
+            s_args.no_cpu = True
+            s = run_cfg2(env, s_args, "strong")
+            extra["strong_scaling"] = {
+                "value": s["value"], "unit": UNIT, "ms_per_step": s["ms_per_step"], "points_total": N_J * N_E,
+                "points_per_gpu": s["points_per_gpu"], "kernel_ms": s["roofline"]["kernel_ms"],
+                "e2e": s["e2e"], "e2e_compact": s["e2e_compact"],
+                "limiter": "fixed per-step cost (structure scan, affine expansion, the idle instantiation's launch, the flag "
+                           "barrier) = ms_per_step - kernel_ms = %.3f ms against %.3f ms of sweep" %
+                           (s["ms_per_step"] - s["roofline"]["kernel_ms"], s["roofline"]["kernel_ms"])}
+    else:
+        res = bc.run(name, env, steps=args.steps if args.steps_given else {"cfg1": 50, "cfg3": 5, "cfg4": 3, "cfg5": 10}[name],
+                     warmup=args.warmup, scaling=args.scaling, want_cpu=not args.no_cpu)
+    secondary = None
+    if name == "cfg2" and world == 1 and not args.no_secondary:
+        secondary = {}
+        for k, st in (("cfg1", 20), ("cfg3", 3), ("cfg4", 2), ("cfg5", 5)):
+            try:
+                secondary[k] = bc.run(k, env, steps=st, warmup=3, scaling="weak", want_cpu=not args.no_cpu)
+            except Exception as exc:    # a secondary config must not take the headline line down with it
+                secondary[k] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic, ncu_note = None, None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)
-            traffic = tj.get("bytes_per_launch")
-            ncu_note = {"kernel": tj.get("kernel"),
-                        "binding": "no single unit saturated: latency bound at 8 warps/SM (255 registers, 113 KB smem per CTA)",
-                        "fp64_plus_dmma_pipe_pct_of_peak": tj.get("fp64_plus_dmma_shared_pipe_pct_of_peak"),
-                        "dmma_subpipe_pct_of_peak": tj.get("dmma_subpipe_pct_of_peak"),
-                        "fp64_pipe_pct_of_peak": tj.get("fp64_pipe_pct_of_peak"),
-                        "lsu_data_pipe_pct_of_peak": tj.get("lsu_data_pipe_pct_of_peak"),
-                        "issue_active_pct_of_peak": tj.get("issue_active_pct_of_peak")}
-        except Exception:
-            pass
-        achieved_tf = FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
-        achieved_gbs = BYTES_PER_POINT * n_pts / (k_ms * 1e-3) / 1e9
+        unit = res.get("unit", UNIT)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu": n_pts, "l2": "256 MB flush between timed steps; "
-                       "each step also writes 2.05 GB of R/T", "variant": args.variant,
-                       "parallelism": "J axis sharded, dp%d" % world, "host_affinity": numa},
-            "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak, "traffic": traffic,
-                         "traffic_source": "profiles/traffic.json (ncu --set full, dram bytes read+written per launch)",
-                         "ncu": ncu_note,
-                         "peak_source": "tx_measure_fp64_peak: register-resident DFMA loop, measured in this run "
-                                        "(MEASURED_PEAKS.json carries no FP64 figure)",
-                         "flops_per_point": FLOPS_PER_POINT, "kernel_ms": k_ms,
-                         "executed": {"flops_per_point": EXECUTED_FLOPS_PER_POINT,
-                                      "achieved": EXECUTED_FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12,
-                                      "frac": EXECUTED_FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12 / fp64_peak,
-                                      "note": "frac above is ALGORITHMIC flops (SURVEY 8d: one inverse + one product per "
-                                              "site) over the measured DFMA peak; the telescoped sweep executes fewer, "
-                                              "so the algorithmic fraction can exceed 1"},
-                         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": achieved_gbs / hbm_peak, "bytes_per_point": BYTES_PER_POINT,
-                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}},
-            "cpu_baseline": cpu, "clocks": clocks, "parity_max_rel_err_vs_reference_golden": parity,
-            "wall_s_timed_region": t_wall,
+            "metric": METRIC if unit == UNIT else "bardeen geometries/sec", "value": res["value"], "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+            "config": config_dict(name, world, args.scaling),
+            "run": {"l2": "256 MB flush between timed steps (outside the event pair); every step also streams its own result arrays",
+                    "host_affinity": env.affinity, "timing": "CUDA events on the launching stream, max over ranks"},
+            "e2e": res.get("e2e"), "gpu_launches": res.get("gpu_launches"), "roofline": res.get("roofline"),
+            "cpu_baseline": res.get("cpu_baseline"), "clocks": res.get("clocks"),
         }
+        for k, v in res.items():
+            if k not in line and k not in ("workload", "unit", "n_gpus", "scaling"):
+                line[k] = v
+        line.update(extra)
+        if secondary is not None:
+            line["secondary"] = secondary
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=13)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary block (configs 1, 3, 4, 5)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-run at N > 1")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 200 if args.impl == "ours" else 5
     if args.impl == "reference":
         reference_arm(args)
     else:

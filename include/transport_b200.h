@@ -39,7 +39,11 @@ enum {
 /* How the lead self-energies are obtained. */
 enum {
     TX_LEAD_CLOSED = 0,     /* wfm.g_closed fused into the sweep (wfm/__init__.py:335-340)    */
-    TX_LEAD_TABLE = 1       /* Sigma_L, Sigma_R supplied per energy (from tx_surface_gf_* or caller) */
+    TX_LEAD_TABLE = 1,      /* Sigma_L, Sigma_R supplied per energy (from tx_surface_gf_* or caller) */
+    /* host-pointer sweep entries only: the self-energy tables are built on the device ahead of the sweep and
+     * never leave it; parameters (imE, tolerance, iteration cap) from tx_context_set_lead_params              */
+    TX_LEAD_SANCHO = 2,     /* Sancho-Rubio decimation of the multi-channel lead (TX_GF_SANCHO)               */
+    TX_LEAD_SEPARABLE = 3   /* h01 = t*I leads by the separable closed form (TX_GF_SEPARABLE)                 */
 };
 
 /* Structure of the hopping blocks tnn. */
@@ -83,6 +87,31 @@ int tx_context_create(int device, tx_context** out);
 int tx_context_destroy(tx_context* ctx);
 int tx_context_set_stream(tx_context* ctx, void* stream, int use_stream);
 int tx_context_set_option(tx_context* ctx, int option, int value);
+/* Parameters of the device-built lead tables (TX_LEAD_SANCHO, TX_LEAD_SEPARABLE): z = E + i*imE, decimation stops
+ * at max|alpha|,|beta| < conv_tol or after max_iter iterations (then the sweep returns TX_ERR_NOCONV).  Defaults
+ * 0, 1e-14, 200.  ctx = NULL addresses the per-device default context.  tx_context_last_lead_iterations returns the
+ * mean number of decimation iterations per (energy, lead) of the last host-pointer sweep of the context. */
+int tx_context_set_lead_params(tx_context* ctx, double imE, double conv_tol, int max_iter);
+int tx_context_last_lead_iterations(tx_context* ctx, double* mean_iterations);
+
+/* ---- multi-GPU gather fused into the sweep ("NCCL is used only to gather the T(E) arrays") ----
+ * One process per GPU.  Each rank allocates its copy of the gathered array with tx_peer_alloc, exports it
+ * (tx_peer_export: 64 opaque bytes, CUDA IPC) to the other ranks of the node over the host-side process group, and
+ * maps theirs with tx_peer_open.  tx_context_set_gather then makes every sweep issued through `ctx` store the
+ * per-point total transmission (the t_total output) ALSO to peers[q][offset + point] for q < n_peers (<= 8; the
+ * rank's own buffer is one of them), straight from the K3 epilogue over NVLink, so no collective follows the sweep;
+ * n_peers = 0 switches it off.  tx_peer_barrier_dev enqueues a device-side barrier on `stream`: rank `rank` raises
+ * flag_peers[q][rank] = epoch on every rank q and waits for flag_peers[rank][q] >= epoch for all q (flag arrays: 8
+ * ints each, tx_peer_alloc'ed and exchanged the same way; epoch must grow by 1 per call); after it, every peer's
+ * stores of the preceding sweep are visible to later work on `stream`.  *timed_out (device int) is set to 1 if a
+ * peer did not arrive within ~2 s (the kernel then returns instead of hanging the GPU). */
+int tx_peer_alloc(long long bytes, void** ptr);
+int tx_peer_free(void* ptr);
+int tx_peer_export(const void* ptr, unsigned char* handle64);
+int tx_peer_open(const unsigned char* handle64, void** ptr);
+int tx_peer_close(void* ptr);
+int tx_context_set_gather(tx_context* ctx, double* const* peers, int n_peers, long long offset);
+int tx_peer_barrier_dev(int* const* flag_peers, int n_peers, int rank, int epoch, int* timed_out, void* stream);
 
 /* ---- the hot path: batched T(E) sweep -------------------------------------------------- */
 /*
@@ -280,6 +309,29 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
                          const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
                          double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
                          int* nR_below, double* Mavg, void* workspace, void* stream);
+/* The same pass driven by the REGION PARAMETERS of bardeen.Hsysmat (:690-750) instead of assembled arrays: the three
+ * Hamiltonians of kernel_well (:90-125) / kernel_well_prime (:455-500) — left well (Vinf, VL, HCprime, VRprime, Vinf),
+ * right well (Vinf, VLprime, HCprime, VR, Vinf), system (Vinf, VL, HC, VR, Vinf) — are assembled ON THE DEVICE, so a sweep
+ * over step heights / barrier parameters ships a few doubles per geometry (rbstep.py:43-104 loops kernel_well over VR).
+ *   tinf, tL, tR, Vinf [n]: per-channel scalar hoppings (positive t: the blocks hold -t, :718-744) and outer potential
+ *   VL, VLprime, VR, VRprime [n_pot][n], n_pot = 1 (shared) or P
+ *   hc0 [n_hc][NC][n][n], hcU / hcL [n_hc][NC-1][n][n]: the chain HC (diagonal blocks, HC[j][j+1], HC[j+1][j]; real);
+ *   hp0, hpU, hpL: the same for HCprime (NULL = HC);  n_hc = 1 or P
+ *   cutL, cutR_states, cutR_count [P][n] as in tx_bardeen_wells;  row_cut != 0 zeroes |M|^2 rows m >= nR_below (:181)
+ *   max_states: capacity of EL, ER [P][n][max_states], Mavg [P][n][max_states][n].  *max_needed receives the largest
+ *   count; when it exceeds max_states (or max_states = 0) only the counts nL, nR_states, nR_below are returned and the
+ *   caller calls again with larger buffers.
+ *   Vb [nVb], muR, kBT, I [P][n][n][nVb] (or NULL): bardeen.current (:537-575) of |Mavg|^2 on the device.
+ * Host pointers; the device workspace is kept between calls (calls are serialised per process). */
+int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* tR, const double* Vinf,
+                            const double* VL, const double* VLprime, const double* VR, const double* VRprime, int n_pot,
+                            const double* hc0, const double* hcU, const double* hcL,
+                            const double* hp0, const double* hpU, const double* hpL, int n_hc,
+                            int Ninf, int NL, int NR, int NC, int n, int P,
+                            const double* cutL, const double* cutR_states, const double* cutR_count,
+                            double interval, int sign_fix, int row_cut, int max_states, int* max_needed,
+                            double* EL, int* nL, double* ER, int* nR_states, int* nR_below, double* Mavg,
+                            const double* Vb, int nVb, double muR, double kBT, double* I);
 /* bardeen.current (:537-575, nFD :1014-1020): I[p][alpha][beta][i] = 2 pi sum_m stat(E[p][alpha][m], Vb[i])
  * M2[p][alpha][m][beta], stat = fL (1 - fR) - fR (1 - fL), muL = muR + Vb[i].  E [P][n][nb], M2 [P][n][nb][n]. */
 int tx_bardeen_current(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,

@@ -1,142 +1,296 @@
 #!/usr/bin/env python
-"""Secondary measurements: BASELINE configs 1, 3, 4 and 5 on one GPU (config 2 is bench.py's headline).
+"""BASELINE configs 1, 3, 4 and 5 (config 2 is bench.py's headline) under the same measurement rules as bench.py.
 
-    python scripts/bench_configs.py [cfg1] [cfg3] [cfg4] [cfg5] [--small]
+    python scripts/bench_configs.py [cfg1] [cfg3] [cfg4] [cfg5] [--small] [--steps K]
 
-For each config: device-resident sweep timed with CUDA events (3 warm-ups, L2 flush between steps),
-parity of a subsample against the numpy oracle, roofline fraction (FP64), one JSON line each.
+bench.py imports `run(name, env, ...)` for its `--config` flag and for the `secondary` block of its default line.
+Every config reports: device-resident throughput (CUDA events, >= 3 warm-ups, L2 flush between steps, max over
+ranks), roofline of the dominant kernel, e2e through the public host-buffer API, the CPU baseline (reference-loop
+port where the reference's algorithm can run, labelled otherwise), parity inside the run, and clocks sampled during
+the timed region.  Multi-GPU: the energy (cfg1/3/4) or geometry (cfg5) axis is sharded, no collective.
 """
 import ctypes
 import json
+import multiprocessing as mp
 import os
 import sys
 import time
 
 import numpy as np
-import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from oracle import rgf_oracle  # noqa: E402  (checker only)
-from transport_b200 import _lib, configs, leads  # noqa: E402
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
-lib = _lib.load()
-if os.environ.get("TX_VARIANT"):
-    _lib.check(lib.tx_set_variant(int(os.environ["TX_VARIANT"])))
-if os.environ.get("TX_KMAX"):
-    _lib.check(lib.tx_set_option(1, int(os.environ["TX_KMAX"])))
-if os.environ.get("TX_GEXP"):
-    _lib.check(lib.tx_set_option(2, int(os.environ["TX_GEXP"])))
-if os.environ.get("TX_NO_STRUCTURE"):
-    _lib.check(lib.tx_set_option(0, 0))
-dev = torch.device("cuda", 0)
-torch.cuda.set_device(0)
-flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+import benchutil as bu  # noqa: E402
+from transport_b200 import _lib, configs, shard  # noqa: E402
 
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-def dev_c(a):
-    return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
+WORKLOADS = {
+    "cfg1": "cfg1: rbbarrier spinless chain with rectangular barrier, n_loc_dof=1, M=13, 10^4 energies",
+    "cfg2": "cfg2: rbmenez-style two spin-1/2 impurities, n_loc_dof=8, M=8, 1000 J x 1000 E, all 8 sources",
+    "cfg3": "cfg3: disordered scattering region, n_loc_dof=8, N=10^4 sites (M=10002), 10^5 energies, all 8 sources",
+    "cfg4": "cfg4: square-lattice ribbon, n_loc_dof=64, L=32 slices (M=34), 4096 energies, Sancho-Rubio leads eta=1e-8, Caroli trace",
+    "cfg5": "cfg5: bardeen rbstep sweep, 256 step heights per pass, N_L=N_R=200 and 800 (S=451, 1651), 99 bias points",
+}
 
 
-def fp64_peak():
-    v, ms = ctypes.c_double(), ctypes.c_double()
-    _lib.check(lib.tx_measure_fp64_peak(ctypes.byref(v), ctypes.byref(ms)))
-    return v.value
+def _slice(n_base, env, scaling):
+    """This rank's contiguous slice of the unit axis: weak = a grid world x finer, strong = the base grid split."""
+    total = n_base * env.world if scaling == "weak" else n_base
+    lo, hi = shard.split_range(total, env.world, env.rank)
+    return total, lo, hi
 
 
-def timed(fn, steps=5, warmup=3):
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    ms = []
-    for _ in range(steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms.append(a.elapsed_time(b))
-    return float(np.mean(ms))
+def _std(name, env, scaling, units_total, ms, extra):
+    out = {"workload": WORKLOADS[name], "value": units_total / (ms * 1e-3), "unit": bu.UNIT, "ms_per_step": ms,
+           "n_gpus": env.world, "scaling": scaling, "units_per_step_all_gpus": int(units_total)}
+    out.update(extra)
+    return out
 
 
-def rel_err(got, want):
-    scale = np.maximum(np.abs(want), 1e-13 * np.abs(want).max(axis=-1, keepdims=True))
-    return float(np.max(np.abs(got - want) / np.where(scale == 0, 1, scale)))
+# ---------------------------------------------------------------------------------------------- CPU legs
+def _cpu_kernel_loops(args):
+    """Reference-loop port (oracle.wfm_oracle.kernel_loops) over a list of energies x sources."""
+    bu.one_thread_blas()
+    from oracle import wfm_oracle
+    h, tnn, tnnn, Es, srcs = args
+    t0 = time.perf_counter()
+    acc = 0.0
+    for E in Es:
+        for s in srcs:
+            Rs, Ts = wfm_oracle.kernel_loops(h, tnn, tnnn, 1.0, E, "g_closed", s, False, False, all_debug=False)
+            acc += Ts.sum()
+    return time.perf_counter() - t0, acc
 
 
-def run_small(name, h, tnn, Es, n_src_all, flops_per_point, check_idx, steps):
-    """Closed-form leads, scalar hopping, n <= 16: tx_transmission_sweep_dev."""
-    n, M, nE = h.shape[-1], h.shape[0], len(Es)
-    d_h, d_t, d_E = dev_c(h), dev_c(tnn), dev_c(Es)
-    R = torch.empty((nE, n, n), dtype=torch.float64, device=dev)
+def _cpu_rgf(args):
+    bu.one_thread_blas()
+    from oracle import rgf_oracle
+    h, tnn, Es, srcs = args
+    t0 = time.perf_counter()
+    rgf_oracle.transmission_closed(h, tnn, Es, srcs)
+    return time.perf_counter() - t0, 0.0
+
+
+def _cpu_ribbon(args):
+    """numpy restatement of cfg4's pipeline for a few energies: Sancho-Rubio leads + recursive sweep + Caroli trace."""
+    bu.one_thread_blas()
+    from oracle import rgf_oracle
+    h, tnn, Es, eta = args
+    t0 = time.perf_counter()
+    z = Es + 1j * eta
+    gL, _ = rgf_oracle.sancho_rubio(h[0], tnn[0], z, -1)
+    gR, _ = rgf_oracle.sancho_rubio(h[-1], tnn[-1], z, 1)
+    SL = np.conj(tnn[0]).T @ gL @ tnn[0]
+    SR = tnn[-1] @ gR @ np.conj(tnn[-1]).T
+    _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, SL, SR)
+    car = rgf_oracle.caroli_trace(GN0, SL, SR)
+    return time.perf_counter() - t0, float(car.sum())
+
+
+def _cpu_bardeen(args):
+    bu.one_thread_blas()
+    from oracle import bardeen_oracle as bo
+    VRs, NLR = args
+    one = np.eye(1)
+    HC = _barrier_HC()
+    t0 = time.perf_counter()
+    for v in VRs:
+        bo.kernel_well(one, one, one, 0.5 * one, 0.0 * one, (v + 0.5) * one, v * one, 0.5 * one, 20, NLR, NLR, HC, HC, one,
+                       0.1 * one, interval=1e-2)
+    return time.perf_counter() - t0, 0.0
+
+
+def _pool_rate(worker, chunks, units):
+    """Runs `chunks` on one worker process each; returns (units/s aggregate, wall s, cores)."""
+    cores = len(chunks)
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(worker, chunks)
+        wall = time.perf_counter() - t0
+    return units / wall, wall, cores
+
+
+# ---------------------------------------------------------------------------------------------- cfg1 / cfg3
+def _run_small_blocks(name, env, h, tnn, tnnn, Es_fn, n_base, flops_per_point, steps, warmup, scaling, want_cpu, want_e2e,
+                      parity_fn, cpu_fn):
+    torch = env.torch
+    lib = env.lib
+    n, M = h.shape[-1], h.shape[0]
+    total, lo, hi = _slice(n_base, env, scaling)
+    Es = Es_fn(total)[lo:hi]
+    nE = len(Es)
+    d_h, d_t, d_E = env.dev_c(h), env.dev_c(tnn), env.dev_c(Es)
+    R = torch.empty((nE, n, n), dtype=torch.float64, device=env.dev)
     T = torch.empty_like(R)
-    res = torch.empty((nE, n), dtype=torch.float64, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    res = torch.empty((nE, n), dtype=torch.float64, device=env.dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=env.dev)
+    st = env.stream.cuda_stream
 
     def step():
         _lib.check(lib.tx_transmission_sweep_dev(d_h.data_ptr(), 1, None, None, d_t.data_ptr(), 1, n, M, 1,
                                                  d_E.data_ptr(), nE, _lib.TX_LEAD_CLOSED, None, None, 1,
                                                  _lib.TX_HOP_SCALAR, None, None, n, R.data_ptr(), T.data_ptr(),
                                                  res.data_ptr(), None, flag.data_ptr(), st))
-    ms = timed(step, steps=steps)
-    assert int(flag.item()) == 0
-    Th = T.cpu().numpy()
-    Rh = R.cpu().numpy()
-    resid = float(np.nanmax(np.abs(res.cpu().numpy())))
-    t0 = time.perf_counter()
-    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es[check_idx], np.eye(n))
-    cpu_s = time.perf_counter() - t0
-    err = max(rel_err(Th[check_idx], oT), rel_err(Rh[check_idx], oR))
-    # conditioning floor: how much the ORACLE's own answer moves when E is perturbed by ~1 ulp
-    pR, pT = rgf_oracle.transmission_closed(h, tnn, Es[check_idx] * (1 + 2.2e-16), np.eye(n))
-    floor = max(rel_err(pT, oT), rel_err(pR, oR))
-    peak = fp64_peak()
-    ach = flops_per_point * nE / (ms * 1e-3) / 1e12
-    return {"config": name, "n": n, "M": M, "points": nE, "sources": n, "ms_per_sweep": ms,
-            "points_per_s": nE / (ms * 1e-3), "flops_per_point": flops_per_point,
-            "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak},
-            "parity_max_rel_err_vs_oracle": err, "oracle_change_under_1ulp_energy_perturbation": floor,
-            "checked_points": int(len(check_idx)),
-            "unitarity_max_abs": resid,
-            "cpu_oracle_rgf_numpy_points_per_s_1core": len(check_idx) / cpu_s}
+    sampler = bu.ClockSampler(env)
+    l0 = int(lib.tx_launch_counter())
+    ms, wall = env.timed(step, steps, warmup, sampler)
+    launches = (int(lib.tx_launch_counter()) - l0) * steps // (steps + max(warmup, 3))
+    assert int(flag.item()) == 0, "singular block in the benchmark sweep"
+    Th, Rh = T.cpu().numpy(), R.cpu().numpy()
+    resid = np.abs(res.cpu().numpy())
+    peak = env.fp64_peak()
+    hbm, hbm_src = bu.hbm_peak()
+    ach = flops_per_point * nE / (ms * 1e-3) / 1e12            # this rank's kernel: nE points in ms (max over ranks)
+    bytes_pt = 24 + 16 * n * n
+    roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "flops_per_point": flops_per_point, "kernel_ms": ms,
+            "peak_source": "tx_measure_fp64_peak (register-resident DFMA loop, measured in this run)",
+            "hbm": {"achieved": bytes_pt * nE / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "frac": bytes_pt * nE / (ms * 1e-3) / 1e9 / hbm, "bytes_per_point": bytes_pt, "peak_source": hbm_src}}
+    out = _std(name, env, scaling, total, ms, {"roofline": roof, "gpu_launches": launches, "clocks": sampler.summary(),
+                                               "unitarity_max_abs": float(np.nanmax(resid)),
+                                               "unitarity_median_abs": float(np.nanmedian(resid))})
+    if env.rank == 0:
+        out.update(parity_fn(Es, Rh, Th, lo))
+    if want_e2e:
+        from transport_b200.sweep import transmission_sweep
+        Rp = torch.empty((1, nE, n, n), dtype=torch.float64, pin_memory=True).numpy()
+        Tp = torch.empty((1, nE, n, n), dtype=torch.float64, pin_memory=True).numpy()
+        ph, pt, pE = env.pin(h), env.pin(tnn), env.pin(Es)
+        transmission_sweep(ph, pt, pE, out=(Rp, Tp))
+        env.barrier()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            transmission_sweep(ph, pt, pE, out=(Rp, Tp))
+            _ = float(Tp[0, 0, 0, 0])
+        env.barrier()
+        dt = env.max_over_ranks((time.perf_counter() - t0) / reps)
+        out["e2e"] = {"value": total / dt, "unit": bu.UNIT, "h2d_bytes_per_step": int(ph.nbytes + pt.nbytes + pE.nbytes),
+                      "d2h_bytes_per_step": int(Rp.nbytes + Tp.nbytes), "ms_per_step": dt * 1e3,
+                      "api": "transport_b200.sweep.transmission_sweep -> tx_transmission_sweep_spin (host pointers)"}
+        assert np.array_equal(Tp[0], Th), "e2e path and device-resident path disagree"
+    if want_cpu and env.rank == 0 and env.world == 1:
+        out["cpu_baseline"] = cpu_fn()
+    return out
 
 
-def cfg1():
-    h, tnn, _ = configs.barrier_blocks(0.4, 11)
-    Es = configs.barrier_energies(10_000)
-    return run_small("cfg1 rbbarrier n=1 M=13, 1e4 energies", h, tnn, Es, 1, 8 * 1 * 13 * 2, np.arange(0, 10_000, 97), 10)
+def run_cfg1(env, steps=20, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False):
+    h, tnn, tnnn = configs.barrier_blocks(0.4, 11)
+    n_base = 10_000
+    g = np.load(os.path.join(GOLDEN, "cfg1_barrier.npz"))
+
+    def parity(Es, Rh, Th, lo):
+        if env.world > 1:
+            return {}
+        got_T, got_R = Th[::50, 0], Rh[::50, 0]
+        err = max(bu.rel_err(got_T, g["T"][:, 0]), bu.rel_err(got_R, g["R"][:, 0]))
+        return {"parity_max_rel_err": err, "parity_against": "tests/golden/cfg1_barrier.npz (unmodified reference, every 50th energy)"}
+
+    def cpu():
+        cores = os.cpu_count() or 1
+        Es = configs.barrier_energies(n_base)
+        chunks = [(h, tnn, tnnn, Es[i::cores], [np.array([1.0])]) for i in range(cores)]
+        rate, wall, cores = _pool_rate(_cpu_kernel_loops, chunks, n_base)
+        return {"value": rate, "unit": bu.UNIT, "cores": cores, "kind": "port",
+                "sample": "all %d energies x 1 source, reference-loop port (dense assembly + inverse), %.1f s wall" % (n_base, wall)}
+
+    return _run_small_blocks("cfg1", env, h, tnn, tnnn, lambda k: configs.barrier_energies(k), n_base, 8 * 1 * 13 * 2, steps, warmup,
+                             scaling, want_cpu, want_e2e, parity, cpu)
 
 
-def cfg3(small=False):
+def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False):
     N = 1000 if small else 10_000
-    nE = 10_000 if small else 100_000
-    h, tnn, _ = configs.disordered_blocks(N=N, n=8, W=0.05, seed=1234)
-    Es = np.linspace(-1.9, 1.9, nE).astype(complex)
-    idx = np.arange(0, nE, nE // 8)
-    return run_small("cfg3 disordered chain n=8 N=%d, %d energies" % (N, nE), h, tnn, Es, 8,
-                     8 * 8 ** 3 * (N + 2) * 2, idx, 3)
+    n_base = 10_000 if small else 100_000
+    h, tnn, tnnn = configs.disordered_blocks(N=N, n=8, W=0.05, seed=1234)
+    hp_path = os.path.join(GOLDEN, "cfg3_hp_M10002.npz")
+
+    def parity(Es, Rh, Th, lo):
+        from oracle import rgf_oracle
+        out = {}
+        if not small and env.world == 1 and os.path.exists(hp_path):
+            g = np.load(hp_path)
+            idx = g["idx"]
+            eT = np.abs(Th[idx] - g["T_hp"]) / np.maximum(np.abs(g["T_hp"]), 1e-13 * np.abs(g["T_hp"]).max(-1, keepdims=True))
+            eR = np.abs(Rh[idx] - g["R_hp"]) / np.maximum(np.abs(g["R_hp"]), 1e-13 * np.abs(g["R_hp"]).max(-1, keepdims=True))
+            dev = np.maximum(eT.max(axis=(1, 2)), eR.max(axis=(1, 2)))                 # per energy
+            f64 = g["f64_err"]                                                        # numpy float64 recursion vs truth
+            kap = g["kappa"]
+            out.update({"parity_max_rel_err": float(dev.max()),
+                        "parity_against": "tests/golden/cfg3_hp_M10002.npz: long-double recursion (eps 1.1e-19) validated "
+                                          "by mpmath at 50 digits; %d energies incl. the worst-unitarity ones" % len(idx),
+                        "float64_numpy_oracle_max_rel_err_vs_extended_precision": float(f64.max()),
+                        "device_over_float64_oracle_error_ratio_median": float(np.median(dev / np.maximum(f64, 1e-300))),
+                        "device_over_float64_oracle_error_ratio_max": float(np.max(dev / np.maximum(f64, 1e-300))),
+                        "kappa_max": float(kap.max()),
+                        "device_err_over_kappa_eps_max": float(np.max(dev / (kap * 2.2e-16))),
+                        "float64_oracle_err_over_kappa_eps_max": float(np.max(f64 / (kap * 2.2e-16)))})
+        else:
+            idx = np.arange(0, len(Es), max(1, len(Es) // 8))
+            oR, oT = rgf_oracle.transmission_closed(h, tnn, Es[idx], np.eye(8))
+            out.update({"parity_max_rel_err": max(bu.rel_err(Th[idx], oT), bu.rel_err(Rh[idx], oR)),
+                        "parity_against": "oracle/rgf_oracle.py (float64 numpy recursion) on %d energies" % len(idx)})
+        return out
+
+    def cpu():
+        from oracle import wfm_oracle
+        cores = os.cpu_count() or 1
+        # (a) the numpy restatement of the recursive algorithm at full length, one energy batch per core
+        per = 2
+        Es = np.linspace(-1.9, 1.9, cores * per).astype(complex)
+        chunks = [(h, tnn, Es[i::cores], np.eye(8)) for i in range(cores)]
+        rgf_rate, rgf_wall, _ = _pool_rate(_cpu_rgf, chunks, cores * per)
+        # (b) the reference's own algorithm (dense assembly + dense inverse, Python loops) at M in {64, 128, 256},
+        #     one source, fitted t(M) = a M^2 + b M^3 and extrapolated to M = 10 002; the
+        #     reference itself cannot run there: 102 GB dense matrix
+        Ms, ts = [32, 64, 128], []
+        for Mq in Ms:
+            hq, tq, t3q = configs.disordered_blocks(N=Mq - 2, n=8, W=0.05, seed=1234)
+            t0 = time.perf_counter()
+            wfm_oracle.kernel_loops(hq, tq, t3q, 1.0, complex(-0.7), "g_closed", np.eye(8)[0], False, False, all_debug=False)
+            ts.append(time.perf_counter() - t0)
+        A = np.array([[m ** 2, m ** 3] for m in Ms], dtype=float)
+        (a, b), *_ = np.linalg.lstsq(A, np.array(ts), rcond=None)
+        t_full = (a * (N + 2) ** 2 + b * (N + 2) ** 3) * 8                      # x 8 sources per point
+        return {"value": cores / t_full, "unit": bu.UNIT, "cores": cores, "kind": "port",
+                "sample": "EXTRAPOLATED: reference-loop port timed at M=%s (%s s per call), fit a M^2 + b M^3 -> %.3g s per point "
+                          "(8 sources) at M=%d, x %d cores; the dense path cannot run at this size (102 GB)"
+                          % (Ms, ["%.2f" % t for t in ts], t_full, N + 2, cores),
+                "rgf_numpy_restatement": {"value": rgf_rate, "unit": bu.UNIT, "cores": cores,
+                                          "sample": "%d energies x 8 sources at full length, %.1f s wall" % (cores * per, rgf_wall)}}
+
+    return _run_small_blocks("cfg3", env, h, tnn, tnnn, lambda k: np.linspace(-1.9, 1.9, k).astype(complex), n_base,
+                             8 * 8 ** 3 * (N + 2) * 2, steps, warmup, scaling, want_cpu, want_e2e, parity, cpu)
 
 
-def cfg4(small=False):
+# ---------------------------------------------------------------------------------------------- cfg4
+def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False):
+    torch = env.torch
+    lib = env.lib
     n = 32 if small else 64
-    nE = 256 if small else 4096
+    n_base = 256 if small else 4096
     h, tnn, _ = configs.ribbon_blocks(width=n, L=32, W=1.0, seed=1234)
-    Es = np.linspace(-3.5, 3.5, nE).astype(complex)
+    total, lo, hi = _slice(n_base, env, scaling)
+    Es = np.linspace(-3.5, 3.5, total).astype(complex)[lo:hi]
+    nE = len(Es)
     eta = 1e-8
     M = h.shape[0]
-    d_h, d_t, d_E = dev_c(h), dev_c(tnn), dev_c(Es)
-    sigL = torch.empty((nE, n, n, 2), dtype=torch.float64, device=dev)
+    d_h, d_t, d_E = env.dev_c(h), env.dev_c(tnn), env.dev_c(Es)
+    sigL = torch.empty((nE, n, n, 2), dtype=torch.float64, device=env.dev)
     sigR = torch.empty_like(sigL)
-    nit = torch.zeros((2, nE), dtype=torch.int32, device=dev)
-    ok = torch.zeros((2, nE), dtype=torch.int32, device=dev)
-    conv = torch.zeros((2, nE), dtype=torch.float64, device=dev)
-    car = torch.empty(nE, dtype=torch.float64, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    nit = torch.zeros((2, nE), dtype=torch.int32, device=env.dev)
+    ok = torch.zeros((2, nE), dtype=torch.int32, device=env.dev)
+    conv = torch.zeros((2, nE), dtype=torch.float64, device=env.dev)
+    car = torch.empty(nE, dtype=torch.float64, device=env.dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=env.dev)
     wse = int(lib.tx_sweep_workspace_elems(n, nE))
-    work = torch.empty((max(wse, 1), 2), dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    work = torch.empty((max(wse, 1), 2), dtype=torch.float64, device=env.dev)
+    st = env.stream.cuda_stream
     nn16 = n * n * 16
 
     def leads_step():
@@ -154,154 +308,217 @@ def cfg4(small=False):
                                                        _lib.TX_HOP_SCALAR, None, n, None, None, None, None,
                                                        car.data_ptr(), work.data_ptr() if wse else None,
                                                        flag.data_ptr(), st))
-    def leads_separable_step():   # the same leads by the separable closed form (h01 = -I): eta -> 0 limit
-        _lib.check(lib.tx_surface_gf_dev(d_h.data_ptr(), d_t.data_ptr(), n, d_E.data_ptr(), nE, -1, _lib.TX_GF_SEPARABLE,
-                                         0.0, 0.0, 0, 0, 0, None, sigL.data_ptr(), None, None, None, flag.data_ptr(), st))
-        _lib.check(lib.tx_surface_gf_dev(d_h.data_ptr() + (M - 1) * nn16, d_t.data_ptr() + (M - 2) * nn16, n,
-                                         d_E.data_ptr(), nE, 1, _lib.TX_GF_SEPARABLE, 0.0, 0.0, 0, 0, 0, None,
-                                         sigR.data_ptr(), None, None, None, flag.data_ptr(), st))
-    ms_leads_sep = timed(leads_separable_step, steps=2, warmup=1)
-    sweep_step()
-    torch.cuda.synchronize()
-    car_sep = car.cpu().numpy().copy()
-    ms_leads = timed(leads_step, steps=2, warmup=1)
-    ms_sweep = timed(sweep_step, steps=2, warmup=1)
+
+    def step():
+        leads_step()
+        sweep_step()
+
+    sampler = bu.ClockSampler(env)
+    l0 = int(lib.tx_launch_counter())
+    ms, wall = env.timed(step, steps, warmup, sampler)
+    launches = (int(lib.tx_launch_counter()) - l0) * steps // (steps + max(warmup, 3))
+    ms_leads, _ = env.timed(leads_step, max(1, steps // 2), 3)
+    ms_sweep, _ = env.timed(sweep_step, max(1, steps // 2), 3)
     assert bool(ok.all().item()), "Sancho-Rubio did not converge everywhere"
+    assert int(flag.item()) == 0
     n_it = float(nit.double().mean().item())
     carh = car.cpu().numpy()
-    idx = np.arange(0, nE, max(1, nE // 6))
-    SL = torch.view_as_complex(sigL[idx]).cpu().numpy()
-    SR = torch.view_as_complex(sigR[idx]).cpu().numpy()
-    _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es[idx], SL, SR)        # same tables on both sides
-    want = rgf_oracle.caroli_trace(GN0, SL, SR)
-    err = float(np.max(np.abs(carh[idx] - want) / np.maximum(np.abs(want), 1e-12)))
-    flops = 8 * n ** 3 * M * 2 + 2 * n_it * (8 + 6 * 8) * n ** 3
-    peak = fp64_peak()
-    ms = ms_leads + ms_sweep
+    flops_sweep = 8 * n ** 3 * M * 2
+    flops_leads = 2 * n_it * (8 + 6 * 8) * n ** 3
+    flops = flops_sweep + flops_leads
+    peak = env.fp64_peak()
     ach = flops * nE / (ms * 1e-3) / 1e12
-    return {"config": "cfg4 ribbon n=%d L=32, %d energies, Sancho-Rubio eta=1e-8" % (n, nE), "n": n, "M": M,
-            "points": nE, "ms_leads": ms_leads, "ms_sweep": ms_sweep, "points_per_s": nE / (ms * 1e-3),
-            "sancho_iterations_mean": n_it, "flops_per_point": flops,
-            "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak},
-            "parity_caroli_max_rel_err_vs_oracle_same_tables": err, "checked_points": int(len(idx)),
-            "separable_leads": {"ms_leads": ms_leads_sep, "points_per_s": nE / ((ms_leads_sep + ms_sweep) * 1e-3),
-                                "median_rel_diff_of_T_vs_sancho_eta_1e-8": float(np.median(np.abs(car_sep - carh) / np.maximum(np.abs(carh), 1e-12))),
-                                "note": "TX_GF_SEPARABLE: h01 = -I commutes with h00, g = U diag(g_closed) U^dag (eta -> 0)"},
-            "kernel": "CTA-per-point generic kernel; DMMA block products, shared-memory staged Gauss-Jordan inverse"}
+    roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "flops_per_point": flops, "kernel_ms": ms, "sancho_iterations_mean": n_it,
+            "kernels": {"surface_gf_sancho (both leads)": {"ms": ms_leads, "flops_per_point": flops_leads,
+                                                           "frac": flops_leads * nE / (ms_leads * 1e-3) / 1e12 / peak},
+                        "rgf_sweep_generic": {"ms": ms_sweep, "flops_per_point": flops_sweep,
+                                              "frac": flops_sweep * nE / (ms_sweep * 1e-3) / 1e12 / peak}},
+            "peak_source": "tx_measure_fp64_peak (register-resident DFMA loop, measured in this run; the DMMA path shares the pipe)"}
+    out = _std("cfg4", env, scaling, total, ms, {"roofline": roof, "gpu_launches": launches, "clocks": sampler.summary()})
+    if env.rank == 0:
+        from oracle import rgf_oracle
+        idx = np.arange(0, nE, max(1, nE // 6))
+        SL = torch.view_as_complex(sigL[idx]).cpu().numpy()
+        SR = torch.view_as_complex(sigR[idx]).cpu().numpy()
+        _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es[idx], SL, SR)
+        want = rgf_oracle.caroli_trace(GN0, SL, SR)
+        out["parity_max_rel_err"] = float(np.max(np.abs(carh[idx] - want) / np.maximum(np.abs(want), 1e-12)))
+        out["parity_against"] = ("oracle/rgf_oracle.py Caroli trace on the device's own Sancho-Rubio tables, %d energies "
+                                 "(parity of multi-channel leads is unpinned by the reference: g_iter refuses n>2)" % len(idx))
+        hp_path = os.path.join(GOLDEN, "cfg4_leads_hp.npz")
+        if not small and env.world == 1 and os.path.exists(hp_path):
+            g = np.load(hp_path)
+            li = g["idx"]
+            SLd = torch.view_as_complex(sigL[li]).cpu().numpy()
+            den = np.abs(g["sigL_hp"]).max(axis=(1, 2), keepdims=True)
+            out["leads_max_err_vs_extended_precision"] = float(np.max(np.abs(SLd - g["sigL_hp"]) / den))
+            out["leads_float64_numpy_err_vs_extended_precision"] = float(g["f64_err"].max())
+    if want_e2e:
+        from transport_b200.sweep import transmission_sweep
+        ph, pt, pE = env.pin(h), env.pin(tnn), env.pin(Es)
+        car2 = transmission_sweep(ph, pt, pE, converger=("sancho", eta), want_rt=False, want_caroli=True)
+        env.barrier()
+        reps = 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            car2 = transmission_sweep(ph, pt, pE, converger=("sancho", eta), want_rt=False, want_caroli=True)
+            _ = float(car2[0, 0])
+        env.barrier()
+        dt = env.max_over_ranks((time.perf_counter() - t0) / reps)
+        assert np.array_equal(car2[0], carh), "e2e path and device-resident path disagree"
+        out["e2e"] = {"value": total / dt, "unit": bu.UNIT, "h2d_bytes_per_step": int(ph.nbytes + pt.nbytes + pE.nbytes),
+                      "d2h_bytes_per_step": int(car2.nbytes), "ms_per_step": dt * 1e3,
+                      "api": "transport_b200.sweep.transmission_sweep(converger=('sancho', eta), want_caroli) -> "
+                             "tx_transmission_sweep_spin (host pointers; self-energy tables stay on the device)"}
+    if want_cpu and env.rank == 0 and env.world == 1:
+        cores = os.cpu_count() or 1
+        per = 2
+        Ec = np.linspace(-3.5, 3.5, cores * per).astype(complex)
+        chunks = [(h, tnn, Ec[i::cores], eta) for i in range(cores)]
+        rate, wall_c, cores = _pool_rate(_cpu_ribbon, chunks, cores * per)
+        out["cpu_baseline"] = {"value": rate, "unit": bu.UNIT, "cores": cores, "kind": "port",
+                               "sample": "numpy restatement (Sancho-Rubio + recursive sweep + Caroli trace; the reference refuses "
+                                         "n>2 iterative leads, wfm/__init__.py:502) on %d energies, %.1f s wall" % (cores * per, wall_c)}
+    return out
 
 
-def cfg5(small=False):
-    """rbstep.py-style sweep of the right-well step height (rbstep.py:43-104): P geometries in one device pass —
-    bound states of both wells, window-averaged matrix elements, current over the bias grid of rbbarrier.py:447-450."""
-    from oracle import bardeen_oracle as bo                      # checker + CPU baseline only
+# ---------------------------------------------------------------------------------------------- cfg5
+def _barrier_HC():
+    HC = np.zeros((11, 11, 1, 1), dtype=complex)
+    for j in range(11):
+        HC[j, j] = 0.4
+    for j in range(10):
+        HC[j, j + 1] = HC[j + 1, j] = -1.0
+    return HC
+
+
+def run_cfg5(env, steps=5, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False):
+    """rbstep.py-style sweep of the right-well step height (rbstep.py:43-104): P geometries per device pass — bound
+    states of both wells, window-averaged matrix elements, current over the bias grid of rbbarrier.py:447-450.
+    The unit of `value` is geometries/s; the two sizes N_LR = 200 and 800 are reported side by side and `value` is
+    the S = 451 one (rbstep.py's own size)."""
+    torch = env.torch
+    lib = env.lib
     from transport_b200 import bardeen
-    out = []
     one = np.eye(1)
     sizes = (200,) if small else (200, 800)
-    if os.environ.get("TX_CFG5_NLR"):
-        sizes = (int(os.environ["TX_CFG5_NLR"]),)
-    if os.environ.get("TX_EIG_MODE"):
-        _lib.check(lib.tx_set_option(3, int(os.environ["TX_EIG_MODE"])))
+    P_base = 64 if small else 256
+    per_size = []
     for NLR in sizes:
-        P = 64 if small else 256
-        VRs = np.linspace(-0.05, 0.05, P)
+        total, lo, hi = _slice(P_base, env, scaling)
+        VRs = np.linspace(-0.05, 0.05, total)[lo:hi]
+        P = len(VRs)
         Vinf, VL = 0.5 * one, 0.0 * one
-        HC = np.zeros((11, 11, 1, 1), dtype=complex)
-        for j in range(11):
-            HC[j, j] = 0.4
-        for j in range(10):
-            HC[j, j + 1] = HC[j + 1, j] = -1.0
-        arrs = {k: [] for k in ("dL", "eL", "dR", "eR", "h0", "hU", "hL")}
-        t0 = time.time()
-        for v in VRs:
-            VR = v * one
-            bL = bardeen.hsys_site_blocks(one, one, one, Vinf, VL, Vinf, 20, NLR, NLR, HC)
-            bR = bardeen.hsys_site_blocks(one, one, one, Vinf, VR + Vinf, VR, 20, NLR, NLR, HC)
-            bS = bardeen.hsys_site_blocks(one, one, one, Vinf, VL, VR, 20, NLR, NLR, HC)
-            a, b = bardeen._channel_tridiagonals(bL); arrs["dL"].append(a); arrs["eL"].append(b)
-            a, b = bardeen._channel_tridiagonals(bR); arrs["dR"].append(a); arrs["eR"].append(b)
-            hd = [np.real(x - y) for x, y in zip(bS, bL)]
-            arrs["h0"].append(hd[0]); arrs["hU"].append(hd[1]); arrs["hL"].append(hd[2])
-        host_assembly_s = time.time() - t0
-        A = {k: np.ascontiguousarray(np.array(v), dtype=np.float64) for k, v in arrs.items()}
-        S = A["dL"].shape[-1]
+        HC = _barrier_HC()
         interval = 1e-2
+        t0 = time.perf_counter()
+        A = bardeen.step_sweep_arrays(one, one, one, Vinf, VL, VRs, 20, NLR, NLR, HC)
+        host_assembly_s = time.perf_counter() - t0
+        S = A["dL"].shape[-1]
         cut = np.full((P, 1), 0.1 - 2.0)
-        # e2e through the host entry (H2D + counts + second pass sized from the counts + D2H)
-        t0 = time.time()
         r = bardeen.wells_batched(A["dL"], A["eL"], A["dR"], A["eR"], cut, cut + interval, cut, A["h0"], A["hU"], A["hL"],
                                   interval, sign_fix=True)
-        e2e_first_s = time.time() - t0
-        t0 = time.time()
-        r = bardeen.wells_batched(A["dL"], A["eL"], A["dR"], A["eR"], cut, cut + interval, cut, A["h0"], A["hU"], A["hL"],
-                                  interval, sign_fix=True)
-        e2e_s = time.time() - t0
-        ms = int(max(r["nL"].max(), r["nR_states"].max()))
-        # device resident
-        D = {k: torch.from_numpy(v).to(dev) for k, v in A.items()}
-        dcut = torch.from_numpy(cut).to(dev); dcut2 = torch.from_numpy(cut + interval).to(dev)
-        EL = torch.zeros((P, 1, ms), dtype=torch.float64, device=dev); ER = torch.zeros_like(EL)
-        Mavg = torch.zeros((P, 1, ms, 1), dtype=torch.float64, device=dev)
-        nL = torch.zeros((P, 1), dtype=torch.int32, device=dev); nRs = torch.zeros_like(nL); nRb = torch.zeros_like(nL)
-        ws = torch.empty(int(lib.tx_bardeen_workspace_bytes(P, 1, S, ms)), dtype=torch.uint8, device=dev)
-        Vb = torch.linspace(-0.05, 0.05, 99, dtype=torch.float64, device=dev)
-        Iab = torch.zeros((P, 1, 1, 99), dtype=torch.float64, device=dev)
+        ms_states = int(max(r["nL"].max(), r["nR_states"].max()))
+        D = {k: env.dev_f(v) for k, v in A.items()}
+        dcut, dcut2 = env.dev_f(cut), env.dev_f(cut + interval)
+        EL = torch.zeros((P, 1, ms_states), dtype=torch.float64, device=env.dev)
+        ER = torch.zeros_like(EL)
+        Mavg = torch.zeros((P, 1, ms_states, 1), dtype=torch.float64, device=env.dev)
+        nL = torch.zeros((P, 1), dtype=torch.int32, device=env.dev)
+        nRs, nRb = torch.zeros_like(nL), torch.zeros_like(nL)
+        ws = torch.empty(int(lib.tx_bardeen_workspace_bytes(P, 1, S, ms_states)), dtype=torch.uint8, device=env.dev)
+        Vb = torch.linspace(-0.05, 0.05, 99, dtype=torch.float64, device=env.dev)
+        Iab = torch.zeros((P, 1, 1, 99), dtype=torch.float64, device=env.dev)
         M2 = torch.zeros_like(Mavg)
-        st = torch.cuda.current_stream().cuda_stream
-
-        def wells_step():
-            _lib.check(lib.tx_bardeen_wells_dev(D["dL"].data_ptr(), D["eL"].data_ptr(), D["dR"].data_ptr(), D["eR"].data_ptr(),
-                                                dcut.data_ptr(), dcut2.data_ptr(), dcut.data_ptr(), D["h0"].data_ptr(),
-                                                D["hU"].data_ptr(), D["hL"].data_ptr(), P, 1, S, ms, interval, 1,
-                                                EL.data_ptr(), nL.data_ptr(), ER.data_ptr(), nRs.data_ptr(), nRb.data_ptr(),
-                                                Mavg.data_ptr(), ws.data_ptr(), st))
+        st = env.stream.cuda_stream
 
         def step():
-            wells_step()
+            _lib.check(lib.tx_bardeen_wells_dev(D["dL"].data_ptr(), D["eL"].data_ptr(), D["dR"].data_ptr(), D["eR"].data_ptr(),
+                                                dcut.data_ptr(), dcut2.data_ptr(), dcut.data_ptr(), D["h0"].data_ptr(),
+                                                D["hU"].data_ptr(), D["hL"].data_ptr(), P, 1, S, ms_states, interval, 1,
+                                                EL.data_ptr(), nL.data_ptr(), ER.data_ptr(), nRs.data_ptr(), nRb.data_ptr(),
+                                                Mavg.data_ptr(), ws.data_ptr(), st))
             torch.mul(Mavg, Mavg, out=M2)
-            _lib.check(lib.tx_bardeen_current_dev(EL.data_ptr(), M2.data_ptr(), P, 1, ms, Vb.data_ptr(), 99, -1.95, 0.01,
+            _lib.check(lib.tx_bardeen_current_dev(EL.data_ptr(), M2.data_ptr(), P, 1, ms_states, Vb.data_ptr(), 99, -1.95, 0.01,
                                                   Iab.data_ptr(), st))
-        def eigenvalues_only_step():
-            for dd, ee, cc, nn, EE in ((D["dL"], D["eL"], dcut, nL, EL), (D["dR"], D["eR"], dcut2, nRs, ER)):
-                _lib.check(lib.tx_tridiag_eigh_below_dev(dd.data_ptr(), ee.data_ptr(), S, P, cc.data_ptr(), nn.data_ptr(), ms,
-                                                         EE.data_ptr(), None, None, st))
-        ms_step = timed(step, steps=5, warmup=3)
-        ms_evals = timed(eigenvalues_only_step, steps=5, warmup=2)
-        ms_wells = timed(wells_step, steps=5, warmup=3)
+        sampler = bu.ClockSampler(env)
+        l0 = int(lib.tx_launch_counter())
+        ms, wall = env.timed(step, steps, warmup, sampler)
+        launches = (int(lib.tx_launch_counter()) - l0) * steps // (steps + max(warmup, 3))
         assert np.array_equal(nL.cpu().numpy(), r["nL"]) and np.allclose(Mavg.cpu().numpy(), r["Mavg"], rtol=1e-12, atol=0)
-        # parity + CPU baseline: the oracle's kernel_well (dense LAPACK eigh x4, as the reference) on a few geometries
-        idx = [0, P // 2, P - 1] if NLR == 200 else [P // 3]
-        err, cpu_s = 0.0, 0.0
-        for p in idx:
-            VR = VRs[p] * one
-            t0 = time.time()
-            E0, M0 = bo.kernel_well(one, one, one, Vinf, VL, VR + Vinf, VR, Vinf, 20, NLR, NLR, HC, HC, one, 0.1 * one,
-                                    interval=interval)
-            cpu_s += time.time() - t0
-            mu, nu = int(r["nL"][p, 0]), int(r["nR_below"][p, 0])
-            M = r["Mavg"][p, 0, :mu, 0] ** 2
-            M[nu:] = 0.0
-            big = M0[0, :, 0] > 1e-30
-            err = max(err, float(np.max(np.abs(r["EL"][p, 0, :mu] - E0[0].real))),
-                      float(np.max(np.abs(M[big] - M0[0, big, 0]) / M0[0, big, 0])) if big.any() else 0.0)
         states = int(r["nL"].sum() + r["nR_states"].sum())
-        out.append({"config": "cfg5 bardeen rbstep sweep: %d step heights, N_L=N_R=%d (S=%d), interval 1e-2, 99 bias points" % (P, NLR, S),
-                    "geometries": P, "S": S, "bound_states_total": states, "max_states": ms,
-                    "ms_per_sweep_device_resident": ms_step, "ms_wells_only": ms_wells, "ms_eigenvalues_only": ms_evals,
-                    "geometries_per_s": P / (ms_step * 1e-3),
-                    "e2e_host_call_s": e2e_s, "e2e_first_call_s": e2e_first_s, "e2e_geometries_per_s": P / e2e_s,
-                    "host_assembly_s": host_assembly_s,
-                    "cpu_oracle_dense_eigh_s_per_geometry_1core": cpu_s / len(idx),
-                    "speedup_device_resident_vs_1core": (cpu_s / len(idx)) / (ms_step * 1e-3 / P),
-                    "parity_max_err_vs_oracle(E abs, |M|^2 rel)": err, "checked_geometries": len(idx),
-                    "kernel": "Sturm multisection (warp per eigenvalue) + twisted factorisation + windowed dot products"})
+        # executed work of the eigenvalue stage: states x Sturm counts x S sites x 3 FP64 instructions (DESIGN.md §3)
+        item = {"N_LR": NLR, "S": S, "geometries_per_gpu": P, "bound_states": states, "max_states": ms_states,
+                "ms_per_step": ms, "geometries_per_s": total / (ms * 1e-3), "gpu_launches": launches,
+                "clocks": sampler.summary(), "host_assembly_s_python": host_assembly_s,
+                "roofline": {"bound": "fp64 (latency: chains of S dependent FMAs on shared-memory resident data)",
+                             "achieved": states * 53 * S * 3 * 2 / (ms * 1e-3) / 1e12, "peak": env.fp64_peak(), "unit": "TFLOP/s",
+                             "frac": states * 53 * S * 3 * 2 / (ms * 1e-3) / 1e12 / env.fp64_peak(), "traffic": None,
+                             "note": "algorithmic work = 53 bisection counts x S sites x 3 FP64 instructions per eigenvalue "
+                                     "(DESIGN.md §3); the kernels are parallelism-bound, not pipe-bound"}}
+        if env.rank == 0:
+            from oracle import bardeen_oracle as bo
+            idx = [0, P // 2, P - 1] if NLR == 200 else [P // 3]
+            err, cpu_s = 0.0, 0.0
+            for p in idx:
+                VR = VRs[p] * one
+                t0 = time.perf_counter()
+                E0, M0 = bo.kernel_well(one, one, one, Vinf, VL, VR + Vinf, VR, Vinf, 20, NLR, NLR, HC, HC, one, 0.1 * one,
+                                        interval=interval)
+                cpu_s += time.perf_counter() - t0
+                mu, nu = int(r["nL"][p, 0]), int(r["nR_below"][p, 0])
+                Msq = r["Mavg"][p, 0, :mu, 0] ** 2
+                Msq[nu:] = 0.0
+                big = M0[0, :, 0] > 1e-30
+                err = max(err, float(np.max(np.abs(r["EL"][p, 0, :mu] - E0[0].real))),
+                          float(np.max(np.abs(Msq[big] - M0[0, big, 0]) / M0[0, big, 0])) if big.any() else 0.0)
+            item["parity_max_err"] = err
+            item["parity_against"] = "oracle/bardeen_oracle.kernel_well (dense eigh as the reference; pinned to reference goldens) on %d geometries: E absolute, |M|^2 relative" % len(idx)
+            item["cpu_oracle_s_per_geometry_1core_blas_default"] = cpu_s / len(idx)
+        if want_e2e:
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                rr = bardeen.step_sweep(one, one, one, Vinf, VL, VRs, 20, NLR, NLR, HC, E_cutoff=0.1, interval=interval,
+                                        Vb=np.linspace(-0.05, 0.05, 99), muR=-1.95, kBT=0.01)
+                _ = float(rr["I"][0, 0, 0, 0])
+            env.barrier()
+            dt = env.max_over_ranks((time.perf_counter() - t0) / reps)
+            assert np.allclose(rr["I"], Iab.cpu().numpy(), rtol=1e-12, atol=1e-300)
+            item["e2e"] = {"value": total / dt, "unit": "geometries/s", "ms_per_step": dt * 1e3,
+                           "h2d_bytes_per_step": int(rr["h2d_bytes"]), "d2h_bytes_per_step": int(rr["d2h_bytes"]),
+                           "api": "transport_b200.bardeen.step_sweep (geometry parameters in, states / matrix elements / current out)"}
+        if want_cpu and env.rank == 0 and env.world == 1:
+            cores = min(os.cpu_count() or 1, 8 if NLR == 800 else 32)
+            chunks = [([VRs[(i * 7) % P]], NLR) for i in range(cores)]
+            rate, wall_c, cores = _pool_rate(_cpu_bardeen, chunks, cores)
+            item["cpu_baseline"] = {"value": rate, "unit": "geometries/s", "cores": cores, "kind": "port",
+                                    "sample": "%d geometries (one per core), oracle kernel_well = the reference's dense-eigh algorithm, %.1f s wall" % (cores, wall_c)}
+        per_size.append(item)
+    head = per_size[0]
+    out = {"workload": WORKLOADS["cfg5"], "value": head["geometries_per_s"], "unit": "geometries/s", "ms_per_step": head["ms_per_step"],
+           "n_gpus": env.world, "scaling": scaling, "units_per_step_all_gpus": int(P_base * (env.world if scaling == "weak" else 1)),
+           "roofline": head["roofline"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "sizes": per_size}
+    for k in ("e2e", "cpu_baseline", "parity_max_err", "parity_against"):
+        if k in head:
+            out[k if k != "parity_max_err" else "parity_max_rel_err"] = head[k]
     return out
+
+
+RUNNERS = {"cfg1": run_cfg1, "cfg3": run_cfg3, "cfg4": run_cfg4, "cfg5": run_cfg5}
+
+
+def run(name, env, **kw):
+    return RUNNERS[name](env, **kw)
 
 
 if __name__ == "__main__":
     small = "--small" in sys.argv
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3", "cfg4"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3", "cfg4", "cfg5"]
+    env = bu.Env()
+    env.init_dist()
     for w in which:
-        out = {"cfg1": cfg1, "cfg3": lambda: cfg3(small), "cfg4": lambda: cfg4(small), "cfg5": lambda: cfg5(small)}[w]()
-        for line in (out if isinstance(out, list) else [out]):
-            print(json.dumps(line), flush=True)
+        res = run(w, env, small=small)
+        if env.rank == 0:
+            print(json.dumps(res), flush=True)

@@ -225,3 +225,75 @@ def test_batched_step_sweep_against_oracle(eig_mode):
         M = r["Mavg"][p, 0, :mu, 0] ** 2
         M[nu:] = 0.0
         assert m2_err(M, M0[0, :, 0]) < MTOL
+
+
+def _barrier_HC(n=1, J=0.0):
+    HC = np.zeros((11, 11, n, n), dtype=complex)
+    for j in range(11):
+        HC[j, j] = 0.4 * np.eye(n)
+        if n == 2 and j == 5:
+            HC[j, j] += J / 2 * np.array([[0, 1], [1, 0]])
+    for j in range(10):
+        HC[j, j + 1] = HC[j + 1, j] = -1.0 * np.eye(n)
+    return HC
+
+
+def test_region_sweep_matches_host_assembled_sweep():
+    """tx_bardeen_region_sweep (device-side assembly from region parameters, rbstep.py:43-104 as one pass) against the
+    same sweep through host-assembled arrays (wells_batched) and, per geometry, against kernel_well + current."""
+    one = np.eye(1)
+    HC = _barrier_HC()
+    VRs = np.linspace(-0.05, 0.05, 9)
+    Vinf, VL = 0.5 * one, 0.0 * one
+    interval = 1e-2
+    A = bardeen.step_sweep_arrays(one, one, one, Vinf, VL, VRs, 20, 60, 60, HC)
+    P = len(VRs)
+    cut = np.full((P, 1), 0.1 - 2.0)
+    r0 = bardeen.wells_batched(A["dL"], A["eL"], A["dR"], A["eR"], cut, cut + interval, cut, A["h0"], A["hU"], A["hL"],
+                               interval, sign_fix=True)
+    Vb = np.linspace(-0.05, 0.05, 11)
+    for attempt in range(2):          # second call: buffer capacity cached, single pass
+        r1 = bardeen.step_sweep(one, one, one, Vinf, VL, VRs, 20, 60, 60, HC, E_cutoff=0.1 * one, interval=interval,
+                                Vb=Vb, muR=-1.95, kBT=0.01, row_cut=True)
+        assert np.array_equal(r1["nL"], r0["nL"]) and np.array_equal(r1["nR_states"], r0["nR_states"])
+        assert np.array_equal(r1["nR_below"], r0["nR_below"])
+        ms = r0["EL"].shape[-1]
+        assert np.array_equal(r1["EL"][..., :ms], r0["EL"]) and np.array_equal(r1["Mavg"][:, :, :ms], r0["Mavg"])
+    for p in (0, 4, 8):
+        VR = VRs[p] * one
+        E, M = bardeen.kernel_well(one, one, one, Vinf, VL, VR + Vinf, VR, Vinf, 20, 60, 60, HC, HC, one, 0.1 * one,
+                                   interval=interval)
+        I = bardeen.current(E, M, Vb, one, -1.95, 0.01)
+        assert np.allclose(r1["I"][p], I, rtol=1e-12, atol=1e-300)
+
+
+def test_region_sweep_two_channels_with_hcprime():
+    """n_loc_dof = 2 with HCprime != HC (the kernel_well_prime arrangement, rbmenez_nosup_el.py:97-108) and per-geometry
+    potentials, against the host-assembled path."""
+    n = 2
+    I2 = np.eye(n)
+    HCp = _barrier_HC(n, 0.0)
+    HC = _barrier_HC(n, 0.5)
+    P = 3
+    VRv = np.array([[0.0, 0.01], [0.02, -0.01], [-0.03, 0.0]])
+    cutL = np.full((P, n), 0.1 - 2.0)
+    Vinf = 0.5 * I2
+    dL, eL, dR, eR, h0, hU, hL = [], [], [], [], [], [], []
+    for p in range(P):
+        VR = np.diag(VRv[p])
+        bL = bardeen.hsys_site_blocks(I2, I2, I2, Vinf, 0 * I2, Vinf, 8, 30, 30, HCp)
+        bR = bardeen.hsys_site_blocks(I2, I2, I2, Vinf, VR + Vinf, VR, 8, 30, 30, HCp)
+        bS = bardeen.hsys_site_blocks(I2, I2, I2, Vinf, 0 * I2, VR, 8, 30, 30, HC)
+        a, b = bardeen._channel_tridiagonals(bL); dL.append(a); eL.append(b)
+        a, b = bardeen._channel_tridiagonals(bR); dR.append(a); eR.append(b)
+        hd = [np.real(x - y) for x, y in zip(bS, bL)]
+        h0.append(hd[0]); hU.append(hd[1]); hL.append(hd[2])
+    r0 = bardeen.wells_batched(np.array(dL), np.array(eL), np.array(dR), np.array(eR), cutL, cutL, cutL, np.array(h0),
+                               np.array(hU), np.array(hL), 1e-2, sign_fix=False)
+    r1 = bardeen.region_sweep(I2, I2, I2, Vinf, np.zeros((1, n)), VRv + 0.5, VRv, np.full((1, n), 0.5), 8, 30, 30, HC, HCp,
+                              cutL, cutL, cutL, interval=1e-2, sign_fix=False)
+    ms = r0["EL"].shape[-1]
+    assert np.array_equal(r1["nL"], r0["nL"]) and np.array_equal(r1["nR_states"], r0["nR_states"])
+    assert np.array_equal(r1["EL"][..., :ms], r0["EL"]) and np.array_equal(r1["ER"][..., :ms], r0["ER"])
+    assert np.array_equal(r1["Mavg"][:, :, :ms], r0["Mavg"])
+    assert np.abs(r1["Mavg"]).max() > 0

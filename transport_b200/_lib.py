@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libtransport_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "transport_b200.h")
 
 TX_OK, TX_ERR_ARG, TX_ERR_CUDA, TX_ERR_SINGULAR, TX_ERR_NOCONV, TX_ERR_UNSUPPORTED = range(6)
-TX_LEAD_CLOSED, TX_LEAD_TABLE = 0, 1
+TX_LEAD_CLOSED, TX_LEAD_TABLE, TX_LEAD_SANCHO, TX_LEAD_SEPARABLE = 0, 1, 2, 3
 TX_HOP_AUTO, TX_HOP_SCALAR, TX_HOP_GENERAL = 0, 1, 2
 TX_GF_CLOSED, TX_GF_RICEMELE, TX_GF_FIXEDPOINT, TX_GF_SANCHO, TX_GF_SEPARABLE = 0, 1, 2, 3, 4
 
@@ -58,6 +58,15 @@ _SIGNATURES = {
     "tx_context_destroy": (c_int, [_P]),
     "tx_context_set_stream": (c_int, [_P, _P, c_int]),
     "tx_context_set_option": (c_int, [_P, c_int, c_int]),
+    "tx_context_set_lead_params": (c_int, [_P, c_double, c_double, c_int]),
+    "tx_context_last_lead_iterations": (c_int, [_P, _P]),
+    "tx_context_set_gather": (c_int, [_P, _P, c_int, ctypes.c_longlong]),
+    "tx_peer_alloc": (c_int, [ctypes.c_longlong, _P]),
+    "tx_peer_free": (c_int, [_P]),
+    "tx_peer_export": (c_int, [_P, _P]),
+    "tx_peer_open": (c_int, [_P, _P]),
+    "tx_peer_close": (c_int, [_P]),
+    "tx_peer_barrier_dev": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "tx_surface_gf": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
                               _P, _P, _P, _P, _P]),
     "tx_surface_gf_dev": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
@@ -75,6 +84,8 @@ _SIGNATURES = {
     "tx_bardeen_wells": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, c_double, c_int] + [_P] * 8),
     "tx_bardeen_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int, c_int]),
     "tx_bardeen_wells_dev": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, c_double, c_int] + [_P] * 8),
+    "tx_bardeen_region_sweep": (c_int, [_P] * 8 + [c_int] + [_P] * 6 + [c_int] * 7 + [_P] * 3 + [c_double, c_int, c_int, c_int, _P]
+                                + [_P] * 6 + [_P, c_int, c_double, c_double, _P]),
     "tx_bardeen_current": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P]),
     "tx_bardeen_current_dev": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P]),
     "tx_bardeen_ts": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),

@@ -225,6 +225,137 @@ def wells_batched(dL, eL, dR, eR, cutL, cutR_states, cutR_count, hd0, hdU, hdL, 
     return out
 
 
+_region_capacity = {}     # (P, n, S) -> max_states of the last call: sweeps of similar geometries take one pass
+
+
+def region_sweep(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR, HC, HCprime=None, cutL=None,
+                 cutR_states=None, cutR_count=None, interval=1e-9, sign_fix=True, row_cut=False, Vb=None, muR=0.0,
+                 kBT=0.0):
+    """P geometries of the inf|L|C|R|inf chain given by their REGION PARAMETERS, assembled on the device
+    (tx_bardeen_region_sweep): bound states of both wells, window-averaged matrix elements and, with `Vb`, the current.
+
+    tinfty, tL, tR, Vinfty: [n] per-channel scalars (or [n,n] diagonal matrices as the reference passes them);
+    VL, VLprime, VR, VRprime: [n] / [n,n] (shared) or [P,n];  HC, HCprime: [NC,NC,n,n] (shared) or [P,NC,NC,n,n], real
+    nearest-neighbour chains;  cut*: [P,n].  Returns dict(EL, nL, ER, nR_states, nR_below, Mavg[, I], h2d_bytes, d2h_bytes)."""
+    lib = _lib.load()
+
+    def chan(x):
+        x = np.asarray(x)
+        if x.ndim == 2 and x.shape[0] == x.shape[1] and not np.any(x - np.diagflat(np.diagonal(x))):
+            x = np.diagonal(x)
+        if np.any(np.imag(x)):
+            raise NotImplementedError("complex region parameters are not covered by the device path")
+        return as_f64(np.real(x))
+
+    tinf_c, tL_c, tR_c, Vinf_c = chan(tinfty), chan(tL), chan(tR), chan(Vinfty)
+    n = len(tinf_c)
+
+    def pots(x):
+        x = np.asarray(x)
+        if x.ndim == 2 and x.shape == (n, n) and n > 1:
+            return chan(x)[None]
+        x = as_f64(np.real(x))
+        return x.reshape(-1, n) if x.ndim > 1 or n == 1 else x[None]
+
+    Vs = [pots(v) for v in (VL, VLprime, VR, VRprime)]
+    n_pot = max(v.shape[0] for v in Vs)
+    Vs = [as_f64(np.broadcast_to(v, (n_pot, n))) for v in Vs]
+
+    def chain(H):
+        H = np.asarray(H)
+        if np.any(np.imag(H)):
+            raise NotImplementedError("complex HC is not covered by the device path")
+        H = np.real(H)
+        if H.ndim == 4:
+            H = H[None]
+        NC = H.shape[1]
+        if NC % 2 != 1: raise ValueError
+        for i in range(NC):
+            for j in range(NC):
+                if abs(i - j) > 1 and np.any(H[:, i, j]):
+                    raise NotImplementedError("HC couples sites beyond nearest neighbours: not a tridiagonal chain")
+        idx = np.arange(NC)
+        return (as_f64(H[:, idx, idx]), as_f64(H[:, idx[:-1], idx[:-1] + 1]), as_f64(H[:, idx[:-1] + 1, idx[:-1]]))
+
+    c0, cU, cL = chain(HC)
+    if HCprime is None:
+        p0 = pU = pL = None
+    else:
+        p0, pU, pL = chain(HCprime)
+        if p0.shape != c0.shape: raise ValueError
+    n_hc, NC = c0.shape[0], c0.shape[1]
+    cutL, cutRs, cutRc = as_f64(cutL), as_f64(cutR_states), as_f64(cutR_count)
+    P = cutL.shape[0]
+    if n_pot not in (1, P) or n_hc not in (1, P):
+        raise ValueError("per-geometry parameters must have P rows")
+    S = 2 * Ninfty + NL + NR + NC
+    nL = np.zeros((P, n), dtype=np.int32); nRs = np.zeros_like(nL); nRb = np.zeros_like(nL)
+    Vb_a = None if Vb is None else as_f64(Vb)
+    nVb = 0 if Vb is None else len(Vb_a)
+    import ctypes
+    needed = ctypes.c_int(0)
+    ms = _region_capacity.get((P, n, S), 0)
+    while True:
+        EL = np.zeros((P, n, max(ms, 1))); ER = np.zeros_like(EL); Mavg = np.zeros((P, n, max(ms, 1), n))
+        Iab = np.zeros((P, n, n, nVb)) if nVb else None
+        check(lib.tx_bardeen_region_sweep(
+            ptr(tinf_c), ptr(tL_c), ptr(tR_c), ptr(Vinf_c), ptr(Vs[0]), ptr(Vs[1]), ptr(Vs[2]), ptr(Vs[3]), n_pot,
+            ptr(c0), ptr(cU), ptr(cL), ptr(p0), ptr(pU), ptr(pL), n_hc, int(Ninfty), int(NL), int(NR), NC, n, P,
+            ptr(cutL), ptr(cutRs), ptr(cutRc), float(interval), int(sign_fix), int(row_cut), ms, ctypes.byref(needed),
+            ptr(EL), ptr(nL), ptr(ER), ptr(nRs), ptr(nRb), ptr(Mavg), ptr(Vb_a), nVb, float(muR), float(kBT), ptr(Iab)))
+        if needed.value <= ms or needed.value == 0:
+            break
+        ms = needed.value + max(2, needed.value // 16)          # a little head room for the next geometries of a sweep
+    _region_capacity[(P, n, S)] = ms
+    used = max(needed.value, 1)
+    out = dict(EL=EL[:, :, :used], nL=nL, ER=ER[:, :, :used], nR_states=nRs, nR_below=nRb, Mavg=Mavg[:, :, :used])
+    if nVb:
+        out["I"] = Iab
+    out["h2d_bytes"] = int(sum(a.nbytes for a in (tinf_c, tL_c, tR_c, Vinf_c, *Vs, c0, cU, cL, cutL, cutRs, cutRc))
+                           + (0 if p0 is None else p0.nbytes + pU.nbytes + pL.nbytes) + (Vb_a.nbytes if nVb else 0))
+    out["d2h_bytes"] = int(EL.nbytes + ER.nbytes + Mavg.nbytes + 3 * nL.nbytes + (Iab.nbytes if nVb else 0))
+    return out
+
+
+def step_sweep(tinfty, tL, tR, Vinfty, VL, VRs, Ninfty, NL, NR, HC, E_cutoff, interval=1e-9, Vb=None, muR=0.0, kBT=0.0,
+               row_cut=False):
+    """The sweep of rbstep.py:43-104 — `kernel_well` (+ `current`) looped over the right-well step height VR — as ONE
+    device pass over all step heights `VRs` [P] (n_loc_dof = 1): for every VR the wells are (VL, VR + Vinfty) and
+    (VL + ... ) exactly as rbstep.py builds VLprime = Vinfty + VL ... (VLprime = VR + Vinfty on the left of the right
+    well, VRprime = Vinfty on the right of the left well)."""
+    VRs = as_f64(np.atleast_1d(VRs))
+    P = len(VRs)
+    n = np.shape(tinfty)[0]
+    if n != 1:
+        raise NotImplementedError("step_sweep covers n_loc_dof = 1 (rbstep.py); use region_sweep for channel-resolved wells")
+    tLa, tRa = _scalar_hopping(np.asarray(tL)), _scalar_hopping(np.asarray(tR))
+    cut = float(np.max(np.real(E_cutoff)))
+    cutL = np.full((P, n), cut - 2 * np.real(tLa))
+    cutR = np.full((P, n), cut - 2 * np.real(tRa))
+    cutR_states = np.full((P, n), np.inf) if np.isnan(interval) else np.maximum(cutR, cutL) + abs(interval)
+    Vinf0 = float(np.real(np.asarray(Vinfty)[0, 0]))
+    VR_col = VRs[:, None]
+    return region_sweep(tinfty, tL, tR, Vinfty, VL, VR_col + Vinf0, VR_col, np.full((P, n), Vinf0), Ninfty, NL, NR, HC, None,
+                        cutL, cutR_states, cutR, interval, sign_fix=True, row_cut=row_cut, Vb=Vb, muR=muR, kBT=kBT)
+
+
+def step_sweep_arrays(tinfty, tL, tR, Vinfty, VL, VRs, Ninfty, NL, NR, HC):
+    """Host-assembled arrays of the same sweep (the inputs of `wells_batched` / tx_bardeen_wells_dev): dL, eL, dR, eR,
+    h0, hU, hL stacked over the step heights.  Kept for device-resident measurements and as the cross-check of the
+    device assembly."""
+    arrs = {k: [] for k in ("dL", "eL", "dR", "eR", "h0", "hU", "hL")}
+    for v in np.atleast_1d(VRs):
+        VR = v * np.eye(np.shape(tinfty)[0])
+        bL = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, Vinfty, Ninfty, NL, NR, HC)
+        bR = hsys_site_blocks(tinfty, tL, tR, Vinfty, VR + Vinfty, VR, Ninfty, NL, NR, HC)
+        bS = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninfty, NL, NR, HC)
+        a, b = _channel_tridiagonals(bL); arrs["dL"].append(a); arrs["eL"].append(b)
+        a, b = _channel_tridiagonals(bR); arrs["dR"].append(a); arrs["eR"].append(b)
+        hd = [np.real(x - y) for x, y in zip(bS, bL)]
+        arrs["h0"].append(hd[0]); arrs["hU"].append(hd[1]); arrs["hL"].append(hd[2])
+    return {k: np.ascontiguousarray(np.array(v), dtype=np.float64) for k, v in arrs.items()}
+
+
 def _real_blocks(blocks):
     if any(np.any(np.imag(b)) for b in blocks):
         raise NotImplementedError("complex Hsys - HL is not covered by the device path")

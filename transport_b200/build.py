@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtransport_b200.so")
 STAMP = os.path.join(LIBDIR, "build.stamp")
-SOURCES = ["capi.cu", "microbench.cu", "surface_gf.cu", "green.cu", "rgf_generic.cu", "bardeen.cu"]
+SOURCES = ["capi.cu", "microbench.cu", "surface_gf.cu", "green.cu", "rgf_generic.cu", "bardeen.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--fmad=true",

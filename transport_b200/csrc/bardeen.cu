@@ -18,6 +18,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <mutex>
+
 #include "../../include/transport_b200.h"
 #include "tx_host.h"
 
@@ -776,6 +778,101 @@ __global__ void bardeen_ts_kernel(const double* __restrict__ E, const double* __
     T[idx] = NL / (ka * tL[alpha]) * NR / tR[beta] * dos * M2[idx];
 }
 
+
+// Device-side assembly of the three Hamiltonians of kernel_well / kernel_well_prime (bardeen/__init__.py:90-125,
+// :455-500) from the REGION PARAMETERS of Hsysmat (:690-750), one thread per (geometry, site): regions
+// inf | L | C | R | inf with on-site potentials per channel and scalar hoppings per channel; the centre is the chain
+// HC (Hsys) / HCprime (both wells).  Nothing of size S travels over PCIe: a sweep over step heights or barrier
+// parameters ships a few doubles per geometry (as affine_expand_kernel does for the T(E) sweeps).
+//   well L: (Vinf, VL, HCprime, VRprime, Vinf)     well R: (Vinf, VLprime, HCprime, VR, Vinf)     sys: (Vinf, VL, HC, VR, Vinf)
+// Outputs: per-channel tridiagonals dL, eL, dR, eR [P][n][S(-1)] and Hdiff = Hsys - HL as block tridiagonal
+// hd0 [P][S][n][n], hdU / hdL [P][S-1][n][n].
+struct RegionParams {
+    const double *tinf, *tL, *tR, *Vinf;            // [n]
+    const double *VL, *VLp, *VR, *VRp;              // [P or 1][n]
+    long long v_stride;                             // n, or 0 when the potentials are shared by all geometries
+    const double *hc0, *hcU, *hcL;                  // Hsys centre: [NC][n][n], [NC-1][n][n] (upper = [j][j+1], lower = [j+1][j])
+    const double *hp0, *hpU, *hpL;                  // wells' centre (HCprime)
+    long long hc_stride0, hc_stride1;               // per-geometry strides of the centre arrays (0 = shared)
+    int Ninf, NL, NR, NC, n, P, S;
+};
+
+__global__ void bardeen_assemble_kernel(const RegionParams q, double* __restrict__ dL, double* __restrict__ eL,
+                                        double* __restrict__ dR, double* __restrict__ eR, double* __restrict__ hd0,
+                                        double* __restrict__ hdU, double* __restrict__ hdL) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)q.P * q.S) return;
+    const int p = (int)(idx / q.S), j = (int)(idx - (long long)p * q.S);
+    const int n = q.n, S = q.S;
+    const int a = q.Ninf, b = a + q.NL, c = b + q.NC, d = c + q.NR;
+    const double* VL = q.VL + p * q.v_stride;
+    const double* VLp = q.VLp + p * q.v_stride;
+    const double* VR = q.VR + p * q.v_stride;
+    const double* VRp = q.VRp + p * q.v_stride;
+    const double* hc0 = q.hc0 + p * q.hc_stride0;
+    const double* hp0 = q.hp0 + p * q.hc_stride0;
+    const double* hcU = q.hcU + p * q.hc_stride1;
+    const double* hcL = q.hcL + p * q.hc_stride1;
+    const double* hpU = q.hpU + p * q.hc_stride1;
+    const double* hpL = q.hpL + p * q.hc_stride1;
+    const bool centre = j >= b && j < c;
+    const bool cbond = j >= b && j < c - 1;          // bond j -> j+1 inside the centre
+    for (int ch = 0; ch < n; ++ch) {
+        double vl, vr;                               // on-site energy in well L / well R
+        if (j < a || j >= d) vl = vr = q.Vinf[ch];
+        else if (j < b) { vl = VL[ch]; vr = VLp[ch]; }
+        else if (j < c) vl = vr = hp0[((long long)(j - b) * n + ch) * n + ch];
+        else { vl = VRp[ch]; vr = VR[ch]; }
+        dL[((long long)p * n + ch) * S + j] = vl;
+        dR[((long long)p * n + ch) * S + j] = vr;
+        if (j < S - 1) {
+            double t;
+            if (j < a || j >= d - 1) t = -q.tinf[ch];
+            else if (j < b) t = -q.tL[ch];
+            else if (cbond) t = hpU[((long long)(j - b) * n + ch) * n + ch];
+            else t = -q.tR[ch];
+            eL[((long long)p * n + ch) * (S - 1) + j] = t;
+            eR[((long long)p * n + ch) * (S - 1) + j] = t;
+        }
+    }
+    // Hdiff = Hsys - HL: the right region's potential (VR - VRprime) and the centre (HC - HCprime)
+    for (int r = 0; r < n; ++r)
+        for (int cc = 0; cc < n; ++cc) {
+            double v = 0.0;
+            if (centre) v = hc0[((long long)(j - b) * n + r) * n + cc] - hp0[((long long)(j - b) * n + r) * n + cc];
+            else if (j >= c && j < d && r == cc) v = VR[r] - VRp[r];
+            hd0[(((long long)p * S + j) * n + r) * n + cc] = v;
+            if (j < S - 1) {
+                double u = 0.0, l = 0.0;
+                if (cbond) {
+                    u = hcU[((long long)(j - b) * n + r) * n + cc] - hpU[((long long)(j - b) * n + r) * n + cc];
+                    l = hcL[((long long)(j - b) * n + r) * n + cc] - hpL[((long long)(j - b) * n + r) * n + cc];
+                }
+                hdU[(((long long)p * (S - 1) + j) * n + r) * n + cc] = u;
+                hdL[(((long long)p * (S - 1) + j) * n + r) * n + cc] = l;
+            }
+        }
+}
+
+// y = x^2 on Mavg[p][beta][m][alpha]; with row_cut, rows m >= n_below[p][beta] are zeroed (the reference's
+// Mnumus[:nu_cut] of kernel_well :181)
+__global__ void square_kernel(const double* __restrict__ x, double* __restrict__ y, long long count, int ms, int n,
+                              const int* __restrict__ n_below, int row_cut) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long row = i / n;               // (p*n + beta)*ms + m
+    const int m = (int)(row % ms);
+    const long long mat = row / ms;
+    y[i] = (row_cut && m >= n_below[mat]) ? 0.0 : x[i] * x[i];
+}
+
+__global__ void max_int_kernel(const int* __restrict__ a, const int* __restrict__ b, int count, int* __restrict__ out) {
+    int m = 0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) m = max(m, max(a[i], b[i]));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 struct DevMem {
     char* p = nullptr;
     ~DevMem() {
@@ -925,11 +1022,11 @@ long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states) {
     return (long long)(2 * align256((size_t)P * n * max_states * S * 8) + align256((size_t)P * n * n * 8) + 256);
 }
 
-int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
-                         const double* cutL, const double* cutR_states, const double* cutR_count,
-                         const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
-                         double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
-                         int* nR_below, double* Mavg, void* workspace, void* stream) {
+static int wells_dev_impl(const double* dL, const double* eL, const double* dR, const double* eR,
+                          const double* cutL, const double* cutR_states, const double* cutR_count,
+                          const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
+                          double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
+                          int* nR_below, double* Mavg, void* workspace, void* stream, bool counted) {
     if (!dL || !eL || !dR || !eR || !cutL || !cutR_states || !cutR_count || !hd0 || !hdU || !hdL || !EL || !nL || !ER ||
         !nR_states || !nR_below || !Mavg || !workspace)
         return fail(TX_ERR_ARG, "null pointer argument");
@@ -942,8 +1039,10 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
     double* psiL = (double*)workspace;
     double* psiR = (double*)((char*)workspace + bz);
     const int n_mat = P * n;
-    if (int rc = launch_count(dL, eL, S, n_mat, cutL, cutL, nL, nR_below /* overwritten below */, st)) return rc;
-    if (int rc = launch_count(dR, eR, S, n_mat, cutR_states, cutR_count, nR_states, nR_below, st)) return rc;
+    if (!counted) {
+        if (int rc = launch_count(dL, eL, S, n_mat, cutL, cutL, nL, nR_below /* overwritten below */, st)) return rc;
+        if (int rc = launch_count(dR, eR, S, n_mat, cutR_states, cutR_count, nR_states, nR_below, st)) return rc;
+    }
     if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, nullptr, st)) return rc;
     if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, nullptr, st)) return rc;
     static bool attr_set = false;
@@ -960,6 +1059,157 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
                                                           max_states, interval, sign_fix, Mavg);
     TX_CUDA(cudaGetLastError());
     count_launch();
+    return TX_OK;
+}
+
+int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, const double* eR,
+                         const double* cutL, const double* cutR_states, const double* cutR_count,
+                         const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
+                         double interval, int sign_fix, double* EL, int* nL, double* ER, int* nR_states,
+                         int* nR_below, double* Mavg, void* workspace, void* stream) {
+    return wells_dev_impl(dL, eL, dR, eR, cutL, cutR_states, cutR_count, hd0, hdU, hdL, P, n, S, max_states, interval, sign_fix,
+                          EL, nL, ER, nR_states, nR_below, Mavg, workspace, stream, false);
+}
+
+// Grow-only per-device workspace of tx_bardeen_region_sweep (serialised by a mutex: one sweep at a time per process).
+namespace {
+struct RegionWs {
+    char* p = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+};
+RegionWs g_region_ws[16];
+std::mutex g_region_mutex;
+}  // namespace
+
+int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* tR, const double* Vinf,
+                            const double* VL, const double* VLprime, const double* VR, const double* VRprime, int n_pot,
+                            const double* hc0, const double* hcU, const double* hcL,
+                            const double* hp0, const double* hpU, const double* hpL, int n_hc,
+                            int Ninf, int NL, int NR, int NC, int n, int P,
+                            const double* cutL, const double* cutR_states, const double* cutR_count,
+                            double interval, int sign_fix, int row_cut, int max_states, int* max_needed,
+                            double* EL, int* nL, double* ER, int* nR_states, int* nR_below, double* Mavg,
+                            const double* Vb, int nVb, double muR, double kBT, double* I) {
+    if (!tinf || !tL || !tR || !Vinf || !VL || !VLprime || !VR || !VRprime || !hc0 || !cutL || !cutR_states || !cutR_count ||
+        !max_needed || !nL || !nR_states || !nR_below)
+        return fail(TX_ERR_ARG, "null pointer argument");
+    if (Ninf < 1 || NL < 1 || NR < 1 || NC < 1 || NC % 2 != 1 || n < 1 || P < 1 || max_states < 0)
+        return fail(TX_ERR_ARG, "bad sizes Ninf=%d NL=%d NR=%d NC=%d n=%d P=%d", Ninf, NL, NR, NC, n, P);
+    if (NC > 1 && (!hcU || !hcL)) return fail(TX_ERR_ARG, "centre hoppings missing");
+    if (!(n_pot == 1 || n_pot == P) || !(n_hc == 1 || n_hc == P)) return fail(TX_ERR_ARG, "n_pot / n_hc must be 1 or P");
+    if (max_states > 0 && (!EL || !ER || !Mavg)) return fail(TX_ERR_ARG, "null output buffer");
+    if (I && (!Vb || nVb < 1)) return fail(TX_ERR_ARG, "current requested without a bias grid");
+    if (int rc = have_device()) return rc;
+    if (!hp0) { hp0 = hc0; hpU = hcU; hpL = hcL; }
+    const int S = 2 * Ninf + NL + NR + NC;
+    if ((size_t)S * 8 > 200 * 1024) return fail(TX_ERR_UNSUPPORTED, "chain length S=%d too long", S);
+    const int n_mat = P * n;
+    const size_t nn = (size_t)n * n;
+    const int ms = max_states > 0 ? max_states : 1;
+    const size_t bd = align256((size_t)n_mat * S * 8), bc = align256((size_t)n_mat * 8);
+    const size_t bh = align256((size_t)P * S * nn * 8);
+    const size_t bv = align256((size_t)n_mat * ms * 8), bm = align256((size_t)n_mat * ms * n * 8);
+    const size_t bw = max_states > 0 ? (size_t)tx_bardeen_workspace_bytes(P, n, S, max_states) : 0;
+    const size_t bpar = align256((size_t)(4 + 4 * n_pot) * n * 8);
+    const size_t bhc = align256((size_t)n_hc * NC * nn * 8);
+    const size_t bI = I ? align256((size_t)P * nn * nVb * 8) : 0, bVb = I ? align256((size_t)nVb * 8) : 0;
+    const size_t total = 4 * bd + 6 * bc + 3 * bh + 2 * bv + 2 * bm + bw + bpar + 6 * bhc + bI + bVb + 512;
+
+    int dev = 0;
+    TX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_region_mutex);
+    RegionWs& ws = g_region_ws[dev & 15];
+    if (!ws.st) TX_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+    if (total > ws.cap) {
+        if (ws.p) cudaFree(ws.p);
+        ws.p = nullptr;
+        ws.cap = 0;
+        TX_CUDA(cudaMalloc(&ws.p, total + total / 4));
+        ws.cap = total + total / 4;
+    }
+    cudaStream_t st = ws.st;
+    char* q = ws.p;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    double* ddL = (double*)take(bd); double* deL = (double*)take(bd);
+    double* ddR = (double*)take(bd); double* deR = (double*)take(bd);
+    double* dcL = (double*)take(bc); double* dcRs = (double*)take(bc); double* dcRc = (double*)take(bc);
+    int* dnL = (int*)take(bc); int* dnRs = (int*)take(bc); int* dnRb = (int*)take(bc);
+    double* dh0 = (double*)take(bh); double* dhU = (double*)take(bh); double* dhL = (double*)take(bh);
+    double* dEL = (double*)take(bv); double* dER = (double*)take(bv);
+    double* dM = (double*)take(bm); double* dM2 = (double*)take(bm);
+    char* wsp = take(bw);
+    double* dpar = (double*)take(bpar);
+    double* dhc[6];
+    for (int i = 0; i < 6; ++i) dhc[i] = (double*)take(bhc);
+    double* dI = (double*)take(bI); double* dVb = (double*)take(bVb);
+    int* dmax = (int*)take(256);
+
+    auto up = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, st); };
+    const size_t bn = (size_t)n * 8, bpn = (size_t)n_pot * n * 8;
+    double* p_tinf = dpar; double* p_tL = dpar + n; double* p_tR = dpar + 2 * n; double* p_Vinf = dpar + 3 * n;
+    double* p_VL = dpar + 4 * n; double* p_VLp = p_VL + (size_t)n_pot * n; double* p_VR = p_VLp + (size_t)n_pot * n;
+    double* p_VRp = p_VR + (size_t)n_pot * n;
+    TX_CUDA(up(p_tinf, tinf, bn)); TX_CUDA(up(p_tL, tL, bn)); TX_CUDA(up(p_tR, tR, bn)); TX_CUDA(up(p_Vinf, Vinf, bn));
+    TX_CUDA(up(p_VL, VL, bpn)); TX_CUDA(up(p_VLp, VLprime, bpn)); TX_CUDA(up(p_VR, VR, bpn)); TX_CUDA(up(p_VRp, VRprime, bpn));
+    const size_t b0 = (size_t)n_hc * NC * nn * 8, b1 = (size_t)n_hc * (NC - 1) * nn * 8;
+    TX_CUDA(up(dhc[0], hc0, b0)); TX_CUDA(up(dhc[3], hp0, b0));
+    if (NC > 1) {
+        TX_CUDA(up(dhc[1], hcU, b1)); TX_CUDA(up(dhc[2], hcL, b1));
+        TX_CUDA(up(dhc[4], hpU, b1)); TX_CUDA(up(dhc[5], hpL, b1));
+    }
+    TX_CUDA(up(dcL, cutL, (size_t)n_mat * 8)); TX_CUDA(up(dcRs, cutR_states, (size_t)n_mat * 8));
+    TX_CUDA(up(dcRc, cutR_count, (size_t)n_mat * 8));
+    TX_CUDA(cudaMemsetAsync(dmax, 0, 4, st));
+
+    RegionParams rp{};
+    rp.tinf = p_tinf; rp.tL = p_tL; rp.tR = p_tR; rp.Vinf = p_Vinf;
+    rp.VL = p_VL; rp.VLp = p_VLp; rp.VR = p_VR; rp.VRp = p_VRp;
+    rp.v_stride = n_pot == 1 ? 0 : n;
+    rp.hc0 = dhc[0]; rp.hcU = dhc[1]; rp.hcL = dhc[2]; rp.hp0 = dhc[3]; rp.hpU = dhc[4]; rp.hpL = dhc[5];
+    rp.hc_stride0 = n_hc == 1 ? 0 : (long long)NC * nn;
+    rp.hc_stride1 = n_hc == 1 ? 0 : (long long)(NC - 1) * nn;
+    rp.Ninf = Ninf; rp.NL = NL; rp.NR = NR; rp.NC = NC; rp.n = n; rp.P = P; rp.S = S;
+    const long long items = (long long)P * S;
+    bardeen_assemble_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(rp, ddL, deL, ddR, deR, dh0, dhU, dhL);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    if (int rc = launch_count(ddL, deL, S, n_mat, dcL, dcL, dnL, dnRb, st)) return rc;
+    if (int rc = launch_count(ddR, deR, S, n_mat, dcRs, dcRc, dnRs, dnRb, st)) return rc;
+    max_int_kernel<<<1, 256, 0, st>>>(dnL, dnRs, n_mat, dmax);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    int needed = 0;
+    TX_CUDA(cudaMemcpyAsync(&needed, dmax, 4, cudaMemcpyDeviceToHost, st));
+    TX_CUDA(cudaStreamSynchronize(st));
+    *max_needed = needed;
+    auto down = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToHost, st); };
+    TX_CUDA(down(nL, dnL, (size_t)n_mat * 4));
+    TX_CUDA(down(nR_states, dnRs, (size_t)n_mat * 4));
+    TX_CUDA(down(nR_below, dnRb, (size_t)n_mat * 4));
+    if (max_states == 0 || needed > max_states || needed == 0) {
+        TX_CUDA(cudaStreamSynchronize(st));
+        return TX_OK;          // counts only: the caller sizes its buffers from *max_needed and calls again
+    }
+    TX_CUDA(cudaMemsetAsync(dEL, 0, bv, st));
+    TX_CUDA(cudaMemsetAsync(dER, 0, bv, st));
+    TX_CUDA(cudaMemsetAsync(dM, 0, bm, st));
+    if (int rc = wells_dev_impl(ddL, deL, ddR, deR, dcL, dcRs, dcRc, dh0, dhU, dhL, P, n, S, max_states, interval, sign_fix, dEL,
+                                dnL, dER, dnRs, dnRb, dM, wsp, st, true))
+        return rc;
+    TX_CUDA(down(EL, dEL, (size_t)n_mat * max_states * 8));
+    TX_CUDA(down(ER, dER, (size_t)n_mat * max_states * 8));
+    TX_CUDA(down(Mavg, dM, (size_t)n_mat * max_states * n * 8));
+    if (I) {
+        const long long cnt = (long long)n_mat * max_states * n;
+        square_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(dM, dM2, cnt, max_states, n, dnRb, row_cut);
+        TX_CUDA(cudaGetLastError());
+        count_launch();
+        TX_CUDA(up(dVb, Vb, (size_t)nVb * 8));
+        if (int rc = tx_bardeen_current_dev(dEL, dM2, P, n, max_states, dVb, nVb, muR, kBT, dI, st)) return rc;
+        TX_CUDA(down(I, dI, (size_t)P * nn * nVb * 8));
+    }
+    TX_CUDA(cudaStreamSynchronize(st));
     return TX_OK;
 }
 

@@ -84,6 +84,11 @@ struct tx_context {
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
     bool follows_defaults = false;        // default contexts track tx_set_variant / tx_set_option
+    PeerGather gather{};                  // tx_context_set_gather (n = 0: none)
+    double lead_imE = 0.0, lead_tol = 1e-14;   // tx_context_set_lead_params (TX_LEAD_SANCHO / TX_LEAD_SEPARABLE)
+    int lead_max_iter = 200;
+    double last_lead_iters = 0.0;         // mean Sancho-Rubio iterations of the last host sweep (both leads)
+    DevBuf nit, okb;
 };
 
 namespace {
@@ -295,13 +300,13 @@ struct SweepOut {
     int n_up, spin_n;
 };
 
-int check_spin(const SweepOut& o, int n) {
+int check_spin(const SweepOut& o, int n, bool has_gather = false) {
     if ((o.R == nullptr) != (o.T == nullptr)) return fail(TX_ERR_ARG, "R and T must be given together (or both NULL)");
     if (o.spin) {
         if (o.spin_n != 2 && o.spin_n != 4) return fail(TX_ERR_ARG, "spin_n must be 2 or 4");
         if (o.n_up < 0 || o.n_up > n) return fail(TX_ERR_ARG, "n_up=%d outside 0..n", o.n_up);
     }
-    if (!o.R && !o.resid && !o.t_total && !o.caroli && !o.spin) return fail(TX_ERR_ARG, "no output array given");
+    if (!o.R && !o.resid && !o.t_total && !o.caroli && !o.spin && !has_gather) return fail(TX_ERR_ARG, "no output array given");
     return TX_OK;
 }
 
@@ -388,7 +393,7 @@ int tx_context_destroy(tx_context* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->scratch_ev) cudaEventSynchronize(c->scratch_ev);
     DevBuf* bufs[] = {&c->h, &c->h1, &c->par, &c->tnn, &c->E, &c->sigL, &c->sigR, &c->src, &c->R, &c->T, &c->resid,
-                      &c->ttot, &c->caroli, &c->spin, &c->big, &c->flag, &c->expand, &c->nondiag};
+                      &c->ttot, &c->caroli, &c->spin, &c->big, &c->flag, &c->expand, &c->nondiag, &c->nit, &c->okb};
     for (DevBuf* b : bufs) b->release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -405,6 +410,44 @@ int tx_context_set_stream(tx_context* c, void* stream, int use_stream) {
     std::lock_guard<std::mutex> lock(c->mu);
     c->user_stream = reinterpret_cast<cudaStream_t>(stream);
     c->has_user_stream = use_stream != 0;
+    return TX_OK;
+}
+
+int tx_context_set_lead_params(tx_context* c, double imE, double conv_tol, int max_iter) {
+    if (!(conv_tol >= 0.0) || max_iter < 1) return fail(TX_ERR_ARG, "bad lead parameters");
+    if (!c) {
+        if (tx_device_count() < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+        if (int rc = default_context(&c)) return rc;
+    }
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->lead_imE = imE;
+    c->lead_tol = conv_tol;
+    c->lead_max_iter = max_iter;
+    return TX_OK;
+}
+
+int tx_context_last_lead_iterations(tx_context* c, double* mean_iterations) {
+    if (!mean_iterations) return fail(TX_ERR_ARG, "null pointer argument");
+    if (!c) {
+        if (tx_device_count() < 1) return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+        if (int rc = default_context(&c)) return rc;
+    }
+    std::lock_guard<std::mutex> lock(c->mu);
+    *mean_iterations = c->last_lead_iters;
+    return TX_OK;
+}
+
+int tx_context_set_gather(tx_context* c, double* const* peers, int n_peers, long long offset) {
+    if (!c) return fail(TX_ERR_ARG, "null context");
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peers) || offset < 0) return fail(TX_ERR_ARG, "bad gather spec (n_peers <= 8)");
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->gather = PeerGather{};
+    for (int q = 0; q < n_peers; ++q) {
+        if (!peers[q]) return fail(TX_ERR_ARG, "null peer pointer %d", q);
+        c->gather.dst[q] = peers[q];
+    }
+    c->gather.n = n_peers;
+    c->gather.off = offset;
     return TX_OK;
 }
 
@@ -533,6 +576,7 @@ int sweep_small_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     p.spin = o.spin;
     p.n_up = o.n_up;
     p.spin_n = o.spin_n;
+    p.gather = cx.gather;
     p.singular = singular_flag;
     p.nondiag_max = nullptr;
     p.nondiag_stride = 0;
@@ -615,6 +659,7 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     p.spin = o.spin;
     p.n_up = o.n_up;
     p.spin_n = o.spin_n;
+    p.gather = cx.gather;
     p.work = reinterpret_cast<cd*>(workspace);
     p.singular = singular_flag;
     p.n_pts = (long long)n_ham * nE;
@@ -699,6 +744,7 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
     if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham))
         return fail(TX_ERR_ARG, "n_h/n_t must be 1 or n_ham");
     if (sources && src_idx) return fail(TX_ERR_ARG, "give sources or src_idx, not both");
+    if (lead_mode < TX_LEAD_CLOSED || lead_mode > TX_LEAD_SEPARABLE) return fail(TX_ERR_ARG, "unknown lead_mode %d", lead_mode);
     {
         const SweepOut chk{R, T, resid, t_total, caroli, spin, n_up, spin_n};
         if (int rc = check_spin(chk, n)) return rc;
@@ -793,6 +839,49 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
 
     const bool large = (n > 16) || (caroli != nullptr);
     bool copied_out = false;
+    // Lead stage (K1) for the modes that need device tables: iterative / separable multi-channel leads for any n, and
+    // closed-form leads ahead of the large-block kernel.  The tables never leave the device.
+    int n_sig_use = n_sig;
+    const bool build_tables = lead_mode == TX_LEAD_SANCHO || lead_mode == TX_LEAD_SEPARABLE || (large && lead_mode == TX_LEAD_CLOSED);
+    bool check_conv = false;
+    if (build_tables) {
+        // the lead blocks must be common to all Hamiltonians of the batch
+        const size_t lead_off_R = (size_t)(M - 1) * nn, hop_off_R = (size_t)(M - 2) * nn;
+        for (int q = 1; q < n_h; ++q)
+            if (memcmp(h + (size_t)q * M * nn, h, nn * sizeof(tx_cplx)) ||
+                memcmp(h + (size_t)q * M * nn + lead_off_R, h + lead_off_R, nn * sizeof(tx_cplx)))
+                return fail(TX_ERR_UNSUPPORTED, "device-built lead tables need identical lead blocks in every Hamiltonian; pass tables");
+        for (int q = 1; q < n_t; ++q)
+            if (memcmp(tnn + (size_t)q * (M - 1) * nn, tnn, nn * sizeof(tx_cplx)) ||
+                memcmp(tnn + (size_t)q * (M - 1) * nn + hop_off_R, tnn + hop_off_R, nn * sizeof(tx_cplx)))
+                return fail(TX_ERR_UNSUPPORTED, "device-built lead tables need identical lead hoppings in every Hamiltonian; pass tables");
+        if (h1)
+            for (size_t i = 0; i < nn; ++i)
+                if (h1[i].re != 0 || h1[i].im != 0 || h1[lead_off_R + i].re != 0 || h1[lead_off_R + i].im != 0)
+                    return fail(TX_ERR_UNSUPPORTED, "affine term on the lead blocks is not supported with device-built lead tables");
+        const size_t bs = (size_t)nE * nn * sizeof(tx_cplx);
+        if ((rc = ws.sigL.ensure(bs)) || (rc = ws.sigR.ensure(bs))) return rc;
+        const int gf_mode = lead_mode == TX_LEAD_SANCHO ? TX_GF_SANCHO : (lead_mode == TX_LEAD_SEPARABLE ? TX_GF_SEPARABLE : TX_GF_CLOSED);
+        check_conv = gf_mode == TX_GF_SANCHO;
+        int *nitL = nullptr, *nitR = nullptr, *okL = nullptr, *okR = nullptr;
+        if (check_conv) {
+            if ((rc = ws.nit.ensure(2 * (size_t)nE * sizeof(int))) || (rc = ws.okb.ensure(2 * (size_t)nE * sizeof(int)))) return rc;
+            nitL = (int*)ws.nit.ptr;  nitR = nitL + nE;
+            okL = (int*)ws.okb.ptr;   okR = okL + nE;
+        }
+        const double imE = gf_mode == TX_GF_CLOSED ? 0.0 : ws.lead_imE;
+        const tx_cplx* dh = (const tx_cplx*)ws.h.ptr;
+        const tx_cplx* dt = (const tx_cplx*)ws.tnn.ptr;
+        rc = tx_surface_gf_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, -1, gf_mode, imE, ws.lead_tol, 0, 0, ws.lead_max_iter, nullptr,
+                               (tx_cplx*)ws.sigL.ptr, nitL, nullptr, okL, (int*)ws.flag.ptr, st);
+        if (rc) return rc;
+        rc = tx_surface_gf_dev(dh + lead_off_R, dt + hop_off_R, n, (const tx_cplx*)ws.E.ptr, nE, 1, gf_mode, imE, ws.lead_tol, 0, 0,
+                               ws.lead_max_iter, nullptr, (tx_cplx*)ws.sigR.ptr, nitR, nullptr, okR, (int*)ws.flag.ptr, st);
+        if (rc) return rc;
+        n_sig_use = 1;
+        lead_mode = TX_LEAD_TABLE;
+    }
+    const bool have_tables = lead_mode == TX_LEAD_TABLE;
     if (!large) {
         // Chunk the Hamiltonian axis so that the device->host copy of chunk c overlaps the sweep of
         // chunk c+1 (two streams, one event per chunk).  The results dominate the PCIe traffic.
@@ -817,8 +906,8 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
                 h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr + p0 : nullptr,
                 (const tx_cplx*)ws.tnn.ptr + (n_t > 1 ? p0 * t_ham : 0), n_t > 1 ? np_ : 1, n, M, np_,
                 (const tx_cplx*)ws.E.ptr, nE, lead_mode,
-                bytes_sig ? (const tx_cplx*)ws.sigL.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr,
-                bytes_sig ? (const tx_cplx*)ws.sigR.ptr + (n_sig > 1 ? p0 * s_ham : 0) : nullptr, n_sig > 1 ? np_ : 1,
+                have_tables ? (const tx_cplx*)ws.sigL.ptr + (n_sig_use > 1 ? p0 * s_ham : 0) : nullptr,
+                have_tables ? (const tx_cplx*)ws.sigR.ptr + (n_sig_use > 1 ? p0 * s_ham : 0) : nullptr, n_sig_use > 1 ? np_ : 1,
                 hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, o, (int*)ws.flag.ptr, st);
             if (rc) return rc;
             if (n_chunks == 1) break;   // single chunk: the copies below follow on the same stream
@@ -837,35 +926,7 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
         }
         if (copied_out) TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
     } else {
-        // generic-size path (n <= 64): self-energy tables first (K1), then one CTA per point
-        int n_sig_use = n_sig;
-        if (lead_mode == TX_LEAD_CLOSED) {
-            // closed-form leads must be common to all Hamiltonians of the batch
-            const size_t lead_off_R = (size_t)(M - 1) * nn, hop_off_R = (size_t)(M - 2) * nn;
-            for (int q = 1; q < n_h; ++q)
-                if (memcmp(h + (size_t)q * M * nn, h, nn * sizeof(tx_cplx)) ||
-                    memcmp(h + (size_t)q * M * nn + lead_off_R, h + lead_off_R, nn * sizeof(tx_cplx)))
-                    return fail(TX_ERR_UNSUPPORTED, "large-block sweep with closed-form leads needs identical lead blocks; pass tables");
-            for (int q = 1; q < n_t; ++q)
-                if (memcmp(tnn + (size_t)q * (M - 1) * nn, tnn, nn * sizeof(tx_cplx)) ||
-                    memcmp(tnn + (size_t)q * (M - 1) * nn + hop_off_R, tnn + hop_off_R, nn * sizeof(tx_cplx)))
-                    return fail(TX_ERR_UNSUPPORTED, "large-block sweep with closed-form leads needs identical lead hoppings; pass tables");
-            if (h1)
-                for (size_t i = 0; i < nn; ++i)
-                    if (h1[i].re != 0 || h1[i].im != 0 || h1[lead_off_R + i].re != 0 || h1[lead_off_R + i].im != 0)
-                        return fail(TX_ERR_UNSUPPORTED, "affine term on the lead blocks is not supported by the large-block sweep");
-            const size_t bs = (size_t)nE * nn * sizeof(tx_cplx);
-            if ((rc = ws.sigL.ensure(bs)) || (rc = ws.sigR.ensure(bs))) return rc;
-            const tx_cplx* dh = (const tx_cplx*)ws.h.ptr;
-            const tx_cplx* dt = (const tx_cplx*)ws.tnn.ptr;
-            rc = tx_surface_gf_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, -1, TX_GF_CLOSED, 0.0, 0.0, 0, 0, 0, nullptr,
-                                   (tx_cplx*)ws.sigL.ptr, nullptr, nullptr, nullptr, (int*)ws.flag.ptr, st);
-            if (rc) return rc;
-            rc = tx_surface_gf_dev(dh + lead_off_R, dt + hop_off_R, n, (const tx_cplx*)ws.E.ptr, nE, 1, TX_GF_CLOSED, 0.0, 0.0,
-                                   0, 0, 0, nullptr, (tx_cplx*)ws.sigR.ptr, nullptr, nullptr, nullptr, (int*)ws.flag.ptr, st);
-            if (rc) return rc;
-            n_sig_use = 1;
-        }
+        // generic-size path (n <= 64): one CTA per point on the device tables
         const size_t wse = rgf_generic_workspace_elems(n, (long long)n_pts);
         if (wse && (rc = ws.big.ensure(wse * sizeof(tx_cplx)))) return rc;
         if (caroli && (rc = ws.caroli.ensure(n_pts * sizeof(double)))) return rc;
@@ -892,7 +953,22 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
     if (bytes_res) TX_CUDA(cudaMemcpyAsync(resid, ws.resid.ptr, bytes_res, cudaMemcpyDeviceToHost, st));
     if (t_total) TX_CUDA(cudaMemcpyAsync(t_total, ws.ttot.ptr, n_pts * sizeof(double), cudaMemcpyDeviceToHost, st));
     TX_CUDA(cudaMemcpyAsync(&flag, ws.flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<int> conv_host;
+    if (check_conv) {
+        conv_host.resize(4 * (size_t)nE);
+        TX_CUDA(cudaMemcpyAsync(conv_host.data(), ws.nit.ptr, 2 * (size_t)nE * sizeof(int), cudaMemcpyDeviceToHost, st));
+        TX_CUDA(cudaMemcpyAsync(conv_host.data() + 2 * (size_t)nE, ws.okb.ptr, 2 * (size_t)nE * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     TX_CUDA(cudaStreamSynchronize(st));
+    if (check_conv) {
+        double iters = 0.0;
+        for (size_t i = 0; i < 2 * (size_t)nE; ++i) iters += conv_host[i];
+        ws.last_lead_iters = iters / (2.0 * nE);
+        for (size_t i = 0; i < 2 * (size_t)nE; ++i)
+            if (!conv_host[2 * (size_t)nE + i])
+                return fail(TX_ERR_NOCONV, "Sancho-Rubio decimation did not converge at energy index %zu (%s lead) within %d iterations",
+                            i % nE, i < (size_t)nE ? "left" : "right", ws.lead_max_iter);
+    }
     if (flag) return fail(TX_ERR_SINGULAR, "a singular block was met during the sweep (results contain inf/nan there)");
     return TX_OK;
 }

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
 
     // ---- epilogue: per-channel R/T with the reference's formulas (:108-130)
     double tsum = 0.0;
-    if (p.R || p.ttot || p.resid || p.spin) {
+    if (p.R || p.ttot || p.gather.n || p.resid || p.spin) {
         for (int i = 0; i < p.n_src; ++i) {
             double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector
             for (int c = 0; c < n; ++c) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
             }
         }
     }
-    if (p.ttot) {
+    if (p.ttot || p.gather.n) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tsum;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
         if (threadIdx.x == 0) {
             double tot = 0.0;
             for (int w = 0; w < GEN_THREADS / 32; ++w) tot += s_red[w];
-            p.ttot[pt] = tot;
+            store_total(p.ttot, p.gather, pt, tot);
         }
         __syncthreads();
     }

@@ -25,6 +25,7 @@ struct GenericParams {
     double* caroli;          // [n_pts] or null
     double* spin;            // [n_pts][n_src][spin_n] or null (see emit_spin in rgf_small.cuh)
     int n_up, spin_n;
+    PeerGather gather;
     cd* work;                // global workspace or null (then dynamic shared memory)
     int* singular;
     long long n_pts;

@@ -797,10 +797,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8(const SweepParams p) {
             emit(i, wu >= wd, rr, tt);
         }
     }
-    if (p.ttot) {
+    if (p.ttot || p.gather.n) {
 #pragma unroll
         for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
-        if (active && li == 0) p.ttot[pt] = tsum;
+        if (active && li == 0) store_total(p.ttot, p.gather, pt, tsum);
     }
 }
 

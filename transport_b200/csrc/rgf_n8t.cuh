@@ -611,10 +611,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             emit(i, wu >= wd, rr, tt);
         }
     }
-    if (p.ttot) {
+    if (p.ttot || p.gather.n) {
         tsum += __shfl_xor_sync(FULLM, tsum, 2);
         tsum += __shfl_xor_sync(FULLM, tsum, 1);
-        if (active && tid == 0) p.ttot[pt] = tsum;
+        if (active && tid == 0) store_total(p.ttot, p.gather, pt, tsum);
     }
     __syncwarp();   // the epilogue's shared-memory reads are done before the next item's prologue writes
     }   // persistent loop over the warp's items

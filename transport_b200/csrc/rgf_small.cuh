@@ -43,6 +43,7 @@ struct SweepParams {
     double* ttot;            // [n_pts] or null: sum over sources and channels of T (= Tr[Gamma_R G Gamma_L G^dag] for all sources)
     double* spin;            // [n_pts][n_src][spin_n] or null: spin-resolved channel sums (emit_spin below)
     int n_up, spin_n;        // channels [0, n_up) carry electron spin up; spin_n = 2 (T only) or 4 (T and R)
+    PeerGather gather;       // n = 0: none; else the per-point total also goes to the peers' buffers
     int* singular;           // device flag, set to 1 if a zero pivot was met
     const int* nondiag_max;  // [n_ham or 1] or null: largest site index whose on-site block is not diagonal (-1: none)
     long long nondiag_stride;
@@ -616,10 +617,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_small(const SweepParams p
             emit(i, wu >= wd, rr, tt);
         }
     }
-    if (p.ttot) {
+    if (p.ttot || p.gather.n) {
 #pragma unroll
         for (int off = LP / 2; off >= 1; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
-        if (active && li == 0) p.ttot[pt] = tsum;
+        if (active && li == 0) store_total(p.ttot, p.gather, pt, tsum);
     }
 }
 

@@ -11,6 +11,19 @@ struct __align__(16) cd {
     double x, y;
 };
 
+// Multi-GPU gather fused into the K3 epilogue: the per-point total transmission is ALSO stored into the result
+// buffers of up to 8 ranks (peer memory mapped over NVLink with CUDA IPC, peer.cu) at element `off + point`, so the
+// "NCCL all-gather of the T(E) arrays" of SURVEY.md §8e rides on the sweep itself instead of following it.
+struct PeerGather {
+    double* dst[8];
+    long long off;
+    int n;
+};
+__device__ __forceinline__ void store_total(double* ttot, const PeerGather& pg, long long pt, double v) {
+    if (ttot) ttot[pt] = v;
+    for (int q = 0; q < pg.n; ++q) pg.dst[q][pg.off + pt] = v;
+}
+
 __host__ __device__ __forceinline__ cd mk(double x, double y) {
     cd r;
     r.x = x;

@@ -5,7 +5,12 @@ arithmetic runs in libtransport_b200.so on the GPU.
 import numpy as np
 
 from . import _lib
-from ._lib import (TX_HOP_AUTO, TX_LEAD_CLOSED, TX_LEAD_TABLE, TransportError, as_c128, as_f64, check, ptr)
+import threading
+
+from ._lib import (TX_HOP_AUTO, TX_LEAD_CLOSED, TX_LEAD_SANCHO, TX_LEAD_SEPARABLE, TX_LEAD_TABLE, TransportError, as_c128,
+                   as_f64, check, ptr)
+
+_lead_lock = threading.Lock()   # keeps "set lead parameters, sweep" atomic on the shared default context
 
 
 def _norm_blocks(h, tnn):
@@ -82,7 +87,10 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
       h      [M,n,n] or [P,M,n,n]   on-site blocks (block 0 / M-1 = first cell of left / right lead)
       tnn    [M-1,n,n] or [P,M-1,n,n] upper hopping blocks H_{j,j+1}
       Es     [nE] complex energies
-      converger  "g_closed" (fused closed-form leads) or "table" with sigL/sigR [nE,n,n] or [P,nE,n,n]
+      converger  "g_closed" (fused closed-form leads); "table" with sigL/sigR [nE,n,n] or [P,nE,n,n];
+             ("sancho", eta[, tol[, max_iter]]) Sancho-Rubio decimation of multi-channel leads at E + i*eta, or
+             "separable" / ("separable", eta) for leads whose hopping block is t*I -- both build the self-energy
+             tables on the device ahead of the sweep (they never travel to the host)
       sources None -> all n one-hot sources; else [n_src, n] real amplitude vectors (Ajsigma)
       h1, params  optional affine family: Hamiltonian p = h + params[p]*h1  (h must then be [M,n,n])
       out    optional (R, T) float64 arrays to fill (e.g. views of pinned memory)
@@ -128,6 +136,13 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
         if sigL.shape != sigR.shape or sigL.shape[1:] != (len(Es), n, n) or sigL.shape[0] not in (1, n_ham):
             raise ValueError("sigL/sigR must be [nE,n,n] or [P,nE,n,n]")
         lead_mode, n_sig = TX_LEAD_TABLE, sigL.shape[0]
+    elif converger == "separable" or (isinstance(converger, tuple) and converger and converger[0] in ("sancho", "separable")):
+        kind = converger if isinstance(converger, str) else converger[0]
+        args = () if isinstance(converger, str) else tuple(converger[1:])
+        lead_params = (float(args[0]) if len(args) > 0 else 0.0, float(args[1]) if len(args) > 1 else 1e-14,
+                       int(args[2]) if len(args) > 2 else 200)
+        lead_mode, n_sig = (TX_LEAD_SANCHO if kind == "sancho" else TX_LEAD_SEPARABLE), 1
+        sigL = sigR = None
     else:
         raise Exception("converger = " + str(converger) + " not supported")
 
@@ -169,11 +184,31 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
             if spin.shape != shape[:3] + (spin_n,) or spin.dtype != np.float64:
                 raise ValueError("spin_out must be float64 of shape %s" % (shape[:3] + (spin_n,),))
 
-    rc = lib.tx_transmission_sweep_spin(context._h if context is not None else None,
+    cxh = context._h if context is not None else None
+    if lead_mode in (TX_LEAD_SANCHO, TX_LEAD_SEPARABLE):
+        _lead_lock.acquire()
+        check(lib.tx_context_set_lead_params(cxh, *lead_params))
+    try:
+        rc = _call_sweep(lib, cxh, h, n_h, h1, params, tnn, n_t, n, M, n_ham, Es, lead_mode, sigL, sigR, n_sig, src, n_src,
+                         R, T, resid, total, caroli, n_up, spin_n, spin)
+    finally:
+        if lead_mode in (TX_LEAD_SANCHO, TX_LEAD_SEPARABLE):
+            _lead_lock.release()
+    if rc == _lib.TX_ERR_NOCONV:
+        raise Exception(lib.tx_last_error().decode())
+    return _finish(rc, want_rt, want_resid, want_total, want_caroli, want_spin, R, T, resid, total, caroli, spin)
+
+
+def _call_sweep(lib, cxh, h, n_h, h1, params, tnn, n_t, n, M, n_ham, Es, lead_mode, sigL, sigR, n_sig, src, n_src,
+                R, T, resid, total, caroli, n_up, spin_n, spin):
+    return lib.tx_transmission_sweep_spin(cxh,
                                         ptr(h), n_h, ptr(h1), ptr(params), ptr(tnn), n_t, n, M, n_ham,
                                         ptr(Es), len(Es), lead_mode, ptr(sigL), ptr(sigR), n_sig,
                                         TX_HOP_AUTO, ptr(src), None, n_src, ptr(R), ptr(T), ptr(resid), ptr(total),
                                         ptr(caroli), n_up, spin_n, ptr(spin))
+
+
+def _finish(rc, want_rt, want_resid, want_total, want_caroli, want_spin, R, T, resid, total, caroli, spin):
     if rc == _lib.TX_ERR_SINGULAR:
         # numpy raises LinAlgError for an exactly singular E - H' (wfm/__init__.py:162)
         raise np.linalg.LinAlgError("Singular matrix")
