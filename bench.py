@@ -369,10 +369,11 @@ def run_cfg2(env, args, scaling):
     compact = {}
     for spin_n in (2, 4):
         sp = torch.empty((n_j, N_E, NLOC, spin_n), dtype=torch.float64, pin_memory=True).numpy()
+        tt = torch.empty((n_j, N_E), dtype=torch.float64, pin_memory=True).numpy()
 
-        def comp(sp=sp, spin_n=spin_n):
+        def comp(sp=sp, tt=tt, spin_n=spin_n):
             tot, s = transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, want_rt=False, want_total=True, want_spin=spin_n,
-                                        spin_out=sp)
+                                        spin_out=sp, total_out=tt)
             return float(s[0, 0, 0, 0]) + float(tot[0, 0])
         dtc = time_e2e(comp, n_e2e)
         compact[spin_n] = {"value": n_pts_total / dtc, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -496,6 +497,9 @@ def gpu_arm(args):
 
 
 def main():
+    import faulthandler
+    # a hung leg dumps every thread's stack to stderr and ends the process instead of burning the box's time limit
+    faulthandler.dump_traceback_later(int(os.environ.get("TX_BENCH_WATCHDOG", "1200")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

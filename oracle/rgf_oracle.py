@@ -179,7 +179,7 @@ def sancho_rubio(h00, h01, zs, side, tol=1e-14, max_iter=200):
     return np.linalg.inv(zI - eps_s), it
 
 
-def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stats=False):
+def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stats=False, cond_max=None, max_extend=3):
     """The same two blocks by the *telescoped* sweep the sm_100a kernel `rgf_sweep_n8t` runs (scalar hopping
     t_j = tau_j I only).  Inside a chunk of sites [a..b] the left-connected g_j are never formed:
 
@@ -190,6 +190,12 @@ def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stat
     so a chunk of k sites costs k-1 products + 1 inverse + 2 products instead of k inverses + k products.
     A chunk is closed after `kmax` sites or as soon as max|D_j| / prod|t| exceeds `gmax` (error growth
     bound); with kmax=1 this is exactly `rgf_blocks`.  Checker for the kernel's numerics; not product code.
+
+    `cond_max`: the kernel's guard against closing a chunk on a nearly singular D_a.  In long, nearly closed chains
+    (localised regime) the right-connected g_a has poles next to the real axis, |g_a| ~ 1e6, and the next inverse undoes
+    it with a cancellation that costs cond(D_a) * eps of relative accuracy (the plain recursion meets this at every
+    site).  If max|D_a| max|D_a^-1| exceeds cond_max the chunk is NOT closed there: it is extended by one more site (up
+    to `max_extend` times), which needs no inverse of the offending matrix at all.
     """
     Es = np.asarray(Es, dtype=complex)
     M, n = h.shape[0], h.shape[-1]
@@ -208,6 +214,7 @@ def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stat
         tprod = 1.0 + 0j
         scale = 1.0
         k = 0
+        extended = 0
         while True:
             z = zE - h[j]
             if j == M - 1:
@@ -225,7 +232,14 @@ def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stat
             growth = np.abs(D).max() / max(scale, 1e-300)
             a = j
             if j == 0 or k >= kmax or growth > gmax:
-                break
+                if cond_max is None or j == 0 or extended >= max_extend:
+                    break
+                Xtry = np.linalg.inv(D)
+                dmax, xmax = np.abs(D).max(axis=(1, 2)) / max(scale, 1e-300), np.abs(Xtry).max(axis=(1, 2)) * max(scale, 1e-300)
+                # a resonance pole: |D^-1| >> |D| = O(1); evanescent growth makes both large and is left to `gmax`
+                if not np.any((dmax * xmax > cond_max) & (xmax > 4096.0 * dmax)):
+                    break
+                extended += 1          # nearly singular: take one more site instead of inverting here
             Dp2, Dp1 = Dp1, D
             j -= 1
         X = np.linalg.inv(D)

@@ -105,6 +105,20 @@ def _cpu_bardeen(args):
     return time.perf_counter() - t0, 0.0
 
 
+def _cpu_dense_fit(args):
+    """The reference's own algorithm (dense assembly + dense inverse, Python loops) timed at a few chain lengths."""
+    bu.one_thread_blas()
+    from oracle import wfm_oracle
+    Ms, = args
+    ts = []
+    for Mq in Ms:
+        hq, tq, t3q = configs.disordered_blocks(N=Mq - 2, n=8, W=0.05, seed=1234)
+        t0 = time.perf_counter()
+        wfm_oracle.kernel_loops(hq, tq, t3q, 1.0, complex(-0.7), "g_closed", np.eye(8)[0], False, False, all_debug=False)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
 def _pool_rate(worker, chunks, units):
     """Runs `chunks` on one worker process each; returns (units/s aggregate, wall s, cores)."""
     cores = len(chunks)
@@ -208,7 +222,7 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
     N = 1000 if small else 10_000
     n_base = 10_000 if small else 100_000
     h, tnn, tnnn = configs.disordered_blocks(N=N, n=8, W=0.05, seed=1234)
-    hp_path = os.path.join(GOLDEN, "cfg3_hp_M10002.npz")
+    hp_path = os.path.join(GOLDEN, "hp_cfg3_M10002.npz")
 
     def parity(Es, Rh, Th, lo):
         from oracle import rgf_oracle
@@ -222,7 +236,7 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
             f64 = g["f64_err"]                                                        # numpy float64 recursion vs truth
             kap = g["kappa"]
             out.update({"parity_max_rel_err": float(dev.max()),
-                        "parity_against": "tests/golden/cfg3_hp_M10002.npz: long-double recursion (eps 1.1e-19) validated "
+                        "parity_against": "tests/golden/hp_cfg3_M10002.npz: long-double recursion (eps 1.1e-19) validated "
                                           "by mpmath at 50 digits; %d energies incl. the worst-unitarity ones" % len(idx),
                         "float64_numpy_oracle_max_rel_err_vs_extended_precision": float(f64.max()),
                         "device_over_float64_oracle_error_ratio_median": float(np.median(dev / np.maximum(f64, 1e-300))),
@@ -238,7 +252,6 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
         return out
 
     def cpu():
-        from oracle import wfm_oracle
         cores = os.cpu_count() or 1
         # (a) the numpy restatement of the recursive algorithm at full length, one energy batch per core
         per = 2
@@ -248,12 +261,10 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
         # (b) the reference's own algorithm (dense assembly + dense inverse, Python loops) at M in {64, 128, 256},
         #     one source, fitted t(M) = a M^2 + b M^3 and extrapolated to M = 10 002; the
         #     reference itself cannot run there: 102 GB dense matrix
-        Ms, ts = [32, 64, 128], []
-        for Mq in Ms:
-            hq, tq, t3q = configs.disordered_blocks(N=Mq - 2, n=8, W=0.05, seed=1234)
-            t0 = time.perf_counter()
-            wfm_oracle.kernel_loops(hq, tq, t3q, 1.0, complex(-0.7), "g_closed", np.eye(8)[0], False, False, all_debug=False)
-            ts.append(time.perf_counter() - t0)
+        #     (timed in a worker process like every other CPU leg: BLAS in the parent is not fork-safe once pools ran)
+        Ms = [32, 64, 128]
+        with mp.get_context("fork").Pool(1) as pool:
+            ts = pool.map(_cpu_dense_fit, [(Ms,)])[0]
         A = np.array([[m ** 2, m ** 3] for m in Ms], dtype=float)
         (a, b), *_ = np.linalg.lstsq(A, np.array(ts), rcond=None)
         t_full = (a * (N + 2) ** 2 + b * (N + 2) ** 3) * 8                      # x 8 sources per point
@@ -346,7 +357,7 @@ def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
         out["parity_max_rel_err"] = float(np.max(np.abs(carh[idx] - want) / np.maximum(np.abs(want), 1e-12)))
         out["parity_against"] = ("oracle/rgf_oracle.py Caroli trace on the device's own Sancho-Rubio tables, %d energies "
                                  "(parity of multi-channel leads is unpinned by the reference: g_iter refuses n>2)" % len(idx))
-        hp_path = os.path.join(GOLDEN, "cfg4_leads_hp.npz")
+        hp_path = os.path.join(GOLDEN, "hp_cfg4_leads.npz")
         if not small and env.world == 1 and os.path.exists(hp_path):
             g = np.load(hp_path)
             li = g["idx"]
@@ -514,6 +525,8 @@ def run(name, env, **kw):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("TX_BENCH_WATCHDOG", "1200")), exit=True)
     small = "--small" in sys.argv
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3", "cfg4", "cfg5"]
     env = bu.Env()

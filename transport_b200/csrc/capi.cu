@@ -74,7 +74,7 @@ struct tx_context {
     std::mutex mu;
     Options opt;
     DevBuf h, h1, par, tnn, E, sigL, sigR, src, R, T, resid, ttot, caroli, spin, big, flag;
-    DevBuf expand, nondiag;
+    DevBuf expand, nondiag, restart;      // restart: g_{b+1} of the chunk in flight, per resident warp (rgf_sweep_n8t)
     cudaStream_t own_stream = nullptr;    // created on first use
     cudaStream_t user_stream = nullptr;   // tx_context_set_stream
     bool has_user_stream = false;
@@ -198,17 +198,17 @@ int scan_structure(tx_context& cx, SweepParams& p, cudaStream_t st, bool want_ta
 
 // Telescoped sweep (rgf_n8t.cuh): the default for 5 <= n <= 8 with scalar hopping.  Persistent grid: as many CTAs
 // as are resident on the device, each warp striding over its items.
-template <int LEAD, int MINB, bool FULL, bool DIAG>
-int launch_n8t_inst(const tx_context& cx, const SweepParams& p, cudaStream_t st) {
+template <int LEAD, int MINB, bool FULL, bool DIAG, bool GUARD>
+int launch_n8t_guard(tx_context& cx, const SweepParams& p, cudaStream_t st) {
     constexpr int WARPS = 4;
     const size_t smem = (size_t)WARPS * N8TCfg::PER_WARP_BYTES;
     static int resident[16] = {0};
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
     if (!resident[dev & 15]) {
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_n8t<LEAD, MINB, FULL, DIAG, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
-        TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgf_sweep_n8t<LEAD, MINB, FULL, DIAG>, WARPS * 32, smem));
+        TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgf_sweep_n8t<LEAD, MINB, FULL, DIAG, GUARD>, WARPS * 32, smem));
         TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         resident[dev & 15] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
@@ -217,27 +217,44 @@ int launch_n8t_inst(const tx_context& cx, const SweepParams& p, cudaStream_t st)
     const long long n_warps = (p.n_pts / p.nE) * warps_per_ham;
     long long blocks = (n_warps + WARPS - 1) / WARPS;
     if (blocks > resident[dev & 15]) blocks = resident[dev & 15];
-    rgf_sweep_n8t<LEAD, MINB, FULL, DIAG><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, cx.opt.chunk_kmax, 2 * cx.opt.chunk_gexp, warps_per_ham, n_warps);
+    if (GUARD) {
+        const size_t scratch = (size_t)resident[dev & 15] * WARPS * 8 * 64 * sizeof(cd);
+        if (scratch > cx.restart.cap) TX_CUDA(cudaDeviceSynchronize());
+        if (int rc = cx.restart.ensure(scratch)) return rc;
+        cx.scratch_used = true;
+    }
+    rgf_sweep_n8t<LEAD, MINB, FULL, DIAG, GUARD><<<(unsigned)blocks, WARPS * 32, smem, st>>>(p, cx.opt.chunk_kmax, 2 * cx.opt.chunk_gexp, warps_per_ham, n_warps,
+                                                                                  reinterpret_cast<double2*>(cx.restart.ptr));
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
 }
 
-template <int LEAD, int MINB, bool FULL>
-int launch_n8t_full(tx_context& cx, SweepParams p, cudaStream_t st) {
+// chains longer than one chunk get the conditioning guard (rgf_n8t.cuh)
+template <int LEAD, int MINB, bool FULL, bool DIAG>
+int launch_n8t_inst(tx_context& cx, const SweepParams& p, cudaStream_t st) {
+    if (p.M > cx.opt.chunk_kmax) return launch_n8t_guard<LEAD, MINB, FULL, DIAG, true>(cx, p, st);
+    return launch_n8t_guard<LEAD, MINB, FULL, DIAG, false>(cx, p, st);
+}
+
+// Once per sweep (not per chunk of the Hamiltonian axis): structure scan of the on-site blocks and expansion of an
+// affine family, both into the context's scratch; `p` is rewritten to point at the results.
+int prepare_n8(tx_context& cx, SweepParams& p, cudaStream_t st, bool want_tail) {
     p.nondiag_max = nullptr;
+    p.nondiag_stride = 0;
     p.site_class = nullptr;
     p.class_stride = 0;
     p.class_count = nullptr;
     p.class_sites = 0;
     if (cx.opt.diag_tail) {
-        int rc = scan_structure(cx, p, st, false);
+        int rc = scan_structure(cx, p, st, want_tail);
         if (rc) return rc;
     }
-    {
-        int rc = materialise_affine(cx, p, st);
-        if (rc) return rc;
-    }
+    return materialise_affine(cx, p, st);
+}
+
+template <int LEAD, int MINB, bool FULL>
+int launch_n8t_full(tx_context& cx, const SweepParams& p, cudaStream_t st) {
     if (!cx.opt.diag_tail) return launch_n8t_inst<LEAD, MINB, FULL, false>(cx, p, st);
     // both instantiations; the one the device-side site statistics do not select returns at once
     int rc = launch_n8t_inst<LEAD, MINB, FULL, true>(cx, p, st);
@@ -251,20 +268,9 @@ int launch_n8t(tx_context& cx, const SweepParams& p, cudaStream_t st) {
 }
 
 template <int LEAD, int MINB, int PIVX, int DMB = 1>
-int launch_n8(tx_context& cx, SweepParams p, cudaStream_t st) {
+int launch_n8(tx_context& cx, const SweepParams& p, cudaStream_t st) {
     constexpr int WARPS = 4;
-    p.nondiag_max = nullptr;
-    p.nondiag_stride = 0;
-    p.site_class = nullptr;
-    p.class_stride = 0;
-    if (cx.opt.diag_tail) {
-        int rc = scan_structure(cx, p, st, LEAD == LEAD_CLOSED);
-        if (rc) return rc;
-    }
-    {
-        int rc = materialise_affine(cx, p, st);
-        if (rc) return rc;
-    }
+    (void)cx;
     const size_t smem = (size_t)WARPS * N8Cfg::PER_WARP_BYTES;
     static bool attr_done[16] = {false};
     int dev = 0;
@@ -393,7 +399,7 @@ int tx_context_destroy(tx_context* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->scratch_ev) cudaEventSynchronize(c->scratch_ev);
     DevBuf* bufs[] = {&c->h, &c->h1, &c->par, &c->tnn, &c->E, &c->sigL, &c->sigR, &c->src, &c->R, &c->T, &c->resid,
-                      &c->ttot, &c->caroli, &c->spin, &c->big, &c->flag, &c->expand, &c->nondiag, &c->nit, &c->okb};
+                      &c->ttot, &c->caroli, &c->spin, &c->big, &c->flag, &c->expand, &c->nondiag, &c->restart, &c->nit, &c->okb};
     for (DevBuf* b : bufs) b->release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -513,6 +519,34 @@ int tx_sweep_launch_count(int n, int M, int hop_mode) {
 
 namespace {
 
+// Chunk c of the Hamiltonian axis [p0, p0 + np_) of a prepared sweep: every per-Hamiltonian pointer moves, the batch-wide
+// site statistics stay.
+SweepParams slice_params(const SweepParams& p, long long p0, long long np_) {
+    SweepParams q = p;
+    const long long o_pts = p0 * p.nE;
+    q.h += p0 * p.h_stride;
+    q.tnn += p0 * p.t_stride;
+    if (q.sigL) q.sigL += p0 * p.sig_stride;
+    if (q.sigR) q.sigR += p0 * p.sig_stride;
+    if (q.params) q.params += p0;
+    if (q.R) q.R += o_pts * p.n_src * p.n;
+    if (q.T) q.T += o_pts * p.n_src * p.n;
+    if (q.resid) q.resid += o_pts * p.n_src;
+    if (q.ttot) q.ttot += o_pts;
+    if (q.spin) q.spin += o_pts * p.n_src * p.spin_n;
+    q.gather.off += o_pts;
+    if (q.nondiag_max) q.nondiag_max += p0 * p.nondiag_stride;
+    if (q.site_class) q.site_class += p0 * p.class_stride;
+    q.n_pts = np_ * p.nE;
+    return q;
+}
+
+// Called after the launches of every chunk (the host entry records an event and queues the chunk's device->host copies).
+struct ChunkHook {
+    virtual int after_chunk(int c, long long p0, long long np_, cudaStream_t st) = 0;
+    virtual ~ChunkHook() {}
+};
+
 // Argument checks of the device-pointer sweep (run before any CUDA call, so that bad arguments are reported as
 // such even without a device).
 int check_small_args(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
@@ -547,7 +581,7 @@ int check_small_args(const tx_cplx* h, int n_h, const tx_cplx* h1, const double*
 int sweep_small_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
                     const tx_cplx* tnn, int n_t, int n, int M, int n_ham, const tx_cplx* E, int nE, int lead_mode,
                     const tx_cplx* sigL, const tx_cplx* sigR, int n_sig, int hop_mode, const double* sources, int n_src,
-                    const SweepOut& o, int* singular_flag, cudaStream_t st) {
+                    const SweepOut& o, int* singular_flag, cudaStream_t st, int n_chunks = 1, ChunkHook* hook = nullptr) {
     if (int rc = check_small_args(h, n_h, h1, params, tnn, n_t, n, M, n_ham, E, nE, lead_mode, sigL, sigR, n_sig, hop_mode,
                                   sources, n_src, o, singular_flag))
         return rc;
@@ -596,24 +630,36 @@ int sweep_small_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     // on another stream: order this call behind them
     if (cx.scratch_used && cx.scratch_stream != st && cx.scratch_ev) TX_CUDA(cudaStreamWaitEvent(st, cx.scratch_ev, 0));
     cx.scratch_used = false;
-    int rc = TX_ERR_UNSUPPORTED;
-    switch (N) {
-        case 1: rc = dispatch_modes<1, 1, 4, 4>(p, hop, lead, st); break;
-        case 2: rc = dispatch_modes<2, 1, 4, 4>(p, hop, lead, st); break;
-        case 4: rc = dispatch_modes<4, 2, 3, 3>(p, hop, lead, st); break;
-        case 8:
-            if (hop == HOP_SCALAR && cx.opt.variant != 0) {
-                // default: telescoped sweep; its warps take eight energies of one Hamiltonian, so very short energy
-                // axes that are not a multiple of eight go to the plain sweep (one point per four lanes) instead
-                if (cx.opt.variant == 13 && (nE >= 64 || nE % 8 == 0))
-                    rc = (lead == LEAD_TABLE) ? launch_n8t<LEAD_TABLE, 2>(cx, p, st) : launch_n8t<LEAD_CLOSED, 2>(cx, p, st);
+    // kernel family; the n = 8 scalar-hopping kernels share one preparation per sweep
+    // default: telescoped sweep; its warps take eight energies of one Hamiltonian, so very short energy axes that are
+    // not a multiple of eight go to the plain sweep (one point per four lanes) instead
+    const bool fam_n8 = N == 8 && hop == HOP_SCALAR && cx.opt.variant != 0;
+    const bool fam_n8t = fam_n8 && cx.opt.variant == 13 && (nE >= 64 || nE % 8 == 0);
+    int rc = TX_OK;
+    if (fam_n8) rc = prepare_n8(cx, p, st, !fam_n8t && lead == LEAD_CLOSED);
+    if (rc) return rc;
+    if (n_chunks < 1) n_chunks = 1;
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long p0 = (long long)n_ham * c / n_chunks, p1 = (long long)n_ham * (c + 1) / n_chunks;
+        if (p1 <= p0) continue;
+        const SweepParams q = n_chunks == 1 ? p : slice_params(p, p0, p1 - p0);
+        rc = TX_ERR_UNSUPPORTED;
+        switch (N) {
+            case 1: rc = dispatch_modes<1, 1, 4, 4>(q, hop, lead, st); break;
+            case 2: rc = dispatch_modes<2, 1, 4, 4>(q, hop, lead, st); break;
+            case 4: rc = dispatch_modes<4, 2, 3, 3>(q, hop, lead, st); break;
+            case 8:
+                if (fam_n8t)
+                    rc = (lead == LEAD_TABLE) ? launch_n8t<LEAD_TABLE, 2>(cx, q, st) : launch_n8t<LEAD_CLOSED, 2>(cx, q, st);
+                else if (fam_n8)
+                    rc = (lead == LEAD_TABLE) ? launch_n8<LEAD_TABLE, 3, 0>(cx, q, st) : launch_n8<LEAD_CLOSED, 3, 0>(cx, q, st);
                 else
-                    rc = (lead == LEAD_TABLE) ? launch_n8<LEAD_TABLE, 3, 0>(cx, p, st) : launch_n8<LEAD_CLOSED, 3, 0>(cx, p, st);
-            } else {
-                rc = dispatch_modes<8, 4, 3, 2>(p, hop, lead, st);
-            }
-            break;
-        case 16: rc = dispatch_modes<16, 16, 3, 2>(p, hop, lead, st); break;
+                    rc = dispatch_modes<8, 4, 3, 2>(q, hop, lead, st);
+                break;
+            case 16: rc = dispatch_modes<16, 16, 3, 2>(q, hop, lead, st); break;
+        }
+        if (rc) return rc;
+        if (hook && (rc = hook->after_chunk(c, p0, p1 - p0, st))) return rc;
     }
     if (rc == TX_OK && cx.scratch_used) {
         if (!cx.scratch_ev) TX_CUDA(cudaEventCreateWithFlags(&cx.scratch_ev, cudaEventDisableTiming));
@@ -891,39 +937,36 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
         if (!ws.copy_stream) TX_CUDA(cudaStreamCreateWithFlags(&ws.copy_stream, cudaStreamNonBlocking));
         if (!ws.ev[0])
             for (int i = 0; i < 2; ++i) TX_CUDA(cudaEventCreateWithFlags(&ws.ev[i], cudaEventDisableTiming));
-        const size_t h_ham = (size_t)M * nn, t_ham = (size_t)(M - 1) * nn, s_ham = (size_t)nE * nn;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int p0 = (int)((long long)n_ham * c / n_chunks), p1 = (int)((long long)n_ham * (c + 1) / n_chunks);
-            const int np_ = p1 - p0;
-            if (np_ <= 0) continue;
-            const size_t o_pts = (size_t)p0 * nE;
-            const SweepOut o{R ? (double*)ws.R.ptr + o_pts * n_src * n : nullptr, R ? (double*)ws.T.ptr + o_pts * n_src * n : nullptr,
-                             bytes_res ? (double*)ws.resid.ptr + o_pts * n_src : nullptr,
-                             t_total ? (double*)ws.ttot.ptr + o_pts : nullptr, nullptr,
-                             spin ? (double*)ws.spin.ptr + o_pts * n_src * spin_n : nullptr, n_up, spin_n};
-            rc = sweep_small_dev(ws,
-                (const tx_cplx*)ws.h.ptr + (n_h > 1 ? p0 * h_ham : 0), n_h > 1 ? np_ : 1,
-                h1 ? (const tx_cplx*)ws.h1.ptr : nullptr, h1 ? (const double*)ws.par.ptr + p0 : nullptr,
-                (const tx_cplx*)ws.tnn.ptr + (n_t > 1 ? p0 * t_ham : 0), n_t > 1 ? np_ : 1, n, M, np_,
-                (const tx_cplx*)ws.E.ptr, nE, lead_mode,
-                have_tables ? (const tx_cplx*)ws.sigL.ptr + (n_sig_use > 1 ? p0 * s_ham : 0) : nullptr,
-                have_tables ? (const tx_cplx*)ws.sigR.ptr + (n_sig_use > 1 ? p0 * s_ham : 0) : nullptr, n_sig_use > 1 ? np_ : 1,
-                hop_mode, bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, o, (int*)ws.flag.ptr, st);
-            if (rc) return rc;
-            if (n_chunks == 1) break;   // single chunk: the copies below follow on the same stream
-            cudaEvent_t ev = ws.ev[c & 1];
-            TX_CUDA(cudaEventRecord(ev, st));
-            TX_CUDA(cudaStreamWaitEvent(ws.copy_stream, ev, 0));
-            if (R) {
-                const size_t ob = (size_t)np_ * nE * n_src * n * sizeof(double);
-                TX_CUDA(cudaMemcpyAsync(R + o_pts * n_src * n, o.R, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
-                TX_CUDA(cudaMemcpyAsync(T + o_pts * n_src * n, o.T, ob, cudaMemcpyDeviceToHost, ws.copy_stream));
+        // one preparation (structure scan, affine expansion) for the whole batch; per chunk only the sweep kernels
+        struct CopyOut : ChunkHook {
+            tx_context& ws; double *R, *T, *spin; size_t row, srow; int nE, n_chunks; bool* copied;
+            CopyOut(tx_context& w, double* r, double* t, double* s, size_t row_, size_t srow_, int nE_, int nc, bool* cp)
+                : ws(w), R(r), T(t), spin(s), row(row_), srow(srow_), nE(nE_), n_chunks(nc), copied(cp) {}
+            int after_chunk(int c, long long p0, long long np_, cudaStream_t st) override {
+                if (n_chunks == 1) return TX_OK;          // single chunk: the copies follow on the same stream
+                cudaEvent_t ev = ws.ev[c & 1];
+                TX_CUDA(cudaEventRecord(ev, st));
+                TX_CUDA(cudaStreamWaitEvent(ws.copy_stream, ev, 0));
+                const size_t o_pts = (size_t)p0 * nE, pts = (size_t)np_ * nE;
+                if (R) {
+                    TX_CUDA(cudaMemcpyAsync(R + o_pts * row, (double*)ws.R.ptr + o_pts * row, pts * row * sizeof(double), cudaMemcpyDeviceToHost, ws.copy_stream));
+                    TX_CUDA(cudaMemcpyAsync(T + o_pts * row, (double*)ws.T.ptr + o_pts * row, pts * row * sizeof(double), cudaMemcpyDeviceToHost, ws.copy_stream));
+                }
+                if (spin)
+                    TX_CUDA(cudaMemcpyAsync(spin + o_pts * srow, (double*)ws.spin.ptr + o_pts * srow, pts * srow * sizeof(double),
+                                            cudaMemcpyDeviceToHost, ws.copy_stream));
+                *copied = true;
+                return TX_OK;
             }
-            if (spin)
-                TX_CUDA(cudaMemcpyAsync(spin + o_pts * n_src * spin_n, o.spin, (size_t)np_ * nE * n_src * spin_n * sizeof(double),
-                                        cudaMemcpyDeviceToHost, ws.copy_stream));
-            copied_out = true;
-        }
+        } hook(ws, R, T, spin, (size_t)n_src * n, (size_t)n_src * spin_n, nE, n_chunks, &copied_out);
+        const SweepOut o{R ? (double*)ws.R.ptr : nullptr, R ? (double*)ws.T.ptr : nullptr, bytes_res ? (double*)ws.resid.ptr : nullptr,
+                         t_total ? (double*)ws.ttot.ptr : nullptr, nullptr, spin ? (double*)ws.spin.ptr : nullptr, n_up, spin_n};
+        rc = sweep_small_dev(ws, (const tx_cplx*)ws.h.ptr, n_h, h1 ? (const tx_cplx*)ws.h1.ptr : nullptr,
+                             h1 ? (const double*)ws.par.ptr : nullptr, (const tx_cplx*)ws.tnn.ptr, n_t, n, M, n_ham,
+                             (const tx_cplx*)ws.E.ptr, nE, lead_mode, have_tables ? (const tx_cplx*)ws.sigL.ptr : nullptr,
+                             have_tables ? (const tx_cplx*)ws.sigR.ptr : nullptr, n_sig_use, hop_mode,
+                             bytes_src ? (const double*)ws.src.ptr : nullptr, n_src, o, (int*)ws.flag.ptr, st, n_chunks, &hook);
+        if (rc) return rc;
         if (copied_out) TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
     } else {
         // generic-size path (n <= 64): one CTA per point on the device tables

@@ -77,7 +77,7 @@ __device__ __forceinline__ unsigned n8_key(double2 a, int row, bool is_used) {
 // reciprocal of pivot k+1 is computed while that reload is in flight.
 template <int PIVX, int SWZ = 0>
 __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, double2* gt, int grp, int row0, int* singular,
-                                          unsigned zmask) {
+                                          unsigned zmask, unsigned* xmax = nullptr) {
     constexpr int N = 8, LP = 4, GPW = 8;
     const int lane = threadIdx.x & 31;
     const int gbase = lane & ~(LP - 1);
@@ -219,8 +219,14 @@ __device__ __forceinline__ void n8_invert(double2 (&A)[2][8], double2* pv, doubl
     for (int j = 0; j < N; ++j) {
         const int col = (int)((perm >> (4 * j)) & 0xFu);
         const int base = col * 8, sw = SWZ ? col : (col & 1) * 5;   // SWZ: layout of rgf_n8t.cuh
-        gt[base + (krow0 ^ sw)] = cmul2(A[0][j], dinv0);
-        gt[base + (krow1 ^ sw)] = cmul2(A[1][j], dinv1);
+        const double2 v0 = cmul2(A[0][j], dinv0), v1 = cmul2(A[1][j], dinv1);
+        gt[base + (krow0 ^ sw)] = v0;
+        gt[base + (krow1 ^ sw)] = v1;
+        if (xmax) {   // largest |entry| of the inverse (high words), for the caller's conditioning guard
+            const unsigned m0 = max((unsigned)__double2hiint(v0.x) & 0x7fffffffu, (unsigned)__double2hiint(v0.y) & 0x7fffffffu);
+            const unsigned m1 = max((unsigned)__double2hiint(v1.x) & 0x7fffffffu, (unsigned)__double2hiint(v1.y) & 0x7fffffffu);
+            *xmax = max(*xmax, max(m0, m1));
+        }
     }
     __syncwarp();
 }

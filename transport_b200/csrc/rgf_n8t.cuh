@@ -53,9 +53,10 @@ __device__ __forceinline__ void cdmma(double (&re)[2], double (&im)[2], const do
     dmma_8x8x4(im, a.y, b.x);
 }
 
-template <int LEAD, int MINB, bool FULL, bool DIAG>
+template <int LEAD, int MINB, bool FULL, bool DIAG, bool GUARD>
 __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, const int kmax, const int gexp2,
-                                                           const int warps_per_ham, const long long n_warps) {
+                                                           const int warps_per_ham, const long long n_warps,
+                                                           double2* __restrict__ restart_scratch) {
     constexpr int N = 8, RP = 2, GPW = 8;
     constexpr unsigned FULLM = 0xffffffffu;
     extern __shared__ double2 smem_all[];
@@ -97,6 +98,11 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
     // padded to a multiple of eight per Hamiltonian), so the block fragments of a site are loaded once and shared by
     // the eight points; finished warps take the next item on their own (no CTA-wide tail).
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    // g_{b+1}^T of the chunk in flight, kept in an L2-resident scratch (8 KB per resident warp) for the rare restart
+    // of a chunk by the conditioning guard below
+    auto gsave = [&]() -> double2* {   // recomputed where it is used: not worth a live register pair
+        return restart_scratch + ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * (GPW * 64) + gid * 8 + 2 * tid;
+    };
     for (long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp; wg < n_warps; wg += wstride) {
     const int ham = (int)(wg / warps_per_ham);
     const int e_raw = (int)(wg - (long long)ham * warps_per_ham) * GPW + gid;
@@ -295,6 +301,16 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         }
     };
 
+    // Conditioning guard.  In long, nearly closed chains (localised regime) the right-connected g_a can have a pole next
+    // to the real axis: D_a is nearly singular, |g_a| ~ 1e6, and the next chunk undoes it with a cancellation that costs
+    // cond(D_a) eps of relative accuracy (the plain recursion meets this at every site; measured on BASELINE config 3:
+    // unitarity residual 4.8e-8 at one energy of 1e5, 2e-8 relative error on T).  If max|U_a| max|U_a^-1| exceeds 2^CONDX
+    // the chunk is NOT closed at a: it is restarted from its first site (g_{b+1} reloaded from the scratch) and made one
+    // site longer, so the offending matrix is never inverted; at most three times per chunk.
+    // oracle/rgf_oracle.py:rgf_blocks_telescoped(cond_max=...) is the numpy restatement.  GUARD is instantiated for chains
+    // longer than one chunk (M > kmax); short chains keep the leaner code.
+    constexpr int CONDX = 17, CONDR = 12;
+    int xlen = 0;   // 0: normal chunk; else (restarts << 16) | forced length of the chunk being redone
     double2 Ya[GPW][2], Yb[GPW][2];
     int j = M - 1;
     while (j >= 0) {
@@ -366,11 +382,11 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         if (j > 0) prefetch(j - 1);
         // one more site: Q <- U_j from P = U_{j+1}; false if the chunk has to be closed at the current site
         auto advance = [&](const double2 (&P)[GPW][2], double2 (&Q)[GPW][2]) -> bool {
-            if (!(j > 0 && k < kmax)) return false;
+            if (!(j > 0 && k < (xlen ? (xlen & 0xffff) : kmax))) return false;
             const double2 tj = tn;
             const double kap = fma(tj.x, tj.x, tj.y * tj.y);
             if (!(kap > 0.0)) return false;           // decoupled site (or NaN): it starts its own chunk
-            if (grown(P, nrm)) return false;          // P = U_{j+1} is the newest matrix of the chunk
+            if (xlen == 0 && grown(P, nrm)) return false;   // P = U_{j+1} is the newest matrix of the chunk
             --j;
             ++k;
             const double rk = fast_rcp(kap);
@@ -405,6 +421,10 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
 
         // -------------------------------------------------------------- close the chunk at site a
         // D_a / d_a -> XB (slot (q; r; c) = U_a[c][r]),  U_{a+1} -> YB stored transposed
+        unsigned umax = 0u, xmax = 0u;
+        auto absmax2 = [](double2 u, double2 v) -> unsigned {
+            return max(max(hi_abs(u.x), hi_abs(u.y)), max(hi_abs(v.x), hi_abs(v.y)));
+        };
         if (phase == 0) {
 #pragma unroll
             for (int q = 0; q < GPW; ++q) {
@@ -412,6 +432,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 XB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
                 YB[q * N8TCfg::PSTRIDE + x0i] = Yb[q][0];
                 YB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
+                if (GUARD) umax = max(umax, absmax2(Ya[q][0], Ya[q][1]));
             }
         } else {
 #pragma unroll
@@ -420,6 +441,7 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 XB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
                 YB[q * N8TCfg::PSTRIDE + x0i] = Ya[q][0];
                 YB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
+                if (GUARD) umax = max(umax, absmax2(Yb[q][0], Yb[q][1]));
             }
         }
         __syncwarp();
@@ -431,8 +453,31 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
 #pragma unroll
                 for (int c = 0; c < N; ++c) A[s][c] = xb[n8t_idx(row0 + s, c)];
             __syncwarp();
-            n8_invert<0, 1>(A, PV, xb, gid, row0, p.singular, zmask);   // X[k][c] -> slot (c; k): stored transposed
+            n8_invert<0, 1>(A, PV, xb, gid, row0, p.singular, zmask, GUARD ? &xmax : nullptr);   // X[k][c] -> slot (c; k): stored transposed
         }
+        if (GUARD && a > 0 && (xlen >> 16) < 3) {
+            // warp maxima of max|U_a| (over the eight points) and max|U_a^-1|: their product bounds every point's
+            // condition estimate from above (a conservative trigger)
+            umax = __reduce_max_sync(FULLM, umax);
+            xmax = __reduce_max_sync(FULLM, xmax);
+            // a resonance pole shows as |U^-1| >> |U| = O(1); evanescent growth inside the chunk makes BOTH large (that
+            // is what the growth bound handles, and a longer chunk would only make it worse): trigger on the former only
+            const int uexp = (int)(umax >> 20) - 1023, xexp = (int)(xmax >> 20) - 1023;
+            if (xexp + uexp > CONDX && xexp - uexp > CONDR) {
+                xlen = ((xlen >> 16) + 1) << 16 | (k + 1);
+                if (b < M - 1) {
+                    const double2* gs = gsave();
+#pragma unroll
+                    for (int q = 0; q < GPW; ++q) {
+                        Ya[q][0] = gs[q * 64];
+                        Ya[q][1] = gs[q * 64 + 1];
+                    }
+                }
+                j = b;
+                continue;                             // same chunk again, one site longer
+            }
+        }
+        xlen = 0;
         // W <- tau W X   and   g_a^T = X^T Y_{a+1}   (the X fragment serves as B of the first and A of the second);
         // undoing the scaling:  X = Xs / d_a,  Y_{a+1} = d_{a+1} U_{a+1}
         {
@@ -480,6 +525,14 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
             }
         }
         __syncwarp();   // every fragment of X and Y_{a+1} has been read: XB / YB may be overwritten
+        if (GUARD && a > 0) {    // g_a^T: the start of the next chunk, should the guard have to restart it
+            double2* gs = gsave();
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {
+                gs[q * 64] = Ya[q][0];
+                gs[q * 64 + 1] = Ya[q][1];
+            }
+        }
         j = a - 1;
     }
 

@@ -80,7 +80,7 @@ class Context:
 def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, params=None,
                        sigL=None, sigR=None, want_resid=False, out=None, want_total=False,
                        want_caroli=False, want_rt=True, want_spin=False, n_elec_up=None, spin_out=None,
-                       context=None):
+                       total_out=None, context=None):
     """Reflection / transmission probabilities for every (Hamiltonian, energy, source).
 
     Args
@@ -97,7 +97,7 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
       want_rt  False: the per-channel arrays are neither allocated, written nor copied (compact sweeps)
       want_spin  2 or 4 (True = 4): spin-resolved sums fused into the device epilogue, [P, nE, n_src, want_spin] =
              (T no-flip, T flip[, R no-flip, R flip]) with channels [:n_elec_up] = electron spin up (default n//2;
-             run_wfm_gate.py:404-405,473-477); `spin_out` optionally supplies the array to fill
+             run_wfm_gate.py:404-405,473-477); `spin_out` / `total_out` optionally supply the arrays to fill (e.g. pinned memory)
       context  a `Context` (own workspace / stream) or None for the per-device default context
     Returns
       R, T  float64 [P, nE, n_src, n] (if want_rt)  (+ resid [P, nE, n_src] = sum R + sum T - 1 if want_resid,
@@ -169,7 +169,11 @@ def transmission_sweep(h, tnn, Es, converger="g_closed", sources=None, h1=None, 
         if R.shape != shape or T.shape != shape or R.dtype != np.float64 or T.dtype != np.float64:
             raise ValueError("out arrays must be float64 of shape %s" % (shape,))
     resid = np.empty(shape[:3], dtype=np.float64) if want_resid else None
-    total = np.empty(shape[:2], dtype=np.float64) if want_total else None
+    total = None
+    if want_total:
+        total = np.empty(shape[:2], dtype=np.float64) if total_out is None else total_out
+        if total.shape != shape[:2] or total.dtype != np.float64:
+            raise ValueError("total_out must be float64 of shape %s" % (shape[:2],))
     caroli = np.empty(shape[:2], dtype=np.float64) if want_caroli else None
     spin, spin_n, n_up = None, 0, 0
     if want_spin:
