@@ -340,10 +340,10 @@ int tx_bardeen_current_dev(const double* E, const double* M2, int P, int n, int 
                            double kBT, double* I, void* stream);
 /* bardeen.Ts_bardeen (:577-632): T[alpha][m][beta] = NL/(k tL[alpha]) NR/tR[beta] dos M2[alpha][m][beta];
  * per-channel lead parameters tL, VL, tR, VR [n].  Outside the band k and dos take the real parts of numpy's
- * complex branches (k = 0 or pi, dos = 0).  flags [2 + n*n]: flags[0] = number of wavenumbers outside the band,
- * flags[1] = number of densities of states above the band top, flags[2 + alpha*n + beta] = number of m with a
- * real density of states; the reference (:611, :624, max of the imaginary parts) raises ValueError when
- * flags[0] > 0, flags[1] > 0 or one of the remaining counts is 0. */
+ * complex branches (k = 0 or pi, dos = 0, on BOTH sides of the band).  flags [2 + n*n]: flags[0] = number of wavenumbers
+ * outside the band, flags[1] = 0 (reserved), flags[2 + alpha*n + beta] = number of m with a real density of states;
+ * the reference (:611, :624, max of the imaginary parts) raises ValueError when flags[0] > 0 or one of the per-(alpha,
+ * beta) counts is 0. */
 int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double* tL, const double* VL, const double* tR,
                   const double* VR, int NL, int NR, double* T, int* flags);
 

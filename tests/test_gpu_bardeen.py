@@ -80,6 +80,15 @@ def test_ts_bardeen_errors():
     assert T[0, 0, 0] == 0.0 and np.allclose(T, T0, rtol=1e-13)
     with pytest.raises(ValueError):                                     # :624 every m below the band bottom
         bardeen.Ts_bardeen(mixed[:, :1], M[:, :1], np.eye(1), np.eye(1), 0 * np.eye(1), 0.05 * np.eye(1), 5, 5)
+    # ABOVE the right band top (x > 1) numpy's complex branch also gives a negative imaginary part: a mixed row passes
+    # with T = 0 there, exactly like the oracle (the reference's own arithmetic); only an all-outside row raises
+    above = np.array([[-1.2 + 0j, 0.3, 1.9]])                           # VR = -1: x = -0.1, 0.65, 1.45
+    Ma = np.ones((1, 3, 1))
+    Ta = bardeen.Ts_bardeen(above, Ma, np.eye(1), np.eye(1), 0 * np.eye(1), -1.0 * np.eye(1), 5, 5)
+    Ta0 = bo.Ts_bardeen(above, Ma, np.eye(1), np.eye(1), 0 * np.eye(1), -1.0 * np.eye(1), 5, 5)
+    assert Ta[0, 2, 0] == 0.0 and Ta[0, 1, 0] > 0 and np.allclose(Ta, Ta0, rtol=1e-13)
+    with pytest.raises(ValueError):
+        bardeen.Ts_bardeen(above[:, 2:], Ma[:, 2:], np.eye(1), np.eye(1), 0 * np.eye(1), -1.0 * np.eye(1), 5, 5)
     E = np.array([[-1.5 + 0j, 2.5]])
     with pytest.raises(ValueError):                                     # :611 complex wavenumber
         bardeen.Ts_bardeen(E, np.ones((1, 2, 1)), np.eye(1), np.eye(1), 0 * np.eye(1), 0 * np.eye(1), 5, 5)
@@ -297,3 +306,52 @@ def test_region_sweep_two_channels_with_hcprime():
     assert np.array_equal(r1["EL"][..., :ms], r0["EL"]) and np.array_equal(r1["ER"][..., :ms], r0["ER"])
     assert np.array_equal(r1["Mavg"][:, :, :ms], r0["Mavg"])
     assert np.abs(r1["Mavg"]).max() > 0
+
+
+def test_kernel_well_prime_ragged_padding_weights_last_state():
+    """kernel_well_prime un-raggeds the right-well channels with copies of a channel's last bound state (:484-490) and
+    the copies take part in the window average (:510-519).  With a window wide enough to hold the last state AND others
+    the device must weight it by 1 + (n_bound_right - nR[beta]).  Checked against the same average formed in numpy from
+    the device's own eigenvectors (the reference's value depends on LAPACK's arbitrary eigenvector signs there)."""
+    g = load_golden("bardeen_prime_ragged.npz")
+    n = 2
+    interval = 8e-2
+    a = _args(g)
+    tinfty, tL, tR, Vinfty, VL, VLp, VR, VRp, Ninf, NL, NR, HC = a
+    HCp, Ecut = g["HCprime"], g["E_cutoff"]
+    bL = bardeen.hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VRp, Ninf, NL, NR, HCp)
+    bR = bardeen.hsys_site_blocks(tinfty, tL, tR, Vinfty, VLp, VR, Ninf, NL, NR, HCp)
+    bS = bardeen.hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninf, NL, NR, HC)
+    dL, eL = bardeen._channel_tridiagonals(bL)
+    dR, eR = bardeen._channel_tridiagonals(bR)
+    hd = [np.real(s - l) for s, l in zip(bS, bL)]
+    cut = (np.real(np.diagonal(Ecut)) - 2.0)[None]
+    r = bardeen.wells_batched(dL[None], eL[None], dR[None], eR[None], cut, cut, cut, hd[0][None], hd[1][None], hd[2][None],
+                              interval, sign_fix=False, want_states=True)
+    nR = r["nR_states"][0]
+    assert nR[0] != nR[1], "the fixture must be ragged"
+    longest = int(nR.max())
+    S = dL.shape[-1]
+    Hd = np.zeros((S, S, n, n))
+    for j in range(S):
+        Hd[j, j] = hd[0][j]
+    for j in range(S - 1):
+        Hd[j, j + 1] = hd[1][j]
+        Hd[j + 1, j] = hd[2][j]
+    checked = 0
+    for alpha in range(n):
+        for m in range(int(r["nL"][0, alpha])):
+            for beta in range(n):
+                w = np.ones(nR[beta])
+                w[-1] += longest - nR[beta]
+                inside = np.abs(r["EL"][0, alpha, m] - r["ER"][0, beta, :nR[beta]]) < interval
+                if not inside.any():
+                    assert r["Mavg"][0, beta, m, alpha] == 0.0
+                    continue
+                y = Hd[:, :, beta, alpha] @ r["psiL"][0, alpha, m]
+                els = r["psiR"][0, beta, :nR[beta]] @ y
+                want = np.sum(w[inside] * els[inside]) / np.sum(w[inside])
+                assert np.isclose(r["Mavg"][0, beta, m, alpha], want, rtol=1e-9, atol=1e-18), (alpha, m, beta)
+                if inside[-1] and inside.sum() > 1 and longest > nR[beta]:
+                    checked += 1
+    assert checked > 0, "no window held the padded last state together with another one: widen the interval"

@@ -716,3 +716,63 @@ def test_staged_inverse_blocked_gauss_jordan(n, inverse_mode):
     with pytest.raises(_lib.TransportError) as ei:
         check(_lib.load().tx_debug_invert_staged(ptr(as_c128(S[None])), ptr(out[:1]), 1, n))
     assert ei.value.code == _lib.TX_ERR_SINGULAR
+
+
+@pytest.mark.parametrize("name", ["nnn_n1_M8.npz", "nnn_n2_M6.npz", "nnn_n2_M7.npz", "nnn_n3_M5.npz"])
+def test_next_nearest_neighbour_blocks_through_reference_signatures(name):
+    """nonzero tnnn through wfm.kernel / wfm.Green / the psi output (reference: block-pentadiagonal dense assembly,
+    wfm/__init__.py:209-213; here: sites paired into super-blocks), against the live reference's output."""
+    g = load_golden(name)
+    h, tnn, tnnn = g["h"], g["tnn"], g["tnnn"]
+    for i, E in enumerate(g["Es"]):
+        for s, src in enumerate(g["sources"]):
+            Rs, Ts = wfm.kernel(h, tnn, tnnn, 1.0, E, "g_closed", src, False, False, all_debug=True)
+            _check(Rs, Ts, g["R"][i, s], g["T"][i, s])
+        psi = wfm.kernel(h, tnn, tnnn, 1.0, E, "g_closed", g["sources"][0], True, False, all_debug=False)
+        assert np.allclose(psi, g["psi"][i], rtol=1e-10, atol=1e-13)
+        G = wfm.Green(h, tnn, tnnn, 1.0, E, "g_closed")
+        assert G.shape == g["G"][i].shape and np.allclose(G, g["G"][i], rtol=1e-10, atol=1e-13)
+    Rh = wfm.Rhat_matrix(h, tnn, tnnn, 1.0, g["Es"][1])
+    n = h.shape[-1]
+    ka = np.arccos((g["Es"][1] - np.diagonal(h[0])) / (-2.0))
+    assert np.allclose(Rh, 2j * g["G"][1][0, 0] * np.sin(ka)[None, :] - np.eye(n), rtol=1e-10, atol=1e-13)
+
+
+def test_ts_wfm_well_channel_dependent_lead_potentials():
+    """VL = VR = diag(0, Delta) as rbmenez_sup_inel.py:135 passes them: every channel keeps its own lead on-site energy
+    (bardeen/__init__.py:651, :667 multiply the matrices elementwise with the identity).  alpha = 0 against the live
+    reference's wfm.kernel on the same blocks, alpha = 1 (which the reference's kernel refuses, :67-70) against the
+    recursive numpy oracle."""
+    from transport_b200 import bardeen
+    g = load_golden("well_channel_potentials.npz")
+    HC, tL, VLR, Emas = g["HC"], g["tL"], g["VLR"], g["Emas"]
+    Tb = bardeen.Ts_wfm_well(tL, tL, VLR, VLR, HC, Emas)
+    assert Tb.shape == (2, 4, 2)
+    assert rt_err(Tb[:, :, 0].T, g["T_alpha0"]) < RTOL
+    h, tnn, tnnn = bardeen.blocks_from_HC(tL, tL, VLR, VLR, HC)
+    assert h[0][1, 1] == VLR[1, 1] and h[-1][1, 1] == VLR[1, 1] and h[0][0, 1] == 0
+    _, oT = rgf_oracle.transmission_closed(h, tnn, Emas[1].astype(complex), np.eye(2)[[1]])
+    assert rt_err(Tb[:, :, 1].T, oT[:, 0]) < RTOL
+    # the old behaviour (lead potential of channel 0 used for every channel) is measurably different
+    h_wrong, _, _ = bardeen.blocks_from_HC(1.0, 1.0, 0.0, 0.0, HC)
+    _, oT_wrong = rgf_oracle.transmission_closed(h_wrong, tnn, Emas[1].astype(complex), np.eye(2)[[1]])
+    assert np.max(np.abs(oT_wrong - oT)) > 1e-3
+
+
+def test_landauer_current_pinned_to_reference_fcdmft():
+    """SURVEY §8f row 4, pinned: the reference's matrix-Gamma Landauer current (fcdmft.landauer, fcdmft/__init__.py:224-292,
+    golden produced by the unmodified function) against the device path — Caroli trace of the same system as a wfm chain
+    (sweep epilogue, matrix Gamma) -> tx_landauer_current (Fermi window, trapezoid rule)."""
+    from transport_b200 import current
+    g = load_golden("landauer_fcdmft.npz")
+    E = g["energies"]
+    car = transmission_sweep(g["h"], g["tnn"], E.astype(complex), sources=np.eye(2)[:1], want_rt=False, want_caroli=True)
+    for tag, kBT in (("kT0", 0.0), ("kT005", 0.05)):
+        want_j = np.real(g["jE_" + tag])
+        I, jE = current.landauer_current(car[0], E, float(g["muL"]), float(g["muR"]), kBT, want_density=True)
+        assert np.allclose(jE[0], want_j, rtol=1e-11, atol=1e-15)
+        assert np.isclose(I[0], float(g["I_" + tag]), rtol=1e-11)
+    # the Fermi-window / trapezoid kernel alone, on the reference's own transmission function
+    T_ref = np.real(g["jE_kT0"]) * 2 * np.pi        # inside the bias window n_L - n_R = 1 at kBT = 0
+    window = (E <= float(g["muL"])) & (E > float(g["muR"]))
+    assert np.allclose(car[0][window], T_ref[window], rtol=1e-11)

@@ -210,3 +210,32 @@ def test_telescoped_restatement_matches_plain_recursion(kmax, gmax):
         assert rt_err(T1, T0) < 1e-10 and rt_err(R1, R0) < 1e-10
         if kmax == 1:
             assert np.allclose(G1, G0, rtol=1e-13, atol=1e-15) and np.allclose(W1, W0, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["nnn_n1_M8.npz", "nnn_n2_M6.npz", "nnn_n2_M7.npz", "nnn_n3_M5.npz"])
+def test_next_nearest_neighbour_goldens(name):
+    """nonzero tnnn (wfm/__init__.py:209-213): the dense restatement against the live reference's output"""
+    g = load_golden(name)
+    R, T = _sweep(g["h"], g["tnn"], g["tnnn"], g["Es"], "g_closed", g["sources"])
+    assert rt_err(T, g["T"]) < TOL and rt_err(R, g["R"]) < TOL
+    G = wfm_oracle.Green(g["h"], g["tnn"], g["tnnn"], 1.0, g["Es"][1], "g_closed")
+    assert np.allclose(G, g["G"][1], rtol=1e-12, atol=1e-14)
+
+
+def test_landauer_oracle_against_reference_fcdmft_golden():
+    """oracle/landauer_oracle.py against the unmodified fcdmft.landauer (fcdmft/__init__.py:224-292); the same system as a
+    wfm chain gives the same Tr[G_adv Lambda_R G_ret Lambda_L] as Caroli trace (current conservation)."""
+    from oracle import landauer_oracle as lo
+    g = load_golden("landauer_fcdmft.npz")
+    eye = np.eye(2)
+    LL = (0 * eye[None], float(g["V"]) * eye[None], g["cL"][None], float(g["muL"]))
+    RL = (0 * eye[None], float(g["V"]) * eye[None], g["cR"][None], float(g["muR"]))
+    for tag, kBT in (("kT0", 0.0), ("kT005", 0.05)):
+        jE = lo.landauer(g["energies"], kBT, g["MBGF"], LL, RL)
+        assert np.max(np.abs(jE - g["jE_" + tag])) < 1e-15
+        assert abs(lo.current(g["energies"], jE) - float(g["I_" + tag])) < 1e-15
+    Es = g["energies"].astype(complex)
+    SL, SR = rgf_oracle.closed_selfenergies(g["h"], g["tnn"], Es)
+    _, GN0 = rgf_oracle.rgf_blocks(g["h"], g["tnn"], Es, SL, SR)
+    T = np.real(lo.transmission(g["energies"], g["MBGF"], LL, RL))
+    assert np.allclose(rgf_oracle.caroli_trace(GN0, SL, SR), T, rtol=1e-12)

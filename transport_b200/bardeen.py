@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib, leads
 from ._lib import as_c128, as_f64, check, ptr
+from .superblocks import pair_into_superblocks, sweep_with_tnnn  # noqa: F401  (re-exported)
 from .sweep import transmission_sweep
 
 
@@ -66,55 +67,6 @@ def blocks_from_HC(tL, tR, VL, VR, HC):
     return h, tnn, tnnn
 
 
-def pair_into_superblocks(h, tnn, tnnn):
-    """Block-pentadiagonal (h, tnn, tnnn) with M sites -> block-tridiagonal (H, T) with ceil(M/2)
-    super-sites of size 2n.  An odd chain is padded with one decoupled dummy site far off in energy."""
-    M, n = h.shape[0], h.shape[-1]
-    if M % 2:
-        h = np.concatenate([h, 1e6 * np.eye(n, dtype=complex)[None]])
-        tnn = np.concatenate([tnn, np.zeros((1, n, n), dtype=complex)])
-        tnnn = np.concatenate([tnnn, np.zeros((1, n, n), dtype=complex)])
-        M += 1
-    K = M // 2
-    H = np.zeros((K, 2 * n, 2 * n), dtype=complex)
-    T = np.zeros((K - 1, 2 * n, 2 * n), dtype=complex)
-    for k in range(K):
-        a, b = 2 * k, 2 * k + 1
-        H[k, :n, :n] = h[a]
-        H[k, n:, n:] = h[b]
-        H[k, :n, n:] = tnn[a]
-        H[k, n:, :n] = np.conj(tnn[a]).T
-        if k + 1 < K:
-            T[k, :n, :n] = tnnn[a]          # site a   -> a+2
-            T[k, n:, :n] = tnn[b]           # site b   -> b+1 = a+2
-            T[k, n:, n:] = tnnn[b]          # site b   -> b+2
-    return H, T, M
-
-
-def sweep_with_tnnn(h, tnn, tnnn, Es, sources):
-    """R, T [nE, n_src, n] for a chain with next-nearest-neighbour blocks (closed-form leads on the
-    original first/last sites), via super-blocks and table self-energies."""
-    h, tnn, tnnn = as_c128(h), as_c128(tnn), as_c128(tnnn)
-    M0, n = h.shape[0], h.shape[-1]
-    Es = as_c128(np.atleast_1d(Es))
-    SL, SR = leads.self_energies_batched(h, tnn, Es, "g_closed")
-    H, T, M = pair_into_superblocks(h, tnn, tnnn)
-    last_in_block = (M0 - 1) % 2                # position of the last real site inside its super-block
-    K = H.shape[0]
-    kR = (M0 - 1) // 2
-    if kR != K - 1:
-        raise AssertionError("internal: right lead must sit in the last super-block")
-    sigL = np.zeros((len(Es), 2 * n, 2 * n), dtype=complex)
-    sigR = np.zeros_like(sigL)
-    sigL[:, :n, :n] = SL
-    o = last_in_block * n
-    sigR[:, o:o + n, o:o + n] = SR
-    src = np.zeros((len(sources), 2 * n))
-    src[:, :n] = np.asarray(sources, dtype=float)
-    R2, T2 = transmission_sweep(H, T, Es, "table", sources=src, sigL=sigL, sigR=sigR)
-    return R2[0, :, :, :n], T2[0, :, :, o:o + n]
-
-
 def Ts_wfm_well(tL, tR, VL, VR, HC, Emas, verbose=0) -> np.ndarray:
     """Transmission probabilities at the bound-state energies Emas[alpha, m], final spin resolved:
     Tbmas[beta, m, alpha] (bardeen/__init__.py:634-685), one batched device sweep."""
@@ -122,11 +74,9 @@ def Ts_wfm_well(tL, tR, VL, VR, HC, Emas, verbose=0) -> np.ndarray:
     if np.shape(Emas)[0] != np.shape(HC)[-1]: raise ValueError
     n = np.shape(HC)[-1]
     n_bound = np.shape(Emas)[-1]
-    tLs = tL[0, 0] if np.ndim(tL) == 2 else tL              # the reference passes tL[alpha,alpha]; tL = t*I
-    tRs = tR[0, 0] if np.ndim(tR) == 2 else tR
-    VLs = VL[0, 0] if np.ndim(VL) == 2 else VL
-    VRs = VR[0, 0] if np.ndim(VR) == 2 else VR
-    h, tnn, tnnn = blocks_from_HC(tLs, tRs, VLs, VRs, HC)
+    # the reference multiplies the parameter MATRICES elementwise with the identity (:651-653, :667-668): the
+    # per-channel diagonal survives (drivers pass VL = diag(0, Delta), rbmenez_sup_inel.py:135), off-diagonals drop
+    h, tnn, tnnn = blocks_from_HC(tL, tR, VL, VR, HC)
     Es = np.asarray(Emas, dtype=complex).reshape(-1)        # index alpha*n_bound + m
     sources = np.eye(n)
     if np.any(tnnn):

@@ -666,12 +666,21 @@ bardeen_melem_kernel(const double* __restrict__ EL, const int* __restrict__ nL, 
     }
     const double Em = EL[chL * max_states + m];
     const double* Er = ER + chR * max_states;
+    // kernel_well_prime (no sign fix) un-raggeds the right-well channels by appending copies of a channel's LAST bound
+    // state up to the longest channel (:484-490); the copies take part in the window average, i.e. the last state
+    // carries the weight 1 + (n_bound_right - nR[beta]).  kernel_well (sign fix) has no such padding.
+    int pad = 0;
+    if (!sign_fix) {
+        int longest = 0;
+        for (int b = 0; b < n; ++b) longest = max(longest, min(nR[(size_t)p * n + b], max_states));
+        pad = longest - nr;
+    }
     // window (uniform over the CTA)
     int cnt = 0, nearest = -1;
     double dmin = DBL_MAX;
     for (int k = 0; k < nr; ++k) {
         const double dE = fabs(Em - Er[k]);
-        if (dE < interval) ++cnt;
+        if (dE < interval) cnt += (k == nr - 1) ? 1 + pad : 1;
         if (dE < dmin) {
             dmin = dE;
             nearest = k;
@@ -713,7 +722,7 @@ bardeen_melem_kernel(const double* __restrict__ EL, const int* __restrict__ nL, 
         double el = s_red[0] + s_red[1] + s_red[2] + s_red[3];
         __syncthreads();
         if (sign_fix && el < 0.0) el = -el;
-        sum += el;
+        sum += (!use_nearest && k == nr - 1) ? el * (double)(1 + pad) : el;
     }
     if (threadIdx.x == 0) *out = sum / (double)(use_nearest ? 1 : cnt);
 }
@@ -747,9 +756,10 @@ __global__ void bardeen_current_kernel(const double* __restrict__ E, const doubl
 // Tbmas[alpha][m][beta] = NL/(k tL[alpha]) NR/tR[beta] dos M2[alpha][m][beta]   (bardeen:577-632)
 // k = Re arccos((E - VL[alpha]) / (-2 tL[alpha])), dos = Re 1/sqrt(1 - ((E - VR[beta]) / (2 tR[beta]))^2) with
 // numpy's complex branches (the reference's Emas is complex): outside the band k = 0 or pi and dos = 0.
-// flag[0] counts wavenumbers outside the band (:611 raises on any, for tL > 0), flag[1] densities of states above
-// the band top (x > 1, :624 raises), flag[2 + alpha*n + beta] the in-band ones: below the band bottom the
-// reference's check (max of the imaginary parts, which are negative there) fires only if NO m is in band.
+// flag[0] counts wavenumbers outside the band (:611 raises on any, for tL > 0), flag[2 + alpha*n + beta] the in-band
+// densities of states: outside the band (x < -1 AND x > 1: numpy's 1/sqrt(1 - x^2) of a complex x with zero imaginary
+// part has a NEGATIVE imaginary part on both sides) the reference's check (:624, max of the imaginary parts) fires
+// only if NO m of that (alpha, beta) is in band; flag[1] is kept in the layout and stays 0.
 __global__ void bardeen_ts_kernel(const double* __restrict__ E, const double* __restrict__ M2, int n, int nb,
                                   const double* __restrict__ tL, const double* __restrict__ VL,
                                   const double* __restrict__ tR, const double* __restrict__ VR, double NL, double NR,
@@ -772,8 +782,6 @@ __global__ void bardeen_ts_kernel(const double* __restrict__ E, const double* __
     if (arg >= 0.0) {
         dos = 1.0 / sqrt(arg);
         atomicAdd(flag + 2 + alpha * n + beta, 1);
-    } else if (x > 1.0) {
-        atomicAdd(flag + 1, 1);
     }
     T[idx] = NL / (ka * tL[alpha]) * NR / tR[beta] * dos * M2[idx];
 }

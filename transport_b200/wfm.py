@@ -7,7 +7,7 @@ raise.  Host code here only validates arguments and shapes the way the reference
 """
 import numpy as np
 
-from . import _lib, leads
+from . import _lib, leads, superblocks
 from .sweep import transmission_sweep
 
 
@@ -37,9 +37,7 @@ def kernel(h, tnn, tnnn, tl, E, converger, Ajsigma,
     assert len(Ajsigma) == np.shape(h[0])[0]               # :74
     if not len(tnn) + 1 == len(h): raise ValueError        # Hmat's checks, :179-180
     if not len(tnnn) + 2 == len(h): raise ValueError
-    if np.any(tnnn):
-        raise NotImplementedError("next-nearest-neighbour blocks: use transport_b200.bardeen.Ts_wfm_well "
-                                  "(pairs sites into super-blocks)")
+    has_nnn = bool(np.any(tnnn))        # block-pentadiagonal H (:209-213): sites are paired into super-blocks
     n = np.shape(h[0])[0]
     Es = np.array([E], dtype=complex)
 
@@ -54,13 +52,20 @@ def kernel(h, tnn, tnnn, tl, E, converger, Ajsigma,
     if is_psi_jsigma:                                      # :98-99
         from . import green
         vL = -2 * np.imag(np.diagonal(SigL))
-        col = green.green_column0(h, tnn, Es, SigL[None], SigR[None])[0]      # [M, n, n]
+        if has_nnn:
+            col = superblocks.green_column0_with_tnnn(h, tnn, tnnn, Es, SigL[None], SigR[None])[0]
+        else:
+            col = green.green_column0(h, tnn, Es, SigL[None], SigR[None])[0]      # [M, n, n]
         return 1j * np.dot(col, Ajsigma * vL)
     if is_Rhat:                                            # :103-105: formula is commented out upstream
         raise NameError("name 'Rhat_matrix' is not defined")
 
     src = np.asarray(Ajsigma, dtype=float)[None, :]
-    if _is_str(converger, "g_closed"):
+    if has_nnn:
+        tables = (SigL[None], SigR[None]) if need_sigma else None
+        R, T = superblocks.sweep_with_tnnn(h, tnn, tnnn, Es, src, converger, tables)
+        R, T = R[None], T[None]
+    elif _is_str(converger, "g_closed"):
         R, T = transmission_sweep(h, tnn, Es, "g_closed", sources=src)
     else:
         R, T = transmission_sweep(h, tnn, Es, "table", sources=src, sigL=SigL[None], sigR=SigR[None])
@@ -76,10 +81,10 @@ def Green(h, tnn, tnnn, tl, E, converger, verbose=0) -> np.ndarray:
     from . import green
     if not len(tnn) + 1 == len(h): raise ValueError
     if not len(tnnn) + 2 == len(h): raise ValueError
-    if np.any(tnnn):
-        raise NotImplementedError("Green with next-nearest-neighbour blocks")
     SigL, SigR = SelfEnergies(h, tnn, tnnn, E, converger, verbose=verbose)
     Es = np.array([E], dtype=complex)
+    if np.any(tnnn):
+        return superblocks.green_full_with_tnnn(h, tnn, tnnn, Es, SigL[None], SigR[None])[0]
     return green.green_full(h, tnn, Es, SigL[None], SigR[None])[0]
 
 
@@ -167,10 +172,12 @@ def Rhat_matrix(h, tnn, tnnn, tl, E, converger="g_closed") -> np.ndarray:
     from . import green
     if not len(tnn) + 1 == len(h): raise ValueError
     if not len(tnnn) + 2 == len(h): raise ValueError
-    if np.any(tnnn): raise NotImplementedError("Rhat with next-nearest-neighbour blocks")
     n = np.shape(h[0])[0]
     SigL, SigR = SelfEnergies(h, tnn, tnnn, E, converger)
-    G00 = green.green_column0(h, tnn, np.array([E], dtype=complex), SigL[None], SigR[None])[0, 0]
+    if np.any(tnnn):
+        G00 = superblocks.green_column0_with_tnnn(h, tnn, tnnn, np.array([E], dtype=complex), SigL[None], SigR[None])[0, 0]
+    else:
+        G00 = green.green_column0(h, tnn, np.array([E], dtype=complex), SigL[None], SigR[None])[0, 0]
     ka_L = np.arccos((E - np.diagonal(h[0])) / (-2 * tl))
     return 2 * tl * complex(0, 1) * G00 * np.sin(ka_L)[None, :] - np.eye(n)
 
