@@ -1,32 +1,93 @@
-"""Per-source-line instruction and stall-sample totals of an .ncu-rep (needs -lineinfo and --import-source on).
-usage: python scripts/ncu_lines.py rep.ncu-rep [top]"""
-import csv, io, subprocess, sys, collections
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
-cur_file = None; hdr = None; tot_i = tot_s = 0
-agg = collections.OrderedDict()
-for r in rows:
-    if not r: continue
-    if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name": continue
-    if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; continue
-    if hdr is None or len(r) < 8: continue
-    if r[0] == "":   # sass row
+#!/usr/bin/env python
+"""Per-source-line attribution of an .ncu-rep (built with -lineinfo, captured with --import-source on):
+joins the SASS page (executed warp-instructions and stall samples per instruction address) with the line table of the
+cubin (nvdisasm -g) and prints, per source line, warp-instructions, FP64-pipe issue slots (DFMA/DMUL/DADD/DSETP = 1,
+DMMA.8x8x4 = 8: the FP64 tensor path shares the pipe and moves 8 FMA per lane) and stall samples.
+
+usage: python scripts/ncu_lines.py REPORT.ncu-rep LIB.so KERNEL_SUBSTRING [launch_index] [top_n]
+"""
+import collections
+import csv
+import glob
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, lib, pattern = sys.argv[1], sys.argv[2], sys.argv[3]
+launch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+top = int(sys.argv[5]) if len(sys.argv) > 5 else 45
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# the CSV holds one table per profiled launch, each introduced by a "Kernel Name" style preamble line
+tables, cur, last = [], None, -1
+for row in csv.reader(io.StringIO(raw)):
+    if row and row[0] == "Address":
+        hdr = row
         continue
-    key = (cur_file, int(r[0]), r[1].strip()[:90])
-    try:
-        ni = int(r[7]); ns = int(r[6])
-    except ValueError:
-        continue
-    a = agg.setdefault(key, [0, 0]); a[0] += ni; a[1] += ns
-    tot_i += ni; tot_s += ns
-print("total warp-instr %d samples %d" % (tot_i, tot_s))
-for (f, ln, src), (ni, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print("%-14s %4d  instr %5.1f%%  samples %5.1f%%  %s" % (f, ln, 100.0 * ni / tot_i, 100.0 * ns / max(tot_s, 1), src))
-if len(sys.argv) > 3:   # region totals for one file: name:lo-hi,...
-    for spec in sys.argv[3].split(","):
-        f, rng = spec.split(":"); lo, hi = map(int, rng.split("-"))
-        ni = sum(v[0] for k, v in agg.items() if k[0] == f and lo <= k[1] <= hi)
-        ns = sum(v[1] for k, v in agg.items() if k[0] == f and lo <= k[1] <= hi)
-        print("%-28s instr %5.1f%% (%d)  samples %5.1f%%" % (spec, 100.0 * ni / tot_i, ni, 100.0 * ns / max(tot_s, 1)))
+    if row and re.match(r"^0x[0-9a-f]+$|^[0-9a-f]+$", row[0]):
+        addr = int(row[0], 16)
+        if cur is None or addr <= last:          # addresses restart: next profiled launch
+            cur = {"hdr": hdr, "rows": []}
+            tables.append(cur)
+        last = addr
+        cur["rows"].append(row)
+tab = tables[launch]
+ix = {h: i for i, h in enumerate(tab["hdr"])}
+
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
+line_of = {}
+for cub in glob.glob(os.path.join(tmp, "*.cubin")):
+    txt = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
+    inside, where = False, None
+    for ln in txt.splitlines():
+        if ln.startswith(".text."):
+            inside = pattern in ln
+            where = None
+            continue
+        if not inside:
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            where = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+        if m and where:
+            line_of.setdefault(int(m.group(1), 16), where)
+    if line_of:
+        break
+
+per = collections.defaultdict(lambda: [0, 0, 0])
+tot = [0, 0, 0]
+base = None
+for r in tab["rows"]:
+    addr = int(r[ix["Address"]], 16)
+    if base is None:
+        base = addr
+    sass = r[ix["Source"]]
+    n = int(float(r[ix["Instructions Executed"]] or 0))
+    s = int(float(r[ix["# Samples"]] or 0))
+    op = sass.split()[1] if sass.startswith("@") else sass.split()[0]
+    slots = n * (8 if op.startswith("DMMA") else 1 if re.match(r"D(FMA|MUL|ADD|SETP|MNMX)", op) else 0)
+    key = line_of.get(addr - base, ("?", 0))
+    for i, v in enumerate((n, slots, s)):
+        per[key][i] += v
+        tot[i] += v
+src_cache = {}
+
+
+def text(key):
+    f, l = key
+    if f not in src_cache:
+        cand = glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "transport_b200", "csrc", f))
+        src_cache[f] = open(cand[0]).read().splitlines() if cand else []
+    return src_cache[f][l - 1].strip()[:90] if 0 < l <= len(src_cache[f]) else ""
+
+
+print("total warp-instr %d  fp64-pipe slots %d  samples %d" % tuple(tot))
+for key, (n, sl, s) in sorted(per.items(), key=lambda kv: -kv[1][1] - kv[1][0] * 0.2)[:top]:
+    print("%-14s %5d  instr %5.1f%%  fp64slots %5.1f%%  samples %5.1f%%  %s"
+          % (key[0], key[1], 100.0 * n / tot[0], 100.0 * sl / max(tot[1], 1), 100.0 * s / max(tot[2], 1), text(key)))

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "tx_debug_invert_staged": (c_int, [_P, _P, c_int, c_int]),
     "tx_debug_last_invert_ms": (c_double, []),
     "tx_debug_gemm_ms": (c_int, [c_int, c_int, c_int, _P]),
+    "tx_debug_gemm_tma_ms": (c_int, [c_int, c_int, c_int, _P]),
     "tx_measure_fp64_peak": (c_int, [_P, _P]),
     "tx_measure_dmma_peak": (c_int, [_P, _P]),
     "tx_microbench": (c_int, [c_int, _P]),

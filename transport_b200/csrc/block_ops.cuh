@@ -15,13 +15,40 @@ __device__ __forceinline__ cd ld_op(const cd* A, int n, int r, int c, int op) {
     return mk(v.x, -v.y);
 }
 
+// ---- TMA staging of a product's B operand (n = 64, blocks in the L2-resident global workspace) ------------------
+// ncu on the direct-from-L2 product showed operand fetch as half of the stall samples: every B fragment is re-read by
+// the eight tile rows and every A fragment by both strips, 640 KB of L2 traffic per 64 x 64 product and CTA, 7 TB/s
+// over the chip.  Here the whole B block (64 KB) is brought into shared memory ONCE per product by the TMA engine
+// (cp.async.bulk global -> shared, one 1 KB row per copy into rows padded to 66 elements so that the DMMA fragment
+// reads are bank-conflict free, completion on an mbarrier), A fragments come straight from L2 (one tile row per warp,
+// so each is read once): 128 KB per product.  The staging block is the one the blocked inverse uses between products.
+struct TmaStage {
+    cd* buf;                       // shared memory, TMA_LD * 64 elements
+    unsigned long long* bar;       // mbarrier (shared memory), initialised with tma_stage_init
+    unsigned parity;               // phase parity of the next wait (per thread, all threads in step)
+};
+constexpr int TMA_LD = 66;
+__host__ __device__ inline size_t tma_stage_bytes(int n) { return (size_t)n * TMA_LD * sizeof(cd); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_stage_init(TmaStage& ts, cd* buf, unsigned long long* bar) {
+    ts.buf = buf;
+    ts.bar = bar;
+    ts.parity = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 // C = op(A) * op(B)            (C must not alias A or B)
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
-                                     double cscale = 1.0);
+                                     double cscale = 1.0, TmaStage* ts = nullptr);
 
-__device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n) {
+__device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n, TmaStage* ts = nullptr) {
     if ((n & 7) == 0 && n >= 16) {
-        cta_gemm_dmma(C, A, opA, B, opB, n, 1.0, false);
+        cta_gemm_dmma(C, A, opA, B, opB, n, 1.0, false, 1.0, ts);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -113,12 +140,96 @@ __device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const c
     __syncthreads();
 }
 
+// The same product with B staged in shared memory by TMA (see TmaStage); 8 warps, one tile row each, all eight column
+// tiles of the row in registers (32 accumulators), so every A fragment is fetched once.
+template <int N>
+__device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, TmaStage& ts, double sgn,
+                                            bool accumulate, double cscale) {
+    static_assert(N == 64, "one tile row per warp, eight warps");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // B (global, possibly written by this CTA a moment ago) and the staging block (shared, last touched by ordinary
+    // loads / stores) are about to be accessed through the async proxy: order the generic-proxy accesses first
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(ts.bar)), "r"((unsigned)(N * N * sizeof(cd)))
+                         : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int r = lane; r < N; r += 32)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(ts.buf + r * TMA_LD)),
+                         "l"(B + r * N), "r"((unsigned)(N * sizeof(cd))), "r"(smem_u32(ts.bar))
+                         : "memory");
+    }
+    double re[8][2], im[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
+    const int tr = warp << 3;
+    const cd* pa = A + (tr + g) * N + t;                         // A[tr+g][k+t], k += 4
+    cd a = pa[0];
+    {   // wait for the staged block (bounded: a lost copy must not hang the GPU)
+        unsigned done = 0;
+        for (int spin = 0; !done; ++spin) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"(smem_u32(ts.bar)), "r"(ts.parity)
+                         : "memory");
+            if (spin > (1 << 24)) __trap();
+        }
+        ts.parity ^= 1u;
+    }
+    const cd* pb = ts.buf + t * TMA_LD + g;                      // B[k+t][u*8+g]
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+        const cd ac = a;
+        if (k + 4 < N) a = pa[k + 4];
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            cd bc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bc[u] = pb[k * TMA_LD + (h + u) * 8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dmma844(re[h + u], ac.x, bc[u].x);
+                dmma844(im[h + u], ac.x, bc[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dmma844(re[h + u], -ac.y, bc[u].y);
+                dmma844(im[h + u], ac.y, bc[u].x);
+            }
+        }
+    }
+    cd* pc = C + (tr + g) * N + 2 * t;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+            if (accumulate) {
+                const cd c0 = pc[u * 8 + i];
+                v.x = fma(cscale, c0.x, v.x);
+                v.y = fma(cscale, c0.y, v.y);
+            }
+            pc[u * 8 + i] = v;
+        }
+    }
+    __syncthreads();
+}
+
 // C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
 // A warp works on a strip of up to four 8x8 output tiles of one tile row: the A fragment of a k-step is loaded
 // once and reused for the four column tiles (16 DMMA per 5 fragment loads), and the loads of the next k-step are
 // issued before the DMMAs of the current one (operands usually sit in L2/L1, not in shared memory).
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
-                                     double cscale) {
+                                     double cscale, TmaStage* ts) {
+    if (ts != nullptr && n == 64 && opA == OP_N && opB == OP_N && blockDim.x == 256) {
+        cta_gemm_dmma_nn_tma<64>(C, A, B, *ts, sgn, accumulate, cscale);
+        return;
+    }
     if (n == 64 && opA == OP_N && opB == OP_N) {
         cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate, cscale);
         return;
@@ -182,9 +293,10 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
 }
 
 // C = cscale * C + sgn * op(A) * op(B)
-__device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, double cscale = 1.0) {
+__device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, double cscale = 1.0,
+                                    TmaStage* ts = nullptr) {
     if ((n & 7) == 0 && n >= 16) {
-        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true, cscale);
+        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true, cscale, ts);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {

@@ -27,13 +27,22 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
     __shared__ double s_vL[64], s_vR[64];
     __shared__ double s_red[GEN_THREADS / 32];
     __shared__ double s_red4[4][GEN_THREADS / 32];
+    __shared__ unsigned long long s_tma_bar;
     const int n = p.n, M = p.M, nn = n * n;
-    const long long pt = blockIdx.x;
+    // persistent grid: the global workspace (blocks too large for shared memory) is indexed by CTA, not by point, so a
+    // few hundred of them stay L2-resident however long the sweep is
+    cd* base = p.work ? p.work + (long long)blockIdx.x * GEN_MATS * nn : reinterpret_cast<cd*>(gen_smem);
+    cd* stage = p.work ? reinterpret_cast<cd*>(gen_smem) : nullptr;   // inverse staging when blocks are global
+    TmaStage tma_stage;
+    TmaStage* ts = nullptr;   // n = 64: the products stage their B operand through the same block by TMA (block_ops.cuh)
+    if (stage != nullptr && n == 64 && p.use_tma) {
+        tma_stage_init(tma_stage, stage, &s_tma_bar);
+        ts = &tma_stage;
+    }
+    for (long long pt = blockIdx.x; pt < p.n_pts; pt += gridDim.x) {
     const int ham = (int)(pt / p.nE);
     const int e = (int)(pt - (long long)ham * p.nE);
     const cd E = p.E[e];
-    cd* base = p.work ? p.work + pt * (long long)GEN_MATS * nn : reinterpret_cast<cd*>(gen_smem);
-    cd* stage = p.work ? reinterpret_cast<cd*>(gen_smem) : nullptr;   // inverse staging when blocks are global
     cd* G = base;            // current g_j, finally G_00
     cd* W = base + nn;       // running product, finally G_{M-1,0}
     cd* A = base + 2 * nn;
@@ -135,9 +144,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                         prev[idx] = mk(r == c ? -kap : 0.0, 0.0);
                     }
                     __syncthreads();
-                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0);
+                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, 1.0, ts);
                 } else {
-                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap);
+                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap, ts);
                 }
                 cd* sw = prev;
                 prev = cur;
@@ -149,11 +158,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
             // close at site a = j:  cur = D_a, prev = D_{a+1} (identity if k == 1)
             cta_inverse_staged(cur, stage, n, s_colk, s_ipiv, p.singular);   // X
             if (prev_is_identity) cta_copy(G, cur, nn);
-            else cta_gemm(G, prev, OP_N, cur, OP_N, n);                      // g_a = D_{a+1} X
+            else cta_gemm(G, prev, OP_N, cur, OP_N, n, ts);                  // g_a = D_{a+1} X
             if (b == M - 1) {
                 for_each4(W, [&](int idx) { return cur[idx]; }, [&](int, cd v) { return v * tau; });
             } else {
-                cta_gemm(tmp, W, OP_N, cur, OP_N, n);                        // W X
+                cta_gemm(tmp, W, OP_N, cur, OP_N, n, ts);                    // W X
                 for_each4(W, [&](int idx) { return tmp[idx]; }, [&](int, cd v) { return v * tau; });
             }
             --j;
@@ -303,13 +312,41 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
             p.caroli[pt] = tot;
         }
     }
+    __syncthreads();   // the static shared arrays and the workspace are reused by the next point
+    }   // persistent loop over points
 }
 
 // Host-side launcher used by capi.cu.  `work` must hold n_pts*GEN_MATS*n*n elements when the blocks
 // do not fit in shared memory (use rgf_generic_workspace_elems to size it).
+// Number of CTAs the generic sweep keeps resident (its grid; the workspace is per CTA).
+static int generic_resident_ctas(size_t smem) {
+    static int cached[16] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 296;
+    if (!cached[dev & 15]) {
+        int per_sm = 0, sms = 0;
+        if (smem > 16 * 1024) cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgf_sweep_generic, GEN_THREADS, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev & 15] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    return cached[dev & 15];
+}
+
+static size_t generic_stage_bytes(int n) {
+    size_t b = inverse_stage_bytes(n);
+    if (n == 64 && tma_stage_bytes(n) > b) b = tma_stage_bytes(n);
+    return b;
+}
+
+// Host-side launcher used by capi.cu.  `work` must hold rgf_generic_workspace_elems(n, n_pts) elements when the blocks do
+// not fit in shared memory: GEN_MATS blocks per RESIDENT CTA (bounded: a persistent grid strides over the points), not per point.
 size_t rgf_generic_workspace_elems(int n, long long n_pts) {
     const size_t bytes = (size_t)GEN_MATS * n * n * sizeof(cd);
-    return bytes > 200 * 1024 ? (size_t)n_pts * GEN_MATS * n * n : 0;
+    if (bytes <= 200 * 1024) return 0;
+    long long ctas = generic_resident_ctas(generic_stage_bytes(n));
+    if (n_pts < ctas) ctas = n_pts;
+    return (size_t)ctas * GEN_MATS * n * n;
 }
 
 int launch_rgf_generic(GenericParams p, cudaStream_t st) {
@@ -317,14 +354,21 @@ int launch_rgf_generic(GenericParams p, cudaStream_t st) {
     size_t smem = bytes;
     if (bytes > 200 * 1024) {
         if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
-        smem = inverse_stage_bytes(p.n);         // staging block for the inverse
+        smem = generic_stage_bytes(p.n);         // staging block for the inverse and the TMA-staged product operand
     } else {
         p.work = nullptr;
     }
+    p.use_tma = tma_mode();
     if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
         TX_CUDA(cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (p.n_pts > 0x7fffffffLL) return fail(TX_ERR_ARG, "too many points for one launch");
-    rgf_sweep_generic<<<(unsigned)p.n_pts, GEN_THREADS, smem, st>>>(p);
+    long long grid = p.n_pts;
+    if (p.work) {
+        const long long ctas = generic_resident_ctas(smem);
+        if (grid > ctas) grid = ctas;
+    } else if (grid > 0x7fffffffLL) {
+        return fail(TX_ERR_ARG, "too many points for one launch");
+    }
+    rgf_sweep_generic<<<(unsigned)grid, GEN_THREADS, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;

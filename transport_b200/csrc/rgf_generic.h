@@ -31,6 +31,7 @@ struct GenericParams {
     long long n_pts;
     int n, M, nE, n_src, hop_scalar;
     int kmax, gexp;          // telescoped sweep (scalar hopping): longest chunk, log2 of the growth bound
+    int use_tma;             // n = 64: TMA-staged product operand (set by the launcher from tx_set_option(5, .))
 };
 
 size_t rgf_generic_workspace_elems(int n, long long n_pts);

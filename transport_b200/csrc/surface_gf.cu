@@ -41,9 +41,11 @@ struct GfParams {
     int n, nE, side, mode;
     double imE, conv_tol;
     int conv_rep, min_iter, max_iter, ith;
+    int use_tma;        // n = 64: stage the products' B operand in shared memory by TMA (tx_set_option(5, .))
 };
 
 constexpr int GF_THREADS = 256;
+int g_use_tma = 1;   // tx_set_option(5, value)
 constexpr int GF_MAX_MATS = 9;
 
 // wfm.g_RiceMele for spin channel s (wfm/__init__.py:379-403)
@@ -245,6 +247,14 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
     // resident CTAs need one, and a few hundred of them stay L2-resident
     cd* base = (p.scratch != nullptr) ? p.scratch + (long long)blockIdx.x * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
     cd* stage = (p.scratch != nullptr) ? reinterpret_cast<cd*>(gf_smem) : nullptr;   // inverse staging when blocks are global
+    // n = 64 with the blocks in the global workspace: the products stage their B operand through the same block by TMA
+    __shared__ unsigned long long s_tma_bar;
+    TmaStage tma_stage;
+    TmaStage* ts = nullptr;
+    if (stage != nullptr && n == 64 && p.use_tma) {
+        tma_stage_init(tma_stage, stage, &s_tma_bar);
+        ts = &tma_stage;
+    }
     cd* m0 = base;               // g / result
     cd* m1 = base + nn;
     cd* m2 = base + 2 * nn;
@@ -337,9 +347,9 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
         for (it = 1; it <= p.max_iter; ++it) {
             cta_z_minus(G, z, eps, n);
             cta_inverse_staged(G, stage, n, s_colk, s_ipiv, p.singular);
-            cta_gemm(T1, G, OP_N, beta, OP_N, n);               // G beta
-            cta_gemm(T2, G, OP_N, alpha, OP_N, n);              // G alpha
-            cta_gemm(tmp, alpha, OP_N, T1, OP_N, n);            // alpha G beta
+            cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);           // G beta
+            cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);          // G alpha
+            cta_gemm(tmp, alpha, OP_N, T1, OP_N, n, ts);        // alpha G beta
             {
                 const int bd = blockDim.x;
                 int idx = threadIdx.x;
@@ -363,9 +373,9 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
                 }
             }
             __syncthreads();
-            cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0);    // + beta G alpha
-            cta_gemm(tmp, alpha, OP_N, T2, OP_N, n);            // alpha G alpha
-            cta_gemm(G, beta, OP_N, T1, OP_N, n);               // beta G beta (G is free now)
+            cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0, 1.0, ts);    // + beta G alpha
+            cta_gemm(tmp, alpha, OP_N, T2, OP_N, n, ts);        // alpha G alpha
+            cta_gemm(G, beta, OP_N, T1, OP_N, n, ts);           // beta G beta (G is free now)
             {                                                    // new alpha = tmp, new beta = G: swap roles, no copies
                 cd* sw = alpha;
                 alpha = tmp;
@@ -414,9 +424,17 @@ __global__ void __launch_bounds__(GF_THREADS) invert_staged_kernel(const cd* __r
 
 // Measurement hook: `reps` products C = A B per CTA on blocks in global memory (what the large-block paths do).
 __global__ void __launch_bounds__(GF_THREADS, 2) gemm_bench_kernel(const cd* __restrict__ A, const cd* __restrict__ B, cd* C, int n,
-                                                                    int reps) {
+                                                                    int reps, int use_tma) {
+    extern __shared__ double2 gf_smem[];
+    __shared__ unsigned long long s_bar;
     const long long off = (long long)blockIdx.x * n * n;
-    for (int r = 0; r < reps; ++r) cta_gemm(C + off, A + off, OP_N, B + off, OP_N, n);
+    TmaStage tma_stage;
+    TmaStage* ts = nullptr;
+    if (use_tma && n == 64) {
+        tma_stage_init(tma_stage, reinterpret_cast<cd*>(gf_smem), &s_bar);
+        ts = &tma_stage;
+    }
+    for (int r = 0; r < reps; ++r) cta_gemm(C + off, A + off, OP_N, B + off, OP_N, n, ts);
 }
 
 // One CTA per energy, persistent over the energy axis (grid = resident CTAs).
@@ -477,6 +495,7 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     p.scratch_per = 0;
     if (bytes > 200 * 1024) {
         smem = inverse_stage_bytes(n);          // staging block for the inverse
+        if (n == 64 && tma_stage_bytes(n) > smem) smem = tma_stage_bytes(n);   // ... and for the TMA-staged product operand
         p.scratch_per = (long long)mats * n * n;
     }
     if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
@@ -517,6 +536,15 @@ int check_gf_args(const void* h00, const void* h01, int n, const void* E, int nE
 
 }  // namespace
 
+namespace tx {
+int set_tma_mode(int on) {
+    g_use_tma = on != 0;
+    return TX_OK;
+}
+int tma_mode() { return g_use_tma; }
+}  // namespace tx
+
+
 extern "C" {
 
 int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, int mode,
@@ -547,6 +575,7 @@ int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cp
     p.min_iter = min_iter;
     p.max_iter = max_iter;
     p.ith = -1;
+    p.use_tma = g_use_tma;
     cd* owned = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     rc = launch_gf(p, st, &owned);
@@ -610,6 +639,7 @@ static int gf_host(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx*
     p.min_iter = min_iter;
     p.max_iter = max_iter;
     p.ith = ith;
+    p.use_tma = g_use_tma;
     cd* owned = nullptr;
     rc = launch_gf(p, nullptr, &owned);
     cudaError_t e = cudaDeviceSynchronize();
@@ -688,8 +718,14 @@ int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
     return TX_OK;
 }
 
-int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out) {
+static int gemm_bench(int n, int count, int reps, int use_tma, double* ms_out);
+int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out) { return gemm_bench(n, count, reps, 0, ms_out); }
+int tx_debug_gemm_tma_ms(int n, int count, int reps, double* ms_out) { return gemm_bench(n, count, reps, 1, ms_out); }
+static int gemm_bench(int n, int count, int reps, int use_tma, double* ms_out) {
     if (n < 8 || n > 64 || count < 1 || reps < 1 || !ms_out) return fail(TX_ERR_ARG, "bad arguments");
+    if (use_tma && n != 64) return fail(TX_ERR_ARG, "the TMA-staged product is the n = 64 path");
+    const size_t smem = use_tma ? tma_stage_bytes(n) : 0;
+    if (smem) TX_CUDA(cudaFuncSetAttribute(gemm_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t bytes = (size_t)count * n * n * sizeof(cd);
     cd *dA = nullptr, *dB = nullptr, *dC = nullptr;
     TX_CUDA(cudaMalloc(&dA, bytes));
@@ -700,9 +736,9 @@ int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out) {
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
-    gemm_bench_kernel<<<count, GF_THREADS>>>(dA, dB, dC, n, 1);
+    gemm_bench_kernel<<<count, GF_THREADS, smem>>>(dA, dB, dC, n, 1, use_tma);
     cudaEventRecord(ev0);
-    gemm_bench_kernel<<<count, GF_THREADS>>>(dA, dB, dC, n, reps);
+    gemm_bench_kernel<<<count, GF_THREADS, smem>>>(dA, dB, dC, n, reps, use_tma);
     cudaEventRecord(ev1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms = 0.f;

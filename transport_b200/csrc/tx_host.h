@@ -9,6 +9,9 @@ int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 // bardeen.cu: 0 auto, 1 warp per state, 2 lane per state (tx_set_option(3, mode)).
 int set_eig_mode(int mode);
+// surface_gf.cu: TMA staging of the n = 64 products' B operand (tx_set_option(5, on)); read by rgf_generic.cu too.
+int set_tma_mode(int on);
+int tma_mode();
 }  // namespace tx
 
 #define TX_CUDA(call)                                                                              \
