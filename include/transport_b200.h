@@ -332,6 +332,9 @@ int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* 
                             double interval, int sign_fix, int row_cut, int max_states, int* max_needed,
                             double* EL, int* nL, double* ER, int* nR_states, int* nR_below, double* Mavg,
                             const double* Vb, int nVb, double muR, double kBT, double* I);
+/* Small real matrix product for the basis changes of kernel_well (:156-166): C[M][N] = opA(A) diag(w) opB(B), contraction
+ * length K; transA: A is stored [K][M] (else [M][K]); transB: B is stored [N][K] (else [K][N]); w [K] or NULL.  Host pointers. */
+int tx_real_gemm(const double* A, const double* B, const double* w, double* C, int M, int N, int K, int transA, int transB);
 /* bardeen.current (:537-575, nFD :1014-1020): I[p][alpha][beta][i] = 2 pi sum_m stat(E[p][alpha][m], Vb[i])
  * M2[p][alpha][m][beta], stat = fL (1 - fR) - fR (1 - fL), muL = muR + Vb[i].  E [P][n][nb], M2 [P][n][nb][n]. */
 int tx_bardeen_current(const double* E, const double* M2, int P, int n, int nb, const double* Vb, int nVb, double muR,

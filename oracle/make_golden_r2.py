@@ -149,7 +149,45 @@ def landauer_fcdmft(ref):
              muR=-0.25, h=h, tnn=tnn, **out)
 
 
-MAKERS = {"cicc_spin32": cicc_spin32, "nnn_chains": nnn_chains, "well_channel_potentials": well_channel_potentials,
+def kernel_well_n2(ref):
+    """bardeen.kernel_well with n_loc_dof = 2 and a separate observable basis (HCobs != HC), the call of
+    rbmenez_spinless_el.py:45-127 (HC = V_C + (J/2) sigma_x on the central sites, HCobs without the spin mixing).
+    With exactly degenerate observable channels (HCobs = V_C 1) the reference classifies the ROWS of its basis-changed
+    matrix with the right-well list's <S_z> sequence (:213-227) while they index left-well states (:166), and LAPACK's order
+    inside a degenerate pair is arbitrary: its split between the two spin channels is then an artefact of the eigensolver
+    (totals are not).  Fixtures: two cases with a small Zeeman term in HCobs (non-degenerate, ordering unique) and one
+    degenerate case in which the two lists happen to come out in the same order."""
+    import contextlib
+    import io
+    bardeen = ref["bardeen"]
+    n = 2
+    tLR = 1.0 * np.eye(n)
+    Vinfty = 0.5 * tLR
+    VLR = 0.0 * tLR
+    sx, sz = np.array([[0, 1], [1, 0]]), np.diag([1.0, -1.0])
+
+    def chains(J, B):
+        NC = 11
+        HC = np.zeros((NC, NC, n, n), dtype=complex)
+        HCobs = np.zeros_like(HC)
+        for i in range(NC):
+            HCobs[i, i] = 0.4 * tLR + B * sz
+            HC[i, i] = HCobs[i, i] + (J / 2) * sx
+            if i + 1 < NC:
+                HC[i, i + 1] = HC[i + 1, i] = HCobs[i, i + 1] = HCobs[i + 1, i] = -1.0 * tLR
+        return HC, HCobs
+    for tag, J, B, NLR, Ninf in (("zeeman_J5", -0.5, 0.03, 40, 10), ("zeeman_J2", -0.2, -0.05, 36, 8), ("degenerate_J05", -0.05, 0.0, 30, 8)):
+        HC, HCobs = chains(J, B)
+        with contextlib.redirect_stdout(io.StringIO()):
+            E, M = bardeen.kernel_well(1.0 * tLR, tLR, tLR, Vinfty, VLR, Vinfty, VLR, Vinfty, Ninf, NLR, NLR, HC, HCobs, sz,
+                                       E_cutoff=0.1 * np.eye(n), verbose=0)
+        np.savez(os.path.join(OUT, "bardeen_well_n2_%s.npz" % tag), tinfty=1.0 * tLR, tL=tLR, tR=tLR, Vinfty=Vinfty, VL=VLR,
+                 VLprime=Vinfty, VR=VLR, VRprime=Vinfty, Ninfty=Ninf, NL=NLR, NR=NLR, HC=HC, HCobs=HCobs, defines_Sz=sz,
+                 E_cutoff=0.1 * np.eye(n), interval=1e-12, E=E, M=M)
+        print(tag, E.shape, M.shape)
+
+
+MAKERS = {"kernel_well_n2": kernel_well_n2, "cicc_spin32": cicc_spin32, "nnn_chains": nnn_chains, "well_channel_potentials": well_channel_potentials,
           "landauer_fcdmft": landauer_fcdmft}
 
 

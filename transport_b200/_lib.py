@@ -86,6 +86,7 @@ _SIGNATURES = {
     "tx_bardeen_wells_dev": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, c_double, c_int] + [_P] * 8),
     "tx_bardeen_region_sweep": (c_int, [_P] * 8 + [c_int] + [_P] * 6 + [c_int] * 7 + [_P] * 3 + [c_double, c_int, c_int, c_int, _P]
                                 + [_P] * 6 + [_P, c_int, c_double, c_double, _P]),
+    "tx_real_gemm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int]),
     "tx_bardeen_current": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P]),
     "tx_bardeen_current_dev": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_double, c_double, _P, _P]),
     "tx_bardeen_ts": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),

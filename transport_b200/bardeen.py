@@ -360,8 +360,8 @@ def kernel_well(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR
     if n != len(defines_Sz): raise ValueError
     tLa, tRa = _scalar_hopping(tL), _scalar_hopping(tR)
     if n != 1 or np.any(np.asarray(HC) - np.asarray(HCobs)):
-        raise NotImplementedError("kernel_well is covered for n_loc_dof = 1 with HCobs = HC; "
-                                  "spin-resolved wells go through kernel_well_prime")
+        return _kernel_well_general(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR, np.asarray(HC),
+                                    np.asarray(HCobs), np.asarray(defines_Sz), E_cutoff, interval, expval_tol, tLa, tRa)
     bL = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VRprime, Ninfty, NL, NR, HC)
     bR = hsys_site_blocks(tinfty, tL, tR, Vinfty, VLprime, VR, Ninfty, NL, NR, HC)
     bS = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VR, Ninfty, NL, NR, HC)
@@ -380,6 +380,200 @@ def kernel_well(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR
     M = r["Mavg"][0, :, :mu_cut, :].copy()
     M[:, nu_cut:, :] = 0.0
     return Emas, M * M
+
+
+def _common_spin_basis(blocks, n):
+    """A unitary U that diagonalises every n x n block of `blocks` (they must be normal and commute pairwise), or
+    NotImplementedError.  For the reference's drivers (rbmenez_spinless_el.py:97-108: every block is a 1 + b sigma_x) this
+    is the sigma_x eigenbasis; in it the well Hamiltonians decouple into n independent real symmetric tridiagonals."""
+    U = np.eye(n, dtype=complex)
+    for B in blocks:
+        Br = U.conj().T @ B @ U
+        if np.max(np.abs(Br - np.diag(np.diagonal(Br)))) <= 1e-13 * max(1.0, np.max(np.abs(Br))):
+            continue
+        if np.max(np.abs(Br - Br.conj().T)) > 1e-13:
+            raise NotImplementedError("non-Hermitian spin block: the well Hamiltonians do not decouple into chains")
+        # refine U inside the degenerate subspaces of what has been diagonalised so far: only valid if nothing was yet
+        # resolved (first non-scalar block) -- otherwise the blocks do not share an eigenbasis
+        if not np.allclose(U, np.eye(n)):
+            raise NotImplementedError("the spin blocks of the wells do not share one eigenbasis")
+        _, U = np.linalg.eigh(B)
+    for B in blocks:
+        Br = U.conj().T @ B @ U
+        off = Br - np.diag(np.diagonal(Br))
+        if np.max(np.abs(off)) > 1e-12 * max(1.0, np.max(np.abs(Br))) or np.max(np.abs(np.imag(np.diagonal(Br)))) > 1e-12:
+            raise NotImplementedError("the spin blocks of the wells do not share one real eigenbasis")
+    return U
+
+
+def _all_states(d, e):
+    """All eigenpairs of the n_mat tridiagonals d [n_mat,S], e [n_mat,S-1] on the device: (E [n_mat,S], psi [n_mat,S,S])."""
+    n_mat, S = d.shape
+    top = float(np.max(np.abs(d)) + 2 * np.max(np.abs(e)) + 1.0)       # above every Gershgorin disc
+    cut = np.full(n_mat, top)
+    E = np.zeros((n_mat, S))
+    psi = np.zeros((n_mat, S, S))
+    ns = np.zeros(n_mat, dtype=np.int32)
+    nb = np.zeros(n_mat, dtype=np.int32)
+    check(_lib.load().tx_tridiag_eigh_below(ptr(as_f64(d)), ptr(as_f64(e)), S, n_mat, ptr(cut), ptr(cut), S, ptr(E), ptr(psi),
+                                            ptr(ns), ptr(nb)))
+    if np.any(ns != S):
+        raise AssertionError("internal: incomplete spectrum")
+    return E, psi
+
+
+def _real_gemm(A, B, w=None, transA=False, transB=False):
+    """opA(A) diag(w) opB(B) on the device (tx_real_gemm)."""
+    A, B = as_f64(A), as_f64(B)
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == K
+    C = np.empty((M, N))
+    wv = None if w is None else as_f64(w)
+    check(_lib.load().tx_real_gemm(ptr(A), ptr(B), ptr(wv), ptr(C), M, N, K, int(transA), int(transB)))
+    return C
+
+
+def _kernel_well_general(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, NR, HC, HCobs, defines_Sz, E_cutoff,
+                         interval, expval_tol, tLa, tRa):
+    """kernel_well (bardeen/__init__.py:17-257) for n_loc_dof > 1 with a separate observable basis (HCobs != HC), as
+    rbmenez_spinless_el.py:45-127 calls it.
+
+    The reference diagonalises four dense (S n)^2 Hamiltonians.  Here the spin blocks of the wells are required to share
+    one eigenbasis U (every driver: a 1 + b sigma_x per site), in which H_L and H_R decouple into n real symmetric
+    tridiagonals per well, and the observable Hamiltonians (HCobs) must conserve the channel (the reference asserts it,
+    :104, :112), which makes them n tridiagonals in the original basis.  All eigenpairs come from the device's
+    tridiagonal solver; the matrix elements <psi_n|H_sys - H_L|psi_m> (:127-151), the overlaps <psi_m|psi_mu> (:160-163)
+    and the change of basis (:166) are device products; only index bookkeeping (cut-offs :174-182, classification by
+    <S_z> :192-232, the final sums :236-250) runs on the host, restated from the reference including its index quirks.
+    """
+    n = HC.shape[-1]
+    NC = HC.shape[0]
+    S = 2 * Ninfty + NL + NR + NC
+    if np.isnan(interval):
+        raise NotImplementedError("adaptive (NaN) interval with n_loc_dof > 1")
+    spin_blocks = [np.asarray(x, dtype=complex) for x in (Vinfty, VL, VLprime, VR, VRprime)]
+    for i in range(NC):
+        for j in range(NC):
+            if abs(i - j) <= 1:
+                spin_blocks.append(np.asarray(HC[i, j], dtype=complex))
+    for t in (tinfty, tL, tR):
+        _scalar_hopping(np.asarray(t))
+    U = _common_spin_basis(spin_blocks, n)
+    rot = lambda B: np.diag(np.real(np.diagonal(U.conj().T @ np.asarray(B, dtype=complex) @ U)))
+    HCr = np.zeros_like(HC)
+    for i in range(NC):
+        for j in range(NC):
+            if abs(i - j) <= 1:
+                HCr[i, j] = rot(HC[i, j])
+    Vi, VLr, VLpr, VRr, VRpr = rot(Vinfty), rot(VL), rot(VLprime), rot(VR), rot(VRprime)
+    bL = hsys_site_blocks(tinfty, tL, tR, Vi, VLr, VRpr, Ninfty, NL, NR, HCr)
+    bR = hsys_site_blocks(tinfty, tL, tR, Vi, VLpr, VRr, Ninfty, NL, NR, HCr)
+    bS = hsys_site_blocks(tinfty, tL, tR, Vi, VLr, VRr, Ninfty, NL, NR, HCr)
+    dL, eL = _channel_tridiagonals(bL)
+    dR, eR = _channel_tridiagonals(bR)
+    hd = _real_blocks([s_ - l_ for s_, l_ in zip(bS, bL)])
+    # observable basis: channel conserving in the ORIGINAL basis (:104, :112)
+    bLo = hsys_site_blocks(tinfty, tL, tR, Vinfty, VL, VRprime, Ninfty, NL, NR, HCobs)
+    bRo = hsys_site_blocks(tinfty, tL, tR, Vinfty, VLprime, VR, Ninfty, NL, NR, HCobs)
+    assert _is_channel_diagonal(bLo)
+    assert _is_channel_diagonal(bRo)
+    dLo, eLo = _channel_tridiagonals(bLo)
+    dRo, eRo = _channel_tridiagonals(bRo)
+
+    # ---- M_m for EVERY eigenstate of H_L (get_mstates has no cutoff, :755-761), averaged over the right-well states
+    #      inside the window with the sign fix of :141
+    top = float(max(np.max(np.abs(dL)), np.max(np.abs(dR))) + 2 * max(np.max(np.abs(eL)), np.max(np.abs(eR))) + 1.0)
+    cut_all = np.full((1, n), top)
+    r = wells_batched(dL[None], eL[None], dR[None], eR[None], cut_all, cut_all, cut_all, hd[0][None], hd[1][None], hd[2][None],
+                      interval, sign_fix=True, want_states=True)
+    if np.any(r["nL"] != S) or np.any(r["nR_states"] != S):
+        raise AssertionError("internal: incomplete spectrum")
+    EL, ER, psiL = r["EL"][0], r["ER"][0], r["psiL"][0]                # [n,S], [n,S], [n,S,S]
+    # the reference averages over the right-well states of ALL channels inside the window: the device returns the mean
+    # per final channel beta, the counts recombine them (elements between different rotated channels vanish but count)
+    cnt = np.zeros((n, S, n))                                          # [beta, m, alpha]
+    for a in range(n):
+        for b in range(n):
+            cnt[b, :, a] = np.count_nonzero(np.abs(EL[a][:, None] - ER[b][None, :]) < interval, axis=1)
+    tot = cnt.sum(axis=0)                                              # [m, alpha]
+    Mm = np.where(tot > 0, (cnt * r["Mavg"][0]).sum(axis=0) / np.where(tot > 0, tot, 1), 0.0)   # [m, alpha]
+
+    # ---- observable states below the cutoff, merged and sorted by energy like the reference's dense eigh
+    ELo, phiL = _all_states(dLo, eLo)                                  # [n,S], [n,S,S] in the original channels
+    ERo, _ = _all_states(dRo, eRo)
+    cutE = np.max(E_cutoff)
+
+    def merged(Eo):
+        order = np.argsort(Eo.reshape(-1), kind="stable")
+        return [(int(i // S), int(i % S)) for i in order]
+    mus, nus = merged(ELo), merged(ERo)
+    mu_cut = (sum(1 for (a, l) in mus if ELo[a, l] + 2 * np.real(tLa) < cutE) // n) * n
+    nu_cut = (sum(1 for (a, l) in nus if ERo[a, l] + 2 * np.real(tRa) < cutE) // n) * n
+    mus, nus = mus[:mu_cut], nus[:nu_cut]
+    rows = mus[:nu_cut]                 # the ROW index of Mnumus also runs over the left-well observable states (:166)
+    if nu_cut > mu_cut:
+        raise NotImplementedError("more right- than left-well states below the cutoff")
+
+    # ---- Mnumus = C^dag diag(M) C with C[(c,k),(a,l)] = <chi_ck|phi_al> conj(U[a,c])   (:160-166)
+    need = sorted(set(mus))
+    per_chan = {a: [l for (a2, l) in need if a2 == a] for a in range(n)}
+    O = {}
+    for c in range(n):
+        for a in range(n):
+            if per_chan[a]:
+                O[c, a] = _real_gemm(psiL[c], phiL[a][per_chan[a]], transB=True)        # [S, K_a]
+    pos = {(a, l): i for a in range(n) for i, l in enumerate(per_chan[a])}
+    Q = {}
+    for a1 in range(n):
+        for a2 in range(n):
+            if not per_chan[a1] or not per_chan[a2]:
+                continue
+            acc = np.zeros((len(per_chan[a1]), len(per_chan[a2])), dtype=complex)
+            for c in range(n):
+                acc += U[a1, c] * np.conj(U[a2, c]) * _real_gemm(O[c, a1], O[c, a2], w=Mm[:, c], transA=True)
+            Q[a1, a2] = acc
+    Mnumus = np.empty((len(rows), mu_cut))
+    for i, (a1, l1) in enumerate(rows):
+        for jx, (a2, l2) in enumerate(mus):
+            q = Q[a1, a2][pos[a1, l1], pos[a2, l2]]
+            Mnumus[i, jx] = np.real(np.conj(q) * q)
+
+    # ---- classification by <S_z> (:192-232) and the final sums (:236-250), with the reference's index conventions
+    expvals = np.linalg.eigvalsh(np.asarray(defines_Sz, dtype=complex))
+
+    def classify(a):
+        sz = np.real(np.asarray(defines_Sz)[a, a])
+        idx = None
+        for k in range(n):
+            if abs(sz - expvals[k]) < expval_tol:
+                idx = k
+        if idx is None:
+            raise Exception("<Sz> = " + str(sz) + " not an eigenval of Sz")
+        return idx
+    mu_cls = [classify(a) for (a, l) in mus]
+    nu_cls = [classify(a) for (a, l) in nus]
+    mucount = np.bincount(mu_cls, minlength=n)
+    nucount = np.bincount(nu_cls, minlength=n)
+    nmu, nnu = int(mucount.min()), int(nucount.min())
+    E_out = np.zeros((n, nmu), dtype=complex)
+    M4 = np.zeros((n, max(nucount.max(), 1), n, max(mucount.max(), 1)))    # [Sz(nu), rank of nu, Sz(mu), rank of mu]
+    seen_mu = np.zeros(n, dtype=int)
+    for jx, (a, l) in enumerate(mus):
+        ca = mu_cls[jx]
+        if seen_mu[ca] < nmu:
+            E_out[ca, seen_mu[ca]] = ELo[a, l]
+        seen_nu = np.zeros(n, dtype=int)
+        for i in range(len(nus)):
+            cb = nu_cls[i]
+            M4[cb, seen_nu[cb], ca, seen_mu[ca]] = Mnumus[i, jx]
+            seen_nu[cb] += 1
+        seen_mu[ca] += 1
+    Mbmas_eff = np.empty((n, nmu, n))
+    for beta in range(n):
+        for alpha in range(n):
+            Mbmas_eff[beta, :, alpha] = M4[alpha, :nnu, beta, :nmu].sum(axis=0)      # the alpha/beta swap of :238
+    return E_out, Mbmas_eff
 
 
 def current(Emas, Mbmas, Vb, tbulk, muR, kBT, verbose=0) -> np.ndarray:

@@ -874,6 +874,21 @@ __global__ void square_kernel(const double* __restrict__ x, double* __restrict__
     y[i] = (row_cut && m >= n_below[mat]) ? 0.0 : x[i] * x[i];
 }
 
+// C[i][j] = sum_k opA(A)[i][k] w[k] opB(B)[k][j] for small real matrices (basis changes of kernel_well :156-166):
+// transA: A stored [K][M] (else [M][K]); transB: B stored [N][K] (else [K][N]); w may be null.  One thread per element.
+__global__ void real_gemm_kernel(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ w,
+                                 double* __restrict__ C, int M, int N, int K, int transA, int transB) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= M || j >= N) return;
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double a = transA ? A[(size_t)k * M + i] : A[(size_t)i * K + k];
+        const double b = transB ? B[(size_t)j * K + k] : B[(size_t)k * N + j];
+        acc = fma(w ? a * w[k] : a, b, acc);
+    }
+    C[(size_t)i * N + j] = acc;
+}
+
 __global__ void max_int_kernel(const int* __restrict__ a, const int* __restrict__ b, int count, int* __restrict__ out) {
     int m = 0;
     for (int i = threadIdx.x; i < count; i += blockDim.x) m = max(m, max(a[i], b[i]));
@@ -1314,6 +1329,27 @@ int tx_bardeen_current(const double* E, const double* M2, int P, int n, int nb, 
     TX_CUDA(cudaMemcpy(dV, Vb, (size_t)nVb * 8, cudaMemcpyHostToDevice));
     if (int rc = tx_bardeen_current_dev(dE, dM, P, n, nb, dV, nVb, muR, kBT, dI, nullptr)) return rc;
     TX_CUDA(cudaMemcpy(I, dI, bI, cudaMemcpyDeviceToHost));
+    return TX_OK;
+}
+
+int tx_real_gemm(const double* A, const double* B, const double* w, double* C, int M, int N, int K, int transA, int transB) {
+    if (!A || !B || !C || M < 1 || N < 1 || K < 1) return fail(TX_ERR_ARG, "bad arguments");
+    if (int rc = have_device()) return rc;
+    const size_t bA = align256((size_t)M * K * 8), bB = align256((size_t)N * K * 8), bC = align256((size_t)M * N * 8), bw = align256((size_t)K * 8);
+    DevMem mem;
+    TX_CUDA(cudaMalloc(&mem.p, bA + bB + bC + bw + 256));
+    double* dA = (double*)mem.p;
+    double* dB = (double*)(mem.p + bA);
+    double* dC = (double*)(mem.p + bA + bB);
+    double* dw = (double*)(mem.p + bA + bB + bC);
+    TX_CUDA(cudaMemcpy(dA, A, (size_t)M * K * 8, cudaMemcpyHostToDevice));
+    TX_CUDA(cudaMemcpy(dB, B, (size_t)N * K * 8, cudaMemcpyHostToDevice));
+    if (w) TX_CUDA(cudaMemcpy(dw, w, (size_t)K * 8, cudaMemcpyHostToDevice));
+    dim3 block(32, 8), grid((N + 31) / 32, (M + 7) / 8);
+    real_gemm_kernel<<<grid, block>>>(dA, dB, w ? dw : nullptr, dC, M, N, K, transA, transB);
+    TX_CUDA(cudaGetLastError());
+    count_launch();
+    TX_CUDA(cudaMemcpy(C, dC, (size_t)M * N * 8, cudaMemcpyDeviceToHost));
     return TX_OK;
 }
 
