@@ -56,7 +56,11 @@ def cfg3():
     Es = np.linspace(-1.9, 1.9, 100_000).astype(complex)
     worst_path = os.path.join(ROOT, "gpurun_out", "cfg3_worst_idx.json")
     worst = json.load(open(worst_path))["worst_idx"][:48] if os.path.exists(worst_path) else []
-    idx = np.array(sorted(set(worst) | set(range(1000, 100_000, 3125))), dtype=np.int64)
+    keep = set()
+    old = os.path.join(OUT, "hp_cfg3_M10002.npz")
+    if os.path.exists(old):                    # energies of earlier fixtures stay (they were the worst of earlier kernels)
+        keep = set(int(i) for i in np.load(old)["idx"])
+    idx = np.array(sorted(set(worst) | keep | set(range(1000, 100_000, 3125))), dtype=np.int64)
     print("cfg3: %d energies (%d worst-unitarity + stride)" % (len(idx), len(worst)), flush=True)
     cores = os.cpu_count() or 1
     t0 = time.time()
@@ -85,6 +89,8 @@ def cfg3():
         dev_k = max(_relerr(T[k], m[1]).max(), _relerr(R[k], m[0]).max())
         assert dev_k < 1e-7, (k, dev_k, kap[k])
         R[k], T[k] = m[0], m[1]
+    # the float64 recursion's error against the FINAL truth (mpmath where it ran)
+    f64_err = np.maximum(_relerr(oT, T).max(axis=(1, 2)), _relerr(oR, R).max(axis=(1, 2)))
     np.savez(os.path.join(OUT, "hp_cfg3_M10002.npz"), idx=idx, Es=Es[idx], R_hp=R, T_hp=T, kappa=kap, f64_err=f64_err,
              f64_unitarity=f64_unit, hp_unitarity=unit, mp_checked=np.array([idx[k] for k in sub]),
              ld_vs_mp_max_rel=ld_vs_mp, worst_idx=np.array(worst, dtype=np.int64))

@@ -179,7 +179,8 @@ def sancho_rubio(h00, h01, zs, side, tol=1e-14, max_iter=200):
     return np.linalg.inv(zI - eps_s), it
 
 
-def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stats=False, cond_max=None, max_extend=3):
+def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stats=False, cond_max=None, max_extend=3,
+                          pole_max=None):
     """The same two blocks by the *telescoped* sweep the sm_100a kernel `rgf_sweep_n8t` runs (scalar hopping
     t_j = tau_j I only).  Inside a chunk of sites [a..b] the left-connected g_j are never formed:
 
@@ -196,6 +197,8 @@ def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stat
     it with a cancellation that costs cond(D_a) * eps of relative accuracy (the plain recursion meets this at every
     site).  If max|D_a| max|D_a^-1| exceeds cond_max the chunk is NOT closed there: it is extended by one more site (up
     to `max_extend` times), which needs no inverse of the offending matrix at all.
+    `pole_max` is the criterion the kernel uses (rgf_n8t.cuh, GMAXX): extend when max|t_{a-1} g_a| > pole_max, g_a = D_{a+1}
+    D_a^-1 — the quantity whose size IS the amplification of the next chunk's rounding errors.
     """
     Es = np.asarray(Es, dtype=complex)
     M, n = h.shape[0], h.shape[-1]
@@ -232,6 +235,15 @@ def rgf_blocks_telescoped(h, tnn, Es, SigL, SigR, kmax=8, gmax=64.0, return_stat
             growth = np.abs(D).max() / max(scale, 1e-300)
             a = j
             if j == 0 or k >= kmax or growth > gmax:
+                if pole_max is not None and j > 0 and extended < max_extend:
+                    Xtry = np.linalg.inv(D)
+                    gtry = (Dp1 @ Xtry) if k > 1 else Xtry
+                    if np.max(np.abs(gtry)) * abs(tau_all[j - 1]) <= pole_max:
+                        break
+                    extended += 1
+                    Dp2, Dp1 = Dp1, D
+                    j -= 1
+                    continue
                 if cond_max is None or j == 0 or extended >= max_extend:
                     break
                 Xtry = np.linalg.inv(D)

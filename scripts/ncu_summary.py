@@ -35,9 +35,17 @@ hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 ops, samp = collections.Counter(), collections.Counter()
 ti = ts = 0
+last_addr = -1
 for r in rows[2:]:
     if len(r) < len(hdr):
         continue
+    try:                                   # the page repeats every profiled launch (and each one twice): first table only
+        addr = int(r[ix['Address']], 16)
+    except ValueError:
+        continue
+    if addr <= last_addr:
+        break
+    last_addr = addr
     m = re.match(r'(@!?U?P\d+\s+)?([A-Z0-9_.]+)', r[ix['Source']].strip())
     op = m.group(2).split('.')[0] if m else '?'
     try:

@@ -220,11 +220,9 @@ def region_sweep(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, N
             H = H[None]
         NC = H.shape[1]
         if NC % 2 != 1: raise ValueError
-        for i in range(NC):
-            for j in range(NC):
-                if abs(i - j) > 1 and np.any(H[:, i, j]):
-                    raise NotImplementedError("HC couples sites beyond nearest neighbours: not a tridiagonal chain")
         idx = np.arange(NC)
+        if np.any(H[:, np.abs(idx[:, None] - idx[None, :]) > 1]):
+            raise NotImplementedError("HC couples sites beyond nearest neighbours: not a tridiagonal chain")
         return (as_f64(H[:, idx, idx]), as_f64(H[:, idx[:-1], idx[:-1] + 1]), as_f64(H[:, idx[:-1] + 1, idx[:-1]]))
 
     c0, cU, cL = chain(HC)

@@ -301,15 +301,15 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
         }
     };
 
-    // Conditioning guard.  In long, nearly closed chains (localised regime) the right-connected g_a can have a pole next
-    // to the real axis: D_a is nearly singular, |g_a| ~ 1e6, and the next chunk undoes it with a cancellation that costs
-    // cond(D_a) eps of relative accuracy (the plain recursion meets this at every site; measured on BASELINE config 3:
-    // unitarity residual 4.8e-8 at one energy of 1e5, 2e-8 relative error on T).  If max|U_a| max|U_a^-1| exceeds 2^CONDX
-    // the chunk is NOT closed at a: it is restarted from its first site (g_{b+1} reloaded from the scratch) and made one
-    // site longer, so the offending matrix is never inverted; at most three times per chunk.
-    // oracle/rgf_oracle.py:rgf_blocks_telescoped(cond_max=...) is the numpy restatement.  GUARD is instantiated for chains
-    // longer than one chunk (M > kmax); short chains keep the leaner code.
-    constexpr int CONDX = 17, CONDR = 12;
+    // Conditioning guard (GUARD: chains longer than one chunk).  In long, nearly closed chains (localised regime) the
+    // right-connected g_a can have a pole next to the real axis: |g_a| ~ 1e6, and the next chunk, which starts from
+    // z - |t|^2 g_a, undoes it with a cancellation that costs |t g_a| eps of relative accuracy (the plain recursion meets
+    // this at every site; measured on BASELINE config 3: unitarity residual 4.8e-8, relative errors 1e-8 where
+    // kappa(E) eps = 1e-11).  g_a is therefore formed BEFORE the (irreversible) update of W; if |t_{a-1} g_a| exceeds
+    // 2^GMAXX for any of the warp's points the chunk is not closed at a: it is restarted from its first site (g_{b+1}
+    // reloaded from an L2 scratch) and made one site longer, so the pole is never inverted; at most three times per
+    // chunk.  oracle/rgf_oracle.py:rgf_blocks_telescoped(cond_max=...) restates the idea in numpy.
+    constexpr int GMAXX = 8;
     int xlen = 0;   // 0: normal chunk; else (restarts << 16) | forced length of the chunk being redone
     double2 Ya[GPW][2], Yb[GPW][2];
     int j = M - 1;
@@ -421,10 +421,6 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
 
         // -------------------------------------------------------------- close the chunk at site a
         // D_a / d_a -> XB (slot (q; r; c) = U_a[c][r]),  U_{a+1} -> YB stored transposed
-        unsigned umax = 0u, xmax = 0u;
-        auto absmax2 = [](double2 u, double2 v) -> unsigned {
-            return max(max(hi_abs(u.x), hi_abs(u.y)), max(hi_abs(v.x), hi_abs(v.y)));
-        };
         if (phase == 0) {
 #pragma unroll
             for (int q = 0; q < GPW; ++q) {
@@ -432,7 +428,6 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 XB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
                 YB[q * N8TCfg::PSTRIDE + x0i] = Yb[q][0];
                 YB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
-                if (GUARD) umax = max(umax, absmax2(Ya[q][0], Ya[q][1]));
             }
         } else {
 #pragma unroll
@@ -441,7 +436,6 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
                 XB[q * N8TCfg::PSTRIDE + x1i] = Yb[q][1];
                 YB[q * N8TCfg::PSTRIDE + x0i] = Ya[q][0];
                 YB[q * N8TCfg::PSTRIDE + x1i] = Ya[q][1];
-                if (GUARD) umax = max(umax, absmax2(Yb[q][0], Yb[q][1]));
             }
         }
         __syncwarp();
@@ -453,37 +447,69 @@ __global__ void __launch_bounds__(128, MINB) rgf_sweep_n8t(const SweepParams p, 
 #pragma unroll
                 for (int c = 0; c < N; ++c) A[s][c] = xb[n8t_idx(row0 + s, c)];
             __syncwarp();
-            n8_invert<0, 1>(A, PV, xb, gid, row0, p.singular, zmask, GUARD ? &xmax : nullptr);   // X[k][c] -> slot (c; k): stored transposed
+            n8_invert<0, 1>(A, PV, xb, gid, row0, p.singular, zmask);   // X[k][c] -> slot (c; k): stored transposed
         }
-        if (GUARD && a > 0 && (xlen >> 16) < 3) {
-            // warp maxima of max|U_a| (over the eight points) and max|U_a^-1|: their product bounds every point's
-            // condition estimate from above (a conservative trigger)
-            umax = __reduce_max_sync(FULLM, umax);
-            xmax = __reduce_max_sync(FULLM, xmax);
-            // a resonance pole shows as |U^-1| >> |U| = O(1); evanescent growth inside the chunk makes BOTH large (that
-            // is what the growth bound handles, and a longer chunk would only make it worse): trigger on the former only
-            const int uexp = (int)(umax >> 20) - 1023, xexp = (int)(xmax >> 20) - 1023;
-            if (xexp + uexp > CONDX && xexp - uexp > CONDR) {
-                xlen = ((xlen >> 16) + 1) << 16 | (k + 1);
-                if (b < M - 1) {
-                    const double2* gs = gsave();
-#pragma unroll
-                    for (int q = 0; q < GPW; ++q) {
-                        Ya[q][0] = gs[q * 64];
-                        Ya[q][1] = gs[q * 64 + 1];
-                    }
-                }
-                j = b;
-                continue;                             // same chunk again, one site longer
-            }
-        }
-        xlen = 0;
         // W <- tau W X   and   g_a^T = X^T Y_{a+1}   (the X fragment serves as B of the first and A of the second);
         // undoing the scaling:  X = Xs / d_a,  Y_{a+1} = d_{a+1} U_{a+1}
         {
             const double rda = rdcur;
             const double gsc = dprev * rda;
             const double2 tq = make_double2(tau.x * rda, tau.y * rda);
+            if (GUARD) {
+                // g_a^T = X^T Y_{a+1} first, into Ya (the register copies of U_a, U_{a+1} are dead after the close)
+                unsigned gmx = 0u;
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    const double2* xq = XB + q * N8TCfg::PSTRIDE;
+                    const double2* yq = YB + q * N8TCfg::PSTRIDE;
+                    const double2 x0 = xq[f0i], x1 = xq[f1i];     // Xs[2t+s][g]
+                    const double2 y0 = yq[f0i], y1 = yq[f1i];     // U_{a+1}[2t+s][g]
+                    double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0};
+                    cdmma(gr, gi, x0, y0);
+                    cdmma(gr, gi, x1, y1);
+                    Ya[q][0] = make_double2(gr[0] * gsc, gi[0] * gsc);
+                    Ya[q][1] = make_double2(gr[1] * gsc, gi[1] * gsc);
+                    gmx = max(gmx, max(max(hi_abs(Ya[q][0].x), hi_abs(Ya[q][0].y)), max(hi_abs(Ya[q][1].x), hi_abs(Ya[q][1].y))));
+                }
+                if (a > 0 && (xlen >> 16) < 3) {
+                    gmx = __reduce_max_sync(FULLM, gmx);
+                    const double kapn = fma(tn.x, tn.x, tn.y * tn.y);       // |t_{a-1}|^2 (prefetched with site a-1)
+                    if (kapn > 0.0 && 2 * ((int)(gmx >> 20) - 1023) + expo(kapn) > 2 * GMAXX) {
+                        xlen = ((xlen >> 16) + 1) << 16 | (k + 1);
+                        if (b < M - 1) {
+                            const double2* gs = gsave();
+#pragma unroll
+                            for (int q = 0; q < GPW; ++q) {
+                                Ya[q][0] = gs[q * 64];
+                                Ya[q][1] = gs[q * 64 + 1];
+                            }
+                        }
+                        __syncwarp();
+                        j = b;
+                        continue;                     // same chunk again, one site longer
+                    }
+                }
+                xlen = 0;
+                // W <- tau W X
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    const double2* xq = XB + q * N8TCfg::PSTRIDE;
+                    double2* wq = WB + q * N8TCfg::PSTRIDE;
+                    if (b == M - 1) {
+                        const double2 c0 = xq[x0i], c1 = xq[x1i];     // Xs[g][2t+s]
+                        wq[f0i] = cmul2(c0, tq);
+                        wq[f1i] = cmul2(c1, tq);
+                    } else {
+                        const double2 x0 = xq[f0i], x1 = xq[f1i];
+                        const double2 w0 = wq[f0i], w1 = wq[f1i];     // W[g][2t+s]
+                        double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0};
+                        cdmma(wr, wi, w0, x0);
+                        cdmma(wr, wi, w1, x1);
+                        wq[f0i] = make_double2(fma(wr[0], tq.x, -(wi[0] * tq.y)), fma(wi[0], tq.x, wr[0] * tq.y));
+                        wq[f1i] = make_double2(fma(wr[1], tq.x, -(wi[1] * tq.y)), fma(wi[1], tq.x, wr[1] * tq.y));
+                    }
+                }
+            } else
             if (b == M - 1) {
                 // first chunk: W_M = I, so W = tau X is a scaled copy (X[g][2t+s] sits at the transposing slots)
 #pragma unroll
