@@ -394,6 +394,18 @@ def run_cfg2(env, args, scaling):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d random (J,E) points of the same grid x 8 sources, %.1f s wall" % (cores * 500, wall)}
 
+    # totals only: T(E) = Tr[Gamma_R G Gamma_L G^dag] per point, the array north_star's gather is about (8 B per point)
+    tt = torch.empty((n_j, N_E), dtype=torch.float64, pin_memory=True).numpy()
+
+    def totals(tt=tt):
+        tot = transmission_sweep(ph0, ptn, pE, h1=ph1, params=pJ, want_rt=False, want_total=True, total_out=tt)
+        return float(tot[0, 0])
+    dtt = time_e2e(totals, n_e2e)
+    e2e_total = {"value": n_pts_total / dtt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(tt.nbytes),
+                 "ms_per_step": dtt * 1e3, "outputs": "T(E) = Tr[Gamma_R G Gamma_L G^dag] per (J, E) point only",
+                 "pcie_frac": tt.nbytes / dtt / 1e9 / pcie}
+    del tt
+
     if pg is not None:
         pg.close()
     fp64_peak = env.fp64_peak()
@@ -412,7 +424,7 @@ def run_cfg2(env, args, scaling):
     exe_tf = EXECUTED_FLOPS_PER_POINT * n_pts / (k_ms * 1e-3) / 1e12
     return {
         "value": value, "ms_per_step": ms_per_step, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
-        "e2e_compact": compact[2], "e2e_compact4": compact[4], "cpu_baseline": cpu,
+        "e2e_compact": compact[2], "e2e_compact4": compact[4], "e2e_total": e2e_total, "cpu_baseline": cpu,
         "parity_max_rel_err": parity,
         "parity_against": "tests/golden/cfg2_cicc.npz (unmodified reference, 5 J x 25 E x 8 sources)" if parity is not None else None,
         "gather": {"mode": {"peer": "fused: K3 epilogue stores the per-point totals into every rank's buffer over NVLink (CUDA IPC peer "
@@ -457,7 +469,7 @@ def gpu_arm(args):
             extra["strong_scaling"] = {
                 "value": s["value"], "unit": UNIT, "ms_per_step": s["ms_per_step"], "points_total": N_J * N_E,
                 "points_per_gpu": s["points_per_gpu"], "kernel_ms": s["roofline"]["kernel_ms"],
-                "e2e": s["e2e"], "e2e_compact": s["e2e_compact"],
+                "e2e": s["e2e"], "e2e_compact": s["e2e_compact"], "e2e_total": s["e2e_total"],
                 "limiter": "fixed per-step cost (structure scan, affine expansion, the idle instantiation's launch, the flag "
                            "barrier) = ms_per_step - kernel_ms = %.3f ms against %.3f ms of sweep" %
                            (s["ms_per_step"] - s["roofline"]["kernel_ms"], s["roofline"]["kernel_ms"])}

@@ -787,7 +787,12 @@ def test_cfg3_full_length_against_extended_precision():
     singular blocks the kernel's conditioning guard steps around)."""
     g = load_golden("hp_cfg3_M10002.npz")
     h, tnn, _ = configs.disordered_blocks(N=10_000, n=8, W=0.05, seed=1234)
-    R, T, res = transmission_sweep(h, tnn, g["Es"].astype(complex), want_resid=True)
+    # the whole 1e5-energy axis in one sweep, as BASELINE names it (a point's chunk boundaries depend on its warp mates)
+    Es = np.linspace(-1.9, 1.9, 100_000).astype(complex)
+    assert np.array_equal(Es[g["idx"]], g["Es"].astype(complex))
+    R, T, res = transmission_sweep(h, tnn, Es, want_resid=True)
+    assert np.max(np.abs(res)) < 5e-9                      # all 1e5 energies (measured 1.2e-9 at an energy with kappa ~ 1e7)
+    R, T, res = R[:, g["idx"]], T[:, g["idx"]], res[:, g["idx"]]
 
     def rel(a, b):
         den = np.maximum(np.abs(b), 1e-13 * np.abs(b).max(-1, keepdims=True))
