@@ -805,3 +805,16 @@ def test_cfg3_full_length_against_extended_precision():
     assert np.median(dev) < 1e-10
     # unitarity: bounded by the same conditioning
     assert np.all(np.abs(res[0]).max(axis=-1) <= 1e-10 + 60.0 * g["kappa"] * 2.2e-16)
+
+
+def test_cfg4_sancho_leads_against_extended_precision():
+    """Sancho-Rubio self-energy of the config-4 ribbon lead (n = 64) at eta = 1e-8 against the long-double decimation of
+    tests/golden/hp_cfg4_leads.npz (oracle/make_golden_hp.py).  At eta = 1e-8 the surface Green's function itself is
+    conditioned like 1/eta: the float64 numpy decimation is off by 8e-9 = 0.8 eps/eta, the device by the same amount."""
+    g = load_golden("hp_cfg4_leads.npz")
+    h, tnn, _ = configs.ribbon_blocks(width=64, L=32, W=1.0, seed=1234)
+    SL, _ = leads.self_energies_batched(h, tnn, g["Es"].astype(complex), ("sancho", float(g["eta"])))
+    den = np.abs(g["sigL_hp"]).max(axis=(1, 2), keepdims=True)
+    err = (np.abs(SL - g["sigL_hp"]) / den).max(axis=(1, 2))
+    assert np.max(err) < 4 * 2.2e-16 / float(g["eta"])              # a few eps / eta
+    assert np.max(err) < 3 * np.max(g["f64_err"]) + 1e-10           # the level of the float64 numpy decimation
