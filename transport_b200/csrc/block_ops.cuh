@@ -28,6 +28,13 @@ struct TmaStage {
     unsigned parity;               // phase parity of the next wait (per thread, all threads in step)
 };
 constexpr int TMA_LD = 66;
+// Optional fused epilogue of the TMA-staged product: a second accumulate destination (C2 += sgn A B, e.g. the two
+// renormalised on-site blocks of the Sancho-Rubio step that receive the same product) and a per-thread running maximum of
+// |stored value|^2 (the convergence test of the decimation without another pass over the blocks).
+struct GemmEpi {
+    cd* C2 = nullptr;
+    double* tmax = nullptr;
+};
 __host__ __device__ inline size_t tma_stage_bytes(int n) { return (size_t)n * TMA_LD * sizeof(cd); }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -144,7 +151,7 @@ __device__ inline void cta_gemm_dmma_nn(cd* C, const cd* __restrict__ A, const c
 // tiles of the row in registers (32 accumulators), so every A fragment is fetched once.
 template <int N>
 __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, TmaStage& ts, double sgn,
-                                            bool accumulate, double cscale) {
+                                            bool accumulate, double cscale, const GemmEpi epi = GemmEpi()) {
     static_assert(N == 64, "one tile row per warp, eight warps");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -209,15 +216,43 @@ __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, con
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+            if (epi.C2) {
+                cd* p2 = epi.C2 + (tr + g) * N + 2 * t + u * 8 + i;
+                const cd c2 = *p2;
+                *p2 = mk(c2.x + v.x, c2.y + v.y);
+            }
             if (accumulate) {
                 const cd c0 = pc[u * 8 + i];
                 v.x = fma(cscale, c0.x, v.x);
                 v.y = fma(cscale, c0.y, v.y);
             }
             pc[u * 8 + i] = v;
+            if (epi.tmax) {
+                const double m = norm2(v);
+                *epi.tmax = (m > *epi.tmax || !(m == m)) ? m : *epi.tmax;
+            }
         }
     }
     __syncthreads();
+}
+
+// Block maximum of a per-thread value (NaN wins), broadcast to all threads.
+__device__ inline double cta_reduce_max(double m) {
+    __shared__ double s_rmax[32];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = (o > m || !(o == o)) ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) s_rmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) {
+        const double o = s_rmax[w];
+        r = (o > r || !(o == o)) ? o : r;
+    }
+    __syncthreads();
+    return r;
 }
 
 // C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
@@ -516,7 +551,7 @@ __device__ __forceinline__ cd crecip_fast(cd z) {
 // Per column: 2 barriers and 2 complex FMAs per thread instead of 4-5 barriers and a full read-modify-write of the block.
 // S == X: in place on a block that already lives in shared memory (leading dimension n); the permutation is then undone
 // through registers (n <= 48 with 256 threads: at most 9 entries per thread).
-__device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
+__device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, const cd* zminus_src = nullptr, cd zval = mk(0.0, 0.0)) {
     __shared__ cd s_R[8 * 64];
     __shared__ cd s_prow[8];
     __shared__ cd s_colk2[2 * 64];
@@ -526,9 +561,15 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular) {
     const int ld = in_place ? n : n + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (!in_place) {
+        // staged copy; with zminus_src the block to invert is z - H, formed on the fly (X is then output only)
         for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
             const int r = idx / n, c = idx - r * n;
-            S[r * ld + c] = X[idx];
+            if (zminus_src) {
+                const cd hv = zminus_src[idx];
+                S[r * ld + c] = (r == c) ? mk(zval.x - hv.x, zval.y - hv.y) : mk(-hv.x, -hv.y);
+            } else {
+                S[r * ld + c] = X[idx];
+            }
         }
         __syncthreads();
     }

@@ -344,6 +344,38 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
         int it = 0, ok = 0;
         double resid = 0.0;
         const double tol2 = p.conv_tol * p.conv_tol;
+        if (ts != nullptr) {
+            // n = 64 with TMA-staged products: z - eps is formed while the inverse stages its block, the product alpha G beta
+            // is accumulated into both on-site blocks by its own epilogue, and the epilogues of the two hopping products
+            // carry the convergence maximum -- no elementwise pass over the blocks is left in the iteration
+            for (it = 1; it <= p.max_iter; ++it) {
+                cta_inverse_blocked(G, stage, n, p.singular, eps, z);                   // G = (z - eps)^-1
+                cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);                               // G beta
+                cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);                              // G alpha
+                GemmEpi both;
+                both.C2 = eps;
+                cta_gemm_dmma_nn_tma<64>(epss, alpha, T1, *ts, 1.0, true, 1.0, both);    // epss, eps += alpha G beta
+                cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0, 1.0, ts);               // eps += beta G alpha
+                double tmax = 0.0;
+                GemmEpi conv;
+                conv.tmax = &tmax;
+                cta_gemm_dmma_nn_tma<64>(tmp, alpha, T2, *ts, 1.0, false, 1.0, conv);    // alpha G alpha
+                cta_gemm_dmma_nn_tma<64>(G, beta, T1, *ts, 1.0, false, 1.0, conv);       // beta G beta (G is free now)
+                {
+                    cd* sw = alpha;
+                    alpha = tmp;
+                    tmp = sw;
+                    sw = beta;
+                    beta = G;
+                    G = sw;
+                }
+                resid = cta_reduce_max(tmax);
+                if (resid < tol2) {
+                    ok = 1;
+                    break;
+                }
+            }
+        } else
         for (it = 1; it <= p.max_iter; ++it) {
             cta_z_minus(G, z, eps, n);
             cta_inverse_staged(G, stage, n, s_colk, s_ipiv, p.singular);
