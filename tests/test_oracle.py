@@ -239,3 +239,25 @@ def test_landauer_oracle_against_reference_fcdmft_golden():
     _, GN0 = rgf_oracle.rgf_blocks(g["h"], g["tnn"], Es, SL, SR)
     T = np.real(lo.transmission(g["energies"], g["MBGF"], LL, RL))
     assert np.allclose(rgf_oracle.caroli_trace(GN0, SL, SR), T, rtol=1e-12)
+
+
+def test_extended_precision_oracles_agree_with_float64_and_each_other():
+    """oracle/rgf_oracle_hp.py (the truth behind tests/golden/hp_cfg3_M10002.npz): the long-double recursion against the
+    float64 one on a chain where both are well conditioned, and mpmath at 50 digits against long double on a short chain;
+    and the fixture itself: unitarity of the stored truth, float64-oracle error consistent with what is stored."""
+    from oracle import rgf_oracle_hp as hp
+    from transport_b200 import configs
+    h, tnn, _ = configs.disordered_blocks(N=120, n=8, W=0.05, seed=1234)
+    Es = np.linspace(-1.7, 1.7, 5).astype(complex)
+    R0, T0 = rgf_oracle.transmission_closed(h, tnn, Es, np.eye(8))
+    R1, T1 = hp.transmission_closed_ld(h, tnn, Es, np.eye(8))
+    assert rt_err(T0, T1.astype(float)) < 1e-11 and rt_err(R0, R1.astype(float)) < 1e-11
+    assert float(np.max(np.abs(R1.sum(-1) + T1.sum(-1) - 1))) < 1e-16
+    hs, ts, _ = configs.disordered_blocks(N=20, n=8, W=0.05, seed=7)
+    R2, T2, unit = hp.transmission_closed_mp(hs, ts, Es[1], np.eye(8), dps=50)
+    R3, T3 = hp.transmission_closed_ld(hs, ts, Es[1:2], np.eye(8))
+    assert unit < 1e-40 and rt_err(T3[0].astype(float), T2) < 1e-14 and rt_err(R3[0].astype(float), R2) < 1e-14
+    g = load_golden("hp_cfg3_M10002.npz")
+    assert np.max(np.abs(g["R_hp"].sum(-1) + g["T_hp"].sum(-1) - 1)) < 1e-14          # mpmath truth, rounded to float64
+    assert len(g["mp_checked"]) == len(g["idx"])                                       # every energy went through mpmath
+    assert np.max(g["kappa"]) > 1e9 and np.max(g["f64_err"] / (g["kappa"] * 2.2e-16)) > 100
