@@ -106,17 +106,23 @@ def _cpu_bardeen(args):
 
 
 def _cpu_dense_fit(args):
-    """The reference's own algorithm (dense assembly + dense inverse, Python loops) timed at a few chain lengths."""
+    """The reference's own algorithm (dense assembly + dense inverse, Python loops) timed where it can run: one call at
+    M = 128 (its O((M n)^2) Python loops dominate there) and the LAPACK inverse alone at two sizes for the cubic term."""
     bu.one_thread_blas()
     from oracle import wfm_oracle
-    Ms, = args
-    ts = []
-    for Mq in Ms:
-        hq, tq, t3q = configs.disordered_blocks(N=Mq - 2, n=8, W=0.05, seed=1234)
+    M0, = args
+    hq, tq, t3q = configs.disordered_blocks(N=M0 - 2, n=8, W=0.05, seed=1234)
+    t0 = time.perf_counter()
+    wfm_oracle.kernel_loops(hq, tq, t3q, 1.0, complex(-0.7), "g_closed", np.eye(8)[0], False, False, all_debug=False)
+    t_call = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    t_inv = {}
+    for N in (8 * M0, 2048):
+        A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
         t0 = time.perf_counter()
-        wfm_oracle.kernel_loops(hq, tq, t3q, 1.0, complex(-0.7), "g_closed", np.eye(8)[0], False, False, all_debug=False)
-        ts.append(time.perf_counter() - t0)
-    return ts
+        np.linalg.inv(A)
+        t_inv[N] = time.perf_counter() - t0
+    return t_call, t_inv[8 * M0], t_inv[2048]
 
 
 def _pool_rate(worker, chunks, units):
@@ -262,16 +268,17 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
         #     one source, fitted t(M) = a M^2 + b M^3 and extrapolated to M = 10 002; the
         #     reference itself cannot run there: 102 GB dense matrix
         #     (timed in a worker process like every other CPU leg: BLAS in the parent is not fork-safe once pools ran)
-        Ms = [32, 64, 128]
+        M0 = 128
         with mp.get_context("fork").Pool(1) as pool:
-            ts = pool.map(_cpu_dense_fit, [(Ms,)])[0]
-        A = np.array([[m ** 2, m ** 3] for m in Ms], dtype=float)
-        (a, b), *_ = np.linalg.lstsq(A, np.array(ts), rcond=None)
-        t_full = (a * (N + 2) ** 2 + b * (N + 2) ** 3) * 8                      # x 8 sources per point
+            t_call, t_inv_small, t_inv_2048 = pool.map(_cpu_dense_fit, [(M0,)])[0]
+        a = max(t_call - t_inv_small, 0.0) / M0 ** 2                               # Python loops: O((M n)^2)
+        b = t_inv_2048 / 2048.0 ** 3 * 8 ** 3                                      # LAPACK inverse: O((M n)^3), per M^3
+        t_full = (a * (N + 2) ** 2 + b * (N + 2) ** 3) * 8                         # x 8 sources per point
+        Ms, ts = [M0], [t_call]
         return {"value": cores / t_full, "unit": bu.UNIT, "cores": cores, "kind": "port",
-                "sample": "EXTRAPOLATED: reference-loop port timed at M=%s (%s s per call), fit a M^2 + b M^3 -> %.3g s per point "
-                          "(8 sources) at M=%d, x %d cores; the dense path cannot run at this size (102 GB)"
-                          % (Ms, ["%.2f" % t for t in ts], t_full, N + 2, cores),
+                "sample": "EXTRAPOLATED: reference-loop port timed at M=%s (%s s per call: Python loops a M^2) + LAPACK inverse of a "
+                          "2048^2 block (%.2f s: b M^3) -> %.3g s per point (8 sources) at M=%d, x %d cores; the dense path cannot "
+                          "run at this size (102 GB)" % (Ms, ["%.2f" % t for t in ts], t_inv_2048, t_full, N + 2, cores),
                 "rgf_numpy_restatement": {"value": rgf_rate, "unit": bu.UNIT, "cores": cores,
                                           "sample": "%d energies x 8 sources at full length, %.1f s wall" % (cores * per, rgf_wall)}}
 
@@ -488,7 +495,10 @@ def run_cfg5(env, steps=5, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
             item["parity_against"] = "oracle/bardeen_oracle.kernel_well (dense eigh as the reference; pinned to reference goldens) on %d geometries: E absolute, |M|^2 relative" % len(idx)
             item["cpu_oracle_s_per_geometry_1core_blas_default"] = cpu_s / len(idx)
         if want_e2e:
-            reps = 3
+            reps = 5
+            bardeen.step_sweep(one, one, one, Vinf, VL, VRs, 20, NLR, NLR, HC, E_cutoff=0.1, interval=interval,
+                               Vb=np.linspace(-0.05, 0.05, 99), muR=-1.95, kBT=0.01)      # warm-up: workspace + buffer capacity
+            env.barrier()
             t0 = time.perf_counter()
             for _ in range(reps):
                 rr = bardeen.step_sweep(one, one, one, Vinf, VL, VRs, 20, NLR, NLR, HC, E_cutoff=0.1, interval=interval,
