@@ -131,7 +131,8 @@ int tx_peer_barrier_dev(int* const* flag_peers, int n_peers, int rank, int epoch
  *  sources  [n_src][n] real incident amplitudes (Ajsigma) or NULL
  *  src_idx  [n_src] channel indices of one-hot sources or NULL; if both are NULL all n one-hot
  *           sources are evaluated (n_src must then equal n)
- *  R, T     [n_ham][nE][n_src][n] doubles: per-channel reflection / transmission probabilities
+ *  R, T     [n_ham][nE][n_src][n] doubles: per-channel reflection / transmission probabilities (both may be NULL when
+ *           another output is requested: nothing of that size is then allocated, written or copied)
  *  resid    [n_ham][nE][n_src] doubles or NULL: sum(R)+sum(T)-1 (the reference's unitarity
  *           assert, wfm/__init__.py:135, evaluated on the device)
  *  t_total  [n_ham][nE] doubles or NULL: transmission summed over all evaluated sources and

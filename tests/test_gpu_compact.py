@@ -148,3 +148,68 @@ def test_contexts_run_concurrently_from_threads():
     assert rt_err(T6, T0) < 1e-11
     R1, T1 = transmission_sweep(g["h"], g["tnn"], g["Es"])
     assert np.array_equal(T1, T0)
+
+
+def test_device_built_lead_tables_through_the_host_sweep():
+    """TX_LEAD_SANCHO / TX_LEAD_SEPARABLE: the host sweep builds the self-energy tables on the device ahead of the sweep
+    (they never travel to the host).  Same numbers as the two-call route (tables to the host and back), for a large
+    block (n = 24, CTA-per-point kernel) and a small one (n = 8, register kernel in table mode)."""
+    from transport_b200 import leads
+    for n, M in ((24, 6), (8, 7)):
+        h, tnn, _ = configs.ribbon_blocks(width=n, L=M - 2, W=0.8, seed=3)
+        Es = np.linspace(-2.5, 2.5, 16).astype(complex)
+        for conv in (("sancho", 1e-6), ("separable", 1e-6), "separable"):
+            SL, SR = leads.self_energies_batched(h, tnn, Es, conv)
+            srcs = np.eye(n)[:2]
+            R0, T0, c0 = transmission_sweep(h, tnn, Es, "table", sigL=SL, sigR=SR, sources=srcs, want_caroli=True)
+            R1, T1, c1 = transmission_sweep(h, tnn, Es, conv, sources=srcs, want_caroli=True)
+            assert np.array_equal(c1, c0) and np.array_equal(T1, T0) and np.array_equal(R1, R0)
+            only = transmission_sweep(h, tnn, Es, conv, sources=srcs, want_rt=False, want_caroli=True)
+            assert np.array_equal(only, c0)
+    # a decimation that cannot converge inside its iteration cap is reported, not returned
+    h, tnn, _ = configs.ribbon_blocks(width=24, L=3, W=0.0, seed=3)
+    with pytest.raises(Exception, match="did not converge"):
+        transmission_sweep(h, tnn, np.array([0.3 + 0j]), ("sancho", 1e-12, 1e-14, 3), want_rt=False, want_caroli=True)
+
+
+def test_context_on_a_caller_stream_and_device_entry():
+    """tx_context_set_stream: the host entry issues on the caller's stream; the device entry on two different streams
+    through one context (scratch reuse ordered by an event) gives the bits of the default path."""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    g = load_golden("cfg2_cicc.npz")
+    R0, T0 = transmission_sweep(g["h"], g["tnn"], g["Es"])
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with Context(0, stream=s1.cuda_stream) as cx:
+        R1, T1 = transmission_sweep(g["h"], g["tnn"], g["Es"], context=cx)
+    assert np.array_equal(T1, T0) and np.array_equal(R1, R0)
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    Js, Es = configs.cfg2_grid(64, 64)
+    want_R, want_T = transmission_sweep(h0, tnn, Es, h1=h1, params=Js)
+
+    def dc(a):
+        return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
+    d_h0, d_h1, d_t, d_E = dc(h0), dc(h1), dc(tnn), dc(Es)
+    halves = []
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.tx_context_create(0, ctypes.byref(ctx)))
+    try:
+        for st, sl in ((s1, slice(0, 32)), (s2, slice(32, 64))):
+            dJ = torch.from_numpy(np.ascontiguousarray(Js[sl])).to(dev)
+            R = torch.empty((32 * 64, 8, 8), dtype=torch.float64, device=dev)
+            T = torch.empty_like(R)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            _lib.check(lib.tx_transmission_sweep_spin_dev(ctx, d_h0.data_ptr(), 1, d_h1.data_ptr(), dJ.data_ptr(), d_t.data_ptr(), 1,
+                                                          8, 8, 32, d_E.data_ptr(), 64, _lib.TX_LEAD_CLOSED, None, None, 1,
+                                                          _lib.TX_HOP_SCALAR, None, None, 8, R.data_ptr(), T.data_ptr(), None, None,
+                                                          0, 0, None, flag.data_ptr(), st.cuda_stream))
+            halves.append((R, T, flag, dJ))
+        torch.cuda.synchronize()
+    finally:
+        lib.tx_context_destroy(ctx)
+    got_T = np.concatenate([hh[1].cpu().numpy().reshape(32, 64, 8, 8) for hh in halves])
+    got_R = np.concatenate([hh[0].cpu().numpy().reshape(32, 64, 8, 8) for hh in halves])
+    assert np.array_equal(got_T, want_T) and np.array_equal(got_R, want_R)
