@@ -18,6 +18,7 @@
 #include <float.h>
 #include <math.h>
 
+#include <cstring>
 #include <mutex>
 
 #include "../../include/transport_b200.h"
@@ -1095,10 +1096,15 @@ int tx_bardeen_wells_dev(const double* dL, const double* eL, const double* dR, c
 }
 
 // Grow-only per-device workspace of tx_bardeen_region_sweep (serialised by a mutex: one sweep at a time per process).
+// All inputs travel as ONE host-to-device copy and all outputs as ONE device-to-host copy through a pinned staging block:
+// the call used to issue ~20 small copies from pageable memory and a mid-stream synchronisation, which cost three times
+// the device pass at S = 451.
 namespace {
 struct RegionWs {
     char* p = nullptr;
     size_t cap = 0;
+    char* host = nullptr;      // pinned staging: packed inputs, then packed outputs
+    size_t host_cap = 0;
     cudaStream_t st = nullptr;
 };
 RegionWs g_region_ws[16];
@@ -1134,10 +1140,27 @@ int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* 
     const size_t bh = align256((size_t)P * S * nn * 8);
     const size_t bv = align256((size_t)n_mat * ms * 8), bm = align256((size_t)n_mat * ms * n * 8);
     const size_t bw = max_states > 0 ? (size_t)tx_bardeen_workspace_bytes(P, n, S, max_states) : 0;
-    const size_t bpar = align256((size_t)(4 + 4 * n_pot) * n * 8);
-    const size_t bhc = align256((size_t)n_hc * NC * nn * 8);
-    const size_t bI = I ? align256((size_t)P * nn * nVb * 8) : 0, bVb = I ? align256((size_t)nVb * 8) : 0;
-    const size_t total = 4 * bd + 6 * bc + 3 * bh + 2 * bv + 2 * bm + bw + bpar + 6 * bhc + bI + bVb + 512;
+    const size_t bn = (size_t)n * 8, bpn = (size_t)n_pot * n * 8;
+    const size_t b0 = (size_t)n_hc * NC * nn * 8, b1 = (size_t)n_hc * (NC - 1) * nn * 8;
+    const size_t bI = I ? align256((size_t)P * nn * nVb * 8) : 0;
+    // packed input block (same layout on the host and on the device)
+    size_t in_bytes = 0;
+    auto in_take = [&](size_t b) { size_t o = in_bytes; in_bytes += align256(b); return o; };
+    const size_t o_par = in_take(4 * bn + 4 * bpn);
+    size_t o_hc[6];
+    for (int i = 0; i < 6; ++i) o_hc[i] = in_take((i % 3 == 0) ? b0 : (b1 ? b1 : 8));
+    const size_t o_cL = in_take((size_t)n_mat * 8), o_cRs = in_take((size_t)n_mat * 8), o_cRc = in_take((size_t)n_mat * 8);
+    const size_t o_Vb = in_take(I ? (size_t)nVb * 8 : 8);
+    // packed output block: header (needed), the three counts, then (with max_states > 0) EL, ER, Mavg, I
+    size_t out_bytes = 0;
+    auto out_take = [&](size_t b) { size_t o = out_bytes; out_bytes += align256(b); return o; };
+    const size_t o_max = out_take(256);
+    const size_t o_nL = out_take((size_t)n_mat * 4), o_nRs = out_take((size_t)n_mat * 4), o_nRb = out_take((size_t)n_mat * 4);
+    const size_t out_counts = out_bytes;
+    const size_t o_EL = out_take(bv), o_ER = out_take(bv), o_M = out_take(bm);
+    const size_t o_I = out_take(bI ? bI : 8);
+    const size_t total = 4 * bd + 3 * bh + bm + bw + in_bytes + out_bytes + 512;
+    const size_t host_total = in_bytes + out_bytes;
 
     int dev = 0;
     TX_CUDA(cudaGetDevice(&dev));
@@ -1151,45 +1174,61 @@ int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* 
         TX_CUDA(cudaMalloc(&ws.p, total + total / 4));
         ws.cap = total + total / 4;
     }
+    if (host_total > ws.host_cap) {
+        if (ws.host) cudaFreeHost(ws.host);
+        ws.host = nullptr;
+        ws.host_cap = 0;
+        TX_CUDA(cudaHostAlloc((void**)&ws.host, host_total + host_total / 4, cudaHostAllocDefault));
+        ws.host_cap = host_total + host_total / 4;
+    }
     cudaStream_t st = ws.st;
     char* q = ws.p;
     auto take = [&](size_t b) { char* r = q; q += b; return r; };
     double* ddL = (double*)take(bd); double* deL = (double*)take(bd);
     double* ddR = (double*)take(bd); double* deR = (double*)take(bd);
-    double* dcL = (double*)take(bc); double* dcRs = (double*)take(bc); double* dcRc = (double*)take(bc);
-    int* dnL = (int*)take(bc); int* dnRs = (int*)take(bc); int* dnRb = (int*)take(bc);
     double* dh0 = (double*)take(bh); double* dhU = (double*)take(bh); double* dhL = (double*)take(bh);
-    double* dEL = (double*)take(bv); double* dER = (double*)take(bv);
-    double* dM = (double*)take(bm); double* dM2 = (double*)take(bm);
+    double* dM2 = (double*)take(bm);
     char* wsp = take(bw);
-    double* dpar = (double*)take(bpar);
-    double* dhc[6];
-    for (int i = 0; i < 6; ++i) dhc[i] = (double*)take(bhc);
-    double* dI = (double*)take(bI); double* dVb = (double*)take(bVb);
-    int* dmax = (int*)take(256);
+    char* din = take(in_bytes);
+    char* dout = take(out_bytes);
+    char* hin = ws.host;
+    char* hout = ws.host + in_bytes;
 
-    auto up = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, st); };
-    const size_t bn = (size_t)n * 8, bpn = (size_t)n_pot * n * 8;
-    double* p_tinf = dpar; double* p_tL = dpar + n; double* p_tR = dpar + 2 * n; double* p_Vinf = dpar + 3 * n;
-    double* p_VL = dpar + 4 * n; double* p_VLp = p_VL + (size_t)n_pot * n; double* p_VR = p_VLp + (size_t)n_pot * n;
-    double* p_VRp = p_VR + (size_t)n_pot * n;
-    TX_CUDA(up(p_tinf, tinf, bn)); TX_CUDA(up(p_tL, tL, bn)); TX_CUDA(up(p_tR, tR, bn)); TX_CUDA(up(p_Vinf, Vinf, bn));
-    TX_CUDA(up(p_VL, VL, bpn)); TX_CUDA(up(p_VLp, VLprime, bpn)); TX_CUDA(up(p_VR, VR, bpn)); TX_CUDA(up(p_VRp, VRprime, bpn));
-    const size_t b0 = (size_t)n_hc * NC * nn * 8, b1 = (size_t)n_hc * (NC - 1) * nn * 8;
-    TX_CUDA(up(dhc[0], hc0, b0)); TX_CUDA(up(dhc[3], hp0, b0));
-    if (NC > 1) {
-        TX_CUDA(up(dhc[1], hcU, b1)); TX_CUDA(up(dhc[2], hcL, b1));
-        TX_CUDA(up(dhc[4], hpU, b1)); TX_CUDA(up(dhc[5], hpL, b1));
+    // pack and upload
+    {
+        double* hp = (double*)(hin + o_par);
+        std::memcpy(hp, tinf, bn); std::memcpy(hp + n, tL, bn); std::memcpy(hp + 2 * n, tR, bn); std::memcpy(hp + 3 * n, Vinf, bn);
+        const size_t np = (size_t)n_pot * n;
+        std::memcpy(hp + 4 * n, VL, bpn); std::memcpy(hp + 4 * n + np, VLprime, bpn);
+        std::memcpy(hp + 4 * n + 2 * np, VR, bpn); std::memcpy(hp + 4 * n + 3 * np, VRprime, bpn);
+        std::memcpy(hin + o_hc[0], hc0, b0); std::memcpy(hin + o_hc[3], hp0, b0);
+        if (NC > 1) {
+            std::memcpy(hin + o_hc[1], hcU, b1); std::memcpy(hin + o_hc[2], hcL, b1);
+            std::memcpy(hin + o_hc[4], hpU, b1); std::memcpy(hin + o_hc[5], hpL, b1);
+        }
+        std::memcpy(hin + o_cL, cutL, (size_t)n_mat * 8); std::memcpy(hin + o_cRs, cutR_states, (size_t)n_mat * 8);
+        std::memcpy(hin + o_cRc, cutR_count, (size_t)n_mat * 8);
+        if (I) std::memcpy(hin + o_Vb, Vb, (size_t)nVb * 8);
     }
-    TX_CUDA(up(dcL, cutL, (size_t)n_mat * 8)); TX_CUDA(up(dcRs, cutR_states, (size_t)n_mat * 8));
-    TX_CUDA(up(dcRc, cutR_count, (size_t)n_mat * 8));
-    TX_CUDA(cudaMemsetAsync(dmax, 0, 4, st));
+    TX_CUDA(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, st));
+    const bool full = max_states > 0;
+    TX_CUDA(cudaMemsetAsync(dout, 0, full ? out_bytes : out_counts, st));   // needed = 0; EL, ER, Mavg zero beyond the counts
+
+    double* dpar = (double*)(din + o_par);
+    double* dcL = (double*)(din + o_cL); double* dcRs = (double*)(din + o_cRs); double* dcRc = (double*)(din + o_cRc);
+    double* dVb = (double*)(din + o_Vb);
+    int* dmax = (int*)(dout + o_max);
+    int* dnL = (int*)(dout + o_nL); int* dnRs = (int*)(dout + o_nRs); int* dnRb = (int*)(dout + o_nRb);
+    double* dEL = (double*)(dout + o_EL); double* dER = (double*)(dout + o_ER); double* dM = (double*)(dout + o_M);
+    double* dI = (double*)(dout + o_I);
 
     RegionParams rp{};
-    rp.tinf = p_tinf; rp.tL = p_tL; rp.tR = p_tR; rp.Vinf = p_Vinf;
-    rp.VL = p_VL; rp.VLp = p_VLp; rp.VR = p_VR; rp.VRp = p_VRp;
+    rp.tinf = dpar; rp.tL = dpar + n; rp.tR = dpar + 2 * n; rp.Vinf = dpar + 3 * n;
+    rp.VL = dpar + 4 * n; rp.VLp = rp.VL + (size_t)n_pot * n; rp.VR = rp.VLp + (size_t)n_pot * n;
+    rp.VRp = rp.VR + (size_t)n_pot * n;
     rp.v_stride = n_pot == 1 ? 0 : n;
-    rp.hc0 = dhc[0]; rp.hcU = dhc[1]; rp.hcL = dhc[2]; rp.hp0 = dhc[3]; rp.hpU = dhc[4]; rp.hpL = dhc[5];
+    rp.hc0 = (double*)(din + o_hc[0]); rp.hcU = (double*)(din + o_hc[1]); rp.hcL = (double*)(din + o_hc[2]);
+    rp.hp0 = (double*)(din + o_hc[3]); rp.hpU = (double*)(din + o_hc[4]); rp.hpL = (double*)(din + o_hc[5]);
     rp.hc_stride0 = n_hc == 1 ? 0 : (long long)NC * nn;
     rp.hc_stride1 = n_hc == 1 ? 0 : (long long)(NC - 1) * nn;
     rp.Ninf = Ninf; rp.NL = NL; rp.NR = NR; rp.NC = NC; rp.n = n; rp.P = P; rp.S = S;
@@ -1202,37 +1241,32 @@ int tx_bardeen_region_sweep(const double* tinf, const double* tL, const double* 
     max_int_kernel<<<1, 256, 0, st>>>(dnL, dnRs, n_mat, dmax);
     TX_CUDA(cudaGetLastError());
     count_launch();
-    int needed = 0;
-    TX_CUDA(cudaMemcpyAsync(&needed, dmax, 4, cudaMemcpyDeviceToHost, st));
+    // No host round trip for the counts: the eigensolver and the matrix elements run against the caller's capacity (they
+    // clamp to max_states); when it turns out too small the caller is told through *max_needed and calls again.
+    if (full) {
+        if (int rc = wells_dev_impl(ddL, deL, ddR, deR, dcL, dcRs, dcRc, dh0, dhU, dhL, P, n, S, max_states, interval, sign_fix,
+                                    dEL, dnL, dER, dnRs, dnRb, dM, wsp, st, true))
+            return rc;
+        if (I) {
+            const long long cnt = (long long)n_mat * max_states * n;
+            square_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(dM, dM2, cnt, max_states, n, dnRb, row_cut);
+            TX_CUDA(cudaGetLastError());
+            count_launch();
+            if (int rc = tx_bardeen_current_dev(dEL, dM2, P, n, max_states, dVb, nVb, muR, kBT, dI, st)) return rc;
+        }
+    }
+    TX_CUDA(cudaMemcpyAsync(hout, dout, full ? out_bytes : out_counts, cudaMemcpyDeviceToHost, st));
     TX_CUDA(cudaStreamSynchronize(st));
+    const int needed = *(const int*)(hout + o_max);
     *max_needed = needed;
-    auto down = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToHost, st); };
-    TX_CUDA(down(nL, dnL, (size_t)n_mat * 4));
-    TX_CUDA(down(nR_states, dnRs, (size_t)n_mat * 4));
-    TX_CUDA(down(nR_below, dnRb, (size_t)n_mat * 4));
-    if (max_states == 0 || needed > max_states || needed == 0) {
-        TX_CUDA(cudaStreamSynchronize(st));
-        return TX_OK;          // counts only: the caller sizes its buffers from *max_needed and calls again
-    }
-    TX_CUDA(cudaMemsetAsync(dEL, 0, bv, st));
-    TX_CUDA(cudaMemsetAsync(dER, 0, bv, st));
-    TX_CUDA(cudaMemsetAsync(dM, 0, bm, st));
-    if (int rc = wells_dev_impl(ddL, deL, ddR, deR, dcL, dcRs, dcRc, dh0, dhU, dhL, P, n, S, max_states, interval, sign_fix, dEL,
-                                dnL, dER, dnRs, dnRb, dM, wsp, st, true))
-        return rc;
-    TX_CUDA(down(EL, dEL, (size_t)n_mat * max_states * 8));
-    TX_CUDA(down(ER, dER, (size_t)n_mat * max_states * 8));
-    TX_CUDA(down(Mavg, dM, (size_t)n_mat * max_states * n * 8));
-    if (I) {
-        const long long cnt = (long long)n_mat * max_states * n;
-        square_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(dM, dM2, cnt, max_states, n, dnRb, row_cut);
-        TX_CUDA(cudaGetLastError());
-        count_launch();
-        TX_CUDA(up(dVb, Vb, (size_t)nVb * 8));
-        if (int rc = tx_bardeen_current_dev(dEL, dM2, P, n, max_states, dVb, nVb, muR, kBT, dI, st)) return rc;
-        TX_CUDA(down(I, dI, (size_t)P * nn * nVb * 8));
-    }
-    TX_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(nL, hout + o_nL, (size_t)n_mat * 4);
+    std::memcpy(nR_states, hout + o_nRs, (size_t)n_mat * 4);
+    std::memcpy(nR_below, hout + o_nRb, (size_t)n_mat * 4);
+    if (!full || needed > max_states || needed == 0) return TX_OK;   // counts only: size the buffers from *max_needed, call again
+    std::memcpy(EL, hout + o_EL, (size_t)n_mat * max_states * 8);
+    std::memcpy(ER, hout + o_ER, (size_t)n_mat * max_states * 8);
+    std::memcpy(Mavg, hout + o_M, (size_t)n_mat * max_states * n * 8);
+    if (I) std::memcpy(I, hout + o_I, (size_t)P * nn * nVb * 8);
     return TX_OK;
 }
 
