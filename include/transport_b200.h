@@ -142,9 +142,11 @@ int tx_peer_barrier_dev(int* const* flag_peers, int n_peers, int rank, int epoch
  *           matrices Gamma = i(Sigma - Sigma^dag) — the total transmission when the self-energies
  *           are not diagonal (multi-channel ribbon leads)
  *
- * Block sizes n <= 16 run the register-resident kernel; 16 < n <= 64 (or any n when `caroli` is
+ * Block sizes n <= 16 run the register-resident kernel; 16 < n <= 128 (or any n when `caroli` is
  * requested) run the CTA-per-point kernel tx_transmission_sweep_large_dev, which takes table
  * self-energies only (the host entry builds the tables with tx_surface_gf_dev for closed-form leads).
+ * n <= 64: 256 threads, two CTAs per SM; 64 < n <= 128 (run_wfm_gate.get_hblocks gives n = 72 at TwoS = 5,
+ * 128 at TwoS = 7): 512 threads, one CTA per SM.  n > 128 returns TX_ERR_UNSUPPORTED.
  *
  * tx_transmission_sweep takes HOST pointers and performs the host<->device copies itself;
  * tx_transmission_sweep_dev takes DEVICE pointers and a cudaStream_t (as void*), launches
@@ -216,7 +218,7 @@ long long tx_launch_counter(void);
 
 /* ---- lead surface Green's functions and self-energies (K1) -------------------------------- */
 /*
- * Batched over energies, one CTA per energy, any n <= 64.  `side` = -1 for the left lead (incoming,
+ * Batched over energies, one CTA per energy, any n <= 128 (TX_GF_SEPARABLE: n <= 64).  `side` = -1 for the left lead (incoming,
  * wfm/__init__.py:283), +1 for the right lead (:284).  `mode` is one of TX_GF_*:
  *   CLOSED      wfm.g_closed   (:306-340)  h00, h01 diagonal in channel space
  *   RICEMELE    wfm.g_RiceMele (:352-414)  n = 2*n_spin, [A spins..., B spins...] ordering
@@ -243,7 +245,7 @@ int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cp
 int tx_g_ith(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, double imE,
              int ith, const tx_cplx* g_prev, tx_cplx* g_out);
 
-/* ---- Green's function blocks and Hamiltonian assembly (generic n <= 64) ------------------- */
+/* ---- Green's function blocks and Hamiltonian assembly (generic n <= 128) ------------------ */
 /* First block column G[:,0] -> [nE][M][n][n]  (psi_jsigma of wfm.kernel, :98-99). Host pointers. */
 int tx_green_column0(const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
                      const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* G);
@@ -377,7 +379,7 @@ int tx_set_option(int option, int value);
  * routine of the sweep (in-place Gauss-Jordan with implicit partial pivoting). Host pointers. */
 int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n);
 
-/* Same for the CTA-cooperative inverse of the large-block paths (n <= 64; blocked tensor-core Gauss-Jordan with
+/* Same for the CTA-cooperative inverse of the large-block paths (n <= 128; blocked tensor-core Gauss-Jordan with
  * implicit partial pivoting when n is a multiple of 8 and >= 16).  Returns TX_ERR_SINGULAR on a zero pivot. */
 int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n);
 /* Measurement hook: device time of `count` CTAs each doing `reps` n x n complex products on global-memory blocks. */

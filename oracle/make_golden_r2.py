@@ -36,6 +36,26 @@ def cicc_spin32(ref):
     np.savez(os.path.join(OUT, "cicc_spin32_n32.npz"), h=h, tnn=tnn, tnnn=tnnn, Es=Es, sources=srcs, R=R, T=T)
 
 
+def cicc_large_spins(ref):
+    """Two spin-5/2 and two spin-7/2 impurities: n_loc_dof = 2 (2s+1)^2 = 72 and 128, the 512-thread instantiation of the
+    large-block kernel, straight from run_wfm_gate.get_hblocks (run_wfm_gate.py:80-143).  The blocks are not stored (1 MB):
+    the fixture keeps the builder arguments, and this script asserts that transport_b200.configs.cicc_blocks reproduces
+    the reference's blocks bit for bit."""
+    wfm, gate = ref["wfm"], ref["run_wfm_gate"]
+    for TwoS in (5, 7):
+        args = (TwoS, 1.0, -0.3, 0.05, 0.0, 0.0, 1)
+        h, tnn, tnnn = gate.get_hblocks(*args, the_dist=1)
+        hb, tb, _ = configs.cicc_blocks(*args, 1)
+        assert np.allclose(h, hb, atol=0, rtol=0) and np.array_equal(tnn, tb), "cicc builder deviates from reference"
+        n = h.shape[-1]
+        assert n == 2 * (TwoS + 1) ** 2
+        Es = np.array([-1.95, -1.4, -0.6], dtype=complex)
+        idx = [0, n // 3 + 1, n - 1]
+        srcs = np.eye(n)[idx]
+        R, T = sweep(wfm, h, tnn, tnnn, 1.0, Es, "g_closed", list(srcs), all_debug=True)
+        np.savez(os.path.join(OUT, "cicc_builder_n%d.npz" % n), builder_args=np.array(args), the_dist=1, Es=Es, sources=srcs, R=R, T=T)
+
+
 def nnn_chains(ref):
     """Nonzero next-nearest-neighbour blocks through the reference's own pentadiagonal assembly (wfm.Hmat :209-213):
     kernel (R, T), the wavefunction output and the full Green's function, even and odd chain lengths."""
@@ -187,7 +207,7 @@ def kernel_well_n2(ref):
         print(tag, E.shape, M.shape)
 
 
-MAKERS = {"kernel_well_n2": kernel_well_n2, "cicc_spin32": cicc_spin32, "nnn_chains": nnn_chains, "well_channel_potentials": well_channel_potentials,
+MAKERS = {"kernel_well_n2": kernel_well_n2, "cicc_spin32": cicc_spin32, "cicc_large_spins": cicc_large_spins, "nnn_chains": nnn_chains, "well_channel_potentials": well_channel_potentials,
           "landauer_fcdmft": landauer_fcdmft}
 
 

@@ -537,7 +537,8 @@ __device__ __forceinline__ cd crecip_fast(cd z) {
     return mk(z.x * r, -z.y * r);
 }
 
-// Blocked Gauss-Jordan inverse for n a multiple of 8 (n <= 64), X in global memory, S a shared-memory staging block
+// Blocked Gauss-Jordan inverse for n a multiple of 8 (n <= NMAX, 4 n <= blockDim.x: NMAX = 64 with 256 threads, NMAX = 128 with
+// 512), X in global memory, S a staging block (shared memory; global for the largest blocks)
 // of n rows with leading dimension n + 1 (conflict-free fragment accesses).  Per panel of 8 columns:
 //   1. the 8 elimination steps on the n x 8 panel run in registers, two entries per thread (4n threads), with
 //      IMPLICIT partial pivoting over the rows not used so far: no row is moved, the pivot row of step k is recorded
@@ -552,12 +553,15 @@ __device__ __forceinline__ cd crecip_fast(cd z) {
 // Per column: 2 barriers and 2 complex FMAs per thread instead of 4-5 barriers and a full read-modify-write of the block.
 // S == X: in place on a block that already lives in shared memory (leading dimension n); the permutation is then undone
 // through registers (n <= 48 with 256 threads: at most 9 entries per thread).
+template <int NMAX = 64>
 __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, const cd* zminus_src = nullptr, cd zval = mk(0.0, 0.0)) {
-    __shared__ cd s_R[8 * 64];
+    static_assert(NMAX == 64 || NMAX == 128, "row index in the low 7 or 8 bits of the pivot key");
+    constexpr unsigned RB = NMAX - 1 + NMAX;          // low bits that carry NMAX - row (1 .. NMAX)
+    __shared__ cd s_R[8 * NMAX];
     __shared__ cd s_prow[8];
-    __shared__ cd s_colk2[2 * 64];
+    __shared__ cd s_colk2[2 * NMAX];
     __shared__ unsigned s_key[32];
-    __shared__ int s_perm[64];
+    __shared__ int s_perm[NMAX];
     const bool in_place = S == X;
     const int ld = in_place ? n : n + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -584,7 +588,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
         cd a1 = act ? S[r * ld + kb + 2 * cp + 1] : mk(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            cd* colk = s_colk2 + (j & 1) * 64;
+            cd* colk = s_colk2 + (j & 1) * NMAX;
             // stage 1: column j of the panel to shared memory, pivot = largest |.|^2 among the unused rows.  The key is
             // the high word of |a|^2 (sign 0, exponent, 20 mantissa bits: monotone, NaN above everything) with 64 - row
             // in its low 7 bits: one REDUX per warp picks the pivot (13 mantissa bits decide — ample for partial
@@ -593,7 +597,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
             if (act && cp == (j >> 1)) {
                 const cd v = (j & 1) ? a1 : a0;
                 colk[r] = v;
-                if (!used) key = ((unsigned)__double2hiint(norm2(v)) & ~127u) | (unsigned)(64 - r);
+                if (!used) key = ((unsigned)__double2hiint(norm2(v)) & ~RB) | (unsigned)(NMAX - r);
             }
             key = __reduce_max_sync(0xffffffffu, key);
             if (lane == 0) s_key[warp] = key;
@@ -602,7 +606,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
             // this alone took the 64 x 64 inverse from 71 to 61 us (tried and measured without gain: publishing every
             // candidate's reciprocal ahead of the barrier; letting the four owners of the pivot row scale it for everybody)
             key = __reduce_max_sync(0xffffffffu, lane < nwarps ? s_key[lane] : 0u);
-            const int pr = 64 - (int)(key & 127u);
+            const int pr = NMAX - (int)(key & RB);
             const cd pivot = colk[pr];
             if (threadIdx.x == 0) {
                 s_perm[kb + j] = pr;
@@ -643,7 +647,7 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
             const int j = idx / n, c = idx - j * n;
             if (c < kb || c >= kb + 8) {
                 const int pr = s_perm[kb + j];
-                s_R[j * 64 + c] = S[pr * ld + c];
+                s_R[j * NMAX + c] = S[pr * ld + c];
                 S[pr * ld + c] = mk(0.0, 0.0);
             }
         }
@@ -656,8 +660,8 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
                 const cd gb = S[(tr * 8 + g) * ld + kb + 4 + t];
                 for (int tc = 0; tc < tiles; ++tc) {
                     if (tc * 8 == kb) continue;
-                    const cd ra = s_R[t * 64 + tc * 8 + g];
-                    const cd rb = s_R[(4 + t) * 64 + tc * 8 + g];
+                    const cd ra = s_R[t * NMAX + tc * 8 + g];
+                    const cd rb = s_R[(4 + t) * NMAX + tc * 8 + g];
                     cd* cp = S + (tr * 8 + g) * ld + tc * 8 + 2 * t;
                     const cd c0 = cp[0], c1 = cp[1];
                     double re[2] = {c0.x, c1.x}, im[2] = {c0.y, c1.y};
@@ -688,20 +692,25 @@ __device__ inline void cta_inverse_blocked(cd* X, cd* S, int n, int* singular, c
     __syncthreads();
 }
 
-// Bytes of shared-memory staging the inverse of a global-memory block needs (leading dimension n + 1 for the blocked path).
+// Bytes of staging the inverse of a global-memory block needs (leading dimension n + 1 for the blocked path).
 __host__ __device__ inline size_t inverse_stage_bytes(int n) { return (size_t)n * (n + 1) * sizeof(cd); }
+// TX_STAGE_SMEM_MAX_N (tx_common.cuh): beyond it the staging block is a per-CTA block of the global workspace (L2-resident).
+__host__ __device__ inline bool inverse_stage_in_smem(int n) { return n <= TX_STAGE_SMEM_MAX_N; }
 
 // Inverse of X using the shared-memory staging block S (inverse_stage_bytes(n)) when X itself lives in global memory:
 // every elimination step rewrites the block, which must not go through L2 sixty-four times.
+template <int NMAX = 64>
 __device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ipiv, int* singular) {
     if (S == nullptr || S == X) {
         // block already in shared memory: blocked in place while the un-permutation fits the registers
-        if ((n & 7) == 0 && n >= 16 && n * n <= 9 * (int)blockDim.x && 4 * n <= (int)blockDim.x) cta_inverse_blocked(X, X, n, singular);
+        if ((n & 7) == 0 && n >= 16 && n * n <= 9 * (int)blockDim.x && 4 * n <= (int)blockDim.x)   // (implies n <= NMAX)
+            cta_inverse_blocked<NMAX>(X, X, n, singular);
         else cta_inverse(X, n, colk, ipiv, singular);
         return;
     }
-    if ((n & 7) == 0 && n >= 16 && n <= 64) {
-        cta_inverse_blocked(X, S, n, singular);
+    // (NMAX = 64: every caller runs 256 threads; the wider instantiation is also asked for n <= 64 never, but checks)
+    if ((n & 7) == 0 && n >= 16 && n <= NMAX && (NMAX == 64 || 4 * n <= (int)blockDim.x)) {
+        cta_inverse_blocked<NMAX>(X, S, n, singular);
         return;
     }
     cta_copy(S, X, n * n);

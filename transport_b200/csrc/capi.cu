@@ -675,7 +675,7 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
                     int n_sig, int hop_mode, const double* sources, int n_src, const SweepOut& o, tx_cplx* workspace,
                     int* singular_flag, cudaStream_t st) {
     if (!h || !tnn || !E || !sigL || !sigR || !singular_flag) return fail(TX_ERR_ARG, "null pointer argument");
-    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..64", n);
+    if (n < 1 || n > TX_MAX_N) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..%d", n, TX_MAX_N);
     if (M < 2 || n_ham < 1 || nE < 1 || n_src < 1) return fail(TX_ERR_ARG, "bad sizes");
     if (!(n_h == 1 || n_h == n_ham) || !(n_t == 1 || n_t == n_ham) || !(n_sig == 1 || n_sig == n_ham))
         return fail(TX_ERR_ARG, "n_h/n_t/n_sig must be 1 or n_ham");
@@ -970,7 +970,7 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
         if (rc) return rc;
         if (copied_out) TX_CUDA(cudaStreamSynchronize(ws.copy_stream));
     } else {
-        // generic-size path (n <= 64): one CTA per point on the device tables
+        // generic-size path (n <= 128): one CTA per point on the device tables
         const size_t wse = rgf_generic_workspace_elems(n, (long long)n_pts);
         if (wse && (rc = ws.big.ensure(wse * sizeof(tx_cplx)))) return rc;
         if (caroli && (rc = ws.caroli.ensure(n_pts * sizeof(double)))) return rc;

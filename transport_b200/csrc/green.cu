@@ -1,4 +1,5 @@
-// Generic-size Green's-function blocks, one CTA per energy (any n <= 64):
+// Generic-size Green's-function blocks, one CTA per energy (any n <= 128; the two work blocks sit in shared memory up to
+// n = 80 and in a global scratch beyond):
 //   tx_green_column0  first block column G[:,0]  -> wavefunction psi_j = i G[j,0] (A o v_L)
 //                     (transport/wfm/__init__.py:98-99)
 //   tx_green_full     all M x M blocks of inv(E - H')           (wfm.Green, :139-166)
@@ -24,6 +25,7 @@ struct GreenParams {
     const cd* sigR;
     cd* out;          // column0: [nE][M][n][n]; full: [nE][M][M][n][n]
     cd* work;         // full: [nE][2][M][n][n]  (gL, gR)
+    cd* ax;           // [nE][2][n][n] work blocks when they do not fit in shared memory, else null
     int* singular;
     int n, M, nE;
 };
@@ -32,12 +34,12 @@ constexpr int GR_THREADS = 128;
 
 __global__ void __launch_bounds__(GR_THREADS) green_column0_kernel(const GreenParams p) {
     extern __shared__ double2 gr_smem[];
-    __shared__ int s_ipiv[64];
-    __shared__ cd s_colk[64];
+    __shared__ int s_ipiv[TX_MAX_N];
+    __shared__ cd s_colk[TX_MAX_N];
     const int n = p.n, M = p.M, nn = n * n;
     const int e = blockIdx.x;
     const cd E = p.E[e];
-    cd* A = reinterpret_cast<cd*>(gr_smem);
+    cd* A = p.ax ? p.ax + (long long)e * 2 * nn : reinterpret_cast<cd*>(gr_smem);
     cd* X = A + nn;
     cd* Gc = p.out + (long long)e * M * nn;
     const cd* SL = p.sigL + (long long)e * nn;
@@ -67,12 +69,12 @@ __global__ void __launch_bounds__(GR_THREADS) green_column0_kernel(const GreenPa
 
 __global__ void __launch_bounds__(GR_THREADS) green_full_kernel(const GreenParams p) {
     extern __shared__ double2 gr_smem[];
-    __shared__ int s_ipiv[64];
-    __shared__ cd s_colk[64];
+    __shared__ int s_ipiv[TX_MAX_N];
+    __shared__ cd s_colk[TX_MAX_N];
     const int n = p.n, M = p.M, nn = n * n;
     const int e = blockIdx.x;
     const cd E = p.E[e];
-    cd* A = reinterpret_cast<cd*>(gr_smem);
+    cd* A = p.ax ? p.ax + (long long)e * 2 * nn : reinterpret_cast<cd*>(gr_smem);
     cd* X = A + nn;
     cd* G = p.out + (long long)e * M * M * nn;
     cd* gL = p.work + (long long)e * 2 * M * nn;
@@ -239,7 +241,7 @@ struct DevMem {
 int green_host(int which, const tx_cplx* h, const tx_cplx* tnn, int n, int M, const tx_cplx* E, int nE,
                const tx_cplx* sigL, const tx_cplx* sigR, tx_cplx* out) {
     if (!h || !tnn || !E || !sigL || !sigR || !out) return fail(TX_ERR_ARG, "null pointer argument");
-    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..64", n);
+    if (n < 1 || n > TX_MAX_N) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..%d", n, TX_MAX_N);
     if (M < 2 || nE < 1) return fail(TX_ERR_ARG, "bad sizes M=%d nE=%d", M, nE);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
@@ -251,8 +253,11 @@ int green_host(int which, const tx_cplx* h, const tx_cplx* tnn, int n, int M, co
     const size_t b_s = (size_t)nE * nn * bc;
     const size_t b_out = (size_t)nE * (which == 0 ? M : (size_t)M * M) * nn * bc;
     const size_t b_work = which == 0 ? 0 : (size_t)nE * 2 * M * nn * bc;
+    size_t smem = 2 * nn * bc;
+    const size_t b_ax = smem > 200 * 1024 ? (size_t)nE * smem : 0;
+    if (b_ax) smem = 0;
     DevMem d;
-    TX_CUDA(cudaMalloc(&d.p, b_h + b_t + b_E + 2 * b_s + b_out + b_work + 256));
+    TX_CUDA(cudaMalloc(&d.p, b_h + b_t + b_E + 2 * b_s + b_out + b_work + b_ax + 256));
     char* q = d.p;
     GreenParams p{};
     p.h = (const cd*)q;      TX_CUDA(cudaMemcpy(q, h, b_h, cudaMemcpyHostToDevice));      q += b_h;
@@ -262,11 +267,11 @@ int green_host(int which, const tx_cplx* h, const tx_cplx* tnn, int n, int M, co
     p.sigR = (const cd*)q;   TX_CUDA(cudaMemcpy(q, sigR, b_s, cudaMemcpyHostToDevice));   q += b_s;
     p.out = (cd*)q;          q += b_out;
     p.work = (cd*)q;         q += b_work;
+    p.ax = b_ax ? (cd*)q : nullptr;  q += b_ax;
     p.singular = (int*)q;    TX_CUDA(cudaMemset(q, 0, 4));
     p.n = n;
     p.M = M;
     p.nE = nE;
-    const size_t smem = 2 * nn * bc;
     if (which == 0) {
         if (smem > 48 * 1024)
             TX_CUDA(cudaFuncSetAttribute(green_column0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,6 +1,8 @@
-// K2/K3 for block sizes beyond the register-resident kernel (16 < n <= 64): one CTA per
+// K2/K3 for block sizes beyond the register-resident kernel (16 < n <= 128): one CTA per
 // (Hamiltonian, energy) point, blocks in shared memory (n <= 40) or an L2-resident global
-// workspace, CTA-cooperative GEMM / pivoted Gauss-Jordan from block_ops.cuh.
+// workspace, CTA-cooperative GEMM / pivoted Gauss-Jordan from block_ops.cuh.  Two instantiations:
+// 256 threads, two CTAs per SM for n <= 64; 512 threads, one CTA per SM for 64 < n <= 128 (the blocked
+// inverse wants 4 n threads; run_wfm_gate.get_hblocks gives n = 72 at TwoS = 5, 128 at TwoS = 7).
 //
 // Same recursion as rgf_small.cuh (replaces wfm.kernel, transport/wfm/__init__.py:29-137, for
 // multi-channel leads).  Lead self-energies always come from a table (K1).  Besides the reference's
@@ -17,22 +19,25 @@ using namespace tx;
 
 namespace tx {
 
-constexpr int GEN_THREADS = 256;
 constexpr int GEN_MATS = 5;
 
-__global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const GenericParams p) {
+template <int GEN_THREADS, int NMAX, int MINB>
+__global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const GenericParams p) {
     extern __shared__ double2 gen_smem[];
-    __shared__ int s_ipiv[64];
-    __shared__ cd s_colk[64];
-    __shared__ double s_vL[64], s_vR[64];
+    __shared__ int s_ipiv[NMAX];
+    __shared__ cd s_colk[NMAX];
+    __shared__ double s_vL[NMAX], s_vR[NMAX];
     __shared__ double s_red[GEN_THREADS / 32];
     __shared__ double s_red4[4][GEN_THREADS / 32];
     __shared__ unsigned long long s_tma_bar;
     const int n = p.n, M = p.M, nn = n * n;
     // persistent grid: the global workspace (blocks too large for shared memory) is indexed by CTA, not by point, so a
     // few hundred of them stay L2-resident however long the sweep is
-    cd* base = p.work ? p.work + (long long)blockIdx.x * GEN_MATS * nn : reinterpret_cast<cd*>(gen_smem);
-    cd* stage = p.work ? reinterpret_cast<cd*>(gen_smem) : nullptr;   // inverse staging when blocks are global
+    cd* base = p.work ? p.work + (long long)blockIdx.x * p.work_per_cta : reinterpret_cast<cd*>(gen_smem);
+    // inverse staging when the blocks are global: shared memory, or (n > 104) one more block of the workspace
+    cd* stage = p.work ? reinterpret_cast<cd*>(gen_smem) : nullptr;
+    if constexpr (NMAX > TX_STAGE_SMEM_MAX_N)
+        if (p.work && !inverse_stage_in_smem(n)) stage = base + GEN_MATS * nn;
     TmaStage tma_stage;
     TmaStage* ts = nullptr;   // n = 64: the products stage their B operand through the same block by TMA (block_ops.cuh)
     if (stage != nullptr && n == 64 && p.use_tma) {
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 tau = tau * conj(t0);
             }
             // close at site a = j:  cur = D_a, prev = D_{a+1} (identity if k == 1)
-            cta_inverse_staged(cur, stage, n, s_colk, s_ipiv, p.singular);   // X
+            cta_inverse_staged<NMAX>(cur, stage, n, s_colk, s_ipiv, p.singular);   // X
             if (prev_is_identity) cta_copy(G, cur, nn);
             else cta_gemm(G, prev, OP_N, cur, OP_N, n, ts);                  // g_a = D_{a+1} X
             if (b == M - 1) {
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
                 cta_copy(W, X, nn);
             }
         }
-        cta_inverse_staged(A, stage, n, s_colk, s_ipiv, p.singular);
+        cta_inverse_staged<NMAX>(A, stage, n, s_colk, s_ipiv, p.singular);
         if (j == M - 1) {
             cta_copy(G, A, nn);
             cta_copy(W, A, nn);
@@ -316,27 +321,37 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) rgf_sweep_generic(const Generi
     }   // persistent loop over points
 }
 
-// Host-side launcher used by capi.cu.  `work` must hold n_pts*GEN_MATS*n*n elements when the blocks
-// do not fit in shared memory (use rgf_generic_workspace_elems to size it).
 // Number of CTAs the generic sweep keeps resident (its grid; the workspace is per CTA).
-static int generic_resident_ctas(size_t smem) {
-    static int cached[16] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 296;
-    if (!cached[dev & 15]) {
-        int per_sm = 0, sms = 0;
-        if (smem > 16 * 1024) cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgf_sweep_generic, GEN_THREADS, smem);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cached[dev & 15] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
-    }
-    return cached[dev & 15];
+constexpr int GEN_THREADS_SMALL = 256, GEN_THREADS_BIG = 512;
+static const void* generic_kernel(bool big) {
+    return big ? (const void*)rgf_sweep_generic<GEN_THREADS_BIG, 128, 1> : (const void*)rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2>;
 }
 
+static int generic_resident_ctas(size_t smem, bool big) {
+    static int cached[16][2] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return big ? 148 : 296;
+    int& slot = cached[dev & 15][big ? 1 : 0];
+    if (!slot) {
+        int per_sm = 0, sms = 0;
+        if (smem > 16 * 1024) cudaFuncSetAttribute(generic_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel(big), big ? GEN_THREADS_BIG : GEN_THREADS_SMALL, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slot = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    return slot;
+}
+
+// dynamic shared memory when the blocks live in the global workspace: inverse staging and the TMA-staged product operand
 static size_t generic_stage_bytes(int n) {
-    size_t b = inverse_stage_bytes(n);
+    size_t b = inverse_stage_in_smem(n) ? inverse_stage_bytes(n) : 0;
     if (n == 64 && tma_stage_bytes(n) > b) b = tma_stage_bytes(n);
     return b;
+}
+
+// elements of the global workspace one resident CTA owns: GEN_MATS blocks (+ the inverse staging block beyond n = 104)
+static size_t generic_per_cta_elems(int n) {
+    return (size_t)GEN_MATS * n * n + (inverse_stage_in_smem(n) ? 0 : (size_t)n * (n + 1));
 }
 
 // Host-side launcher used by capi.cu.  `work` must hold rgf_generic_workspace_elems(n, n_pts) elements when the blocks do
@@ -344,31 +359,35 @@ static size_t generic_stage_bytes(int n) {
 size_t rgf_generic_workspace_elems(int n, long long n_pts) {
     const size_t bytes = (size_t)GEN_MATS * n * n * sizeof(cd);
     if (bytes <= 200 * 1024) return 0;
-    long long ctas = generic_resident_ctas(generic_stage_bytes(n));
+    long long ctas = generic_resident_ctas(generic_stage_bytes(n), n > 64);
     if (n_pts < ctas) ctas = n_pts;
-    return (size_t)ctas * GEN_MATS * n * n;
+    return (size_t)ctas * generic_per_cta_elems(n);
 }
 
 int launch_rgf_generic(GenericParams p, cudaStream_t st) {
+    if (p.n < 1 || p.n > TX_MAX_N) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..%d", p.n, TX_MAX_N);
+    const bool big = p.n > 64;
     const size_t bytes = (size_t)GEN_MATS * p.n * p.n * sizeof(cd);
     size_t smem = bytes;
     if (bytes > 200 * 1024) {
         if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
         smem = generic_stage_bytes(p.n);         // staging block for the inverse and the TMA-staged product operand
+        p.work_per_cta = (long long)generic_per_cta_elems(p.n);
     } else {
         p.work = nullptr;
     }
     p.use_tma = tma_mode();
-    if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
-        TX_CUDA(cudaFuncSetAttribute(rgf_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 16 * 1024)   // the kernel also has 11 KB (n <= 64) / 26 KB of static shared memory
+        TX_CUDA(cudaFuncSetAttribute(generic_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = p.n_pts;
     if (p.work) {
-        const long long ctas = generic_resident_ctas(smem);
+        const long long ctas = generic_resident_ctas(smem, big);
         if (grid > ctas) grid = ctas;
     } else if (grid > 0x7fffffffLL) {
         return fail(TX_ERR_ARG, "too many points for one launch");
     }
-    rgf_sweep_generic<<<(unsigned)grid, GEN_THREADS, smem, st>>>(p);
+    if (big) rgf_sweep_generic<GEN_THREADS_BIG, 128, 1><<<(unsigned)grid, GEN_THREADS_BIG, smem, st>>>(p);
+    else rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2><<<(unsigned)grid, GEN_THREADS_SMALL, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;

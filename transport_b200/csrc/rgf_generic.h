@@ -27,6 +27,7 @@ struct GenericParams {
     int n_up, spin_n;
     PeerGather gather;
     cd* work;                // global workspace or null (then dynamic shared memory)
+    long long work_per_cta;  // elements of `work` per resident CTA (set by the launcher)
     int* singular;
     long long n_pts;
     int n, M, nE, n_src, hop_scalar;

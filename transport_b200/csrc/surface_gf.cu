@@ -235,10 +235,11 @@ __global__ void __launch_bounds__(GF_THREADS) separable_gf_kernel(const GfParams
     }
 }
 
-__device__ void surface_gf_body(const GfParams& p, const int e) {
+template <int NMAX>
+__device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) {
     extern __shared__ double2 gf_smem[];
-    __shared__ int s_ipiv[64];
-    __shared__ cd s_colk[64];
+    __shared__ int s_ipiv[NMAX];
+    __shared__ cd s_colk[NMAX];
     __shared__ int s_flag;
     const int n = p.n;
     const int nn = n * n;
@@ -246,7 +247,10 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
     // the global workspace (blocks too large for shared memory) is indexed by CTA, not by energy: only the
     // resident CTAs need one, and a few hundred of them stay L2-resident
     cd* base = (p.scratch != nullptr) ? p.scratch + (long long)blockIdx.x * p.scratch_per : reinterpret_cast<cd*>(gf_smem);
-    cd* stage = (p.scratch != nullptr) ? reinterpret_cast<cd*>(gf_smem) : nullptr;   // inverse staging when blocks are global
+    // inverse staging when blocks are global: shared memory, or (n > 104) one more block of the workspace
+    cd* stage = (p.scratch != nullptr) ? reinterpret_cast<cd*>(gf_smem) : nullptr;
+    if constexpr (NMAX > TX_STAGE_SMEM_MAX_N)
+        if (p.scratch != nullptr && !inverse_stage_in_smem(n)) stage = base + p.scratch_per - (long long)n * (n + 1);
     // n = 64 with the blocks in the global workspace: the products stage their B operand through the same block by TMA
     __shared__ unsigned long long s_tma_bar;
     TmaStage tma_stage;
@@ -299,7 +303,7 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
                     cta_gemm_acc(m1, p.h01, OP_H, m2, OP_N, n, -1.0);
                 }
             }
-            cta_inverse_staged(m1, stage, n, s_colk, s_ipiv, p.singular);
+            cta_inverse_staged<NMAX>(m1, stage, n, s_colk, s_ipiv, p.singular);
             cta_copy(m0, m1, nn);
             it_done = ith;
             if (p.ith < 0) {
@@ -381,7 +385,7 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
         } else
         for (it = 1; it <= p.max_iter; ++it) {
             cta_z_minus(G, z, eps, n);
-            cta_inverse_staged(G, stage, n, s_colk, s_ipiv, p.singular);
+            cta_inverse_staged<NMAX>(G, stage, n, s_colk, s_ipiv, p.singular);
             cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);           // G beta
             cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);          // G alpha
             cta_gemm(tmp, alpha, OP_N, T1, OP_N, n, ts);        // alpha G beta
@@ -426,7 +430,7 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
             }
         }
         cta_z_minus(m0, z, epss, n);
-        cta_inverse_staged(m0, stage, n, s_colk, s_ipiv, p.singular);
+        cta_inverse_staged<NMAX>(m0, stage, n, s_colk, s_ipiv, p.singular);
         if (threadIdx.x == 0) {
             if (p.n_iter) p.n_iter[e] = it;
             if (p.conv) p.conv[e] = sqrt(resid);
@@ -439,22 +443,24 @@ __device__ void surface_gf_body(const GfParams& p, const int e) {
 }
 
 // Unit-test hook for the CTA-cooperative inverse of block_ops.cuh (staged / blocked path): one CTA per block.
-__global__ void __launch_bounds__(GF_THREADS) invert_staged_kernel(const cd* __restrict__ in, cd* __restrict__ out, int n,
-                                                                   int* singular, int unblocked) {
+// `gstage`: per-CTA staging blocks in global memory for n beyond the shared-memory staging (n > 104), else null.
+template <int THREADS, int NMAX>
+__global__ void __launch_bounds__(THREADS) invert_staged_kernel(const cd* __restrict__ in, cd* __restrict__ out, int n,
+                                                                int* singular, int unblocked, cd* gstage) {
     extern __shared__ double2 gf_smem[];
-    __shared__ int s_ipiv[64];
-    __shared__ cd s_colk[64];
+    __shared__ int s_ipiv[NMAX];
+    __shared__ cd s_colk[NMAX];
     const long long off = (long long)blockIdx.x * n * n;
     cta_copy(out + off, in + off, n * n);
+    cd* S = gstage ? gstage + (long long)blockIdx.x * n * (n + 1) : reinterpret_cast<cd*>(gf_smem);
     if (unblocked) {                                    // 1: the column-by-column Gauss-Jordan, for A/B measurements;
-        cd* S = reinterpret_cast<cd*>(gf_smem);         // 2: the block resident in shared memory (in-place paths, n <= 48)
-        cta_copy(S, out + off, n * n);
+        cta_copy(S, out + off, n * n);                  // 2: the block resident in shared memory (in-place paths, n <= 48)
         if (unblocked == 1) cta_inverse(S, n, s_colk, s_ipiv, singular);
-        else cta_inverse_staged(S, nullptr, n, s_colk, s_ipiv, singular);
+        else cta_inverse_staged<NMAX>(S, nullptr, n, s_colk, s_ipiv, singular);
         cta_copy(out + off, S, n * n);
         return;
     }
-    cta_inverse_staged(out + off, reinterpret_cast<cd*>(gf_smem), n, s_colk, s_ipiv, singular);
+    cta_inverse_staged<NMAX>(out + off, S, n, s_colk, s_ipiv, singular);
 }
 
 // Measurement hook: `reps` products C = A B per CTA on blocks in global memory (what the large-block paths do).
@@ -472,12 +478,18 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gemm_bench_kernel(const cd* __r
     for (int r = 0; r < reps; ++r) cta_gemm(C + off, A + off, OP_N, B + off, OP_N, n, ts);
 }
 
-// One CTA per energy, persistent over the energy axis (grid = resident CTAs).
-__global__ void __launch_bounds__(GF_THREADS, 2) surface_gf_kernel(const GfParams p) {
+// One CTA per energy, persistent over the energy axis (grid = resident CTAs).  256 threads, two CTAs per SM for n <= 64;
+// 512 threads, one CTA per SM for 64 < n <= 128 (the blocked inverse wants 4 n threads).
+template <int THREADS, int NMAX, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) surface_gf_kernel(const GfParams p) {
     for (int e = blockIdx.x; e < p.nE; e += gridDim.x) {
-        surface_gf_body(p, e);
+        surface_gf_body<NMAX>(p, e);
         __syncthreads();
     }
+}
+constexpr int GF_THREADS_BIG = 512;
+const void* gf_kernel(bool big) {
+    return big ? (const void*)surface_gf_kernel<GF_THREADS_BIG, 128, 1> : (const void*)surface_gf_kernel<GF_THREADS, 64, 2>;
 }
 
 // grow-only workspace of the decimation for blocks beyond shared memory (per device)
@@ -525,24 +537,27 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     }
     const size_t mats = (p.mode == TX_GF_SANCHO) ? GF_MAX_MATS : 3;
     const size_t bytes = mats * (size_t)n * n * sizeof(cd);
+    const bool big = n > 64;
     size_t smem = bytes;
     p.scratch = nullptr;
     p.scratch_per = 0;
+    size_t scratch_bytes = 0;
     if (bytes > 200 * 1024) {
-        smem = inverse_stage_bytes(n);          // staging block for the inverse
+        smem = inverse_stage_in_smem(n) ? inverse_stage_bytes(n) : 0;          // staging block for the inverse
         if (n == 64 && tma_stage_bytes(n) > smem) smem = tma_stage_bytes(n);   // ... and for the TMA-staged product operand
-        p.scratch_per = (long long)mats * n * n;
+        p.scratch_per = (long long)mats * n * n + (inverse_stage_in_smem(n) ? 0 : (long long)n * (n + 1));
+        scratch_bytes = (size_t)p.scratch_per * sizeof(cd);
     }
-    if (smem > 16 * 1024)   // the kernel also has ~11 KB of static shared memory
-        TX_CUDA(cudaFuncSetAttribute(surface_gf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 16 * 1024)   // the kernel also has 11 KB (n <= 64) / 26 KB of static shared memory
+        TX_CUDA(cudaFuncSetAttribute(gf_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 1;
     TX_CUDA(cudaGetDevice(&dev));
     TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_gf_kernel, GF_THREADS, smem));
+    TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_kernel(big), big ? GF_THREADS_BIG : GF_THREADS, smem));
     const int grid = (int)((long long)p.nE < (long long)sms * per_sm ? p.nE : sms * (per_sm > 0 ? per_sm : 1));
     if (p.scratch_per) {
         GfScratch& sc = g_gf_scratch[dev & 15];
-        const size_t need = (size_t)grid * bytes;
+        const size_t need = (size_t)grid * scratch_bytes;
         if (need > sc.cap) {
             TX_CUDA(cudaDeviceSynchronize());
             if (sc.ptr) cudaFree(sc.ptr);
@@ -553,7 +568,8 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
         }
         p.scratch = reinterpret_cast<cd*>(sc.ptr);
     }
-    surface_gf_kernel<<<grid, GF_THREADS, smem, st>>>(p);
+    if (big) surface_gf_kernel<GF_THREADS_BIG, 128, 1><<<grid, GF_THREADS_BIG, smem, st>>>(p);
+    else surface_gf_kernel<GF_THREADS, 64, 2><<<grid, GF_THREADS, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
@@ -561,7 +577,8 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
 
 int check_gf_args(const void* h00, const void* h01, int n, const void* E, int nE, int side, int mode) {
     if (!h00 || !h01 || !E) return fail(TX_ERR_ARG, "null pointer argument");
-    if (n < 1 || n > 64) return fail(TX_ERR_UNSUPPORTED, "surface GF block size n=%d outside 1..64", n);
+    if (n < 1 || n > TX_MAX_N) return fail(TX_ERR_UNSUPPORTED, "surface GF block size n=%d outside 1..%d", n, TX_MAX_N);
+    if (mode == TX_GF_SEPARABLE && n > 64) return fail(TX_ERR_UNSUPPORTED, "separable leads: block size n=%d outside 1..64", n);
     if (nE < 1) return fail(TX_ERR_ARG, "nE must be positive");
     if (side != 1 && side != -1) return fail(TX_ERR_ARG, "side must be +1 or -1");
     if (mode < TX_GF_CLOSED || mode > TX_GF_SEPARABLE) return fail(TX_ERR_ARG, "unknown surface GF mode %d", mode);
@@ -713,29 +730,34 @@ static float g_last_invert_ms = 0.f;
 double tx_debug_last_invert_ms(void) { return (double)g_last_invert_ms; }
 
 int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
-    if (!in || !out || count < 1 || n < 1 || n > 64) return fail(TX_ERR_ARG, "bad arguments");
+    if (!in || !out || count < 1 || n < 1 || n > TX_MAX_N) return fail(TX_ERR_ARG, "bad arguments");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
         cudaGetLastError();
         return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     }
     const size_t bytes = (size_t)count * n * n * sizeof(cd);
-    cd *din = nullptr, *dout = nullptr;
+    const bool big = n > 64, gs = !inverse_stage_in_smem(n);
+    cd *din = nullptr, *dout = nullptr, *dstage = nullptr;
     int* dflag = nullptr;
     TX_CUDA(cudaMalloc(&din, bytes));
     TX_CUDA(cudaMalloc(&dout, bytes));
     TX_CUDA(cudaMalloc(&dflag, sizeof(int)));
+    if (gs) TX_CUDA(cudaMalloc(&dstage, (size_t)count * inverse_stage_bytes(n)));
     TX_CUDA(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
     TX_CUDA(cudaMemset(dflag, 0, sizeof(int)));
-    const size_t smem = inverse_stage_bytes(n);
+    const size_t smem = gs ? 0 : inverse_stage_bytes(n);
     const int unblocked = getenv("TX_INVERT_UNBLOCKED") ? 1 : (getenv("TX_INVERT_INPLACE") ? 2 : 0);
-    TX_CUDA(cudaFuncSetAttribute(invert_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    const void* kern = big ? (const void*)invert_staged_kernel<GF_THREADS_BIG, 128> : (const void*)invert_staged_kernel<GF_THREADS, 64>;
+    TX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
-    invert_staged_kernel<<<count, GF_THREADS, smem>>>((const cd*)din, dout, n, dflag, unblocked);   // warm-up (same result)
-    cudaEventRecord(ev0);
-    invert_staged_kernel<<<count, GF_THREADS, smem>>>((const cd*)din, dout, n, dflag, unblocked);
+    for (int rep = 0; rep < 2; ++rep) {                 // the first launch is a warm-up (same result)
+        if (rep == 1) cudaEventRecord(ev0);
+        if (big) invert_staged_kernel<GF_THREADS_BIG, 128><<<count, GF_THREADS_BIG, smem>>>((const cd*)din, dout, n, dflag, unblocked, dstage);
+        else invert_staged_kernel<GF_THREADS, 64><<<count, GF_THREADS, smem>>>((const cd*)din, dout, n, dflag, unblocked, dstage);
+    }
     cudaEventRecord(ev1);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -748,6 +770,7 @@ int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n) {
     cudaFree(din);
     cudaFree(dout);
     cudaFree(dflag);
+    if (dstage) cudaFree(dstage);
     if (e != cudaSuccess) return fail(TX_ERR_CUDA, "invert_staged_kernel failed: %s", cudaGetErrorString(e));
     if (flag) return fail(TX_ERR_SINGULAR, "singular block");
     return TX_OK;

@@ -7,6 +7,12 @@
 
 namespace tx {
 
+// Largest block edge (n_loc_dof) of the CTA-cooperative large-block paths, and the largest one whose inverse staging block
+// (n (n + 1) 16 B = 175 KB at n = 104) still fits the shared memory of an SM next to the static arrays of the kernels.
+constexpr int TX_MAX_N = 128;
+constexpr int TX_STAGE_SMEM_MAX_N = 104;
+
+
 struct __align__(16) cd {
     double x, y;
 };
