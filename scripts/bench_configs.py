@@ -287,12 +287,14 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
 
 
 # ---------------------------------------------------------------------------------------------- cfg4
-def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False):
+def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=True, small=False, width=None, n_energies=None,
+             L=32):
+    """`width`, `n_energies`, `L`: the same workload at another ribbon width / grid (scripts/bench_wide_blocks.py)."""
     torch = env.torch
     lib = env.lib
-    n = 32 if small else 64
-    n_base = 256 if small else 4096
-    h, tnn, _ = configs.ribbon_blocks(width=n, L=32, W=1.0, seed=1234)
+    n = width or (32 if small else 64)
+    n_base = n_energies or (256 if small else 4096)
+    h, tnn, _ = configs.ribbon_blocks(width=n, L=L, W=1.0, seed=1234)
     total, lo, hi = _slice(n_base, env, scaling)
     Es = np.linspace(-3.5, 3.5, total).astype(complex)[lo:hi]
     nE = len(Es)
