@@ -233,7 +233,7 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
     def parity(Es, Rh, Th, lo):
         from oracle import rgf_oracle
         out = {}
-        if not small and env.world == 1 and os.path.exists(hp_path):
+        if not small and width is None and n_energies is None and env.world == 1 and os.path.exists(hp_path):
             g = np.load(hp_path)
             idx = g["idx"]
             eT = np.abs(Th[idx] - g["T_hp"]) / np.maximum(np.abs(g["T_hp"]), 1e-13 * np.abs(g["T_hp"]).max(-1, keepdims=True))
@@ -367,7 +367,7 @@ def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
         out["parity_against"] = ("oracle/rgf_oracle.py Caroli trace on the device's own Sancho-Rubio tables, %d energies "
                                  "(parity of multi-channel leads is unpinned by the reference: g_iter refuses n>2)" % len(idx))
         hp_path = os.path.join(GOLDEN, "hp_cfg4_leads.npz")
-        if not small and env.world == 1 and os.path.exists(hp_path):
+        if not small and width is None and n_energies is None and env.world == 1 and os.path.exists(hp_path):
             g = np.load(hp_path)
             li = g["idx"]
             SLd = torch.view_as_complex(sigL[li]).cpu().numpy()
