@@ -51,10 +51,11 @@ def test_reference_goldens_two_large_spins(n):
 
 
 @pytest.mark.parametrize("n,scalar", [(72, True), (72, False), (80, True), (96, True), (104, False), (112, True), (120, False),
-                                      (128, True), (128, False), (70, True), (99, False)])
+                                      (128, True), (128, False), (70, True), (99, False), (98, True), (50, True), (18, True), (121, True)])
 def test_wide_block_sweep_and_caroli(n, scalar):
     """telescoped (scalar hopping) and plain recursion, inverse staging in shared memory (n <= 104) and in the global
-    workspace, block edges that are not a multiple of 8 (scalar products, column-by-column inverse)"""
+    workspace, block edges that are not a multiple of 8 (telescoped sweep: work blocks padded to the tensor-core tile with
+    decoupled channels; plain recursion: scalar products, column-by-column inverse)"""
     M = 5
     h, tnn = _random_chain(n, M, scalar, n)
     Es = np.array([-1.4, 0.3, 1.2], dtype=complex)
@@ -115,7 +116,7 @@ def test_staged_inverse_wide(n):
     assert ei.value.code == _lib.TX_ERR_SINGULAR
 
 
-@pytest.mark.parametrize("n", [72, 112])
+@pytest.mark.parametrize("n", [72, 112, 50])
 def test_sancho_ribbon_leads_wide(n):
     """Sancho-Rubio lead tables of a ribbon wider than 64 channels against the numpy decimation and the fixed-point map;
     the sweep with the same tables against the oracle's Caroli trace; clean ribbon: integer channel count"""
@@ -138,6 +139,35 @@ def test_sancho_ribbon_leads_wide(n):
     eps = np.linalg.eigvalsh(h[0].real)
     open_ch = np.array([np.sum(np.abs(E.real - eps) < 2.0) for E in Es])
     assert np.allclose(np.asarray(car2).reshape(-1), open_ch, atol=1e-4)
+
+
+def test_padded_block_edge_with_affine_family_sources_and_spin_sums():
+    """n = 50 (two spin-2 impurities' block edge) through the padded telescoped sweep: affine family, superposed sources,
+    spin-resolved sums, unitarity; against the oracle and against the unpadded plain sweep (kmax = 1)"""
+    n, M = 50, 6
+    h, tnn = _random_chain(n, M, True, 11)
+    h1 = np.zeros_like(h)
+    h1[2] = np.diag(np.linspace(-1, 1, n))
+    Js = np.array([-0.4, 0.0, 0.7])
+    Es = np.array([-1.7, -0.2, 0.9, 1.6], dtype=complex)
+    rng = np.random.default_rng(3)
+    srcs = np.vstack([np.eye(n)[[0, 49]], rng.standard_normal((1, n))])
+    R, T, res, tot, spin = transmission_sweep(h, tnn, Es, h1=h1, params=Js, sources=srcs, want_resid=True, want_total=True,
+                                              want_spin=4)
+    assert np.max(np.abs(res)) < UNIT
+    for p in range(3):
+        oR, oT = rgf_oracle.transmission_closed(h + Js[p] * h1, tnn, Es, srcs)
+        assert rt_err(T[p], oT) < RTOL and rt_err(R[p], oR) < RTOL
+    assert np.allclose(tot, T.sum(axis=(2, 3)), rtol=1e-12)
+    assert np.allclose(spin[..., 0] + spin[..., 1], T.sum(axis=-1), rtol=1e-12)
+    assert np.allclose(spin[..., 2] + spin[..., 3], R.sum(axis=-1), rtol=1e-12)
+    lib = _lib.load()
+    _lib.check(lib.tx_set_option(1, 1))          # one inverse per site: no padding, scalar products
+    try:
+        R1, T1 = transmission_sweep(h, tnn, Es, h1=h1, params=Js, sources=srcs)
+    finally:
+        _lib.check(lib.tx_set_option(1, 32))
+    assert rt_err(T1, T) < RTOL and rt_err(R1, R) < RTOL
 
 
 def test_green_blocks_wide():

@@ -51,12 +51,16 @@ __device__ __forceinline__ void tma_stage_init(TmaStage& ts, cd* buf, unsigned l
 }
 
 // C = op(A) * op(B)            (C must not alias A or B)
+// FIXN: block edge known at compile time (64: the cfg4 instantiations of the sweep and lead kernels, which then hold only
+// the n = 64 product routines) or 0 (any n; multiples of 8 from 16 on take the tensor-core path).
+template <int FIXN = 0>
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
                                      double cscale = 1.0, TmaStage* ts = nullptr);
 
+template <int FIXN = 0>
 __device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n, TmaStage* ts = nullptr) {
-    if ((n & 7) == 0 && n >= 16) {
-        cta_gemm_dmma(C, A, opA, B, opB, n, 1.0, false, 1.0, ts);
+    if (FIXN == 64 || ((n & 7) == 0 && n >= 16)) {
+        cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, 1.0, false, 1.0, ts);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -256,19 +260,102 @@ __device__ inline double cta_reduce_max(double m) {
     return r;
 }
 
+// Run-time size, no transposes (every product of the telescoped sweep and of the decimation at n != 64): per-lane operand
+// pointers advanced by constants instead of re-deriving r * n + c behind an op switch for every fragment (the index
+// arithmetic was 39 % of the instructions of the generic routine), and the column tiles of a tile row are split EVENLY over
+// the ceil(tiles / 4) strips (n = 72: 9 tiles as 3 + 3 + 3 instead of 4 + 4 + 1).  More, narrower strips that would fill the
+// warps better were measured and lose: every strip re-reads the A fragments of its tile row from L2, and operand fetch, not
+// warp balance, binds these products (n = 104 with strips of 2: 389 ms against 308 ms for the cfg4 workload).
+__device__ inline void cta_gemm_dmma_nn_rt(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, int n, double sgn,
+                                           bool accumulate, double cscale) {
+    constexpr int NT = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tiles = n >> 3;
+    const int strips = (tiles + NT - 1) / NT;
+    const int base = tiles / strips, rem = tiles - base * strips;   // strip s holds base + (s < rem) tiles
+    const long long kstep = 4LL * n;
+    for (int item = warp; item < tiles * strips; item += nwarps) {
+        const int trow = item / strips, s = item - trow * strips;
+        const int tr = trow << 3;
+        const int tc0 = s * base + min(s, rem);
+        const int nt = base + (s < rem ? 1 : 0);
+        double re[NT][2], im[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
+        const cd* pa = A + (long long)(tr + g) * n + t;              // A[tr+g][k+t], k += 4
+        const cd* pb = B + (long long)t * n + (tc0 << 3) + g;        // B[k+t][(tc0+u)*8+g], k += 4
+        cd a = *pa;
+        cd b[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) b[u] = (u < nt) ? pb[u * 8] : mk(0.0, 0.0);
+        for (int k = 0; k < n; k += 4) {
+            const cd ac = a;
+            cd bc[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) bc[u] = b[u];
+            if (k + 4 < n) {
+                pa += 4;
+                pb += kstep;
+                a = *pa;
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    if (u < nt) b[u] = pb[u * 8];
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u)
+                if (u < nt) {
+                    dmma844(re[u], ac.x, bc[u].x);
+                    dmma844(im[u], ac.x, bc[u].y);
+                }
+#pragma unroll
+            for (int u = 0; u < NT; ++u)
+                if (u < nt) {
+                    dmma844(re[u], -ac.y, bc[u].y);
+                    dmma844(im[u], ac.y, bc[u].x);
+                }
+        }
+        cd* pc = C + (long long)(tr + g) * n + (tc0 << 3) + 2 * t;
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            if (u < nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+                    if (accumulate) {
+                        const cd c0 = pc[u * 8 + i];
+                        v.x = fma(cscale, c0.x, v.x);
+                        v.y = fma(cscale, c0.y, v.y);
+                    }
+                    pc[u * 8 + i] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // C = sgn*op(A)*op(B) (+ C if accumulate).  C must not alias A or B.  Requires n % 8 == 0.
 // A warp works on a strip of up to four 8x8 output tiles of one tile row: the A fragment of a k-step is loaded
 // once and reused for the four column tiles (16 DMMA per 5 fragment loads), and the loads of the next k-step are
 // issued before the DMMAs of the current one (operands usually sit in L2/L1, not in shared memory).
+template <int FIXN>
 __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, bool accumulate,
                                      double cscale, TmaStage* ts) {
-    if (ts != nullptr && n == 64 && opA == OP_N && opB == OP_N && blockDim.x == 256) {
-        cta_gemm_dmma_nn_tma<64>(C, A, B, *ts, sgn, accumulate, cscale);
-        return;
-    }
-    if (n == 64 && opA == OP_N && opB == OP_N) {
-        cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate, cscale);
-        return;
+    if constexpr (FIXN == 64) {
+        if (ts != nullptr && opA == OP_N && opB == OP_N && blockDim.x == 256) {
+            cta_gemm_dmma_nn_tma<64>(C, A, B, *ts, sgn, accumulate, cscale);
+            return;
+        }
+        if (opA == OP_N && opB == OP_N) {
+            cta_gemm_dmma_nn<64>(C, A, B, sgn, accumulate, cscale);
+            return;
+        }
+    } else {
+        if (opA == OP_N && opB == OP_N) {
+            cta_gemm_dmma_nn_rt(C, A, B, n, sgn, accumulate, cscale);
+            return;
+        }
     }
     constexpr int NT = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -329,10 +416,11 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
 }
 
 // C = cscale * C + sgn * op(A) * op(B)
+template <int FIXN = 0>
 __device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, double cscale = 1.0,
                                     TmaStage* ts = nullptr) {
-    if ((n & 7) == 0 && n >= 16) {
-        cta_gemm_dmma(C, A, opA, B, opB, n, sgn, true, cscale, ts);
+    if (FIXN == 64 || ((n & 7) == 0 && n >= 16)) {
+        cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, sgn, true, cscale, ts);
         return;
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {

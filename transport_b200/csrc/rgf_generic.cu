@@ -21,7 +21,7 @@ namespace tx {
 
 constexpr int GEN_MATS = 5;
 
-template <int GEN_THREADS, int NMAX, int MINB>
+template <int GEN_THREADS, int NMAX, int MINB, int FIXN>
 __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const GenericParams p) {
     extern __shared__ double2 gen_smem[];
     __shared__ int s_ipiv[NMAX];
@@ -30,7 +30,11 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     __shared__ double s_red[GEN_THREADS / 32];
     __shared__ double s_red4[4][GEN_THREADS / 32];
     __shared__ unsigned long long s_tma_bar;
-    const int n = p.n, M = p.M, nn = n * n;
+    // nr: block edge of the inputs and outputs; n: edge of the work blocks, = nr, or nr rounded up to the 8 x 8 tensor-core
+    // tile in the telescoped sweep (two spin-1, spin-2, spin-3 impurities give nr = 18, 50, 98): the padding channels are
+    // decoupled and carry z = 1 + |t_j|^2, which keeps D_j = 1 and g = 1 there (as in rgf_n8t.cuh), so neither the
+    // recurrence nor the inverse meets anything singular, and the products and the inverse run on the tensor cores
+    const int nr = p.n, n = p.np, M = p.M, nn = n * n, nnr = nr * nr;
     // persistent grid: the global workspace (blocks too large for shared memory) is indexed by CTA, not by point, so a
     // few hundred of them stay L2-resident however long the sweep is
     cd* base = p.work ? p.work + (long long)blockIdx.x * p.work_per_cta : reinterpret_cast<cd*>(gen_smem);
@@ -40,10 +44,11 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
         if (p.work && !inverse_stage_in_smem(n)) stage = base + GEN_MATS * nn;
     TmaStage tma_stage;
     TmaStage* ts = nullptr;   // n = 64: the products stage their B operand through the same block by TMA (block_ops.cuh)
-    if (stage != nullptr && n == 64 && p.use_tma) {
-        tma_stage_init(tma_stage, stage, &s_tma_bar);
-        ts = &tma_stage;
-    }
+    if constexpr (FIXN == 64)
+        if (stage != nullptr && p.use_tma) {
+            tma_stage_init(tma_stage, stage, &s_tma_bar);
+            ts = &tma_stage;
+        }
     for (long long pt = blockIdx.x; pt < p.n_pts; pt += gridDim.x) {
     const int ham = (int)(pt / p.nE);
     const int e = (int)(pt - (long long)ham * p.nE);
@@ -55,13 +60,13 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     cd* Y = base + 4 * nn;
     const cd* hb = p.h + ham * p.h_stride;
     const cd* tb = p.tnn + ham * p.t_stride;
-    const cd* SL = p.sigL + ham * p.sig_stride + (long long)e * nn;
-    const cd* SR = p.sigR + ham * p.sig_stride + (long long)e * nn;
+    const cd* SL = p.sigL + ham * p.sig_stride + (long long)e * nnr;
+    const cd* SR = p.sigR + ham * p.sig_stride + (long long)e * nnr;
     const double par = p.h1 ? p.params[ham] : 0.0;
 
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {      // v = -2 Im diag Sigma  (:91)
-        s_vL[c] = -2.0 * SL[c * n + c].y;
-        s_vR[c] = -2.0 * SR[c * n + c].y;
+    for (int c = threadIdx.x; c < nr; c += blockDim.x) {     // v = -2 Im diag Sigma  (:91)
+        s_vL[c] = -2.0 * SL[c * nr + c].y;
+        s_vR[c] = -2.0 * SR[c * nr + c].y;
     }
 
     // Elementwise passes over blocks that sit in L2 / HBM: four independent loads per thread and array before the first
@@ -82,21 +87,27 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     struct ZIn {
         cd h, w, s;
     };
-    // z_j = E - h_j (- Sigma on the end blocks) into dst
-    auto build_z = [&](cd* dst, int j) {
-        const cd* hj = hb + (long long)j * nn;
-        const cd* wj = p.h1 ? p.h1 + (long long)j * nn : nullptr;
+    // z_j = E - h_j (- Sigma on the end blocks) into dst; padding channels: diagonal 1 + padk
+    auto build_z = [&](cd* dst, int j, double padk) {
+        const cd* hj = hb + (long long)j * nnr;
+        const cd* wj = p.h1 ? p.h1 + (long long)j * nnr : nullptr;
         const cd* sg = (j == M - 1) ? SR : (j == 0 ? SL : nullptr);
         for_each4(dst,
                   [&](int idx) {
                       ZIn in;
-                      in.h = hj[idx];
-                      in.w = wj ? wj[idx] : mk(0.0, 0.0);
-                      in.s = sg ? sg[idx] : mk(0.0, 0.0);
+                      int src = idx;
+                      if (n != nr) {
+                          const int r = idx / n, c = idx - r * n;
+                          src = (r < nr && c < nr) ? r * nr + c : -1;
+                      }
+                      in.h = src >= 0 ? hj[src] : mk(0.0, 0.0);
+                      in.w = (wj && src >= 0) ? wj[src] : mk(0.0, 0.0);
+                      in.s = (sg && src >= 0) ? sg[src] : mk(0.0, 0.0);
                       return in;
                   },
                   [&](int idx, ZIn in) {
                       const int r = idx / n, c = idx - r * n;
+                      if (r >= nr || c >= nr) return mk(r == c ? 1.0 + padk : 0.0, 0.0);
                       cd hv = in.h;
                       if (wj) {
                           hv.x = fma(par, in.w.x, hv.x);
@@ -120,10 +131,10 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
         while (j >= 0) {
             const int b = j;
             cd tau = mk(1.0, 0.0);
-            double S2 = norm2(tb[(long long)((b < M - 1) ? b : M - 2) * nn]);
-            build_z(cur, b);
+            double S2 = norm2(tb[(long long)((b < M - 1) ? b : M - 2) * nnr]);
+            build_z(cur, b, b < M - 1 ? norm2(tb[(long long)b * nnr]) : 0.0);
             if (b < M - 1) {
-                const cd t0 = tb[(long long)b * nn];
+                const cd t0 = tb[(long long)b * nnr];
                 const double kap = norm2(t0);
                 tau = conj(t0);
                 struct Two {
@@ -135,13 +146,13 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
             int k = 1;
             bool prev_is_identity = true;
             while (j > 0 && k < p.kmax) {
-                const cd t0 = tb[(long long)(j - 1) * nn];
+                const cd t0 = tb[(long long)(j - 1) * nnr];
                 const double kap = norm2(t0);
                 if (!(kap > 0.0)) break;                                   // decoupled site: its own chunk
                 if (!(cta_maxnorm2(cur, nn) < gmax2 * S2)) break;          // growth bound (also stops on NaN)
                 --j;
                 ++k;
-                build_z(tmp, j);
+                build_z(tmp, j, kap);
                 // D_j = z_j D_{j+1} - kap D_{j+2}: the scaling of D_{j+2} rides on the product's epilogue
                 if (prev_is_identity) {
                     for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
@@ -149,9 +160,9 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
                         prev[idx] = mk(r == c ? -kap : 0.0, 0.0);
                     }
                     __syncthreads();
-                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, 1.0, ts);
+                    cta_gemm_acc<FIXN>(prev, tmp, OP_N, cur, OP_N, n, 1.0, 1.0, ts);
                 } else {
-                    cta_gemm_acc(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap, ts);
+                    cta_gemm_acc<FIXN>(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap, ts);
                 }
                 cd* sw = prev;
                 prev = cur;
@@ -163,18 +174,18 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
             // close at site a = j:  cur = D_a, prev = D_{a+1} (identity if k == 1)
             cta_inverse_staged<NMAX>(cur, stage, n, s_colk, s_ipiv, p.singular);   // X
             if (prev_is_identity) cta_copy(G, cur, nn);
-            else cta_gemm(G, prev, OP_N, cur, OP_N, n, ts);                  // g_a = D_{a+1} X
+            else cta_gemm<FIXN>(G, prev, OP_N, cur, OP_N, n, ts);                  // g_a = D_{a+1} X
             if (b == M - 1) {
                 for_each4(W, [&](int idx) { return cur[idx]; }, [&](int, cd v) { return v * tau; });
             } else {
-                cta_gemm(tmp, W, OP_N, cur, OP_N, n, ts);                    // W X
+                cta_gemm<FIXN>(tmp, W, OP_N, cur, OP_N, n, ts);                    // W X
                 for_each4(W, [&](int idx) { return tmp[idx]; }, [&](int, cd v) { return v * tau; });
             }
             --j;
         }
     } else
     for (int j = M - 1; j >= 0; --j) {
-        build_z(A, j);
+        build_z(A, j, 0.0);
         if (j < M - 1) {
             const cd* t = tb + (long long)j * nn;
             if (p.hop_scalar) {
@@ -190,9 +201,9 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
                 }
                 __syncthreads();
             } else {
-                cta_gemm(X, t, OP_N, G, OP_N, n);               // t g
-                cta_gemm_acc(A, X, OP_N, t, OP_H, n, -1.0);     // A -= (t g) t^dag
-                cta_gemm(X, W, OP_N, t, OP_H, n);               // W t^dag
+                cta_gemm<FIXN>(X, t, OP_N, G, OP_N, n);               // t g
+                cta_gemm_acc<FIXN>(A, X, OP_N, t, OP_H, n, -1.0);     // A -= (t g) t^dag
+                cta_gemm<FIXN>(X, W, OP_N, t, OP_H, n);               // W t^dag
                 cta_copy(W, X, nn);
             }
         }
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
             cta_copy(G, A, nn);
             cta_copy(W, A, nn);
         } else {
-            cta_gemm(X, W, OP_N, A, OP_N, n);                   // (W t^dag) g_j
+            cta_gemm<FIXN>(X, W, OP_N, A, OP_N, n);                   // (W t^dag) g_j
             cta_copy(W, X, nn);
             cta_copy(G, A, nn);
         }
@@ -212,8 +223,8 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     if (p.R || p.ttot || p.gather.n || p.resid || p.spin) {
         for (int i = 0; i < p.n_src; ++i) {
             double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector
-            for (int c = 0; c < n; ++c) {
-                const double a = p.sources ? p.sources[(long long)i * n + c] : (c == i ? 1.0 : 0.0);
+            for (int c = 0; c < nr; ++c) {
+                const double a = p.sources ? p.sources[(long long)i * nr + c] : (c == i ? 1.0 : 0.0);
                 f2 = fma(a, a * s_vL[c], f2);
                 if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
             }
@@ -221,10 +232,10 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
             double sp[4] = {0.0, 0.0, 0.0, 0.0};               // T same / other sector, R same / other (emit_spin)
             const double rflux = 1.0 / sqrt(f2);
             double part = 0.0;
-            for (int s = threadIdx.x; s < n; s += blockDim.x) {
+            for (int s = threadIdx.x; s < nr; s += blockDim.x) {
                 double ur = 0, ui = 0, wr = 0, wi = 0, mine = 0;
-                for (int c = 0; c < n; ++c) {
-                    const double a = p.sources ? p.sources[(long long)i * n + c] : (c == i ? 1.0 : 0.0);
+                for (int c = 0; c < nr; ++c) {
+                    const double a = p.sources ? p.sources[(long long)i * nr + c] : (c == i ? 1.0 : 0.0);
                     const double av = a * s_vL[c];
                     const cd g = G[s * n + c], w = W[s * n + c];
                     ur = fma(g.x, av, ur);
@@ -238,8 +249,8 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
                 const double yr = -wi * ft, yi = wr * ft;
                 const double rr = fma(xr, xr, xi * xi), tt = fma(yr, yr, yi * yi);
                 if (p.R) {
-                    p.R[(pt * p.n_src + i) * n + s] = rr;
-                    p.T[(pt * p.n_src + i) * n + s] = tt;
+                    p.R[(pt * p.n_src + i) * nr + s] = rr;
+                    p.T[(pt * p.n_src + i) * nr + s] = tt;
                 }
                 part += rr + tt;
                 tsum += tt;
@@ -294,14 +305,19 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     if (p.caroli) {
         for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
             const int r = idx / n, c = idx - r * n;
-            const cd a = SR[idx], b = conj(SR[c * n + r]);
+            if (r >= nr || c >= nr) {                           // padding channels carry no Gamma
+                A[idx] = mk(0.0, 0.0);
+                X[idx] = mk(0.0, 0.0);
+                continue;
+            }
+            const cd a = SR[r * nr + c], b = conj(SR[c * nr + r]);
             A[idx] = mk(-(a.y - b.y), a.x - b.x);               // i (a - b)
-            const cd a2 = SL[idx], b2 = conj(SL[c * n + r]);
+            const cd a2 = SL[r * nr + c], b2 = conj(SL[c * nr + r]);
             X[idx] = mk(-(a2.y - b2.y), a2.x - b2.x);
         }
         __syncthreads();
-        cta_gemm(Y, A, OP_N, W, OP_N, n);                       // Gamma_R W
-        cta_gemm(A, Y, OP_N, X, OP_N, n);                       // Gamma_R W Gamma_L
+        cta_gemm<FIXN>(Y, A, OP_N, W, OP_N, n);                       // Gamma_R W
+        cta_gemm<FIXN>(A, Y, OP_N, X, OP_N, n);                       // Gamma_R W Gamma_L
         double tr = 0.0;
         for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
             const cd y = A[idx], w = W[idx];
@@ -323,19 +339,24 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
 
 // Number of CTAs the generic sweep keeps resident (its grid; the workspace is per CTA).
 constexpr int GEN_THREADS_SMALL = 256, GEN_THREADS_BIG = 512;
-static const void* generic_kernel(bool big) {
-    return big ? (const void*)rgf_sweep_generic<GEN_THREADS_BIG, 128, 1> : (const void*)rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2>;
+static int generic_padded_edge(int n) { return n > 16 ? ((n + 7) & ~7) : n; }
+
+// instantiation by block edge: 0: n < 64 (256 threads), 1: n = 64 (256 threads, compile-time products, TMA staging), 2: n > 64
+static int generic_kind(int n) { return n > 64 ? 2 : (n == 64 ? 1 : 0); }
+static const void* generic_kernel(int kind) {
+    return kind == 2 ? (const void*)rgf_sweep_generic<GEN_THREADS_BIG, 128, 1, 0>
+                     : (kind == 1 ? (const void*)rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2, 64> : (const void*)rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2, 0>);
 }
 
-static int generic_resident_ctas(size_t smem, bool big) {
-    static int cached[16][2] = {};
+static int generic_resident_ctas(size_t smem, int kind) {
+    static int cached[16][3] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return big ? 148 : 296;
-    int& slot = cached[dev & 15][big ? 1 : 0];
+    if (cudaGetDevice(&dev) != cudaSuccess) return kind == 2 ? 148 : 296;
+    int& slot = cached[dev & 15][kind];
     if (!slot) {
         int per_sm = 0, sms = 0;
-        if (smem > 16 * 1024) cudaFuncSetAttribute(generic_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel(big), big ? GEN_THREADS_BIG : GEN_THREADS_SMALL, smem);
+        if (smem > 16 * 1024) cudaFuncSetAttribute(generic_kernel(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel(kind), kind == 2 ? GEN_THREADS_BIG : GEN_THREADS_SMALL, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slot = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
@@ -356,38 +377,43 @@ static size_t generic_per_cta_elems(int n) {
 
 // Host-side launcher used by capi.cu.  `work` must hold rgf_generic_workspace_elems(n, n_pts) elements when the blocks do
 // not fit in shared memory: GEN_MATS blocks per RESIDENT CTA (bounded: a persistent grid strides over the points), not per point.
-size_t rgf_generic_workspace_elems(int n, long long n_pts) {
+size_t rgf_generic_workspace_elems(int n_in, long long n_pts) {
+    const int n = generic_padded_edge(n_in);     // sized for the padded work blocks whichever sweep runs
     const size_t bytes = (size_t)GEN_MATS * n * n * sizeof(cd);
     if (bytes <= 200 * 1024) return 0;
-    long long ctas = generic_resident_ctas(generic_stage_bytes(n), n > 64);
+    long long ctas = generic_resident_ctas(generic_stage_bytes(n), generic_kind(n));
     if (n_pts < ctas) ctas = n_pts;
     return (size_t)ctas * generic_per_cta_elems(n);
 }
 
 int launch_rgf_generic(GenericParams p, cudaStream_t st) {
     if (p.n < 1 || p.n > TX_MAX_N) return fail(TX_ERR_UNSUPPORTED, "block size n=%d outside 1..%d", p.n, TX_MAX_N);
-    const bool big = p.n > 64;
-    const size_t bytes = (size_t)GEN_MATS * p.n * p.n * sizeof(cd);
+    // work-block edge: the telescoped sweep pads block edges beyond 16 to a multiple of the tensor-core tile
+    const int np = (p.hop_scalar && p.kmax > 1) ? generic_padded_edge(p.n) : p.n;
+    p.np = np;
+    const int kind = generic_kind(np);
+    const size_t bytes = (size_t)GEN_MATS * np * np * sizeof(cd);
     size_t smem = bytes;
     if (bytes > 200 * 1024) {
         if (!p.work) return fail(TX_ERR_ARG, "generic sweep needs a workspace for n=%d", p.n);
-        smem = generic_stage_bytes(p.n);         // staging block for the inverse and the TMA-staged product operand
-        p.work_per_cta = (long long)generic_per_cta_elems(p.n);
+        smem = generic_stage_bytes(np);          // staging block for the inverse and the TMA-staged product operand
+        p.work_per_cta = (long long)generic_per_cta_elems(np);
     } else {
         p.work = nullptr;
     }
     p.use_tma = tma_mode();
     if (smem > 16 * 1024)   // the kernel also has 11 KB (n <= 64) / 26 KB of static shared memory
-        TX_CUDA(cudaFuncSetAttribute(generic_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(generic_kernel(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = p.n_pts;
     if (p.work) {
-        const long long ctas = generic_resident_ctas(smem, big);
+        const long long ctas = generic_resident_ctas(smem, kind);
         if (grid > ctas) grid = ctas;
     } else if (grid > 0x7fffffffLL) {
         return fail(TX_ERR_ARG, "too many points for one launch");
     }
-    if (big) rgf_sweep_generic<GEN_THREADS_BIG, 128, 1><<<(unsigned)grid, GEN_THREADS_BIG, smem, st>>>(p);
-    else rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2><<<(unsigned)grid, GEN_THREADS_SMALL, smem, st>>>(p);
+    if (kind == 2) rgf_sweep_generic<GEN_THREADS_BIG, 128, 1, 0><<<(unsigned)grid, GEN_THREADS_BIG, smem, st>>>(p);
+    else if (kind == 1) rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2, 64><<<(unsigned)grid, GEN_THREADS_SMALL, smem, st>>>(p);
+    else rgf_sweep_generic<GEN_THREADS_SMALL, 64, 2, 0><<<(unsigned)grid, GEN_THREADS_SMALL, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;

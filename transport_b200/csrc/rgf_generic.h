@@ -31,6 +31,7 @@ struct GenericParams {
     int* singular;
     long long n_pts;
     int n, M, nE, n_src, hop_scalar;
+    int np;                  // edge of the work blocks (set by the launcher: n, or n padded to a multiple of 8)
     int kmax, gexp;          // telescoped sweep (scalar hopping): longest chunk, log2 of the growth bound
     int use_tma;             // n = 64: TMA-staged product operand (set by the launcher from tx_set_option(5, .))
 };

@@ -68,14 +68,15 @@ __device__ cd ricemele_channel(const cd* diag, const cd* off, int n, int s, cd E
 }
 
 // sigma = h01^dag g h01 (side=-1)  or  h01 g h01^dag (side=+1)
+template <int FIXN>
 __device__ void emit_sigma(const GfParams& p, const cd* g, cd* tmp, cd* out) {
     const int n = p.n;
     if (p.side == -1) {
-        cta_gemm(tmp, g, OP_N, p.h01, OP_N, n);
-        cta_gemm(out, p.h01, OP_H, tmp, OP_N, n);
+        cta_gemm<FIXN>(tmp, g, OP_N, p.h01, OP_N, n);
+        cta_gemm<FIXN>(out, p.h01, OP_H, tmp, OP_N, n);
     } else {
-        cta_gemm(tmp, g, OP_N, p.h01, OP_H, n);
-        cta_gemm(out, p.h01, OP_N, tmp, OP_N, n);
+        cta_gemm<FIXN>(tmp, g, OP_N, p.h01, OP_H, n);
+        cta_gemm<FIXN>(out, p.h01, OP_N, tmp, OP_N, n);
     }
 }
 
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(GF_THREADS) separable_gf_kernel(const GfParams
     }
 }
 
-template <int NMAX>
+template <int NMAX, int FIXN>
 __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) {
     extern __shared__ double2 gf_smem[];
     __shared__ int s_ipiv[NMAX];
@@ -255,10 +256,11 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
     __shared__ unsigned long long s_tma_bar;
     TmaStage tma_stage;
     TmaStage* ts = nullptr;
-    if (stage != nullptr && n == 64 && p.use_tma) {
-        tma_stage_init(tma_stage, stage, &s_tma_bar);
-        ts = &tma_stage;
-    }
+    if constexpr (FIXN == 64)
+        if (stage != nullptr && p.use_tma) {
+            tma_stage_init(tma_stage, stage, &s_tma_bar);
+            ts = &tma_stage;
+        }
     cd* m0 = base;               // g / result
     cd* m1 = base + nn;
     cd* m2 = base + 2 * nn;
@@ -296,11 +298,11 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
             cta_z_minus(m1, z, p.h00, n);
             if (ith > 0) {
                 if (p.side == 1) {                              // t g t^dag   (:548)
-                    cta_gemm(m2, m0, OP_N, p.h01, OP_H, n);
-                    cta_gemm_acc(m1, p.h01, OP_N, m2, OP_N, n, -1.0);
+                    cta_gemm<FIXN>(m2, m0, OP_N, p.h01, OP_H, n);
+                    cta_gemm_acc<FIXN>(m1, p.h01, OP_N, m2, OP_N, n, -1.0);
                 } else {                                        // t^dag g t   (:550)
-                    cta_gemm(m2, m0, OP_N, p.h01, OP_N, n);
-                    cta_gemm_acc(m1, p.h01, OP_H, m2, OP_N, n, -1.0);
+                    cta_gemm<FIXN>(m2, m0, OP_N, p.h01, OP_N, n);
+                    cta_gemm_acc<FIXN>(m1, p.h01, OP_H, m2, OP_N, n, -1.0);
                 }
             }
             cta_inverse_staged<NMAX>(m1, stage, n, s_colk, s_ipiv, p.singular);
@@ -348,14 +350,16 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
         int it = 0, ok = 0;
         double resid = 0.0;
         const double tol2 = p.conv_tol * p.conv_tol;
-        if (ts != nullptr) {
+        bool fused = false;
+        if constexpr (FIXN == 64) fused = ts != nullptr;
+        if constexpr (FIXN == 64) if (fused) {
             // n = 64 with TMA-staged products: z - eps is formed while the inverse stages its block, the product alpha G beta
             // is accumulated into both on-site blocks by its own epilogue, and the epilogues of the two hopping products
             // carry the convergence maximum -- no elementwise pass over the blocks is left in the iteration
             for (it = 1; it <= p.max_iter; ++it) {
                 cta_inverse_blocked(G, stage, n, p.singular, eps, z);                   // G = (z - eps)^-1
-                cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);                               // G beta
-                cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);                              // G alpha
+                cta_gemm<FIXN>(T1, G, OP_N, beta, OP_N, n, ts);                               // G beta
+                cta_gemm<FIXN>(T2, G, OP_N, alpha, OP_N, n, ts);                              // G alpha
                 // the four remaining products in an order that lets two of them reuse the staged operand
                 double tmax = 0.0;
                 GemmEpi both, conv, conv_reuse, acc_reuse;
@@ -382,13 +386,14 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
                     break;
                 }
             }
-        } else
+        }
+        if (!fused)
         for (it = 1; it <= p.max_iter; ++it) {
             cta_z_minus(G, z, eps, n);
             cta_inverse_staged<NMAX>(G, stage, n, s_colk, s_ipiv, p.singular);
-            cta_gemm(T1, G, OP_N, beta, OP_N, n, ts);           // G beta
-            cta_gemm(T2, G, OP_N, alpha, OP_N, n, ts);          // G alpha
-            cta_gemm(tmp, alpha, OP_N, T1, OP_N, n, ts);        // alpha G beta
+            cta_gemm<FIXN>(T1, G, OP_N, beta, OP_N, n, ts);           // G beta
+            cta_gemm<FIXN>(T2, G, OP_N, alpha, OP_N, n, ts);          // G alpha
+            cta_gemm<FIXN>(tmp, alpha, OP_N, T1, OP_N, n, ts);        // alpha G beta
             {
                 const int bd = blockDim.x;
                 int idx = threadIdx.x;
@@ -412,9 +417,9 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
                 }
             }
             __syncthreads();
-            cta_gemm_acc(eps, beta, OP_N, T2, OP_N, n, 1.0, 1.0, ts);    // + beta G alpha
-            cta_gemm(tmp, alpha, OP_N, T2, OP_N, n, ts);        // alpha G alpha
-            cta_gemm(G, beta, OP_N, T1, OP_N, n, ts);           // beta G beta (G is free now)
+            cta_gemm_acc<FIXN>(eps, beta, OP_N, T2, OP_N, n, 1.0, 1.0, ts);    // + beta G alpha
+            cta_gemm<FIXN>(tmp, alpha, OP_N, T2, OP_N, n, ts);        // alpha G alpha
+            cta_gemm<FIXN>(G, beta, OP_N, T1, OP_N, n, ts);           // beta G beta (G is free now)
             {                                                    // new alpha = tmp, new beta = G: swap roles, no copies
                 cd* sw = alpha;
                 alpha = tmp;
@@ -439,7 +444,7 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
     }
     (void)s_flag;
     if (p.g) cta_copy(p.g + (long long)e * nn, m0, nn);
-    if (p.sigma) emit_sigma(p, m0, m1, p.sigma + (long long)e * nn);
+    if (p.sigma) emit_sigma<FIXN>(p, m0, m1, p.sigma + (long long)e * nn);
 }
 
 // Unit-test hook for the CTA-cooperative inverse of block_ops.cuh (staged / blocked path): one CTA per block.
@@ -475,21 +480,27 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gemm_bench_kernel(const cd* __r
         tma_stage_init(tma_stage, reinterpret_cast<cd*>(gf_smem), &s_bar);
         ts = &tma_stage;
     }
-    for (int r = 0; r < reps; ++r) cta_gemm(C + off, A + off, OP_N, B + off, OP_N, n, ts);
+    for (int r = 0; r < reps; ++r) {
+        if (n == 64) cta_gemm<64>(C + off, A + off, OP_N, B + off, OP_N, n, ts);
+        else cta_gemm<0>(C + off, A + off, OP_N, B + off, OP_N, n, ts);
+    }
 }
 
 // One CTA per energy, persistent over the energy axis (grid = resident CTAs).  256 threads, two CTAs per SM for n <= 64;
 // 512 threads, one CTA per SM for 64 < n <= 128 (the blocked inverse wants 4 n threads).
-template <int THREADS, int NMAX, int MINB>
+template <int THREADS, int NMAX, int MINB, int FIXN>
 __global__ void __launch_bounds__(THREADS, MINB) surface_gf_kernel(const GfParams p) {
     for (int e = blockIdx.x; e < p.nE; e += gridDim.x) {
-        surface_gf_body<NMAX>(p, e);
+        surface_gf_body<NMAX, FIXN>(p, e);
         __syncthreads();
     }
 }
 constexpr int GF_THREADS_BIG = 512;
-const void* gf_kernel(bool big) {
-    return big ? (const void*)surface_gf_kernel<GF_THREADS_BIG, 128, 1> : (const void*)surface_gf_kernel<GF_THREADS, 64, 2>;
+// instantiation by block edge: 0: n < 64, 1: n = 64 (compile-time products, TMA staging, fused decimation), 2: n > 64
+int gf_kind(int n) { return n > 64 ? 2 : (n == 64 ? 1 : 0); }
+const void* gf_kernel(int kind) {
+    return kind == 2 ? (const void*)surface_gf_kernel<GF_THREADS_BIG, 128, 1, 0>
+                     : (kind == 1 ? (const void*)surface_gf_kernel<GF_THREADS, 64, 2, 64> : (const void*)surface_gf_kernel<GF_THREADS, 64, 2, 0>);
 }
 
 // grow-only workspace of the decimation for blocks beyond shared memory (per device)
@@ -537,7 +548,7 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     }
     const size_t mats = (p.mode == TX_GF_SANCHO) ? GF_MAX_MATS : 3;
     const size_t bytes = mats * (size_t)n * n * sizeof(cd);
-    const bool big = n > 64;
+    const int kind = gf_kind(n);
     size_t smem = bytes;
     p.scratch = nullptr;
     p.scratch_per = 0;
@@ -549,11 +560,11 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
         scratch_bytes = (size_t)p.scratch_per * sizeof(cd);
     }
     if (smem > 16 * 1024)   // the kernel also has 11 KB (n <= 64) / 26 KB of static shared memory
-        TX_CUDA(cudaFuncSetAttribute(gf_kernel(big), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TX_CUDA(cudaFuncSetAttribute(gf_kernel(kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 1;
     TX_CUDA(cudaGetDevice(&dev));
     TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_kernel(big), big ? GF_THREADS_BIG : GF_THREADS, smem));
+    TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_kernel(kind), kind == 2 ? GF_THREADS_BIG : GF_THREADS, smem));
     const int grid = (int)((long long)p.nE < (long long)sms * per_sm ? p.nE : sms * (per_sm > 0 ? per_sm : 1));
     if (p.scratch_per) {
         GfScratch& sc = g_gf_scratch[dev & 15];
@@ -568,8 +579,9 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
         }
         p.scratch = reinterpret_cast<cd*>(sc.ptr);
     }
-    if (big) surface_gf_kernel<GF_THREADS_BIG, 128, 1><<<grid, GF_THREADS_BIG, smem, st>>>(p);
-    else surface_gf_kernel<GF_THREADS, 64, 2><<<grid, GF_THREADS, smem, st>>>(p);
+    if (kind == 2) surface_gf_kernel<GF_THREADS_BIG, 128, 1, 0><<<grid, GF_THREADS_BIG, smem, st>>>(p);
+    else if (kind == 1) surface_gf_kernel<GF_THREADS, 64, 2, 64><<<grid, GF_THREADS, smem, st>>>(p);
+    else surface_gf_kernel<GF_THREADS, 64, 2, 0><<<grid, GF_THREADS, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
     return TX_OK;
