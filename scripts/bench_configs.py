@@ -233,7 +233,7 @@ def run_cfg3(env, steps=3, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
     def parity(Es, Rh, Th, lo):
         from oracle import rgf_oracle
         out = {}
-        if not small and width is None and n_energies is None and env.world == 1 and os.path.exists(hp_path):
+        if not small and env.world == 1 and os.path.exists(hp_path):
             g = np.load(hp_path)
             idx = g["idx"]
             eT = np.abs(Th[idx] - g["T_hp"]) / np.maximum(np.abs(g["T_hp"]), 1e-13 * np.abs(g["T_hp"]).max(-1, keepdims=True))
