@@ -37,12 +37,13 @@ def cicc_spin32(ref):
 
 
 def cicc_large_spins(ref):
-    """Two spin-5/2 and two spin-7/2 impurities: n_loc_dof = 2 (2s+1)^2 = 72 and 128, the 512-thread instantiation of the
-    large-block kernel, straight from run_wfm_gate.get_hblocks (run_wfm_gate.py:80-143).  The blocks are not stored (1 MB):
+    """Two spin-2, 5/2, 3, 7/2 impurities: n_loc_dof = 2 (2s+1)^2 = 50, 72, 98, 128 -- block edges beyond 64 (the 512-thread
+    instantiation of the large-block kernel) and edges that are not a multiple of the 8 x 8 tensor-core tile (padded work
+    blocks), straight from run_wfm_gate.get_hblocks (run_wfm_gate.py:80-143).  The blocks are not stored (1 MB):
     the fixture keeps the builder arguments, and this script asserts that transport_b200.configs.cicc_blocks reproduces
     the reference's blocks bit for bit."""
     wfm, gate = ref["wfm"], ref["run_wfm_gate"]
-    for TwoS in (5, 7):
+    for TwoS in (4, 5, 6, 7):
         args = (TwoS, 1.0, -0.3, 0.05, 0.0, 0.0, 1)
         h, tnn, tnnn = gate.get_hblocks(*args, the_dist=1)
         hb, tb, _ = configs.cicc_blocks(*args, 1)

@@ -34,9 +34,9 @@ def _random_chain(n, M, scalar, seed):
     return h, tnn
 
 
-@pytest.mark.parametrize("n", [72, 128])
+@pytest.mark.parametrize("n", [50, 72, 98, 128])
 def test_reference_goldens_two_large_spins(n):
-    """the reference's own R/T for two spin-5/2 (n = 72) and spin-7/2 (n = 128) impurities; the blocks come from
+    """the reference's own R/T for two spin-2 (n = 50), 5/2 (72), 3 (98) and 7/2 (128) impurities; the blocks come from
     configs.cicc_blocks, which the generating script holds bit-equal to run_wfm_gate.get_hblocks"""
     g = load_golden("cicc_builder_n%d.npz" % n)
     a = g["builder_args"]

@@ -80,6 +80,20 @@ def test_closed_lead_goldens_dense_and_rgf(name):
     assert rt_err(T2, g["T"]) < 1e-11 and rt_err(R2, g["R"]) < 1e-11
 
 
+@pytest.mark.parametrize("n", [50, 72, 98, 128])
+def test_rgf_oracle_against_reference_goldens_of_large_spins(n):
+    """two spin-2 ... spin-7/2 impurities (run_wfm_gate.get_hblocks, n_loc_dof = 50 ... 128): the recursive oracle against
+    the live reference's R/T; the blocks are rebuilt by configs.cicc_blocks (held bit-equal to the reference's by the
+    generating script, oracle/make_golden_r2.py cicc_large_spins)"""
+    from transport_b200 import configs
+    g = load_golden("cicc_builder_n%d.npz" % n)
+    a = g["builder_args"]
+    h, tnn, tnnn = configs.cicc_blocks(int(a[0]), a[1], a[2], a[3], a[4], a[5], int(a[6]), int(g["the_dist"]))
+    assert h.shape[-1] == n and not np.any(tnnn)
+    R, T = rgf_oracle.transmission_closed(h, tnn, g["Es"], g["sources"])
+    assert rt_err(T, g["T"]) < 1e-10 and rt_err(R, g["R"]) < 1e-10
+
+
 def test_nondiag_lead_selfenergies():
     g = load_golden("nondiag_lead_hop_n4.npz")
     SL, SR = rgf_oracle.closed_selfenergies(g["h"], g["tnn"], g["Es"])
