@@ -266,13 +266,65 @@ __device__ inline double cta_reduce_max(double m) {
 // the ceil(tiles / 4) strips (n = 72: 9 tiles as 3 + 3 + 3 instead of 4 + 4 + 1).  More, narrower strips that would fill the
 // warps better were measured and lose: every strip re-reads the A fragments of its tile row from L2, and operand fetch, not
 // warp balance, binds these products (n = 104 with strips of 2: 389 ms against 308 ms for the cfg4 workload).
+// One strip of NTT tiles (compile time: ncu showed the `u < nt` predicates around the DMMAs and the guarded prefetch as a
+// third of the instructions, each predicate a BSSY / BSYNC / WARPSYNC around an mma.sync); the last k-step is peeled, so
+// the loop body prefetches unconditionally.
+template <int NTT>
+__device__ __forceinline__ void gemm_rt_strip(cd* pc, const cd* __restrict__ pa, const cd* __restrict__ pb, int n, long long kstep,
+                                              double sgn, bool accumulate, double cscale) {
+    double re[NTT][2], im[NTT][2];
+#pragma unroll
+    for (int u = 0; u < NTT; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
+    cd a = *pa;
+    cd b[NTT];
+#pragma unroll
+    for (int u = 0; u < NTT; ++u) b[u] = pb[u * 8];
+    auto kstep_mma = [&](const cd ac, const cd (&bc)[NTT]) {
+#pragma unroll
+        for (int u = 0; u < NTT; ++u) {
+            dmma844(re[u], ac.x, bc[u].x);
+            dmma844(im[u], ac.x, bc[u].y);
+        }
+#pragma unroll
+        for (int u = 0; u < NTT; ++u) {
+            dmma844(re[u], -ac.y, bc[u].y);
+            dmma844(im[u], ac.y, bc[u].x);
+        }
+    };
+    for (int k = 4; k < n; k += 4) {
+        const cd ac = a;
+        cd bc[NTT];
+#pragma unroll
+        for (int u = 0; u < NTT; ++u) bc[u] = b[u];
+        pa += 4;
+        pb += kstep;
+        a = *pa;
+#pragma unroll
+        for (int u = 0; u < NTT; ++u) b[u] = pb[u * 8];
+        kstep_mma(ac, bc);
+    }
+    kstep_mma(a, b);
+#pragma unroll
+    for (int u = 0; u < NTT; ++u) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+            if (accumulate) {
+                const cd c0 = pc[u * 8 + i];
+                v.x = fma(cscale, c0.x, v.x);
+                v.y = fma(cscale, c0.y, v.y);
+            }
+            pc[u * 8 + i] = v;
+        }
+    }
+}
+
 __device__ inline void cta_gemm_dmma_nn_rt(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, int n, double sgn,
                                            bool accumulate, double cscale) {
-    constexpr int NT = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int tiles = n >> 3;
-    const int strips = (tiles + NT - 1) / NT;
+    const int strips = (tiles + 3) >> 2;
     const int base = tiles / strips, rem = tiles - base * strips;   // strip s holds base + (s < rem) tiles
     const long long kstep = 4LL * n;
     for (int item = warp; item < tiles * strips; item += nwarps) {
@@ -280,56 +332,14 @@ __device__ inline void cta_gemm_dmma_nn_rt(cd* C, const cd* __restrict__ A, cons
         const int tr = trow << 3;
         const int tc0 = s * base + min(s, rem);
         const int nt = base + (s < rem ? 1 : 0);
-        double re[NT][2], im[NT][2];
-#pragma unroll
-        for (int u = 0; u < NT; ++u) re[u][0] = re[u][1] = im[u][0] = im[u][1] = 0.0;
         const cd* pa = A + (long long)(tr + g) * n + t;              // A[tr+g][k+t], k += 4
         const cd* pb = B + (long long)t * n + (tc0 << 3) + g;        // B[k+t][(tc0+u)*8+g], k += 4
-        cd a = *pa;
-        cd b[NT];
-#pragma unroll
-        for (int u = 0; u < NT; ++u) b[u] = (u < nt) ? pb[u * 8] : mk(0.0, 0.0);
-        for (int k = 0; k < n; k += 4) {
-            const cd ac = a;
-            cd bc[NT];
-#pragma unroll
-            for (int u = 0; u < NT; ++u) bc[u] = b[u];
-            if (k + 4 < n) {
-                pa += 4;
-                pb += kstep;
-                a = *pa;
-#pragma unroll
-                for (int u = 0; u < NT; ++u)
-                    if (u < nt) b[u] = pb[u * 8];
-            }
-#pragma unroll
-            for (int u = 0; u < NT; ++u)
-                if (u < nt) {
-                    dmma844(re[u], ac.x, bc[u].x);
-                    dmma844(im[u], ac.x, bc[u].y);
-                }
-#pragma unroll
-            for (int u = 0; u < NT; ++u)
-                if (u < nt) {
-                    dmma844(re[u], -ac.y, bc[u].y);
-                    dmma844(im[u], ac.y, bc[u].x);
-                }
-        }
         cd* pc = C + (long long)(tr + g) * n + (tc0 << 3) + 2 * t;
-#pragma unroll
-        for (int u = 0; u < NT; ++u) {
-            if (u < nt) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    cd v = mk(sgn * re[u][i], sgn * im[u][i]);
-                    if (accumulate) {
-                        const cd c0 = pc[u * 8 + i];
-                        v.x = fma(cscale, c0.x, v.x);
-                        v.y = fma(cscale, c0.y, v.y);
-                    }
-                    pc[u * 8 + i] = v;
-                }
-            }
+        switch (nt) {                                                // warp-uniform
+            case 4: gemm_rt_strip<4>(pc, pa, pb, n, kstep, sgn, accumulate, cscale); break;
+            case 3: gemm_rt_strip<3>(pc, pa, pb, n, kstep, sgn, accumulate, cscale); break;
+            case 2: gemm_rt_strip<2>(pc, pa, pb, n, kstep, sgn, accumulate, cscale); break;
+            default: gemm_rt_strip<1>(pc, pa, pb, n, kstep, sgn, accumulate, cscale); break;
         }
     }
     __syncthreads();
