@@ -24,6 +24,9 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 # the CSV holds one table per profiled launch, each introduced by a "Kernel Name" style preamble line
 tables, cur, last = [], None, -1
 for row in csv.reader(io.StringIO(raw)):
+    if row and row[0] == "Kernel Name":          # preamble of the next profiled launch
+        cur = None
+        continue
     if row and row[0] == "Address":
         hdr = row
         continue

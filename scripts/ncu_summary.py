@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep: key metrics + per-opcode instruction/stall breakdown.
-usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [out.csv]"""
+usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [out.csv] [launch_index]"""
 import collections
 import csv
 import io
@@ -10,7 +10,8 @@ import sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr, units, vals = rows[0], rows[1], rows[2 + launch]
 keep = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
@@ -36,10 +37,15 @@ ix = {h: i for i, h in enumerate(hdr)}
 ops, samp = collections.Counter(), collections.Counter()
 ti = ts = 0
 last_addr = -1
-for r in rows[2:]:
-    if len(r) < len(hdr):
+seen = -1                                  # index of the profiled launch whose table is being read
+for r in rows:
+    if r and r[0] == "Kernel Name":        # preamble of the next profiled launch
+        seen += 1
+        last_addr = -1
         continue
-    try:                                   # the page repeats every profiled launch (and each one twice): first table only
+    if seen != launch or len(r) < len(hdr):
+        continue
+    try:                                   # (older reports repeat a launch's table: first copy only)
         addr = int(r[ix['Address']], 16)
     except ValueError:
         continue
