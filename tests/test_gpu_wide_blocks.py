@@ -170,6 +170,32 @@ def test_padded_block_edge_with_affine_family_sources_and_spin_sums():
     assert rt_err(T1, T) < RTOL and rt_err(R1, R) < RTOL
 
 
+@pytest.mark.parametrize("n", [96, 104])
+def test_tma_staged_operand_of_the_wide_products(n):
+    """n = 96 ... 104: the run-time-n product stages its B operand in shared memory by TMA (tx_set_option(5, .)); same
+    results as with fragments straight from L2, for the sweep and for the Sancho-Rubio lead tables"""
+    M = 5
+    h, tnn = _random_chain(n, M, True, n + 5)
+    Es = np.array([-1.4, 0.3, 1.2], dtype=complex)
+    srcs = np.eye(n)[[1, n - 1]]
+    hr, tr, _ = configs.ribbon_blocks(width=n, L=4, W=0.5, seed=2)
+    lib = _lib.load()
+    out = []
+    try:
+        for mode in (1, 0):
+            _lib.check(lib.tx_set_option(5, mode))
+            R, T, car = transmission_sweep(h, tnn, Es, sources=srcs, want_caroli=True)
+            SL, SR = leads.self_energies_batched(hr, tr, Es, ("sancho", 1e-4, 1e-14))
+            out.append((R, T, car, SL, SR))
+    finally:
+        _lib.check(lib.tx_set_option(5, 1))
+    oR, oT = rgf_oracle.transmission_closed(h, tnn, Es, srcs)
+    for R, T, car, SL, SR in out:
+        assert rt_err(T[0], oT) < RTOL and rt_err(R[0], oR) < RTOL
+    for a, b in zip(out[0], out[1]):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
 def test_green_blocks_wide():
     """first block column and full Green's function at n = 72 (work blocks in shared memory) and n = 96 (global scratch)"""
     for n in (72, 96):

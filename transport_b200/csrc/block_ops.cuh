@@ -36,7 +36,9 @@ struct GemmEpi {
     double* tmax = nullptr;
     bool reuse_staged = false;     // B is the block the previous product staged: no copy, no wait
 };
-__host__ __device__ inline size_t tma_stage_bytes(int n) { return (size_t)n * TMA_LD * sizeof(cd); }
+// staging block of an n x n operand: rows padded to n + 2 elements (n % 8 == 0: the DMMA fragment reads of the four k-rows
+// of a step then fall into disjoint bank groups); n = 64: TMA_LD
+__host__ __device__ inline size_t tma_stage_bytes(int n) { return (size_t)n * (n + 2) * sizeof(cd); }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_stage_init(TmaStage& ts, cd* buf, unsigned long long* bar) {
@@ -260,6 +262,42 @@ __device__ inline double cta_reduce_max(double m) {
     return r;
 }
 
+// Where the run-time-n product stages its B operand (cfg4 workload, Sancho-Rubio leads + sweep, staged vs fragments from L2):
+// n = 56: 46.0 vs 45.2 ms, 72: 101.8 vs 97.4, 96: 208.5 vs 213.3, 104: 271.5 vs 283.8 -- the copy sits at the head of every
+// product with nothing to overlap it (one CTA per SM), so it only pays once a product is long enough; beyond n = 104 the
+// staging block does not fit next to the kernels' static shared memory.
+__host__ __device__ inline bool tma_stage_pays(int n) { return (n & 7) == 0 && n >= 96 && n <= TX_STAGE_SMEM_MAX_N; }
+
+// Bring the n x n block B (global memory, n % 8 == 0) into the staging block with rows padded to n + 2 elements: one bulk
+// copy per row issued by the lanes of warp 0, completion on the mbarrier; every thread of the CTA returns once the block
+// has landed.  (Run-time-n counterpart of the prologue of cta_gemm_dmma_nn_tma.)
+__device__ inline void tma_stage_load(TmaStage& ts, const cd* __restrict__ B, int n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ld = n + 2;
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(ts.bar)), "r"((unsigned)(n * n * sizeof(cd)))
+                         : "memory");
+        __syncwarp();
+        for (int r = lane; r < n; r += 32)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(ts.buf + r * ld)),
+                         "l"(B + (long long)r * n), "r"((unsigned)(n * sizeof(cd))), "r"(smem_u32(ts.bar))
+                         : "memory");
+    }
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {   // bounded: a lost copy must not hang the GPU
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(ts.bar)), "r"(ts.parity)
+                     : "memory");
+        if (spin > (1 << 24)) __trap();
+    }
+    ts.parity ^= 1u;
+}
+
 // Run-time size, no transposes (every product of the telescoped sweep and of the decimation at n != 64): per-lane operand
 // pointers advanced by constants instead of re-deriving r * n + c behind an op switch for every fragment (the index
 // arithmetic was 39 % of the instructions of the generic routine), and the column tiles of a tile row are split EVENLY over
@@ -319,21 +357,30 @@ __device__ __forceinline__ void gemm_rt_strip(cd* pc, const cd* __restrict__ pa,
     }
 }
 
+// `ts`: stage B in shared memory first (TMA), so that only the A fragments -- one load per k-step and lane instead of up to
+// five -- come from L2 (ncu on the n = 72 lead kernel: 23 % of all stall samples were DMMAs waiting for L2 operands).
 __device__ inline void cta_gemm_dmma_nn_rt(cd* C, const cd* __restrict__ A, const cd* __restrict__ B, int n, double sgn,
-                                           bool accumulate, double cscale) {
+                                           bool accumulate, double cscale, TmaStage* ts = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int tiles = n >> 3;
     const int strips = (tiles + 3) >> 2;
     const int base = tiles / strips, rem = tiles - base * strips;   // strip s holds base + (s < rem) tiles
-    const long long kstep = 4LL * n;
+    long long kstep = 4LL * n;
+    int ldb = n;
+    if (ts != nullptr) {
+        tma_stage_load(*ts, B, n);
+        B = ts->buf;
+        ldb = n + 2;
+        kstep = 4LL * ldb;
+    }
     for (int item = warp; item < tiles * strips; item += nwarps) {
         const int trow = item / strips, s = item - trow * strips;
         const int tr = trow << 3;
         const int tc0 = s * base + min(s, rem);
         const int nt = base + (s < rem ? 1 : 0);
         const cd* pa = A + (long long)(tr + g) * n + t;              // A[tr+g][k+t], k += 4
-        const cd* pb = B + (long long)t * n + (tc0 << 3) + g;        // B[k+t][(tc0+u)*8+g], k += 4
+        const cd* pb = B + (long long)t * ldb + (tc0 << 3) + g;      // B[k+t][(tc0+u)*8+g], k += 4
         cd* pc = C + (long long)(tr + g) * n + (tc0 << 3) + 2 * t;
         switch (nt) {                                                // warp-uniform
             case 4: gemm_rt_strip<4>(pc, pa, pb, n, kstep, sgn, accumulate, cscale); break;
@@ -363,7 +410,7 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
         }
     } else {
         if (opA == OP_N && opB == OP_N) {
-            cta_gemm_dmma_nn_rt(C, A, B, n, sgn, accumulate, cscale);
+            cta_gemm_dmma_nn_rt(C, A, B, n, sgn, accumulate, cscale, ts);
             return;
         }
     }

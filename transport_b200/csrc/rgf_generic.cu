@@ -43,12 +43,12 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     if constexpr (NMAX > TX_STAGE_SMEM_MAX_N)
         if (p.work && !inverse_stage_in_smem(n)) stage = base + GEN_MATS * nn;
     TmaStage tma_stage;
-    TmaStage* ts = nullptr;   // n = 64: the products stage their B operand through the same block by TMA (block_ops.cuh)
-    if constexpr (FIXN == 64)
-        if (stage != nullptr && p.use_tma) {
-            tma_stage_init(tma_stage, stage, &s_tma_bar);
-            ts = &tma_stage;
-        }
+    TmaStage* ts = nullptr;   // the products stage their B operand through the same block by TMA (block_ops.cuh)
+    // (the staging block must be the shared-memory one; other edges: multiples of 8 run the run-time-n staged product)
+    if (stage != nullptr && p.use_tma && (FIXN == 64 || tma_stage_pays(n))) {
+        tma_stage_init(tma_stage, stage, &s_tma_bar);
+        ts = &tma_stage;
+    }
     for (long long pt = blockIdx.x; pt < p.n_pts; pt += gridDim.x) {
     const int ham = (int)(pt / p.nE);
     const int e = (int)(pt - (long long)ham * p.nE);
@@ -366,7 +366,7 @@ static int generic_resident_ctas(size_t smem, int kind) {
 // dynamic shared memory when the blocks live in the global workspace: inverse staging and the TMA-staged product operand
 static size_t generic_stage_bytes(int n) {
     size_t b = inverse_stage_in_smem(n) ? inverse_stage_bytes(n) : 0;
-    if (n == 64 && tma_stage_bytes(n) > b) b = tma_stage_bytes(n);
+    if ((n == 64 || tma_stage_pays(n)) && tma_stage_bytes(n) > b) b = tma_stage_bytes(n);
     return b;
 }
 

@@ -256,11 +256,10 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
     __shared__ unsigned long long s_tma_bar;
     TmaStage tma_stage;
     TmaStage* ts = nullptr;
-    if constexpr (FIXN == 64)
-        if (stage != nullptr && p.use_tma) {
-            tma_stage_init(tma_stage, stage, &s_tma_bar);
-            ts = &tma_stage;
-        }
+    if (stage != nullptr && p.use_tma && (FIXN == 64 || tma_stage_pays(n))) {
+        tma_stage_init(tma_stage, stage, &s_tma_bar);
+        ts = &tma_stage;
+    }
     cd* m0 = base;               // g / result
     cd* m1 = base + nn;
     cd* m2 = base + 2 * nn;
@@ -476,7 +475,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) gemm_bench_kernel(const cd* __r
     const long long off = (long long)blockIdx.x * n * n;
     TmaStage tma_stage;
     TmaStage* ts = nullptr;
-    if (use_tma && n == 64) {
+    if (use_tma) {
         tma_stage_init(tma_stage, reinterpret_cast<cd*>(gf_smem), &s_bar);
         ts = &tma_stage;
     }
@@ -555,7 +554,7 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     size_t scratch_bytes = 0;
     if (bytes > 200 * 1024) {
         smem = inverse_stage_in_smem(n) ? inverse_stage_bytes(n) : 0;          // staging block for the inverse
-        if (n == 64 && tma_stage_bytes(n) > smem) smem = tma_stage_bytes(n);   // ... and for the TMA-staged product operand
+        if ((n == 64 || tma_stage_pays(n)) && tma_stage_bytes(n) > smem) smem = tma_stage_bytes(n);   // ... and the TMA-staged product operand
         p.scratch_per = (long long)mats * n * n + (inverse_stage_in_smem(n) ? 0 : (long long)n * (n + 1));
         scratch_bytes = (size_t)p.scratch_per * sizeof(cd);
     }
@@ -793,7 +792,7 @@ int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out) { return gemm_b
 int tx_debug_gemm_tma_ms(int n, int count, int reps, double* ms_out) { return gemm_bench(n, count, reps, 1, ms_out); }
 static int gemm_bench(int n, int count, int reps, int use_tma, double* ms_out) {
     if (n < 8 || n > 64 || count < 1 || reps < 1 || !ms_out) return fail(TX_ERR_ARG, "bad arguments");
-    if (use_tma && n != 64) return fail(TX_ERR_ARG, "the TMA-staged product is the n = 64 path");
+    if (use_tma && ((n & 7) || !inverse_stage_in_smem(n))) return fail(TX_ERR_ARG, "the TMA-staged product needs n % 8 == 0 and n <= 104");
     const size_t smem = use_tma ? tma_stage_bytes(n) : 0;
     if (smem) TX_CUDA(cudaFuncSetAttribute(gemm_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t bytes = (size_t)count * n * n * sizeof(cd);
