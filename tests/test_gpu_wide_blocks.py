@@ -196,6 +196,19 @@ def test_tma_staged_operand_of_the_wide_products(n):
         assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("n", [24, 50, 72])
+def test_all_one_hot_sources_shortcut_equals_explicit_sources(n):
+    """sources=None (every channel as a one-hot source: O(n) per source in the epilogue) against the same sources passed
+    explicitly (general superposition path), all outputs"""
+    h, tnn = _random_chain(n, 4, True, n + 9)
+    Es = np.array([-1.1, 0.6], dtype=complex)
+    a = transmission_sweep(h, tnn, Es, want_resid=True, want_total=True, want_spin=4)
+    b = transmission_sweep(h, tnn, Es, sources=np.eye(n), want_resid=True, want_total=True, want_spin=4)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and np.allclose(x, y, rtol=1e-13, atol=1e-15)
+    assert np.max(np.abs(a[2])) < UNIT
+
+
 def test_green_blocks_wide():
     """first block column and full Green's function at n = 72 (work blocks in shared memory) and n = 96 (global scratch)"""
     for n in (72, 96):

@@ -223,10 +223,16 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     if (p.R || p.ttot || p.gather.n || p.resid || p.spin) {
         for (int i = 0; i < p.n_src; ++i) {
             double f2 = 0.0, wu = 0.0, wd = 0.0;   // wu, wd: incident weight per electron-spin sector
-            for (int c = 0; c < nr; ++c) {
-                const double a = p.sources ? p.sources[(long long)i * nr + c] : (c == i ? 1.0 : 0.0);
-                f2 = fma(a, a * s_vL[c], f2);
-                if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
+            if (p.sources) {
+                for (int c = 0; c < nr; ++c) {
+                    const double a = p.sources[(long long)i * nr + c];
+                    f2 = fma(a, a * s_vL[c], f2);
+                    if (c < p.n_up) wu = fma(a, a, wu); else wd = fma(a, a, wd);
+                }
+            } else {                               // one-hot source i: O(n) per source instead of O(n^2)
+                f2 = s_vL[i];
+                wu = i < p.n_up ? 1.0 : 0.0;
+                wd = 1.0 - wu;
             }
             const bool src_up = wu >= wd;
             double sp[4] = {0.0, 0.0, 0.0, 0.0};               // T same / other sector, R same / other (emit_spin)
@@ -234,15 +240,25 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
             double part = 0.0;
             for (int s = threadIdx.x; s < nr; s += blockDim.x) {
                 double ur = 0, ui = 0, wr = 0, wi = 0, mine = 0;
-                for (int c = 0; c < nr; ++c) {
-                    const double a = p.sources ? p.sources[(long long)i * nr + c] : (c == i ? 1.0 : 0.0);
-                    const double av = a * s_vL[c];
-                    const cd g = G[s * n + c], w = W[s * n + c];
-                    ur = fma(g.x, av, ur);
-                    ui = fma(g.y, av, ui);
-                    wr = fma(w.x, av, wr);
-                    wi = fma(w.y, av, wi);
-                    if (c == s) mine = a;
+                if (p.sources) {
+                    for (int c = 0; c < nr; ++c) {
+                        const double a = p.sources[(long long)i * nr + c];
+                        const double av = a * s_vL[c];
+                        const cd g = G[s * n + c], w = W[s * n + c];
+                        ur = fma(g.x, av, ur);
+                        ui = fma(g.y, av, ui);
+                        wr = fma(w.x, av, wr);
+                        wi = fma(w.y, av, wi);
+                        if (c == s) mine = a;
+                    }
+                } else {
+                    const double av = s_vL[i];
+                    const cd g = G[s * n + i], w = W[s * n + i];
+                    ur = fma(g.x, av, 0.0);
+                    ui = fma(g.y, av, 0.0);
+                    wr = fma(w.x, av, 0.0);
+                    wi = fma(w.y, av, 0.0);
+                    mine = (s == i) ? 1.0 : 0.0;
                 }
                 const double fr = sqrt(s_vL[s]) * rflux, ft = sqrt(s_vR[s]) * rflux;
                 const double xr = (-ui - mine) * fr, xi = ur * fr;
