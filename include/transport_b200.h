@@ -362,7 +362,7 @@ int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double
  *   option 3: eigenvalue kernel of the Bardeen path: 0 (default) picks by batch size, 1 a warp per eigenvalue
  *             (multisection, shortest critical path), 2 a lane per eigenvalue (bracketed interpolation, least arithmetic; chosen
  *             automatically from 2048 state slots per call).  Process-wide only.
- *   option 5: n = 64 blocks in the global workspace: value != 0 (default) stages the B operand of every product in shared
+ *   option 5: n = 64 and 96 <= n <= 104 blocks in the global workspace: value != 0 (default) stages the B operand of every product in shared
  *             memory with the TMA engine (cp.async.bulk + mbarrier), 0 reads all fragments straight from L2 (A/B runs).
  *             Process-wide only.
  *   option 4: kernel of the 5 <= n <= 8, scalar-hopping sweep (= tx_set_variant):
@@ -384,7 +384,7 @@ int tx_debug_invert(const tx_cplx* in, tx_cplx* out, int count, int n);
 int tx_debug_invert_staged(const tx_cplx* in, tx_cplx* out, int count, int n);
 /* Measurement hook: device time of `count` CTAs each doing `reps` n x n complex products on global-memory blocks. */
 int tx_debug_gemm_ms(int n, int count, int reps, double* ms_out);
-/* The same with the B operand staged in shared memory by TMA (cp.async.bulk + mbarrier; n = 64 only). */
+/* The same with the B operand staged in shared memory by TMA (cp.async.bulk + mbarrier; n a multiple of 8). */
 int tx_debug_gemm_tma_ms(int n, int count, int reps, double* ms_out);
 /* Device time in ms of the last tx_debug_invert_staged kernel launch (CUDA events; measurement hook). */
 double tx_debug_last_invert_ms(void);

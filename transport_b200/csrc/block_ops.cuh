@@ -853,7 +853,7 @@ __device__ inline void cta_inverse_staged(cd* X, cd* S, int n, cd* colk, int* ip
         else cta_inverse(X, n, colk, ipiv, singular);
         return;
     }
-    // (NMAX = 64: every caller runs 256 threads; the wider instantiation is also asked for n <= 64 never, but checks)
+    // (NMAX = 64: every caller runs 256 threads; the 512-thread instantiation checks its thread count)
     if ((n & 7) == 0 && n >= 16 && n <= NMAX && (NMAX == 64 || 4 * n <= (int)blockDim.x)) {
         cta_inverse_blocked<NMAX>(X, S, n, singular);
         return;
