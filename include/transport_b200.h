@@ -241,6 +241,22 @@ int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cp
                       double imE, double conv_tol, int conv_rep, int min_iter, int max_iter,
                       tx_cplx* g, tx_cplx* sigma, int* n_iter, double* conv, int* converged,
                       int* singular_flag, void* stream);
+
+/*
+ * Both semi-infinite continuations of ONE periodic lead from a single Sancho-Rubio decimation: the right lead (side +1,
+ * g_R = (z - h00 - h01 g_R h01^dag)^-1, Sigma_R = h01 g_R h01^dag) and the left lead (side -1,
+ * g_L = (z - h00 - h01^dag g_L h01)^-1, Sigma_L = h01^dag g_L h01), z = E + i imE.  The decimation carries the bulk block
+ * h00 + sum (alpha G beta + beta G alpha) and one surface block h00 + sum alpha G beta; the other surface block is their
+ * difference plus h00, so a junction whose two leads are the same material (wfm.SelfEnergies, wfm/__init__.py:283-287, calls
+ * its converger once per lead) costs one decimation instead of two.  Every output may be NULL; n_iter / conv / converged
+ * [nE] as in tx_surface_gf.  The host sweep entry uses it by itself when TX_LEAD_SANCHO meets identical lead blocks.
+ */
+int tx_surface_gf_pair(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, double imE, double conv_tol,
+                       int max_iter, tx_cplx* gL, tx_cplx* sigL, tx_cplx* gR, tx_cplx* sigR, int* n_iter, double* conv,
+                       int* converged);
+int tx_surface_gf_pair_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, double imE, double conv_tol,
+                           int max_iter, tx_cplx* gL, tx_cplx* sigL, tx_cplx* gR, tx_cplx* sigR, int* n_iter, double* conv,
+                           int* converged, int* singular_flag, void* stream);
 /* One fixed-point step, wfm.g_ith (:532-551): ith = 0 -> inv(z - h00); else inv(z - h00 - t g_prev t^dag). */
 int tx_g_ith(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, int side, double imE,
              int ith, const tx_cplx* g_prev, tx_cplx* g_out);

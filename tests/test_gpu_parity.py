@@ -415,6 +415,42 @@ def test_ribbon_sancho_leads_cfg4_downscaled():
             assert np.allclose(car[0], open_ch, atol=1e-4)      # clean ribbon: T = number of open channels
 
 
+@pytest.mark.parametrize("n", [3, 24, 64, 72])
+def test_one_decimation_yields_both_lead_surfaces(n):
+    """tx_surface_gf_pair: the left and right continuations of one periodic lead from a single Sancho-Rubio decimation
+    (other surface block = bulk + h00 - surface) against the two independent decimations, the numpy oracle and the
+    fixed-point maps of both sides (wfm/__init__.py:547-551); general complex hopping, not just ribbons"""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    h00 = 0.4 * (A + A.conj().T) / 2 / np.sqrt(n)
+    t = -np.eye(n) + 0.2 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    Es = np.array([-1.3, 0.1, 0.9], dtype=complex)
+    eta = 1e-3
+    gL, gR, sL, sR, conv, nit, ok = leads.surface_gf_pair(h00, t, Es, imE=eta, conv_tol=1e-14, want_g=True)
+    assert ok.all()
+    for side, g, sig in ((-1, gL, sL), (1, gR, sR)):
+        ((g1, s1), _, _, ok1) = leads.surface_gf(h00, t, Es, side, _lib.TX_GF_SANCHO, imE=eta, conv_tol=1e-14, max_iter=200,
+                                                 full=True, want_sigma=True)
+        assert ok1.all()
+        # (two correct decimations differ by round-off amplified by |G|^2 ~ 1/eta^2: 5e-11 here)
+        assert np.abs(g - g1).max() < 1e-9 * np.abs(g1).max() and np.abs(sig - s1).max() < 1e-9 * np.abs(s1).max()
+        go, _ = rgf_oracle.sancho_rubio(h00, t, Es + 1j * eta, side)
+        assert np.abs(g - go).max() < 1e-9 * np.abs(go).max()
+        for i, E in enumerate(Es):
+            step = wfm_oracle.g_ith(h00, t, E, side, eta, 1, g[i])
+            assert np.linalg.norm(step - g[i]) < 1e-9 * np.linalg.norm(g[i])
+    # identical lead blocks: the host sweep and self_energies_batched take the single decimation by themselves
+    M = 4
+    h = np.array([h00] * M)
+    h[1:-1] += 0.1 * np.eye(n)
+    tnn = np.array([t] * (M - 1))
+    SL, SR = leads.self_energies_batched(h, tnn, Es, ("sancho", eta, 1e-14))
+    assert np.array_equal(SL, sL) and np.array_equal(SR, sR)
+    car = transmission_sweep(h, tnn, Es, ("sancho", eta), sources=np.eye(n)[:1], want_rt=False, want_caroli=True)
+    car_t = transmission_sweep(h, tnn, Es, "table", sigL=sL, sigR=sR, sources=np.eye(n)[:1], want_rt=False, want_caroli=True)
+    assert np.allclose(car, car_t, rtol=1e-12, atol=1e-14)
+
+
 def test_all_kernel_variants_agree():
     """Every kernel of the n=8 sweep (register-resident, plain DMMA, telescoped) gives the golden answer;
     the DMMA kernel is also exercised with padding (n=5..7), table leads and mixed Hamiltonians per warp."""

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "tx_peer_barrier_dev": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "tx_surface_gf": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
                               _P, _P, _P, _P, _P]),
+    "tx_surface_gf_pair": (c_int, [_P, _P, c_int, _P, c_int, c_double, c_double, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "tx_surface_gf_pair_dev": (c_int, [_P, _P, c_int, _P, c_int, c_double, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tx_surface_gf_dev": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int,
                                   _P, _P, _P, _P, _P, _P, _P]),
     "tx_g_ith": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_double, c_int, _P, _P]),

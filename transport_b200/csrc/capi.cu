@@ -919,12 +919,23 @@ int tx_transmission_sweep_spin(tx_context* ctx, const tx_cplx* h, int n_h, const
         const double imE = gf_mode == TX_GF_CLOSED ? 0.0 : ws.lead_imE;
         const tx_cplx* dh = (const tx_cplx*)ws.h.ptr;
         const tx_cplx* dt = (const tx_cplx*)ws.tnn.ptr;
-        rc = tx_surface_gf_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, -1, gf_mode, imE, ws.lead_tol, 0, 0, ws.lead_max_iter, nullptr,
-                               (tx_cplx*)ws.sigL.ptr, nitL, nullptr, okL, (int*)ws.flag.ptr, st);
-        if (rc) return rc;
-        rc = tx_surface_gf_dev(dh + lead_off_R, dt + hop_off_R, n, (const tx_cplx*)ws.E.ptr, nE, 1, gf_mode, imE, ws.lead_tol, 0, 0,
-                               ws.lead_max_iter, nullptr, (tx_cplx*)ws.sigR.ptr, nitR, nullptr, okR, (int*)ws.flag.ptr, st);
-        if (rc) return rc;
+        // both leads the same material (the usual junction): one decimation yields both surfaces
+        const bool same_leads = gf_mode == TX_GF_SANCHO && !memcmp(h, h + lead_off_R, nn * sizeof(tx_cplx)) &&
+                                !memcmp(tnn, tnn + hop_off_R, nn * sizeof(tx_cplx));
+        if (same_leads) {
+            rc = tx_surface_gf_pair_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, imE, ws.lead_tol, ws.lead_max_iter, nullptr,
+                                        (tx_cplx*)ws.sigL.ptr, nullptr, (tx_cplx*)ws.sigR.ptr, nitL, nullptr, okL, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+            TX_CUDA(cudaMemcpyAsync(nitR, nitL, (size_t)nE * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            TX_CUDA(cudaMemcpyAsync(okR, okL, (size_t)nE * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        } else {
+            rc = tx_surface_gf_dev(dh, dt, n, (const tx_cplx*)ws.E.ptr, nE, -1, gf_mode, imE, ws.lead_tol, 0, 0, ws.lead_max_iter, nullptr,
+                                   (tx_cplx*)ws.sigL.ptr, nitL, nullptr, okL, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+            rc = tx_surface_gf_dev(dh + lead_off_R, dt + hop_off_R, n, (const tx_cplx*)ws.E.ptr, nE, 1, gf_mode, imE, ws.lead_tol, 0, 0,
+                                   ws.lead_max_iter, nullptr, (tx_cplx*)ws.sigR.ptr, nitR, nullptr, okR, (int*)ws.flag.ptr, st);
+            if (rc) return rc;
+        }
         n_sig_use = 1;
         lead_mode = TX_LEAD_TABLE;
     }

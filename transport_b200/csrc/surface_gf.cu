@@ -29,6 +29,8 @@ struct GfParams {
     const cd* E;        // [nE]
     cd* g;              // [nE][n][n] or null
     cd* sigma;          // [nE][n][n] or null:  side=-1: h01^dag g h01 ; side=+1: h01 g h01^dag
+    cd* g2;             // SANCHO only: the OTHER semi-infinite continuation of the same lead (side -p.side), or null
+    cd* sigma2;         //   ... and its self-energy, or null
     const cd* g_prev;   // g_ith only
     int* n_iter;        // [nE] or null
     double* conv;       // [nE] or null
@@ -69,9 +71,9 @@ __device__ cd ricemele_channel(const cd* diag, const cd* off, int n, int s, cd E
 
 // sigma = h01^dag g h01 (side=-1)  or  h01 g h01^dag (side=+1)
 template <int FIXN>
-__device__ void emit_sigma(const GfParams& p, const cd* g, cd* tmp, cd* out) {
+__device__ void emit_sigma(const GfParams& p, int side, const cd* g, cd* tmp, cd* out) {
     const int n = p.n;
-    if (p.side == -1) {
+    if (side == -1) {
         cta_gemm<FIXN>(tmp, g, OP_N, p.h01, OP_N, n);
         cta_gemm<FIXN>(out, p.h01, OP_H, tmp, OP_N, n);
     } else {
@@ -433,6 +435,21 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
                 break;
             }
         }
+        if (p.g2 || p.sigma2) {
+            // The decimation carries both surfaces of the lead: eps = h00 + sum (alpha G beta + beta G alpha) is the bulk
+            // block, epss = h00 + sum alpha G beta this side's surface block, so the surface block of the OTHER
+            // semi-infinite continuation (roles of alpha and beta exchanged) is h00 + sum beta G alpha = eps + h00 - epss:
+            // when both leads of a junction are the same material, one decimation serves both.
+            for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                const cd a = eps[idx], b = p.h00[idx], c = epss[idx];
+                T1[idx] = mk(a.x + b.x - c.x, a.y + b.y - c.y);
+            }
+            __syncthreads();
+            cta_z_minus(m0, z, T1, n);
+            cta_inverse_staged<NMAX>(m0, stage, n, s_colk, s_ipiv, p.singular);
+            if (p.g2) cta_copy(p.g2 + (long long)e * nn, m0, nn);
+            if (p.sigma2) emit_sigma<FIXN>(p, -p.side, m0, T2, p.sigma2 + (long long)e * nn);
+        }
         cta_z_minus(m0, z, epss, n);
         cta_inverse_staged<NMAX>(m0, stage, n, s_colk, s_ipiv, p.singular);
         if (threadIdx.x == 0) {
@@ -443,7 +460,7 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
     }
     (void)s_flag;
     if (p.g) cta_copy(p.g + (long long)e * nn, m0, nn);
-    if (p.sigma) emit_sigma<FIXN>(p, m0, m1, p.sigma + (long long)e * nn);
+    if (p.sigma) emit_sigma<FIXN>(p, p.side, m0, m1, p.sigma + (long long)e * nn);
 }
 
 // Unit-test hook for the CTA-cooperative inverse of block_ops.cuh (staged / blocked path): one CTA per block.
@@ -647,6 +664,95 @@ int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cp
         cudaFree(owned);
     }
     return rc;
+}
+
+// Both semi-infinite continuations of ONE periodic lead (on-site block h00, hopping h01 from a cell to the next) from a
+// single Sancho-Rubio decimation: the right lead (side +1, cells 0, 1, 2, ...: g_R = (z - h00 - h01 g_R h01^dag)^-1) and the
+// left lead (side -1: g_L = (z - h00 - h01^dag g_L h01)^-1).  A junction whose two leads are the same material needs one
+// decimation instead of two (wfm.SelfEnergies, wfm/__init__.py:283-287, calls its converger once per lead).
+int tx_surface_gf_pair_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, double imE, double conv_tol,
+                           int max_iter, tx_cplx* gL, tx_cplx* sigL, tx_cplx* gR, tx_cplx* sigR, int* n_iter, double* conv,
+                           int* converged, int* singular_flag, void* stream) {
+    int rc = check_gf_args(h00, h01, n, E, nE, 1, TX_GF_SANCHO);
+    if (rc) return rc;
+    if (!singular_flag) return fail(TX_ERR_ARG, "singular_flag is required");
+    if (!gL && !sigL && !gR && !sigR) return fail(TX_ERR_ARG, "no output requested");
+    GfParams p{};
+    p.h00 = reinterpret_cast<const cd*>(h00);
+    p.h01 = reinterpret_cast<const cd*>(h01);
+    p.E = reinterpret_cast<const cd*>(E);
+    p.g = reinterpret_cast<cd*>(gR);
+    p.sigma = reinterpret_cast<cd*>(sigR);
+    p.g2 = reinterpret_cast<cd*>(gL);
+    p.sigma2 = reinterpret_cast<cd*>(sigL);
+    p.n_iter = n_iter;
+    p.conv = conv;
+    p.converged = converged;
+    p.singular = singular_flag;
+    p.n = n;
+    p.nE = nE;
+    p.side = 1;
+    p.mode = TX_GF_SANCHO;
+    p.imE = imE;
+    p.conv_tol = conv_tol;
+    p.max_iter = max_iter;
+    p.ith = -1;
+    p.use_tma = g_use_tma;
+    cd* owned = nullptr;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    rc = launch_gf(p, st, &owned);
+    if (owned) {
+        cudaStreamSynchronize(st);
+        cudaFree(owned);
+    }
+    return rc;
+}
+
+int tx_surface_gf_pair(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx* E, int nE, double imE, double conv_tol,
+                       int max_iter, tx_cplx* gL, tx_cplx* sigL, tx_cplx* gR, tx_cplx* sigR, int* n_iter, double* conv,
+                       int* converged) {
+    int rc = check_gf_args(h00, h01, n, E, nE, 1, TX_GF_SANCHO);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(TX_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    const size_t nn = (size_t)n * n, bm = nn * sizeof(cd), bE = ((size_t)nE * sizeof(cd) + 255) & ~(size_t)255;
+    const size_t bg = (size_t)nE * bm, bi = ((size_t)nE * 4 + 255) & ~(size_t)255, bc = ((size_t)nE * 8 + 255) & ~(size_t)255;
+    char* d = nullptr;
+    TX_CUDA(cudaMalloc(&d, 2 * bm + bE + 4 * bg + 2 * bi + bc + 256));
+    auto cleanup = [&](int code) {
+        cudaFree(d);
+        return code;
+    };
+    char* q = d;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    char *dh = take(bm), *dt = take(bm), *dE = take(bE);
+    char* out[4];
+    for (int i = 0; i < 4; ++i) out[i] = take(bg);
+    char *dni = take(bi), *dok = take(bi), *dcv = take(bc), *dflag = take(256);
+    if (cudaMemcpy(dh, h00, bm, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dt, h01, bm, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dE, E, (size_t)nE * sizeof(cd), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemset(dflag, 0, 4) != cudaSuccess)
+        return cleanup(fail(TX_ERR_CUDA, "host to device copy failed"));
+    tx_cplx* host[4] = {gL, sigL, gR, sigR};
+    rc = tx_surface_gf_pair_dev((const tx_cplx*)dh, (const tx_cplx*)dt, n, (const tx_cplx*)dE, nE, imE, conv_tol, max_iter,
+                                gL ? (tx_cplx*)out[0] : nullptr, sigL ? (tx_cplx*)out[1] : nullptr, gR ? (tx_cplx*)out[2] : nullptr,
+                                sigR ? (tx_cplx*)out[3] : nullptr, (int*)dni, (double*)dcv, (int*)dok, (int*)dflag, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc) return cleanup(rc);
+    if (e != cudaSuccess) return cleanup(fail(TX_ERR_CUDA, "surface GF kernel failed: %s", cudaGetErrorString(e)));
+    bool bad = false;
+    for (int i = 0; i < 4; ++i)
+        if (host[i]) bad |= cudaMemcpy(host[i], out[i], bg, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (n_iter) bad |= cudaMemcpy(n_iter, dni, (size_t)nE * 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (conv) bad |= cudaMemcpy(conv, dcv, (size_t)nE * 8, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (converged) bad |= cudaMemcpy(converged, dok, (size_t)nE * 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    int flag = 0;
+    bad |= cudaMemcpy(&flag, dflag, 4, cudaMemcpyDeviceToHost) != cudaSuccess;
+    if (bad) return cleanup(fail(TX_ERR_CUDA, "device to host copy failed"));
+    if (flag) return cleanup(fail(TX_ERR_SINGULAR, "singular block in the surface GF iteration"));
+    return cleanup(TX_OK);
 }
 
 // Host-pointer convenience wrappers ----------------------------------------------------------

@@ -38,6 +38,30 @@ def surface_gf(diag, offdiag, Es, inoutsign, mode, imE=0.0, conv_tol=0.0, conv_r
     return (first,)
 
 
+def surface_gf_pair(diag, offdiag, Es, imE=0.0, conv_tol=SANCHO_TOL, max_iter=SANCHO_MAX_ITER, want_g=False):
+    """Both semi-infinite continuations of one periodic lead (diag, offdiag) from a single Sancho-Rubio decimation
+    (tx_surface_gf_pair): returns (Sigma_L, Sigma_R, conv, n_iter, converged), each Sigma [nE,n,n]; with want_g
+    (g_L, g_R, Sigma_L, Sigma_R, conv, n_iter, converged)."""
+    lib = _lib.load()
+    diag, offdiag = as_c128(diag), as_c128(offdiag)
+    Es = as_c128(np.atleast_1d(Es))
+    n, nE = diag.shape[0], len(Es)
+    if diag.shape != (n, n) or offdiag.shape != (n, n):
+        raise ValueError
+    sigL = np.empty((nE, n, n), dtype=np.complex128)
+    sigR = np.empty_like(sigL)
+    gL = np.empty_like(sigL) if want_g else None
+    gR = np.empty_like(sigL) if want_g else None
+    nit = np.zeros(nE, dtype=np.int32)
+    conv = np.zeros(nE, dtype=np.float64)
+    ok = np.ones(nE, dtype=np.int32)
+    check(lib.tx_surface_gf_pair(ptr(diag), ptr(offdiag), n, ptr(Es), nE, float(imE), float(conv_tol), int(max_iter),
+                                 ptr(gL), ptr(sigL), ptr(gR), ptr(sigR), ptr(nit), ptr(conv), ptr(ok)))
+    if want_g:
+        return gL, gR, sigL, sigR, conv, nit, ok.astype(bool)
+    return sigL, sigR, conv, nit, ok.astype(bool)
+
+
 def g_ith(diag, offdiag, Es, inoutsign, imE, ith, g_prev):
     """One fixed-point step for every energy; g_prev [nE,n,n] (ignored for ith == 0)."""
     lib = _lib.load()
@@ -99,6 +123,13 @@ def self_energies_batched(h, tnn, Es, converger):
     elif mode == _lib.TX_GF_FIXEDPOINT:
         if len(h0) > 2:                                          # :502
             raise NotImplementedError("Iterative diatomic and spin combined not supported")
+    if mode == _lib.TX_GF_SANCHO and np.array_equal(h0, hN) and np.array_equal(t0, tN):
+        # both leads the same material: one decimation carries both surfaces (tx_surface_gf_pair)
+        sigL, sigR, conv, nit, ok = surface_gf_pair(h0, t0, Es, **kw)
+        if not np.all(ok):
+            bad = int(np.argmin(ok))
+            raise Exception("Sancho-Rubio decimation did not converge at E index %d (residual %.1e)" % (bad, conv[bad]))
+        return sigL, sigR
     out = []
     for (d, o, side) in ((h0, t0, -1), (hN, tN, 1)):
         (g_sig, conv, nit, ok) = surface_gf(d, o, Es, side, mode, full=True, want_sigma=True, **kw)
