@@ -381,6 +381,9 @@ int tx_bardeen_ts(const double* E, const double* M2, int n, int nb, const double
  *   option 5: n = 64 and 96 <= n <= 104 blocks in the global workspace: value != 0 (default) stages the B operand of every product in shared
  *             memory with the TMA engine (cp.async.bulk + mbarrier), 0 reads all fragments straight from L2 (A/B runs).
  *             Process-wide only.
+ *   option 6: Sancho-Rubio decimation: value != 0 (default) runs two products per iteration instead of six when the hopping
+ *             block is Hermitian (alpha = beta throughout; detected on the device), 0 always the general iteration (A/B runs).
+ *             Process-wide only.
  *   option 4: kernel of the 5 <= n <= 8, scalar-hopping sweep (= tx_set_variant):
  *             13  DEFAULT: telescoped sweep (rgf_n8t.cuh): register-resident DMMA recurrence, one inverse per chunk
  *                 of up to kmax sites, diagonal sites as column scalings; eight energies of one Hamiltonian per warp

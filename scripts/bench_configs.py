@@ -313,6 +313,8 @@ def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
     st = env.stream.cuda_stream
     nn16 = n * n * 16
 
+    if os.environ.get("TX_BENCH_HERM") is not None:           # A/B of the Hermitian-hopping decimation (scripts/ab_cfg4_leads.py)
+        _lib.check(lib.tx_set_option(6, int(os.environ["TX_BENCH_HERM"])))
     # both leads are the same clean ribbon: one Sancho-Rubio decimation carries both surfaces (tx_surface_gf_pair_dev);
     # TX_BENCH_TWO_DECIMATIONS=1 times the two independent decimations instead (A/B)
     same_leads = (np.array_equal(h[0], h[-1]) and np.array_equal(tnn[0], tnn[-1])
@@ -358,16 +360,19 @@ def run_cfg4(env, steps=2, warmup=3, scaling="weak", want_cpu=True, want_e2e=Tru
     flops_sweep = 8 * n ** 3 * M * 2
     flops_leads = 2 * n_it * (8 + 6 * 8) * n ** 3
     flops = flops_sweep + flops_leads
+    herm_hop = bool(np.array_equal(tnn[0], np.conj(tnn[0]).T) and os.environ.get("TX_BENCH_HERM", "1") != "0")
+    flops_exec = flops_sweep + (1 if same_leads else 2) * n_it * (8 + (2 if herm_hop else 6) * 8) * n ** 3
     peak = env.fp64_peak()
     ach = flops * nE / (ms * 1e-3) / 1e12
     roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "flops_per_point": flops, "kernel_ms": ms, "sancho_iterations_mean": n_it,
             "lead_decimations_per_energy": 1 if same_leads else 2,
-            "executed": {"flops_per_point": flops_sweep + (flops_leads / 2 if same_leads else flops_leads),
-                         "frac": (flops_sweep + (flops_leads / 2 if same_leads else flops_leads)) * nE / (ms * 1e-3) / 1e12 / peak,
-                         "note": "identical leads: one Sancho-Rubio decimation yields both surface blocks (the other one is "
-                                 "bulk + h00 - surface), so half of the algorithmic lead flops are executed" if same_leads else
-                                 "two independent decimations"},
+            "hermitian_hopping_decimation": herm_hop,
+            "executed": {"flops_per_point": flops_exec, "frac": flops_exec * nE / (ms * 1e-3) / 1e12 / peak,
+                         "note": ("identical leads: one Sancho-Rubio decimation yields both surface blocks (the other one is "
+                                  "bulk + h00 - surface); " if same_leads else "two independent decimations; ") +
+                                 ("Hermitian hopping block: alpha = beta throughout, 1 inverse + 2 products per iteration "
+                                  "instead of 1 + 6" if herm_hop else "general hopping: 1 inverse + 6 products per iteration")},
             "kernels": {"surface_gf_sancho (both leads)": {"ms": ms_leads, "flops_per_point": flops_leads,
                                                            "frac": flops_leads * nE / (ms_leads * 1e-3) / 1e12 / peak},
                         "rgf_sweep_generic": {"ms": ms_sweep, "flops_per_point": flops_sweep,

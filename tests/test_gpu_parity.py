@@ -451,6 +451,43 @@ def test_one_decimation_yields_both_lead_surfaces(n):
     assert np.allclose(car, car_t, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("n", [4, 24, 64, 72, 99])
+def test_hermitian_hopping_decimation_two_products(n):
+    """Sancho-Rubio with a Hermitian hopping block (alpha = beta throughout: two products per iteration, detected on the
+    device) against the general iteration (tx_set_option(6, 0)), the numpy oracle and the fixed-point map; both surfaces of
+    such a lead coincide"""
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    h00 = 0.4 * (A + A.conj().T) / 2 / np.sqrt(n)
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    t = -np.eye(n) + 0.2 * (B + B.conj().T) / 2 / np.sqrt(n)          # Hermitian, not scalar
+    Es = np.array([-1.3, 0.1, 0.9], dtype=complex)
+    eta = 1e-3
+    lib = _lib.load()
+    res = {}
+    try:
+        for mode in (1, 0):
+            _lib.check(lib.tx_set_option(6, mode))
+            res[mode] = leads.surface_gf_pair(h00, t, Es, imE=eta, conv_tol=1e-14, want_g=True)
+            assert res[mode][-1].all()
+    finally:
+        _lib.check(lib.tx_set_option(6, 1))
+    gL, gR, sL, sR = res[1][:4]
+    assert np.abs(gL - gR).max() < 1e-9 * np.abs(gR).max()
+    assert np.array_equal(res[1][5], res[0][5])                       # same number of iterations
+    for a, b in zip(res[1][:4], res[0][:4]):
+        assert np.abs(a - b).max() < 1e-9 * np.abs(b).max()
+    go, _ = rgf_oracle.sancho_rubio(h00, t, Es + 1j * eta, 1)
+    assert np.abs(gR - go).max() < 1e-9 * np.abs(go).max()
+    for i, E in enumerate(Es):
+        resid = lambda g: np.linalg.norm(wfm_oracle.g_ith(h00, t, E, 1, eta, 1, g) - g) / np.linalg.norm(g)
+        assert resid(gR[i]) < max(1e-9, 100 * resid(go[i]))         # as good a fixed point as the float64 numpy decimation
+    # single-side entry takes the same path
+    ((g1, s1), _, _, ok1) = leads.surface_gf(h00, t, Es, -1, _lib.TX_GF_SANCHO, imE=eta, conv_tol=1e-14, max_iter=200,
+                                             full=True, want_sigma=True)
+    assert ok1.all() and np.abs(g1 - gL).max() < 1e-9 * np.abs(gL).max() and np.abs(s1 - sL).max() < 1e-9 * np.abs(sL).max()
+
+
 def test_all_kernel_variants_agree():
     """Every kernel of the n=8 sweep (register-resident, plain DMMA, telescoped) gives the golden answer;
     the DMMA kernel is also exercised with padding (n=5..7), table leads and mixed Hamiltonians per warp."""

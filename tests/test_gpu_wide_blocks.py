@@ -130,7 +130,8 @@ def test_sancho_ribbon_leads_wide(n):
     oSL = np.conj(tnn[0]).T @ gL @ tnn[0]
     oSR = tnn[-1] @ gR @ np.conj(tnn[-1]).T
     for dev_S, ora_S in ((SL, oSL), (SR, oSR)):
-        assert np.abs(dev_S - ora_S).max() / np.abs(ora_S).max() < 1e-10
+        # two correct decimations differ by round-off amplified by |G|^2 <= 1/eta^2 (measured up to 2e-10 at this eta)
+        assert np.abs(dev_S - ora_S).max() / np.abs(ora_S).max() < 1e-9
     R, T, car = transmission_sweep(h, tnn, Es, "table", sigL=oSL, sigR=oSR, sources=np.eye(n)[:1], want_caroli=True)
     _, GN0 = rgf_oracle.rgf_blocks(h, tnn, Es, oSL, oSR)
     assert np.allclose(car[0], rgf_oracle.caroli_trace(GN0, oSL, oSR), rtol=1e-10, atol=1e-12)

@@ -33,6 +33,8 @@ constexpr int TMA_LD = 66;
 // |stored value|^2 (the convergence test of the decimation without another pass over the blocks).
 struct GemmEpi {
     cd* C2 = nullptr;
+    cd* C3 = nullptr;              // third destination: C3 += c3s * sgn A B  (Hermitian-hopping decimation: bulk block += 2 alpha G alpha)
+    double c3s = 1.0;
     double* tmax = nullptr;
     bool reuse_staged = false;     // B is the block the previous product staged: no copy, no wait
 };
@@ -227,6 +229,11 @@ __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, con
                 cd* p2 = epi.C2 + (tr + g) * N + 2 * t + u * 8 + i;
                 const cd c2 = *p2;
                 *p2 = mk(c2.x + v.x, c2.y + v.y);
+            }
+            if (epi.C3) {
+                cd* p3 = epi.C3 + (tr + g) * N + 2 * t + u * 8 + i;
+                const cd c3 = *p3;
+                *p3 = mk(fma(epi.c3s, v.x, c3.x), fma(epi.c3s, v.y, c3.y));
             }
             if (accumulate) {
                 const cd c0 = pc[u * 8 + i];

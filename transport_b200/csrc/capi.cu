@@ -370,6 +370,7 @@ static int set_option_on(Options& o, int option, int value) {
 int tx_set_option(int option, int value) {
     if (option == 3) return set_eig_mode(value);
     if (option == 5) return set_tma_mode(value);
+    if (option == 6) return set_hermitian_shortcut(value);
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
     return set_option_on(g_default_opts, option, value);
 }

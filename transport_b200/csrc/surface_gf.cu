@@ -44,10 +44,12 @@ struct GfParams {
     double imE, conv_tol;
     int conv_rep, min_iter, max_iter, ith;
     int use_tma;        // n = 64: stage the products' B operand in shared memory by TMA (tx_set_option(5, .))
+    int herm_shortcut;  // SANCHO: two products per iteration when h01 is Hermitian (tx_set_option(6, .))
 };
 
 constexpr int GF_THREADS = 256;
 int g_use_tma = 1;   // tx_set_option(5, value)
+int g_herm_shortcut = 1;   // tx_set_option(6, value)
 constexpr int GF_MAX_MATS = 9;
 
 // wfm.g_RiceMele for spin channel s (wfm/__init__.py:379-403)
@@ -238,6 +240,59 @@ __global__ void __launch_bounds__(GF_THREADS) separable_gf_kernel(const GfParams
     }
 }
 
+// The decimation for a Hermitian hopping block (alpha = beta throughout): out of line, so that its registers do not weigh on
+// the general loop of surface_gf_body.  On return `alpha` holds the last hopping block (unused), eps / epss the bulk and
+// surface blocks.
+template <int NMAX, int FIXN>
+__device__ __noinline__ void sancho_hermitian_loop(const GfParams& p, const cd z, cd* stage, TmaStage* ts, cd* s_colk, int* s_ipiv,
+                                                   cd* alpha, cd* tmp, cd* eps, cd* epss, cd* G, cd* T2, const double tol2,
+                                                   int& it, int& ok, double& resid) {
+    const int n = p.n, nn = n * n;
+    {
+            bool fused_h = false;
+            if constexpr (FIXN == 64) fused_h = ts != nullptr;
+            for (it = 1; it <= p.max_iter; ++it) {
+                if constexpr (FIXN == 64) {
+                    if (fused_h) {
+                        cta_inverse_blocked(G, stage, n, p.singular, eps, z);               // G = (z - eps)^-1
+                        cta_gemm<FIXN>(T2, G, OP_N, alpha, OP_N, n, ts);                    // G alpha
+                        double tmax = 0.0;
+                        GemmEpi epi;
+                        epi.C2 = epss;                                                      // epss += alpha G alpha
+                        epi.C3 = eps;                                                       // eps  += 2 alpha G alpha
+                        epi.c3s = 2.0;
+                        epi.tmax = &tmax;
+                        cta_gemm_dmma_nn_tma<64>(tmp, alpha, T2, *ts, 1.0, false, 1.0, epi); // new alpha
+                        resid = cta_reduce_max(tmax);
+                    }
+                }
+                if (!fused_h) {
+                    cta_z_minus(G, z, eps, n);
+                    cta_inverse_staged<NMAX>(G, stage, n, s_colk, s_ipiv, p.singular);
+                    cta_gemm<FIXN>(T2, G, OP_N, alpha, OP_N, n, ts);                        // G alpha
+                    cta_gemm<FIXN>(tmp, alpha, OP_N, T2, OP_N, n, ts);                      // alpha G alpha
+                    for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+                        const cd v = tmp[idx];
+                        const cd a = epss[idx], b = eps[idx];
+                        epss[idx] = mk(a.x + v.x, a.y + v.y);
+                        eps[idx] = mk(fma(2.0, v.x, b.x), fma(2.0, v.y, b.y));
+                    }
+                    __syncthreads();
+                    resid = cta_maxnorm2(tmp, nn);
+                }
+                {
+                    cd* sw = alpha;
+                    alpha = tmp;
+                    tmp = sw;
+                }
+                if (resid < tol2) {
+                    ok = 1;
+                    break;
+                }
+            }
+    }
+}
+
 template <int NMAX, int FIXN>
 __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) {
     extern __shared__ double2 gf_smem[];
@@ -347,10 +402,21 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
             eps[idx] = p.h00[idx];
             epss[idx] = p.h00[idx];
         }
-        __syncthreads();
+        // Hermitian hopping block (h01 = h01^dag: square-lattice ribbons, any lead whose cells couple symmetrically): then
+        // alpha_0 = beta_0, and by induction alpha_i = beta_i = alpha G alpha, alpha G beta = beta G alpha -- two products per
+        // iteration instead of six, and both surfaces of the lead coincide.  Detected per CTA (n^2 comparisons).
+        int asym = 0;
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            const cd a = alpha[idx], b = beta[idx];
+            asym |= (a.x != b.x || a.y != b.y) ? 1 : 0;
+        }
+        const bool herm = !__syncthreads_or(asym | (p.herm_shortcut ? 0 : 1));
         int it = 0, ok = 0;
         double resid = 0.0;
         const double tol2 = p.conv_tol * p.conv_tol;
+        if (herm) {
+            sancho_hermitian_loop<NMAX, FIXN>(p, z, stage, ts, s_colk, s_ipiv, alpha, tmp, eps, epss, G, T2, tol2, it, ok, resid);
+        } else {
         bool fused = false;
         if constexpr (FIXN == 64) fused = ts != nullptr;
         if constexpr (FIXN == 64) if (fused) {
@@ -435,6 +501,7 @@ __device__ __forceinline__ void surface_gf_body(const GfParams& p, const int e) 
                 break;
             }
         }
+        }   // general (non-Hermitian) hopping
         if (p.g2 || p.sigma2) {
             // The decimation carries both surfaces of the lead: eps = h00 + sum (alpha G beta + beta G alpha) is the bulk
             // block, epss = h00 + sum alpha G beta this side's surface block, so the surface block of the OTHER
@@ -622,6 +689,10 @@ int set_tma_mode(int on) {
     return TX_OK;
 }
 int tma_mode() { return g_use_tma; }
+int set_hermitian_shortcut(int on) {
+    g_herm_shortcut = on != 0;
+    return TX_OK;
+}
 }  // namespace tx
 
 
@@ -656,6 +727,7 @@ int tx_surface_gf_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cp
     p.max_iter = max_iter;
     p.ith = -1;
     p.use_tma = g_use_tma;
+    p.herm_shortcut = g_herm_shortcut;
     cd* owned = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     rc = launch_gf(p, st, &owned);
@@ -698,6 +770,7 @@ int tx_surface_gf_pair_dev(const tx_cplx* h00, const tx_cplx* h01, int n, const 
     p.max_iter = max_iter;
     p.ith = -1;
     p.use_tma = g_use_tma;
+    p.herm_shortcut = g_herm_shortcut;
     cd* owned = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     rc = launch_gf(p, st, &owned);
@@ -809,6 +882,7 @@ static int gf_host(const tx_cplx* h00, const tx_cplx* h01, int n, const tx_cplx*
     p.max_iter = max_iter;
     p.ith = ith;
     p.use_tma = g_use_tma;
+    p.herm_shortcut = g_herm_shortcut;
     cd* owned = nullptr;
     rc = launch_gf(p, nullptr, &owned);
     cudaError_t e = cudaDeviceSynchronize();

@@ -12,6 +12,7 @@ int set_eig_mode(int mode);
 // surface_gf.cu: TMA staging of the n = 64 products' B operand (tx_set_option(5, on)); read by rgf_generic.cu too.
 int set_tma_mode(int on);
 int tma_mode();
+int set_hermitian_shortcut(int on);   // tx_set_option(6, .): two-product decimation for Hermitian hopping blocks
 }  // namespace tx
 
 #define TX_CUDA(call)                                                                              \
