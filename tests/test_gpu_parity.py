@@ -415,7 +415,7 @@ def test_ribbon_sancho_leads_cfg4_downscaled():
             assert np.allclose(car[0], open_ch, atol=1e-4)      # clean ribbon: T = number of open channels
 
 
-@pytest.mark.parametrize("n", [3, 24, 64, 72])
+@pytest.mark.parametrize("n", [3, 24, 64, 72, 96])
 def test_one_decimation_yields_both_lead_surfaces(n):
     """tx_surface_gf_pair: the left and right continuations of one periodic lead from a single Sancho-Rubio decimation
     (other surface block = bulk + h00 - surface) against the two independent decimations, the numpy oracle and the
