@@ -1046,6 +1046,13 @@ long long tx_bardeen_workspace_bytes(int P, int n, int S, int max_states) {
     return (long long)(2 * align256((size_t)P * n * max_states * S * 8) + align256((size_t)P * n * n * 8) + 256);
 }
 
+namespace {
+struct EigFork {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+}  // namespace
+
 static int wells_dev_impl(const double* dL, const double* eL, const double* dR, const double* eR,
                           const double* cutL, const double* cutR_states, const double* cutR_count,
                           const double* hd0, const double* hdU, const double* hdL, int P, int n, int S, int max_states,
@@ -1067,8 +1074,28 @@ static int wells_dev_impl(const double* dL, const double* eL, const double* dR, 
         if (int rc = launch_count(dL, eL, S, n_mat, cutL, cutL, nL, nR_below /* overwritten below */, st)) return rc;
         if (int rc = launch_count(dR, eR, S, n_mat, cutR_states, cutR_count, nR_states, nR_below, st)) return rc;
     }
-    if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, nullptr, st)) return rc;
-    if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, nullptr, st)) return rc;
+    // The eigenproblems of the two wells are independent and their grids (a few hundred small CTAs for a sweep of 256
+    // geometries) leave most of the GPU idle: the right well runs on an auxiliary stream, forked from and joined to `st`
+    // by events (legal under stream capture too).  One auxiliary stream per device; the enqueue is serialised.
+    {
+        static EigFork forks[16];
+        static std::mutex fork_mu;
+        int dev = 0;
+        TX_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(fork_mu);
+        EigFork& f = forks[dev & 15];
+        if (!f.aux) {
+            TX_CUDA(cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking));
+            TX_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+            TX_CUDA(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
+        }
+        TX_CUDA(cudaEventRecord(f.fork, st));
+        TX_CUDA(cudaStreamWaitEvent(f.aux, f.fork, 0));
+        if (int rc = launch_eig(dL, eL, S, n_mat, cutL, nL, max_states, EL, psiL, nullptr, st)) return rc;
+        if (int rc = launch_eig(dR, eR, S, n_mat, cutR_states, nR_states, max_states, ER, psiR, nullptr, f.aux)) return rc;
+        TX_CUDA(cudaEventRecord(f.join, f.aux));
+        TX_CUDA(cudaStreamWaitEvent(st, f.join, 0));
+    }
     static bool attr_set = false;
     if (!attr_set) {
         TX_CUDA(cudaFuncSetAttribute(bardeen_melem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
