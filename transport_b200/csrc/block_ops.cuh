@@ -63,7 +63,11 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
 
 template <int FIXN = 0>
 __device__ inline void cta_gemm(cd* C, const cd* A, int opA, const cd* B, int opB, int n, TmaStage* ts = nullptr) {
-    if (FIXN == 64 || ((n & 7) == 0 && n >= 16)) {
+    if constexpr (FIXN == 64) {
+        cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, 1.0, false, 1.0, ts);
+        return;
+    }
+    if ((n & 7) == 0 && n >= 16) {
         cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, 1.0, false, 1.0, ts);
         return;
     }
@@ -483,7 +487,11 @@ __device__ inline void cta_gemm_dmma(cd* C, const cd* A, int opA, const cd* B, i
 template <int FIXN = 0>
 __device__ inline void cta_gemm_acc(cd* C, const cd* A, int opA, const cd* B, int opB, int n, double sgn, double cscale = 1.0,
                                     TmaStage* ts = nullptr) {
-    if (FIXN == 64 || ((n & 7) == 0 && n >= 16)) {
+    if constexpr (FIXN == 64) {
+        cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, sgn, true, cscale, ts);
+        return;
+    }
+    if ((n & 7) == 0 && n >= 16) {
         cta_gemm_dmma<FIXN>(C, A, opA, B, opB, n, sgn, true, cscale, ts);
         return;
     }
