@@ -33,8 +33,17 @@ def main(edges):
     torch, lib = env.torch, env.lib
     M, nE = 8, 1184
     Es = np.linspace(-1.9, 1.9, nE).astype(complex)
+    # TX_BENCH_DIAG_SITES=1: only sites 2 and 5 keep a dense block (two impurities with spacer sites, as get_hblocks
+    # builds them); the others are diagonal and become row scalings in the telescoped sweep
+    spacer = bool(os.environ.get("TX_BENCH_DIAG_SITES"))
+    if os.environ.get("TX_BENCH_SCAN") is not None:      # A/B: structure scan (diagonal sites as row scalings) on / off
+        _lib.check(lib.tx_set_option(0, int(os.environ["TX_BENCH_SCAN"])))
     for n in edges:
         h, tnn = chain(n, M, n)
+        if spacer:
+            for j in range(1, M - 1):
+                if j not in (2, 5):
+                    h[j] = np.diag(np.real(np.diagonal(h[j]))) * 3
         SL, SR = leads.self_energies_batched(h, tnn, Es, "g_closed")
         d_h, d_t, d_E = env.dev_c(h), env.dev_c(tnn), env.dev_c(Es)
         sigL, sigR = env.dev_c(SL), env.dev_c(SR)
@@ -57,7 +66,7 @@ def main(edges):
         want = oT.sum(axis=(1, 2))
         got = tot.cpu().numpy()[idx]
         flops = 8 * n ** 3 * M * 2
-        print(json.dumps({"n": n, "M": M, "nE": nE, "ms": ms, "points_per_s": nE / (ms * 1e-3),
+        print(json.dumps({"n": n, "M": M, "nE": nE, "diagonal_spacer_sites": spacer, "structure_scan": os.environ.get("TX_BENCH_SCAN", "1"), "ms": ms, "points_per_s": nE / (ms * 1e-3),
                           "fp64_frac_algorithmic": flops * nE / (ms * 1e-3) / 1e12 / env.fp64_peak(),
                           "caroli_trace_max_rel_err_vs_oracle_total_T": float(np.max(np.abs(got - want) / np.abs(want)))}), flush=True)
 

@@ -210,6 +210,42 @@ def test_all_one_hot_sources_shortcut_equals_explicit_sources(n):
     assert np.max(np.abs(a[2])) < UNIT
 
 
+@pytest.mark.parametrize("n", [24, 50, 64, 72, 128])
+def test_diagonal_sites_as_row_scalings_in_the_large_block_sweep(n):
+    """chains whose interior on-site blocks are mostly diagonal (spacer sites between two impurities, as
+    run_wfm_gate.get_hblocks builds them): the telescoped large-block sweep turns those sites into row scalings (structure
+    scan, tx_set_option(0, .)); against the oracle, and against the same sweep with the scan switched off; affine family
+    whose affine term is diagonal on some sites and dense on others"""
+    M = 9
+    rng = np.random.default_rng(n + 17)
+    h, tnn = _random_chain(n, M, True, n + 17)
+    dense = (2, 6)
+    for j in range(1, M - 1):
+        if j not in dense:
+            h[j] = np.diag(0.3 * rng.standard_normal(n))
+    h1 = np.zeros_like(h)
+    h1[2] = h[2] * 0.5                                   # dense affine term on a dense site
+    h1[4] = np.diag(rng.standard_normal(n))              # diagonal affine term on a diagonal site
+    Js = np.array([-0.5, 0.8])
+    Es = np.array([-1.6, -0.3, 0.7, 1.5], dtype=complex)
+    srcs = np.eye(n)[[0, n - 1]]
+    lib = _lib.load()
+    outs = {}
+    try:
+        for scan in (1, 0):
+            _lib.check(lib.tx_set_option(0, scan))
+            outs[scan] = transmission_sweep(h, tnn, Es, h1=h1, params=Js, sources=srcs, want_resid=True, want_caroli=True)
+    finally:
+        _lib.check(lib.tx_set_option(0, 1))
+    R, T, res, car = outs[1]
+    assert np.max(np.abs(res)) < UNIT
+    for p in range(2):
+        oR, oT = rgf_oracle.transmission_closed(h + Js[p] * h1, tnn, Es, srcs)
+        assert rt_err(T[p], oT) < RTOL and rt_err(R[p], oR) < RTOL
+    for a, b in zip(outs[1], outs[0]):
+        assert np.allclose(a, b, rtol=1e-11, atol=1e-13)
+
+
 def test_green_blocks_wide():
     """first block column and full Green's function at n = 72 (work blocks in shared memory) and n = 96 (global scratch)"""
     for n in (72, 96):

@@ -718,6 +718,20 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     p.hop_scalar = (hop_mode == TX_HOP_SCALAR) ? 1 : 0;
     p.kmax = cx.opt.chunk_kmax;
     p.gexp = cx.opt.chunk_gexp;
+    if (p.hop_scalar && p.kmax > 1 && cx.opt.diag_tail && M > 2) {
+        // structure scan (one warp per site): diagonal on-site blocks become row scalings in the telescoped sweep
+        SweepParams sp{};
+        sp.h = p.h;
+        sp.h_stride = p.h_stride;
+        sp.h1 = p.h1;
+        sp.n_pts = p.n_pts;
+        sp.nE = nE;
+        sp.M = M;
+        sp.n = n;
+        if (int rc = scan_structure(cx, sp, st, false)) return rc;
+        p.site_class = sp.site_class;
+        p.class_stride = sp.class_stride;
+    }
     return launch_rgf_generic(p, st);
 }
 

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     __shared__ int s_ipiv[NMAX];
     __shared__ cd s_colk[NMAX];
     __shared__ double s_vL[NMAX], s_vR[NMAX];
+    __shared__ cd s_zd[NMAX];            // diagonal of z_j at a diagonal site
     __shared__ double s_red[GEN_THREADS / 32];
     __shared__ double s_red4[4][GEN_THREADS / 32];
     __shared__ unsigned long long s_tma_bar;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
     const cd* SL = p.sigL + ham * p.sig_stride + (long long)e * nnr;
     const cd* SR = p.sigR + ham * p.sig_stride + (long long)e * nnr;
     const double par = p.h1 ? p.params[ham] : 0.0;
+    const int* cls = p.site_class ? p.site_class + ham * p.class_stride : nullptr;
 
     for (int c = threadIdx.x; c < nr; c += blockDim.x) {     // v = -2 Im diag Sigma  (:91)
         s_vL[c] = -2.0 * SL[c * nr + c].y;
@@ -152,6 +154,37 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
                 if (!(cta_maxnorm2(cur, nn) < gmax2 * S2)) break;          // growth bound (also stops on NaN)
                 --j;
                 ++k;
+                if (cls != nullptr && j > 0 && cls[j] >= 1) {
+                    // DIAGONAL on-site block (clean spacer sites between the impurities, barrier regions: most sites of the
+                    // reference's own chains): z_j D_{j+1} is a row scaling, O(n^2) instead of a product
+                    const cd* hj = hb + (long long)j * nnr;
+                    const cd* wj = p.h1 ? p.h1 + (long long)j * nnr : nullptr;
+                    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+                        if (r < nr) {
+                            cd hv = hj[r * nr + r];
+                            if (wj) {
+                                const cd w = wj[r * nr + r];
+                                hv.x = fma(par, w.x, hv.x);
+                                hv.y = fma(par, w.y, hv.y);
+                            }
+                            s_zd[r] = mk(E.x - hv.x, E.y - hv.y);
+                        } else {
+                            s_zd[r] = mk(1.0 + kap, 0.0);                      // padding channels keep D = 1
+                        }
+                    }
+                    __syncthreads();
+                    struct Two {
+                        cd c, q;
+                    };
+                    const bool ident = prev_is_identity;
+                    for_each4(prev, [&](int idx) { Two t; t.c = cur[idx]; t.q = ident ? mk(0.0, 0.0) : prev[idx]; return t; },
+                              [&](int idx, Two t) {
+                                  const int r = idx / n, c = idx - r * n;
+                                  const cd q = ident ? mk(r == c ? 1.0 : 0.0, 0.0) : t.q;
+                                  const cd v = s_zd[r] * t.c;
+                                  return mk(fma(-kap, q.x, v.x), fma(-kap, q.y, v.y));
+                              });
+                } else {
                 build_z(tmp, j, kap);
                 // D_j = z_j D_{j+1} - kap D_{j+2}: the scaling of D_{j+2} rides on the product's epilogue
                 if (prev_is_identity) {
@@ -163,6 +196,7 @@ __global__ void __launch_bounds__(GEN_THREADS, MINB) rgf_sweep_generic(const Gen
                     cta_gemm_acc<FIXN>(prev, tmp, OP_N, cur, OP_N, n, 1.0, 1.0, ts);
                 } else {
                     cta_gemm_acc<FIXN>(prev, tmp, OP_N, cur, OP_N, n, 1.0, -kap, ts);
+                }
                 }
                 cd* sw = prev;
                 prev = cur;

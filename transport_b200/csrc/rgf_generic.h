@@ -26,6 +26,8 @@ struct GenericParams {
     double* spin;            // [n_pts][n_src][spin_n] or null (see emit_spin in rgf_small.cuh)
     int n_up, spin_n;
     PeerGather gather;
+    const int* site_class;   // structure scan (rgf_n8.cuh): [n_h][M], >= 1: on-site block (and its affine term) diagonal; or null
+    long long class_stride;  // M, or 0 when all Hamiltonians share the blocks
     cd* work;                // global workspace or null (then dynamic shared memory)
     long long work_per_cta;  // elements of `work` per resident CTA (set by the launcher)
     int* singular;
