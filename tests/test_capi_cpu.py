@@ -159,3 +159,25 @@ def test_bardeen_argument_errors_match_reference():
         if _lib.device_count() > 0:
             raise _lib.TransportError(2, "gpu present")
         bardeen.current(np.array([[0.0]]), np.ones((1, 1, 1)), np.array([0.1]), one, 0.0, 0.1)
+
+
+@pytest.mark.parametrize("n,M", [(1, 6), (2, 7), (3, 5), (2, 4)])
+def test_superblock_pairing_reproduces_the_pentadiagonal_matrix(n, M):
+    """host logic of the next-nearest-neighbour path: pairing sites into super-blocks of size 2n turns the reference's
+    block-pentadiagonal dense matrix (wfm.Hmat, wfm/__init__.py:168-215, restated in oracle.wfm_oracle.Hmat) into a
+    block-tridiagonal one with the same entries (an odd chain gets one decoupled dummy site)"""
+    from oracle import wfm_oracle
+    from transport_b200 import superblocks
+    rng = np.random.default_rng(10 * n + M)
+    A = rng.standard_normal((M, n, n)) + 1j * rng.standard_normal((M, n, n))
+    h = (A + np.conj(np.swapaxes(A, 1, 2))) / 2
+    tnn = rng.standard_normal((M - 1, n, n)) + 1j * rng.standard_normal((M - 1, n, n))
+    tnnn = rng.standard_normal((M - 2, n, n)) + 1j * rng.standard_normal((M - 2, n, n))
+    want = wfm_oracle.Hmat(h, tnn, tnnn)
+    H, T, Mp = superblocks.pair_into_superblocks(h, tnn, tnnn)
+    K = H.shape[0]
+    assert Mp == M + M % 2 and H.shape == (K, 2 * n, 2 * n) and T.shape == (K - 1, 2 * n, 2 * n)
+    got = wfm_oracle.Hmat(H, T, np.zeros((max(K - 2, 0), 2 * n, 2 * n), complex))
+    assert np.array_equal(got[:M * n, :M * n], want)
+    if M % 2:                                            # the dummy site is decoupled
+        assert not np.any(got[:M * n, M * n:]) and not np.any(got[M * n:, :M * n])

@@ -719,7 +719,10 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     p.kmax = cx.opt.chunk_kmax;
     p.gexp = cx.opt.chunk_gexp;
     if (p.hop_scalar && p.kmax > 1 && cx.opt.diag_tail && M > 2) {
-        // structure scan (one warp per site): diagonal on-site blocks become row scalings in the telescoped sweep
+        // structure scan (one warp per site): diagonal on-site blocks become row scalings in the telescoped sweep.  The scan's
+        // buffer is the context's scratch: same ordering protocol across streams as in sweep_small_dev
+        if (cx.scratch_used && cx.scratch_stream != st && cx.scratch_ev) TX_CUDA(cudaStreamWaitEvent(st, cx.scratch_ev, 0));
+        cx.scratch_used = false;
         SweepParams sp{};
         sp.h = p.h;
         sp.h_stride = p.h_stride;
@@ -731,6 +734,13 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
         if (int rc = scan_structure(cx, sp, st, false)) return rc;
         p.site_class = sp.site_class;
         p.class_stride = sp.class_stride;
+        const int rc = launch_rgf_generic(p, st);
+        if (rc == TX_OK) {
+            if (!cx.scratch_ev) TX_CUDA(cudaEventCreateWithFlags(&cx.scratch_ev, cudaEventDisableTiming));
+            TX_CUDA(cudaEventRecord(cx.scratch_ev, st));
+            cx.scratch_stream = st;
+        }
+        return rc;
     }
     return launch_rgf_generic(p, st);
 }
