@@ -50,7 +50,8 @@ def config_dict(name, world, scaling):
     """The `config` object of the JSON line: identical keys and values in both arms (ours / reference)."""
     from bench_configs import WORKLOADS
     return {"workload": WORKLOADS[name], "config": name, "scaling": scaling, "parallelism": "dp%d" % world,
-            "dtype": "complex128 arithmetic, float64 outputs"}
+            "dtype": "complex128 arithmetic, float64 outputs",
+            "l2": "GPU arm: 256 MB L2 flush between timed steps, outside the event pair (CPU arm: not applicable)"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (cfg2)
