@@ -191,8 +191,10 @@ def region_sweep(tinfty, tL, tR, Vinfty, VL, VLprime, VR, VRprime, Ninfty, NL, N
 
     def chan(x):
         x = np.asarray(x)
-        if x.ndim == 2 and x.shape[0] == x.shape[1] and not np.any(x - np.diagflat(np.diagonal(x))):
-            x = np.diagonal(x)
+        if x.ndim == 2 and x.shape[0] == x.shape[1]:
+            d = np.diagonal(x)
+            if np.count_nonzero(x) == np.count_nonzero(d):      # diagonal matrix -> its diagonal
+                x = d
         if np.any(np.imag(x)):
             raise NotImplementedError("complex region parameters are not covered by the device path")
         return as_f64(np.real(x))
