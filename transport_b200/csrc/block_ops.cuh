@@ -223,33 +223,55 @@ __device__ inline void cta_gemm_dmma_nn_tma(cd* C, const cd* __restrict__ A, con
             }
         }
     }
+    // Epilogue in batches of two tiles (four elements): the old values a batch reads (C for an accumulating product, the
+    // second or third destination) are loaded before its first store, one destination at a time (sixteen registers of loads
+    // in flight).  Warps issue in order, so a read-modify-write per element is a chain of sixteen L2 latencies (ncu: 11 % of
+    // the samples of the Hermitian decimation sat on these lines).
     cd* pc = C + (tr + g) * N + 2 * t;
+    auto add_into = [&](cd* D, const double scale) {           // D += scale * sgn * (A B)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+        for (int u0 = 0; u0 < 8; u0 += 2) {
+            cd o[2][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            cd v = mk(sgn * re[u][i], sgn * im[u][i]);
-            if (epi.C2) {
-                cd* p2 = epi.C2 + (tr + g) * N + 2 * t + u * 8 + i;
-                const cd c2 = *p2;
-                *p2 = mk(c2.x + v.x, c2.y + v.y);
-            }
-            if (epi.C3) {
-                cd* p3 = epi.C3 + (tr + g) * N + 2 * t + u * 8 + i;
-                const cd c3 = *p3;
-                *p3 = mk(fma(epi.c3s, v.x, c3.x), fma(epi.c3s, v.y, c3.y));
-            }
-            if (accumulate) {
-                const cd c0 = pc[u * 8 + i];
-                v.x = fma(cscale, c0.x, v.x);
-                v.y = fma(cscale, c0.y, v.y);
-            }
-            pc[u * 8 + i] = v;
-            if (epi.tmax) {
-                const double m = norm2(v);
-                *epi.tmax = (m > *epi.tmax || !(m == m)) ? m : *epi.tmax;
-            }
+            for (int du = 0; du < 2; ++du)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) o[du][i] = D[(u0 + du) * 8 + i];
+#pragma unroll
+            for (int du = 0; du < 2; ++du)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double f = scale * sgn;
+                    D[(u0 + du) * 8 + i] = mk(fma(f, re[u0 + du][i], o[du][i].x), fma(f, im[u0 + du][i], o[du][i].y));
+                }
         }
+    };
+    if (epi.C2) add_into(epi.C2 + (tr + g) * N + 2 * t, 1.0);
+    if (epi.C3) add_into(epi.C3 + (tr + g) * N + 2 * t, epi.c3s);
+#pragma unroll
+    for (int u0 = 0; u0 < 8; u0 += 2) {
+        cd o[2][2];
+        if (accumulate) {
+#pragma unroll
+            for (int du = 0; du < 2; ++du)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) o[du][i] = pc[(u0 + du) * 8 + i];
+        }
+#pragma unroll
+        for (int du = 0; du < 2; ++du)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int u = u0 + du;
+                cd v = mk(sgn * re[u][i], sgn * im[u][i]);
+                if (accumulate) {
+                    v.x = fma(cscale, o[du][i].x, v.x);
+                    v.y = fma(cscale, o[du][i].y, v.y);
+                }
+                pc[u * 8 + i] = v;
+                if (epi.tmax) {
+                    const double m = norm2(v);
+                    *epi.tmax = (m > *epi.tmax || !(m == m)) ? m : *epi.tmax;
+                }
+            }
     }
     __syncthreads();
 }
@@ -366,7 +388,7 @@ __device__ __forceinline__ void gemm_rt_strip(cd* pc, const cd* __restrict__ pa,
             pc[u * 8 + i] = v;
         }
     }
-}
+}   // (loads batched ahead of the stores were measured here too: the extra registers spill, 5 % slower)
 
 // `ts`: stage B in shared memory first (TMA), so that only the A fragments -- one load per k-step and lane instead of up to
 // five -- come from L2 (ncu on the n = 72 lead kernel: 23 % of all stall samples were DMMAs waiting for L2 operands).
