@@ -42,16 +42,21 @@ ix = {h: i for i, h in enumerate(tab["hdr"])}
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-line_of = {}
+# every .text section whose (mangled) name contains the pattern; a template has many instantiations, so the one whose
+# instruction count equals the profiled kernel's SASS table is taken (pass the full mangled name to be sure)
+n_sass = len(tab["rows"])
+sections = []
 for cub in glob.glob(os.path.join(tmp, "*.cubin")):
     txt = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-    inside, where = False, None
+    cur_map, where = None, None
     for ln in txt.splitlines():
         if ln.startswith(".text."):
-            inside = pattern in ln
+            cur_map = {} if pattern in ln else None
+            if cur_map is not None:
+                sections.append((ln.strip(), cur_map))
             where = None
             continue
-        if not inside:
+        if cur_map is None:
             continue
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
         if m:
@@ -59,9 +64,13 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m and where:
-            line_of.setdefault(int(m.group(1), 16), where)
-    if line_of:
-        break
+            cur_map.setdefault(int(m.group(1), 16), where)
+if not sections:
+    sys.exit("no .text section matches %r" % pattern)
+sections.sort(key=lambda sm: abs(len(sm[1]) - n_sass))
+name, line_of = sections[0]
+if len(sections) > 1:
+    print("# %d sections match %r; using %s (%d instructions with line info, SASS table %d)" % (len(sections), pattern, name, len(line_of), n_sass), file=sys.stderr)
 
 per = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0, 0]
