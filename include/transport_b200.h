@@ -150,7 +150,9 @@ int tx_peer_barrier_dev(int* const* flag_peers, int n_peers, int rank, int epoch
  *
  * tx_transmission_sweep takes HOST pointers and performs the host<->device copies itself;
  * tx_transmission_sweep_dev takes DEVICE pointers and a cudaStream_t (as void*), launches
- * asynchronously and performs no copies.
+ * asynchronously and performs no copies.  After one warm-up call with the same sizes (which grows the
+ * context's scratch and sets the kernel attributes) the device entries allocate nothing and do not synchronise:
+ * they may be captured into a CUDA graph and replayed (tests/test_gpu_compact.py).
  */
 int tx_transmission_sweep(const tx_cplx* h, int n_h, const tx_cplx* h1, const double* params,
                           const tx_cplx* tnn, int n_t, int n, int M, int n_ham,

@@ -213,3 +213,56 @@ def test_context_on_a_caller_stream_and_device_entry():
     got_T = np.concatenate([hh[1].cpu().numpy().reshape(32, 64, 8, 8) for hh in halves])
     got_R = np.concatenate([hh[0].cpu().numpy().reshape(32, 64, 8, 8) for hh in halves])
     assert np.array_equal(got_T, want_T) and np.array_equal(got_R, want_R)
+
+
+def test_device_entry_under_cuda_graph_capture():
+    """the stream-asynchronous device entry is capture-safe after one warm-up call (which sizes the context's scratch and
+    sets the kernel attributes): a CUDA graph of the whole sweep (structure scan, affine expansion, both sweep
+    instantiations) replays to the bits of the direct call, also after the parameters in the captured buffers change"""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    h0, h1, tnn, _ = configs.cicc_affine(1, 1.0, 0.0, 0.0, 0.0, 3, 2)
+    Js, Es = configs.cfg2_grid(48, 64)
+
+    def dc(a):
+        return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))).to(dev)
+    d_h0, d_h1, d_t, d_E = dc(h0), dc(h1), dc(tnn), dc(Es)
+    dJ = torch.from_numpy(np.ascontiguousarray(Js)).to(dev)
+    R = torch.zeros((48 * 64, 8, 8), dtype=torch.float64, device=dev)
+    T = torch.zeros_like(R)
+    spin = torch.zeros((48 * 64, 8, 2), dtype=torch.float64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.tx_context_create(0, ctypes.byref(ctx)))
+    s = torch.cuda.Stream()
+
+    def launch():
+        _lib.check(lib.tx_transmission_sweep_spin_dev(ctx, d_h0.data_ptr(), 1, d_h1.data_ptr(), dJ.data_ptr(), d_t.data_ptr(), 1,
+                                                      8, 8, 48, d_E.data_ptr(), 64, _lib.TX_LEAD_CLOSED, None, None, 1,
+                                                      _lib.TX_HOP_SCALAR, None, None, 8, R.data_ptr(), T.data_ptr(), None, None,
+                                                      4, 2, spin.data_ptr(), flag.data_ptr(), s.cuda_stream))
+    try:
+        with torch.cuda.stream(s):
+            launch()                                  # warm-up outside the capture
+            s.synchronize()
+            want_R, want_T = transmission_sweep(h0, tnn, Es, h1=h1, params=Js)
+            assert np.array_equal(T.cpu().numpy().reshape(48, 64, 8, 8), want_T)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                launch()
+            for Jscale in (1.0, 0.5):
+                dJ.copy_(torch.from_numpy(np.ascontiguousarray(Js * Jscale)))
+                R.zero_(); T.zero_(); spin.zero_()
+                torch.cuda.synchronize()
+                graph.replay()
+                torch.cuda.synchronize()
+                want_R, want_T, want_spin = transmission_sweep(h0, tnn, Es, h1=h1, params=Js * Jscale, want_spin=2, n_elec_up=4)
+                assert np.array_equal(T.cpu().numpy().reshape(48, 64, 8, 8), want_T)
+                assert np.array_equal(R.cpu().numpy().reshape(48, 64, 8, 8), want_R)
+                assert np.array_equal(spin.cpu().numpy().reshape(48, 64, 8, 2), want_spin)
+        assert int(flag.item()) == 0
+    finally:
+        torch.cuda.synchronize()
+        lib.tx_context_destroy(ctx)
