@@ -177,6 +177,43 @@ def _run_small_blocks(name, env, h, tnn, tnnn, Es_fn, n_base, flops_per_point, s
                                                "unitarity_median_abs": float(np.nanmedian(resid))})
     if env.rank == 0:
         out.update(parity_fn(Es, Rh, Th, lo))
+    if name == "cfg1" and env.world == 1:
+        # launch-latency bound (one ~12 us step): the same step captured into a CUDA graph and replayed back to back,
+        # without the L2 flush between steps (so this is a launch-rate figure next to `value`, not a replacement)
+        side = torch.cuda.Stream()
+        side.wait_stream(env.stream)
+        with torch.cuda.stream(side):
+            def step_side():
+                _lib.check(lib.tx_transmission_sweep_dev(d_h.data_ptr(), 1, None, None, d_t.data_ptr(), 1, n, M, 1,
+                                                         d_E.data_ptr(), nE, _lib.TX_LEAD_CLOSED, None, None, 1,
+                                                         _lib.TX_HOP_SCALAR, None, None, n, R.data_ptr(), T.data_ptr(),
+                                                         res.data_ptr(), None, flag.data_ptr(), side.cuda_stream))
+            step_side()
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step_side()
+            reps = 200
+            for _ in range(10):
+                graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(reps):
+                graph.replay()
+            e1.record(side)
+            side.synchronize()
+            g_ms = e0.elapsed_time(e1) / reps
+            e0.record(side)
+            for _ in range(reps):
+                step_side()
+            e1.record(side)
+            side.synchronize()
+            d_ms = e0.elapsed_time(e1) / reps
+        assert np.array_equal(T.cpu().numpy(), Th)
+        out["back_to_back"] = {"cuda_graph_replay_ms_per_sweep": g_ms, "direct_calls_ms_per_sweep": d_ms,
+                               "cuda_graph_points_per_s": nE / (g_ms * 1e-3), "direct_points_per_s": nE / (d_ms * 1e-3),
+                               "note": "200 sweeps issued back to back on one stream, no L2 flush in between (results stay "
+                                       "L2-resident): the launch rate of the device entry, direct and as a replayed CUDA graph"}
     if want_e2e:
         from transport_b200.sweep import transmission_sweep
         Rp = torch.empty((1, nE, n, n), dtype=torch.float64, pin_memory=True).numpy()
