@@ -150,6 +150,40 @@ def test_contexts_run_concurrently_from_threads():
     assert np.array_equal(T1, T0)
 
 
+def test_large_block_sweeps_with_device_built_leads_from_two_threads():
+    """two host threads, one context and stream each, large blocks with Sancho-Rubio lead tables built on the device: the
+    lead kernel's per-device workspace and each context's sweep workspace are shared resources whose reuse across streams
+    is ordered by events on the device; results equal the serial ones bit for bit"""
+    hA, tA, _ = configs.ribbon_blocks(width=64, L=5, W=1.0, seed=5)
+    hB, tB, _ = configs.ribbon_blocks(width=72, L=4, W=0.5, seed=6)
+    EsA = np.linspace(-2.5, 2.5, 40).astype(complex)
+    EsB = np.linspace(-2.0, 2.0, 24).astype(complex)
+    kwA = dict(converger=("sancho", 1e-6), sources=np.eye(64)[:2], want_caroli=True)
+    kwB = dict(converger=("sancho", 1e-6), sources=np.eye(72)[:2], want_caroli=True)
+    wantA = transmission_sweep(hA, tA, EsA, **kwA)
+    wantB = transmission_sweep(hB, tB, EsB, **kwB)
+    out, errs = {}, []
+
+    def work(key, reps):
+        try:
+            with Context(0) as cx:
+                for _ in range(reps):
+                    out[key] = transmission_sweep(hA, tA, EsA, context=cx, **kwA) if key == "a" else \
+                        transmission_sweep(hB, tB, EsB, context=cx, **kwB)
+        except Exception as exc:      # surfaced below
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=("a", 5)), threading.Thread(target=work, args=("b", 5))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for got, want in ((out["a"], wantA), (out["b"], wantB)):
+        for x, y in zip(got, want):
+            assert np.array_equal(x, y)
+
+
 def test_device_built_lead_tables_through_the_host_sweep():
     """TX_LEAD_SANCHO / TX_LEAD_SEPARABLE: the host sweep builds the self-energy tables on the device ahead of the sweep
     (they never travel to the host).  Same numbers as the two-call route (tables to the host and back), for a large

@@ -718,11 +718,12 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
     p.hop_scalar = (hop_mode == TX_HOP_SCALAR) ? 1 : 0;
     p.kmax = cx.opt.chunk_kmax;
     p.gexp = cx.opt.chunk_gexp;
+    // The structure scan's buffer and the caller's workspace of a context are reused from call to call: same ordering
+    // protocol across streams as in sweep_small_dev (an event behind the last user, waited for on the device)
+    if (cx.scratch_used && cx.scratch_stream != st && cx.scratch_ev) TX_CUDA(cudaStreamWaitEvent(st, cx.scratch_ev, 0));
+    cx.scratch_used = false;
     if (p.hop_scalar && p.kmax > 1 && cx.opt.diag_tail && M > 2) {
-        // structure scan (one warp per site): diagonal on-site blocks become row scalings in the telescoped sweep.  The scan's
-        // buffer is the context's scratch: same ordering protocol across streams as in sweep_small_dev
-        if (cx.scratch_used && cx.scratch_stream != st && cx.scratch_ev) TX_CUDA(cudaStreamWaitEvent(st, cx.scratch_ev, 0));
-        cx.scratch_used = false;
+        // structure scan (one warp per site): diagonal on-site blocks become row scalings in the telescoped sweep
         SweepParams sp{};
         sp.h = p.h;
         sp.h_stride = p.h_stride;
@@ -734,15 +735,15 @@ int sweep_large_dev(tx_context& cx, const tx_cplx* h, int n_h, const tx_cplx* h1
         if (int rc = scan_structure(cx, sp, st, false)) return rc;
         p.site_class = sp.site_class;
         p.class_stride = sp.class_stride;
-        const int rc = launch_rgf_generic(p, st);
-        if (rc == TX_OK) {
-            if (!cx.scratch_ev) TX_CUDA(cudaEventCreateWithFlags(&cx.scratch_ev, cudaEventDisableTiming));
-            TX_CUDA(cudaEventRecord(cx.scratch_ev, st));
-            cx.scratch_stream = st;
-        }
-        return rc;
     }
-    return launch_rgf_generic(p, st);
+    const int rc = launch_rgf_generic(p, st);
+    if (rc == TX_OK) {
+        if (!cx.scratch_ev) TX_CUDA(cudaEventCreateWithFlags(&cx.scratch_ev, cudaEventDisableTiming));
+        TX_CUDA(cudaEventRecord(cx.scratch_ev, st));
+        cx.scratch_stream = st;
+        cx.scratch_used = true;
+    }
+    return rc;
 }
 
 int resolve_context(tx_context* ctx, tx_context** out) {

@@ -14,6 +14,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <vector>
 
 #include "block_ops.cuh"
@@ -590,8 +591,12 @@ const void* gf_kernel(int kind) {
 struct GfScratch {
     void* ptr = nullptr;
     size_t cap = 0;
+    cudaEvent_t done = nullptr;        // recorded behind the last kernel that used the workspace
+    cudaStream_t last = nullptr;       // ... and the stream it ran on
+    bool used = false;
 };
 GfScratch g_gf_scratch[16];
+std::mutex g_gf_scratch_mu;            // the workspace is shared by every caller of a device: uses are serialised
 
 int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     const int n = p.n;
@@ -649,8 +654,15 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     TX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_kernel(kind), kind == 2 ? GF_THREADS_BIG : GF_THREADS, smem));
     const int grid = (int)((long long)p.nE < (long long)sms * per_sm ? p.nE : sms * (per_sm > 0 ? per_sm : 1));
+    std::unique_lock<std::mutex> scratch_lock(g_gf_scratch_mu, std::defer_lock);
+    GfScratch* used_scratch = nullptr;
     if (p.scratch_per) {
+        // one grow-only workspace per device, indexed by CTA: a call on another stream (or from another host thread) waits
+        // on the device for the previous user -- no host synchronisation
+        scratch_lock.lock();
         GfScratch& sc = g_gf_scratch[dev & 15];
+        used_scratch = &sc;
+        if (sc.used && sc.last != st && sc.done) TX_CUDA(cudaStreamWaitEvent(st, sc.done, 0));
         const size_t need = (size_t)grid * scratch_bytes;
         if (need > sc.cap) {
             TX_CUDA(cudaDeviceSynchronize());
@@ -667,6 +679,12 @@ int launch_gf(GfParams p, cudaStream_t st, cd** scratch_owner) {
     else surface_gf_kernel<GF_THREADS, 64, 2, 0><<<grid, GF_THREADS, smem, st>>>(p);
     count_launch();
     TX_CUDA(cudaGetLastError());
+    if (used_scratch) {
+        if (!used_scratch->done) TX_CUDA(cudaEventCreateWithFlags(&used_scratch->done, cudaEventDisableTiming));
+        TX_CUDA(cudaEventRecord(used_scratch->done, st));
+        used_scratch->last = st;
+        used_scratch->used = true;
+    }
     return TX_OK;
 }
 
